@@ -1,0 +1,195 @@
+"""ctypes binding of libarrowgpu.so (include/arrowgpu.h).
+
+This module is a plain FFI table: every function is the C-ABI entry point of the same name.
+It never falls back to a CPU implementation — if the library is missing or no sm_100 device
+is usable the calls fail loudly (NativeError).
+"""
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libarrowgpu.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "arrowgpu.h")
+
+# status codes (include/arrowgpu.h)
+AG_OK, AG_ERR_INVALID, AG_ERR_INDEX, AG_ERR_NOT_IMPLEMENTED, AG_ERR_TYPE, AG_ERR_CUDA, AG_ERR_OOM = range(7)
+NO_ERROR_POS = (1 << 63) - 1
+
+# arrow.Type ids
+NULL, BOOL, UINT8, INT8, UINT16, INT16, UINT32, INT32, UINT64, INT64, FLOAT16, FLOAT32, FLOAT64 = range(13)
+# ArithmeticOp
+OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_ABS, OP_NEGATE = 0, 1, 2, 3, 4, 5
+OP_SIGN, OP_ADD_CHECKED, OP_SUB_CHECKED, OP_MUL_CHECKED, OP_DIV_CHECKED, OP_ABS_CHECKED, OP_NEGATE_CHECKED = 20, 21, 22, 23, 24, 25, 26
+# CompareOperator
+CMP_EQ, CMP_NE, CMP_GT, CMP_GE, CMP_LT, CMP_LE = range(6)
+SHAPE_AA, SHAPE_AS, SHAPE_SA = range(3)
+BITOP_AND, BITOP_OR, BITOP_XOR, BITOP_ANDNOT, BITOP_XNOR = range(5)
+KLEENE_AND, KLEENE_OR, KLEENE_ANDNOT = range(3)
+DROP_NULLS, EMIT_NULLS = 0, 1
+
+
+class NativeError(RuntimeError):
+    """A C-ABI call returned a non-zero ag_status."""
+
+    def __init__(self, status, message, func):
+        super().__init__(f"{func}: status {status}: {message}")
+        self.status = status
+        self.message = message
+        self.func = func
+
+
+_p = C.c_void_p
+_i = C.c_int
+_i8 = C.c_int8
+_i64 = C.c_int64
+_sz = C.c_size_t
+_u64 = C.c_uint64
+_pi64 = C.POINTER(C.c_int64)
+
+# name -> argtypes.  Every function returns ag_status (int) unless listed in _SPECIAL.
+_SIGS = {
+    "ag_init": [_i],
+    "ag_shutdown": [],
+    "ag_device_count": [C.POINTER(_i)],
+    "ag_device_info": [C.POINTER(_i), C.POINTER(_i), C.POINTER(_sz), C.POINTER(_i), C.POINTER(_i)],
+    "ag_host_alloc": [C.POINTER(_p), _sz],
+    "ag_host_realloc": [C.POINTER(_p), _sz, _sz],
+    "ag_host_free": [_p],
+    "ag_host_register": [_p, _sz],
+    "ag_host_unregister": [_p],
+    "ag_dev_alloc": [C.POINTER(_p), _sz],
+    "ag_dev_free": [_p],
+    "ag_dev_memset": [_p, _i, _sz, _p],
+    "ag_upload": [_p, _p, _sz, _p],
+    "ag_download": [_p, _p, _sz, _p],
+    "ag_copy_dev": [_p, _p, _sz, _p],
+    "ag_stream_create": [C.POINTER(_p)],
+    "ag_stream_destroy": [_p],
+    "ag_stream_sync": [_p],
+    "ag_event_create": [C.POINTER(_p)],
+    "ag_event_destroy": [_p],
+    "ag_event_record": [_p, _p],
+    "ag_event_sync": [_p],
+    "ag_event_elapsed_ms": [_p, _p, C.POINTER(C.c_float)],
+    "ag_flush_l2": [_p],
+    # sum
+    "ag_sum_f64": [_p, _sz, C.POINTER(C.c_double)],
+    "ag_sum_i64": [_p, _sz, C.POINTER(C.c_int64)],
+    "ag_sum_u64": [_p, _sz, C.POINTER(C.c_uint64)],
+    "ag_sum_f64_reforder": [_p, _sz, C.POINTER(C.c_double)],
+    "ag_sum_f64_dev": [_p, _sz, _p, _p],
+    "ag_sum_i64_dev": [_p, _sz, _p, _p],
+    "ag_sum_u64_dev": [_p, _sz, _p, _p],
+    "ag_sum_f64_reforder_dev": [_p, _sz, _p, _p],
+    # arithmetic
+    "ag_arith_binary": [_i, _i8, _p, _p, _p, _i64],
+    "ag_arith_arr_scalar": [_i, _i8, _p, _p, _p, _i64],
+    "ag_arith_scalar_arr": [_i, _i8, _p, _p, _p, _i64],
+    "ag_arith_unary_same": [_i, _i8, _p, _p, _i64],
+    "ag_arith_unary_diff": [_i, _i, _i8, _p, _p, _i64],
+    "ag_arith_binary_dev": [_i, _i8, _i, _p, _p, _p, _i64, _p],
+    "ag_arith_unary_same_dev": [_i, _i8, _p, _p, _i64, _p],
+    "ag_arith_unary_diff_dev": [_i, _i, _i8, _p, _p, _i64, _p],
+    "ag_arith_checked": [_i, _i8, _i, _p, _p, _i64, _p, _p, _i64, _p, _i64, _pi64],
+    "ag_arith_checked_dev": [_i, _i8, _i, _p, _p, _i64, _p, _p, _i64, _p, _i64, _p, _p],
+    "ag_error_word_reset_dev": [_p, _p],
+    # compare
+    "ag_compare": [_i, _i, _i, _p, _p, _p, _i64, _i],
+    "ag_compare_dev": [_i, _i, _i, _p, _p, _p, _i64, _i, _p],
+    # bitmaps
+    "ag_bitmap_op": [_i, _p, _i64, _p, _i64, _p, _i64, _i64],
+    "ag_bitmap_copy": [_p, _i64, _i64, _p, _i64],
+    "ag_bitmap_invert": [_p, _i64, _i64, _p, _i64],
+    "ag_bitmap_set": [_p, _i64, _i64, _i],
+    "ag_bitmap_popcount": [_p, _i64, _i64, _pi64],
+    "ag_bitmap_op_dev": [_i, _p, _i64, _p, _i64, _p, _i64, _i64, _p],
+    "ag_bitmap_copy_dev": [_p, _i64, _i64, _p, _i64, _p],
+    "ag_bitmap_invert_dev": [_p, _i64, _i64, _p, _i64, _p],
+    "ag_bitmap_set_dev": [_p, _i64, _i64, _i, _p],
+    "ag_bitmap_popcount_dev": [_p, _i64, _i64, _p, _p],
+    "ag_kleene": [_i, _p, _p, _i64, _p, _p, _i64, _p, _p, _i64, _i64],
+    "ag_kleene_dev": [_i, _p, _p, _i64, _p, _p, _i64, _p, _p, _i64, _i64, _p],
+    # filter / take
+    "ag_filter_output_size": [_p, _p, _i64, _i64, _i, _pi64],
+    "ag_filter_primitive": [_i, _p, _p, _i64, _p, _p, _i64, _i64, _i, _p, _p, _pi64, _pi64],
+    "ag_filter_output_size_dev": [_p, _p, _i64, _i64, _i, _p, _p],
+    "ag_filter_primitive_dev": [_i, _p, _p, _i64, _p, _p, _i64, _i64, _i, _p, _p, _i64, _p, _p],
+    "ag_filter_compare_scalar_dev": [_i, _i, _p, _p, _i64, _p, _i64, _p, _p],
+    "ag_take_indices": [_i, _p, _p, _i64, _i64, _i, _p, _p, _pi64],
+    "ag_take_indices_dev": [_i, _p, _p, _i64, _i64, _i, _p, _p, _i64, _p, _p],
+    "ag_take_primitive": [_i, _p, _p, _i64, _i64, _i, _i, _p, _p, _i64, _i64, _i, _p, _p, _pi64, _pi64, _pi64],
+    "ag_take_primitive_dev": [_i, _p, _p, _i64, _i64, _i, _i, _p, _p, _i64, _i64, _i, _p, _p, _p, _p],
+    # parity helpers
+    "ag_checksum64_dev": [_p, _sz, _p, _p],
+    "ag_generate_dev": [_i, _u64, _i64, _i64, _p, _sz, _p],
+}
+for _op in ("eq", "ne", "gt", "ge"):
+    for _sh in ("aa", "as", "sa"):
+        _SIGS[f"ag_cmp_{_op}_{_sh}"] = [_i, _p, _p, _p, _i64, _i]
+
+_SPECIAL = {
+    "ag_last_error": (None, [C.c_char_p, _sz]),
+    "ag_version": (C.c_char_p, []),
+    "ag_kernel_launch_count": (C.c_uint64, []),
+}
+
+_lib = None
+
+
+def build(verbose=False):
+    """Compile libarrowgpu.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    out = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc"), "-j8"], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("libarrowgpu build failed:\n" + out.stdout[-4000:] + out.stderr[-4000:])
+    if verbose:
+        print(out.stdout[-2000:])
+    return LIB_PATH
+
+
+def raw():
+    """The CDLL itself (restype/argtypes set, no error translation)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(AG_ERR_CUDA, f"{LIB_PATH} is missing: run __graft_entry__.build() "
+                              "(there is no CPU fallback)", "load")
+        lib = C.CDLL(LIB_PATH)
+        for name, argtypes in _SIGS.items():
+            fn = getattr(lib, name)
+            fn.restype = C.c_int
+            fn.argtypes = argtypes
+        for name, (restype, argtypes) in _SPECIAL.items():
+            fn = getattr(lib, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+    return _lib
+
+
+def last_error():
+    buf = C.create_string_buffer(512)
+    raw().ag_last_error(buf, 512)
+    return buf.value.decode("utf-8", "replace")
+
+
+def call(name, *args):
+    """Call a status-returning entry point; raise NativeError on failure."""
+    st = getattr(raw(), name)(*args)
+    if st != AG_OK:
+        raise NativeError(st, last_error(), name)
+    return st
+
+
+def call_status(name, *args):
+    """Call and return (status, message) without raising."""
+    st = getattr(raw(), name)(*args)
+    return st, (last_error() if st != AG_OK else "")
+
+
+def declared_symbols():
+    """Every function name declared in include/arrowgpu.h (for the export check)."""
+    import re
+    text = open(HEADER_PATH).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ag_[a-z0-9_]+)\s*\(", text)))

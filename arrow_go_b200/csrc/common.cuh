@@ -1,0 +1,180 @@
+// common.cuh — runtime internals shared by every translation unit of libarrowgpu.so.
+// Not part of the public ABI (see include/arrowgpu.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <stdio.h>
+#include <atomic>
+
+#include "../../include/arrowgpu.h"
+
+namespace ag {
+
+// ---------------------------------------------------------------- errors ----------
+void set_error(const char* fmt, ...);
+ag_status cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define AG_CUDA_TRY(expr)                                                        \
+  do {                                                                           \
+    cudaError_t _e = (expr);                                                     \
+    if (_e != cudaSuccess) return ::ag::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+#define AG_TRY(expr)                     \
+  do {                                   \
+    ag_status _s = (expr);               \
+    if (_s != AG_OK) return _s;          \
+  } while (0)
+
+#define AG_FAIL(code, ...)               \
+  do {                                   \
+    ::ag::set_error(__VA_ARGS__);        \
+    return (code);                       \
+  } while (0)
+
+// ---------------------------------------------------------------- runtime ---------
+// Per-stream scratch: kernels on one stream are serialised by the stream, so one
+// workspace per stream is race-free without stream-ordered allocation per call.
+struct Workspace {
+  // fixed small area
+  void* partials;        // kMaxPartials * 16 bytes (sum partials, per-block counters)
+  unsigned* ticket;      // last-block-done tickets; kernels leave them at 0
+  int64_t* scalars;      // 16 x int64 device scalars (counts, error words)
+  // growable area (decoupled look-back tile status for filter / take_indices)
+  unsigned long long* tile_status;
+  size_t tile_status_cap;  // in elements
+  // pinned host mirror of `scalars` for cheap readback
+  int64_t* h_scalars;
+};
+
+constexpr int kMaxPartials = 4096;
+
+ag_status ensure_init();
+int sm_count();
+cudaStream_t resolve_stream(ag_stream_t s);
+ag_status get_workspace(cudaStream_t s, Workspace** ws);
+ag_status ensure_tile_status(Workspace* ws, size_t n_tiles, cudaStream_t s);
+void count_launch(int n = 1);
+ag_status check_launch(const char* what);
+
+// Pooled streams for the synchronous host-pointer entry points (each call owns its streams
+// for its duration, so concurrent cgo callers never share a stream or a workspace).
+ag_status acquire_call_stream(cudaStream_t* st);
+void release_call_stream(cudaStream_t st);
+struct CallStream {
+  cudaStream_t st = nullptr;
+  ag_status acquire() { return acquire_call_stream(&st); }
+  ~CallStream() { if (st) release_call_stream(st); }
+  operator cudaStream_t() const { return st; }
+};
+
+// Device temp allocation (stream-ordered pool).
+ag_status dev_alloc_async(void** p, size_t nbytes, cudaStream_t s);
+ag_status dev_free_async(void* p, cudaStream_t s);
+
+// ---------------------------------------------------------------- type helpers ----
+inline int type_width(int type) {
+  switch (type) {
+    case AG_TYPE_UINT8: case AG_TYPE_INT8: return 1;
+    case AG_TYPE_UINT16: case AG_TYPE_INT16: return 2;
+    case AG_TYPE_UINT32: case AG_TYPE_INT32: case AG_TYPE_FLOAT32: return 4;
+    case AG_TYPE_UINT64: case AG_TYPE_INT64: case AG_TYPE_FLOAT64: return 8;
+    default: return 0;
+  }
+}
+inline bool type_is_signed_int(int type) {
+  return type == AG_TYPE_INT8 || type == AG_TYPE_INT16 || type == AG_TYPE_INT32 || type == AG_TYPE_INT64;
+}
+inline bool type_is_unsigned_int(int type) {
+  return type == AG_TYPE_UINT8 || type == AG_TYPE_UINT16 || type == AG_TYPE_UINT32 || type == AG_TYPE_UINT64;
+}
+inline bool type_is_float(int type) { return type == AG_TYPE_FLOAT32 || type == AG_TYPE_FLOAT64; }
+
+inline int64_t bytes_for_bits(int64_t nbits) { return (nbits + 7) >> 3; }
+
+// Grid sizing: persistent-style grids are multiples of the SM count.
+inline int grid_for(int64_t work_items, int items_per_block, int blocks_per_sm) {
+  int64_t want = (work_items + items_per_block - 1) / items_per_block;
+  int64_t cap = (int64_t)sm_count() * blocks_per_sm;
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+
+// ---------------------------------------------------------------- device helpers --
+#ifdef __CUDACC__
+
+// Streaming 128-bit load / store (evict-first: every byte on this path is touched once).
+template <typename V>
+__device__ __forceinline__ V ld_stream(const V* p) { return __ldcs(p); }
+template <typename V>
+__device__ __forceinline__ void st_stream(V* p, V v) { __stcs(p, v); }
+
+// Read 32 bits of an LSB-first bitmap starting at absolute bit position `bit`
+// (relative to byte pointer `base`), touching only bytes in [lo_byte, hi_byte).
+// Bits that fall outside are returned as 0.  Interior reads use aligned 32-bit loads.
+__device__ __forceinline__ uint32_t bitmap_load32(const uint8_t* __restrict__ base, int64_t bit,
+                                                  int64_t lo_byte, int64_t hi_byte) {
+  // aligned 4-byte window index relative to the 4-byte aligned address at or below base
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(base);
+  const int64_t mis = (int64_t)(addr & 3);       // base = abase + mis
+  const uint8_t* abase = base - mis;
+  const int64_t abit = bit + mis * 8;            // bit position relative to abase
+  const int64_t w = abit >> 5;                   // aligned word index (floor; abit >= 0 whenever any bit is valid)
+  const int sh = (int)(abit & 31);
+  const int64_t lo = lo_byte + mis, hi = hi_byte + mis;  // valid byte range relative to abase
+  auto load_word = [&](int64_t wi) -> uint32_t {
+    const int64_t b0 = wi * 4;
+    if (b0 >= lo && b0 + 4 <= hi) return *reinterpret_cast<const uint32_t*>(abase + b0);
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int64_t b = b0 + k;
+      if (b >= lo && b < hi) v |= (uint32_t)abase[b] << (8 * k);
+    }
+    return v;
+  };
+  const uint32_t w0 = load_word(w);
+  if (sh == 0) return w0;
+  const uint32_t w1 = load_word(w + 1);
+  return __funnelshift_r(w0, w1, sh);
+}
+
+// mask with bits [a, b) set, 0 <= a <= b <= 32
+__device__ __forceinline__ uint32_t bit_range_mask(int a, int b) {
+  const uint32_t hi = (b >= 32) ? 0xffffffffu : ((1u << b) - 1u);
+  const uint32_t lo = (a >= 32) ? 0xffffffffu : ((1u << a) - 1u);
+  return hi & ~lo;
+}
+
+// Store the bits of `value` selected by `mask` into the aligned 32-bit word at `wp`,
+// preserving every other bit and never touching a byte whose 8 mask bits are all zero
+// (edge words of a bitmap may extend past the caller's buffer).
+__device__ __forceinline__ void bitmap_store32_masked(uint32_t* wp, uint32_t value, uint32_t mask) {
+  if (mask == 0xffffffffu) { *wp = value; return; }
+  uint8_t* bp = reinterpret_cast<uint8_t*>(wp);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t m = (mask >> (8 * k)) & 0xffu;
+    if (m == 0) continue;
+    const uint32_t v = (value >> (8 * k)) & 0xffu;
+    if (m == 0xffu) bp[k] = (uint8_t)v;
+    else bp[k] = (uint8_t)((bp[k] & ~m) | (v & m));
+  }
+}
+
+__device__ __forceinline__ bool bit_is_set(const uint8_t* __restrict__ bits, int64_t i) {
+  return (bits[i >> 3] >> (i & 7)) & 1;
+}
+
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {  // splitmix64 finaliser
+  z += 0x9e3779b97f4a7c15ull;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
+
+#endif  // __CUDACC__
+
+}  // namespace ag

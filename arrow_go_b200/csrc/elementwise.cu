@@ -1,0 +1,512 @@
+// elementwise.cu — scalar arithmetic kernels on sm_100a.
+//
+// Replaces arithmetic_{binary,arr_scalar,scalar_arr,unary_same_types,unary_diff_type}_{avx2,sse4}
+// (arrow/compute/internal/kernels/_lib/base_arithmetic.cc:465-483) under ScalarBinary /
+// ScalarUnary (kernels/helpers.go:42-60,193-236: every slot is computed, nulls included), and
+// the pure-Go checked integer kernels (kernels/base_arithmetic.go:84-108,154-161,249-294) under
+// ScalarBinaryNotNull (helpers.go:284-380).
+//
+// Roofline: HBM.  arr⊕arr moves 3 x width bytes per row (24 B for float64), arr⊕scalar 2 x width.
+// One add per 24 bytes -> no tensor cores, no shared-memory reuse: the job is to keep
+// >= 64 KB of 128-bit loads in flight per SM and to write with full 128-byte lines.
+//
+// Layout: 256-thread blocks, persistent grid of 148 x 8 blocks; each thread moves 4 independent
+// 16-byte vectors per operand per iteration (ld.global.cs / st.global.cs — streaming, evict
+// first: every byte is touched once).  Pointers that are only element-aligned (Arrow slices,
+// Appendix D of SURVEY.md) take the scalar grid-stride path with the same arithmetic.
+#include "common.cuh"
+
+#include <type_traits>
+
+namespace ag {
+
+constexpr int kEwThreads = 256;
+constexpr int kEwUnroll = 4;
+constexpr int kEwBlocksPerSM = 8;
+
+// ---------------------------------------------------------------- functors ---------
+// Integers run on the unsigned type of the same width: two's-complement add/sub/mul have
+// the same low bits for signed and unsigned operands (base_arithmetic.cc:121-148 makes the
+// same move for Multiply), so int8/uint8 ... int64/uint64 share kernels.
+struct OpAdd { template <typename T> static __device__ __forceinline__ T apply(T a, T b) { return (T)(a + b); } };
+struct OpSub { template <typename T> static __device__ __forceinline__ T apply(T a, T b) { return (T)(a - b); } };
+struct OpMul {
+  template <typename T> static __device__ __forceinline__ T apply(T a, T b) {
+    if constexpr (std::is_floating_point<T>::value) return a * b;
+    else if constexpr (sizeof(T) == 8) return (T)(a * b);
+    else return (T)((uint32_t)a * (uint32_t)b);
+  }
+};
+// explicit round-to-nearest intrinsics: no FMA contraction, no reassociation
+template <> __device__ __forceinline__ double OpAdd::apply<double>(double a, double b) { return __dadd_rn(a, b); }
+template <> __device__ __forceinline__ float OpAdd::apply<float>(float a, float b) { return __fadd_rn(a, b); }
+template <> __device__ __forceinline__ double OpSub::apply<double>(double a, double b) { return __dsub_rn(a, b); }
+template <> __device__ __forceinline__ float OpSub::apply<float>(float a, float b) { return __fsub_rn(a, b); }
+template <> __device__ __forceinline__ double OpMul::apply<double>(double a, double b) { return __dmul_rn(a, b); }
+template <> __device__ __forceinline__ float OpMul::apply<float>(float a, float b) { return __fmul_rn(a, b); }
+
+template <typename T, int N> struct alignas(16) Vec { T v[N]; };
+
+template <typename T>
+__device__ __forceinline__ Vec<T, 16 / sizeof(T)> ldv(const T* p, int64_t vi) {
+  const uint4 r = __ldcs(reinterpret_cast<const uint4*>(p) + vi);
+  return *reinterpret_cast<const Vec<T, 16 / sizeof(T)>*>(&r);
+}
+template <typename T>
+__device__ __forceinline__ void stv(T* p, int64_t vi, const Vec<T, 16 / sizeof(T)>& v) {
+  __stcs(reinterpret_cast<uint4*>(p) + vi, *reinterpret_cast<const uint4*>(&v));
+}
+
+// ---------------------------------------------------------------- binary -----------
+template <typename T, typename Op, int kShape>
+__global__ void __launch_bounds__(kEwThreads)
+binary_vec_kernel(const T* __restrict__ l, const T* __restrict__ r, T* __restrict__ out, int64_t n, T scalar) {
+  constexpr int N = 16 / sizeof(T);
+  const int64_t nvec = n / N;
+  const int64_t stride = (int64_t)gridDim.x * kEwThreads;
+  int64_t vi = (int64_t)blockIdx.x * kEwThreads + threadIdx.x;
+  for (; vi + (kEwUnroll - 1) * stride < nvec; vi += kEwUnroll * stride) {
+    Vec<T, N> a[kEwUnroll], b[kEwUnroll];
+#pragma unroll
+    for (int k = 0; k < kEwUnroll; ++k) {
+      if (kShape != AG_SHAPE_SA) a[k] = ldv(l, vi + k * stride);
+      if (kShape != AG_SHAPE_AS) b[k] = ldv(r, vi + k * stride);
+    }
+#pragma unroll
+    for (int k = 0; k < kEwUnroll; ++k) {
+      Vec<T, N> o;
+#pragma unroll
+      for (int e = 0; e < N; ++e)
+        o.v[e] = Op::template apply<T>(kShape == AG_SHAPE_SA ? scalar : a[k].v[e], kShape == AG_SHAPE_AS ? scalar : b[k].v[e]);
+      stv(out, vi + k * stride, o);
+    }
+  }
+  for (; vi < nvec; vi += stride) {
+    Vec<T, N> a, b, o;
+    if (kShape != AG_SHAPE_SA) a = ldv(l, vi);
+    if (kShape != AG_SHAPE_AS) b = ldv(r, vi);
+#pragma unroll
+    for (int e = 0; e < N; ++e)
+      o.v[e] = Op::template apply<T>(kShape == AG_SHAPE_SA ? scalar : a.v[e], kShape == AG_SHAPE_AS ? scalar : b.v[e]);
+    stv(out, vi, o);
+  }
+  // tail (< N elements): block 0
+  if (blockIdx.x == 0) {
+    const int64_t i = nvec * N + threadIdx.x;
+    if (i < n)
+      out[i] = Op::template apply<T>(kShape == AG_SHAPE_SA ? scalar : l[i], kShape == AG_SHAPE_AS ? scalar : r[i]);
+  }
+}
+
+template <typename T, typename Op, int kShape>
+__global__ void __launch_bounds__(kEwThreads)
+binary_scalar_kernel(const T* __restrict__ l, const T* __restrict__ r, T* __restrict__ out, int64_t n, T scalar) {
+  const int64_t stride = (int64_t)gridDim.x * kEwThreads;
+  int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x;
+  for (; i + (kEwUnroll - 1) * stride < n; i += kEwUnroll * stride) {
+    T a[kEwUnroll], b[kEwUnroll];
+#pragma unroll
+    for (int k = 0; k < kEwUnroll; ++k) {
+      a[k] = (kShape == AG_SHAPE_SA) ? scalar : __ldcs(l + i + k * stride);
+      b[k] = (kShape == AG_SHAPE_AS) ? scalar : __ldcs(r + i + k * stride);
+    }
+#pragma unroll
+    for (int k = 0; k < kEwUnroll; ++k) __stcs(out + i + k * stride, Op::template apply<T>(a[k], b[k]));
+  }
+  for (; i < n; i += stride)
+    out[i] = Op::template apply<T>(kShape == AG_SHAPE_SA ? scalar : l[i], kShape == AG_SHAPE_AS ? scalar : r[i]);
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <typename T, typename Op, int kShape>
+static ag_status launch_binary_t(const void* l, const void* r, void* out, int64_t n, const void* scalar_host, cudaStream_t st) {
+  T scalar = T(0);
+  if (kShape != AG_SHAPE_AA) scalar = *reinterpret_cast<const T*>(scalar_host);
+  const T* lp = reinterpret_cast<const T*>(l);
+  const T* rp = reinterpret_cast<const T*>(r);
+  T* op = reinterpret_cast<T*>(out);
+  constexpr int N = 16 / sizeof(T);
+  const bool vec = aligned16(out) && (kShape == AG_SHAPE_SA || aligned16(l)) && (kShape == AG_SHAPE_AS || aligned16(r));
+  if (vec) {
+    const int grid = grid_for(n / N + 1, kEwThreads * kEwUnroll, kEwBlocksPerSM);
+    binary_vec_kernel<T, Op, kShape><<<grid, kEwThreads, 0, st>>>(lp, rp, op, n, scalar);
+  } else {
+    const int grid = grid_for(n, kEwThreads * kEwUnroll, kEwBlocksPerSM);
+    binary_scalar_kernel<T, Op, kShape><<<grid, kEwThreads, 0, st>>>(lp, rp, op, n, scalar);
+  }
+  return check_launch("binary_kernel");
+}
+
+template <typename T, typename Op>
+static ag_status launch_binary_shape(int shape, const void* l, const void* r, void* out, int64_t n, cudaStream_t st) {
+  switch (shape) {
+    case AG_SHAPE_AA: return launch_binary_t<T, Op, AG_SHAPE_AA>(l, r, out, n, nullptr, st);
+    case AG_SHAPE_AS: return launch_binary_t<T, Op, AG_SHAPE_AS>(l, nullptr, out, n, r, st);
+    case AG_SHAPE_SA: return launch_binary_t<T, Op, AG_SHAPE_SA>(nullptr, r, out, n, l, st);
+    default: AG_FAIL(AG_ERR_INVALID, "arith: bad operand shape %d", shape);
+  }
+}
+
+template <typename T>
+static ag_status launch_binary_op(int8_t op, int shape, const void* l, const void* r, void* out, int64_t n, cudaStream_t st) {
+  switch (op) {
+    // the *_CHECKED aliases are the plain loops here, like the reference's native code
+    // (base_arithmetic.cc:445-462); the checking variants are ag_arith_checked.
+    case AG_OP_ADD: case AG_OP_ADD_CHECKED: return launch_binary_shape<T, OpAdd>(shape, l, r, out, n, st);
+    case AG_OP_SUB: case AG_OP_SUB_CHECKED: return launch_binary_shape<T, OpSub>(shape, l, r, out, n, st);
+    case AG_OP_MUL: case AG_OP_MUL_CHECKED: return launch_binary_shape<T, OpMul>(shape, l, r, out, n, st);
+    default: AG_FAIL(AG_ERR_NOT_IMPLEMENTED, "arith: binary op %d has no native kernel (the reference has none either)", (int)op);
+  }
+}
+
+ag_status arith_binary_dev(int type, int8_t op, int shape, const void* l, const void* r, void* out, int64_t n, cudaStream_t st) {
+  if (n < 0) AG_FAIL(AG_ERR_INVALID, "arith: negative length");
+  if (n == 0) return AG_OK;
+  const int w = type_width(type);
+  if (w == 0) AG_FAIL(AG_ERR_TYPE, "arith: unsupported type id %d", type);
+  const uintptr_t m = (uintptr_t)(w - 1);
+  if (((uintptr_t)out & m) || (shape != AG_SHAPE_SA && ((uintptr_t)l & m)) || (shape != AG_SHAPE_AS && ((uintptr_t)r & m)))
+    AG_FAIL(AG_ERR_INVALID, "arith: operand not aligned to its element width");
+  switch (type) {
+    case AG_TYPE_UINT8: case AG_TYPE_INT8: return launch_binary_op<uint8_t>(op, shape, l, r, out, n, st);
+    case AG_TYPE_UINT16: case AG_TYPE_INT16: return launch_binary_op<uint16_t>(op, shape, l, r, out, n, st);
+    case AG_TYPE_UINT32: case AG_TYPE_INT32: return launch_binary_op<uint32_t>(op, shape, l, r, out, n, st);
+    case AG_TYPE_UINT64: case AG_TYPE_INT64: return launch_binary_op<unsigned long long>(op, shape, l, r, out, n, st);
+    case AG_TYPE_FLOAT32: return launch_binary_op<float>(op, shape, l, r, out, n, st);
+    case AG_TYPE_FLOAT64: return launch_binary_op<double>(op, shape, l, r, out, n, st);
+    default: AG_FAIL(AG_ERR_TYPE, "arith: unsupported type id %d", type);
+  }
+}
+
+// ---------------------------------------------------------------- unary ------------
+// AbsoluteValue base_arithmetic.cc:160-176 (floats: clear the sign bit; signed ints:
+// (x + mask) ^ mask), Negate :194-205, NegateChecked :207-219 (unsigned -> 0), Sign :221-234.
+struct UAbs {
+  template <typename TO, typename T> static __device__ __forceinline__ TO apply(T x) {
+    if constexpr (std::is_same<T, float>::value) return __uint_as_float(__float_as_uint(x) & 0x7fffffffu);
+    else if constexpr (std::is_same<T, double>::value) return __longlong_as_double(__double_as_longlong(x) & 0x7fffffffffffffffll);
+    else if constexpr (std::is_unsigned<T>::value) return x;
+    else {
+      using U = typename std::make_unsigned<T>::type;
+      const U mask = (U)(x >> (sizeof(T) * 8 - 1));
+      return (T)(((U)x + mask) ^ mask);
+    }
+  }
+};
+struct UNeg {
+  template <typename TO, typename T> static __device__ __forceinline__ TO apply(T x) {
+    if constexpr (std::is_same<T, float>::value) return __uint_as_float(__float_as_uint(x) ^ 0x80000000u);
+    else if constexpr (std::is_same<T, double>::value) return __longlong_as_double(__double_as_longlong(x) ^ (long long)0x8000000000000000ull);
+    else { using U = typename std::make_unsigned<T>::type; return (T)((U)0 - (U)x); }
+  }
+};
+struct UNegChecked {  // identical to UNeg except unsigned -> 0 (base_arithmetic.cc:213-214)
+  template <typename TO, typename T> static __device__ __forceinline__ TO apply(T x) {
+    if constexpr (std::is_unsigned<T>::value) return 0;
+    else return UNeg::apply<TO, T>(x);
+  }
+};
+struct USign {
+  template <typename TO, typename T> static __device__ __forceinline__ TO apply(T x) {
+    if constexpr (std::is_floating_point<T>::value) return (TO)(isnan(x) ? x : ((x == 0) ? T(0) : (signbit(x) ? T(-1) : T(1))));
+    else if constexpr (std::is_unsigned<T>::value) return (TO)(x > 0 ? 1 : 0);
+    else return (TO)(x > 0 ? 1 : (x ? -1 : 0));
+  }
+};
+
+template <typename T, typename Op>
+__global__ void __launch_bounds__(kEwThreads)
+unary_vec_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t n) {
+  constexpr int N = 16 / sizeof(T);
+  const int64_t nvec = n / N;
+  const int64_t stride = (int64_t)gridDim.x * kEwThreads;
+  int64_t vi = (int64_t)blockIdx.x * kEwThreads + threadIdx.x;
+  for (; vi + (kEwUnroll - 1) * stride < nvec; vi += kEwUnroll * stride) {
+    Vec<T, N> a[kEwUnroll];
+#pragma unroll
+    for (int k = 0; k < kEwUnroll; ++k) a[k] = ldv(in, vi + k * stride);
+#pragma unroll
+    for (int k = 0; k < kEwUnroll; ++k) {
+      Vec<T, N> o;
+#pragma unroll
+      for (int e = 0; e < N; ++e) o.v[e] = Op::template apply<T, T>(a[k].v[e]);
+      stv(out, vi + k * stride, o);
+    }
+  }
+  for (; vi < nvec; vi += stride) {
+    Vec<T, N> a = ldv(in, vi), o;
+#pragma unroll
+    for (int e = 0; e < N; ++e) o.v[e] = Op::template apply<T, T>(a.v[e]);
+    stv(out, vi, o);
+  }
+  if (blockIdx.x == 0) {
+    const int64_t i = nvec * N + threadIdx.x;
+    if (i < n) out[i] = Op::template apply<T, T>(in[i]);
+  }
+}
+
+template <typename TI, typename TO, typename Op>
+__global__ void __launch_bounds__(kEwThreads)
+unary_scalar_kernel(const TI* __restrict__ in, TO* __restrict__ out, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * kEwThreads;
+  for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < n; i += stride)
+    out[i] = Op::template apply<TO, TI>(in[i]);
+}
+
+template <typename T, typename Op>
+static ag_status launch_unary_same_t(const void* in, void* out, int64_t n, cudaStream_t st) {
+  constexpr int N = 16 / sizeof(T);
+  if (aligned16(in) && aligned16(out)) {
+    const int grid = grid_for(n / N + 1, kEwThreads * kEwUnroll, kEwBlocksPerSM);
+    unary_vec_kernel<T, Op><<<grid, kEwThreads, 0, st>>>((const T*)in, (T*)out, n);
+  } else {
+    const int grid = grid_for(n, kEwThreads * kEwUnroll, kEwBlocksPerSM);
+    unary_scalar_kernel<T, T, Op><<<grid, kEwThreads, 0, st>>>((const T*)in, (T*)out, n);
+  }
+  return check_launch("unary_kernel");
+}
+
+template <typename T>
+static ag_status launch_unary_same_op(int8_t op, const void* in, void* out, int64_t n, cudaStream_t st) {
+  switch (op) {
+    case AG_OP_ABS: case AG_OP_ABS_CHECKED: return launch_unary_same_t<T, UAbs>(in, out, n, st);
+    case AG_OP_NEGATE: return launch_unary_same_t<T, UNeg>(in, out, n, st);
+    case AG_OP_NEGATE_CHECKED: return launch_unary_same_t<T, UNegChecked>(in, out, n, st);
+    case AG_OP_SIGN: return launch_unary_same_t<T, USign>(in, out, n, st);
+    default: AG_FAIL(AG_ERR_NOT_IMPLEMENTED, "arith: unary op %d has no native kernel", (int)op);
+  }
+}
+
+ag_status arith_unary_same_dev(int type, int8_t op, const void* in, void* out, int64_t n, cudaStream_t st) {
+  if (n < 0) AG_FAIL(AG_ERR_INVALID, "arith: negative length");
+  if (n == 0) return AG_OK;
+  switch (type) {
+    case AG_TYPE_UINT8: return launch_unary_same_op<uint8_t>(op, in, out, n, st);
+    case AG_TYPE_INT8: return launch_unary_same_op<int8_t>(op, in, out, n, st);
+    case AG_TYPE_UINT16: return launch_unary_same_op<uint16_t>(op, in, out, n, st);
+    case AG_TYPE_INT16: return launch_unary_same_op<int16_t>(op, in, out, n, st);
+    case AG_TYPE_UINT32: return launch_unary_same_op<uint32_t>(op, in, out, n, st);
+    case AG_TYPE_INT32: return launch_unary_same_op<int32_t>(op, in, out, n, st);
+    case AG_TYPE_UINT64: return launch_unary_same_op<unsigned long long>(op, in, out, n, st);
+    case AG_TYPE_INT64: return launch_unary_same_op<long long>(op, in, out, n, st);
+    case AG_TYPE_FLOAT32: return launch_unary_same_op<float>(op, in, out, n, st);
+    case AG_TYPE_FLOAT64: return launch_unary_same_op<double>(op, in, out, n, st);
+    default: AG_FAIL(AG_ERR_TYPE, "arith: unsupported type id %d", type);
+  }
+}
+
+template <typename TI>
+static ag_status launch_sign_diff(int otype, const void* in, void* out, int64_t n, cudaStream_t st) {
+  const int grid = grid_for(n, kEwThreads * kEwUnroll, kEwBlocksPerSM);
+#define AG_SIGN_CASE(ID, TO) \
+  case ID: unary_scalar_kernel<TI, TO, USign><<<grid, kEwThreads, 0, st>>>((const TI*)in, (TO*)out, n); break;
+  switch (otype) {
+    AG_SIGN_CASE(AG_TYPE_UINT8, uint8_t) AG_SIGN_CASE(AG_TYPE_INT8, int8_t)
+    AG_SIGN_CASE(AG_TYPE_UINT16, uint16_t) AG_SIGN_CASE(AG_TYPE_INT16, int16_t)
+    AG_SIGN_CASE(AG_TYPE_UINT32, uint32_t) AG_SIGN_CASE(AG_TYPE_INT32, int32_t)
+    AG_SIGN_CASE(AG_TYPE_UINT64, unsigned long long) AG_SIGN_CASE(AG_TYPE_INT64, long long)
+    AG_SIGN_CASE(AG_TYPE_FLOAT32, float) AG_SIGN_CASE(AG_TYPE_FLOAT64, double)
+    default: AG_FAIL(AG_ERR_TYPE, "arith: unsupported output type id %d", otype);
+  }
+#undef AG_SIGN_CASE
+  return check_launch("sign_diff_kernel");
+}
+
+ag_status arith_unary_diff_dev(int itype, int otype, int8_t op, const void* in, void* out, int64_t n, cudaStream_t st) {
+  if (op != AG_OP_SIGN) AG_FAIL(AG_ERR_NOT_IMPLEMENTED, "arith: unary_diff_type only implements SIGN (base_arithmetic.cc:427-438)");
+  if (n < 0) AG_FAIL(AG_ERR_INVALID, "arith: negative length");
+  if (n == 0) return AG_OK;
+  switch (itype) {
+    case AG_TYPE_UINT8: return launch_sign_diff<uint8_t>(otype, in, out, n, st);
+    case AG_TYPE_INT8: return launch_sign_diff<int8_t>(otype, in, out, n, st);
+    case AG_TYPE_UINT16: return launch_sign_diff<uint16_t>(otype, in, out, n, st);
+    case AG_TYPE_INT16: return launch_sign_diff<int16_t>(otype, in, out, n, st);
+    case AG_TYPE_UINT32: return launch_sign_diff<uint32_t>(otype, in, out, n, st);
+    case AG_TYPE_INT32: return launch_sign_diff<int32_t>(otype, in, out, n, st);
+    case AG_TYPE_UINT64: return launch_sign_diff<unsigned long long>(otype, in, out, n, st);
+    case AG_TYPE_INT64: return launch_sign_diff<long long>(otype, in, out, n, st);
+    default: AG_FAIL(AG_ERR_NOT_IMPLEMENTED, "arith: sign with differing types needs an integer input");
+  }
+}
+
+// ---------------------------------------------------------------- checked ----------
+// base_arithmetic.go:249-278: carry = ((a&b) | ((a|b) &^ out)) >> shiftBy, "carry > 0", with
+// shiftBy = bits-1 (unsigned) or bits-2 (signed) evaluated in the operand type (arithmetic
+// shift for signed).  We restate the formula bit for bit, including what it does for signed
+// operands (it flags a carry into the sign bit that is not carried out).
+template <typename ST> struct ChkAdd {
+  static __device__ __forceinline__ ST apply(ST a, ST b, bool& bad) {
+    using U = typename std::make_unsigned<ST>::type;
+    constexpr int shift_by = (int)sizeof(ST) * 8 - 1 - (std::is_signed<ST>::value ? 1 : 0);
+    const ST o = (ST)((U)a + (U)b);
+    const ST c = (ST)((ST)((ST)(a & b) | ((ST)(a | b) & (ST)~o)) >> shift_by);
+    bad = c > 0;
+    return o;
+  }
+};
+template <typename ST> struct ChkSub {
+  static __device__ __forceinline__ ST apply(ST a, ST b, bool& bad) {
+    using U = typename std::make_unsigned<ST>::type;
+    constexpr int shift_by = (int)sizeof(ST) * 8 - 1 - (std::is_signed<ST>::value ? 1 : 0);
+    const ST o = (ST)((U)a - (U)b);
+    const ST c = (ST)((ST)((ST)((ST)~a & b) | ((ST)~(ST)(a ^ b) & o)) >> shift_by);
+    bad = c > 0;
+    return o;
+  }
+};
+// mulWithOverflow base_arithmetic.go:84-108 (division-based test; an overflowing slot yields 0)
+template <typename ST> struct ChkMul {
+  static __device__ __forceinline__ ST apply(ST a, ST b, bool& bad) {
+    using U = typename std::make_unsigned<ST>::type;
+    constexpr ST tmax = std::is_signed<ST>::value ? (ST)(((U)1 << (sizeof(ST) * 8 - 1)) - 1) : (ST)~(U)0;
+    constexpr ST tmin = std::is_signed<ST>::value ? (ST)((U)1 << (sizeof(ST) * 8 - 1)) : (ST)0;
+    bool ovf = false;
+    if (a > 0) { if (b > 0) { ovf = a > (ST)(tmax / b); } else { ovf = b < (ST)(tmin / a); } }
+    else if (b > 0) { ovf = a < (ST)(tmin / b); }
+    else { ovf = (a != 0) && (b < (ST)(tmax / a)); }
+    bad = ovf;
+    return ovf ? (ST)0 : (ST)((U)a * (U)b);
+  }
+};
+// Div / DivChecked base_arithmetic.go:154-161,287-294: b == 0 -> error (value 0); Go's
+// MinInt / -1 wraps to MinInt.
+template <typename ST> struct ChkDiv {
+  static __device__ __forceinline__ ST apply(ST a, ST b, bool& bad) {
+    using U = typename std::make_unsigned<ST>::type;
+    bad = (b == 0);
+    if (b == 0) return 0;
+    if constexpr (std::is_signed<ST>::value) {
+      constexpr ST tmin = (ST)((U)1 << (sizeof(ST) * 8 - 1));
+      if (a == tmin && b == (ST)-1) return a;
+    }
+    return (ST)(a / b);
+  }
+};
+
+// kNotNull: ScalarBinaryNotNull slot semantics (null slots written as 0, not computed);
+// otherwise ScalarBinary (every slot computed — MUL_CHECKED, base_arithmetic.go:279-286).
+template <typename ST, typename Op, int kShape, bool kNotNull>
+__global__ void __launch_bounds__(kEwThreads)
+checked_kernel(const ST* __restrict__ l, const uint8_t* __restrict__ lvalid, int64_t loff,
+               const ST* __restrict__ r, const uint8_t* __restrict__ rvalid, int64_t roff,
+               ST* __restrict__ out, int64_t n, ST scalar, long long* __restrict__ first_bad) {
+  const int64_t stride = (int64_t)gridDim.x * kEwThreads;
+  long long my_bad = AG_NO_ERROR_POS;
+  for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < n; i += stride) {
+    bool valid = true;
+    if (kNotNull) {
+      if (kShape != AG_SHAPE_SA && lvalid) valid = bit_is_set(lvalid, loff + i);
+      if (kShape != AG_SHAPE_AS && rvalid) valid = valid && bit_is_set(rvalid, roff + i);
+    }
+    ST o = 0;
+    if (valid) {
+      const ST a = (kShape == AG_SHAPE_SA) ? scalar : l[i];
+      const ST b = (kShape == AG_SHAPE_AS) ? scalar : r[i];
+      bool bad;
+      o = Op::apply(a, b, bad);
+      if (bad && (long long)i < my_bad) my_bad = (long long)i;
+    }
+    out[i] = o;
+  }
+  // lowest failing row: warp min, then one atomicMin per warp that saw a failure
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) {
+    const long long o = __shfl_xor_sync(0xffffffffu, my_bad, m);
+    my_bad = o < my_bad ? o : my_bad;
+  }
+  if ((threadIdx.x & 31) == 0 && my_bad != AG_NO_ERROR_POS) atomicMin(first_bad, my_bad);
+}
+
+template <typename ST, typename Op, bool kNotNull>
+static ag_status launch_checked_shape(int shape, const void* l, const uint8_t* lvalid, int64_t loff,
+                                      const void* r, const uint8_t* rvalid, int64_t roff,
+                                      void* out, int64_t n, int64_t* d_first_bad, cudaStream_t st) {
+  const int grid = grid_for(n, kEwThreads * kEwUnroll, kEwBlocksPerSM);
+  long long* fb = reinterpret_cast<long long*>(d_first_bad);
+  switch (shape) {
+    case AG_SHAPE_AA:
+      checked_kernel<ST, Op, AG_SHAPE_AA, kNotNull><<<grid, kEwThreads, 0, st>>>((const ST*)l, lvalid, loff, (const ST*)r, rvalid, roff, (ST*)out, n, ST(0), fb);
+      break;
+    case AG_SHAPE_AS:
+      checked_kernel<ST, Op, AG_SHAPE_AS, kNotNull><<<grid, kEwThreads, 0, st>>>((const ST*)l, lvalid, loff, nullptr, nullptr, 0, (ST*)out, n, *(const ST*)r, fb);
+      break;
+    case AG_SHAPE_SA:
+      checked_kernel<ST, Op, AG_SHAPE_SA, kNotNull><<<grid, kEwThreads, 0, st>>>(nullptr, nullptr, 0, (const ST*)r, rvalid, roff, (ST*)out, n, *(const ST*)l, fb);
+      break;
+    default: AG_FAIL(AG_ERR_INVALID, "arith_checked: bad operand shape %d", shape);
+  }
+  return check_launch("checked_kernel");
+}
+
+template <typename ST>
+static ag_status launch_checked_op(int8_t op, int shape, const void* l, const uint8_t* lvalid, int64_t loff,
+                                   const void* r, const uint8_t* rvalid, int64_t roff,
+                                   void* out, int64_t n, int64_t* d_first_bad, cudaStream_t st) {
+  switch (op) {
+    case AG_OP_ADD_CHECKED: return launch_checked_shape<ST, ChkAdd<ST>, true>(shape, l, lvalid, loff, r, rvalid, roff, out, n, d_first_bad, st);
+    case AG_OP_SUB_CHECKED: return launch_checked_shape<ST, ChkSub<ST>, true>(shape, l, lvalid, loff, r, rvalid, roff, out, n, d_first_bad, st);
+    case AG_OP_MUL_CHECKED: return launch_checked_shape<ST, ChkMul<ST>, false>(shape, l, lvalid, loff, r, rvalid, roff, out, n, d_first_bad, st);
+    case AG_OP_DIV: case AG_OP_DIV_CHECKED: return launch_checked_shape<ST, ChkDiv<ST>, true>(shape, l, lvalid, loff, r, rvalid, roff, out, n, d_first_bad, st);
+    default: AG_FAIL(AG_ERR_NOT_IMPLEMENTED, "arith_checked: op %d is not a checked integer op", (int)op);
+  }
+}
+
+ag_status arith_checked_dev(int type, int8_t op, int shape, const void* l, const uint8_t* lvalid, int64_t loff,
+                            const void* r, const uint8_t* rvalid, int64_t roff,
+                            void* out, int64_t n, int64_t* d_first_bad, cudaStream_t st) {
+  if (n < 0) AG_FAIL(AG_ERR_INVALID, "arith_checked: negative length");
+  if (n == 0) return AG_OK;
+  // null scalar: "fast path if one side is entirely null" (helpers.go:287,314,341) — output untouched
+  if ((shape == AG_SHAPE_SA && !l) || (shape == AG_SHAPE_AS && !r)) return AG_OK;
+  switch (type) {
+    case AG_TYPE_INT8: return launch_checked_op<int8_t>(op, shape, l, lvalid, loff, r, rvalid, roff, out, n, d_first_bad, st);
+    case AG_TYPE_INT16: return launch_checked_op<int16_t>(op, shape, l, lvalid, loff, r, rvalid, roff, out, n, d_first_bad, st);
+    case AG_TYPE_INT32: return launch_checked_op<int32_t>(op, shape, l, lvalid, loff, r, rvalid, roff, out, n, d_first_bad, st);
+    case AG_TYPE_INT64: return launch_checked_op<long long>(op, shape, l, lvalid, loff, r, rvalid, roff, out, n, d_first_bad, st);
+    case AG_TYPE_UINT8: return launch_checked_op<uint8_t>(op, shape, l, lvalid, loff, r, rvalid, roff, out, n, d_first_bad, st);
+    case AG_TYPE_UINT16: return launch_checked_op<uint16_t>(op, shape, l, lvalid, loff, r, rvalid, roff, out, n, d_first_bad, st);
+    case AG_TYPE_UINT32: return launch_checked_op<uint32_t>(op, shape, l, lvalid, loff, r, rvalid, roff, out, n, d_first_bad, st);
+    case AG_TYPE_UINT64: return launch_checked_op<unsigned long long>(op, shape, l, lvalid, loff, r, rvalid, roff, out, n, d_first_bad, st);
+    default: AG_FAIL(AG_ERR_TYPE, "arith_checked: type id %d is not an integer type", type);
+  }
+}
+
+__global__ void reset_error_word_kernel(long long* w) { *w = AG_NO_ERROR_POS; }
+
+ag_status error_word_reset(int64_t* d_word, cudaStream_t st) {
+  reset_error_word_kernel<<<1, 1, 0, st>>>((long long*)d_word);
+  return check_launch("reset_error_word_kernel");
+}
+
+}  // namespace ag
+
+using namespace ag;
+
+extern "C" {
+
+ag_status ag_arith_binary_dev(int type, int8_t op, int shape, const void* l, const void* r, void* out, int64_t n, ag_stream_t s) {
+  AG_TRY(ensure_init());
+  return arith_binary_dev(type, op, shape, l, r, out, n, resolve_stream(s));
+}
+ag_status ag_arith_unary_same_dev(int type, int8_t op, const void* in, void* out, int64_t n, ag_stream_t s) {
+  AG_TRY(ensure_init());
+  return arith_unary_same_dev(type, op, in, out, n, resolve_stream(s));
+}
+ag_status ag_arith_unary_diff_dev(int itype, int otype, int8_t op, const void* in, void* out, int64_t n, ag_stream_t s) {
+  AG_TRY(ensure_init());
+  return arith_unary_diff_dev(itype, otype, op, in, out, n, resolve_stream(s));
+}
+ag_status ag_arith_checked_dev(int type, int8_t op, int shape, const void* l, const uint8_t* lvalid, int64_t loff,
+                               const void* r, const uint8_t* rvalid, int64_t roff,
+                               void* out, int64_t n, int64_t* d_first_bad, ag_stream_t s) {
+  AG_TRY(ensure_init());
+  if (!d_first_bad) AG_FAIL(AG_ERR_INVALID, "arith_checked: NULL error word");
+  return arith_checked_dev(type, op, shape, l, lvalid, loff, r, rvalid, roff, out, n, d_first_bad, resolve_stream(s));
+}
+ag_status ag_error_word_reset_dev(int64_t* d_word, ag_stream_t s) {
+  AG_TRY(ensure_init());
+  return error_word_reset(d_word, resolve_stream(s));
+}
+
+}  // extern "C"

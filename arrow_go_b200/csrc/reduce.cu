@@ -1,0 +1,269 @@
+// reduce.cu — arrow/math Sum on sm_100a.
+//
+// Replaces sum_{float64,int64,uint64}_{avx2,sse4,neon} (arrow/math/_lib/float64.c:20-26,
+// int64.c:21-27, uint64.c; Go entry Float64Funcs.Sum arrow/math/float64.go:34-39).
+// Validity bitmaps are ignored, exactly like the reference (it sums values[offset:offset+len]).
+//
+// Roofline: HBM.  8 algorithmic bytes per row, ~0.125 flop/byte.
+//
+// Shape of the reduction (fixed => the float64 result is a pure function of (data, n)):
+//   * the input is viewed as PAIRS (x[2j], x[2j+1]); an odd last element is folded in at the end;
+//   * G = sum_grid(n) blocks of 256 threads; thread t of the grid owns pairs t, t+S, t+2S, ...
+//     (S = 256*G), with 4 pair-loads in flight per iteration, each feeding its own two
+//     accumulators (8 independent chains per thread);
+//   * thread sum -> warp xor-shuffle tree -> block tree (fixed) -> partials[G];
+//   * the last block to finish (ticket) reduces partials[] with the same fixed tree.
+// 16-byte aligned inputs use 128-bit ld.global.cs; 8-byte aligned ones use two 64-bit loads
+// with the SAME pair->thread mapping, so alignment never changes the result.
+#include "common.cuh"
+
+namespace ag {
+
+constexpr int kSumThreads = 256;
+constexpr int kSumUnroll = 4;
+constexpr int kSumBlocksPerSM = 8;
+constexpr int kSumMaxBlocks = 148 * kSumBlocksPerSM;  // fixed: independent of the SM count found
+
+static inline int sum_grid(size_t n_pairs) {
+  // a block-iteration consumes 256*4 pairs; small inputs get few blocks (latency), big ones 1184
+  size_t want = (n_pairs + (size_t)kSumThreads * kSumUnroll - 1) / ((size_t)kSumThreads * kSumUnroll);
+  if (want < 1) want = 1;
+  if (want > (size_t)kSumMaxBlocks) want = kSumMaxBlocks;
+  return (int)want;
+}
+
+template <typename T> struct Pair { T x, y; };
+
+template <typename T, bool kAligned>
+__device__ __forceinline__ Pair<T> load_pair(const T* __restrict__ in, size_t j) {
+  Pair<T> p;
+  if (kAligned) {
+    const ulonglong2 v = __ldcs(reinterpret_cast<const ulonglong2*>(in) + j);
+    p.x = *reinterpret_cast<const T*>(&v.x);
+    p.y = *reinterpret_cast<const T*>(&v.y);
+  } else {
+    p.x = __ldcs(in + 2 * j);
+    p.y = __ldcs(in + 2 * j + 1);
+  }
+  return p;
+}
+
+template <typename T>
+__device__ __forceinline__ T shfl_xor_t(T v, int m) {
+  unsigned long long u = *reinterpret_cast<unsigned long long*>(&v);
+  u = __shfl_xor_sync(0xffffffffu, u, m);
+  return *reinterpret_cast<T*>(&u);
+}
+
+// fixed tree over the 256 threads of a block; result valid in thread 0
+template <typename T>
+__device__ __forceinline__ T block_tree_sum(T v, T* smem /* >= 8 */) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) v = v + shfl_xor_t(v, m);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  T r = T(0);
+  if (warp == 0) {
+    r = (lane < kSumThreads / 32) ? smem[lane] : T(0);
+#pragma unroll
+    for (int m = 4; m >= 1; m >>= 1) r = r + shfl_xor_t(r, m);
+  }
+  __syncthreads();
+  return r;
+}
+
+template <typename T, bool kAligned>
+__global__ void __launch_bounds__(kSumThreads)
+sum_kernel(const T* __restrict__ in, size_t n, T* __restrict__ partials, unsigned* __restrict__ ticket,
+           T* __restrict__ out) {
+  __shared__ T smem[8];
+  __shared__ bool is_last;
+  const size_t n_pairs = n >> 1;
+  const size_t stride = (size_t)gridDim.x * kSumThreads;
+  T ax[kSumUnroll], ay[kSumUnroll];
+#pragma unroll
+  for (int k = 0; k < kSumUnroll; ++k) { ax[k] = T(0); ay[k] = T(0); }
+
+  size_t j = (size_t)blockIdx.x * kSumThreads + threadIdx.x;
+  // main loop: all 4 loads in range
+  for (; j + (kSumUnroll - 1) * stride < n_pairs; j += kSumUnroll * stride) {
+    Pair<T> p[kSumUnroll];
+#pragma unroll
+    for (int k = 0; k < kSumUnroll; ++k) p[k] = load_pair<T, kAligned>(in, j + k * stride);
+#pragma unroll
+    for (int k = 0; k < kSumUnroll; ++k) { ax[k] = ax[k] + p[k].x; ay[k] = ay[k] + p[k].y; }
+  }
+  // remainder: same accumulator assignment (slot k gets pair j + k*stride)
+#pragma unroll
+  for (int k = 0; k < kSumUnroll; ++k) {
+    const size_t jj = j + k * stride;
+    if (jj < n_pairs) {
+      const Pair<T> p = load_pair<T, kAligned>(in, jj);
+      ax[k] = ax[k] + p.x; ay[k] = ay[k] + p.y;
+    }
+  }
+  T v = ((ax[0] + ay[0]) + (ax[1] + ay[1])) + ((ax[2] + ay[2]) + (ax[3] + ay[3]));
+  v = block_tree_sum(v, smem);
+
+  if (gridDim.x == 1) {
+    if (threadIdx.x == 0) { if (n & 1) v = v + in[n - 1]; *out = v; }
+    return;
+  }
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = v;
+    __threadfence();
+    const unsigned t = atomicAdd(ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // fixed-order reduction of the partials: thread t takes t, t+256, ... then the block tree
+  T acc = T(0);
+  for (unsigned i = threadIdx.x; i < gridDim.x; i += kSumThreads) acc = acc + __ldcg(partials + i);
+  acc = block_tree_sum(acc, smem);
+  if (threadIdx.x == 0) {
+    if (n & 1) acc = acc + in[n - 1];
+    *out = acc;
+    *ticket = 0;  // leave the workspace ready for the next launch on this stream
+  }
+}
+
+// Reference association order (float64_avx2_amd64.s:36-43,86-174): 32 interleaved serial
+// chains over the first n&~31 elements — lane j of ONE warp owns chain j, so every load is a
+// fully coalesced 256-byte row — combined as (y0+y4)+(y2+y6) + (y1+y5)+(y3+y7) per ymm lane,
+// lo128+hi128, hadd, then the n&31 tail sequentially.  n < 32: purely sequential.
+// Latency-bound by design (n/32 dependent DADDs); bit-exact with the reference on any input.
+__global__ void __launch_bounds__(32) sum_f64_reforder_kernel(const double* __restrict__ in, size_t n, double* out) {
+  const int lane = threadIdx.x;
+  const size_t body = (n > 31) ? (n & ~(size_t)31) : 0;
+  double acc = 0.0;
+  size_t k = 0;
+  // 8 independent loads in flight per lane; the adds stay in chain order
+  for (; k + 8 * 32 <= body; k += 8 * 32) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldcs(in + k + u * 32 + lane);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc = __dadd_rn(acc, v[u]);
+  }
+  for (; k < body; k += 32) acc = __dadd_rn(acc, __ldcs(in + k + lane));
+  double s = 0.0;
+  if (body) {
+    // lane j = 4*y + q  (ymm register y, 64-bit lane q)
+    // t_y = acc[y] + acc[y+4]  for y in 0..3            -> xor 16
+    double t = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 16));
+    // u0 = t0 + t2, u1 = t1 + t3                         -> xor 8 (valid in y<2)
+    double u = __dadd_rn(t, __shfl_xor_sync(0xffffffffu, t, 8));
+    // v = u0 + u1                                         -> xor 4 (valid in y==0, lanes q=0..3)
+    double v = __dadd_rn(u, __shfl_xor_sync(0xffffffffu, u, 4));
+    // w0 = v[0]+v[2], w1 = v[1]+v[3]                      -> xor 2
+    double w = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 2));
+    // hadd: w0 + w1                                       -> xor 1
+    s = __dadd_rn(w, __shfl_xor_sync(0xffffffffu, w, 1));
+  }
+  if (lane == 0) {
+    for (size_t i = body; i < n; ++i) s = __dadd_rn(s, in[i]);
+    *out = s;
+  }
+}
+
+template <typename T>
+static ag_status launch_sum(const T* d_in, size_t n, T* d_res, cudaStream_t st) {
+  if (n == 0) {
+    AG_CUDA_TRY(cudaMemsetAsync(d_res, 0, sizeof(T), st));
+    return AG_OK;
+  }
+  if ((reinterpret_cast<uintptr_t>(d_in) & 7) != 0) AG_FAIL(AG_ERR_INVALID, "sum: input is not 8-byte aligned");
+  Workspace* ws;
+  AG_TRY(get_workspace(st, &ws));
+  const int grid = sum_grid(n >> 1);
+  const bool aligned = (reinterpret_cast<uintptr_t>(d_in) & 15) == 0;
+  if (aligned)
+    sum_kernel<T, true><<<grid, kSumThreads, 0, st>>>(d_in, n, (T*)ws->partials, ws->ticket, d_res);
+  else
+    sum_kernel<T, false><<<grid, kSumThreads, 0, st>>>(d_in, n, (T*)ws->partials, ws->ticket, d_res);
+  return check_launch("sum_kernel");
+}
+
+// Host-pointer flavour: stage the whole column to HBM with chunked async copies (the copy is
+// >100x the kernel time, so there is nothing to gain from overlapping the reduction), then run
+// exactly the same kernel as the device flavour => identical bits.
+template <typename T, typename F>
+static ag_status host_sum(const T* buf, size_t n, T* res, F&& launch) {
+  if (!res) AG_FAIL(AG_ERR_INVALID, "sum: NULL result pointer");
+  AG_TRY(ensure_init());
+  if (n == 0) { *res = T(0); return AG_OK; }
+  if (!buf) AG_FAIL(AG_ERR_INVALID, "sum: NULL buffer");
+  CallStream cs;  // a private pooled stream per call keeps concurrent host calls independent
+  AG_TRY(cs.acquire());
+  T* d_in = nullptr;
+  T* d_res = nullptr;
+  ag_status rc = AG_OK;
+  do {
+    if ((rc = dev_alloc_async((void**)&d_in, n * sizeof(T) + sizeof(T), cs)) != AG_OK) break;
+    d_res = d_in + n;
+    const size_t chunk = (size_t)8 << 20;  // elements (64 MiB)
+    cudaError_t e = cudaSuccess;
+    for (size_t off = 0; off < n && e == cudaSuccess; off += chunk) {
+      const size_t len = (n - off < chunk) ? (n - off) : chunk;
+      e = cudaMemcpyAsync(d_in + off, buf + off, len * sizeof(T), cudaMemcpyHostToDevice, cs);
+    }
+    if (e != cudaSuccess) { rc = cuda_fail(e, "H2D", __FILE__, __LINE__); break; }
+    if ((rc = launch(d_in, n, d_res, cs)) != AG_OK) break;
+    e = cudaMemcpyAsync(res, d_res, sizeof(T), cudaMemcpyDeviceToHost, cs);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
+    if (e != cudaSuccess) { rc = cuda_fail(e, "D2H", __FILE__, __LINE__); break; }
+  } while (0);
+  if (d_in) cudaFreeAsync(d_in, cs);
+  cudaStreamSynchronize(cs);
+  return rc;
+}
+
+static ag_status launch_reforder(const double* d_in, size_t n, double* d_res, cudaStream_t st) {
+  if (n == 0) { AG_CUDA_TRY(cudaMemsetAsync(d_res, 0, sizeof(double), st)); return AG_OK; }
+  sum_f64_reforder_kernel<<<1, 32, 0, st>>>(d_in, n, d_res);
+  return check_launch("sum_f64_reforder_kernel");
+}
+
+}  // namespace ag
+
+using namespace ag;
+
+extern "C" {
+
+ag_status ag_sum_f64_dev(const double* d, size_t n, double* d_res, ag_stream_t s) {
+  AG_TRY(ensure_init());
+  return launch_sum<double>(d, n, d_res, resolve_stream(s));
+}
+ag_status ag_sum_i64_dev(const int64_t* d, size_t n, int64_t* d_res, ag_stream_t s) {
+  AG_TRY(ensure_init());
+  // wrapping two's-complement sum == unsigned sum (int64.c:21-27)
+  return launch_sum<unsigned long long>((const unsigned long long*)d, n, (unsigned long long*)d_res, resolve_stream(s));
+}
+ag_status ag_sum_u64_dev(const uint64_t* d, size_t n, uint64_t* d_res, ag_stream_t s) {
+  AG_TRY(ensure_init());
+  return launch_sum<unsigned long long>((const unsigned long long*)d, n, (unsigned long long*)d_res, resolve_stream(s));
+}
+ag_status ag_sum_f64_reforder_dev(const double* d, size_t n, double* d_res, ag_stream_t s) {
+  AG_TRY(ensure_init());
+  return launch_reforder(d, n, d_res, resolve_stream(s));
+}
+
+ag_status ag_sum_f64(const double* buf, size_t n, double* res) {
+  return host_sum<double>(buf, n, res, [](const double* d, size_t m, double* r, cudaStream_t st) { return launch_sum<double>(d, m, r, st); });
+}
+ag_status ag_sum_i64(const int64_t* buf, size_t n, int64_t* res) {
+  return host_sum<unsigned long long>((const unsigned long long*)buf, n, (unsigned long long*)res,
+      [](const unsigned long long* d, size_t m, unsigned long long* r, cudaStream_t st) { return launch_sum<unsigned long long>(d, m, r, st); });
+}
+ag_status ag_sum_u64(const uint64_t* buf, size_t n, uint64_t* res) {
+  return host_sum<unsigned long long>((const unsigned long long*)buf, n, (unsigned long long*)res,
+      [](const unsigned long long* d, size_t m, unsigned long long* r, cudaStream_t st) { return launch_sum<unsigned long long>(d, m, r, st); });
+}
+ag_status ag_sum_f64_reforder(const double* buf, size_t n, double* res) {
+  return host_sum<double>(buf, n, res, [](const double* d, size_t m, double* r, cudaStream_t st) { return launch_reforder(d, m, r, st); });
+}
+
+}  // extern "C"

@@ -1,0 +1,366 @@
+/*
+ * arrowgpu.h — C ABI of the B200 (sm_100a) implementation of arrow-go's vectorised
+ * columnar compute hot path.
+ *
+ * This header is the drop-in boundary: every entry point replaces one native
+ * (c2goasm) inner loop or one pure-Go kernel body of the reference, and is what a
+ * cgo package inside arrow-go would bind (see INTEGRATION.md for the Go side).
+ * Reference citations are relative to the arrow-go tree (commit b3dacd2a).
+ *
+ * Conventions
+ *   - Plain pointers and sizes only.  No CUDA or torch types appear here.
+ *   - Every function returns an ag_status; AG_OK == 0.  ag_last_error() returns the
+ *     calling thread's last message.  Status codes map 1:1 onto arrow-go's error
+ *     sentinels (arrow/errors.go:21-28).
+ *   - Two flavours of every compute entry point:
+ *       ag_xxx(...)      HOST pointers.  Synchronous.  The library stages the
+ *                        buffers to HBM (pinned, chunked, full-duplex), runs the
+ *                        kernel(s) and copies the result back.  This is the form a
+ *                        per-span exec.ArrayKernelExec binds.
+ *       ag_xxx_dev(...)  DEVICE pointers + a stream.  Asynchronous.  Used when a
+ *                        record batch has been uploaded once (ag_upload) and many
+ *                        kernels run over it before anything is downloaded.
+ *   - `type` arguments are arrow.Type ids (arrow/datatype.go:36-72 ==
+ *     kernels/_lib/types.h:20-34); `op` arguments are kernels.ArithmeticOp values
+ *     (arrow/compute/internal/kernels/base_arithmetic.go:37-82 ==
+ *     _lib/base_arithmetic.cc:31-74).
+ *   - Bitmaps are Arrow LSB-first bitmaps addressed by (byte pointer, bit offset).
+ *     Bits outside [offset, offset+length) are never modified.
+ *   - Value pointers only need element alignment (a slice start is only
+ *     element-aligned); 16-byte aligned inputs take the vectorised path.
+ *   - All entry points are thread-safe and re-entrant (cgo calls arrive on arbitrary
+ *     OS threads, arrow/compute/exec.go:164-170).
+ *   - There is NO CPU fallback: without a usable sm_100 device every compute entry
+ *     point returns AG_ERR_CUDA.
+ */
+#ifndef ARROWGPU_H
+#define ARROWGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes (arrow/errors.go:21-28) --------------------------------------- */
+typedef int ag_status;
+#define AG_OK                   0
+#define AG_ERR_INVALID          1 /* arrow.ErrInvalid: overflow, divide by zero, length mismatch, bad argument */
+#define AG_ERR_INDEX            2 /* arrow.ErrIndex: take index out of bounds */
+#define AG_ERR_NOT_IMPLEMENTED  3 /* arrow.ErrNotImplemented */
+#define AG_ERR_TYPE             4 /* arrow.ErrType */
+#define AG_ERR_CUDA             5 /* device / driver failure (no sentinel in arrow-go; surfaces as ErrInvalid) */
+#define AG_ERR_OOM              6 /* device or pinned allocation failed */
+
+/* ---- arrow.Type ids that cross the boundary (arrow/datatype.go:36-72) ----------- */
+#define AG_TYPE_NULL     0
+#define AG_TYPE_BOOL     1
+#define AG_TYPE_UINT8    2
+#define AG_TYPE_INT8     3
+#define AG_TYPE_UINT16   4
+#define AG_TYPE_INT16    5
+#define AG_TYPE_UINT32   6
+#define AG_TYPE_INT32    7
+#define AG_TYPE_UINT64   8
+#define AG_TYPE_INT64    9
+#define AG_TYPE_FLOAT16 10
+#define AG_TYPE_FLOAT32 11
+#define AG_TYPE_FLOAT64 12
+
+/* ---- kernels.ArithmeticOp (base_arithmetic.go:37-82) ----------------------------- */
+#define AG_OP_ADD             0
+#define AG_OP_SUB             1
+#define AG_OP_MUL             2
+#define AG_OP_DIV             3
+#define AG_OP_ABS             4
+#define AG_OP_NEGATE          5
+#define AG_OP_SIGN           20
+#define AG_OP_ADD_CHECKED    21
+#define AG_OP_SUB_CHECKED    22
+#define AG_OP_MUL_CHECKED    23
+#define AG_OP_DIV_CHECKED    24
+#define AG_OP_ABS_CHECKED    25
+#define AG_OP_NEGATE_CHECKED 26
+
+/* ---- kernels.CompareOperator (kernels/types.go:62-71) ---------------------------- */
+#define AG_CMP_EQ 0
+#define AG_CMP_NE 1
+#define AG_CMP_GT 2
+#define AG_CMP_GE 3
+#define AG_CMP_LT 4 /* executed as GT with operands flipped, like scalar_compare.go:73-99 */
+#define AG_CMP_LE 5 /* executed as GE with operands flipped */
+
+/* operand shapes of the binary entry points (arr_arr / arr_scalar / scalar_arr) */
+#define AG_SHAPE_AA 0
+#define AG_SHAPE_AS 1
+#define AG_SHAPE_SA 2
+
+/* ---- bitmap binary ops (arrow/bitutil/bitmaps.go:601-639) ------------------------ */
+#define AG_BITOP_AND     0
+#define AG_BITOP_OR      1
+#define AG_BITOP_XOR     2
+#define AG_BITOP_ANDNOT  3 /* l & ~r */
+#define AG_BITOP_XNOR    4
+/* Kleene word ops (scalar_boolean.go:103-105,180-182,290-292) */
+#define AG_KLEENE_AND     0
+#define AG_KLEENE_OR      1
+#define AG_KLEENE_ANDNOT  2
+
+/* ---- kernels.NullSelectionBehavior (vector_selection.go:34-39) ------------------- */
+#define AG_DROP_NULLS 0
+#define AG_EMIT_NULLS 1
+
+/* sentinel written to *first_bad / *bad_pos when no element failed */
+#define AG_NO_ERROR_POS INT64_MAX
+
+typedef void* ag_stream_t; /* opaque (a CUDA stream); NULL = the library's default stream */
+typedef void* ag_event_t;  /* opaque (a CUDA event) */
+
+/* ================================================================================= *
+ * Runtime, residency, streams
+ * ================================================================================= */
+
+/* Bind the calling process to one device (one process per GPU) and create the stream
+ * pool.  device < 0 selects LOCAL_RANK from the environment, else device 0.
+ * Idempotent.  Every compute call initialises lazily with device -1 if this was never
+ * called. */
+ag_status ag_init(int device);
+ag_status ag_shutdown(void);
+ag_status ag_device_count(int* count);
+ag_status ag_device_info(int* device, int* sm_count, size_t* hbm_bytes, int* cc_major, int* cc_minor);
+/* Copies the calling thread's last error message (NUL-terminated) into buf. */
+void ag_last_error(char* buf, size_t buflen);
+/* Library version string and the number of kernels this process has launched
+ * (used by bench.py's gpu_launches and by the loaded-native-code check). */
+const char* ag_version(void);
+uint64_t ag_kernel_launch_count(void);
+
+/* Pinned host memory: backs a Go memory.Allocator (arrow/memory/allocator.go:23-27);
+ * shape follows arrow/memory/internal/cgoalloc/allocator.h:13-18.  64-byte aligned,
+ * zero-initialised like memory.GoAllocator / mallocator (calloc). */
+ag_status ag_host_alloc(void** ptr, size_t nbytes);
+ag_status ag_host_realloc(void** ptr, size_t old_nbytes, size_t new_nbytes);
+ag_status ag_host_free(void* ptr);
+/* Page-lock memory the caller already owns (e.g. a Mallocator buffer). */
+ag_status ag_host_register(void* ptr, size_t nbytes);
+ag_status ag_host_unregister(void* ptr);
+
+ag_status ag_dev_alloc(void** dptr, size_t nbytes);   /* stream-ordered pool, zero-filled */
+ag_status ag_dev_free(void* dptr);
+ag_status ag_dev_memset(void* dptr, int byte, size_t nbytes, ag_stream_t s);
+ag_status ag_upload(void* dst_dev, const void* src_host, size_t nbytes, ag_stream_t s);
+ag_status ag_download(void* dst_host, const void* src_dev, size_t nbytes, ag_stream_t s);
+ag_status ag_copy_dev(void* dst_dev, const void* src_dev, size_t nbytes, ag_stream_t s);
+
+ag_status ag_stream_create(ag_stream_t* s);
+ag_status ag_stream_destroy(ag_stream_t s);
+ag_status ag_stream_sync(ag_stream_t s);
+ag_status ag_event_create(ag_event_t* e);
+ag_status ag_event_destroy(ag_event_t e);
+ag_status ag_event_record(ag_event_t e, ag_stream_t s);
+ag_status ag_event_sync(ag_event_t e);
+ag_status ag_event_elapsed_ms(ag_event_t start, ag_event_t stop, float* ms);
+/* Writes `nbytes` of a scratch buffer (> L2) so the next timed launch starts cold. */
+ag_status ag_flush_l2(ag_stream_t s);
+
+/* ================================================================================= *
+ * arrow/math Sum  — replaces sum_{float64,int64,uint64}_{avx2,sse4,neon}
+ *   arrow/math/_lib/float64.c:20-26, int64.c:21-27, uint64.c; Go: float64.go:34-39.
+ *   Validity is ignored (like the reference); n == 0 gives 0.
+ *   Integer sums wrap (two's complement) — bit-exact for any order.
+ *   Float64: default mode is a fixed-shape tree (result is a pure function of data
+ *   and n, independent of grid/alignment; bit-exact with the reference whenever the
+ *   sum is exactly representable, closer to the exact sum otherwise).
+ *   ag_sum_f64_reforder reproduces the reference AVX2 association order
+ *   (float64_avx2_amd64.s:36-43,86-164) bit-for-bit on any input.
+ * ================================================================================= */
+ag_status ag_sum_f64(const double* buf, size_t n, double* res);
+ag_status ag_sum_i64(const int64_t* buf, size_t n, int64_t* res);
+ag_status ag_sum_u64(const uint64_t* buf, size_t n, uint64_t* res);
+ag_status ag_sum_f64_reforder(const double* buf, size_t n, double* res);
+ag_status ag_sum_f64_dev(const double* d_buf, size_t n, double* d_res, ag_stream_t s);
+ag_status ag_sum_i64_dev(const int64_t* d_buf, size_t n, int64_t* d_res, ag_stream_t s);
+ag_status ag_sum_u64_dev(const uint64_t* d_buf, size_t n, uint64_t* d_res, ag_stream_t s);
+ag_status ag_sum_f64_reforder_dev(const double* d_buf, size_t n, double* d_res, ag_stream_t s);
+
+/* ================================================================================= *
+ * Arithmetic — replaces arithmetic_{binary,arr_scalar,scalar_arr,unary_same_types,
+ *   unary_diff_type}_{avx2,sse4} (_lib/base_arithmetic.cc:465-483) and the pure-Go
+ *   fallbacks of base_arithmetic.go.  Computed for EVERY slot (ScalarBinary
+ *   semantics, helpers.go:193-236).  Ops: ADD/SUB/MUL (+_CHECKED aliases, which for
+ *   these entry points are the unchecked loops exactly like the reference's native
+ *   code: base_arithmetic.cc:445-462).  Integers wrap.  The scalar operand is a
+ *   pointer to one element (host memory in both flavours).
+ * ================================================================================= */
+ag_status ag_arith_binary(int type, int8_t op, const void* l, const void* r, void* out, int64_t n);
+ag_status ag_arith_arr_scalar(int type, int8_t op, const void* l, const void* scalar_r, void* out, int64_t n);
+ag_status ag_arith_scalar_arr(int type, int8_t op, const void* scalar_l, const void* r, void* out, int64_t n);
+ag_status ag_arith_unary_same(int type, int8_t op, const void* in, void* out, int64_t n);      /* ABS, NEGATE, SIGN (+_CHECKED aliases) */
+ag_status ag_arith_unary_diff(int itype, int otype, int8_t op, const void* in, void* out, int64_t n); /* SIGN */
+ag_status ag_arith_binary_dev(int type, int8_t op, int shape, const void* d_l, const void* d_r, void* d_out,
+                              int64_t n, ag_stream_t s); /* scalar side: HOST pointer to one element */
+ag_status ag_arith_unary_same_dev(int type, int8_t op, const void* d_in, void* d_out, int64_t n, ag_stream_t s);
+ag_status ag_arith_unary_diff_dev(int itype, int otype, int8_t op, const void* d_in, void* d_out, int64_t n, ag_stream_t s);
+
+/* Checked integer arithmetic with the reference's exact overflow predicate and slot
+ * semantics — no native counterpart exists in the reference; this restates
+ *   ADD_CHECKED / SUB_CHECKED: base_arithmetic.go:249-278 under ScalarBinaryNotNull
+ *       (helpers.go:284-380): only slots valid in BOTH inputs are computed, null slots
+ *       are written as 0;
+ *   MUL_CHECKED: base_arithmetic.go:84-108,279-286 under ScalarBinary (all slots);
+ *   DIV / DIV_CHECKED: base_arithmetic.go:154-161,287-294 (divide by zero -> error),
+ *       ScalarBinaryNotNull.
+ * lvalid / rvalid may be NULL (= all valid); offsets are bit offsets.  A NULL scalar
+ * operand pointer means a null scalar (whole output untouched, status OK).
+ * On overflow / divide by zero returns AG_ERR_INVALID and *first_bad (may be NULL)
+ * receives the lowest failing row; otherwise AG_NO_ERROR_POS. */
+ag_status ag_arith_checked(int type, int8_t op, int shape,
+                           const void* l, const uint8_t* lvalid, int64_t loff,
+                           const void* r, const uint8_t* rvalid, int64_t roff,
+                           void* out, int64_t n, int64_t* first_bad);
+/* Device flavour: *d_first_bad must be initialised to AG_NO_ERROR_POS by the caller
+ * (ag_dev_memset is not enough: use ag_error_word_reset_dev); it is only lowered. */
+ag_status ag_arith_checked_dev(int type, int8_t op, int shape,
+                               const void* d_l, const uint8_t* d_lvalid, int64_t loff,
+                               const void* d_r, const uint8_t* d_rvalid, int64_t roff,
+                               void* d_out, int64_t n, int64_t* d_first_bad, ag_stream_t s);
+ag_status ag_error_word_reset_dev(int64_t* d_word, ag_stream_t s);
+
+/* ================================================================================= *
+ * Comparisons -> bitmap — replaces comparison_{equal,not_equal,greater,greater_equal}
+ *   _{arr_arr,arr_scalar,scalar_arr}_{avx2,sse4} (_lib/scalar_comparison.cc:210-256)
+ *   and compareKernel (scalar_comparisons.go:199-218).  `out_bits` points at the byte
+ *   holding the first output bit, `bit_offset` is used mod 8 exactly like the
+ *   reference; bits outside the written range are preserved.  LT/LE are accepted and
+ *   executed by operand flipping.  NaN: every predicate false except NE.
+ * ================================================================================= */
+ag_status ag_compare(int type, int cmp, int shape, const void* l, const void* r,
+                     uint8_t* out_bits, int64_t n, int bit_offset);
+ag_status ag_compare_dev(int type, int cmp, int shape, const void* d_l, const void* d_r,
+                         uint8_t* d_out_bits, int64_t n, int bit_offset, ag_stream_t s);
+/* Named forms with the reference's exact native signature (type,l,r,out,length,offset). */
+ag_status ag_cmp_eq_aa(int type, const void* l, const void* r, void* out, int64_t n, int offset);
+ag_status ag_cmp_eq_as(int type, const void* l, const void* r, void* out, int64_t n, int offset);
+ag_status ag_cmp_eq_sa(int type, const void* l, const void* r, void* out, int64_t n, int offset);
+ag_status ag_cmp_ne_aa(int type, const void* l, const void* r, void* out, int64_t n, int offset);
+ag_status ag_cmp_ne_as(int type, const void* l, const void* r, void* out, int64_t n, int offset);
+ag_status ag_cmp_ne_sa(int type, const void* l, const void* r, void* out, int64_t n, int offset);
+ag_status ag_cmp_gt_aa(int type, const void* l, const void* r, void* out, int64_t n, int offset);
+ag_status ag_cmp_gt_as(int type, const void* l, const void* r, void* out, int64_t n, int offset);
+ag_status ag_cmp_gt_sa(int type, const void* l, const void* r, void* out, int64_t n, int offset);
+ag_status ag_cmp_ge_aa(int type, const void* l, const void* r, void* out, int64_t n, int offset);
+ag_status ag_cmp_ge_as(int type, const void* l, const void* r, void* out, int64_t n, int offset);
+ag_status ag_cmp_ge_sa(int type, const void* l, const void* r, void* out, int64_t n, int offset);
+
+/* ================================================================================= *
+ * Bitmaps — replaces bitmap_aligned_{and,or,and_not,xor}_{avx2,sse4}
+ *   (arrow/bitutil/_lib/bitmap_ops.c:24-46) plus the Go paths around them:
+ *   alignedBitmapOp / unalignedBitmapOp (bitmaps.go:527-591), CopyBitmap /
+ *   InvertBitmap (:483-491), SetBitsTo (bitutil.go:158), CountSetBits (:89).
+ *   Arbitrary bit offsets on every operand; `out` may alias an input with the same
+ *   offset (propagateNulls accumulates in place, executor.go:340-347).
+ * ================================================================================= */
+ag_status ag_bitmap_op(int bitop, const uint8_t* l, int64_t loff, const uint8_t* r, int64_t roff,
+                       uint8_t* out, int64_t ooff, int64_t nbits);
+ag_status ag_bitmap_copy(const uint8_t* src, int64_t soff, int64_t nbits, uint8_t* dst, int64_t doff);
+ag_status ag_bitmap_invert(const uint8_t* src, int64_t soff, int64_t nbits, uint8_t* dst, int64_t doff);
+ag_status ag_bitmap_set(uint8_t* bits, int64_t off, int64_t nbits, int value);
+ag_status ag_bitmap_popcount(const uint8_t* bits, int64_t off, int64_t nbits, int64_t* count);
+ag_status ag_bitmap_op_dev(int bitop, const uint8_t* d_l, int64_t loff, const uint8_t* d_r, int64_t roff,
+                           uint8_t* d_out, int64_t ooff, int64_t nbits, ag_stream_t s);
+ag_status ag_bitmap_copy_dev(const uint8_t* d_src, int64_t soff, int64_t nbits, uint8_t* d_dst, int64_t doff, ag_stream_t s);
+ag_status ag_bitmap_invert_dev(const uint8_t* d_src, int64_t soff, int64_t nbits, uint8_t* d_dst, int64_t doff, ag_stream_t s);
+ag_status ag_bitmap_set_dev(uint8_t* d_bits, int64_t off, int64_t nbits, int value, ag_stream_t s);
+/* *d_count is overwritten with the population count of [off, off+nbits). */
+ag_status ag_bitmap_popcount_dev(const uint8_t* d_bits, int64_t off, int64_t nbits, int64_t* d_count, ag_stream_t s);
+
+/* Kleene logic on (validity, data) pairs — computeKleene, scalar_boolean.go:29-65 with
+ * the word lambdas at :103-105 (and), :180-182 (or), :290-292 (and_not).  lvalid /
+ * rvalid may be NULL (= all valid).  Both outputs use bit offset ooff. */
+ag_status ag_kleene(int kop, const uint8_t* lvalid, const uint8_t* ldata, int64_t loff,
+                    const uint8_t* rvalid, const uint8_t* rdata, int64_t roff,
+                    uint8_t* out_valid, uint8_t* out_data, int64_t ooff, int64_t nbits);
+ag_status ag_kleene_dev(int kop, const uint8_t* d_lvalid, const uint8_t* d_ldata, int64_t loff,
+                        const uint8_t* d_rvalid, const uint8_t* d_rdata, int64_t roff,
+                        uint8_t* d_out_valid, uint8_t* d_out_data, int64_t ooff, int64_t nbits, ag_stream_t s);
+
+/* ================================================================================= *
+ * Filter — replaces PrimitiveFilter (vector_selection.go:449-520) =
+ *   getFilterOutputSize (:57-81) + primitiveFilterImpl (:267-395) + filterWriter
+ *   (:397-421), and GetTakeIndices (:102-236).
+ *   values: fixed width, bit_width in {8,16,32,64}; `vals` points at element 0 of the
+ *   buffer and voff is the element offset (needed for the validity bitmap too).
+ *   vvalid / mvalid may be NULL.  Output: stable compaction; out_valid (may be NULL when the
+ *   output cannot contain nulls) receives the compacted validity starting at bit 0;
+ *   EMIT_NULLS writes value 0 / validity 0 for null mask slots.
+ * ================================================================================= */
+ag_status ag_filter_output_size(const uint8_t* mask, const uint8_t* mvalid, int64_t moff, int64_t n,
+                                int null_selection, int64_t* out_len);
+ag_status ag_filter_primitive(int bit_width, const void* vals, const uint8_t* vvalid, int64_t voff,
+                              const uint8_t* mask, const uint8_t* mvalid, int64_t moff, int64_t n,
+                              int null_selection, void* out, uint8_t* out_valid,
+                              int64_t* out_len, int64_t* out_nulls);
+ag_status ag_filter_output_size_dev(const uint8_t* d_mask, const uint8_t* d_mvalid, int64_t moff, int64_t n,
+                                    int null_selection, int64_t* d_out_len, ag_stream_t s);
+/* out_capacity = number of rows d_out (and d_out_valid) can hold: the exact output length
+ * when the caller ran ag_filter_output_size_dev first, or n as an upper bound.  Rows past the
+ * capacity are dropped; *d_out_len always receives the full number of emitted rows so a
+ * truncation is detectable.  d_out_valid (may be NULL when the output cannot contain nulls:
+ * no values validity, and DROP_NULLS or no mask validity) must be 4-byte aligned and hold
+ * ceil(out_capacity/32) 32-bit words; it is fully overwritten (Arrow buffers are padded to 64 B). */
+ag_status ag_filter_primitive_dev(int bit_width, const void* d_vals, const uint8_t* d_vvalid, int64_t voff,
+                                  const uint8_t* d_mask, const uint8_t* d_mvalid, int64_t moff, int64_t n,
+                                  int null_selection, void* d_out, uint8_t* d_out_valid, int64_t out_capacity,
+                                  int64_t* d_out_len, ag_stream_t s);
+/* Fused Greater/…(values, scalar) + Filter: one pass over `values`, no intermediate
+ * mask (8 + 8s bytes/row).  Not a reference entry point — an optimisation
+ * the plugin applies to the greater→filter pipeline of config 3; results are identical
+ * to ag_compare followed by ag_filter_primitive. */
+ag_status ag_filter_compare_scalar_dev(int type, int cmp, const void* d_vals, const void* scalar_host,
+                                       int64_t n, void* d_out, int64_t out_capacity, int64_t* d_out_len, ag_stream_t s);
+/* GetTakeIndices: mask -> row indices; index_width 16 or 32 bits (the reference picks
+ * uint16 when n < 65535 else uint32, vector_selection.go:229-235). */
+ag_status ag_take_indices(int index_width, const uint8_t* mask, const uint8_t* mvalid, int64_t moff, int64_t n,
+                          int null_selection, void* out_idx, uint8_t* out_valid, int64_t* out_len);
+ag_status ag_take_indices_dev(int index_width, const uint8_t* d_mask, const uint8_t* d_mvalid, int64_t moff, int64_t n,
+                              int null_selection, void* d_out_idx, uint8_t* d_out_valid, int64_t out_capacity,
+                              int64_t* d_out_len, ag_stream_t s);
+
+/* ================================================================================= *
+ * Take — replaces PrimitiveTake (vector_selection.go:1162-1192) = checkIndexBounds
+ *   (helpers.go:929-981) + primitiveTakeImpl (:813-988).
+ *   out[i] = values[voff + idx[i]]; out_valid[i] = ivalid[ioff+i] & vvalid[voff+idx[i]].
+ *   Null output slots carry value 0 (the reference leaves its zero-initialised
+ *   allocation untouched).  idx_width in {8,16,32,64}; idx_signed: indices are
+ *   reinterpreted as unsigned after the bounds check (:1147-1159).  With bounds_check,
+ *   an out-of-range VALID index gives AG_ERR_INDEX, *bad_pos = lowest offending row and
+ *   *bad_index = its value ("%d out of bounds", helpers.go:951).
+ * ================================================================================= */
+ag_status ag_take_primitive(int bit_width, const void* vals, const uint8_t* vvalid, int64_t voff, int64_t vlen,
+                            int idx_width, int idx_signed, const void* idx, const uint8_t* ivalid, int64_t ioff,
+                            int64_t n, int bounds_check, void* out, uint8_t* out_valid,
+                            int64_t* out_nulls, int64_t* bad_pos, int64_t* bad_index);
+/* d_out_valid: 4-byte aligned, offset 0.  *d_bad_pos must have been reset with
+ * ag_error_word_reset_dev and is only lowered. */
+ag_status ag_take_primitive_dev(int bit_width, const void* d_vals, const uint8_t* d_vvalid, int64_t voff, int64_t vlen,
+                                int idx_width, int idx_signed, const void* d_idx, const uint8_t* d_ivalid, int64_t ioff,
+                                int64_t n, int bounds_check, void* d_out, uint8_t* d_out_valid,
+                                int64_t* d_bad_pos, ag_stream_t s);
+
+/* ================================================================================= *
+ * Parity helpers for inputs too large to bring back to the host:
+ * order-sensitive 64-bit checksum  sum_i mix64(i) * word_i  (mod 2^64)  over a buffer
+ * viewed as little-endian uint64 words (n_words = nbytes/8), and a counter-based
+ * generator so 1B-row datasets are produced on the device and reproduced on the CPU.
+ * ================================================================================= */
+ag_status ag_checksum64_dev(const void* d_buf, size_t n_words, uint64_t* d_res, ag_stream_t s);
+/* kind: 0 = splitmix64(seed + i) as u64; 1 = uniform int64 in [lo, hi] (hi-lo+1 <= 2^32, via
+ * multiply-shift on the high 32 bits); 2 = uniform int32 in [lo, hi]; 3 = double(k) with k
+ * uniform integer in [lo, hi]; 4 = bitmap with P(bit)=lo/hi (n = bits). */
+ag_status ag_generate_dev(int kind, uint64_t seed, int64_t lo, int64_t hi, void* d_out, size_t n, ag_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARROWGPU_H */

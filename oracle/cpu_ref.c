@@ -1,0 +1,632 @@
+/*
+ * cpu_ref.c — ORACLE: CPU restatement of arrow-go's compute hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under arrow_go_b200/ links, loads or calls this
+ * file.  See cpu_ref.h for how it is pinned against the reference.
+ *
+ * Reference paths are relative to the arrow-go tree (commit b3dacd2a):
+ *   K = arrow/compute/internal/kernels
+ */
+#include "cpu_ref.h"
+
+#include <math.h>
+#include <string.h>
+
+/* arrow.Type ids, arrow/datatype.go:36-72 */
+enum { T_BOOL = 1, T_U8 = 2, T_I8 = 3, T_U16 = 4, T_I16 = 5, T_U32 = 6, T_I32 = 7, T_U64 = 8, T_I64 = 9, T_F32 = 11, T_F64 = 12 };
+/* ArithmeticOp, K/base_arithmetic.go:37-82 */
+enum { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2, OP_DIV = 3, OP_ABS = 4, OP_NEG = 5, OP_SIGN = 20,
+       OP_ADD_C = 21, OP_SUB_C = 22, OP_MUL_C = 23, OP_DIV_C = 24, OP_ABS_C = 25, OP_NEG_C = 26 };
+enum { SH_AA = 0, SH_AS = 1, SH_SA = 2 };
+enum { CMP_EQ = 0, CMP_NE = 1, CMP_GT = 2, CMP_GE = 3, CMP_LT = 4, CMP_LE = 5 };
+
+/* ---- bit helpers: arrow/bitutil/bitutil.go:50-80 ------------------------------------ */
+static inline int bit_is_set(const uint8_t* b, int64_t i) { return (b[i >> 3] >> (i & 7)) & 1; }
+static inline void set_bit_to(uint8_t* b, int64_t i, int v) {
+  /* K/_lib/scalar_comparison.cc:59-61 — only bit i of byte i/8 changes */
+  b[i >> 3] = (uint8_t)((b[i >> 3] & ~(1u << (i & 7))) | ((unsigned)(v != 0) << (i & 7)));
+}
+
+/* ====================================================================================== *
+ * arrow/math Sum
+ * ====================================================================================== */
+
+/* float64_avx2_amd64.s:36-43 (8 ymm accumulators zeroed), :86-164 (unrolled body: acc[y] +=
+ * 4 lanes at x[32k + 4y ..]), combine :165-174:
+ *   y1+=y5; y3+=y7; y0+=y4; y2+=y6; y0+=y2; y1+=y3; y0+=y1; xmm = lo128+hi128; hadd;
+ * then the n&31 tail is added sequentially (:52-60).  n < 32 is purely sequential.
+ * volatile stops the compiler from re-associating or contracting. */
+double ref_sum_f64_avx2_order(const double* buf, size_t n) {
+  volatile double acc[8][4];
+  size_t body = n & ~(size_t)31;
+  double s = 0.0;
+  if (n > 31 && body != 0) {
+    for (int y = 0; y < 8; ++y) for (int q = 0; q < 4; ++q) acc[y][q] = 0.0;
+    for (size_t k = 0; k < body; k += 32)
+      for (int y = 0; y < 8; ++y)
+        for (int q = 0; q < 4; ++q) acc[y][q] = acc[y][q] + buf[k + 4 * y + q];
+    volatile double v[4];
+    for (int q = 0; q < 4; ++q) {
+      volatile double t1 = acc[1][q] + acc[5][q];
+      volatile double t3 = acc[3][q] + acc[7][q];
+      volatile double t0 = acc[0][q] + acc[4][q];
+      volatile double t2 = acc[2][q] + acc[6][q];
+      volatile double u0 = t0 + t2;
+      volatile double u1 = t1 + t3;
+      v[q] = u0 + u1;
+    }
+    volatile double w0 = v[0] + v[2];
+    volatile double w1 = v[1] + v[3];
+    s = w0 + w1;
+  } else {
+    body = 0;
+  }
+  volatile double r = s;
+  for (size_t i = body; i < n; ++i) r = r + buf[i];
+  return r;
+}
+
+/* arrow/math/float64.go:41-47 */
+double ref_sum_f64_sequential(const double* buf, size_t n) {
+  volatile double acc = 0.0;
+  for (size_t i = 0; i < n; ++i) acc = acc + buf[i];
+  return acc;
+}
+/* arrow/math/int64.go:41-47, _lib/int64.c:21-27: wrapping */
+int64_t ref_sum_i64(const int64_t* buf, size_t n) {
+  uint64_t acc = 0;
+  for (size_t i = 0; i < n; ++i) acc += (uint64_t)buf[i];
+  return (int64_t)acc;
+}
+uint64_t ref_sum_u64(const uint64_t* buf, size_t n) {
+  uint64_t acc = 0;
+  for (size_t i = 0; i < n; ++i) acc += buf[i];
+  return acc;
+}
+
+/* ====================================================================================== *
+ * Arithmetic, all slots: K/_lib/base_arithmetic.cc:76-285
+ * ====================================================================================== */
+#define BIN_LOOP(T, EXPR)                                                               \
+  do {                                                                                  \
+    const T* L = (const T*)l; const T* R = (const T*)r; T* O = (T*)out;                 \
+    for (int64_t i = 0; i < n; ++i) {                                                   \
+      const T a = (shape == SH_SA) ? L[0] : L[i];                                       \
+      const T b = (shape == SH_AS) ? R[0] : R[i];                                       \
+      O[i] = (T)(EXPR);                                                                 \
+    }                                                                                   \
+  } while (0)
+
+/* integers: arithmetic on the unsigned type of the same width (wraps; the low bits of
+ * signed and unsigned add/sub/mul agree — base_arithmetic.cc:121-148 does the same for
+ * Multiply via to_unsigned / uint32 promotion). */
+#define BIN_INT(UT)                                                                     \
+  switch (op) {                                                                         \
+    case OP_ADD: case OP_ADD_C: BIN_LOOP(UT, (UT)(a + b)); return REF_OK;               \
+    case OP_SUB: case OP_SUB_C: BIN_LOOP(UT, (UT)(a - b)); return REF_OK;               \
+    case OP_MUL: case OP_MUL_C: BIN_LOOP(UT, (UT)((uint64_t)a * (uint64_t)b)); return REF_OK; \
+    default: return REF_ERR_NOT_IMPLEMENTED;                                            \
+  }
+#define BIN_FLT(FT)                                                                     \
+  switch (op) {                                                                         \
+    case OP_ADD: case OP_ADD_C: BIN_LOOP(FT, a + b); return REF_OK;                     \
+    case OP_SUB: case OP_SUB_C: BIN_LOOP(FT, a - b); return REF_OK;                     \
+    case OP_MUL: case OP_MUL_C: BIN_LOOP(FT, a * b); return REF_OK;                     \
+    default: return REF_ERR_NOT_IMPLEMENTED;                                            \
+  }
+
+int ref_arith_binary(int type, int op, int shape, const void* l, const void* r, void* out, int64_t n) {
+  switch (type) {
+    case T_U8: case T_I8: BIN_INT(uint8_t)
+    case T_U16: case T_I16: BIN_INT(uint16_t)
+    case T_U32: case T_I32: BIN_INT(uint32_t)
+    case T_U64: case T_I64: BIN_INT(uint64_t)
+    case T_F32: BIN_FLT(float)
+    case T_F64: BIN_FLT(double)
+    default: return REF_ERR_TYPE;
+  }
+}
+
+/* unary: AbsoluteValue :160-176, Negate :194-205, NegateChecked :207-219 (unsigned -> 0),
+ * Sign :221-234.  Float abs clears the sign bit (NaN payload preserved); float negate
+ * is a sign flip (-x). */
+#define UN_LOOP(TI, TO, EXPR)                                                           \
+  do {                                                                                  \
+    const TI* I = (const TI*)in; TO* O = (TO*)out;                                      \
+    for (int64_t i = 0; i < n; ++i) { const TI x = I[i]; (void)x; O[i] = (TO)(EXPR); }           \
+  } while (0)
+
+#define UN_SINT(ST, UT)                                                                 \
+  switch (op) {                                                                         \
+    case OP_ABS: case OP_ABS_C: UN_LOOP(ST, ST, (ST)(((UT)x + (UT)(x >> (sizeof(ST) * 8 - 1))) ^ (UT)(x >> (sizeof(ST) * 8 - 1)))); return REF_OK; \
+    case OP_NEG: case OP_NEG_C: UN_LOOP(ST, ST, (ST)(0 - (UT)x)); return REF_OK;        \
+    case OP_SIGN: UN_LOOP(ST, ST, x > 0 ? 1 : (x ? -1 : 0)); return REF_OK;             \
+    default: return REF_ERR_NOT_IMPLEMENTED;                                            \
+  }
+#define UN_UINT(UT)                                                                     \
+  switch (op) {                                                                         \
+    case OP_ABS: case OP_ABS_C: UN_LOOP(UT, UT, x); return REF_OK;                      \
+    case OP_NEG: UN_LOOP(UT, UT, (UT)(~x + 1)); return REF_OK;                          \
+    case OP_NEG_C: UN_LOOP(UT, UT, 0); return REF_OK;                                   \
+    case OP_SIGN: UN_LOOP(UT, UT, x > 0 ? 1 : 0); return REF_OK;                        \
+    default: return REF_ERR_NOT_IMPLEMENTED;                                            \
+  }
+
+static inline float f32_abs(float x) { uint32_t u; memcpy(&u, &x, 4); u &= 0x7fffffffu; memcpy(&x, &u, 4); return x; }
+static inline double f64_abs(double x) { uint64_t u; memcpy(&u, &x, 8); u &= 0x7fffffffffffffffull; memcpy(&x, &u, 8); return x; }
+static inline float f32_neg(float x) { uint32_t u; memcpy(&u, &x, 4); u ^= 0x80000000u; memcpy(&x, &u, 4); return x; }
+static inline double f64_neg(double x) { uint64_t u; memcpy(&u, &x, 8); u ^= 0x8000000000000000ull; memcpy(&x, &u, 8); return x; }
+#define SIGN_F(x) (isnan(x) ? (x) : (((x) == 0) ? 0 : (signbit(x) ? -1 : 1)))
+
+int ref_arith_unary_same(int type, int op, const void* in, void* out, int64_t n) {
+  switch (type) {
+    case T_I8: UN_SINT(int8_t, uint8_t)
+    case T_I16: UN_SINT(int16_t, uint16_t)
+    case T_I32: UN_SINT(int32_t, uint32_t)
+    case T_I64: UN_SINT(int64_t, uint64_t)
+    case T_U8: UN_UINT(uint8_t)
+    case T_U16: UN_UINT(uint16_t)
+    case T_U32: UN_UINT(uint32_t)
+    case T_U64: UN_UINT(uint64_t)
+    case T_F32:
+      switch (op) {
+        case OP_ABS: case OP_ABS_C: UN_LOOP(float, float, f32_abs(x)); return REF_OK;
+        case OP_NEG: case OP_NEG_C: UN_LOOP(float, float, f32_neg(x)); return REF_OK;
+        case OP_SIGN: UN_LOOP(float, float, SIGN_F(x)); return REF_OK;
+        default: return REF_ERR_NOT_IMPLEMENTED;
+      }
+    case T_F64:
+      switch (op) {
+        case OP_ABS: case OP_ABS_C: UN_LOOP(double, double, f64_abs(x)); return REF_OK;
+        case OP_NEG: case OP_NEG_C: UN_LOOP(double, double, f64_neg(x)); return REF_OK;
+        case OP_SIGN: UN_LOOP(double, double, SIGN_F(x)); return REF_OK;
+        default: return REF_ERR_NOT_IMPLEMENTED;
+      }
+    default: return REF_ERR_TYPE;
+  }
+}
+
+/* arithmetic_unary_diff_type: only SIGN (base_arithmetic.cc:427-438); result -1/0/1 (NaN
+ * for float NaN when the output is float) converted to the output type. */
+#define SIGN_OUT(TI, SEXPR)                                                             \
+  switch (otype) {                                                                      \
+    case T_U8: UN_LOOP(TI, uint8_t, SEXPR); return REF_OK;                              \
+    case T_I8: UN_LOOP(TI, int8_t, SEXPR); return REF_OK;                               \
+    case T_U16: UN_LOOP(TI, uint16_t, SEXPR); return REF_OK;                            \
+    case T_I16: UN_LOOP(TI, int16_t, SEXPR); return REF_OK;                             \
+    case T_U32: UN_LOOP(TI, uint32_t, SEXPR); return REF_OK;                            \
+    case T_I32: UN_LOOP(TI, int32_t, SEXPR); return REF_OK;                             \
+    case T_U64: UN_LOOP(TI, uint64_t, SEXPR); return REF_OK;                            \
+    case T_I64: UN_LOOP(TI, int64_t, SEXPR); return REF_OK;                             \
+    case T_F32: UN_LOOP(TI, float, SEXPR); return REF_OK;                               \
+    case T_F64: UN_LOOP(TI, double, SEXPR); return REF_OK;                              \
+    default: return REF_ERR_TYPE;                                                       \
+  }
+#define SIGN_S(x) ((x) > 0 ? 1 : ((x) ? -1 : 0))
+#define SIGN_U(x) ((x) > 0 ? 1 : 0)
+
+int ref_arith_unary_diff(int itype, int otype, int op, const void* in, void* out, int64_t n) {
+  if (op != OP_SIGN) return REF_ERR_NOT_IMPLEMENTED;
+  switch (itype) {
+    case T_I8: SIGN_OUT(int8_t, SIGN_S(x))
+    case T_I16: SIGN_OUT(int16_t, SIGN_S(x))
+    case T_I32: SIGN_OUT(int32_t, SIGN_S(x))
+    case T_I64: SIGN_OUT(int64_t, SIGN_S(x))
+    case T_U8: SIGN_OUT(uint8_t, SIGN_U(x))
+    case T_U16: SIGN_OUT(uint16_t, SIGN_U(x))
+    case T_U32: SIGN_OUT(uint32_t, SIGN_U(x))
+    case T_U64: SIGN_OUT(uint64_t, SIGN_U(x))
+    default: return REF_ERR_NOT_IMPLEMENTED; /* float inputs: the Go side only uses same-type Sign */
+  }
+}
+
+/* ====================================================================================== *
+ * Checked integer arithmetic
+ *   ADD_CHECKED  K/base_arithmetic.go:249-263   carry = ((a&b) | ((a|b) &^ out)) >> shiftBy ; carry > 0
+ *   SUB_CHECKED  :264-278                        carry = ((^a&b) | (^(a^b) & out)) >> shiftBy ; carry > 0
+ *     shiftBy = bits-1 for unsigned, bits-2 for signed, evaluated IN THE TYPE OutT — i.e. an
+ *     arithmetic shift followed by a signed "> 0" for signed types.  (For signed types this
+ *     flags exactly "carry into the sign bit without carry out of it"; we restate the formula,
+ *     not the intent.)
+ *   slots: ScalarBinaryNotNull, K/helpers.go:284-380 — visit valid∧valid slots, write the
+ *     zero value into null slots; an all-null side leaves the output untouched.
+ *   MUL_CHECKED  :279-286 + mulWithOverflow :84-108 under ScalarBinary (EVERY slot, null or not);
+ *     an overflowing slot yields 0.
+ *   DIV / DIV_CHECKED :154-161,287-294: b == 0 -> errDivByZero, result 0; else a / b (Go
+ *     semantics: MinInt / -1 wraps to MinInt), ScalarBinaryNotNull.
+ * ====================================================================================== */
+#define CHK_SLOT_VALID(i)                                                               \
+  ((!lvalid || shape == SH_SA || bit_is_set(lvalid, loff + (i))) &&                    \
+   (!rvalid || shape == SH_AS || bit_is_set(rvalid, roff + (i))))
+
+#define CHK_ADDSUB(ST, IS_SIGNED, CARRY_EXPR, RES_EXPR)                                 \
+  do {                                                                                  \
+    const ST* L = (const ST*)l; const ST* R = (const ST*)r; ST* O = (ST*)out;           \
+    const int shift_by = (int)sizeof(ST) * 8 - 1 - (IS_SIGNED);                         \
+    for (int64_t i = 0; i < n; ++i) {                                                   \
+      if (!CHK_SLOT_VALID(i)) { O[i] = 0; continue; }                                   \
+      const ST a = (shape == SH_SA) ? L[0] : L[i];                                      \
+      const ST b = (shape == SH_AS) ? R[0] : R[i];                                      \
+      const ST o = (ST)(RES_EXPR);                                                      \
+      const ST carry = (ST)((ST)(CARRY_EXPR) >> shift_by);                              \
+      if (carry > 0 && i < bad) bad = i;                                                \
+      O[i] = o;                                                                         \
+    }                                                                                   \
+  } while (0)
+
+#define CHK_MUL(ST, UT, TMIN, TMAX)                                                     \
+  do {                                                                                  \
+    const ST* L = (const ST*)l; const ST* R = (const ST*)r; ST* O = (ST*)out;           \
+    for (int64_t i = 0; i < n; ++i) {                                                   \
+      const ST a = (shape == SH_SA) ? L[0] : L[i];                                      \
+      const ST b = (shape == SH_AS) ? R[0] : R[i];                                      \
+      int ovf = 0;                                                                      \
+      if (a > 0) { if (b > 0) { if (a > (TMAX) / b) ovf = 1; } else { if (b < (TMIN) / a) ovf = 1; } } \
+      else if (b > 0) { if (a < (TMIN) / b) ovf = 1; }                                  \
+      else { if (a != 0 && b < (TMAX) / a) ovf = 1; }                                   \
+      if (ovf) { if (i < bad) bad = i; O[i] = 0; }                                      \
+      else O[i] = (ST)((UT)a * (UT)b);                                                  \
+    }                                                                                   \
+  } while (0)
+
+#define CHK_DIV(ST, IS_SIGNED, TMIN)                                                    \
+  do {                                                                                  \
+    const ST* L = (const ST*)l; const ST* R = (const ST*)r; ST* O = (ST*)out;           \
+    for (int64_t i = 0; i < n; ++i) {                                                   \
+      if (!CHK_SLOT_VALID(i)) { O[i] = 0; continue; }                                   \
+      const ST a = (shape == SH_SA) ? L[0] : L[i];                                      \
+      const ST b = (shape == SH_AS) ? R[0] : R[i];                                      \
+      if (b == 0) { if (i < bad) bad = i; O[i] = 0; }                                   \
+      else if ((IS_SIGNED) && a == (TMIN) && b == (ST)-1) O[i] = a; /* Go wraps */      \
+      else O[i] = (ST)(a / b);                                                          \
+    }                                                                                   \
+  } while (0)
+
+#define CHK_TYPE(ST, UT, IS_SIGNED, TMIN, TMAX)                                         \
+  switch (op) {                                                                         \
+    case OP_ADD_C: CHK_ADDSUB(ST, IS_SIGNED, (ST)(a & b) | ((ST)(a | b) & (ST)~o), (UT)a + (UT)b); break;      \
+    case OP_SUB_C: CHK_ADDSUB(ST, IS_SIGNED, (ST)((ST)~a & b) | ((ST)~(ST)(a ^ b) & o), (UT)a - (UT)b); break; \
+    case OP_MUL_C: CHK_MUL(ST, UT, TMIN, TMAX); break;                                  \
+    case OP_DIV: case OP_DIV_C: CHK_DIV(ST, IS_SIGNED, TMIN); break;                    \
+    default: return REF_ERR_NOT_IMPLEMENTED;                                            \
+  }                                                                                     \
+  break;
+
+int ref_arith_checked(int type, int op, int shape,
+                      const void* l, const uint8_t* lvalid, int64_t loff,
+                      const void* r, const uint8_t* rvalid, int64_t roff,
+                      void* out, int64_t n, int64_t* first_bad) {
+  int64_t bad = REF_NO_ERROR_POS;
+  if (first_bad) *first_bad = bad;
+  /* null scalar: "fast path if one side is entirely null" helpers.go:287,314,341 */
+  if ((shape == SH_SA && l == NULL) || (shape == SH_AS && r == NULL)) return REF_OK;
+  switch (type) {
+    case T_I8: CHK_TYPE(int8_t, uint8_t, 1, INT8_MIN, INT8_MAX)
+    case T_I16: CHK_TYPE(int16_t, uint16_t, 1, INT16_MIN, INT16_MAX)
+    case T_I32: CHK_TYPE(int32_t, uint32_t, 1, INT32_MIN, INT32_MAX)
+    case T_I64: CHK_TYPE(int64_t, uint64_t, 1, INT64_MIN, INT64_MAX)
+    case T_U8: CHK_TYPE(uint8_t, uint8_t, 0, 0, UINT8_MAX)
+    case T_U16: CHK_TYPE(uint16_t, uint16_t, 0, 0, UINT16_MAX)
+    case T_U32: CHK_TYPE(uint32_t, uint32_t, 0, 0, UINT32_MAX)
+    case T_U64: CHK_TYPE(uint64_t, uint64_t, 0, 0, UINT64_MAX)
+    default: return REF_ERR_TYPE;
+  }
+  if (first_bad) *first_bad = bad;
+  return bad == REF_NO_ERROR_POS ? REF_OK : REF_ERR_INVALID;
+}
+
+/* ====================================================================================== *
+ * Comparisons: K/_lib/scalar_comparison.cc:63-206 (prefix bits up to the next byte boundary,
+ * 32-wide batches packed LSB-first, tail bits), driver K/scalar_comparisons.go:199-218,
+ * LT/LE by flipping K/../scalar_compare.go:73-99.  Bits outside [offset, offset+n) keep
+ * their value.
+ * ====================================================================================== */
+#define CMP_LOOP(T)                                                                     \
+  do {                                                                                  \
+    const T* L = (const T*)l; const T* R = (const T*)r;                                 \
+    for (int64_t i = 0; i < n; ++i) {                                                   \
+      const T a = (shape == SH_SA) ? L[0] : L[i];                                       \
+      const T b = (shape == SH_AS) ? R[0] : R[i];                                       \
+      int v;                                                                            \
+      switch (cmp) {                                                                    \
+        case CMP_EQ: v = (a == b); break;                                               \
+        case CMP_NE: v = (a != b); break;                                               \
+        case CMP_GT: v = (a > b); break;                                                \
+        case CMP_GE: v = (a >= b); break;                                               \
+        case CMP_LT: v = (b > a); break;                                                \
+        default: v = (b >= a); break;                                                   \
+      }                                                                                 \
+      set_bit_to(out, (int64_t)(offset % 8) + i, v);                                    \
+    }                                                                                   \
+  } while (0)
+
+int ref_compare(int type, int cmp, int shape, const void* l, const void* r, uint8_t* out, int64_t n, int offset) {
+  if (cmp < 0 || cmp > CMP_LE) return REF_ERR_INVALID;
+  switch (type) {
+    case T_U8: CMP_LOOP(uint8_t); break;
+    case T_I8: CMP_LOOP(int8_t); break;
+    case T_U16: CMP_LOOP(uint16_t); break;
+    case T_I16: CMP_LOOP(int16_t); break;
+    case T_U32: CMP_LOOP(uint32_t); break;
+    case T_I32: CMP_LOOP(int32_t); break;
+    case T_U64: CMP_LOOP(uint64_t); break;
+    case T_I64: CMP_LOOP(int64_t); break;
+    case T_F32: CMP_LOOP(float); break;
+    case T_F64: CMP_LOOP(double); break;
+    default: return REF_ERR_TYPE;
+  }
+  return REF_OK;
+}
+
+/* ====================================================================================== *
+ * Bitmaps: arrow/bitutil/bitmaps.go:527-639 (BitmapAnd/Or/Xor/AndNot/Xnor, any offsets,
+ * aligned path -> _lib/bitmap_ops.c:24-46), CopyBitmap/InvertBitmap :483-491,
+ * SetBitsTo bitutil.go:158, CountSetBits :89.
+ * ====================================================================================== */
+int ref_bitmap_op(int bitop, const uint8_t* l, int64_t loff, const uint8_t* r, int64_t roff,
+                  uint8_t* out, int64_t ooff, int64_t n) {
+  for (int64_t i = 0; i < n; ++i) {
+    const int a = bit_is_set(l, loff + i), b = bit_is_set(r, roff + i);
+    int v;
+    switch (bitop) {
+      case 0: v = a & b; break;
+      case 1: v = a | b; break;
+      case 2: v = a ^ b; break;
+      case 3: v = a & !b; break;
+      case 4: v = !(a ^ b); break;
+      default: return REF_ERR_INVALID;
+    }
+    set_bit_to(out, ooff + i, v);
+  }
+  return REF_OK;
+}
+void ref_bitmap_copy(const uint8_t* src, int64_t soff, int64_t n, uint8_t* dst, int64_t doff) {
+  for (int64_t i = 0; i < n; ++i) set_bit_to(dst, doff + i, bit_is_set(src, soff + i));
+}
+void ref_bitmap_invert(const uint8_t* src, int64_t soff, int64_t n, uint8_t* dst, int64_t doff) {
+  for (int64_t i = 0; i < n; ++i) set_bit_to(dst, doff + i, !bit_is_set(src, soff + i));
+}
+void ref_bitmap_set(uint8_t* bits, int64_t off, int64_t n, int value) {
+  for (int64_t i = 0; i < n; ++i) set_bit_to(bits, off + i, value);
+}
+int64_t ref_bitmap_popcount(const uint8_t* bits, int64_t off, int64_t n) {
+  int64_t c = 0;
+  int64_t i = 0;
+  /* byte-at-a-time once aligned: same answer as the bit loop, fast enough for 100M-bit masks */
+  while (i < n && ((off + i) & 7)) { c += bit_is_set(bits, off + i); ++i; }
+  while (i + 8 <= n) { c += __builtin_popcount(bits[(off + i) >> 3]); i += 8; }
+  while (i < n) { c += bit_is_set(bits, off + i); ++i; }
+  return c;
+}
+
+/* Kleene: K/scalar_boolean.go:29-65 computeKleene; word lambdas :103-105 (and),
+ * :180-182 (or), :290-292 (and_not). */
+int ref_kleene(int kop, const uint8_t* lvalid, const uint8_t* ldata, int64_t loff,
+               const uint8_t* rvalid, const uint8_t* rdata, int64_t roff,
+               uint8_t* out_valid, uint8_t* out_data, int64_t ooff, int64_t n) {
+  for (int64_t i = 0; i < n; ++i) {
+    const int lv = lvalid ? bit_is_set(lvalid, loff + i) : 1, ld = bit_is_set(ldata, loff + i);
+    const int rv = rvalid ? bit_is_set(rvalid, roff + i) : 1, rd = bit_is_set(rdata, roff + i);
+    const int lt = lv & ld, lf = lv & !ld, rt = rv & rd, rf = rv & !rd;
+    int ov, od;
+    switch (kop) {
+      case 0: ov = lf | rf | (lt & rt); od = lt & rt; break;
+      case 1: ov = lt | rt | (lf & rf); od = lt | rt; break;
+      case 2: ov = lf | rt | (lt & rf); od = lt & rf; break;
+      default: return REF_ERR_INVALID;
+    }
+    set_bit_to(out_valid, ooff + i, ov);
+    set_bit_to(out_data, ooff + i, od);
+  }
+  return REF_OK;
+}
+
+/* ====================================================================================== *
+ * Filter: K/vector_selection.go
+ *   getFilterOutputSize :57-81 — popcount(mask ∧ valid) for DropNulls, popcount(mask ∨ ¬valid)
+ *     for EmitNulls, CountSetBits(mask) without mask validity.
+ *   primitiveFilterImpl :267-395 walks ≤64-row blocks with four block-level fast paths
+ *     (:303-320) that are shortcuts of the per-row rule of the default branch (:321-392):
+ *       selected  (maskValid ∧ mask)        -> WriteValue; validity = 1 or valuesValid[i]
+ *       EmitNulls ∧ ¬maskValid              -> WriteNull (value 0 :417-421, validity 0)
+ *       otherwise                            -> skipped
+ *     and the no-null path :275-283 copies set-bit runs.  All block counters advance in lock
+ *     step with length min(64, remaining) (internal/bitutils/bit_block_counter.go:82-92,
+ *     144-166, 212-224), so the row rule below is the same function.  We keep the block
+ *     structure anyway so that the block-level branches are exercised as written.
+ *   PrimitiveFilter :449-520 — validity buffer only when either input may have nulls; values
+ *     under selected-but-null value slots are copied as they are.
+ * ====================================================================================== */
+int64_t ref_filter_output_size(const uint8_t* mask, const uint8_t* mvalid, int64_t moff, int64_t n, int null_selection) {
+  int64_t c = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const int m = bit_is_set(mask, moff + i);
+    const int v = mvalid ? bit_is_set(mvalid, moff + i) : 1;
+    c += null_selection ? (m | !v) : (m & v);
+  }
+  return c;
+}
+
+static inline void copy_elem(void* out, int64_t opos, const void* vals, int64_t ipos, int w) {
+  memcpy((char*)out + opos * w, (const char*)vals + ipos * w, (size_t)w);
+}
+
+int ref_filter_primitive(int bit_width, const void* vals, const uint8_t* vvalid, int64_t voff,
+                         const uint8_t* mask, const uint8_t* mvalid, int64_t moff, int64_t n,
+                         int null_selection, void* out, uint8_t* out_valid, int64_t* out_len, int64_t* out_nulls) {
+  if (bit_width != 8 && bit_width != 16 && bit_width != 32 && bit_width != 64) return REF_ERR_TYPE;
+  const int w = bit_width / 8;
+  int64_t opos = 0, nulls = 0;
+  const char* vbase = (const char*)vals + voff * w;
+  for (int64_t blk = 0; blk < n; blk += 64) {
+    const int64_t len = (n - blk < 64) ? (n - blk) : 64;
+    int64_t filter_cnt = 0, data_cnt = 0;
+    for (int64_t i = blk; i < blk + len; ++i) {
+      filter_cnt += bit_is_set(mask, moff + i) & (mvalid ? bit_is_set(mvalid, moff + i) : 1);
+      data_cnt += vvalid ? bit_is_set(vvalid, voff + i) : 1;
+    }
+    if (filter_cnt == len && data_cnt == len) {                       /* :303-308 */
+      if (out_valid) for (int64_t k = 0; k < len; ++k) set_bit_to(out_valid, opos + k, 1);
+      memcpy((char*)out + opos * w, vbase + blk * w, (size_t)(len * w));
+      opos += len;
+    } else if (filter_cnt == len) {                                   /* :309-316 */
+      for (int64_t k = 0; k < len; ++k) {
+        const int v = bit_is_set(vvalid, voff + blk + k);
+        set_bit_to(out_valid, opos + k, v);
+        nulls += !v;
+      }
+      memcpy((char*)out + opos * w, vbase + blk * w, (size_t)(len * w));
+      opos += len;
+    } else if (filter_cnt == 0 && null_selection == 0) {              /* :317-320 */
+      continue;
+    } else {                                                          /* :321-392 */
+      for (int64_t i = blk; i < blk + len; ++i) {
+        const int mv = mvalid ? bit_is_set(mvalid, moff + i) : 1;
+        const int m = bit_is_set(mask, moff + i);
+        if (mv && m) {
+          const int v = vvalid ? bit_is_set(vvalid, voff + i) : 1;
+          if (out_valid) set_bit_to(out_valid, opos, v);
+          nulls += !v;
+          copy_elem(out, opos, vbase, i, w);
+          ++opos;
+        } else if (!mv && null_selection == 1) {
+          if (out_valid) set_bit_to(out_valid, opos, 0);
+          memset((char*)out + opos * w, 0, (size_t)w);
+          ++nulls;
+          ++opos;
+        }
+      }
+    }
+  }
+  if (out_len) *out_len = opos;
+  if (out_nulls) *out_nulls = nulls;
+  return REF_OK;
+}
+
+/* GetTakeIndices: K/vector_selection.go:102-236.  Per row: valid∧true -> index; EmitNulls∧¬valid
+ * -> null slot (builder leaves the value 0); DropNulls drops nulls.  NB: the reference's
+ * EmitNulls loop only advances its validity block counter on non-empty blocks (:131-139), so
+ * after skipping an all-false block its all-valid shortcut can look at a stale block; we
+ * restate the documented row rule (the comment at :111-115), which is what every other branch
+ * implements.  See DESIGN.md "reference quirks". */
+int ref_take_indices(int index_width, const uint8_t* mask, const uint8_t* mvalid, int64_t moff, int64_t n,
+                     int null_selection, void* out_idx, uint8_t* out_valid, int64_t* out_len) {
+  if (index_width != 16 && index_width != 32) return REF_ERR_TYPE;
+  int64_t opos = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const int mv = mvalid ? bit_is_set(mvalid, moff + i) : 1;
+    const int m = bit_is_set(mask, moff + i);
+    if (mv && m) {
+      if (index_width == 16) ((uint16_t*)out_idx)[opos] = (uint16_t)i; else ((uint32_t*)out_idx)[opos] = (uint32_t)i;
+      if (out_valid) set_bit_to(out_valid, opos, 1);
+      ++opos;
+    } else if (!mv && null_selection == 1) {
+      if (index_width == 16) ((uint16_t*)out_idx)[opos] = 0; else ((uint32_t*)out_idx)[opos] = 0;
+      if (out_valid) set_bit_to(out_valid, opos, 0);
+      ++opos;
+    }
+  }
+  if (out_len) *out_len = opos;
+  return REF_OK;
+}
+
+/* ====================================================================================== *
+ * Take: K/vector_selection.go:1162-1192 PrimitiveTake
+ *   checkIndexBounds K/helpers.go:929-981 — valid index slots only; signed: idx < 0 or
+ *     idx >= len; error names the first offender in row order.
+ *   primitiveTakeImpl :878-988 — out[i] = values[idx[i]] for slots that are valid in the index
+ *     and (if values have nulls) in values; other slots are left as allocated (zero).
+ *     Indices are reinterpreted as unsigned of the same width (:1147-1159).
+ * ====================================================================================== */
+static inline uint64_t load_index(const void* idx, int64_t i, int width, int is_signed, int* negative) {
+  *negative = 0;
+  switch (width) {
+    case 8: { if (is_signed) { int8_t v = ((const int8_t*)idx)[i]; *negative = v < 0; return (uint64_t)(int64_t)v; } return ((const uint8_t*)idx)[i]; }
+    case 16: { if (is_signed) { int16_t v = ((const int16_t*)idx)[i]; *negative = v < 0; return (uint64_t)(int64_t)v; } return ((const uint16_t*)idx)[i]; }
+    case 32: { if (is_signed) { int32_t v = ((const int32_t*)idx)[i]; *negative = v < 0; return (uint64_t)(int64_t)v; } return ((const uint32_t*)idx)[i]; }
+    default: { if (is_signed) { int64_t v = ((const int64_t*)idx)[i]; *negative = v < 0; return (uint64_t)v; } return ((const uint64_t*)idx)[i]; }
+  }
+}
+
+int ref_take_primitive(int bit_width, const void* vals, const uint8_t* vvalid, int64_t voff, int64_t vlen,
+                       int idx_width, int idx_signed, const void* idx, const uint8_t* ivalid, int64_t ioff,
+                       int64_t n, int bounds_check, void* out, uint8_t* out_valid,
+                       int64_t* out_nulls, int64_t* bad_pos, int64_t* bad_index) {
+  if (bit_width != 8 && bit_width != 16 && bit_width != 32 && bit_width != 64) return REF_ERR_TYPE;
+  if (idx_width != 8 && idx_width != 16 && idx_width != 32 && idx_width != 64) return REF_ERR_INDEX;
+  const int w = bit_width / 8;
+  if (bad_pos) *bad_pos = REF_NO_ERROR_POS;
+  if (bounds_check) {
+    for (int64_t i = 0; i < n; ++i) {
+      if (ivalid && !bit_is_set(ivalid, ioff + i)) continue;
+      int neg;
+      const uint64_t v = load_index(idx, i, idx_width, idx_signed, &neg);
+      if (neg || v >= (uint64_t)vlen) {
+        if (bad_pos) *bad_pos = i;
+        if (bad_index) *bad_index = (int64_t)v;
+        return REF_ERR_INDEX;
+      }
+    }
+  }
+  int64_t nulls = 0;
+  const char* vbase = (const char*)vals + voff * w;
+  for (int64_t i = 0; i < n; ++i) {
+    int neg;
+    const int iv = ivalid ? bit_is_set(ivalid, ioff + i) : 1;
+    int ok = iv;
+    uint64_t v = 0;
+    if (iv) {
+      v = load_index(idx, i, idx_width, idx_signed, &neg);
+      if (idx_width < 64) v &= ((1ull << idx_width) - 1);   /* unsigned reinterpretation */
+      if (vvalid) ok = bit_is_set(vvalid, voff + (int64_t)v);
+    }
+    if (ok) {
+      copy_elem(out, i, vbase, (int64_t)v, w);
+      if (out_valid) set_bit_to(out_valid, i, 1);
+    } else {
+      memset((char*)out + i * w, 0, (size_t)w);
+      if (out_valid) set_bit_to(out_valid, i, 0);
+      ++nulls;
+    }
+  }
+  if (out_nulls) *out_nulls = nulls;
+  return REF_OK;
+}
+
+/* ====================================================================================== *
+ * Parity helpers (definitions shared with arrow_go_b200/csrc/util.cu)
+ * ====================================================================================== */
+static inline uint64_t mix64(uint64_t z) {
+  z += 0x9e3779b97f4a7c15ull;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
+uint64_t ref_checksum64(const void* buf, size_t n_words) {
+  const uint64_t* p = (const uint64_t*)buf;
+  uint64_t acc = 0;
+  for (size_t i = 0; i < n_words; ++i) acc += mix64((uint64_t)i) * p[i];
+  return acc;
+}
+void ref_generate(int kind, uint64_t seed, int64_t lo, int64_t hi, void* out, size_t n) {
+  const uint64_t span = (uint64_t)(hi - lo) + 1;
+  for (size_t i = 0; i < n; ++i) {
+    const uint64_t z = mix64(seed + (uint64_t)i);
+    const uint64_t k = ((z >> 32) * span) >> 32; /* uniform in [0, span) for span <= 2^32 */
+    switch (kind) {
+      case 0: ((uint64_t*)out)[i] = z; break;
+      case 1: ((int64_t*)out)[i] = lo + (int64_t)k; break;
+      case 2: ((int32_t*)out)[i] = (int32_t)(lo + (int64_t)k); break;
+      case 3: ((double*)out)[i] = (double)(lo + (int64_t)k); break;
+      case 4: {
+        /* bit i set with probability lo/hi */
+        const int bit = ((z >> 32) * (uint64_t)hi >> 32) < (uint64_t)lo;
+        uint8_t* b = (uint8_t*)out;
+        if ((i & 7) == 0) b[i >> 3] = 0;
+        b[i >> 3] |= (uint8_t)(bit << (i & 7));
+        break;
+      }
+      default: return;
+    }
+  }
+}
