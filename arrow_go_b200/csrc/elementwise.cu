@@ -209,7 +209,9 @@ struct UNegChecked {  // identical to UNeg except unsigned -> 0 (base_arithmetic
 };
 struct USign {
   template <typename TO, typename T> static __device__ __forceinline__ TO apply(T x) {
-    if constexpr (std::is_floating_point<T>::value) return (TO)(isnan(x) ? x : ((x == 0) ? T(0) : (signbit(x) ? T(-1) : T(1))));
+    // NaN: the reference's shipped AVX2/SSE4 objects lost the isnan() test of base_arithmetic.cc:224
+    // to -funsafe-math-optimizations (kernels/Makefile:23-27): sign(NaN) = +-1 by sign bit.
+    if constexpr (std::is_floating_point<T>::value) return (TO)((x == 0) ? T(0) : (signbit(x) ? T(-1) : T(1)));
     else if constexpr (std::is_unsigned<T>::value) return (TO)(x > 0 ? 1 : 0);
     else return (TO)(x > 0 ? 1 : (x ? -1 : 0));
   }

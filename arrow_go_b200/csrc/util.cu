@@ -1,6 +1,6 @@
 // util.cu — parity helpers for inputs too large to bring back to the host:
-// an order-sensitive 64-bit checksum and a counter-based generator whose CPU twin lives in
-// oracle/cpu_ref.c (ref_checksum64 / ref_generate).  Not part of the reference's surface.
+// an order-sensitive 64-bit checksum and a counter-based generator (the test suite keeps a CPU
+// twin of both definitions).  Not part of the reference's surface.
 #include "common.cuh"
 
 namespace ag {

@@ -156,7 +156,12 @@ static inline float f32_abs(float x) { uint32_t u; memcpy(&u, &x, 4); u &= 0x7ff
 static inline double f64_abs(double x) { uint64_t u; memcpy(&u, &x, 8); u &= 0x7fffffffffffffffull; memcpy(&x, &u, 8); return x; }
 static inline float f32_neg(float x) { uint32_t u; memcpy(&u, &x, 4); u ^= 0x80000000u; memcpy(&x, &u, 4); return x; }
 static inline double f64_neg(double x) { uint64_t u; memcpy(&u, &x, 8); u ^= 0x8000000000000000ull; memcpy(&x, &u, 8); return x; }
-#define SIGN_F(x) (isnan(x) ? (x) : (((x) == 0) ? 0 : (signbit(x) ? -1 : 1)))
+/* Sign on floats: the source reads isnan(x) ? x : ... (base_arithmetic.cc:224-225) but the
+ * reference's shipped AVX2/SSE4 objects were compiled with -funsafe-math-optimizations /
+ * -fno-trapping-math (kernels/Makefile:23-27) and the NaN test is gone from the instruction
+ * stream: sign(NaN) = +-1 by sign bit.  We follow the instruction stream (it is what runs on
+ * amd64); the pure-Go fallback (base_arithmetic.go:427-441) returns NaN instead. */
+#define SIGN_F(x) (((x) == 0) ? 0 : (signbit(x) ? -1 : 1))
 
 int ref_arith_unary_same(int type, int op, const void* in, void* out, int64_t n) {
   switch (type) {
