@@ -1,0 +1,1077 @@
+// compute.cc — host-side mirror of arrow-go's compute executors and function registry driving
+// the device kernels of libarrowgpu.so.  See arrowgpu_compute.h for the reference map.
+#include "arrowgpu_compute.h"
+
+#include <string.h>
+#include <algorithm>
+#include <mutex>
+
+namespace arrowgpu {
+
+// ---------------------------------------------------------------- types -------------------
+int BitWidth(Type t) {
+  switch (t) {
+    case Type::BOOL: return 1;
+    case Type::UINT8: case Type::INT8: return 8;
+    case Type::UINT16: case Type::INT16: case Type::FLOAT16: return 16;
+    case Type::UINT32: case Type::INT32: case Type::FLOAT32: return 32;
+    case Type::UINT64: case Type::INT64: case Type::FLOAT64: return 64;
+    default: return 0;
+  }
+}
+const char* TypeName(Type t) {
+  static const char* names[] = {"null", "bool", "uint8", "int8", "uint16", "int16", "uint32", "int32", "uint64", "int64", "float16", "float32", "float64"};
+  const int i = (int)t;
+  return (i >= 0 && i <= 12) ? names[i] : "unknown";
+}
+bool IsSignedInteger(Type t) { return t == Type::INT8 || t == Type::INT16 || t == Type::INT32 || t == Type::INT64; }
+bool IsInteger(Type t) { return IsSignedInteger(t) || t == Type::UINT8 || t == Type::UINT16 || t == Type::UINT32 || t == Type::UINT64; }
+bool IsFloating(Type t) { return t == Type::FLOAT32 || t == Type::FLOAT64; }
+bool IsNumeric(Type t) { return IsInteger(t) || IsFloating(t); }
+
+Status Status::FromNative(int c) {
+  if (c == AG_OK) return OK();
+  char buf[512];
+  ag_last_error(buf, sizeof(buf));
+  return Make(c, buf);
+}
+
+#define RETURN_NOT_OK(expr)                \
+  do {                                     \
+    ::arrowgpu::Status _st = (expr);       \
+    if (!_st.ok()) return _st;             \
+  } while (0)
+#define NATIVE(expr)                                            \
+  do {                                                          \
+    int _c = (expr);                                            \
+    if (_c != AG_OK) return ::arrowgpu::Status::FromNative(_c); \
+  } while (0)
+
+static inline int64_t BytesForBits(int64_t n) { return (n + 7) / 8; }
+static inline int64_t DataBytes(Type t, int64_t n) { return t == Type::BOOL ? BytesForBits(n) : n * (BitWidth(t) / 8); }
+
+// ---------------------------------------------------------------- Buffer ------------------
+Buffer::~Buffer() { if (data_) ag_dev_free(data_); }
+
+Status Buffer::Allocate(int64_t nbytes, std::shared_ptr<Buffer>* out) {
+  auto b = std::shared_ptr<Buffer>(new Buffer());
+  void* p = nullptr;
+  NATIVE(ag_dev_alloc(&p, (size_t)(nbytes + 8)));  // +8: bitmap kernels address whole 32-bit words
+  b->data_ = (uint8_t*)p;
+  b->size_ = nbytes;
+  *out = std::move(b);
+  return Status::OK();
+}
+Status Buffer::FromHost(const void* host, int64_t nbytes, std::shared_ptr<Buffer>* out) {
+  RETURN_NOT_OK(Allocate(nbytes, out));
+  if (nbytes) {
+    NATIVE(ag_upload((*out)->data(), host, (size_t)nbytes, nullptr));
+    NATIVE(ag_stream_sync(nullptr));
+  }
+  return Status::OK();
+}
+Status Buffer::ToHost(void* host, int64_t nbytes, int64_t byte_offset) const {
+  if (nbytes) {
+    NATIVE(ag_download(host, data_ + byte_offset, (size_t)nbytes, nullptr));
+    NATIVE(ag_stream_sync(nullptr));
+  }
+  return Status::OK();
+}
+
+// ---------------------------------------------------------------- ArrayData ---------------
+std::shared_ptr<ArrayData> ArrayData::Slice(int64_t off, int64_t len) const {
+  auto d = std::make_shared<ArrayData>(*this);
+  d->offset = offset + off;
+  d->length = len;
+  // array.NewSliceData: a slice of an array with nulls has an unknown null count
+  if (null_count != 0 && !(off == 0 && len == length)) d->null_count = (null_count == length) ? len : kUnknownNullCount;
+  return d;
+}
+
+Status ArrayData::FromHost(Type type, int64_t length, int64_t offset, const uint8_t* validity, const void* values,
+                           int64_t null_count, std::shared_ptr<ArrayData>* out) {
+  if (BitWidth(type) == 0) return Status::TypeError(std::string("unsupported type ") + TypeName(type));
+  if (length < 0 || offset < 0) return Status::Invalid("negative length or offset");
+  auto d = std::make_shared<ArrayData>();
+  d->type = type; d->length = length; d->offset = offset; d->null_count = validity ? null_count : 0;
+  RETURN_NOT_OK(Buffer::FromHost(values, DataBytes(type, offset + length), &d->buffers[1]));
+  if (validity) RETURN_NOT_OK(Buffer::FromHost(validity, BytesForBits(offset + length), &d->buffers[0]));
+  *out = std::move(d);
+  return Status::OK();
+}
+
+Status ArrayData::ToHost(void* values, uint8_t* validity, int64_t* null_count_out) const {
+  if (length == 0) { if (null_count_out) *null_count_out = 0; return Status::OK(); }
+  const int w = BitWidth(type);
+  if (values) {
+    if (type == Type::BOOL) {
+      // re-base to bit 0 on the device, then copy
+      std::shared_ptr<Buffer> tmp;
+      RETURN_NOT_OK(Buffer::Allocate(BytesForBits(length), &tmp));
+      NATIVE(ag_bitmap_copy_dev(buffers[1]->data(), offset, length, tmp->data(), 0, nullptr));
+      RETURN_NOT_OK(tmp->ToHost(values, BytesForBits(length)));
+    } else {
+      RETURN_NOT_OK(buffers[1]->ToHost(values, length * (w / 8), offset * (w / 8)));
+    }
+  }
+  int64_t nulls = null_count;
+  if (buffers[0]) {
+    std::shared_ptr<Buffer> tmp;
+    RETURN_NOT_OK(Buffer::Allocate(BytesForBits(length) + 8, &tmp));
+    NATIVE(ag_bitmap_copy_dev(buffers[0]->data(), offset, length, tmp->data(), 0, nullptr));
+    if (validity) RETURN_NOT_OK(tmp->ToHost(validity, BytesForBits(length)));
+    if (nulls == kUnknownNullCount) {
+      int64_t* cnt = (int64_t*)(tmp->data() + ((BytesForBits(length) + 7) & ~7ll));
+      std::shared_ptr<Buffer> cbuf;
+      RETURN_NOT_OK(Buffer::Allocate(8, &cbuf));
+      (void)cnt;
+      NATIVE(ag_bitmap_popcount_dev(buffers[0]->data(), offset, length, (int64_t*)cbuf->data(), nullptr));
+      int64_t set = 0;
+      RETURN_NOT_OK(cbuf->ToHost(&set, 8));
+      nulls = length - set;
+    }
+  } else {
+    if (validity) memset(validity, 0xff, (size_t)BytesForBits(length));
+    nulls = 0;
+  }
+  if (null_count_out) *null_count_out = nulls;
+  return Status::OK();
+}
+
+int64_t ChunkedArray::NullN() const {
+  int64_t n = 0;
+  for (auto& c : chunks) n += (c->null_count == kUnknownNullCount) ? 1 : c->null_count;  // "may have nulls"
+  return n;
+}
+
+namespace compute {
+Type Datum::type() const {
+  switch (kind) {
+    case DatumKind::SCALAR: return scalar->type;
+    case DatumKind::ARRAY: return array->type;
+    case DatumKind::CHUNKED: return chunked->type;
+    default: return Type::NA;
+  }
+}
+int64_t Datum::Len() const {
+  switch (kind) {
+    case DatumKind::ARRAY: return array->length;
+    case DatumKind::CHUNKED: return chunked->length;
+    default: return -1;
+  }
+}
+}  // namespace compute
+
+// ======================================================================================
+// exec::ArraySpan
+// ======================================================================================
+namespace exec {
+
+void ArraySpan::SetMembers(const ArrayData& d) {
+  type = d.type; len = d.length; nulls = d.null_count; offset = d.offset;
+  for (int i = 0; i < 2; ++i) {
+    buffers[i] = BufferSpan();
+    if (d.buffers[i]) {
+      buffers[i].buf = d.buffers[i]->data();
+      buffers[i].len = d.buffers[i]->size();
+      buffers[i].owner = d.buffers[i];
+    }
+  }
+  if (!buffers[0].buf && type != Type::NA) nulls = 0;  // no validity bitmap => no nulls
+}
+
+void ArraySpan::SetSlice(int64_t off, int64_t length) {
+  if (off == offset && length == len) return;
+  if (type != Type::NA) {
+    if (nulls != 0) nulls = (nulls == len) ? length : kUnknownNullCount;
+  } else {
+    nulls = length;
+  }
+  offset = off; len = length;
+}
+
+Status ArraySpan::UpdateNullCount(int64_t* out) {
+  if (nulls != kUnknownNullCount) { if (out) *out = nulls; return Status::OK(); }
+  if (!buffers[0].buf || buffers[0].len == 0) { nulls = 0; if (out) *out = 0; return Status::OK(); }
+  std::shared_ptr<Buffer> cnt;
+  RETURN_NOT_OK(Buffer::Allocate(8, &cnt));
+  NATIVE(ag_bitmap_popcount_dev(buffers[0].buf, offset, len, (int64_t*)cnt->data(), nullptr));
+  int64_t set = 0;
+  RETURN_NOT_OK(cnt->ToHost(&set, 8));
+  nulls = len - set;
+  if (out) *out = nulls;
+  return Status::OK();
+}
+
+std::shared_ptr<ArrayData> ArraySpan::MakeData() const {
+  auto d = std::make_shared<ArrayData>();
+  d->type = type; d->length = len; d->null_count = nulls; d->offset = offset;
+  for (int i = 0; i < 2; ++i) d->buffers[i] = buffers[i].owner;
+  if (!d->buffers[0]) d->null_count = 0;
+  return d;
+}
+
+}  // namespace exec
+
+// ======================================================================================
+// compute: null propagation, span iteration, executors
+// ======================================================================================
+namespace compute {
+
+using exec::ArraySpan;
+using exec::ExecSpan;
+using exec::ExecValue;
+using exec::KernelCtx;
+
+NullGen GetNullGen(const ExecValue& v) {  // executor.go:190-214
+  if (v.type() == Type::NA) return NullGen::ALL_NULL;
+  if (v.IsScalar()) return v.scalar->valid ? NullGen::ALL_VALID : NullGen::ALL_NULL;
+  const ArraySpan& arr = v.array;
+  // do not count if they haven't been counted already
+  if (arr.nulls == 0 || arr.buffers[0].buf == nullptr) return NullGen::ALL_VALID;
+  if (arr.nulls == arr.len) return NullGen::ALL_NULL;
+  return NullGen::PERHAPS_NULL;
+}
+
+static NullGen GetNullGenDatum(const Datum& d) {  // executor.go:216-230
+  if (d.kind == DatumKind::CHUNKED) return NullGen::PERHAPS_NULL;
+  ExecValue v;
+  if (d.kind == DatumKind::ARRAY) v.array.SetMembers(*d.array);
+  else v.scalar = d.scalar.get();
+  return GetNullGen(v);
+}
+
+Status PropagateNulls(KernelCtx* ctx, const ExecSpan& batch, ArraySpan* out) {  // executor.go:237-349
+  if (out->type == Type::NA) return Status::OK();
+  if (out->offset != 0 && out->buffers[0].buf == nullptr)
+    return Status::Invalid("can only propagate nulls into pre-allocated memory when output offset is non-zero");
+  std::vector<const ArraySpan*> arrs_with_nulls;
+  bool is_all_null = false;
+  const bool prealloc = out->buffers[0].buf != nullptr;
+  for (auto& v : batch.values) {
+    const NullGen g = GetNullGen(v);
+    if (g == NullGen::ALL_NULL) is_all_null = true;
+    if (g != NullGen::ALL_VALID && v.IsArray()) arrs_with_nulls.push_back(&v.array);
+  }
+  auto alloc_bitmap = [&]() -> Status {
+    std::shared_ptr<Buffer> buf;
+    RETURN_NOT_OK(ctx->AllocateBitmap(out->len + out->offset, &buf));
+    out->buffers[0].buf = buf->data(); out->buffers[0].len = buf->size(); out->buffers[0].owner = buf; out->buffers[0].self_alloc = true;
+    return Status::OK();
+  };
+  if (is_all_null) {
+    out->nulls = out->len;
+    if (prealloc) { NATIVE(ag_bitmap_set_dev(out->buffers[0].buf, out->offset, out->len, 0, nullptr)); return Status::OK(); }
+    for (auto* arr : arrs_with_nulls) {
+      if (arr->nulls == arr->len && arr->buffers[0].owner) { out->buffers[0] = arr->buffers[0]; return Status::OK(); }
+    }
+    RETURN_NOT_OK(alloc_bitmap());
+    NATIVE(ag_bitmap_set_dev(out->buffers[0].buf, out->offset, out->len, 0, nullptr));
+    return Status::OK();
+  }
+  out->nulls = kUnknownNullCount;
+  switch (arrs_with_nulls.size()) {
+    case 0:
+      out->nulls = 0;
+      if (prealloc) NATIVE(ag_bitmap_set_dev(out->buffers[0].buf, out->offset, out->len, 1, nullptr));
+      return Status::OK();
+    case 1: {
+      const ArraySpan* arr = arrs_with_nulls[0];
+      out->nulls = arr->nulls;
+      if (prealloc) {
+        NATIVE(ag_bitmap_copy_dev(arr->buffers[0].buf, arr->offset, arr->len, out->buffers[0].buf, out->offset, nullptr));
+        return Status::OK();
+      }
+      if (arr->offset == 0) { out->buffers[0] = arr->buffers[0]; out->buffers[0].self_alloc = false; return Status::OK(); }  // zero-copy share
+      // (the reference also zero-copies byte-aligned offsets with SliceBuffer; a device Buffer has no
+      //  sub-buffer view here, so those are copied like the unaligned case — same bits)
+      RETURN_NOT_OK(alloc_bitmap());
+      NATIVE(ag_bitmap_copy_dev(arr->buffers[0].buf, arr->offset, arr->len, out->buffers[0].buf, 0, nullptr));
+      return Status::OK();
+    }
+    default: {
+      if (!prealloc) RETURN_NOT_OK(alloc_bitmap());
+      uint8_t* ob = out->buffers[0].buf;
+      NATIVE(ag_bitmap_op_dev(AG_BITOP_AND, arrs_with_nulls[0]->buffers[0].buf, arrs_with_nulls[0]->offset,
+                              arrs_with_nulls[1]->buffers[0].buf, arrs_with_nulls[1]->offset, ob, out->offset, out->len, nullptr));
+      for (size_t i = 2; i < arrs_with_nulls.size(); ++i)
+        NATIVE(ag_bitmap_op_dev(AG_BITOP_AND, ob, out->offset, arrs_with_nulls[i]->buffers[0].buf, arrs_with_nulls[i]->offset,
+                                ob, out->offset, out->len, nullptr));
+      return Status::OK();
+    }
+  }
+}
+
+// iterateExecSpans, executor.go:757-863, on chunk lengths only (metadata): testable without a GPU.
+Status IterateExecSpans(const std::vector<std::vector<int64_t>>& lens, const std::vector<bool>& is_chunked,
+                        int64_t max_chunk_size, std::vector<SpanPiece>* out) {
+  out->clear();
+  const size_t nargs = lens.size();
+  int64_t length = -1;
+  bool all_same = true;
+  for (size_t i = 0; i < nargs; ++i) {
+    if (lens[i].empty() && !is_chunked[i]) continue;  // scalar
+    int64_t tot = 0;
+    for (int64_t l : lens[i]) tot += l;
+    if (length < 0) length = tot; else if (length != tot) all_same = false;
+  }
+  if (length < 0) length = 1;  // all scalars: a single row (checkIfAllScalar / PromoteExecSpanScalars)
+  if (!all_same) return Status::Invalid("array args must all be the same length");
+  max_chunk_size = std::min(length, max_chunk_size);
+  std::vector<int> chunk_idx(nargs, 0);
+  std::vector<int64_t> value_pos(nargs, 0);
+  int64_t pos = 0;
+  while (pos != length) {
+    int64_t iter = std::min(length - pos, max_chunk_size);
+    for (size_t i = 0; i < nargs && iter > 0; ++i) {
+      if (!is_chunked[i]) continue;
+      if (lens[i].empty()) { iter = 0; continue; }
+      while (value_pos[i] == lens[i][chunk_idx[i]]) { chunk_idx[i]++; value_pos[i] = 0; }  // exhausted or zero-length chunk
+      iter = std::min(lens[i][chunk_idx[i]] - value_pos[i], iter);
+    }
+    SpanPiece p;
+    p.pos = pos; p.len = iter; p.chunk_index = chunk_idx; p.chunk_pos = value_pos;
+    out->push_back(p);
+    for (size_t i = 0; i < nargs; ++i)
+      if (!(lens[i].empty() && !is_chunked[i])) value_pos[i] += iter;
+    pos += iter;
+    if (iter == 0) break;  // degenerate (empty chunked argument)
+  }
+  return Status::OK();
+}
+
+// ---------------------------------------------------------------- registry ----------------
+Status FunctionRegistry::AddFunction(std::shared_ptr<Function> fn, bool allow_overwrite) {
+  if (!allow_overwrite && fns_.count(fn->Name())) return Status::Make(AG_ERR_INVALID, "already have a function registered with name: " + fn->Name());
+  fns_[fn->Name()] = std::move(fn);
+  return Status::OK();
+}
+Status FunctionRegistry::AddAlias(const std::string& target, const std::string& source) {
+  const Function* f = GetFunction(source);
+  if (!f) return Status::Make(AG_ERR_INVALID, "no function registered with name: " + source);  // arrow.ErrKey
+  for (auto& kv : fns_) if (kv.second.get() == f) { fns_[target] = kv.second; return Status::OK(); }
+  return Status::Invalid("alias source lives in a parent registry");
+}
+const Function* FunctionRegistry::GetFunction(const std::string& name) const {
+  auto it = fns_.find(name);
+  if (it != fns_.end()) return it->second.get();
+  return parent_ ? parent_->GetFunction(name) : nullptr;
+}
+std::vector<std::string> FunctionRegistry::GetFunctionNames() const {
+  std::vector<std::string> names = parent_ ? parent_->GetFunctionNames() : std::vector<std::string>();
+  for (auto& kv : fns_) names.push_back(kv.first);
+  std::sort(names.begin(), names.end());
+  names.erase(std::unique(names.begin(), names.end()), names.end());
+  return names;
+}
+std::unique_ptr<FunctionRegistry> NewChildRegistry(FunctionRegistry* parent) { return std::unique_ptr<FunctionRegistry>(new FunctionRegistry(parent)); }
+
+template <typename K>
+static Status DispatchFirstMatch(const std::string& fname, const std::vector<K>& kernels, const std::vector<Type>& types, const K** out) {
+  for (auto& k : kernels) {  // first match wins (functions.go:209-213)
+    if (k.any_input_type) { *out = &k; return Status::OK(); }
+    if (k.in_types.size() != types.size()) continue;
+    bool ok = true;
+    for (size_t i = 0; i < types.size(); ++i) ok = ok && (k.in_types[i] == types[i]);
+    if (ok) { *out = &k; return Status::OK(); }
+  }
+  std::string sig;
+  for (size_t i = 0; i < types.size(); ++i) sig += std::string(i ? ", " : "") + TypeName(types[i]);
+  return Status::NotImplemented("function '" + fname + "' has no kernel matching input types (" + sig + ")");
+}
+Status ScalarFunction::AddKernel(exec::ScalarKernel k) {
+  if (!k.any_input_type && (int)k.in_types.size() != Arity()) return Status::Invalid("kernel arity does not match function arity");
+  kernels_.push_back(std::move(k));
+  return Status::OK();
+}
+Status ScalarFunction::DispatchExact(const std::vector<Type>& types, const exec::ScalarKernel** out) const {
+  return DispatchFirstMatch(Name(), kernels_, types, out);
+}
+Status VectorFunction::AddKernel(exec::VectorKernel k) { kernels_.push_back(std::move(k)); return Status::OK(); }
+Status VectorFunction::DispatchExact(const std::vector<Type>& types, const exec::VectorKernel** out) const {
+  return DispatchFirstMatch(Name(), kernels_, types, out);
+}
+
+// ---------------------------------------------------------------- scalar executor ---------
+static Status CheckArgs(const Function& fn, const std::vector<Datum>& args) {
+  if ((int)args.size() != fn.Arity())
+    return Status::Invalid("function '" + fn.Name() + "' accepts " + std::to_string(fn.Arity()) + " arguments but " + std::to_string(args.size()) + " passed");
+  for (auto& a : args) if (a.kind == DatumKind::NONE) return Status::Invalid("tried executing function with non-value type");  // checkAllIsValue
+  return Status::OK();
+}
+
+namespace {
+struct ErrorWord {  // device int64 "first failing row", reset per call
+  std::shared_ptr<Buffer> buf;
+  Status Init() { RETURN_NOT_OK(Buffer::Allocate(8, &buf)); NATIVE(ag_error_word_reset_dev((int64_t*)buf->data(), nullptr)); return Status::OK(); }
+  Status Read(int64_t* v) { return buf->ToHost(v, 8); }
+};
+}  // namespace
+
+// scalarExecutor: executor.go:487-728 (Init :435-440, setupPrealloc :658-702, executeSpans :598-623,
+// executeSingleSpan :644-656, emitResult :704-728) + WrapResults :521-580.
+Status ScalarFunction::Execute(const ExecCtx& ectx, const FunctionOptions* opts, const std::vector<Datum>& args, Datum* out) const {
+  RETURN_NOT_OK(CheckArgs(*this, args));
+  std::vector<Type> in_types;
+  for (auto& a : args) in_types.push_back(a.type());
+  const exec::ScalarKernel* kernel = nullptr;
+  RETURN_NOT_OK(DispatchExact(in_types, &kernel));  // NB: implicit casts (DispatchBest + CastDatum, exec.go:101-121) are out of scope
+  const Type out_type = kernel->out_type(in_types);
+
+  // span iteration metadata
+  std::vector<std::vector<int64_t>> lens(args.size());
+  std::vector<bool> is_chunked(args.size(), false);
+  bool have_chunked = false, all_scalar = true;
+  for (size_t i = 0; i < args.size(); ++i) {
+    if (args[i].kind == DatumKind::ARRAY) { lens[i] = {args[i].array->length}; all_scalar = false; }
+    else if (args[i].kind == DatumKind::CHUNKED) {
+      is_chunked[i] = true; have_chunked = true; all_scalar = false;
+      for (auto& c : args[i].chunked->chunks) lens[i].push_back(c->length);
+    }
+  }
+  if (all_scalar) return Status::NotImplemented("scalar-only execution (PromoteExecSpanScalars) is not part of the accelerated path");
+  std::vector<SpanPiece> pieces;
+  RETURN_NOT_OK(IterateExecSpans(lens, is_chunked, ectx.ChunkSize, &pieces));
+  int64_t total = 0;
+  for (size_t i = 0; i < args.size(); ++i) if (args[i].kind != DatumKind::SCALAR) { total = args[i].Len(); break; }
+
+  // setupPrealloc (executor.go:658-702)
+  bool validity_prealloc = false, elide_validity = false;
+  if (out_type != Type::NA) {
+    if (kernel->null_handling == exec::NullHandling::COMPUTED_PREALLOC) validity_prealloc = true;
+    else if (kernel->null_handling == exec::NullHandling::INTERSECTION) {
+      elide_validity = true;
+      for (auto& a : args) if (GetNullGenDatum(a) != NullGen::ALL_VALID) { elide_validity = false; break; }
+      validity_prealloc = !elide_validity;
+    }
+  }
+  const bool data_prealloc = kernel->mem_alloc == exec::MemAlloc::PREALLOC;
+  const bool contiguous = ectx.PreallocContiguous && kernel->can_write_into_slices && data_prealloc &&
+                          (validity_prealloc || elide_validity || kernel->null_handling == exec::NullHandling::OUTPUT_NOT_NULL);
+
+  KernelCtx kctx;
+  kctx.kernel = kernel;
+  kctx.state = opts;
+  ErrorWord err_word;
+  if (kernel->can_fail) { RETURN_NOT_OK(err_word.Init()); kctx.error_word = (int64_t*)err_word.buf->data(); }
+
+  auto prepare_output = [&](int64_t length, ArraySpan* o) -> Status {  // prepareOutput, executor.go:441-470
+    *o = ArraySpan();
+    o->type = out_type; o->len = length; o->offset = 0; o->nulls = kUnknownNullCount;
+    if (validity_prealloc) {
+      std::shared_ptr<Buffer> b;
+      RETURN_NOT_OK(kctx.AllocateBitmap(length, &b));
+      o->buffers[0].buf = b->data(); o->buffers[0].len = b->size(); o->buffers[0].owner = b; o->buffers[0].self_alloc = true;
+    }
+    if (data_prealloc) {
+      std::shared_ptr<Buffer> b;
+      RETURN_NOT_OK(kctx.Allocate(DataBytes(out_type, length), &b));  // allocateDataBuffer, executor.go:155-163
+      o->buffers[1].buf = b->data(); o->buffers[1].len = b->size(); o->buffers[1].owner = b; o->buffers[1].self_alloc = true;
+    }
+    if (kernel->null_handling == exec::NullHandling::OUTPUT_NOT_NULL || elide_validity) o->nulls = 0;
+    return Status::OK();
+  };
+
+  auto build_span = [&](const SpanPiece& p, ExecSpan* span) {
+    span->len = p.len;
+    span->values.assign(args.size(), ExecValue());
+    for (size_t i = 0; i < args.size(); ++i) {
+      ExecValue& v = span->values[i];
+      if (args[i].kind == DatumKind::SCALAR) { v.scalar = args[i].scalar.get(); continue; }
+      const ArrayData& d = (args[i].kind == DatumKind::ARRAY) ? *args[i].array : *args[i].chunked->chunks[p.chunk_index[i]];
+      v.array.SetMembers(d);
+      v.array.SetSlice(d.offset + p.chunk_pos[i], p.len);
+    }
+  };
+
+  auto exec_single = [&](const ExecSpan& span, ArraySpan* o) -> Status {  // executeSingleSpan, executor.go:644-656
+    if (o->type != Type::NA && kernel->null_handling == exec::NullHandling::INTERSECTION && !elide_validity)
+      RETURN_NOT_OK(PropagateNulls(&kctx, span, o));
+    return kernel->exec(&kctx, span, o);
+  };
+
+  std::vector<std::shared_ptr<ArrayData>> results;
+  if (contiguous) {
+    ArraySpan output;
+    RETURN_NOT_OK(prepare_output(total, &output));
+    for (auto& p : pieces) {
+      if (p.len == 0) continue;
+      ExecSpan span;
+      build_span(p, &span);
+      ArraySpan slice = output;
+      slice.SetSlice(p.pos, p.len);       // out.SetSlice(resultOffset, input.Len), executor.go:609
+      slice.nulls = kUnknownNullCount;
+      kctx.row_base = p.pos;
+      RETURN_NOT_OK(exec_single(span, &slice));
+    }
+    output.nulls = (elide_validity || kernel->null_handling == exec::NullHandling::OUTPUT_NOT_NULL) ? 0 : kUnknownNullCount;
+    results.push_back(output.MakeData());
+  } else {
+    for (auto& p : pieces) {
+      if (p.len == 0 && pieces.size() > 1) continue;
+      ExecSpan span;
+      build_span(p, &span);
+      ArraySpan o;
+      RETURN_NOT_OK(prepare_output(p.len, &o));
+      kctx.row_base = p.pos;
+      RETURN_NOT_OK(exec_single(span, &o));
+      results.push_back(o.MakeData());
+    }
+  }
+  if (results.empty()) {  // zero-length input: one empty output
+    ArraySpan o;
+    RETURN_NOT_OK(prepare_output(0, &o));
+    o.nulls = 0;
+    results.push_back(o.MakeData());
+  }
+  if (kernel->can_fail) {
+    int64_t bad = 0;
+    RETURN_NOT_OK(err_word.Read(&bad));
+    if (bad != AG_NO_ERROR_POS) return Status::Invalid(kernel->fail_message);  // the output is released, exec.go:161-170
+  }
+  // emitResult :704-708 recounts nulls lazily; we leave them unknown (ToHost counts on demand)
+  if (have_chunked) {  // WrapResults: Chunked if any input was chunked (executor.go:521-580)
+    auto c = std::make_shared<ChunkedArray>();
+    c->type = out_type; c->chunks = results;
+    for (auto& r : results) c->length += r->length;
+    *out = Datum(c);
+  } else {
+    *out = Datum(results.empty() ? std::make_shared<ArrayData>() : results[0]);
+  }
+  return Status::OK();
+}
+
+// ---------------------------------------------------------------- vector executor ---------
+// vectorExecutor, executor.go:886-1154: chunk-wise kernels run once per aligned span and emit one
+// output array per span; non-chunkwise kernels (array_take) need whole arrays.
+Status VectorFunction::Execute(const ExecCtx& ectx, const FunctionOptions* opts, const std::vector<Datum>& args, Datum* out) const {
+  (void)ectx;
+  RETURN_NOT_OK(CheckArgs(*this, args));
+  std::vector<Type> in_types;
+  for (auto& a : args) in_types.push_back(a.type());
+  const exec::VectorKernel* kernel = nullptr;
+  RETURN_NOT_OK(DispatchExact(in_types, &kernel));
+  const Type out_type = kernel->out_type(in_types);
+  KernelCtx kctx;
+  kctx.kernel = kernel;
+  kctx.state = opts;
+  bool have_chunked = false;
+  std::vector<std::vector<int64_t>> lens(args.size());
+  std::vector<bool> is_chunked(args.size(), false);
+  for (size_t i = 0; i < args.size(); ++i) {
+    if (args[i].kind == DatumKind::SCALAR) return Status::NotImplemented("vector kernels take array-like arguments");
+    if (args[i].kind == DatumKind::ARRAY) lens[i] = {args[i].array->length};
+    else { is_chunked[i] = true; have_chunked = true; for (auto& c : args[i].chunked->chunks) lens[i].push_back(c->length); }
+  }
+  std::vector<std::shared_ptr<ArrayData>> results;
+  if (kernel->can_execute_chunkwise) {
+    // exec.go:152-155: "vector kernel arguments must all be the same length"
+    int64_t l0 = args[0].Len();
+    for (auto& a : args) if (a.Len() != l0) return Status::Invalid("vector kernel arguments must all be the same length");
+    std::vector<SpanPiece> pieces;
+    RETURN_NOT_OK(IterateExecSpans(lens, is_chunked, INT64_MAX, &pieces));
+    if (pieces.empty()) { SpanPiece p; p.pos = 0; p.len = 0; p.chunk_index.assign(args.size(), 0); p.chunk_pos.assign(args.size(), 0); pieces.push_back(p); }
+    for (auto& p : pieces) {
+      ExecSpan span;
+      span.len = p.len;
+      span.values.assign(args.size(), ExecValue());
+      for (size_t i = 0; i < args.size(); ++i) {
+        if (args[i].kind == DatumKind::CHUNKED && args[i].chunked->chunks.empty()) { span.values[i].array.type = in_types[i]; continue; }
+        const ArrayData& d = (args[i].kind == DatumKind::ARRAY) ? *args[i].array : *args[i].chunked->chunks[p.chunk_index[i]];
+        span.values[i].array.SetMembers(d);
+        span.values[i].array.SetSlice(d.offset + p.chunk_pos[i], p.len);
+      }
+      ArraySpan o;
+      o.type = out_type;
+      RETURN_NOT_OK(kernel->exec(&kctx, span, &o));
+      results.push_back(o.MakeData());
+    }
+  } else {
+    if (have_chunked) return Status::NotImplemented("non-chunkwise vector kernel on chunked input (resolved by the meta function)");
+    ExecSpan span;
+    span.values.assign(args.size(), ExecValue());
+    for (size_t i = 0; i < args.size(); ++i) span.values[i].array.SetMembers(*args[i].array);
+    span.len = args.empty() ? 0 : args[0].array->length;
+    ArraySpan o;
+    o.type = out_type;
+    RETURN_NOT_OK(kernel->exec(&kctx, span, &o));
+    results.push_back(o.MakeData());
+  }
+  if (have_chunked) {
+    auto c = std::make_shared<ChunkedArray>();
+    c->type = out_type; c->chunks = results;
+    for (auto& r : results) c->length += r->length;
+    *out = Datum(c);
+  } else {
+    *out = Datum(results[0]);
+  }
+  return Status::OK();
+}
+
+Status CallFunction(const ExecCtx& ctx, const std::string& name, const FunctionOptions* opts, const std::vector<Datum>& args, Datum* out) {
+  FunctionRegistry* reg = ctx.Registry ? ctx.Registry : GetFunctionRegistry();
+  const Function* fn = reg->GetFunction(name);
+  if (!fn) return Status::Make(AG_ERR_INVALID, "no function registered with name: " + name);  // arrow.ErrKey
+  return fn->Execute(ctx, opts, args, out);
+}
+
+// ======================================================================================
+// kernels (arrow/compute/internal/kernels) on device spans
+// ======================================================================================
+namespace {
+
+using exec::ExecResult;
+
+inline const uint8_t* ValuesPtr(const ArraySpan& a) {  // exec.GetSpanValues: Buf[1] advanced by Offset (exec/utils.go:38-44)
+  return a.buffers[1].buf + a.offset * (BitWidth(a.type) / 8);
+}
+inline uint8_t* ValuesPtr(ExecResult* a) { return a->buffers[1].buf + a->offset * (BitWidth(a->type) / 8); }
+
+int ShapeOf(const ExecSpan& b) { return b.values[0].IsArray() ? (b.values[1].IsArray() ? AG_SHAPE_AA : AG_SHAPE_AS) : AG_SHAPE_SA; }
+
+// ScalarBinary over the native loops (helpers.go:193-236 -> base_arithmetic_amd64.go:34-37)
+exec::ArrayKernelExec ArithBinaryExec(int8_t op) {
+  return [op](KernelCtx*, const ExecSpan& batch, ExecResult* out) -> Status {
+    const int shape = ShapeOf(batch);
+    const void* l = batch.values[0].IsArray() ? (const void*)ValuesPtr(batch.values[0].array) : (const void*)batch.values[0].scalar->value;
+    const void* r = batch.values[1].IsArray() ? (const void*)ValuesPtr(batch.values[1].array) : (const void*)batch.values[1].scalar->value;
+    NATIVE(ag_arith_binary_dev((int)out->type, op, shape, l, r, ValuesPtr(out), batch.len, nullptr));
+    return Status::OK();
+  };
+}
+
+// ScalarBinaryNotNull / checked integer kernels (helpers.go:284-380, base_arithmetic.go:249-294)
+exec::ArrayKernelExec ArithCheckedExec(int8_t op) {
+  return [op](KernelCtx* ctx, const ExecSpan& batch, ExecResult* out) -> Status {
+    const int shape = ShapeOf(batch);
+    const ExecValue &a = batch.values[0], &b = batch.values[1];
+    // "fast path if one side is entirely null" (helpers.go:287): nothing is written
+    if ((a.IsScalar() && !a.scalar->valid) || (b.IsScalar() && !b.scalar->valid)) return Status::OK();
+    const void* l = a.IsArray() ? (const void*)a.array.buffers[1].buf : (const void*)a.scalar->value;
+    const void* r = b.IsArray() ? (const void*)b.array.buffers[1].buf : (const void*)b.scalar->value;
+    const int w = BitWidth(out->type) / 8;
+    const uint8_t* lv = (a.IsArray() && a.array.MayHaveNulls()) ? a.array.buffers[0].buf : nullptr;
+    const uint8_t* rv = (b.IsArray() && b.array.MayHaveNulls()) ? b.array.buffers[0].buf : nullptr;
+    const int64_t loff = a.IsArray() ? a.array.offset : 0, roff = b.IsArray() ? b.array.offset : 0;
+    if (a.IsArray()) l = (const uint8_t*)l + loff * w;
+    if (b.IsArray()) r = (const uint8_t*)r + roff * w;
+    NATIVE(ag_arith_checked_dev((int)out->type, op, shape, l, lv, loff, r, rv, roff, ValuesPtr(out), batch.len, ctx->error_word, nullptr));
+    return Status::OK();
+  };
+}
+
+exec::ArrayKernelExec ArithUnaryExec(int8_t op) {
+  return [op](KernelCtx*, const ExecSpan& batch, ExecResult* out) -> Status {
+    NATIVE(ag_arith_unary_same_dev((int)out->type, op, ValuesPtr(batch.values[0].array), ValuesPtr(out), batch.len, nullptr));
+    return Status::OK();
+  };
+}
+
+// compareKernel (scalar_comparisons.go:199-218): output pointer at byte Offset/8, bit prefix Offset%8
+exec::ArrayKernelExec CompareExec(int cmp) {
+  return [cmp](KernelCtx*, const ExecSpan& batch, ExecResult* out) -> Status {
+    const int shape = ShapeOf(batch);
+    const ExecValue &a = batch.values[0], &b = batch.values[1];
+    const void* l = a.IsArray() ? (const void*)ValuesPtr(a.array) : (const void*)a.scalar->value;
+    const void* r = b.IsArray() ? (const void*)ValuesPtr(b.array) : (const void*)b.scalar->value;
+    NATIVE(ag_compare_dev((int)a.type(), cmp, shape, l, r, out->buffers[1].buf + out->offset / 8, batch.len, (int)(out->offset % 8), nullptr));
+    return Status::OK();
+  };
+}
+
+// and / or / xor / and_not (scalar_boolean.go:67-279) incl. the scalar-operand special cases
+exec::ArrayKernelExec BoolBinaryExec(int bitop) {
+  return [bitop](KernelCtx*, const ExecSpan& batch, ExecResult* out) -> Status {
+    const ExecValue &a = batch.values[0], &b = batch.values[1];
+    uint8_t* ob = out->buffers[1].buf;
+    if (a.IsArray() && b.IsArray()) {
+      NATIVE(ag_bitmap_op_dev(bitop, a.array.buffers[1].buf, a.array.offset, b.array.buffers[1].buf, b.array.offset, ob, out->offset, batch.len, nullptr));
+      return Status::OK();
+    }
+    // commutativeBinaryKernel / AndNot CallScalarLeft / CallScalarRight
+    const bool scalar_left = a.IsScalar();
+    const Scalar* s = scalar_left ? a.scalar : b.scalar;
+    const ArraySpan& arr = scalar_left ? b.array : a.array;
+    if (!s->valid) return Status::OK();
+    bool sv = s->value[0] != 0;
+    int op = bitop;
+    if (bitop == AG_BITOP_ANDNOT && !scalar_left) { op = AG_BITOP_AND; sv = !sv; }  // AndNot.CallScalarRight = And with inverted scalar
+    enum { COPY, INVERT, SET0, SET1 } act;
+    switch (op) {
+      case AG_BITOP_AND: act = sv ? COPY : SET0; break;
+      case AG_BITOP_OR: act = sv ? SET1 : COPY; break;
+      case AG_BITOP_XOR: act = sv ? INVERT : COPY; break;
+      default: /* ANDNOT, scalar left */ act = sv ? INVERT : SET0; break;
+    }
+    switch (act) {
+      case COPY: NATIVE(ag_bitmap_copy_dev(arr.buffers[1].buf, arr.offset, arr.len, ob, out->offset, nullptr)); break;
+      case INVERT: NATIVE(ag_bitmap_invert_dev(arr.buffers[1].buf, arr.offset, arr.len, ob, out->offset, nullptr)); break;
+      case SET0: NATIVE(ag_bitmap_set_dev(ob, out->offset, out->len, 0, nullptr)); break;
+      case SET1: NATIVE(ag_bitmap_set_dev(ob, out->offset, out->len, 1, nullptr)); break;
+    }
+    return Status::OK();
+  };
+}
+
+// Kleene and / or / and_not, array ⊕ array (scalar_boolean.go:29-65 computeKleene and callers)
+exec::ArrayKernelExec KleeneExec(int kop, int plain_bitop) {
+  return [kop, plain_bitop](KernelCtx*, const ExecSpan& batch, ExecResult* out) -> Status {
+    const ExecValue &a = batch.values[0], &b = batch.values[1];
+    if (!a.IsArray() || !b.IsArray()) return Status::NotImplemented("Kleene kernels with a scalar operand are not accelerated yet");
+    ArraySpan l = a.array, r = b.array;
+    int64_t ln = 0, rn = 0;
+    RETURN_NOT_OK(l.UpdateNullCount(&ln));
+    RETURN_NOT_OK(r.UpdateNullCount(&rn));
+    if (ln == 0 && rn == 0) {  // :94-98
+      NATIVE(ag_bitmap_set_dev(out->buffers[0].buf, out->offset, out->len, 1, nullptr));
+      out->nulls = 0;
+      NATIVE(ag_bitmap_op_dev(plain_bitop, l.buffers[1].buf, l.offset, r.buffers[1].buf, r.offset, out->buffers[1].buf, out->offset, batch.len, nullptr));
+      return Status::OK();
+    }
+    NATIVE(ag_kleene_dev(kop, ln ? l.buffers[0].buf : nullptr, l.buffers[1].buf, l.offset, rn ? r.buffers[0].buf : nullptr, r.buffers[1].buf, r.offset,
+                         out->buffers[0].buf, out->buffers[1].buf, out->offset, batch.len, nullptr));
+    out->nulls = kUnknownNullCount;
+    return Status::OK();
+  };
+}
+
+// NotExecKernel (scalar_boolean.go:336-347): invert data, share the validity buffer
+Status NotExec(KernelCtx*, const ExecSpan& batch, ExecResult* out) {
+  const ArraySpan& in = batch.values[0].array;
+  NATIVE(ag_bitmap_invert_dev(in.buffers[1].buf, in.offset, in.len, out->buffers[1].buf, out->offset, nullptr));
+  if (in.buffers[0].buf && in.nulls != 0) {
+    if (in.offset == out->offset) { out->buffers[0] = in.buffers[0]; out->buffers[0].self_alloc = false; }
+    else {
+      std::shared_ptr<Buffer> b;
+      RETURN_NOT_OK(Buffer::Allocate((out->offset + out->len + 7) / 8, &b));
+      NATIVE(ag_bitmap_copy_dev(in.buffers[0].buf, in.offset, in.len, b->data(), out->offset, nullptr));
+      out->buffers[0].buf = b->data(); out->buffers[0].len = b->size(); out->buffers[0].owner = b; out->buffers[0].self_alloc = true;
+    }
+  }
+  out->nulls = in.nulls;
+  return Status::OK();
+}
+
+// PrimitiveFilter (vector_selection.go:449-520)
+Status PrimitiveFilterExec(KernelCtx* ctx, const ExecSpan& batch, ExecResult* out) {
+  ArraySpan values = batch.values[0].array, filter = batch.values[1].array;
+  const FilterOptions* opts = static_cast<const FilterOptions*>(ctx->state);
+  const int sel = opts ? (int)opts->NullSelection : (int)DropNulls;
+  int64_t vn = 0, fn = 0;
+  RETURN_NOT_OK(values.UpdateNullCount(&vn));
+  RETURN_NOT_OK(filter.UpdateNullCount(&fn));
+  const uint8_t* mvalid = fn != 0 ? filter.buffers[0].buf : nullptr;
+  const uint8_t* vvalid = vn != 0 ? values.buffers[0].buf : nullptr;
+  // getFilterOutputSize (:57-81)
+  std::shared_ptr<Buffer> scal;
+  RETURN_NOT_OK(Buffer::Allocate(16, &scal));
+  NATIVE(ag_filter_output_size_dev(filter.buffers[1].buf, mvalid, filter.offset, filter.len, sel, (int64_t*)scal->data(), nullptr));
+  int64_t out_len = 0;
+  RETURN_NOT_OK(scal->ToHost(&out_len, 8));
+  out->nulls = (vn == 0 && (sel == DropNulls || fn == 0)) ? 0 : kUnknownNullCount;  // :464-468
+  const bool allocate_validity = vn != 0 || fn != 0;                                  // :473
+  const int bw = BitWidth(values.type);
+  if (bw == 1) return Status::NotImplemented("filter on boolean values is not accelerated (see DESIGN.md, reference quirks)");
+  // preallocateData (:83-93)
+  out->type = values.type; out->len = out_len; out->offset = 0;
+  std::shared_ptr<Buffer> data, valid;
+  RETURN_NOT_OK(ctx->Allocate(out_len * (bw / 8), &data));
+  out->buffers[1].buf = data->data(); out->buffers[1].len = data->size(); out->buffers[1].owner = data; out->buffers[1].self_alloc = true;
+  if (allocate_validity) {
+    RETURN_NOT_OK(ctx->Allocate(((out_len + 31) / 32) * 4, &valid));
+    out->buffers[0].buf = valid->data(); out->buffers[0].len = valid->size(); out->buffers[0].owner = valid; out->buffers[0].self_alloc = true;
+  }
+  if (values.len == 0) return Status::OK();
+  NATIVE(ag_filter_primitive_dev(bw, values.buffers[1].buf, vvalid, values.offset, filter.buffers[1].buf, mvalid, filter.offset, values.len, sel,
+                                 data->data(), allocate_validity ? valid->data() : nullptr, out_len, (int64_t*)scal->data() + 1, nullptr));
+  return Status::OK();
+}
+
+// PrimitiveTake (vector_selection.go:1162-1192)
+Status PrimitiveTakeExec(KernelCtx* ctx, const ExecSpan& batch, ExecResult* out) {
+  ArraySpan values = batch.values[0].array, indices = batch.values[1].array;
+  const TakeOptions* opts = static_cast<const TakeOptions*>(ctx->state);
+  const bool bounds = opts ? opts->BoundsCheck : true;
+  if (!IsInteger(indices.type)) return Status::Invalid("invalid index type for bounds checking");  // helpers.go:978
+  int64_t vn = 0, in_ = 0;
+  RETURN_NOT_OK(values.UpdateNullCount(&vn));
+  RETURN_NOT_OK(indices.UpdateNullCount(&in_));
+  const int bw = BitWidth(values.type);
+  if (bw == 1) return Status::NotImplemented("take on boolean values is not accelerated yet");
+  const bool allocate_validity = vn != 0 || in_ != 0;  // :1175
+  out->type = values.type; out->len = indices.len; out->offset = 0;
+  std::shared_ptr<Buffer> data, valid, word;
+  RETURN_NOT_OK(ctx->Allocate(indices.len * (bw / 8), &data));
+  out->buffers[1].buf = data->data(); out->buffers[1].len = data->size(); out->buffers[1].owner = data; out->buffers[1].self_alloc = true;
+  if (allocate_validity) {
+    RETURN_NOT_OK(ctx->Allocate(((indices.len + 31) / 32) * 4, &valid));
+    out->buffers[0].buf = valid->data(); out->buffers[0].len = valid->size(); out->buffers[0].owner = valid; out->buffers[0].self_alloc = true;
+  }
+  out->nulls = allocate_validity ? kUnknownNullCount : 0;
+  if (indices.len == 0) return Status::OK();
+  RETURN_NOT_OK(Buffer::Allocate(8, &word));
+  NATIVE(ag_error_word_reset_dev((int64_t*)word->data(), nullptr));
+  const int iw = BitWidth(indices.type);
+  NATIVE(ag_take_primitive_dev(bw, values.buffers[1].buf, vn ? values.buffers[0].buf : nullptr, values.offset, values.len, iw, IsSignedInteger(indices.type),
+                               indices.buffers[1].buf + indices.offset * (iw / 8), in_ ? indices.buffers[0].buf : nullptr, indices.offset, indices.len,
+                               bounds ? 1 : 0, data->data(), allocate_validity ? valid->data() : nullptr, (int64_t*)word->data(), nullptr));
+  if (bounds) {
+    int64_t bad = 0;
+    RETURN_NOT_OK(word->ToHost(&bad, 8));
+    if (bad != AG_NO_ERROR_POS) {
+      // "%d out of bounds" with the offending index value (helpers.go:951)
+      uint8_t raw[8] = {0};
+      RETURN_NOT_OK(indices.buffers[1].owner->ToHost(raw, iw / 8, (indices.offset + bad) * (iw / 8)));
+      long long v = 0; unsigned long long uv = 0;
+      memcpy(&uv, raw, 8);
+      if (IsSignedInteger(indices.type)) {
+        switch (iw) { case 8: v = (int8_t)raw[0]; break; case 16: { int16_t t; memcpy(&t, raw, 2); v = t; break; }
+                      case 32: { int32_t t; memcpy(&t, raw, 4); v = t; break; } default: memcpy(&v, raw, 8); }
+        return Status::IndexError(std::to_string(v) + " out of bounds");
+      }
+      return Status::IndexError(std::to_string(uv) + " out of bounds");
+    }
+  }
+  return Status::OK();
+}
+
+Type FirstType(const std::vector<Type>& t) { return t[0]; }
+Type BoolType(const std::vector<Type>&) { return Type::BOOL; }
+
+const Type kNumericTypes[] = {Type::UINT8, Type::INT8, Type::UINT16, Type::INT16, Type::UINT32, Type::INT32, Type::UINT64, Type::INT64, Type::FLOAT32, Type::FLOAT64};
+
+std::shared_ptr<ScalarFunction> MakeArithBinary(const std::string& name, int8_t unchecked_op, int8_t checked_op, bool checked, const char* fail_msg) {
+  // GetArithmeticBinaryKernels (scalar_arithmetic.go:86-95): one [ty,ty]->ty kernel per numeric type
+  auto fn = std::make_shared<ScalarFunction>(name, 2);
+  for (Type t : kNumericTypes) {
+    exec::ScalarKernel k;
+    k.in_types = {t, t};
+    k.out_type = FirstType;
+    if (checked && IsInteger(t)) {  // integral checked funcs use the NotNull versions (base_arithmetic_amd64.go:103-106)
+      k.exec = ArithCheckedExec(checked_op);
+      k.can_fail = true;
+      k.fail_message = fail_msg;
+    } else {
+      k.exec = ArithBinaryExec(checked ? checked_op : unchecked_op);
+    }
+    fn->AddKernel(std::move(k));
+  }
+  return fn;
+}
+
+std::shared_ptr<ScalarFunction> MakeArithUnary(const std::string& name, int8_t op) {
+  auto fn = std::make_shared<ScalarFunction>(name, 1);
+  for (Type t : kNumericTypes) {
+    exec::ScalarKernel k;
+    k.in_types = {t};
+    k.out_type = FirstType;
+    k.exec = ArithUnaryExec(op);
+    fn->AddKernel(std::move(k));
+  }
+  return fn;
+}
+
+std::shared_ptr<ScalarFunction> MakeCompare(const std::string& name, int cmp) {  // CompareKernels, scalar_comparisons.go:654-716
+  auto fn = std::make_shared<ScalarFunction>(name, 2);
+  for (Type t : kNumericTypes) {
+    exec::ScalarKernel k;
+    k.in_types = {t, t};
+    k.out_type = BoolType;
+    k.exec = CompareExec(cmp);
+    fn->AddKernel(std::move(k));
+  }
+  return fn;
+}
+
+std::shared_ptr<ScalarFunction> MakeBool(const std::string& name, exec::ArrayKernelExec ex, exec::NullHandling nh) {  // scalar_bool.go:123-140
+  auto fn = std::make_shared<ScalarFunction>(name, 2);
+  exec::ScalarKernel k;
+  k.in_types = {Type::BOOL, Type::BOOL};
+  k.out_type = BoolType;
+  k.exec = std::move(ex);
+  k.null_handling = nh;
+  fn->AddKernel(std::move(k));
+  return fn;
+}
+
+Status ConcatenateChunks(const ChunkedArray& c, std::shared_ptr<ArrayData>* out);
+
+}  // namespace
+
+// GetFunctionRegistry (registry.go:47-62): the functions of the hot path under their reference names
+FunctionRegistry* GetFunctionRegistry() {
+  static FunctionRegistry* reg = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    reg = new FunctionRegistry();
+    // arithmetic.go:635-636,679-682,782-785: add / sub / multiply (+ "subtract" alias) and _unchecked
+    reg->AddFunction(MakeArithBinary("add", AG_OP_ADD, AG_OP_ADD_CHECKED, true, "overflow"), false);
+    reg->AddFunction(MakeArithBinary("add_unchecked", AG_OP_ADD, AG_OP_ADD_CHECKED, false, ""), false);
+    reg->AddFunction(MakeArithBinary("sub", AG_OP_SUB, AG_OP_SUB_CHECKED, true, "overflow"), false);
+    reg->AddFunction(MakeArithBinary("sub_unchecked", AG_OP_SUB, AG_OP_SUB_CHECKED, false, ""), false);
+    reg->AddAlias("subtract", "sub");
+    reg->AddAlias("subtract_unchecked", "sub_unchecked");
+    reg->AddFunction(MakeArithBinary("multiply", AG_OP_MUL, AG_OP_MUL_CHECKED, true, "overflow"), false);
+    reg->AddFunction(MakeArithBinary("multiply_unchecked", AG_OP_MUL, AG_OP_MUL_CHECKED, false, ""), false);
+    reg->AddFunction(MakeArithUnary("abs_unchecked", AG_OP_ABS), false);
+    reg->AddFunction(MakeArithUnary("negate_unchecked", AG_OP_NEGATE), false);
+    reg->AddFunction(MakeArithUnary("sign", AG_OP_SIGN), false);
+    // scalar_compare.go:102-153
+    reg->AddFunction(MakeCompare("equal", AG_CMP_EQ), false);
+    reg->AddFunction(MakeCompare("not_equal", AG_CMP_NE), false);
+    reg->AddFunction(MakeCompare("greater", AG_CMP_GT), false);
+    reg->AddFunction(MakeCompare("greater_equal", AG_CMP_GE), false);
+    reg->AddFunction(MakeCompare("less", AG_CMP_LT), false);
+    reg->AddFunction(MakeCompare("less_equal", AG_CMP_LE), false);
+    // scalar_bool.go:123-140
+    reg->AddFunction(MakeBool("and", BoolBinaryExec(AG_BITOP_AND), exec::NullHandling::INTERSECTION), false);
+    reg->AddFunction(MakeBool("or", BoolBinaryExec(AG_BITOP_OR), exec::NullHandling::INTERSECTION), false);
+    reg->AddFunction(MakeBool("xor", BoolBinaryExec(AG_BITOP_XOR), exec::NullHandling::INTERSECTION), false);
+    reg->AddFunction(MakeBool("and_not", BoolBinaryExec(AG_BITOP_ANDNOT), exec::NullHandling::INTERSECTION), false);
+    reg->AddFunction(MakeBool("and_kleene", KleeneExec(AG_KLEENE_AND, AG_BITOP_AND), exec::NullHandling::COMPUTED_PREALLOC), false);
+    reg->AddFunction(MakeBool("or_kleene", KleeneExec(AG_KLEENE_OR, AG_BITOP_OR), exec::NullHandling::COMPUTED_PREALLOC), false);
+    reg->AddFunction(MakeBool("and_not_kleene", KleeneExec(AG_KLEENE_ANDNOT, AG_BITOP_ANDNOT), exec::NullHandling::COMPUTED_PREALLOC), false);
+    {
+      auto fn = std::make_shared<ScalarFunction>("not", 1);
+      exec::ScalarKernel k;
+      k.in_types = {Type::BOOL};
+      k.out_type = BoolType;
+      k.exec = NotExec;
+      k.null_handling = exec::NullHandling::COMPUTED_NO_PREALLOC;
+      k.can_write_into_slices = false;
+      fn->AddKernel(std::move(k));
+      reg->AddFunction(fn, false);
+    }
+    // selection.go:593-650: array_filter / array_take vector functions + filter / take meta functions
+    {
+      auto fn = std::make_shared<VectorFunction>("array_filter", 2);
+      exec::VectorKernel k;
+      k.any_input_type = true;
+      k.out_type = FirstType;
+      k.exec = PrimitiveFilterExec;
+      k.null_handling = exec::NullHandling::COMPUTED_NO_PREALLOC;
+      k.mem_alloc = exec::MemAlloc::NO_PREALLOC;
+      k.can_execute_chunkwise = true;
+      fn->AddKernel(std::move(k));
+      reg->AddFunction(fn, false);
+    }
+    {
+      auto fn = std::make_shared<VectorFunction>("array_take", 2);
+      exec::VectorKernel k;
+      k.any_input_type = true;
+      k.out_type = FirstType;
+      k.exec = PrimitiveTakeExec;
+      k.null_handling = exec::NullHandling::COMPUTED_NO_PREALLOC;
+      k.mem_alloc = exec::MemAlloc::NO_PREALLOC;
+      k.can_execute_chunkwise = false;  // selection.go:639
+      fn->AddKernel(std::move(k));
+      reg->AddFunction(fn, false);
+    }
+    reg->AddFunction(std::make_shared<MetaFunction>("filter", 2, [](const ExecCtx& ctx, const FunctionOptions* opts, const std::vector<Datum>& args, Datum* out) -> Status {
+      // filterMetaFunc, selection.go:41-85
+      if (args.size() != 2) return Status::Invalid("filter takes 2 arguments");
+      if (args[1].kind != DatumKind::ARRAY && args[1].kind != DatumKind::CHUNKED) return Status::NotImplemented("filter should be array-like");
+      if (args[1].type() != Type::BOOL) return Status::NotImplemented("filter argument must be boolean type");
+      return CallFunction(ctx, "array_filter", opts, args, out);
+    }), false);
+    reg->AddFunction(std::make_shared<MetaFunction>("take", 2, [](const ExecCtx& ctx, const FunctionOptions* opts, const std::vector<Datum>& args, Datum* out) -> Status {
+      // takeMetaFunc, selection.go:93-114 -> takeArrayImpl :206-244 / takeChunkedImpl :246-300
+      if (args.size() != 2) return Status::Invalid("take takes 2 arguments");
+      if (args[1].kind != DatumKind::ARRAY && args[1].kind != DatumKind::CHUNKED) return Status::NotImplemented("unsupported types for take operation");
+      Datum values = args[0];
+      const bool values_chunked = values.kind == DatumKind::CHUNKED;
+      if (values_chunked) {  // ChunkedPrimitiveTake resolves chunks per index; on the device we gather from one table
+        std::shared_ptr<ArrayData> cat;
+        RETURN_NOT_OK(ConcatenateChunks(*values.chunked, &cat));
+        values = Datum(cat);
+      } else if (values.kind != DatumKind::ARRAY) {
+        return Status::NotImplemented("unsupported types for take operation");
+      }
+      if (args[1].kind == DatumKind::ARRAY) {
+        Datum r;
+        RETURN_NOT_OK(CallFunction(ctx, "array_take", opts, {values, args[1]}, &r));
+        if (!values_chunked) { *out = r; return Status::OK(); }
+        auto c = std::make_shared<ChunkedArray>();
+        c->type = r.array->type; c->chunks = {r.array}; c->length = r.array->length;
+        *out = Datum(c);
+        return Status::OK();
+      }
+      auto c = std::make_shared<ChunkedArray>();
+      c->type = values.type();
+      for (auto& chunk : args[1].chunked->chunks) {  // one array_take per index chunk (selection.go:221-234)
+        Datum r;
+        RETURN_NOT_OK(CallFunction(ctx, "array_take", opts, {values, Datum(chunk)}, &r));
+        c->chunks.push_back(r.array);
+        c->length += r.array->length;
+      }
+      *out = Datum(c);
+      return Status::OK();
+    }), false);
+  });
+  return reg;
+}
+
+namespace {
+Status ConcatenateChunks(const ChunkedArray& c, std::shared_ptr<ArrayData>* out) {  // array.Concatenate on device (D2D)
+  auto d = std::make_shared<ArrayData>();
+  d->type = c.type; d->length = c.length; d->offset = 0;
+  const int w = BitWidth(c.type) / 8;
+  if (w == 0) return Status::NotImplemented("concatenate of boolean chunks");
+  RETURN_NOT_OK(Buffer::Allocate(c.length * w, &d->buffers[1]));
+  bool any_nulls = false;
+  for (auto& ch : c.chunks) any_nulls = any_nulls || (ch->buffers[0] && ch->null_count != 0);
+  if (any_nulls) RETURN_NOT_OK(Buffer::Allocate((c.length + 7) / 8, &d->buffers[0]));
+  int64_t pos = 0;
+  for (auto& ch : c.chunks) {
+    NATIVE(ag_copy_dev(d->buffers[1]->data() + pos * w, ch->buffers[1]->data() + ch->offset * w, (size_t)(ch->length * w), nullptr));
+    if (any_nulls) {
+      if (ch->buffers[0] && ch->null_count != 0) NATIVE(ag_bitmap_copy_dev(ch->buffers[0]->data(), ch->offset, ch->length, d->buffers[0]->data(), pos, nullptr));
+      else NATIVE(ag_bitmap_set_dev(d->buffers[0]->data(), pos, ch->length, 1, nullptr));
+    }
+    pos += ch->length;
+  }
+  d->null_count = any_nulls ? kUnknownNullCount : 0;
+  *out = d;
+  return Status::OK();
+}
+}  // namespace
+
+// arithmetic.go:1090-1142
+static Status ArithImpl(const ExecCtx& ctx, const ArithmeticOptions& opts, const char* fn, const Datum& l, const Datum& r, Datum* out) {
+  std::string name = fn;
+  if (opts.NoCheckOverflow) name += "_unchecked";
+  return CallFunction(ctx, name, nullptr, {l, r}, out);
+}
+Status Add(const ExecCtx& ctx, const ArithmeticOptions& o, const Datum& l, const Datum& r, Datum* out) { return ArithImpl(ctx, o, "add", l, r, out); }
+Status Subtract(const ExecCtx& ctx, const ArithmeticOptions& o, const Datum& l, const Datum& r, Datum* out) { return ArithImpl(ctx, o, "sub", l, r, out); }
+Status Multiply(const ExecCtx& ctx, const ArithmeticOptions& o, const Datum& l, const Datum& r, Datum* out) { return ArithImpl(ctx, o, "multiply", l, r, out); }
+Status Filter(const ExecCtx& ctx, const Datum& values, const Datum& filter, const FilterOptions& opts, Datum* out) {
+  return CallFunction(ctx, "filter", &opts, {values, filter}, out);
+}
+Status Take(const ExecCtx& ctx, const TakeOptions& opts, const Datum& values, const Datum& indices, Datum* out) {
+  return CallFunction(ctx, "take", &opts, {values, indices}, out);
+}
+
+}  // namespace compute
+
+// ======================================================================================
+// math
+// ======================================================================================
+namespace math {
+template <typename T, typename F>
+static Status SumImpl(const ArrayData& a, Type want, T* out, F&& fn) {
+  if (a.type != want) return Status::TypeError(std::string("Sum: expected ") + TypeName(want) + " got " + TypeName(a.type));
+  *out = T(0);
+  if (a.length == 0) return Status::OK();  // float64.go:35-37
+  std::shared_ptr<Buffer> res;
+  RETURN_NOT_OK(Buffer::Allocate(8, &res));
+  NATIVE(fn((const T*)(a.buffers[1]->data()) + a.offset, (size_t)a.length, (T*)res->data(), nullptr));
+  return res->ToHost(out, 8);
+}
+Status SumFloat64(const ArrayData& a, double* out) { return SumImpl<double>(a, Type::FLOAT64, out, ag_sum_f64_dev); }
+Status SumInt64(const ArrayData& a, int64_t* out) { return SumImpl<int64_t>(a, Type::INT64, out, ag_sum_i64_dev); }
+Status SumUint64(const ArrayData& a, uint64_t* out) { return SumImpl<uint64_t>(a, Type::UINT64, out, ag_sum_u64_dev); }
+Status SumFloat64ReferenceOrder(const ArrayData& a, double* out) { return SumImpl<double>(a, Type::FLOAT64, out, ag_sum_f64_reforder_dev); }
+}  // namespace math
+
+}  // namespace arrowgpu

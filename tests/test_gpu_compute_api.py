@@ -1,0 +1,249 @@
+"""The host-side mirror of the reference's compute API (CallFunction / Add / Filter / Take /
+math.Sum) running on the GPU.  These read like the reference's own Go tests and use its literal
+cases (tests/golden/*.json restated from arrow/compute/{arithmetic,vector_selection}_test.go and
+arrow/math/float64_test.go)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from arrow_go_b200 import compute as pc
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+NUMERIC = [pc.UINT8, pc.INT8, pc.UINT16, pc.INT16, pc.UINT32, pc.INT32, pc.UINT64, pc.INT64, pc.FLOAT32, pc.FLOAT64]
+INTS = NUMERIC[:8]
+
+
+def load(name):
+    with open(os.path.join(GOLDEN, name)) as f:
+        return json.load(f)
+
+
+def datum(x, t):
+    return pc.Array.from_pylist(x, t) if isinstance(x, list) else pc.Scalar(x, t)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _init(ag):
+    pc.lib()
+
+
+# ---------------------------------------------------------------- arithmetic -------------
+@pytest.mark.parametrize("t", NUMERIC)
+@pytest.mark.parametrize("no_check", [False, True])
+def test_binary_arithmetic_suite(t, no_check):
+    """BinaryArithmeticSuite[T].TestAdd/TestSub/TestMultiply (arithmetic_test.go:325-425) with both
+    settings of ArithmeticOptions.NoCheckOverflow."""
+    fns = {"add": pc.Add, "subtract": pc.Subtract, "multiply": pc.Multiply}
+    for case in load("arithmetic.json")["cases"]:
+        out = fns[case["op"]](datum(case["left"], t), datum(case["right"], t), no_check_overflow=no_check)
+        assert out.type == t
+        assert out.to_pylist() == case["expected"], (case, no_check)
+
+
+@pytest.mark.parametrize("t", INTS)
+def test_overflow_errors(t):
+    # arithmetic_test.go:352-355, 388-390: checked [max]+[max] and [min]-[max] -> ErrInvalid "overflow"
+    info = np.iinfo(pc.NP_OF[t])
+    mx, mn = pc.Array.from_pylist([int(info.max)], t), pc.Array.from_pylist([int(info.min)], t)
+    with pytest.raises(pc.ArrowError) as e:
+        pc.Add(mx, mx)
+    assert e.value.sentinel == "ErrInvalid" and "overflow" in e.value.msg
+    with pytest.raises(pc.ArrowError) as e:
+        pc.Subtract(mn, mx)
+    assert e.value.sentinel == "ErrInvalid" and "overflow" in e.value.msg
+    # unchecked wraps
+    w = pc.Add(mx, mx, no_check_overflow=True).to_pylist()[0]
+    assert w == (2 * int(info.max) - int(info.min)) % (int(info.max) - int(info.min) + 1) + int(info.min)
+    # a null slot hides the overflow (ScalarBinaryNotNull visits valid slots only)
+    a = pc.Array.from_pylist([None, 1], t)
+    b = pc.Array.from_pylist([int(info.max), int(info.max) - 1], t)
+    assert pc.Add(a, b).to_pylist() == [None, int(info.max)]
+
+
+def test_add_chunked_and_sliced():
+    """Chunked x chunked with misaligned chunk boundaries exercises iterateExecSpans +
+    contiguous preallocation + per-span null propagation at non-zero output offsets
+    (executor.go:598-623, 237-349)."""
+    rng = np.random.default_rng(1)
+    n = 10_000
+    a, b = rng.standard_normal(n), rng.standard_normal(n)
+    av, bv = rng.random(n) > 0.1, rng.random(n) > 0.2
+    cuts_a, cuts_b = [0, 1000, 1001, 4099, 7777, n], [0, 37, 5000, 5003, n]
+    ca = pc.Chunked([pc.Array.from_numpy(a[s:e], av[s:e]) for s, e in zip(cuts_a, cuts_a[1:])], pc.FLOAT64)
+    cb = pc.Chunked([pc.Array.from_numpy(b[s:e], bv[s:e]) for s, e in zip(cuts_b, cuts_b[1:])], pc.FLOAT64)
+    out = pc.Add(ca, cb)
+    assert out.kind == pc.KIND_CHUNKED and len(out) == n
+    vals, valid, nulls = out.to_numpy()
+    assert np.array_equal(valid, av & bv) and nulls == int((~(av & bv)).sum())
+    assert np.array_equal(vals[valid], (a + b)[valid])
+    # sliced arrays: offsets that are not multiples of 8
+    full_a = pc.Array.from_numpy(a, av)
+    full_b = pc.Array.from_numpy(b, bv)
+    out = pc.Subtract(full_a.slice(3, 5000), full_b.slice(13, 5000))
+    vals, valid, _ = out.to_numpy()
+    ev = av[3:5003] & bv[13:5013]
+    assert np.array_equal(valid, ev)
+    assert np.array_equal(vals[ev], (a[3:5003] - b[13:5013])[ev])
+    # int32 checked add over chunks, with nulls
+    ia, ib = rng.integers(-1000, 1000, n).astype(np.int32), rng.integers(-1000, 1000, n).astype(np.int32)
+    cia = pc.Chunked([pc.Array.from_numpy(ia[s:e], av[s:e]) for s, e in zip(cuts_a, cuts_a[1:])], pc.INT32)
+    out = pc.Add(cia, pc.Array.from_numpy(ib, bv))
+    vals, valid, _ = out.to_numpy()
+    assert np.array_equal(valid, av & bv)
+    assert np.array_equal(vals[valid], (ia + ib)[valid])
+    assert (vals[~valid] == 0).all()  # null slots of the NotNull kernels are zero
+
+
+def test_length_mismatch_is_invalid():
+    with pytest.raises(pc.ArrowError) as e:
+        pc.Add(pc.Array.from_pylist([1, 2, 3], pc.INT32), pc.Array.from_pylist([1, 2], pc.INT32))
+    assert e.value.sentinel == "ErrInvalid"
+
+
+# ---------------------------------------------------------------- comparisons ------------
+@pytest.mark.parametrize("t", NUMERIC)
+def test_numeric_compare_suite(t):
+    """NumericCompareSuite (scalar_compare_test.go:299-483): array ⊕ scalar, scalar ⊕ array,
+    null scalar, array ⊕ array."""
+    arr = [0, 0, 1, 1, 2, 2, None]
+    a = pc.Array.from_pylist(arr, t)
+    one = pc.Scalar(1, t)
+    ops = {"equal": lambda x, y: x == y, "not_equal": lambda x, y: x != y, "greater": lambda x, y: x > y,
+           "greater_equal": lambda x, y: x >= y, "less": lambda x, y: x < y, "less_equal": lambda x, y: x <= y}
+    for name, f in ops.items():
+        assert pc.CallFunction(name, [a, one]).to_pylist() == [None if x is None else f(x, 1) for x in arr], name
+        assert pc.CallFunction(name, [one, a]).to_pylist() == [None if x is None else f(1, x) for x in arr], name
+        assert pc.CallFunction(name, [a, pc.Scalar(None, t)]).to_pylist() == [None] * len(arr)
+        other = [1, 0, 2, None, 2, 5, 5]
+        b = pc.Array.from_pylist(other, t)
+        assert pc.CallFunction(name, [a, b]).to_pylist() == [None if (x is None or y is None) else f(x, y) for x, y in zip(arr, other)]
+        assert pc.CallFunction(name, [a, one]).type == pc.BOOL
+    empty = pc.Array.from_pylist([], t)
+    assert pc.CallFunction("equal", [empty, one]).to_pylist() == []
+
+
+def test_compare_sliced_output_offsets():
+    # chunked input => contiguous boolean output written at bit offsets that are not byte aligned
+    rng = np.random.default_rng(2)
+    n = 5001
+    v = rng.integers(0, 100, n).astype(np.int64)
+    cuts = [0, 3, 1000, 1003, 2048, n]
+    c = pc.Chunked([pc.Array.from_numpy(v[s:e]) for s, e in zip(cuts, cuts[1:])], pc.INT64)
+    out = pc.CallFunction("greater", [c, pc.Scalar(89, pc.INT64)])
+    vals, valid, _ = out.to_numpy()
+    assert valid.all() and np.array_equal(vals, v > 89)
+
+
+# ---------------------------------------------------------------- boolean ----------------
+def test_boolean_kernels():
+    """scalar_bool_test.go TestBooleanKernels truth tables (null-intersecting and Kleene)."""
+    T, F, U = True, False, None
+    left = [T, T, T, F, F, F, U, U, U]
+    right = [T, F, U, T, F, U, T, F, U]
+    l, r = pc.Array.from_pylist(left, pc.BOOL), pc.Array.from_pylist(right, pc.BOOL)
+    assert pc.CallFunction("and", [l, r]).to_pylist() == [T, F, U, F, F, U, U, U, U]
+    assert pc.CallFunction("or", [l, r]).to_pylist() == [T, T, U, T, F, U, U, U, U]
+    assert pc.CallFunction("xor", [l, r]).to_pylist() == [F, T, U, T, F, U, U, U, U]
+    assert pc.CallFunction("and_not", [l, r]).to_pylist() == [F, T, U, F, F, U, U, U, U]
+    assert pc.CallFunction("and_kleene", [l, r]).to_pylist() == [T, F, U, F, F, F, U, F, U]
+    assert pc.CallFunction("or_kleene", [l, r]).to_pylist() == [T, T, T, T, F, U, T, U, U]
+    assert pc.CallFunction("and_not_kleene", [l, r]).to_pylist() == [F, T, U, F, F, F, F, U, U]
+    assert pc.CallFunction("not", [l]).to_pylist() == [F, F, F, T, T, T, U, U, U]
+    # array ⊕ scalar equivalence helper (scalar_bool_test.go:40-58)
+    for name in ("and", "or", "xor", "and_not"):
+        for sv in (T, F):
+            want = pc.CallFunction(name, [l, pc.Array.from_pylist([sv] * 9, pc.BOOL)]).to_pylist()
+            assert pc.CallFunction(name, [l, pc.Scalar(sv, pc.BOOL)]).to_pylist() == want, (name, sv)
+            want = pc.CallFunction(name, [pc.Array.from_pylist([sv] * 9, pc.BOOL), r]).to_pylist()
+            assert pc.CallFunction(name, [pc.Scalar(sv, pc.BOOL), r]).to_pylist() == want, (name, sv)
+
+
+# ---------------------------------------------------------------- filter / take ----------
+@pytest.mark.parametrize("t", [pc.INT8, pc.UINT16, pc.INT32, pc.INT64, pc.FLOAT32, pc.FLOAT64])
+def test_filter_numeric(t):
+    for case in load("filter_numeric.json")["cases"]:
+        for sel, key in ((pc.EMIT_NULLS, "emit_null"), (pc.DROP_NULLS, "drop")):
+            v, m = pc.Array.from_pylist(case["values"], t), pc.Array.from_pylist(case["filter"], pc.BOOL)
+            assert pc.Filter(v, m, sel).to_pylist() == case[key], (case, key)
+            # sliced re-run: 3 filler values / 2 filler filter slots either side (vector_selection_test.go:114-145)
+            vs = pc.Array.from_pylist([None] * 3 + case["values"] + [None] * 3, t).slice(3, len(case["values"]))
+            ms = pc.Array.from_pylist([True, False] + case["filter"] + [True, False], pc.BOOL).slice(2, len(case["filter"]))
+            assert pc.Filter(vs, ms, sel).to_pylist() == case[key], ("sliced", case, key)
+    # length mismatch -> ErrInvalid (:480-483)
+    with pytest.raises(pc.ArrowError) as e:
+        pc.Filter(pc.Array.from_pylist([7, 8, 9], t), pc.Array.from_pylist([], pc.BOOL))
+    assert e.value.sentinel == "ErrInvalid"
+
+
+def test_filter_random_vs_compare():
+    """vector_selection_test.go:554-613: filter(values, values <op> scalar) against a naive loop."""
+    rng = np.random.default_rng(0x0FF1CE)
+    for n in (8, 64, 100, 512, 10_000):
+        v = rng.integers(0, 100, n).astype(np.int64)
+        valid = rng.random(n) > 0.1
+        arr = pc.Array.from_numpy(v, valid)
+        for name, f in (("equal", v == 50), ("not_equal", v != 50), ("greater", v > 50), ("less_equal", v <= 50)):
+            mask = pc.CallFunction(name, [arr, pc.Scalar(50, pc.INT64)])
+            got = pc.Filter(arr, mask, pc.DROP_NULLS).to_pylist()
+            assert got == [int(x) for x, ok, keep in zip(v, valid, f) if ok and keep]
+            got = pc.Filter(arr, mask, pc.EMIT_NULLS).to_pylist()
+            assert got == [(int(x) if ok else None) for x, ok, keep in zip(v, valid, f) if (not ok) or keep]
+
+
+def test_filter_chunked():
+    # TestFilterChunkedArray-style (:1006-1018): chunked values x chunked filter -> chunked result
+    v = pc.Chunked([pc.Array.from_pylist([7, 8], pc.INT32), pc.Array.from_pylist([9, 10, 11], pc.INT32)], pc.INT32)
+    m = pc.Chunked([pc.Array.from_pylist([True, False, True], pc.BOOL), pc.Array.from_pylist([None, True], pc.BOOL)], pc.BOOL)
+    out = pc.Filter(v, m, pc.EMIT_NULLS)
+    assert out.kind == pc.KIND_CHUNKED and out.to_pylist() == [7, 9, None, 11]
+    assert pc.Filter(v, m, pc.DROP_NULLS).to_pylist() == [7, 9, 11]
+
+
+@pytest.mark.parametrize("t", [pc.INT8, pc.UINT16, pc.INT32, pc.INT64, pc.FLOAT64])
+def test_take_numeric(t):
+    for case in load("take_numeric.json")["cases"]:
+        for it in (pc.INT32, pc.INT8, pc.UINT32):
+            if it == pc.UINT32 and any(x is not None and x < 0 for x in case["indices"]):
+                continue
+            v, i = pc.Array.from_pylist(case["values"], t), pc.Array.from_pylist(case["indices"], it)
+            if "error_index" in case:
+                with pytest.raises(pc.ArrowError) as e:
+                    pc.Take(v, i)
+                assert e.value.sentinel == "ErrIndex" and f"{case['error_index']} out of bounds" in e.value.msg
+                continue
+            assert pc.Take(v, i).to_pylist() == case["expected"], case
+            # sliced values / sliced indices (checkTake, vector_selection_test.go:213-253)
+            vs = pc.Array.from_pylist([None, None] + case["values"] + [None], t).slice(2, len(case["values"]))
+            is_ = pc.Array.from_pylist([0] + case["indices"] + [0, 0], it).slice(1, len(case["indices"]))
+            assert pc.Take(vs, is_).to_pylist() == case["expected"], ("sliced", case)
+
+
+def test_take_chunked():
+    # :1609-1642 chunked values / chunked indices
+    v = pc.Chunked([pc.Array.from_pylist([7], pc.INT32), pc.Array.from_pylist([8, 9], pc.INT32)], pc.INT32)
+    assert pc.Take(v, pc.Array.from_pylist([0, 1, 0, 2], pc.INT32)).to_pylist() == [7, 8, 7, 9]
+    i = pc.Chunked([pc.Array.from_pylist([0, 1, 0], pc.INT32), pc.Array.from_pylist([], pc.INT32), pc.Array.from_pylist([2], pc.INT32)], pc.INT32)
+    out = pc.Take(v, i)
+    assert out.kind == pc.KIND_CHUNKED and out.to_pylist() == [7, 8, 7, 9]
+    with pytest.raises(pc.ArrowError) as e:
+        pc.Take(v, pc.Array.from_pylist([0, 5], pc.INT32))
+    assert e.value.sentinel == "ErrIndex"
+
+
+# ---------------------------------------------------------------- arrow/math --------------
+def test_math_sum():
+    # arrow/math/float64_test.go:30-48
+    f = pc.Array.from_numpy(np.arange(10000, dtype=np.float64))
+    assert pc.math.sum_float64(f) == 49995000.0
+    assert pc.math.sum_float64(f, reference_order=True) == 49995000.0
+    assert pc.math.sum_float64(pc.Array.from_numpy(np.zeros(0))) == 0.0
+    assert pc.math.sum_int64(pc.Array.from_numpy(np.arange(10000, dtype=np.int64))) == 49995000
+    assert pc.math.sum_uint64(pc.Array.from_numpy(np.arange(10000, dtype=np.uint64))) == 49995000
+    # validity is ignored and slices work (Float64Values() = values[offset:offset+len])
+    x = np.arange(100, dtype=np.float64)
+    a = pc.Array.from_numpy(x, np.arange(100) % 3 != 0)
+    assert pc.math.sum_float64(a.slice(7, 50)) == x[7:57].sum()

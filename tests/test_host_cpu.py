@@ -1,0 +1,74 @@
+"""Host-side mirror (arrow_go_b200/host) — the pieces that are pure metadata and therefore run
+without a GPU: span iteration (restating ExecSpanItrSuite, arrow/compute/exec_internals_test.go:
+394-582), registry contents (function names of Appendix A of SURVEY.md), exact-type dispatch
+(functions.go:204-217)."""
+import pytest
+
+from arrow_go_b200 import compute as pc
+
+
+def sizes(spans):
+    return [s[1] for s in spans]
+
+
+def test_iterate_basics():
+    # TestBasics: two arrays of 100 + a scalar
+    assert sizes(pc.iterate_exec_spans([[100], [100], []], [False, False, False])) == [100]
+    assert sizes(pc.iterate_exec_spans([[100], [100], []], [False, False, False], 16)) == [16, 16, 16, 16, 16, 16, 4]
+
+
+def test_iterate_input_validation():
+    # TestInputValidation: lengths 10 vs 9 -> ErrInvalid either way round; a single array is fine
+    for lens in ([[10], [9]], [[9], [10]]):
+        with pytest.raises(pc.ArrowError) as e:
+            pc.iterate_exec_spans(lens, [False, False])
+        assert e.value.sentinel == "ErrInvalid"
+    assert sizes(pc.iterate_exec_spans([[10]], [False])) == [10]
+
+
+def test_iterate_chunked_arrays():
+    # TestChunkedArrays: chunks {0,20,10} x {15,15} x array(30) x 2 scalars
+    args = [[0, 20, 10], [15, 15], [30], [], []]
+    chunked = [True, True, False, False, False]
+    assert sizes(pc.iterate_exec_spans(args, chunked, 10)) == [10, 5, 5, 10]
+    assert sizes(pc.iterate_exec_spans(args, chunked, 20)) == [15, 5, 10]
+    assert sizes(pc.iterate_exec_spans(args, chunked, 30)) == [15, 5, 10]
+    spans = pc.iterate_exec_spans(args, chunked, 10)
+    assert [s[0] for s in spans] == [0, 10, 15, 20]
+    assert [s[2][0] for s in spans] == [1, 1, 1, 2]  # zero-length first chunk is skipped
+    assert [s[2][1] for s in spans] == [0, 0, 1, 1]
+
+
+def test_iterate_zero_length():
+    # TestZeroLengthInput
+    assert pc.iterate_exec_spans([[]], [True]) == []
+    assert pc.iterate_exec_spans([[0]], [False]) == []
+    assert pc.iterate_exec_spans([[0]], [True]) == []
+
+
+def test_bench_config_spans():
+    # config 2 layout: 1M-row chunks against 999,983-row chunks
+    spans = pc.iterate_exec_spans([[1_000_000] * 100, [999_983] * 100 + [1700]], [True, True])
+    assert sum(sizes(spans)) == 100_000_000
+    assert all(l > 0 for l in sizes(spans))
+    assert len(spans) == 200
+
+
+def test_registry_has_the_reference_function_names():
+    names = set(pc.function_names())
+    for n in ("add", "add_unchecked", "sub", "sub_unchecked", "subtract", "subtract_unchecked", "multiply", "multiply_unchecked",
+              "abs_unchecked", "negate_unchecked", "sign", "equal", "not_equal", "greater", "greater_equal", "less", "less_equal",
+              "and", "or", "xor", "and_not", "and_kleene", "or_kleene", "and_not_kleene", "not",
+              "filter", "array_filter", "take", "array_take"):
+        assert n in names, n
+
+
+def test_exact_type_dispatch():
+    pc.dispatch("add", [pc.FLOAT64, pc.FLOAT64])
+    pc.dispatch("greater", [pc.INT64, pc.INT64])
+    pc.dispatch("and_kleene", [pc.BOOL, pc.BOOL])
+    with pytest.raises(pc.ArrowError) as e:
+        pc.dispatch("add", [pc.INT32, pc.FLOAT64])  # implicit promotion (cast) is out of scope
+    assert e.value.sentinel == "ErrNotImplemented"
+    with pytest.raises(pc.ArrowError):
+        pc.dispatch("no_such_function", [pc.INT32])
