@@ -29,6 +29,19 @@ KLEENE_AND, KLEENE_OR, KLEENE_ANDNOT = range(3)
 DROP_NULLS, EMIT_NULLS = 0, 1
 
 
+class Span3(C.Structure):
+    """ag_span3: one aligned span of a chunked binary call."""
+    _fields_ = [("l", C.c_void_p), ("r", C.c_void_p), ("out", C.c_void_p), ("n", C.c_int64)]
+
+
+def span_table(spans):
+    """[(l_ptr, r_ptr, out_ptr, n), ...] -> ctypes array of ag_span3."""
+    arr = (Span3 * max(len(spans), 1))()
+    for k, (l, r, o, n) in enumerate(spans):
+        arr[k].l, arr[k].r, arr[k].out, arr[k].n = l, r, o, n
+    return arr
+
+
 class NativeError(RuntimeError):
     """A C-ABI call returned a non-zero ag_status."""
 
@@ -89,6 +102,8 @@ _SIGS = {
     "ag_arith_unary_same": [_i, _i8, _p, _p, _i64],
     "ag_arith_unary_diff": [_i, _i, _i8, _p, _p, _i64],
     "ag_arith_binary_dev": [_i, _i8, _i, _p, _p, _p, _i64, _p],
+    "ag_arith_binary_spans": [_i, _i8, _i, _p, _i64],
+    "ag_arith_binary_spans_dev": [_i, _i8, _i, _p, _i64, _p],
     "ag_arith_unary_same_dev": [_i, _i8, _p, _p, _i64, _p],
     "ag_arith_unary_diff_dev": [_i, _i, _i8, _p, _p, _i64, _p],
     "ag_arith_checked": [_i, _i8, _i, _p, _p, _i64, _p, _p, _i64, _p, _i64, _pi64],
@@ -138,12 +153,16 @@ _lib = None
 
 
 def build(verbose=False):
-    """Compile libarrowgpu.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    """Compile libarrowgpu.so (sm_100a kernels + C ABI) and libarrowgpu_host.so (C++ host mirror)
+    in-tree.  nvcc cross-compiles without a GPU."""
     out = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc"), "-j8"], capture_output=True, text=True)
     if out.returncode != 0:
         raise RuntimeError("libarrowgpu build failed:\n" + out.stdout[-4000:] + out.stderr[-4000:])
     if verbose:
         print(out.stdout[-2000:])
+    out = subprocess.run(["make", "-C", os.path.join(_HERE, "host")], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("libarrowgpu_host build failed:\n" + out.stdout[-4000:] + out.stderr[-4000:])
     return LIB_PATH
 
 

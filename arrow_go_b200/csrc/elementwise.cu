@@ -17,6 +17,7 @@
 #include "common.cuh"
 
 #include <type_traits>
+#include <vector>
 
 namespace ag {
 
@@ -177,6 +178,157 @@ ag_status arith_binary_dev(int type, int8_t op, int shape, const void* l, const 
     case AG_TYPE_FLOAT64: return launch_binary_op<double>(op, shape, l, r, out, n, st);
     default: AG_FAIL(AG_ERR_TYPE, "arith: unsupported type id %d", type);
   }
+}
+
+
+// ---------------------------------------------------------------- batched spans -----
+// One launch for ALL aligned spans of a chunked call (iterateExecSpans, executor.go:757-863,
+// yields ~2 spans per chunk boundary; the reference runs its kernel once per span on one
+// goroutine — here a span costs nothing extra).  Work is cut into tiles of kSpanTile rows; a
+// block finds its tile's span by binary search over the prefix array, then runs the same
+// 128-bit streaming loop as binary_vec_kernel (or the element loop when that span's pointers
+// are only element-aligned).
+constexpr int kSpanTile = 4096;
+
+struct SpanDesc {
+  const void* l;
+  const void* r;
+  void* out;
+  long long n;
+  long long first_tile;  // number of tiles before this span
+};
+
+template <typename T, typename Op, int kShape>
+__global__ void __launch_bounds__(kEwThreads)
+binary_spans_kernel(const SpanDesc* __restrict__ spans, int n_spans, long long total_tiles, T scalar) {
+  constexpr int N = 16 / sizeof(T);
+  __shared__ int s_span;
+  for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    if (threadIdx.x == 0) {
+      int lo = 0, hi = n_spans - 1;  // last span with first_tile <= tile
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (spans[mid].first_tile <= tile) lo = mid; else hi = mid - 1;
+      }
+      s_span = lo;
+    }
+    __syncthreads();
+    const SpanDesc sp = spans[s_span];
+    __syncthreads();
+    const long long e0 = (tile - sp.first_tile) * kSpanTile;
+    const int len = (int)((sp.n - e0 < kSpanTile) ? (sp.n - e0) : kSpanTile);
+    const T* l = reinterpret_cast<const T*>(sp.l) + (kShape == AG_SHAPE_SA ? 0 : e0);
+    const T* r = reinterpret_cast<const T*>(sp.r) + (kShape == AG_SHAPE_AS ? 0 : e0);
+    T* out = reinterpret_cast<T*>(sp.out) + e0;
+    const bool vec = ((reinterpret_cast<uintptr_t>(out) | (kShape == AG_SHAPE_SA ? 0 : reinterpret_cast<uintptr_t>(l)) |
+                       (kShape == AG_SHAPE_AS ? 0 : reinterpret_cast<uintptr_t>(r))) & 15) == 0;
+    if (vec) {
+      const int nvec = len / N;
+      constexpr int kIters = kSpanTile / N / kEwThreads;  // vectors per thread in a full tile
+#pragma unroll
+      for (int b = 0; b < kIters; b += kEwUnroll) {
+        Vec<T, N> a[kEwUnroll], c[kEwUnroll];
+#pragma unroll
+        for (int k = 0; k < kEwUnroll; ++k) {
+          const int vi = (b + k) * kEwThreads + threadIdx.x;
+          if (vi < nvec) {
+            if (kShape != AG_SHAPE_SA) a[k] = ldv(l, vi);
+            if (kShape != AG_SHAPE_AS) c[k] = ldv(r, vi);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < kEwUnroll; ++k) {
+          const int vi = (b + k) * kEwThreads + threadIdx.x;
+          if (vi < nvec) {
+            Vec<T, N> o;
+#pragma unroll
+            for (int e = 0; e < N; ++e)
+              o.v[e] = Op::template apply<T>(kShape == AG_SHAPE_SA ? scalar : a[k].v[e], kShape == AG_SHAPE_AS ? scalar : c[k].v[e]);
+            stv(out, vi, o);
+          }
+        }
+      }
+      const int i = nvec * N + threadIdx.x;
+      if (i < len) out[i] = Op::template apply<T>(kShape == AG_SHAPE_SA ? scalar : l[i], kShape == AG_SHAPE_AS ? scalar : r[i]);
+    } else {
+#pragma unroll 4
+      for (int i = threadIdx.x; i < len; i += kEwThreads)
+        __stcs(out + i, Op::template apply<T>(kShape == AG_SHAPE_SA ? scalar : __ldcs(l + i), kShape == AG_SHAPE_AS ? scalar : __ldcs(r + i)));
+    }
+  }
+}
+
+template <typename T, typename Op, int kShape>
+static ag_status launch_spans_t(const SpanDesc* d_spans, int n_spans, long long total_tiles, const void* scalar_host, cudaStream_t st) {
+  T scalar = T(0);
+  if (kShape != AG_SHAPE_AA) scalar = *reinterpret_cast<const T*>(scalar_host);
+  const int grid = grid_for(total_tiles, 1, kEwBlocksPerSM);
+  binary_spans_kernel<T, Op, kShape><<<grid, kEwThreads, 0, st>>>(d_spans, n_spans, total_tiles, scalar);
+  return check_launch("binary_spans_kernel");
+}
+template <typename T, typename Op>
+static ag_status launch_spans_shape(int shape, const SpanDesc* d, int n, long long tiles, const void* sc, cudaStream_t st) {
+  switch (shape) {
+    case AG_SHAPE_AA: return launch_spans_t<T, Op, AG_SHAPE_AA>(d, n, tiles, sc, st);
+    case AG_SHAPE_AS: return launch_spans_t<T, Op, AG_SHAPE_AS>(d, n, tiles, sc, st);
+    case AG_SHAPE_SA: return launch_spans_t<T, Op, AG_SHAPE_SA>(d, n, tiles, sc, st);
+    default: AG_FAIL(AG_ERR_INVALID, "arith: bad operand shape %d", shape);
+  }
+}
+template <typename T>
+static ag_status launch_spans_op(int8_t op, int shape, const SpanDesc* d, int n, long long tiles, const void* sc, cudaStream_t st) {
+  switch (op) {
+    case AG_OP_ADD: case AG_OP_ADD_CHECKED: return launch_spans_shape<T, OpAdd>(shape, d, n, tiles, sc, st);
+    case AG_OP_SUB: case AG_OP_SUB_CHECKED: return launch_spans_shape<T, OpSub>(shape, d, n, tiles, sc, st);
+    case AG_OP_MUL: case AG_OP_MUL_CHECKED: return launch_spans_shape<T, OpMul>(shape, d, n, tiles, sc, st);
+    default: AG_FAIL(AG_ERR_NOT_IMPLEMENTED, "arith: binary op %d has no native kernel", (int)op);
+  }
+}
+
+// spans: HOST array of {l, r, out, n} with DEVICE pointers (the scalar side is a HOST pointer to
+// one element and must be the same pointer in every span).
+ag_status arith_binary_spans_dev(int type, int8_t op, int shape, const ag_span3* spans, int64_t n_spans, cudaStream_t st) {
+  if (n_spans < 0) AG_FAIL(AG_ERR_INVALID, "arith_spans: negative span count");
+  const int w = type_width(type);
+  if (w == 0) AG_FAIL(AG_ERR_TYPE, "arith: unsupported type id %d", type);
+  std::vector<SpanDesc> desc;
+  desc.reserve((size_t)n_spans);
+  long long tiles = 0;
+  const void* scalar_host = nullptr;
+  const uintptr_t m = (uintptr_t)(w - 1);
+  for (int64_t i = 0; i < n_spans; ++i) {
+    const ag_span3& s = spans[i];
+    if (s.n < 0) AG_FAIL(AG_ERR_INVALID, "arith_spans: negative length");
+    if (s.n == 0) continue;
+    if (!s.l || !s.r || !s.out) AG_FAIL(AG_ERR_INVALID, "arith_spans: NULL operand in span %lld", (long long)i);
+    if (((uintptr_t)s.out & m) || (shape != AG_SHAPE_SA && ((uintptr_t)s.l & m)) || (shape != AG_SHAPE_AS && ((uintptr_t)s.r & m)))
+      AG_FAIL(AG_ERR_INVALID, "arith_spans: operand not aligned to its element width");
+    if (shape == AG_SHAPE_AS) scalar_host = s.r;
+    if (shape == AG_SHAPE_SA) scalar_host = s.l;
+    SpanDesc d{s.l, s.r, s.out, (long long)s.n, tiles};
+    desc.push_back(d);
+    tiles += (s.n + kSpanTile - 1) / kSpanTile;
+  }
+  if (desc.empty()) return AG_OK;
+  if (desc.size() > (size_t)INT32_MAX) AG_FAIL(AG_ERR_INVALID, "arith_spans: too many spans");
+  SpanDesc* d_spans = nullptr;
+  AG_TRY(dev_alloc_async((void**)&d_spans, desc.size() * sizeof(SpanDesc), st));
+  // pageable source: the copy is staged before the call returns, so `desc` may die afterwards
+  cudaError_t e = cudaMemcpyAsync(d_spans, desc.data(), desc.size() * sizeof(SpanDesc), cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) { cudaFreeAsync(d_spans, st); return cuda_fail(e, "span table upload", __FILE__, __LINE__); }
+  ag_status rc;
+  const int n = (int)desc.size();
+  switch (type) {
+    case AG_TYPE_UINT8: case AG_TYPE_INT8: rc = launch_spans_op<uint8_t>(op, shape, d_spans, n, tiles, scalar_host, st); break;
+    case AG_TYPE_UINT16: case AG_TYPE_INT16: rc = launch_spans_op<uint16_t>(op, shape, d_spans, n, tiles, scalar_host, st); break;
+    case AG_TYPE_UINT32: case AG_TYPE_INT32: rc = launch_spans_op<uint32_t>(op, shape, d_spans, n, tiles, scalar_host, st); break;
+    case AG_TYPE_UINT64: case AG_TYPE_INT64: rc = launch_spans_op<unsigned long long>(op, shape, d_spans, n, tiles, scalar_host, st); break;
+    case AG_TYPE_FLOAT32: rc = launch_spans_op<float>(op, shape, d_spans, n, tiles, scalar_host, st); break;
+    case AG_TYPE_FLOAT64: rc = launch_spans_op<double>(op, shape, d_spans, n, tiles, scalar_host, st); break;
+    default: rc = AG_ERR_TYPE; set_error("arith: unsupported type id %d", type); break;
+  }
+  cudaFreeAsync(d_spans, st);
+  return rc;
 }
 
 // ---------------------------------------------------------------- unary ------------
@@ -490,6 +642,11 @@ extern "C" {
 ag_status ag_arith_binary_dev(int type, int8_t op, int shape, const void* l, const void* r, void* out, int64_t n, ag_stream_t s) {
   AG_TRY(ensure_init());
   return arith_binary_dev(type, op, shape, l, r, out, n, resolve_stream(s));
+}
+ag_status ag_arith_binary_spans_dev(int type, int8_t op, int shape, const ag_span3* spans, int64_t n_spans, ag_stream_t s) {
+  AG_TRY(ensure_init());
+  if (n_spans > 0 && !spans) AG_FAIL(AG_ERR_INVALID, "arith_spans: NULL span table");
+  return arith_binary_spans_dev(type, op, shape, spans, n_spans, resolve_stream(s));
 }
 ag_status ag_arith_unary_same_dev(int type, int8_t op, const void* in, void* out, int64_t n, ag_stream_t s) {
   AG_TRY(ensure_init());

@@ -129,6 +129,55 @@ static ag_status pipelined_rows(int64_t n, int n_in, const void* const* in, cons
   return rc != AG_OK ? rc : rs;
 }
 
+// Host flavour of the batched-span call: every (span, sub-chunk) becomes one stage of the same
+// 3-deep H2D / kernel / D2H pipeline, so consecutive spans of a chunked call overlap exactly like
+// the chunks of one long span do.
+static ag_status host_arith_binary_spans(int type, int8_t op, int shape, const ag_span3* spans, int64_t n_spans) {
+  AG_TRY(ensure_init());
+  const int w = type_width(type);
+  if (w == 0) AG_FAIL(AG_ERR_TYPE, "arith: unsupported type id %d", type);
+  if (n_spans < 0 || (n_spans > 0 && !spans)) AG_FAIL(AG_ERR_INVALID, "arith_spans: bad span table");
+  int64_t max_n = 0;
+  for (int64_t i = 0; i < n_spans; ++i) {
+    if (spans[i].n < 0) AG_FAIL(AG_ERR_INVALID, "arith_spans: negative length");
+    if (spans[i].n > 0 && (!spans[i].l || !spans[i].r || !spans[i].out)) AG_FAIL(AG_ERR_INVALID, "arith_spans: NULL operand");
+    if (spans[i].n > max_n) max_n = spans[i].n;
+  }
+  if (max_n == 0) return AG_OK;
+  Pipe pipe;
+  AG_TRY(pipe.acquire());
+  int64_t chunk = (kChunkBytes / w) & ~(int64_t)1023;
+  if (chunk > max_n) chunk = max_n;
+  const bool la = shape != AG_SHAPE_SA, ra = shape != AG_SHAPE_AS;
+  void* d_l[kPipe] = {}; void* d_r[kPipe] = {}; void* d_o[kPipe] = {};
+  ag_status rc = AG_OK;
+  for (int sl = 0; sl < kPipe && rc == AG_OK; ++sl) {
+    if (la) rc = dev_alloc_async(&d_l[sl], (size_t)chunk * w + 64, pipe.s[sl]);
+    if (rc == AG_OK && ra) rc = dev_alloc_async(&d_r[sl], (size_t)chunk * w + 64, pipe.s[sl]);
+    if (rc == AG_OK) rc = dev_alloc_async(&d_o[sl], (size_t)chunk * w + 64, pipe.s[sl]);
+  }
+  int64_t ci = 0;
+  for (int64_t i = 0; i < n_spans && rc == AG_OK; ++i) {
+    const ag_span3& sp = spans[i];
+    for (int64_t r0 = 0; r0 < sp.n && rc == AG_OK; r0 += chunk, ++ci) {
+      const int sl = (int)(ci % kPipe);
+      const int64_t len = (sp.n - r0 < chunk) ? (sp.n - r0) : chunk;
+      cudaStream_t st = pipe.s[sl];
+      if (la) rc = h2d(d_l[sl], (const char*)sp.l + r0 * w, (size_t)len * w, st);
+      if (rc == AG_OK && ra) rc = h2d(d_r[sl], (const char*)sp.r + r0 * w, (size_t)len * w, st);
+      if (rc == AG_OK) rc = arith_binary_dev(type, op, shape, la ? d_l[sl] : sp.l, ra ? d_r[sl] : sp.r, d_o[sl], len, st);
+      if (rc == AG_OK) rc = d2h((char*)sp.out + r0 * w, d_o[sl], (size_t)len * w, st);
+    }
+  }
+  for (int sl = 0; sl < kPipe; ++sl) {
+    if (d_l[sl]) cudaFreeAsync(d_l[sl], pipe.s[sl]);
+    if (d_r[sl]) cudaFreeAsync(d_r[sl], pipe.s[sl]);
+    if (d_o[sl]) cudaFreeAsync(d_o[sl], pipe.s[sl]);
+  }
+  ag_status rs = pipe.sync_all();
+  return rc != AG_OK ? rc : rs;
+}
+
 static ag_status host_arith_binary(int type, int8_t op, int shape, const void* l, const void* r, void* out, int64_t n) {
   const int w = type_width(type);
   if (w == 0) AG_FAIL(AG_ERR_TYPE, "arith: unsupported type id %d", type);
@@ -156,6 +205,9 @@ ag_status ag_arith_arr_scalar(int type, int8_t op, const void* l, const void* r,
 }
 ag_status ag_arith_scalar_arr(int type, int8_t op, const void* l, const void* r, void* out, int64_t n) {
   return host_arith_binary(type, op, AG_SHAPE_SA, l, r, out, n);
+}
+ag_status ag_arith_binary_spans(int type, int8_t op, int shape, const ag_span3* spans, int64_t n_spans) {
+  return host_arith_binary_spans(type, op, shape, spans, n_spans);
 }
 ag_status ag_arith_unary_same(int type, int8_t op, const void* in, void* out, int64_t n) {
   const int w = type_width(type);

@@ -200,6 +200,15 @@ ag_status ag_arith_unary_same(int type, int8_t op, const void* in, void* out, in
 ag_status ag_arith_unary_diff(int itype, int otype, int8_t op, const void* in, void* out, int64_t n); /* SIGN */
 ag_status ag_arith_binary_dev(int type, int8_t op, int shape, const void* d_l, const void* d_r, void* d_out,
                               int64_t n, ag_stream_t s); /* scalar side: HOST pointer to one element */
+/* Batched form for chunked arguments: ONE launch (device flavour) / one pipelined transfer
+ * schedule (host flavour) for all the aligned spans iterateExecSpans yields for a call
+ * (arrow/compute/executor.go:757-863).  A compute.Function that receives whole ChunkedDatums
+ * (functions.go:30-41) binds this instead of a per-span kernel.  Results are identical to
+ * calling ag_arith_binary[_dev] once per span.  For AS / SA shapes the scalar side of every
+ * span must be the same host pointer to one element. */
+typedef struct ag_span3 { const void* l; const void* r; void* out; int64_t n; } ag_span3;
+ag_status ag_arith_binary_spans(int type, int8_t op, int shape, const ag_span3* spans, int64_t n_spans);
+ag_status ag_arith_binary_spans_dev(int type, int8_t op, int shape, const ag_span3* spans, int64_t n_spans, ag_stream_t s);
 ag_status ag_arith_unary_same_dev(int type, int8_t op, const void* d_in, void* d_out, int64_t n, ag_stream_t s);
 ag_status ag_arith_unary_diff_dev(int itype, int otype, int8_t op, const void* d_in, void* d_out, int64_t n, ag_stream_t s);
 

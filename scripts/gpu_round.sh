@@ -18,7 +18,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --
     python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/${TAG}_ncu_bench.log 2>&1
 echo "ncu launches rc=$?"
 if [ -n "$KRE" ]; then
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$KRE -s 8 -c 3 -o gpurun_out/${TAG}_prof -f \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$KRE -s 3 -c 2 -o gpurun_out/${TAG}_prof -f \
       python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-others > gpurun_out/${TAG}_ncu_full.log 2>&1
   echo "ncu full rc=$?"
 fi

@@ -97,9 +97,10 @@ def test_kleene_truth_tables(ag, cpu):
         N.KLEENE_OR: [T, T, T, T, F, NUL, T, NUL, NUL],
         N.KLEENE_ANDNOT: [F, T, NUL, F, F, F, F, NUL, NUL],
     }
+    blv, bld, brv, brd = pack_bits(lv), pack_bits(ld), pack_bits(rv), pack_bits(rd)  # keep the buffers alive across the call
     for kop, exp in expect.items():
         ov = np.zeros(2, dtype=np.uint8); od = np.zeros(2, dtype=np.uint8)
-        ag.call("ag_kleene", kop, ptr(pack_bits(lv)), ptr(pack_bits(ld)), 0, ptr(pack_bits(rv)), ptr(pack_bits(rd)), 0, ptr(ov), ptr(od), 0, 9)
+        ag.call("ag_kleene", kop, ptr(blv), ptr(bld), 0, ptr(brv), ptr(brd), 0, ptr(ov), ptr(od), 0, 9)
         gv, gd = unpack_bits(ov, 0, 9), unpack_bits(od, 0, 9)
         for i, (v, d) in enumerate(exp):
             assert bool(gv[i]) == bool(v), (kop, i)

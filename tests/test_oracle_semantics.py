@@ -169,7 +169,8 @@ def test_kleene_vs_pyarrow(cpu):
         for kop, fn in fns.items():
             want = fn(pa.array(ld, mask=~lv), pa.array(rd, mask=~rv))
             ov, od = np.zeros(n // 8 + 2, dtype=np.uint8), np.zeros(n // 8 + 2, dtype=np.uint8)
-            assert cpu.ref_kleene(kop, ptr(pack_bits(lv, 3)), ptr(pack_bits(ld, 3)), 3, ptr(pack_bits(rv, 6)), ptr(pack_bits(rd, 6)), 6, ptr(ov), ptr(od), 1, n) == 0
+            blv, bld, brv, brd = pack_bits(lv, 3), pack_bits(ld, 3), pack_bits(rv, 6), pack_bits(rd, 6)
+            assert cpu.ref_kleene(kop, ptr(blv), ptr(bld), 3, ptr(brv), ptr(brd), 6, ptr(ov), ptr(od), 1, n) == 0
             gv, gd = unpack_bits(ov, 1, n), unpack_bits(od, 1, n)
             wv = np.array([x.is_valid for x in want])
             assert gv.tolist() == wv.tolist()
