@@ -13,27 +13,31 @@
 // fetched only for emitted rows (predicated 8-byte loads; DRAM moves the touched 32-byte
 // sectors), so at low selectivity the kernel can move FEWER bytes than that figure.
 //
-// Single pass, decoupled look-back:
-//   * a tile is 8192 rows = 256 threads x one 32-bit mask word each; tiles are claimed with an
-//     atomic ticket so a tile only ever waits on tiles that are already running;
-//   * popcount per thread -> warp scan -> block scan -> tile aggregate published in a 64-bit
-//     status word (2 flag bits + 62-bit count, one store => no fences needed);
-//   * warp 0 looks back 32 tiles at a time until it meets an inclusive prefix;
-//   * compaction is warp-cooperative: for each of a warp's 32 words the lanes whose bit is set
-//     load row (32k+lane) — coalesced — and store to out[base_k + rank], rank = popc of the
-//     lower set bits: writes of one step are contiguous.
+// Single pass, WARP-granular decoupled look-back (no block barriers, no shared memory):
+//   * a tile is 1024 rows = one warp, one 32-bit mask word per lane; tiles are claimed with an
+//     atomic ticket (a tile only ever waits on tiles that are already running) and the next
+//     ticket is requested while the current tile's loads are in flight;
+//   * popcount per lane -> warp scan -> tile aggregate published in a 64-bit status word
+//     (2 flag bits + 62-bit count, one store => a reader never sees a flag without its value);
+//   * the warp looks back 32 tiles at a time until it meets an inclusive prefix; the other
+//     warps of the SM are in their load/store phases meanwhile, which is what hides the chain;
+//   * compaction is warp-cooperative: for each of the 32 words, lane j owns row 32k+j, so loads
+//     are coalesced; it stores to out[base_k + rank], rank = popc of the lower set bits, so the
+//     writes of one step are contiguous.  Sparse tiles load only the selected rows (DRAM moves
+//     the touched sectors); dense tiles load all 32 x 256 B rows;
 //   * output validity bits are compacted with __reduce_or_sync and merged into pre-zeroed
 //     words with at most two atomicOr per step.
 #include "common.cuh"
 
+#include <stdlib.h>
 #include <type_traits>
 
 namespace ag {
 
 constexpr int kFThreads = 256;
 constexpr int kFWarps = kFThreads / 32;
-constexpr int kFTileRows = kFThreads * 32;  // 8192
-constexpr int kFBlocksPerSM = 6;
+constexpr int kFTileRows = 1024;  // one WARP tile: 32 lanes x one 32-bit mask word
+constexpr int kFBlocksPerSM = 4;
 
 constexpr unsigned long long kFlagShift = 62;
 constexpr unsigned long long kFlagAgg = 1ull << kFlagShift;
@@ -62,10 +66,12 @@ struct FilterParams {
   unsigned long long* status;  // [0] = tile ticket, [1..] = tile status words
   long long* out_len;
   int64_t n_tiles;
+  int dense_threshold;       // tiles emitting at least this many rows load their 1024 values coalesced
 };
 
-// warp 0 only.  Returns the exclusive prefix of `tile` (sum of the aggregates of all earlier tiles)
-// and publishes this tile's inclusive prefix.
+// Whole warp.  Returns the exclusive prefix of `tile` (rows emitted by all earlier tiles) and
+// publishes this tile's inclusive prefix.  One 64-bit word carries flag + count, so a reader
+// never sees a flag without its value.
 __device__ __forceinline__ unsigned long long lookback(unsigned long long* st, int64_t tile, unsigned long long total, int lane) {
   if (tile == 0) {
     if (lane == 0) st_status(st, kFlagIncl | total);
@@ -98,60 +104,47 @@ __device__ __forceinline__ unsigned long long lookback(unsigned long long* st, i
   return running;
 }
 
-
-// Block-wide exclusive scan of the per-thread counts + decoupled look-back across tiles.
-// Returns the global output slot of this thread's first emitted row; *tile_total = rows the
-// tile emits.  Contains two __syncthreads(); every thread of the block must call it.
-__device__ __forceinline__ unsigned long long tile_scan(unsigned cnt, unsigned long long* status, int64_t tile, int64_t n_tiles,
-                                                        long long* out_len, unsigned* s_warp_tot, unsigned long long* s_base,
-                                                        unsigned* tile_total_out) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// Warp-wide exclusive scan of the per-lane counts + look-back.  Returns the global output slot
+// of this lane's first emitted row; *tile_total = rows the warp tile emits.
+__device__ __forceinline__ unsigned long long warp_tile_scan(unsigned cnt, unsigned long long* status, int64_t tile, int64_t n_tiles,
+                                                             long long* out_len, unsigned* tile_total_out) {
+  const int lane = threadIdx.x & 31;
   unsigned incl = cnt;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
     if (lane >= d) incl += t;
   }
-  if (lane == 31) s_warp_tot[warp] = incl;
-  __syncthreads();
-  unsigned warp_base = 0, tile_total = 0;
-#pragma unroll
-  for (int w = 0; w < kFWarps; ++w) {
-    const unsigned t = s_warp_tot[w];
-    if (w < warp) warp_base += t;
-    tile_total += t;
-  }
-  if (warp == 0) {
-    const unsigned long long excl = lookback(status, tile, tile_total, lane);
-    if (lane == 0) {
-      *s_base = excl;
-      if (tile == n_tiles - 1) *out_len = (long long)(excl + tile_total);
-    }
-  }
-  __syncthreads();
-  *tile_total_out = tile_total;
-  return *s_base + warp_base + (incl - cnt);
+  const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+  const unsigned long long excl = lookback(status, tile, total, lane);
+  if (lane == 0 && tile == n_tiles - 1) *out_len = (long long)(excl + total);
+  *tile_total_out = total;
+  return excl + (incl - cnt);
+}
+
+// Warp tiles are claimed with an atomic ticket (a tile only waits on tiles that are already
+// running => forward progress without assuming co-residency); the ticket for the NEXT tile is
+// requested while the current tile's loads are in flight.
+__device__ __forceinline__ long long claim_tile(unsigned long long* ticket, int lane) {
+  unsigned long long t = 0;
+  if (lane == 0) t = atomicAdd(ticket, 1ull);
+  return (long long)__shfl_sync(0xffffffffu, t, 0);
 }
 
 // kMode 0: copy values of type V.  kMode 1: write row indices as V (GetTakeIndices).
 template <typename V, int kMode, bool kValidity>
 __global__ void __launch_bounds__(kFThreads)
 filter_kernel(const FilterParams p) {
-  __shared__ long long s_tile;
-  __shared__ unsigned s_warp_tot[kFWarps];
-  __shared__ unsigned long long s_base;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   const V* __restrict__ vals = reinterpret_cast<const V*>(p.vals) + (kMode == 0 ? p.voff : 0);
   V* __restrict__ out = reinterpret_cast<V*>(p.out);
   const int64_t m_lo = p.moff >> 3, m_hi = (p.moff + p.n + 7) >> 3;
+  const long long cap_words = (p.capacity + 31) >> 5;
 
-  while (true) {
-    if (threadIdx.x == 0) s_tile = (long long)atomicAdd(p.status, 1ull);
-    __syncthreads();
-    const int64_t tile = s_tile;
-    if (tile >= p.n_tiles) break;
-    const int64_t row0 = tile * kFTileRows + (int64_t)threadIdx.x * 32;  // first row of this thread's word
-
+  long long tile = claim_tile(p.status, lane);
+  while (tile < p.n_tiles) {
+    const int64_t wrow0 = tile * kFTileRows;
+    const int64_t row0 = wrow0 + (int64_t)lane * 32;  // first row of this lane's mask word
     uint32_t sel = 0, nul = 0;
     if (row0 < p.n) {
       const int64_t rem = p.n - row0;
@@ -162,45 +155,67 @@ filter_kernel(const FilterParams p) {
       sel = m & mv & range;
       if (p.emit_nulls) nul = ~mv & range;
     }
+    const long long next_tile = claim_tile(p.status, lane);
     const uint32_t emit = sel | nul;
     unsigned tile_total;
-    const unsigned long long my_base = tile_scan(__popc(emit), p.status + 1, tile, p.n_tiles, p.out_len,
-                                                 s_warp_tot, &s_base, &tile_total);
+    const unsigned long long my_base = warp_tile_scan(__popc(emit), p.status + 1, tile, p.n_tiles, p.out_len, &tile_total);
 
     if (tile_total != 0) {
-      const int64_t wrow0 = tile * kFTileRows + (int64_t)warp * 1024;
-#pragma unroll 4
-      for (int k = 0; k < 32; ++k) {
-        const uint32_t w_emit = __shfl_sync(0xffffffffu, emit, k);
-        if (w_emit == 0) continue;  // warp-uniform
-        const uint32_t w_sel = __shfl_sync(0xffffffffu, sel, k);
-        const unsigned long long b = __shfl_sync(0xffffffffu, my_base, k);
-        const bool e = (w_emit >> lane) & 1;
-        const bool s = (w_sel >> lane) & 1;
-        const unsigned rank = __popc(w_emit & ((1u << lane) - 1u));
-        const int64_t row = wrow0 + k * 32 + lane;
-        const unsigned long long pos = b + rank;
-        if (e && (long long)pos < p.capacity) {
-          V v = V(0);
-          if (s) v = (kMode == 0) ? vals[row] : (V)row;
-          out[pos] = v;
+      const bool dense = kMode == 0 && (int)tile_total >= p.dense_threshold && wrow0 + kFTileRows <= p.n;
+#pragma unroll
+      for (int kb = 0; kb < 32; kb += 8) {
+        // phase 1: 8 independent loads in flight per lane (all 8 x 256 B rows when the tile is dense,
+        // only the selected rows' sectors when it is sparse)
+        V v[8];
+        uint32_t w_emit[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          w_emit[u] = __shfl_sync(0xffffffffu, emit, kb + u);
+          const uint32_t w_sel = __shfl_sync(0xffffffffu, sel, kb + u);
+          v[u] = V(0);
+          if (kMode == 0) {
+            if (dense || ((w_sel >> lane) & 1)) v[u] = vals[wrow0 + (kb + u) * 32 + lane];
+            if (!((w_sel >> lane) & 1)) v[u] = V(0);
+          } else {
+            if ((w_sel >> lane) & 1) v[u] = (V)(wrow0 + (kb + u) * 32 + lane);
+          }
         }
-        if (kValidity) {
-          uint32_t vb = 0;
-          if (e && s) vb = (kMode == 0 && p.vvalid) ? (uint32_t)bit_is_set(p.vvalid, p.voff + row) : 1u;
-          const uint32_t pattern = __reduce_or_sync(0xffffffffu, vb << rank);  // rank < 32 whenever vb != 0
-          if (lane == 0 && pattern) {
-            const unsigned sh = (unsigned)(b & 31);
-            const unsigned long long wi = b >> 5;
-            const long long cap_words = (p.capacity + 31) >> 5;
-            if ((long long)wi < cap_words) atomicOr(p.out_valid + wi, pattern << sh);
-            if (sh && (pattern >> (32 - sh)) && (long long)(wi + 1) < cap_words) atomicOr(p.out_valid + wi + 1, pattern >> (32 - sh));
+        // phase 2: compacting stores
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (w_emit[u] == 0) continue;  // warp-uniform
+          const unsigned long long b = __shfl_sync(0xffffffffu, my_base, kb + u);
+          const bool e = (w_emit[u] >> lane) & 1;
+          const unsigned rank = __popc(w_emit[u] & ((1u << lane) - 1u));
+          const unsigned long long pos = b + rank;
+          if (e && (long long)pos < p.capacity) out[pos] = v[u];
+          if (kValidity) {
+            const uint32_t w_sel = __shfl_sync(0xffffffffu, sel, kb + u);
+            const int64_t row = wrow0 + (kb + u) * 32 + lane;
+            uint32_t vb = 0;
+            if (e && ((w_sel >> lane) & 1)) vb = (kMode == 0 && p.vvalid) ? (uint32_t)bit_is_set(p.vvalid, p.voff + row) : 1u;
+            const uint32_t pattern = __reduce_or_sync(0xffffffffu, vb << rank);  // rank < 32 whenever vb != 0
+            if (lane == 0 && pattern) {
+              const unsigned sh = (unsigned)(b & 31);
+              const unsigned long long wi = b >> 5;
+              if ((long long)wi < cap_words) atomicOr(p.out_valid + wi, pattern << sh);
+              if (sh && (pattern >> (32 - sh)) && (long long)(wi + 1) < cap_words) atomicOr(p.out_valid + wi + 1, pattern >> (32 - sh));
+            }
           }
         }
       }
     }
-    __syncthreads();  // s_tile / s_base are rewritten by the next iteration
+    tile = next_tile;
   }
+}
+
+static int filter_dense_threshold() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("AG_FILTER_DENSE_THRESHOLD");
+    cached = e ? atoi(e) : 96;  // rows emitted per 1024-row tile above which coalesced loads win
+  }
+  return cached;
 }
 
 template <typename V, int kMode>
@@ -208,11 +223,12 @@ static ag_status launch_filter_t(FilterParams& p, cudaStream_t st) {
   Workspace* ws;
   AG_TRY(get_workspace(st, &ws));
   p.n_tiles = (p.n + kFTileRows - 1) / kFTileRows;
+  p.dense_threshold = filter_dense_threshold();
   AG_TRY(ensure_tile_status(ws, (size_t)p.n_tiles + 1, st));
   p.status = ws->tile_status;
   AG_CUDA_TRY(cudaMemsetAsync(p.status, 0, ((size_t)p.n_tiles + 1) * sizeof(unsigned long long), st));
   if (p.out_valid) AG_CUDA_TRY(cudaMemsetAsync(p.out_valid, 0, (size_t)((p.capacity + 31) >> 5) * 4, st));
-  const int grid = grid_for(p.n_tiles, 1, kFBlocksPerSM);
+  const int grid = grid_for(p.n_tiles, kFWarps, kFBlocksPerSM);
   if (p.out_valid) filter_kernel<V, kMode, true><<<grid, kFThreads, 0, st>>>(p);
   else filter_kernel<V, kMode, false><<<grid, kFThreads, 0, st>>>(p);
   return check_launch("filter_kernel");
@@ -277,12 +293,12 @@ ag_status take_indices_dev(int index_width, const uint8_t* mask, const uint8_t* 
   AG_FAIL(AG_ERR_TYPE, "take_indices: index width must be 16 or 32");
 }
 
-
 // ---------------------------------------------------------------- fused compare + filter ----
 // Greater/…(values, scalar) -> Filter in ONE pass over `values` (config 3 of BASELINE.json):
 // no intermediate mask, 8 + 8s bytes/row.  A warp keeps its 1024 rows in registers (lane holds
 // rows 32k+lane, k = 0..31 — the layout both the ballot and the compaction loop want), so the
-// values are read from HBM exactly once.  Same result as compare_dev + filter_primitive_dev.
+// values are read from HBM exactly once: 32 coalesced 256-byte loads per warp, all issued
+// before the first vote.  Same result as compare_dev + filter_primitive_dev.
 struct FCmpEq { template <typename T> static __device__ __forceinline__ bool apply(T a, T b) { return a == b; } };
 struct FCmpNe { template <typename T> static __device__ __forceinline__ bool apply(T a, T b) { return a != b; } };
 struct FCmpGt { template <typename T> static __device__ __forceinline__ bool apply(T a, T b) { return a > b; } };
@@ -294,34 +310,32 @@ template <typename T, typename Cmp>
 __global__ void __launch_bounds__(kFThreads)
 fused_cmp_filter_kernel(const T* __restrict__ vals, T scalar, int64_t n, T* __restrict__ out, int64_t capacity,
                         unsigned long long* status, long long* out_len, int64_t n_tiles) {
-  __shared__ long long s_tile;
-  __shared__ unsigned s_warp_tot[kFWarps];
-  __shared__ unsigned long long s_base;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  while (true) {
-    if (threadIdx.x == 0) s_tile = (long long)atomicAdd(status, 1ull);
-    __syncthreads();
-    const int64_t tile = s_tile;
-    if (tile >= n_tiles) break;
-    const int64_t wrow0 = tile * kFTileRows + (int64_t)warp * 1024;
+  const int lane = threadIdx.x & 31;
+  long long tile = claim_tile(status, lane);
+  while (tile < n_tiles) {
+    const int64_t wrow0 = tile * kFTileRows;
     T v[32];
-    uint32_t emit = 0;
+    if (wrow0 + kFTileRows <= n) {
 #pragma unroll
-    for (int kb = 0; kb < 32; kb += 8) {
+      for (int k = 0; k < 32; ++k) v[k] = __ldcs(vals + wrow0 + k * 32 + lane);
+    } else {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int64_t row = wrow0 + (kb + u) * 32 + lane;
-        v[kb + u] = (row < n) ? __ldcs(vals + row) : scalar;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int64_t row = wrow0 + (kb + u) * 32 + lane;
-        const uint32_t bits = __ballot_sync(0xffffffffu, row < n && Cmp::template apply<T>(v[kb + u], scalar));
-        if (lane == kb + u) emit = bits;
+      for (int k = 0; k < 32; ++k) {
+        const int64_t row = wrow0 + k * 32 + lane;
+        v[k] = (row < n) ? __ldcs(vals + row) : scalar;
       }
     }
+    const long long next_tile = claim_tile(status, lane);  // latency hidden behind the loads above
+    __syncwarp();                                          // keep every load ahead of the first vote
+    uint32_t emit = 0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const int64_t row = wrow0 + k * 32 + lane;
+      const uint32_t bits = __ballot_sync(0xffffffffu, row < n && Cmp::template apply<T>(v[k], scalar));
+      if (lane == k) emit = bits;
+    }
     unsigned tile_total;
-    const unsigned long long my_base = tile_scan(__popc(emit), status + 1, tile, n_tiles, out_len, s_warp_tot, &s_base, &tile_total);
+    const unsigned long long my_base = warp_tile_scan(__popc(emit), status + 1, tile, n_tiles, out_len, &tile_total);
     if (tile_total != 0) {
 #pragma unroll
       for (int k = 0; k < 32; ++k) {
@@ -332,7 +346,7 @@ fused_cmp_filter_kernel(const T* __restrict__ vals, T scalar, int64_t n, T* __re
         if (((w_emit >> lane) & 1) && (long long)pos < capacity) out[pos] = v[k];
       }
     }
-    __syncthreads();
+    tile = next_tile;
   }
 }
 
@@ -344,7 +358,7 @@ static ag_status launch_fused_t(const void* vals, const void* scalar_host, int64
   const int64_t n_tiles = (n + kFTileRows - 1) / kFTileRows;
   AG_TRY(ensure_tile_status(ws, (size_t)n_tiles + 1, st));
   AG_CUDA_TRY(cudaMemsetAsync(ws->tile_status, 0, ((size_t)n_tiles + 1) * sizeof(unsigned long long), st));
-  const int grid = grid_for(n_tiles, 1, 2);
+  const int grid = grid_for(n_tiles, kFWarps, 2);
   fused_cmp_filter_kernel<T, Cmp><<<grid, kFThreads, 0, st>>>((const T*)vals, *(const T*)scalar_host, n, (T*)out, capacity,
                                                              ws->tile_status, (long long*)d_out_len, n_tiles);
   return check_launch("fused_cmp_filter_kernel");
