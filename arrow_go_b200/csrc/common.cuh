@@ -94,6 +94,15 @@ inline bool type_is_float(int type) { return type == AG_TYPE_FLOAT32 || type == 
 
 inline int64_t bytes_for_bits(int64_t nbits) { return (nbits + 7) >> 3; }
 
+int blocks_per_sm(const void* kernel, int threads);
+// One-wave grid for a grid-stride kernel: min(blocks needed, SMs x resident blocks per SM).
+template <typename K>
+inline int grid_one_wave(K kernel, int threads, int64_t blocks_needed) {
+  const int64_t cap = (int64_t)sm_count() * blocks_per_sm(reinterpret_cast<const void*>(kernel), threads);
+  if (blocks_needed < 1) blocks_needed = 1;
+  return (int)(blocks_needed < cap ? blocks_needed : cap);
+}
+
 // Grid sizing: persistent-style grids are multiples of the SM count.
 inline int grid_for(int64_t work_items, int items_per_block, int blocks_per_sm) {
   int64_t want = (work_items + items_per_block - 1) / items_per_block;

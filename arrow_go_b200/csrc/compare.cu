@@ -79,15 +79,19 @@ static ag_status launch_cmp_shape(int shape, const void* l, const void* r, uint8
   uint32_t* words = reinterpret_cast<uint32_t*>(p & ~(uintptr_t)3);
   const int shift = (int)(p & 3) * 8 + (bit_offset & 7);
   const int64_t n_words = (n + shift + 31) >> 5;
-  const int grid = grid_for((n_words + 31) >> 5, kCmpThreads / 32, kCmpBlocksPerSM);
+  const int64_t blocks_needed = (((n_words + 31) >> 5) + kCmpThreads / 32 - 1) / (kCmpThreads / 32);
+  int grid;
   switch (shape) {
     case AG_SHAPE_AA:
+      grid = grid_one_wave(compare_kernel<T, Cmp, AG_SHAPE_AA>, kCmpThreads, blocks_needed);
       compare_kernel<T, Cmp, AG_SHAPE_AA><<<grid, kCmpThreads, 0, st>>>((const T*)l, (const T*)r, T(0), words, shift, n, n_words);
       break;
     case AG_SHAPE_AS:
+      grid = grid_one_wave(compare_kernel<T, Cmp, AG_SHAPE_AS>, kCmpThreads, blocks_needed);
       compare_kernel<T, Cmp, AG_SHAPE_AS><<<grid, kCmpThreads, 0, st>>>((const T*)l, nullptr, *(const T*)r, words, shift, n, n_words);
       break;
     case AG_SHAPE_SA:
+      grid = grid_one_wave(compare_kernel<T, Cmp, AG_SHAPE_SA>, kCmpThreads, blocks_needed);
       compare_kernel<T, Cmp, AG_SHAPE_SA><<<grid, kCmpThreads, 0, st>>>(nullptr, (const T*)r, *(const T*)l, words, shift, n, n_words);
       break;
     default: AG_FAIL(AG_ERR_INVALID, "compare: bad operand shape %d", shape);

@@ -130,10 +130,10 @@ static ag_status launch_binary_t(const void* l, const void* r, void* out, int64_
   constexpr int N = 16 / sizeof(T);
   const bool vec = aligned16(out) && (kShape == AG_SHAPE_SA || aligned16(l)) && (kShape == AG_SHAPE_AS || aligned16(r));
   if (vec) {
-    const int grid = grid_for(n / N + 1, kEwThreads * kEwUnroll, kEwBlocksPerSM);
+    const int grid = grid_one_wave(binary_vec_kernel<T, Op, kShape>, kEwThreads, (n / N + kEwThreads * kEwUnroll) / (kEwThreads * kEwUnroll));
     binary_vec_kernel<T, Op, kShape><<<grid, kEwThreads, 0, st>>>(lp, rp, op, n, scalar);
   } else {
-    const int grid = grid_for(n, kEwThreads * kEwUnroll, kEwBlocksPerSM);
+    const int grid = grid_one_wave(binary_scalar_kernel<T, Op, kShape>, kEwThreads, (n + kEwThreads * kEwUnroll - 1) / (kEwThreads * kEwUnroll));
     binary_scalar_kernel<T, Op, kShape><<<grid, kEwThreads, 0, st>>>(lp, rp, op, n, scalar);
   }
   return check_launch("binary_kernel");
@@ -262,7 +262,7 @@ template <typename T, typename Op, int kShape>
 static ag_status launch_spans_t(const SpanDesc* d_spans, int n_spans, long long total_tiles, const void* scalar_host, cudaStream_t st) {
   T scalar = T(0);
   if (kShape != AG_SHAPE_AA) scalar = *reinterpret_cast<const T*>(scalar_host);
-  const int grid = grid_for(total_tiles, 1, kEwBlocksPerSM);
+  const int grid = grid_one_wave(binary_spans_kernel<T, Op, kShape>, kEwThreads, total_tiles);
   binary_spans_kernel<T, Op, kShape><<<grid, kEwThreads, 0, st>>>(d_spans, n_spans, total_tiles, scalar);
   return check_launch("binary_spans_kernel");
 }
@@ -412,7 +412,7 @@ template <typename T, typename Op>
 static ag_status launch_unary_same_t(const void* in, void* out, int64_t n, cudaStream_t st) {
   constexpr int N = 16 / sizeof(T);
   if (aligned16(in) && aligned16(out)) {
-    const int grid = grid_for(n / N + 1, kEwThreads * kEwUnroll, kEwBlocksPerSM);
+    const int grid = grid_one_wave(unary_vec_kernel<T, Op>, kEwThreads, (n / N + kEwThreads * kEwUnroll) / (kEwThreads * kEwUnroll));
     unary_vec_kernel<T, Op><<<grid, kEwThreads, 0, st>>>((const T*)in, (T*)out, n);
   } else {
     const int grid = grid_for(n, kEwThreads * kEwUnroll, kEwBlocksPerSM);

@@ -228,9 +228,9 @@ static ag_status launch_filter_t(FilterParams& p, cudaStream_t st) {
   p.status = ws->tile_status;
   AG_CUDA_TRY(cudaMemsetAsync(p.status, 0, ((size_t)p.n_tiles + 1) * sizeof(unsigned long long), st));
   if (p.out_valid) AG_CUDA_TRY(cudaMemsetAsync(p.out_valid, 0, (size_t)((p.capacity + 31) >> 5) * 4, st));
-  const int grid = grid_for(p.n_tiles, kFWarps, kFBlocksPerSM);
-  if (p.out_valid) filter_kernel<V, kMode, true><<<grid, kFThreads, 0, st>>>(p);
-  else filter_kernel<V, kMode, false><<<grid, kFThreads, 0, st>>>(p);
+  const int64_t blocks_needed = (p.n_tiles + kFWarps - 1) / kFWarps;
+  if (p.out_valid) filter_kernel<V, kMode, true><<<grid_one_wave(filter_kernel<V, kMode, true>, kFThreads, blocks_needed), kFThreads, 0, st>>>(p);
+  else filter_kernel<V, kMode, false><<<grid_one_wave(filter_kernel<V, kMode, false>, kFThreads, blocks_needed), kFThreads, 0, st>>>(p);
   return check_launch("filter_kernel");
 }
 
@@ -358,7 +358,7 @@ static ag_status launch_fused_t(const void* vals, const void* scalar_host, int64
   const int64_t n_tiles = (n + kFTileRows - 1) / kFTileRows;
   AG_TRY(ensure_tile_status(ws, (size_t)n_tiles + 1, st));
   AG_CUDA_TRY(cudaMemsetAsync(ws->tile_status, 0, ((size_t)n_tiles + 1) * sizeof(unsigned long long), st));
-  const int grid = grid_for(n_tiles, kFWarps, 2);
+  const int grid = grid_one_wave(fused_cmp_filter_kernel<T, Cmp>, kFThreads, (n_tiles + kFWarps - 1) / kFWarps);
   fused_cmp_filter_kernel<T, Cmp><<<grid, kFThreads, 0, st>>>((const T*)vals, *(const T*)scalar_host, n, (T*)out, capacity,
                                                              ws->tile_status, (long long*)d_out_len, n_tiles);
   return check_launch("fused_cmp_filter_kernel");

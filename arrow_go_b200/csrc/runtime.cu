@@ -163,6 +163,21 @@ void release_call_stream(cudaStream_t st) {
   g_rt.free_streams.push_back(st);
 }
 
+// Resident blocks per SM for a kernel (cudaOccupancyMaxActiveBlocksPerMultiprocessor), cached per
+// entry point.  Persistent / grid-stride kernels size their grid as SMs x this, so the whole
+// grid is one wave and no tail wave runs at partial occupancy.
+int blocks_per_sm(const void* kernel, int threads) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, int> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(kernel);
+  if (it != cache.end()) return it->second;
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, 0) != cudaSuccess || n < 1) { cudaGetLastError(); n = 1; }
+  cache[kernel] = n;
+  return n;
+}
+
 ag_status dev_alloc_async(void** p, size_t nbytes, cudaStream_t s) {
   if (nbytes == 0) nbytes = 16;
   AG_CUDA_TRY(cudaMallocAsync(p, nbytes, s));

@@ -113,12 +113,12 @@ take_kernel(const TakeParams p) {
 
 template <typename V>
 static ag_status launch_take_v(int idx_width, const TakeParams& p, cudaStream_t st) {
-  const int grid = grid_for(p.n, kTkThreads * kTkUnroll, kTkBlocksPerSM);
+  const int64_t need = (p.n + kTkThreads * kTkUnroll - 1) / (kTkThreads * kTkUnroll);
   switch (idx_width) {
-    case 8: take_kernel<V, uint8_t><<<grid, kTkThreads, 0, st>>>(p); break;
-    case 16: take_kernel<V, uint16_t><<<grid, kTkThreads, 0, st>>>(p); break;
-    case 32: take_kernel<V, uint32_t><<<grid, kTkThreads, 0, st>>>(p); break;
-    case 64: take_kernel<V, unsigned long long><<<grid, kTkThreads, 0, st>>>(p); break;
+    case 8: take_kernel<V, uint8_t><<<grid_one_wave(take_kernel<V, uint8_t>, kTkThreads, need), kTkThreads, 0, st>>>(p); break;
+    case 16: take_kernel<V, uint16_t><<<grid_one_wave(take_kernel<V, uint16_t>, kTkThreads, need), kTkThreads, 0, st>>>(p); break;
+    case 32: take_kernel<V, uint32_t><<<grid_one_wave(take_kernel<V, uint32_t>, kTkThreads, need), kTkThreads, 0, st>>>(p); break;
+    case 64: take_kernel<V, unsigned long long><<<grid_one_wave(take_kernel<V, unsigned long long>, kTkThreads, need), kTkThreads, 0, st>>>(p); break;
     default: AG_FAIL(AG_ERR_INDEX, "take: invalid indices byte width");  // vector_selection.go:1157
   }
   return check_launch("take_kernel");
