@@ -626,6 +626,51 @@ ag_status arith_checked_dev(int type, int8_t op, int shape, const void* l, const
   }
 }
 
+// AbsoluteValueChecked / NegateChecked on signed integers (base_arithmetic.go:295-340): ScalarUnary,
+// i.e. every slot; v == MinInt -> errOverflow.
+template <typename ST, bool kAbs>
+__global__ void __launch_bounds__(kEwThreads)
+unary_checked_kernel(const ST* __restrict__ in, ST* __restrict__ out, int64_t n, long long* __restrict__ first_bad) {
+  using U = typename std::make_unsigned<ST>::type;
+  constexpr ST tmin = (ST)((U)1 << (sizeof(ST) * 8 - 1));
+  const int64_t stride = (int64_t)gridDim.x * kEwThreads;
+  long long my_bad = AG_NO_ERROR_POS;
+  for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < n; i += stride) {
+    const ST v = in[i];
+    if (v == tmin && (long long)i < my_bad) my_bad = (long long)i;
+    out[i] = kAbs ? UAbs::apply<ST, ST>(v) : UNeg::apply<ST, ST>(v);
+  }
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) {
+    const long long o = __shfl_xor_sync(0xffffffffu, my_bad, m);
+    my_bad = o < my_bad ? o : my_bad;
+  }
+  if ((threadIdx.x & 31) == 0 && my_bad != AG_NO_ERROR_POS) atomicMin(first_bad, my_bad);
+}
+
+template <typename ST>
+static ag_status launch_unary_checked(int8_t op, const void* in, void* out, int64_t n, int64_t* d_first_bad, cudaStream_t st) {
+  const int64_t need = (n + kEwThreads * kEwUnroll - 1) / (kEwThreads * kEwUnroll);
+  if (op == AG_OP_ABS_CHECKED)
+    unary_checked_kernel<ST, true><<<grid_one_wave(unary_checked_kernel<ST, true>, kEwThreads, need), kEwThreads, 0, st>>>((const ST*)in, (ST*)out, n, (long long*)d_first_bad);
+  else
+    unary_checked_kernel<ST, false><<<grid_one_wave(unary_checked_kernel<ST, false>, kEwThreads, need), kEwThreads, 0, st>>>((const ST*)in, (ST*)out, n, (long long*)d_first_bad);
+  return check_launch("unary_checked_kernel");
+}
+
+ag_status arith_unary_checked_dev(int type, int8_t op, const void* in, void* out, int64_t n, int64_t* d_first_bad, cudaStream_t st) {
+  if (op != AG_OP_ABS_CHECKED && op != AG_OP_NEGATE_CHECKED) AG_FAIL(AG_ERR_NOT_IMPLEMENTED, "arith_unary_checked: op %d", (int)op);
+  if (n < 0) AG_FAIL(AG_ERR_INVALID, "arith: negative length");
+  if (n == 0) return AG_OK;
+  switch (type) {
+    case AG_TYPE_INT8: return launch_unary_checked<int8_t>(op, in, out, n, d_first_bad, st);
+    case AG_TYPE_INT16: return launch_unary_checked<int16_t>(op, in, out, n, d_first_bad, st);
+    case AG_TYPE_INT32: return launch_unary_checked<int32_t>(op, in, out, n, d_first_bad, st);
+    case AG_TYPE_INT64: return launch_unary_checked<long long>(op, in, out, n, d_first_bad, st);
+    default: return arith_unary_same_dev(type, op, in, out, n, st);  // unsigned / floating: cannot overflow
+  }
+}
+
 __global__ void reset_error_word_kernel(long long* w) { *w = AG_NO_ERROR_POS; }
 
 ag_status error_word_reset(int64_t* d_word, cudaStream_t st) {
@@ -662,6 +707,11 @@ ag_status ag_arith_checked_dev(int type, int8_t op, int shape, const void* l, co
   AG_TRY(ensure_init());
   if (!d_first_bad) AG_FAIL(AG_ERR_INVALID, "arith_checked: NULL error word");
   return arith_checked_dev(type, op, shape, l, lvalid, loff, r, rvalid, roff, out, n, d_first_bad, resolve_stream(s));
+}
+ag_status ag_arith_unary_checked_dev(int type, int8_t op, const void* in, void* out, int64_t n, int64_t* d_first_bad, ag_stream_t s) {
+  AG_TRY(ensure_init());
+  if (!d_first_bad) AG_FAIL(AG_ERR_INVALID, "arith_unary_checked: NULL error word");
+  return arith_unary_checked_dev(type, op, in, out, n, d_first_bad, resolve_stream(s));
 }
 ag_status ag_error_word_reset_dev(int64_t* d_word, ag_stream_t s) {
   AG_TRY(ensure_init());

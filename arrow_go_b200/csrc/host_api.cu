@@ -26,6 +26,7 @@ ag_status arith_unary_diff_dev(int itype, int otype, int8_t op, const void* in, 
 ag_status arith_checked_dev(int type, int8_t op, int shape, const void* l, const uint8_t* lvalid, int64_t loff,
                             const void* r, const uint8_t* rvalid, int64_t roff, void* out, int64_t n, int64_t* d_first_bad, cudaStream_t st);
 ag_status error_word_reset(int64_t* d_word, cudaStream_t st);
+ag_status arith_unary_checked_dev(int type, int8_t op, const void* in, void* out, int64_t n, int64_t* d_first_bad, cudaStream_t st);
 ag_status compare_dev(int type, int cmp, int shape, const void* l, const void* r, uint8_t* out, int64_t n, int off, cudaStream_t st);
 ag_status bitmap_op_dev(int bitop, const uint8_t* l, int64_t loff, const uint8_t* r, int64_t roff, uint8_t* out, int64_t ooff, int64_t n, cudaStream_t st);
 ag_status bitmap_copy_dev(const uint8_t* src, int64_t soff, int64_t n, uint8_t* dst, int64_t doff, bool invert, cudaStream_t st);
@@ -264,6 +265,30 @@ ag_status ag_arith_checked(int type, int8_t op, int shape, const void* l, const 
     if (op == AG_OP_DIV || op == AG_OP_DIV_CHECKED) AG_FAIL(AG_ERR_INVALID, "divide by zero");  // errDivByZero, base_arithmetic.go:139
     AG_FAIL(AG_ERR_INVALID, "overflow");                                                        // errOverflow,  base_arithmetic.go:138
   }
+  return AG_OK;
+}
+
+ag_status ag_arith_unary_checked(int type, int8_t op, const void* in, void* out, int64_t n, int64_t* first_bad) {
+  AG_TRY(ensure_init());
+  if (first_bad) *first_bad = AG_NO_ERROR_POS;
+  const int w = type_width(type);
+  if (w == 0) AG_FAIL(AG_ERR_TYPE, "arith: unsupported type id %d", type);
+  if (n < 0) AG_FAIL(AG_ERR_INVALID, "arith: negative length");
+  if (n == 0) return AG_OK;
+  if (!in || !out) AG_FAIL(AG_ERR_INVALID, "arith: NULL operand");
+  CallStream cs; AG_TRY(cs.acquire());
+  Temps t(cs);
+  void *din, *dout; int64_t* d_bad;
+  AG_TRY(t.alloc(&din, (size_t)n * w)); AG_TRY(t.alloc(&dout, (size_t)n * w)); AG_TRY(t.alloc_t(&d_bad, sizeof(int64_t)));
+  AG_TRY(h2d(din, in, (size_t)n * w, cs));
+  AG_TRY(error_word_reset(d_bad, cs));
+  AG_TRY(arith_unary_checked_dev(type, op, din, dout, n, d_bad, cs));
+  int64_t bad = AG_NO_ERROR_POS;
+  AG_TRY(d2h(&bad, d_bad, sizeof(bad), cs));
+  AG_TRY(d2h(out, dout, (size_t)n * w, cs));
+  AG_TRY(sync(cs));
+  if (first_bad) *first_bad = bad;
+  if (bad != AG_NO_ERROR_POS) AG_FAIL(AG_ERR_INVALID, "overflow");
   return AG_OK;
 }
 

@@ -6,6 +6,8 @@
 // batch" residency (SURVEY.md §7 hard-part 2).
 #include "common.cuh"
 
+#include <ctype.h>
+#include <sched.h>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -256,13 +258,57 @@ const char* ag_version(void) { return "arrowgpu 0.1 (sm_100a)"; }
 uint64_t ag_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 // ---- pinned host memory ---------------------------------------------------------
+// CPUs of the NUMA node the GPU hangs off (sysfs); empty when unknown.  Pinned buffers are
+// allocated and first-touched from one of those CPUs so DMA does not cross the socket link.
+static bool gpu_node_cpus(cpu_set_t* set) {
+  static int state = 0;  // 0 unknown, 1 have set, -1 unavailable
+  static cpu_set_t cached;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  if (state == 0) {
+    state = -1;
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), g_rt.device) == cudaSuccess) {
+      for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+      char path[128];
+      snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+      int node = -1;
+      if (FILE* f = fopen(path, "r")) { if (fscanf(f, "%d", &node) != 1) node = -1; fclose(f); }
+      if (node >= 0) {
+        snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+        if (FILE* f = fopen(path, "r")) {
+          CPU_ZERO(&cached);
+          int a, b; char sep;
+          bool any = false;
+          while (fscanf(f, "%d", &a) == 1) {
+            b = a;
+            if (fscanf(f, "%c", &sep) == 1 && sep == '-') { if (fscanf(f, "%d", &b) != 1) b = a; if (fscanf(f, "%c", &sep) != 1) sep = 0; }
+            for (int c = a; c <= b && c < CPU_SETSIZE; ++c) { CPU_SET(c, &cached); any = true; }
+            if (sep != ',') break;
+          }
+          fclose(f);
+          if (any) state = 1;
+        }
+      }
+    } else {
+      cudaGetLastError();
+    }
+  }
+  if (state == 1) { *set = cached; return true; }
+  return false;
+}
+
 ag_status ag_host_alloc(void** ptr, size_t nbytes) {
   if (!ptr) AG_FAIL(AG_ERR_INVALID, "ag_host_alloc: NULL argument");
   AG_TRY(ensure_init());
   size_t sz = nbytes ? ((nbytes + 63) & ~(size_t)63) : 64;
+  cpu_set_t node_cpus, saved;
+  const bool pin = gpu_node_cpus(&node_cpus) && sched_getaffinity(0, sizeof(saved), &saved) == 0 &&
+                   sched_setaffinity(0, sizeof(node_cpus), &node_cpus) == 0;
   cudaError_t e = cudaHostAlloc(ptr, sz, cudaHostAllocDefault);  // page aligned >= 64 B
+  if (e == cudaSuccess) memset(*ptr, 0, sz);                     // zero-initialised like GoAllocator / calloc
+  if (pin) sched_setaffinity(0, sizeof(saved), &saved);
   if (e != cudaSuccess) { *ptr = nullptr; return cuda_fail(e, "cudaHostAlloc", __FILE__, __LINE__); }
-  memset(*ptr, 0, sz);
   return AG_OK;
 }
 

@@ -660,6 +660,14 @@ exec::ArrayKernelExec ArithCheckedExec(int8_t op) {
   };
 }
 
+// AbsoluteValueChecked / NegateChecked (base_arithmetic.go:295-340): every slot, MinInt -> "overflow"
+exec::ArrayKernelExec ArithUnaryCheckedExec(int8_t op) {
+  return [op](KernelCtx* ctx, const ExecSpan& batch, ExecResult* out) -> Status {
+    NATIVE(ag_arith_unary_checked_dev((int)out->type, op, ValuesPtr(batch.values[0].array), ValuesPtr(out), batch.len, ctx->error_word, nullptr));
+    return Status::OK();
+  };
+}
+
 exec::ArrayKernelExec ArithUnaryExec(int8_t op) {
   return [op](KernelCtx*, const ExecSpan& batch, ExecResult* out) -> Status {
     NATIVE(ag_arith_unary_same_dev((int)out->type, op, ValuesPtr(batch.values[0].array), ValuesPtr(out), batch.len, nullptr));
@@ -713,24 +721,79 @@ exec::ArrayKernelExec BoolBinaryExec(int bitop) {
   };
 }
 
-// Kleene and / or / and_not, array ⊕ array (scalar_boolean.go:29-65 computeKleene and callers)
+// Kleene and / or / and_not (scalar_boolean.go:92-334): array ⊕ array through computeKleene
+// (:29-65); scalar operands through the CallScalarLeft tables (:109-141, :186-221, :296-330) with
+// CallScalarRight = commutative swap (types.go:80-83), and_not's = and_kleene with the scalar
+// inverted (:332-334).
 exec::ArrayKernelExec KleeneExec(int kop, int plain_bitop) {
   return [kop, plain_bitop](KernelCtx*, const ExecSpan& batch, ExecResult* out) -> Status {
+    if (batch.len == 0) return Status::OK();  // SimpleBinary, types.go:91-93
     const ExecValue &a = batch.values[0], &b = batch.values[1];
-    if (!a.IsArray() || !b.IsArray()) return Status::NotImplemented("Kleene kernels with a scalar operand are not accelerated yet");
-    ArraySpan l = a.array, r = b.array;
-    int64_t ln = 0, rn = 0;
-    RETURN_NOT_OK(l.UpdateNullCount(&ln));
-    RETURN_NOT_OK(r.UpdateNullCount(&rn));
-    if (ln == 0 && rn == 0) {  // :94-98
-      NATIVE(ag_bitmap_set_dev(out->buffers[0].buf, out->offset, out->len, 1, nullptr));
-      out->nulls = 0;
-      NATIVE(ag_bitmap_op_dev(plain_bitop, l.buffers[1].buf, l.offset, r.buffers[1].buf, r.offset, out->buffers[1].buf, out->offset, batch.len, nullptr));
+    uint8_t* ov = out->buffers[0].buf;
+    uint8_t* od = out->buffers[1].buf;
+    const int64_t oo = out->offset, n = batch.len;
+    if (a.IsArray() && b.IsArray()) {
+      ArraySpan l = a.array, r = b.array;
+      int64_t ln = 0, rn = 0;
+      RETURN_NOT_OK(l.UpdateNullCount(&ln));
+      RETURN_NOT_OK(r.UpdateNullCount(&rn));
+      if (ln == 0 && rn == 0) {
+        NATIVE(ag_bitmap_set_dev(ov, oo, n, 1, nullptr));
+        out->nulls = 0;
+        NATIVE(ag_bitmap_op_dev(plain_bitop, l.buffers[1].buf, l.offset, r.buffers[1].buf, r.offset, od, oo, n, nullptr));
+        return Status::OK();
+      }
+      NATIVE(ag_kleene_dev(kop, ln ? l.buffers[0].buf : nullptr, l.buffers[1].buf, l.offset, rn ? r.buffers[0].buf : nullptr, r.buffers[1].buf, r.offset,
+                           ov, od, oo, n, nullptr));
+      out->nulls = kUnknownNullCount;
       return Status::OK();
     }
-    NATIVE(ag_kleene_dev(kop, ln ? l.buffers[0].buf : nullptr, l.buffers[1].buf, l.offset, rn ? r.buffers[0].buf : nullptr, r.buffers[1].buf, r.offset,
-                         out->buffers[0].buf, out->buffers[1].buf, out->offset, batch.len, nullptr));
+    // one scalar operand.  Reduce to "scalar on the left" of a (possibly different) kernel.
+    const bool scalar_left = a.IsScalar();
+    const Scalar* sc = scalar_left ? a.scalar : b.scalar;
+    ArraySpan arr = scalar_left ? b.array : a.array;
+    bool s_valid = sc->valid, s_val = sc->value[0] != 0;
+    int op = kop;  // which CallScalarLeft table to use
+    if (kop == AG_KLEENE_ANDNOT && !scalar_left) { op = AG_KLEENE_AND; s_val = !s_val; }  // :332-334 (invertScalar keeps nulls)
+    int64_t an = 0;
+    RETURN_NOT_OK(arr.UpdateNullCount(&an));
+    const uint8_t* av = arr.buffers[0].buf;
+    const uint8_t* ad = arr.buffers[1].buf;
+    const int64_t ao = arr.offset;
+    auto all_valid = [&]() -> Status { NATIVE(ag_bitmap_set_dev(ov, oo, n, 1, nullptr)); out->nulls = 0; return Status::OK(); };
+    auto copy_valid_from_arr = [&]() -> Status {
+      if (an == 0) return all_valid();
+      NATIVE(ag_bitmap_copy_dev(av, ao, n, ov, oo, nullptr));
+      out->nulls = kUnknownNullCount;
+      return Status::OK();
+    };
     out->nulls = kUnknownNullCount;
+    const bool s_true = s_valid && s_val, s_false = s_valid && !s_val;
+    if (op == AG_KLEENE_AND) {          // KleeneAndOpKernel.CallScalarLeft :109-141
+      if (s_false) { RETURN_NOT_OK(all_valid()); NATIVE(ag_bitmap_set_dev(od, oo, n, 0, nullptr)); }
+      else if (s_true) { RETURN_NOT_OK(copy_valid_from_arr()); NATIVE(ag_bitmap_copy_dev(ad, ao, n, od, oo, nullptr)); }
+      else {  // null scalar: valid iff right is (valid and) false
+        if (an == 0) NATIVE(ag_bitmap_invert_dev(ad, ao, n, ov, oo, nullptr));
+        else NATIVE(ag_bitmap_op_dev(AG_BITOP_ANDNOT, av, ao, ad, ao, ov, oo, n, nullptr));
+        NATIVE(ag_bitmap_copy_dev(ad, ao, n, od, oo, nullptr));
+      }
+    } else if (op == AG_KLEENE_OR) {    // KleeneOrOpKernel.CallScalarLeft :186-221
+      if (s_true) { RETURN_NOT_OK(all_valid()); NATIVE(ag_bitmap_set_dev(od, oo, n, 1, nullptr)); }
+      else if (s_false) { RETURN_NOT_OK(copy_valid_from_arr()); NATIVE(ag_bitmap_copy_dev(ad, ao, n, od, oo, nullptr)); }
+      else {  // null scalar: valid iff right is (valid and) true
+        if (an == 0) NATIVE(ag_bitmap_copy_dev(ad, ao, n, ov, oo, nullptr));
+        else NATIVE(ag_bitmap_op_dev(AG_BITOP_AND, av, ao, ad, ao, ov, oo, n, nullptr));
+        NATIVE(ag_bitmap_copy_dev(ad, ao, n, od, oo, nullptr));
+      }
+    } else {                            // KleeneAndNotOpKernel.CallScalarLeft :296-330 (scalar AND NOT array)
+      if (s_false) { RETURN_NOT_OK(all_valid()); NATIVE(ag_bitmap_set_dev(od, oo, n, 0, nullptr)); }
+      else if (s_true) { RETURN_NOT_OK(copy_valid_from_arr()); NATIVE(ag_bitmap_invert_dev(ad, ao, n, od, oo, nullptr)); }
+      else {  // null scalar: valid iff right is (valid and) true
+        if (an == 0) NATIVE(ag_bitmap_copy_dev(ad, ao, n, ov, oo, nullptr));
+        else NATIVE(ag_bitmap_op_dev(AG_BITOP_AND, av, ao, ad, ao, ov, oo, n, nullptr));
+        NATIVE(ag_bitmap_invert_dev(ad, ao, n, od, oo, nullptr));
+      }
+    }
     return Status::OK();
   };
 }
@@ -871,6 +934,20 @@ std::shared_ptr<ScalarFunction> MakeArithUnary(const std::string& name, int8_t o
   return fn;
 }
 
+std::shared_ptr<ScalarFunction> MakeArithUnaryChecked(const std::string& name, int8_t op, bool signed_only) {
+  auto fn = std::make_shared<ScalarFunction>(name, 1);
+  for (Type t : kNumericTypes) {
+    if (signed_only && !IsSignedInteger(t) && !IsFloating(t)) continue;  // GetArithmeticUnarySignedKernels, arithmetic.go:839-840
+    exec::ScalarKernel k;
+    k.in_types = {t};
+    k.out_type = FirstType;
+    if (IsSignedInteger(t)) { k.exec = ArithUnaryCheckedExec(op); k.can_fail = true; k.fail_message = "overflow"; }
+    else k.exec = ArithUnaryExec(op);
+    fn->AddKernel(std::move(k));
+  }
+  return fn;
+}
+
 std::shared_ptr<ScalarFunction> MakeCompare(const std::string& name, int cmp) {  // CompareKernels, scalar_comparisons.go:654-716
   auto fn = std::make_shared<ScalarFunction>(name, 2);
   for (Type t : kNumericTypes) {
@@ -916,6 +993,8 @@ FunctionRegistry* GetFunctionRegistry() {
     reg->AddFunction(MakeArithUnary("abs_unchecked", AG_OP_ABS), false);
     reg->AddFunction(MakeArithUnary("negate_unchecked", AG_OP_NEGATE), false);
     reg->AddFunction(MakeArithUnary("sign", AG_OP_SIGN), false);
+    reg->AddFunction(MakeArithUnaryChecked("abs", AG_OP_ABS_CHECKED, false), false);       // arithmetic.go:822-823
+    reg->AddFunction(MakeArithUnaryChecked("negate", AG_OP_NEGATE_CHECKED, true), false);  // arithmetic.go:839-846
     // scalar_compare.go:102-153
     reg->AddFunction(MakeCompare("equal", AG_CMP_EQ), false);
     reg->AddFunction(MakeCompare("not_equal", AG_CMP_NE), false);

@@ -228,6 +228,12 @@ ag_status ag_arith_checked(int type, int8_t op, int shape,
                            const void* l, const uint8_t* lvalid, int64_t loff,
                            const void* r, const uint8_t* rvalid, int64_t roff,
                            void* out, int64_t n, int64_t* first_bad);
+/* abs / negate (checked) on signed integers: AbsoluteValueChecked / NegateChecked,
+ * base_arithmetic.go:295-340 under ScalarUnary (EVERY slot, null or not): a slot equal to
+ * MinInt gives AG_ERR_INVALID "overflow"; other slots as the unchecked kernels.  Unsigned and
+ * floating types never fail (they behave like ag_arith_unary_same). */
+ag_status ag_arith_unary_checked(int type, int8_t op, const void* in, void* out, int64_t n, int64_t* first_bad);
+ag_status ag_arith_unary_checked_dev(int type, int8_t op, const void* d_in, void* d_out, int64_t n, int64_t* d_first_bad, ag_stream_t s);
 /* Device flavour: *d_first_bad must be initialised to AG_NO_ERROR_POS by the caller
  * (ag_dev_memset is not enough: use ag_error_word_reset_dev); it is only lowered. */
 ag_status ag_arith_checked_dev(int type, int8_t op, int shape,

@@ -320,6 +320,29 @@ int ref_arith_checked(int type, int op, int shape,
   return bad == REF_NO_ERROR_POS ? REF_OK : REF_ERR_INVALID;
 }
 
+/* AbsoluteValueChecked / NegateChecked on signed integers: K/base_arithmetic.go:295-340 under
+ * ScalarUnary (every slot): v == MinInt -> errOverflow; otherwise as the unchecked kernels. */
+int ref_arith_unary_checked(int type, int op, const void* in, void* out, int64_t n, int64_t* first_bad) {
+  int64_t bad = REF_NO_ERROR_POS;
+  if (first_bad) *first_bad = bad;
+  if (op != OP_ABS_C && op != OP_NEG_C) return REF_ERR_NOT_IMPLEMENTED;
+#define UC(ST, TMIN)                                                                    \
+  do { const ST* I = (const ST*)in;                                                     \
+       for (int64_t i = 0; i < n; ++i) if (I[i] == (TMIN) && i < bad) bad = i; } while (0)
+  switch (type) {
+    case T_I8: UC(int8_t, INT8_MIN); break;
+    case T_I16: UC(int16_t, INT16_MIN); break;
+    case T_I32: UC(int32_t, INT32_MIN); break;
+    case T_I64: UC(int64_t, INT64_MIN); break;
+    default: break;
+  }
+#undef UC
+  const int rc = ref_arith_unary_same(type, op, in, out, n);
+  if (rc != REF_OK) return rc;
+  if (first_bad) *first_bad = bad;
+  return bad == REF_NO_ERROR_POS ? REF_OK : REF_ERR_INVALID;
+}
+
 /* ====================================================================================== *
  * Comparisons: K/_lib/scalar_comparison.cc:63-206 (prefix bits up to the next byte boundary,
  * 32-wide batches packed LSB-first, tail bits), driver K/scalar_comparisons.go:199-218,

@@ -45,6 +45,8 @@ int ref_arith_checked(int type, int op, int shape,
                       const void* r, const uint8_t* rvalid, int64_t roff,
                       void* out, int64_t n, int64_t* first_bad);
 
+int ref_arith_unary_checked(int type, int op, const void* in, void* out, int64_t n, int64_t* first_bad);
+
 /* comparisons -> bitmap */
 int ref_compare(int type, int cmp, int shape, const void* l, const void* r, uint8_t* out, int64_t n, int offset);
 

@@ -49,6 +49,7 @@ def cpu():
         lib.ref_arith_unary_same.argtypes = [C.c_int, C.c_int, c_p, c_p, i64]
         lib.ref_arith_unary_diff.argtypes = [C.c_int, C.c_int, C.c_int, c_p, c_p, i64]
         lib.ref_arith_checked.argtypes = [C.c_int, C.c_int, C.c_int, c_p, c_p, i64, c_p, c_p, i64, c_p, i64, C.POINTER(i64)]
+        lib.ref_arith_unary_checked.argtypes = [C.c_int, C.c_int, c_p, c_p, i64, C.POINTER(i64)]
         lib.ref_compare.argtypes = [C.c_int, C.c_int, C.c_int, c_p, c_p, c_p, i64, C.c_int]
         lib.ref_bitmap_op.argtypes = [C.c_int, c_p, i64, c_p, i64, c_p, i64, i64]
         lib.ref_bitmap_copy.restype = None

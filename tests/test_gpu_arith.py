@@ -188,3 +188,27 @@ def test_add_f64_100m_rows_properties(ag):
     want = np.empty(w)
     assert oracle.cpu().ref_arith_binary(N.FLOAT64, N.OP_ADD, N.SHAPE_AA, ptr(ha), ptr(hb), ptr(want), w) == 0
     assert o1.buf.to_numpy(np.float64, w, start * 8).tobytes() == want.tobytes()
+
+
+@pytest.mark.parametrize("type_id", ALL_TYPES, ids=lambda t: TYPE_NAME[t])
+def test_unary_checked_matches_oracle(ag, cpu, type_id):
+    """abs / negate (checked): MinInt anywhere -> "overflow" (base_arithmetic.go:295-340)."""
+    rng = np.random.default_rng(type_id + 900)
+    dt = NP_OF[type_id]
+    isf = type_id in (N.FLOAT32, N.FLOAT64)
+    for n in (1, 100, 4099, 70_001):
+        for plant in (False, True):
+            x = random_values(rng, type_id, n, small=True)
+            if plant and not isf:
+                x[n // 2] = np.iinfo(dt).min
+                x[n - 1] = np.iinfo(dt).min
+            for op in (N.OP_ABS_CHECKED, N.OP_NEGATE_CHECKED):
+                want = np.empty(n, dtype=dt); wb = C.c_int64()
+                wst = cpu.ref_arith_unary_checked(type_id, op, ptr(x), ptr(want), n, C.byref(wb))
+                got = np.empty(n, dtype=dt); gb = C.c_int64()
+                gst, msg = ag.call_status("ag_arith_unary_checked", type_id, op, ptr(x), ptr(got), n, C.byref(gb))
+                assert gst == wst and gb.value == wb.value, (TYPE_NAME[type_id], op, n, plant, msg)
+                if wst == 0:
+                    assert (same_float_class if isf else same_bits)(got, want)
+                else:
+                    assert msg == "overflow" and gb.value == n // 2

@@ -247,3 +247,38 @@ def test_math_sum():
     x = np.arange(100, dtype=np.float64)
     a = pc.Array.from_numpy(x, np.arange(100) % 3 != 0)
     assert pc.math.sum_float64(a.slice(7, 50)) == x[7:57].sum()
+
+
+def test_abs_negate_checked():
+    # "abs" / "negate" fail on MinInt (arithmetic.go:822-846); the _unchecked forms wrap
+    for t in (pc.INT8, pc.INT16, pc.INT32, pc.INT64):
+        mn = int(np.iinfo(pc.NP_OF[t]).min)
+        ok = pc.Array.from_pylist([3, -4, None, 0], t)
+        assert pc.CallFunction("abs", [ok]).to_pylist() == [3, 4, None, 0]
+        assert pc.CallFunction("negate", [ok]).to_pylist() == [-3, 4, None, 0]
+        bad = pc.Array.from_pylist([1, mn], t)
+        for fn in ("abs", "negate"):
+            with pytest.raises(pc.ArrowError) as e:
+                pc.CallFunction(fn, [bad])
+            assert e.value.sentinel == "ErrInvalid" and "overflow" in e.value.msg
+        assert pc.CallFunction("abs_unchecked", [bad]).to_pylist() == [1, mn]
+        assert pc.CallFunction("negate_unchecked", [bad]).to_pylist() == [-1, mn]
+    assert pc.CallFunction("abs", [pc.Array.from_pylist([1.5, -2.5, None], pc.FLOAT64)]).to_pylist() == [1.5, 2.5, None]
+    assert pc.CallFunction("abs", [pc.Array.from_pylist([7, 0], pc.UINT16)]).to_pylist() == [7, 0]
+    assert pc.CallFunction("sign", [pc.Array.from_pylist([-5, 0, 9, None], pc.INT32)]).to_pylist() == [-1, 0, 1, None]
+    with pytest.raises(pc.ArrowError):
+        pc.dispatch("negate", [pc.UINT32])  # negate (checked) has signed / floating kernels only
+
+
+def test_kleene_scalar_operands():
+    """Kleene kernels with a scalar on either side must equal the array ⊕ array result with the
+    scalar broadcast (scalar_bool_test.go:40-58 helper), for true / false / null scalars and arrays
+    with and without nulls."""
+    T, F, U = True, False, None
+    for arr in ([T, F, U, T, F, U, T, T, F], [T, F, T, T, F, F, T, T, F]):
+        a = pc.Array.from_pylist(arr, pc.BOOL)
+        for name in ("and_kleene", "or_kleene", "and_not_kleene"):
+            for sv in (T, F, U):
+                bcast = pc.Array.from_pylist([sv] * len(arr), pc.BOOL)
+                assert pc.CallFunction(name, [a, pc.Scalar(sv, pc.BOOL)]).to_pylist() == pc.CallFunction(name, [a, bcast]).to_pylist(), (name, sv, "right")
+                assert pc.CallFunction(name, [pc.Scalar(sv, pc.BOOL), a]).to_pylist() == pc.CallFunction(name, [bcast, a]).to_pylist(), (name, sv, "left")
