@@ -13,18 +13,17 @@
 // fetched only for emitted rows (predicated 8-byte loads; DRAM moves the touched 32-byte
 // sectors), so at low selectivity the kernel can move FEWER bytes than that figure.
 //
-// Single pass, WARP-granular decoupled look-back (no block barriers, no shared memory):
-//   * a tile is 1024 rows = one warp, one 32-bit mask word per lane; tiles are claimed with an
-//     atomic ticket (a tile only ever waits on tiles that are already running) and the next
-//     ticket is requested while the current tile's loads are in flight;
-//   * popcount per lane -> warp scan -> tile aggregate published in a 64-bit status word
+// Single pass, decoupled look-back over 32K-row BLOCK tiles:
+//   * phase 1 puts the tile's 1024 mask words in shared memory (bitmap mask: coalesced word
+//     loads; fused compare: the values are streamed once and __ballot_sync packs the predicate);
+//   * block scan of the word popcounts -> tile aggregate published in a 64-bit status word
 //     (2 flag bits + 62-bit count, one store => a reader never sees a flag without its value);
-//   * the warp looks back 32 tiles at a time until it meets an inclusive prefix; the other
-//     warps of the SM are in their load/store phases meanwhile, which is what hides the chain;
-//   * compaction is warp-cooperative: for each of the 32 words, lane j owns row 32k+j, so loads
-//     are coalesced; it stores to out[base_k + rank], rank = popc of the lower set bits, so the
-//     writes of one step are contiguous.  Sparse tiles load only the selected rows (DRAM moves
-//     the touched sectors); dense tiles load all 32 x 256 B rows;
+//     warp 0 looks back 32 tiles at a time until it meets an inclusive prefix.  The chain moves
+//     32 tiles per L2 round trip, so tiles must be large: 32 x 32768 rows per ~0.7 us;
+//   * phase 2 is warp-cooperative: for each word, lane j owns row 32k+j; the lanes whose bit is
+//     set load (8 words in flight per lane) and store to out[base_k + rank], rank = popc of the
+//     lower set bits, so the writes of one step are contiguous.  Only the sectors of selected
+//     rows are fetched;
 //   * output validity bits are compacted with __reduce_or_sync and merged into pre-zeroed
 //     words with at most two atomicOr per step.
 #include "common.cuh"
@@ -36,8 +35,9 @@ namespace ag {
 
 constexpr int kFThreads = 256;
 constexpr int kFWarps = kFThreads / 32;
-constexpr int kFTileRows = 1024;  // one WARP tile: 32 lanes x one 32-bit mask word
-constexpr int kFBlocksPerSM = 4;
+constexpr int kFTileRows = 32768;               // rows per BLOCK tile
+constexpr int kFTileWords = kFTileRows / 32;    // 1024 mask words per tile
+constexpr int kFWordsPerThread = kFTileWords / kFThreads;  // 4
 
 constexpr unsigned long long kFlagShift = 62;
 constexpr unsigned long long kFlagAgg = 1ull << kFlagShift;
@@ -55,7 +55,7 @@ struct FilterParams {
   const void* vals;          // element 0 of the values buffer (NULL in index mode)
   const uint8_t* vvalid;     // values validity (may be NULL)
   int64_t voff;
-  const uint8_t* mask;
+  const uint8_t* mask;       // NULL in fused-compare mode
   const uint8_t* mvalid;     // mask validity (may be NULL)
   int64_t moff;
   int64_t n;
@@ -63,15 +63,15 @@ struct FilterParams {
   void* out;
   uint32_t* out_valid;       // 4-byte aligned, pre-zeroed for ceil(capacity/32) words (may be NULL)
   int64_t capacity;          // rows the output buffers can hold
-  unsigned long long* status;  // [0] = tile ticket, [1..] = tile status words
+  unsigned long long* status;  // one status word per tile
   long long* out_len;
   int64_t n_tiles;
-  int dense_threshold;       // tiles emitting at least this many rows load their 1024 values coalesced
 };
 
-// Whole warp.  Returns the exclusive prefix of `tile` (rows emitted by all earlier tiles) and
+// One warp.  Returns the exclusive prefix of `tile` (rows emitted by all earlier tiles) and
 // publishes this tile's inclusive prefix.  One 64-bit word carries flag + count, so a reader
-// never sees a flag without its value.
+// never sees a flag without its value.  Throughput of the chain is 32 tiles per L2 round trip,
+// which is why tiles are 32K rows: 32 x 32768 rows / ~0.7 us >> the HBM rate of any width.
 __device__ __forceinline__ unsigned long long lookback(unsigned long long* st, int64_t tile, unsigned long long total, int lane) {
   if (tile == 0) {
     if (lane == 0) st_status(st, kFlagIncl | total);
@@ -104,140 +104,234 @@ __device__ __forceinline__ unsigned long long lookback(unsigned long long* st, i
   return running;
 }
 
-// Warp-wide exclusive scan of the per-lane counts + look-back.  Returns the global output slot
-// of this lane's first emitted row; *tile_total = rows the warp tile emits.
-__device__ __forceinline__ unsigned long long warp_tile_scan(unsigned cnt, unsigned long long* status, int64_t tile, int64_t n_tiles,
-                                                             long long* out_len, unsigned* tile_total_out) {
-  const int lane = threadIdx.x & 31;
-  unsigned incl = cnt;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += t;
-  }
-  const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-  const unsigned long long excl = lookback(status, tile, total, lane);
-  if (lane == 0 && tile == n_tiles - 1) *out_len = (long long)(excl + total);
-  *tile_total_out = total;
-  return excl + (incl - cnt);
-}
+struct FCmpNone { template <typename T> static __device__ __forceinline__ bool apply(T, T) { return false; } };
+struct FCmpEq { template <typename T> static __device__ __forceinline__ bool apply(T a, T b) { return a == b; } };
+struct FCmpNe { template <typename T> static __device__ __forceinline__ bool apply(T a, T b) { return a != b; } };
+struct FCmpGt { template <typename T> static __device__ __forceinline__ bool apply(T a, T b) { return a > b; } };
+struct FCmpGe { template <typename T> static __device__ __forceinline__ bool apply(T a, T b) { return a >= b; } };
+struct FCmpLt { template <typename T> static __device__ __forceinline__ bool apply(T a, T b) { return b > a; } };
+struct FCmpLe { template <typename T> static __device__ __forceinline__ bool apply(T a, T b) { return b >= a; } };
 
-// Warp tiles are claimed with an atomic ticket (a tile only waits on tiles that are already
-// running => forward progress without assuming co-residency); the ticket for the NEXT tile is
-// requested while the current tile's loads are in flight.
-__device__ __forceinline__ long long claim_tile(unsigned long long* ticket, int lane) {
-  unsigned long long t = 0;
-  if (lane == 0) t = atomicAdd(ticket, 1ull);
-  return (long long)__shfl_sync(0xffffffffu, t, 0);
-}
-
-// kMode 0: copy values of type V.  kMode 1: write row indices as V (GetTakeIndices).
-template <typename V, int kMode, bool kValidity>
+// kMode 0: copy values of type V selected by a bitmap mask.
+// kMode 1: write row indices as V (GetTakeIndices).
+// kMode 2: fused compare: the mask is Cmp(values[row], scalar); V is the arithmetic type.
+//
+// Tile assignment is STATIC (block b owns tiles b, b+G, ...): a tile only waits on lower tiles,
+// every block walks its tiles in increasing order and the grid is launched cooperatively as ONE
+// resident wave (cudaLaunchCooperativeKernel fails instead of deadlocking if it could not be).
+template <typename V, int kMode, bool kValidity, typename Cmp>
 __global__ void __launch_bounds__(kFThreads)
-filter_kernel(const FilterParams p) {
-  const int lane = threadIdx.x & 31;
-  const V* __restrict__ vals = reinterpret_cast<const V*>(p.vals) + (kMode == 0 ? p.voff : 0);
+filter_kernel(const FilterParams p, V scalar) {
+  __shared__ uint32_t s_emit[kFTileWords];
+  __shared__ uint32_t s_sel[kFTileWords];
+  __shared__ uint32_t s_base[kFTileWords];   // exclusive offset of each word inside the tile
+  __shared__ uint32_t s_warp_tot[kFWarps];
+  __shared__ unsigned long long s_tile_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const V* __restrict__ vals = reinterpret_cast<const V*>(p.vals) + (kMode != 1 ? p.voff : 0);
   V* __restrict__ out = reinterpret_cast<V*>(p.out);
   const int64_t m_lo = p.moff >> 3, m_hi = (p.moff + p.n + 7) >> 3;
   const long long cap_words = (p.capacity + 31) >> 5;
+  const uint64_t keep = (kMode == 2) ? l2_policy_evict_last() : 0;
 
-  long long tile = claim_tile(p.status, lane);
-  while (tile < p.n_tiles) {
-    const int64_t wrow0 = tile * kFTileRows;
-    const int64_t row0 = wrow0 + (int64_t)lane * 32;  // first row of this lane's mask word
-    uint32_t sel = 0, nul = 0;
-    if (row0 < p.n) {
-      const int64_t rem = p.n - row0;
-      const uint32_t range = rem >= 32 ? 0xffffffffu : bit_range_mask(0, (int)rem);
-      const uint32_t m = bitmap_load32(p.mask, p.moff + row0, m_lo, m_hi);
-      uint32_t mv = 0xffffffffu;
-      if (p.mvalid) mv = bitmap_load32(p.mvalid, p.moff + row0, m_lo, m_hi);
-      sel = m & mv & range;
-      if (p.emit_nulls) nul = ~mv & range;
-    }
-    const long long next_tile = claim_tile(p.status, lane);
-    const uint32_t emit = sel | nul;
-    unsigned tile_total;
-    const unsigned long long my_base = warp_tile_scan(__popc(emit), p.status + 1, tile, p.n_tiles, p.out_len, &tile_total);
-
-    if (tile_total != 0) {
-      const bool dense = kMode == 0 && (int)tile_total >= p.dense_threshold && wrow0 + kFTileRows <= p.n;
+  for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    const int64_t trow0 = tile * kFTileRows;
+    // ---- phase 1: the tile's 1024 mask words -> shared memory --------------------------------
+    if (kMode == 2) {
+      // Sub-tiles of 8 x kL x 32 rows; warp w owns kL x 32 rows of each; lane j holds rows 32k+j so
+      // every load is a coalesced 256-byte request and __ballot_sync packs word k.  kL = 32 (3
+      // resident blocks/SM) measured faster than kL = 16 (5 blocks/SM): more resident tiles push
+      // the not-yet-compacted tiles out of L2.  The loads carry an L2 evict-last policy: phase 2
+      // re-reads the selected rows from L2, not from HBM.
+      constexpr int kL = 32;                       // loads in flight per lane
+      constexpr int kSubRows = kFWarps * kL * 32;  // 4096
+#pragma unroll 1
+      for (int sub = 0; sub < kFTileRows / kSubRows; ++sub) {
+        const int64_t wrow0 = trow0 + (int64_t)sub * kSubRows + warp * (kL * 32);
+        V v[kL];
+        if (wrow0 + kL * 32 <= p.n) {
 #pragma unroll
-      for (int kb = 0; kb < 32; kb += 8) {
-        // phase 1: 8 independent loads in flight per lane (all 8 x 256 B rows when the tile is dense,
-        // only the selected rows' sectors when it is sparse)
-        V v[8];
-        uint32_t w_emit[8];
+          for (int k = 0; k < kL; ++k) v[k] = ld_l2_hint(vals + wrow0 + k * 32 + lane, keep);
+        } else {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          w_emit[u] = __shfl_sync(0xffffffffu, emit, kb + u);
-          const uint32_t w_sel = __shfl_sync(0xffffffffu, sel, kb + u);
-          v[u] = V(0);
-          if (kMode == 0) {
-            if (dense || ((w_sel >> lane) & 1)) v[u] = vals[wrow0 + (kb + u) * 32 + lane];
-            if (!((w_sel >> lane) & 1)) v[u] = V(0);
-          } else {
-            if ((w_sel >> lane) & 1) v[u] = (V)(wrow0 + (kb + u) * 32 + lane);
+          for (int k = 0; k < kL; ++k) {
+            const int64_t row = wrow0 + k * 32 + lane;
+            v[k] = (row < p.n) ? ld_l2_hint(vals + row, keep) : scalar;
           }
         }
-        // phase 2: compacting stores
+        __syncwarp();  // keep every load ahead of the first vote
+        uint32_t myword = 0;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          if (w_emit[u] == 0) continue;  // warp-uniform
-          const unsigned long long b = __shfl_sync(0xffffffffu, my_base, kb + u);
-          const bool e = (w_emit[u] >> lane) & 1;
-          const unsigned rank = __popc(w_emit[u] & ((1u << lane) - 1u));
-          const unsigned long long pos = b + rank;
-          if (e && (long long)pos < p.capacity) out[pos] = v[u];
-          if (kValidity) {
-            const uint32_t w_sel = __shfl_sync(0xffffffffu, sel, kb + u);
-            const int64_t row = wrow0 + (kb + u) * 32 + lane;
-            uint32_t vb = 0;
-            if (e && ((w_sel >> lane) & 1)) vb = (kMode == 0 && p.vvalid) ? (uint32_t)bit_is_set(p.vvalid, p.voff + row) : 1u;
-            const uint32_t pattern = __reduce_or_sync(0xffffffffu, vb << rank);  // rank < 32 whenever vb != 0
-            if (lane == 0 && pattern) {
-              const unsigned sh = (unsigned)(b & 31);
-              const unsigned long long wi = b >> 5;
-              if ((long long)wi < cap_words) atomicOr(p.out_valid + wi, pattern << sh);
-              if (sh && (pattern >> (32 - sh)) && (long long)(wi + 1) < cap_words) atomicOr(p.out_valid + wi + 1, pattern >> (32 - sh));
+        for (int k = 0; k < kL; ++k) {
+          const int64_t row = wrow0 + k * 32 + lane;
+          const uint32_t bits = __ballot_sync(0xffffffffu, row < p.n && Cmp::template apply<V>(v[k], scalar));
+          if (lane == k) myword = bits;
+        }
+        if (lane < kL) {
+          const int word = sub * (kSubRows / 32) + warp * kL + lane;
+          s_emit[word] = myword;
+          s_sel[word] = myword;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < kFWordsPerThread; ++k) {
+        const int word = k * kFThreads + threadIdx.x;  // coalesced mask reads
+        const int64_t row0 = trow0 + (int64_t)word * 32;
+        uint32_t sel = 0, nul = 0;
+        if (row0 < p.n) {
+          const int64_t rem = p.n - row0;
+          const uint32_t range = rem >= 32 ? 0xffffffffu : bit_range_mask(0, (int)rem);
+          const uint32_t m = bitmap_load32(p.mask, p.moff + row0, m_lo, m_hi);
+          uint32_t mv = 0xffffffffu;
+          if (p.mvalid) mv = bitmap_load32(p.mvalid, p.moff + row0, m_lo, m_hi);
+          sel = m & mv & range;
+          if (p.emit_nulls) nul = ~mv & range;
+        }
+        s_sel[word] = sel;
+        s_emit[word] = sel | nul;
+      }
+    }
+    __syncthreads();
+    // ---- block exclusive scan of the word popcounts (thread t owns words 4t..4t+3) ------------
+    uint32_t cnt[kFWordsPerThread];
+    uint32_t tsum = 0;
+#pragma unroll
+    for (int k = 0; k < kFWordsPerThread; ++k) { cnt[k] = __popc(s_emit[threadIdx.x * kFWordsPerThread + k]); tsum += cnt[k]; }
+    uint32_t incl = tsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_warp_tot[warp] = incl;
+    __syncthreads();
+    uint32_t warp_base = 0, tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < kFWarps; ++w) {
+      const uint32_t t = s_warp_tot[w];
+      if (w < warp) warp_base += t;
+      tile_total += t;
+    }
+    uint32_t run = warp_base + incl - tsum;
+#pragma unroll
+    for (int k = 0; k < kFWordsPerThread; ++k) { s_base[threadIdx.x * kFWordsPerThread + k] = run; run += cnt[k]; }
+    if (warp == 0) {
+      const unsigned long long excl = lookback(p.status, tile, tile_total, lane);
+      if (lane == 0) {
+        s_tile_base = excl;
+        if (tile == p.n_tiles - 1) *p.out_len = (long long)(excl + tile_total);
+      }
+    }
+    __syncthreads();
+    // ---- phase 2: compaction; warp w owns words w*128 .. w*128+127, 32 words at a time ----------
+    if (tile_total != 0) {
+      const unsigned long long tbase = s_tile_base;
+#pragma unroll 1
+      for (int g0 = warp * (kFTileWords / kFWarps); g0 < (warp + 1) * (kFTileWords / kFWarps); g0 += 32) {
+        const uint32_t my_emit = s_emit[g0 + lane];
+        const unsigned group_cnt = __reduce_add_sync(0xffffffffu, __popc(my_emit));
+        if (group_cnt == 0) continue;
+        if (group_cnt <= 256) {
+          // SPARSE group (<= 25 % selected): lane j walks the set bits of ITS word, so all 32 lanes
+          // have loads in flight (4 per lane) instead of the ~3 active lanes of a warp-wide step.
+          // Each lane's rows land in consecutive output slots; neighbouring lanes' runs are adjacent.
+          const uint32_t my_sel = s_sel[g0 + lane];
+          const int64_t wrow = trow0 + (int64_t)(g0 + lane) * 32;
+          unsigned long long pos = tbase + s_base[g0 + lane];
+          uint32_t bits = my_emit;
+          while (bits) {
+            int r[4];
+            V v[4];
+            int cnt = 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              r[u] = -1;
+              v[u] = V(0);
+              if (bits) {
+                r[u] = __ffs(bits) - 1;
+                bits &= bits - 1;
+                ++cnt;
+                if ((my_sel >> r[u]) & 1) v[u] = (kMode == 1) ? (V)(wrow + r[u]) : __ldcs(vals + wrow + r[u]);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (r[u] >= 0 && (long long)(pos + u) < p.capacity) {
+                out[pos + u] = v[u];
+                if (kValidity && ((my_sel >> r[u]) & 1)) {
+                  const bool vb = (kMode == 0 && p.vvalid) ? bit_is_set(p.vvalid, p.voff + wrow + r[u]) : true;
+                  if (vb) atomicOr(p.out_valid + ((pos + u) >> 5), 1u << ((pos + u) & 31));
+                }
+              }
+            }
+            pos += cnt;
+          }
+          continue;
+        }
+        // DENSE group: warp-wide steps, lane j owns row 32k+j (coalesced), 8 words in flight
+#pragma unroll 1
+        for (int j0 = g0; j0 < g0 + 32; j0 += 8) {
+          V v[8];
+          uint32_t w_emit[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            w_emit[u] = s_emit[j0 + u];
+            const uint32_t w_sel = s_sel[j0 + u];
+            const int64_t row = trow0 + (int64_t)(j0 + u) * 32 + lane;
+            v[u] = V(0);
+            if ((w_sel >> lane) & 1) v[u] = (kMode == 1) ? (V)row : __ldcs(vals + row);  // last use: evict-first
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            if (w_emit[u] == 0) continue;  // warp-uniform
+            const unsigned long long b = tbase + s_base[j0 + u];
+            const bool e = (w_emit[u] >> lane) & 1;
+            const unsigned rank = __popc(w_emit[u] & ((1u << lane) - 1u));
+            const unsigned long long pos = b + rank;
+            if (e && (long long)pos < p.capacity) out[pos] = v[u];
+            if (kValidity) {
+              const int64_t row = trow0 + (int64_t)(j0 + u) * 32 + lane;
+              uint32_t vb = 0;
+              if (e && ((s_sel[j0 + u] >> lane) & 1)) vb = (kMode == 0 && p.vvalid) ? (uint32_t)bit_is_set(p.vvalid, p.voff + row) : 1u;
+              const uint32_t pattern = __reduce_or_sync(0xffffffffu, vb << rank);  // rank < 32 whenever vb != 0
+              if (lane == 0 && pattern) {
+                const unsigned sh = (unsigned)(b & 31);
+                const unsigned long long wi = b >> 5;
+                if ((long long)wi < cap_words) atomicOr(p.out_valid + wi, pattern << sh);
+                if (sh && (pattern >> (32 - sh)) && (long long)(wi + 1) < cap_words) atomicOr(p.out_valid + wi + 1, pattern >> (32 - sh));
+              }
             }
           }
         }
       }
     }
-    tile = next_tile;
+    __syncthreads();  // shared arrays are rewritten by the next tile
   }
 }
 
-static int filter_dense_threshold() {
-  static int cached = -1;
-  if (cached < 0) {
-    const char* e = getenv("AG_FILTER_DENSE_THRESHOLD");
-    cached = e ? atoi(e) : 96;  // rows emitted per 1024-row tile above which coalesced loads win
-  }
-  return cached;
-}
-
-template <typename V, int kMode>
-static ag_status launch_filter_t(FilterParams& p, cudaStream_t st) {
+template <typename V, int kMode, typename Cmp>
+static ag_status launch_filter_t(FilterParams& p, V scalar, cudaStream_t st) {
   Workspace* ws;
   AG_TRY(get_workspace(st, &ws));
   p.n_tiles = (p.n + kFTileRows - 1) / kFTileRows;
-  p.dense_threshold = filter_dense_threshold();
-  AG_TRY(ensure_tile_status(ws, (size_t)p.n_tiles + 1, st));
+  AG_TRY(ensure_tile_status(ws, (size_t)p.n_tiles, st));
   p.status = ws->tile_status;
-  AG_CUDA_TRY(cudaMemsetAsync(p.status, 0, ((size_t)p.n_tiles + 1) * sizeof(unsigned long long), st));
+  AG_CUDA_TRY(cudaMemsetAsync(p.status, 0, (size_t)p.n_tiles * sizeof(unsigned long long), st));
   if (p.out_valid) AG_CUDA_TRY(cudaMemsetAsync(p.out_valid, 0, (size_t)((p.capacity + 31) >> 5) * 4, st));
-  const int64_t blocks_needed = (p.n_tiles + kFWarps - 1) / kFWarps;
-  if (p.out_valid) filter_kernel<V, kMode, true><<<grid_one_wave(filter_kernel<V, kMode, true>, kFThreads, blocks_needed), kFThreads, 0, st>>>(p);
-  else filter_kernel<V, kMode, false><<<grid_one_wave(filter_kernel<V, kMode, false>, kFThreads, blocks_needed), kFThreads, 0, st>>>(p);
+  void* args[] = {(void*)&p, (void*)&scalar};
+  if (p.out_valid)
+    AG_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)filter_kernel<V, kMode, true, Cmp>,
+                                            dim3(grid_one_wave(filter_kernel<V, kMode, true, Cmp>, kFThreads, p.n_tiles)), dim3(kFThreads), args, 0, st));
+  else
+    AG_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)filter_kernel<V, kMode, false, Cmp>,
+                                            dim3(grid_one_wave(filter_kernel<V, kMode, false, Cmp>, kFThreads, p.n_tiles)), dim3(kFThreads), args, 0, st));
   return check_launch("filter_kernel");
 }
 
 static ag_status check_filter_args(const FilterParams& p, const char* who) {
   if (p.n < 0 || p.moff < 0 || p.voff < 0 || p.capacity < 0) AG_FAIL(AG_ERR_INVALID, "%s: negative length or offset", who);
   if (!p.out_len) AG_FAIL(AG_ERR_INVALID, "%s: NULL out_len", who);
-  if (p.n > 0 && !p.mask) AG_FAIL(AG_ERR_INVALID, "%s: NULL mask", who);
   if (p.out_valid && (reinterpret_cast<uintptr_t>(p.out_valid) & 3)) AG_FAIL(AG_ERR_INVALID, "%s: out_valid must be 4-byte aligned", who);
   return AG_OK;
 }
@@ -252,6 +346,7 @@ ag_status filter_primitive_dev(int bit_width, const void* vals, const uint8_t* v
   p.out = out; p.out_valid = reinterpret_cast<uint32_t*>(out_valid); p.capacity = capacity;
   p.out_len = reinterpret_cast<long long*>(d_out_len);
   AG_TRY(check_filter_args(p, "filter"));
+  if (n > 0 && !mask) AG_FAIL(AG_ERR_INVALID, "filter: NULL mask");
   if (null_selection != AG_DROP_NULLS && null_selection != AG_EMIT_NULLS) AG_FAIL(AG_ERR_INVALID, "filter: bad null_selection %d", null_selection);
   if ((vvalid || p.emit_nulls) && !out_valid && capacity > 0)
     AG_FAIL(AG_ERR_INVALID, "filter: the output can contain nulls but no output validity buffer was given (vector_selection.go:473)");
@@ -265,10 +360,10 @@ ag_status filter_primitive_dev(int bit_width, const void* vals, const uint8_t* v
   }
   if (((uintptr_t)vals & am) || ((uintptr_t)out & am)) AG_FAIL(AG_ERR_INVALID, "filter: buffers not aligned to the element width");
   switch (bit_width) {
-    case 8: return launch_filter_t<uint8_t, 0>(p, st);
-    case 16: return launch_filter_t<uint16_t, 0>(p, st);
-    case 32: return launch_filter_t<uint32_t, 0>(p, st);
-    default: return launch_filter_t<unsigned long long, 0>(p, st);
+    case 8: return launch_filter_t<uint8_t, 0, FCmpNone>(p, (uint8_t)0, st);
+    case 16: return launch_filter_t<uint16_t, 0, FCmpNone>(p, (uint16_t)0, st);
+    case 32: return launch_filter_t<uint32_t, 0, FCmpNone>(p, 0u, st);
+    default: return launch_filter_t<unsigned long long, 0, FCmpNone>(p, 0ull, st);
   }
 }
 
@@ -281,99 +376,35 @@ ag_status take_indices_dev(int index_width, const uint8_t* mask, const uint8_t* 
   p.out = out_idx; p.out_valid = reinterpret_cast<uint32_t*>(out_valid); p.capacity = capacity;
   p.out_len = reinterpret_cast<long long*>(d_out_len);
   AG_TRY(check_filter_args(p, "take_indices"));
+  if (n > 0 && !mask) AG_FAIL(AG_ERR_INVALID, "take_indices: NULL mask");
   if (n == 0) { AG_CUDA_TRY(cudaMemsetAsync(d_out_len, 0, sizeof(int64_t), st)); return AG_OK; }
   if (index_width == 16) {
     if (n >= 65535) AG_FAIL(AG_ERR_INVALID, "take_indices: uint16 indices need n < 65535 (vector_selection.go:229-231)");
-    return launch_filter_t<uint16_t, 1>(p, st);
+    return launch_filter_t<uint16_t, 1, FCmpNone>(p, (uint16_t)0, st);
   }
   if (index_width == 32) {
     if (n >= 4294967295ll) AG_FAIL(AG_ERR_NOT_IMPLEMENTED, "take_indices: filter length exceeds UINT32_MAX (vector_selection.go:233-235)");
-    return launch_filter_t<uint32_t, 1>(p, st);
+    return launch_filter_t<uint32_t, 1, FCmpNone>(p, 0u, st);
   }
   AG_FAIL(AG_ERR_TYPE, "take_indices: index width must be 16 or 32");
 }
 
 // ---------------------------------------------------------------- fused compare + filter ----
-// Greater/…(values, scalar) -> Filter in ONE pass over `values` (config 3 of BASELINE.json):
-// no intermediate mask, 8 + 8s bytes/row.  A warp keeps its 1024 rows in registers (lane holds
-// rows 32k+lane, k = 0..31 — the layout both the ballot and the compaction loop want), so the
-// values are read from HBM exactly once: 32 coalesced 256-byte loads per warp, all issued
-// before the first vote.  Same result as compare_dev + filter_primitive_dev.
-struct FCmpEq { template <typename T> static __device__ __forceinline__ bool apply(T a, T b) { return a == b; } };
-struct FCmpNe { template <typename T> static __device__ __forceinline__ bool apply(T a, T b) { return a != b; } };
-struct FCmpGt { template <typename T> static __device__ __forceinline__ bool apply(T a, T b) { return a > b; } };
-struct FCmpGe { template <typename T> static __device__ __forceinline__ bool apply(T a, T b) { return a >= b; } };
-struct FCmpLt { template <typename T> static __device__ __forceinline__ bool apply(T a, T b) { return b > a; } };
-struct FCmpLe { template <typename T> static __device__ __forceinline__ bool apply(T a, T b) { return b >= a; } };
-
-template <typename T, typename Cmp>
-__global__ void __launch_bounds__(kFThreads)
-fused_cmp_filter_kernel(const T* __restrict__ vals, T scalar, int64_t n, T* __restrict__ out, int64_t capacity,
-                        unsigned long long* status, long long* out_len, int64_t n_tiles) {
-  const int lane = threadIdx.x & 31;
-  long long tile = claim_tile(status, lane);
-  while (tile < n_tiles) {
-    const int64_t wrow0 = tile * kFTileRows;
-    T v[32];
-    if (wrow0 + kFTileRows <= n) {
-#pragma unroll
-      for (int k = 0; k < 32; ++k) v[k] = __ldcs(vals + wrow0 + k * 32 + lane);
-    } else {
-#pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        const int64_t row = wrow0 + k * 32 + lane;
-        v[k] = (row < n) ? __ldcs(vals + row) : scalar;
-      }
-    }
-    const long long next_tile = claim_tile(status, lane);  // latency hidden behind the loads above
-    __syncwarp();                                          // keep every load ahead of the first vote
-    uint32_t emit = 0;
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const int64_t row = wrow0 + k * 32 + lane;
-      const uint32_t bits = __ballot_sync(0xffffffffu, row < n && Cmp::template apply<T>(v[k], scalar));
-      if (lane == k) emit = bits;
-    }
-    unsigned tile_total;
-    const unsigned long long my_base = warp_tile_scan(__popc(emit), status + 1, tile, n_tiles, out_len, &tile_total);
-    if (tile_total != 0) {
-#pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        const uint32_t w_emit = __shfl_sync(0xffffffffu, emit, k);
-        const unsigned long long b = __shfl_sync(0xffffffffu, my_base, k);
-        const unsigned rank = __popc(w_emit & ((1u << lane) - 1u));
-        const unsigned long long pos = b + rank;
-        if (((w_emit >> lane) & 1) && (long long)pos < capacity) out[pos] = v[k];
-      }
-    }
-    tile = next_tile;
-  }
-}
-
-template <typename T, typename Cmp>
-static ag_status launch_fused_t(const void* vals, const void* scalar_host, int64_t n, void* out, int64_t capacity,
-                                int64_t* d_out_len, cudaStream_t st) {
-  Workspace* ws;
-  AG_TRY(get_workspace(st, &ws));
-  const int64_t n_tiles = (n + kFTileRows - 1) / kFTileRows;
-  AG_TRY(ensure_tile_status(ws, (size_t)n_tiles + 1, st));
-  AG_CUDA_TRY(cudaMemsetAsync(ws->tile_status, 0, ((size_t)n_tiles + 1) * sizeof(unsigned long long), st));
-  const int grid = grid_one_wave(fused_cmp_filter_kernel<T, Cmp>, kFThreads, (n_tiles + kFWarps - 1) / kFWarps);
-  fused_cmp_filter_kernel<T, Cmp><<<grid, kFThreads, 0, st>>>((const T*)vals, *(const T*)scalar_host, n, (T*)out, capacity,
-                                                             ws->tile_status, (long long*)d_out_len, n_tiles);
-  return check_launch("fused_cmp_filter_kernel");
-}
-
+// Greater/…(values, scalar) -> Filter in ONE kernel (config 3 of BASELINE.json): no intermediate
+// mask in HBM.  Phase 1 of a tile streams its 32K values once from HBM to build the mask words in
+// shared memory; phase 2 re-reads only the selected rows, which are still in the 126 MB L2 (a
+// tile is 256 KB and all resident tiles together are < 40 MB), so HBM traffic stays at the
+// algorithmic 8 + 8s bytes/row.  Same result as compare_dev + filter_primitive_dev.
 template <typename T>
-static ag_status launch_fused_cmp(int cmp, const void* vals, const void* scalar_host, int64_t n, void* out, int64_t capacity,
-                                  int64_t* d_out_len, cudaStream_t st) {
+static ag_status launch_fused_cmp(int cmp, FilterParams& p, const void* scalar_host, cudaStream_t st) {
+  const T scalar = *(const T*)scalar_host;
   switch (cmp) {
-    case AG_CMP_EQ: return launch_fused_t<T, FCmpEq>(vals, scalar_host, n, out, capacity, d_out_len, st);
-    case AG_CMP_NE: return launch_fused_t<T, FCmpNe>(vals, scalar_host, n, out, capacity, d_out_len, st);
-    case AG_CMP_GT: return launch_fused_t<T, FCmpGt>(vals, scalar_host, n, out, capacity, d_out_len, st);
-    case AG_CMP_GE: return launch_fused_t<T, FCmpGe>(vals, scalar_host, n, out, capacity, d_out_len, st);
-    case AG_CMP_LT: return launch_fused_t<T, FCmpLt>(vals, scalar_host, n, out, capacity, d_out_len, st);
-    case AG_CMP_LE: return launch_fused_t<T, FCmpLe>(vals, scalar_host, n, out, capacity, d_out_len, st);
+    case AG_CMP_EQ: return launch_filter_t<T, 2, FCmpEq>(p, scalar, st);
+    case AG_CMP_NE: return launch_filter_t<T, 2, FCmpNe>(p, scalar, st);
+    case AG_CMP_GT: return launch_filter_t<T, 2, FCmpGt>(p, scalar, st);
+    case AG_CMP_GE: return launch_filter_t<T, 2, FCmpGe>(p, scalar, st);
+    case AG_CMP_LT: return launch_filter_t<T, 2, FCmpLt>(p, scalar, st);
+    case AG_CMP_LE: return launch_filter_t<T, 2, FCmpLe>(p, scalar, st);
     default: AG_FAIL(AG_ERR_INVALID, "filter_compare: bad operator %d", cmp);
   }
 }
@@ -384,13 +415,15 @@ ag_status filter_compare_scalar_dev(int type, int cmp, const void* vals, const v
   if (!d_out_len || !scalar_host) AG_FAIL(AG_ERR_INVALID, "filter_compare: NULL argument");
   if (n == 0) { AG_CUDA_TRY(cudaMemsetAsync(d_out_len, 0, sizeof(int64_t), st)); return AG_OK; }
   if (!vals || (!out && capacity > 0)) AG_FAIL(AG_ERR_INVALID, "filter_compare: NULL values/output");
+  FilterParams p{};
+  p.vals = vals; p.n = n; p.out = out; p.capacity = capacity; p.out_len = reinterpret_cast<long long*>(d_out_len);
   switch (type) {
-    case AG_TYPE_INT32: return launch_fused_cmp<int32_t>(cmp, vals, scalar_host, n, out, capacity, d_out_len, st);
-    case AG_TYPE_UINT32: return launch_fused_cmp<uint32_t>(cmp, vals, scalar_host, n, out, capacity, d_out_len, st);
-    case AG_TYPE_INT64: return launch_fused_cmp<long long>(cmp, vals, scalar_host, n, out, capacity, d_out_len, st);
-    case AG_TYPE_UINT64: return launch_fused_cmp<unsigned long long>(cmp, vals, scalar_host, n, out, capacity, d_out_len, st);
-    case AG_TYPE_FLOAT32: return launch_fused_cmp<float>(cmp, vals, scalar_host, n, out, capacity, d_out_len, st);
-    case AG_TYPE_FLOAT64: return launch_fused_cmp<double>(cmp, vals, scalar_host, n, out, capacity, d_out_len, st);
+    case AG_TYPE_INT32: return launch_fused_cmp<int32_t>(cmp, p, scalar_host, st);
+    case AG_TYPE_UINT32: return launch_fused_cmp<uint32_t>(cmp, p, scalar_host, st);
+    case AG_TYPE_INT64: return launch_fused_cmp<long long>(cmp, p, scalar_host, st);
+    case AG_TYPE_UINT64: return launch_fused_cmp<unsigned long long>(cmp, p, scalar_host, st);
+    case AG_TYPE_FLOAT32: return launch_fused_cmp<float>(cmp, p, scalar_host, st);
+    case AG_TYPE_FLOAT64: return launch_fused_cmp<double>(cmp, p, scalar_host, st);
     default: AG_FAIL(AG_ERR_NOT_IMPLEMENTED, "filter_compare: fused path covers 32/64-bit types; use compare + filter for type id %d", type);
   }
 }
