@@ -181,8 +181,13 @@ struct Kernel {
   NullHandling null_handling = NullHandling::INTERSECTION;
   MemAlloc mem_alloc = MemAlloc::PREALLOC;
 };
+using BatchKernelExec = std::function<Status(KernelCtx*, const std::vector<ExecSpan>&, std::vector<ExecResult>&)>;
 struct ScalarKernel : Kernel {  // kernel.go:632-640
   bool can_write_into_slices = true;
+  // B200-first extension: when set, the executor hands ALL aligned spans of a chunked call to the
+  // kernel at once (one launch, include/arrowgpu.h ag_arith_binary_spans_dev) instead of calling
+  // `exec` once per span like executeSpans does (executor.go:598-623).  Same results.
+  BatchKernelExec exec_batch;
   bool can_fail = false;        // kernels that lower KernelCtx::error_word
   const char* fail_message = "";
 };

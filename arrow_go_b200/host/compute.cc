@@ -494,6 +494,9 @@ Status ScalarFunction::Execute(const ExecCtx& ectx, const FunctionOptions* opts,
   if (contiguous) {
     ArraySpan output;
     RETURN_NOT_OK(prepare_output(total, &output));
+    const bool batched = static_cast<bool>(kernel->exec_batch) && pieces.size() > 1;
+    std::vector<ExecSpan> all_spans;
+    std::vector<ArraySpan> all_outs;
     for (auto& p : pieces) {
       if (p.len == 0) continue;
       ExecSpan span;
@@ -502,8 +505,17 @@ Status ScalarFunction::Execute(const ExecCtx& ectx, const FunctionOptions* opts,
       slice.SetSlice(p.pos, p.len);       // out.SetSlice(resultOffset, input.Len), executor.go:609
       slice.nulls = kUnknownNullCount;
       kctx.row_base = p.pos;
-      RETURN_NOT_OK(exec_single(span, &slice));
+      if (batched) {
+        // validity still goes span by span (bitmap launches are tiny); the value kernel runs once
+        if (out_type != Type::NA && kernel->null_handling == exec::NullHandling::INTERSECTION && !elide_validity)
+          RETURN_NOT_OK(PropagateNulls(&kctx, span, &slice));
+        all_spans.push_back(std::move(span));
+        all_outs.push_back(slice);
+      } else {
+        RETURN_NOT_OK(exec_single(span, &slice));
+      }
     }
+    if (batched && !all_spans.empty()) RETURN_NOT_OK(kernel->exec_batch(&kctx, all_spans, all_outs));
     output.nulls = (elide_validity || kernel->null_handling == exec::NullHandling::OUTPUT_NOT_NULL) ? 0 : kUnknownNullCount;
     results.push_back(output.MakeData());
   } else {
@@ -636,6 +648,24 @@ exec::ArrayKernelExec ArithBinaryExec(int8_t op) {
     const void* l = batch.values[0].IsArray() ? (const void*)ValuesPtr(batch.values[0].array) : (const void*)batch.values[0].scalar->value;
     const void* r = batch.values[1].IsArray() ? (const void*)ValuesPtr(batch.values[1].array) : (const void*)batch.values[1].scalar->value;
     NATIVE(ag_arith_binary_dev((int)out->type, op, shape, l, r, ValuesPtr(out), batch.len, nullptr));
+    return Status::OK();
+  };
+}
+
+// The same kernel over every aligned span of a chunked call in ONE launch
+exec::BatchKernelExec ArithBinaryBatchExec(int8_t op) {
+  return [op](KernelCtx*, const std::vector<ExecSpan>& spans, std::vector<ExecResult>& outs) -> Status {
+    if (spans.empty()) return Status::OK();
+    const int shape = ShapeOf(spans[0]);
+    std::vector<ag_span3> table(spans.size());
+    for (size_t i = 0; i < spans.size(); ++i) {
+      const ExecValue &a = spans[i].values[0], &b = spans[i].values[1];
+      table[i].l = a.IsArray() ? (const void*)ValuesPtr(a.array) : (const void*)a.scalar->value;
+      table[i].r = b.IsArray() ? (const void*)ValuesPtr(b.array) : (const void*)b.scalar->value;
+      table[i].out = ValuesPtr(&outs[i]);
+      table[i].n = spans[i].len;
+    }
+    NATIVE(ag_arith_binary_spans_dev((int)outs[0].type, op, shape, table.data(), (int64_t)table.size(), nullptr));
     return Status::OK();
   };
 }
@@ -916,6 +946,7 @@ std::shared_ptr<ScalarFunction> MakeArithBinary(const std::string& name, int8_t 
       k.fail_message = fail_msg;
     } else {
       k.exec = ArithBinaryExec(checked ? checked_op : unchecked_op);
+      k.exec_batch = ArithBinaryBatchExec(checked ? checked_op : unchecked_op);
     }
     fn->AddKernel(std::move(k));
   }

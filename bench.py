@@ -52,6 +52,23 @@ def peaks():
         return 6650.0, "fallback"
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the Add kernel from the committed
+    `ncu --set full` capture (profiles/r1/ncu_full_binary_spans_kernel.csv), or None."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r1", "ncu_full_binary_spans_kernel.csv")
+    try:
+        rows = list(csv.reader(open(path)))
+        h = rows[0]
+        ri = [i for i, c in enumerate(h) if c.startswith("dram__bytes_read.sum")][0]
+        wi = [i for i, c in enumerate(h) if c.startswith("dram__bytes_write.sum")][0]
+        scale = lambda c: {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[c[c.index("[") + 1:c.index("]")]]
+        vals = [float(r[ri]) * scale(h[ri]) + float(r[wi]) * scale(h[wi]) for r in rows[1:]]
+        return sum(vals) / len(vals)
+    except Exception:
+        return None
+
+
 def spans_for(n, lc, rc):
     """iterateExecSpans (executor.go:757-863): span = min(remaining of each arg's current chunk)."""
     out, pos = [], 0
@@ -226,6 +243,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
     if world > 1:
+        # keep stdout to the ONE JSON line: NCCL prints its version banner there at VERSION/INFO
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
@@ -408,7 +428,8 @@ def main():
                        "rows_per_gpu": rows, "chunks": f"left {L_CHUNK}-row chunks, right {R_CHUNK}-row chunks -> {len(spans)} spans, one contiguous output",
                        "l2": "inputs (1.6 GB) + output (0.8 GB) per step exceed the 126 MB L2; no flush needed", "parallelism": f"row-range x{world}",
                        "contiguous_ms_per_step": ms_contig, "per_span_launch_ms_per_step": ms_per_span},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_bytes(),
+                         "traffic_note": "bytes per launch, dram__bytes_read+write from profiles/r1/ncu_full_binary_spans_kernel.csv (same kernel, same shape)",
                          "peak_kind": peak_kind, "algorithmic_bytes_per_row": 24, "kernel": "binary_spans_kernel<double,OpAdd,AA>",
                          "contiguous_frac": 24.0 * rows / (ms_contig * 1e-3) / 1e9 / peak},
             "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches_timed), "gpu_launches_total": int(launches_total),
