@@ -114,66 +114,27 @@ struct FCmpLe { template <typename T> static __device__ __forceinline__ bool app
 
 // kMode 0: copy values of type V selected by a bitmap mask.
 // kMode 1: write row indices as V (GetTakeIndices).
-// kMode 2: fused compare: the mask is Cmp(values[row], scalar); V is the arithmetic type.
 //
 // Tile assignment is STATIC (block b owns tiles b, b+G, ...): a tile only waits on lower tiles,
 // every block walks its tiles in increasing order and the grid is launched cooperatively as ONE
 // resident wave (cudaLaunchCooperativeKernel fails instead of deadlocking if it could not be).
-template <typename V, int kMode, bool kValidity, typename Cmp>
+template <typename V, int kMode, bool kValidity>
 __global__ void __launch_bounds__(kFThreads)
-filter_kernel(const FilterParams p, V scalar) {
+filter_kernel(const FilterParams p) {
   __shared__ uint32_t s_emit[kFTileWords];
   __shared__ uint32_t s_sel[kFTileWords];
   __shared__ uint32_t s_base[kFTileWords];   // exclusive offset of each word inside the tile
   __shared__ uint32_t s_warp_tot[kFWarps];
   __shared__ unsigned long long s_tile_base;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const V* __restrict__ vals = reinterpret_cast<const V*>(p.vals) + (kMode != 1 ? p.voff : 0);
+  const V* __restrict__ vals = reinterpret_cast<const V*>(p.vals) + (kMode == 0 ? p.voff : 0);
   V* __restrict__ out = reinterpret_cast<V*>(p.out);
   const int64_t m_lo = p.moff >> 3, m_hi = (p.moff + p.n + 7) >> 3;
   const long long cap_words = (p.capacity + 31) >> 5;
-  const uint64_t keep = (kMode == 2) ? l2_policy_evict_last() : 0;
-
   for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
     const int64_t trow0 = tile * kFTileRows;
     // ---- phase 1: the tile's 1024 mask words -> shared memory --------------------------------
-    if (kMode == 2) {
-      // Sub-tiles of 8 x kL x 32 rows; warp w owns kL x 32 rows of each; lane j holds rows 32k+j so
-      // every load is a coalesced 256-byte request and __ballot_sync packs word k.  kL = 32 (3
-      // resident blocks/SM) measured faster than kL = 16 (5 blocks/SM): more resident tiles push
-      // the not-yet-compacted tiles out of L2.  The loads carry an L2 evict-last policy: phase 2
-      // re-reads the selected rows from L2, not from HBM.
-      constexpr int kL = 32;                       // loads in flight per lane
-      constexpr int kSubRows = kFWarps * kL * 32;  // 4096
-#pragma unroll 1
-      for (int sub = 0; sub < kFTileRows / kSubRows; ++sub) {
-        const int64_t wrow0 = trow0 + (int64_t)sub * kSubRows + warp * (kL * 32);
-        V v[kL];
-        if (wrow0 + kL * 32 <= p.n) {
-#pragma unroll
-          for (int k = 0; k < kL; ++k) v[k] = ld_l2_hint(vals + wrow0 + k * 32 + lane, keep);
-        } else {
-#pragma unroll
-          for (int k = 0; k < kL; ++k) {
-            const int64_t row = wrow0 + k * 32 + lane;
-            v[k] = (row < p.n) ? ld_l2_hint(vals + row, keep) : scalar;
-          }
-        }
-        __syncwarp();  // keep every load ahead of the first vote
-        uint32_t myword = 0;
-#pragma unroll
-        for (int k = 0; k < kL; ++k) {
-          const int64_t row = wrow0 + k * 32 + lane;
-          const uint32_t bits = __ballot_sync(0xffffffffu, row < p.n && Cmp::template apply<V>(v[k], scalar));
-          if (lane == k) myword = bits;
-        }
-        if (lane < kL) {
-          const int word = sub * (kSubRows / 32) + warp * kL + lane;
-          s_emit[word] = myword;
-          s_sel[word] = myword;
-        }
-      }
-    } else {
+    {
 #pragma unroll
       for (int k = 0; k < kFWordsPerThread; ++k) {
         const int word = k * kFThreads + threadIdx.x;  // coalesced mask reads
@@ -310,8 +271,8 @@ filter_kernel(const FilterParams p, V scalar) {
   }
 }
 
-template <typename V, int kMode, typename Cmp>
-static ag_status launch_filter_t(FilterParams& p, V scalar, cudaStream_t st) {
+template <typename V, int kMode>
+static ag_status launch_filter_t(FilterParams& p, cudaStream_t st) {
   Workspace* ws;
   AG_TRY(get_workspace(st, &ws));
   p.n_tiles = (p.n + kFTileRows - 1) / kFTileRows;
@@ -319,13 +280,13 @@ static ag_status launch_filter_t(FilterParams& p, V scalar, cudaStream_t st) {
   p.status = ws->tile_status;
   AG_CUDA_TRY(cudaMemsetAsync(p.status, 0, (size_t)p.n_tiles * sizeof(unsigned long long), st));
   if (p.out_valid) AG_CUDA_TRY(cudaMemsetAsync(p.out_valid, 0, (size_t)((p.capacity + 31) >> 5) * 4, st));
-  void* args[] = {(void*)&p, (void*)&scalar};
+  void* args[] = {(void*)&p};
   if (p.out_valid)
-    AG_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)filter_kernel<V, kMode, true, Cmp>,
-                                            dim3(grid_one_wave(filter_kernel<V, kMode, true, Cmp>, kFThreads, p.n_tiles)), dim3(kFThreads), args, 0, st));
+    AG_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)filter_kernel<V, kMode, true>,
+                                            dim3(grid_one_wave(filter_kernel<V, kMode, true>, kFThreads, p.n_tiles)), dim3(kFThreads), args, 0, st));
   else
-    AG_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)filter_kernel<V, kMode, false, Cmp>,
-                                            dim3(grid_one_wave(filter_kernel<V, kMode, false, Cmp>, kFThreads, p.n_tiles)), dim3(kFThreads), args, 0, st));
+    AG_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)filter_kernel<V, kMode, false>,
+                                            dim3(grid_one_wave(filter_kernel<V, kMode, false>, kFThreads, p.n_tiles)), dim3(kFThreads), args, 0, st));
   return check_launch("filter_kernel");
 }
 
@@ -360,10 +321,10 @@ ag_status filter_primitive_dev(int bit_width, const void* vals, const uint8_t* v
   }
   if (((uintptr_t)vals & am) || ((uintptr_t)out & am)) AG_FAIL(AG_ERR_INVALID, "filter: buffers not aligned to the element width");
   switch (bit_width) {
-    case 8: return launch_filter_t<uint8_t, 0, FCmpNone>(p, (uint8_t)0, st);
-    case 16: return launch_filter_t<uint16_t, 0, FCmpNone>(p, (uint16_t)0, st);
-    case 32: return launch_filter_t<uint32_t, 0, FCmpNone>(p, 0u, st);
-    default: return launch_filter_t<unsigned long long, 0, FCmpNone>(p, 0ull, st);
+    case 8: return launch_filter_t<uint8_t, 0>(p, st);
+    case 16: return launch_filter_t<uint16_t, 0>(p, st);
+    case 32: return launch_filter_t<uint32_t, 0>(p, st);
+    default: return launch_filter_t<unsigned long long, 0>(p, st);
   }
 }
 
@@ -380,31 +341,183 @@ ag_status take_indices_dev(int index_width, const uint8_t* mask, const uint8_t* 
   if (n == 0) { AG_CUDA_TRY(cudaMemsetAsync(d_out_len, 0, sizeof(int64_t), st)); return AG_OK; }
   if (index_width == 16) {
     if (n >= 65535) AG_FAIL(AG_ERR_INVALID, "take_indices: uint16 indices need n < 65535 (vector_selection.go:229-231)");
-    return launch_filter_t<uint16_t, 1, FCmpNone>(p, (uint16_t)0, st);
+    return launch_filter_t<uint16_t, 1>(p, st);
   }
   if (index_width == 32) {
     if (n >= 4294967295ll) AG_FAIL(AG_ERR_NOT_IMPLEMENTED, "take_indices: filter length exceeds UINT32_MAX (vector_selection.go:233-235)");
-    return launch_filter_t<uint32_t, 1, FCmpNone>(p, 0u, st);
+    return launch_filter_t<uint32_t, 1>(p, st);
   }
   AG_FAIL(AG_ERR_TYPE, "take_indices: index width must be 16 or 32");
 }
 
 // ---------------------------------------------------------------- fused compare + filter ----
 // Greater/…(values, scalar) -> Filter in ONE kernel (config 3 of BASELINE.json): no intermediate
-// mask in HBM.  Phase 1 of a tile streams its 32K values once from HBM to build the mask words in
-// shared memory; phase 2 re-reads only the selected rows, which are still in the 126 MB L2 (a
-// tile is 256 KB and all resident tiles together are < 40 MB), so HBM traffic stays at the
-// algorithmic 8 + 8s bytes/row.  Same result as compare_dev + filter_primitive_dev.
+// mask in HBM and every value is read from HBM exactly once (8 + 8s bytes/row).
+//
+// A 32K-row block tile is 32 "segments" of 1024 rows (4 sub-tiles x 8 warps).  Phase 1, per
+// segment: lane j loads rows 32k+j (32 coalesced 256-byte requests in flight), __ballot_sync
+// packs the predicate words, a warp scan of their popcounts gives every selected value its slot,
+// and the values go straight from registers into the segment's staging area in SHARED memory.
+// Then: block scan of the 32 segment counts, look-back for the tile base, and phase 2 copies each
+// staged segment to out[] with fully coalesced stores.  A segment that selects more rows than its
+// staging area holds (kSegCap, > 21 % of 1024) is flagged and compacted by re-reading its rows.
+// Measured at 100M int64 rows, 10 % selected: 190 us (two-step compare + filter: 285 us; the
+// first fused version, which re-read selected rows through L2: 210 us; 512-row segments with the
+// same shared-memory budget: 198 us).
+constexpr int kSegRows = 1024;
+constexpr int kSegsPerTile = kFTileRows / kSegRows;  // 32
+constexpr int kSegCap = 224;                         // staged values per segment
+
+template <typename T, typename Cmp>
+__global__ void __launch_bounds__(kFThreads, 3)
+fused_filter_kernel(const T* __restrict__ vals, T scalar, int64_t n, T* __restrict__ out, int64_t capacity,
+                    unsigned long long* status, long long* out_len, int64_t n_tiles) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* s_emit = reinterpret_cast<uint32_t*>(smem_raw);            // [1024] predicate words
+  uint32_t* s_cnt = s_emit + kFTileWords;                              // [32] rows selected per segment
+  uint32_t* s_excl = s_cnt + kSegsPerTile;                             // [32] exclusive offsets inside the tile
+  T* s_stage = reinterpret_cast<T*>(s_excl + kSegsPerTile);            // [32][kSegCap]
+  __shared__ unsigned long long s_tile_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t trow0 = tile * kFTileRows;
+    // ---- phase 1: stream, predicate, stage --------------------------------------------------
+#pragma unroll 1
+    for (int sub = 0; sub < kSegsPerTile / kFWarps; ++sub) {
+      const int seg = sub * kFWarps + warp;
+      const int64_t wrow0 = trow0 + (int64_t)seg * kSegRows;
+      T v[32];
+      if (wrow0 + kSegRows <= n) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = __ldcs(vals + wrow0 + k * 32 + lane);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const int64_t row = wrow0 + k * 32 + lane;
+          v[k] = (row < n) ? __ldcs(vals + row) : scalar;
+        }
+      }
+      __syncwarp();  // keep every load ahead of the first vote
+      // Every lane sees every ballot, so each lane tracks the running count itself: the slot of a
+      // selected row is (rows selected in earlier words) + (selected rows below it in its word).
+      // No scan and no shuffles; values go from registers straight into the staging area (slots
+      // past kSegCap are dropped — such a segment is flagged and compacted by re-reading).
+      T* stage = s_stage + seg * kSegCap;
+      uint32_t myword = 0;
+      unsigned running = 0;
+      const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const int64_t row = wrow0 + k * 32 + lane;
+        const bool pr = row < n && Cmp::template apply<T>(v[k], scalar);
+        const uint32_t bits = __ballot_sync(0xffffffffu, pr);
+        if (lane == k) myword = bits;
+        const unsigned pos = running + __popc(bits & lt);
+        if (pr && pos < kSegCap) stage[pos] = v[k];
+        running += __popc(bits);
+      }
+      s_emit[seg * 32 + lane] = myword;
+      if (lane == 0) s_cnt[seg] = running;
+    }
+    __syncthreads();
+    // ---- block scan of the 32 segment counts + look-back (warp 0) -----------------------------
+    if (warp == 0) {
+      const unsigned c = s_cnt[lane];
+      unsigned incl = c;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+      }
+      s_excl[lane] = incl - c;
+      const unsigned tile_total = __shfl_sync(0xffffffffu, incl, 31);
+      const unsigned long long excl = lookback(status, tile, tile_total, lane);
+      if (lane == 0) {
+        s_tile_base = excl;
+        if (tile == n_tiles - 1) *out_len = (long long)(excl + tile_total);
+      }
+    }
+    __syncthreads();
+    // ---- phase 2: staged segments -> out[] with coalesced stores --------------------------------
+    const unsigned long long tbase = s_tile_base;
+#pragma unroll 1
+    for (int sub = 0; sub < kSegsPerTile / kFWarps; ++sub) {
+      const int seg = sub * kFWarps + warp;
+      const unsigned total = s_cnt[seg];
+      if (total == 0) continue;
+      const unsigned long long base = tbase + s_excl[seg];
+      if (total <= kSegCap) {
+        const T* stage = s_stage + seg * kSegCap;
+        for (unsigned i = lane; i < total; i += 32)
+          if ((long long)(base + i) < capacity) out[base + i] = stage[i];
+      } else {
+        // overflow: re-read the segment's selected rows (they are at worst in L2)
+        const uint32_t myword = s_emit[seg * 32 + lane];
+        const unsigned cnt = __popc(myword);
+        unsigned incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += t;
+        }
+        const unsigned my_excl = incl - cnt;
+        const int64_t wrow0 = trow0 + (int64_t)seg * kSegRows;
+#pragma unroll 4
+        for (int k = 0; k < 32; ++k) {
+          const uint32_t w = __shfl_sync(0xffffffffu, myword, k);
+          const unsigned off = __shfl_sync(0xffffffffu, my_excl, k);
+          if ((w >> lane) & 1) {
+            const unsigned long long pos = base + off + __popc(w & ((1u << lane) - 1u));
+            if ((long long)pos < capacity) out[pos] = __ldcs(vals + wrow0 + k * 32 + lane);
+          }
+        }
+      }
+    }
+    __syncthreads();  // shared arrays are rewritten by the next tile
+  }
+}
+
+template <typename T, typename Cmp>
+static ag_status launch_fused_t(const void* vals, const void* scalar_host, int64_t n, void* out, int64_t capacity,
+                                int64_t* d_out_len, cudaStream_t st) {
+  Workspace* ws;
+  AG_TRY(get_workspace(st, &ws));
+  const int64_t n_tiles = (n + kFTileRows - 1) / kFTileRows;
+  AG_TRY(ensure_tile_status(ws, (size_t)n_tiles, st));
+  AG_CUDA_TRY(cudaMemsetAsync(ws->tile_status, 0, (size_t)n_tiles * sizeof(unsigned long long), st));
+  const size_t smem = (kFTileWords + 2 * kSegsPerTile) * sizeof(uint32_t) + (size_t)kSegsPerTile * kSegCap * sizeof(T);
+  static std::atomic<bool> attr_set{false};  // per instantiation
+  if (!attr_set.load()) {
+    AG_CUDA_TRY(cudaFuncSetAttribute((const void*)fused_filter_kernel<T, Cmp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set.store(true);
+  }
+  int per_sm = 0;
+  AG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_filter_kernel<T, Cmp>, kFThreads, smem));
+  if (per_sm < 1) per_sm = 1;
+  int64_t grid = (int64_t)sm_count() * per_sm;
+  if (grid > n_tiles) grid = n_tiles;
+  const T* a_vals = (const T*)vals;
+  T a_scalar = *(const T*)scalar_host;
+  T* a_out = (T*)out;
+  unsigned long long* a_status = ws->tile_status;
+  long long* a_len = (long long*)d_out_len;
+  int64_t a_n = n, a_cap = capacity, a_tiles = n_tiles;
+  void* args[] = {&a_vals, &a_scalar, &a_n, &a_out, &a_cap, &a_status, &a_len, &a_tiles};
+  AG_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)fused_filter_kernel<T, Cmp>, dim3((unsigned)grid), dim3(kFThreads), args, smem, st));
+  return check_launch("fused_filter_kernel");
+}
+
 template <typename T>
-static ag_status launch_fused_cmp(int cmp, FilterParams& p, const void* scalar_host, cudaStream_t st) {
-  const T scalar = *(const T*)scalar_host;
+static ag_status launch_fused_cmp(int cmp, const void* vals, const void* scalar_host, int64_t n, void* out, int64_t capacity,
+                                  int64_t* d_out_len, cudaStream_t st) {
   switch (cmp) {
-    case AG_CMP_EQ: return launch_filter_t<T, 2, FCmpEq>(p, scalar, st);
-    case AG_CMP_NE: return launch_filter_t<T, 2, FCmpNe>(p, scalar, st);
-    case AG_CMP_GT: return launch_filter_t<T, 2, FCmpGt>(p, scalar, st);
-    case AG_CMP_GE: return launch_filter_t<T, 2, FCmpGe>(p, scalar, st);
-    case AG_CMP_LT: return launch_filter_t<T, 2, FCmpLt>(p, scalar, st);
-    case AG_CMP_LE: return launch_filter_t<T, 2, FCmpLe>(p, scalar, st);
+    case AG_CMP_EQ: return launch_fused_t<T, FCmpEq>(vals, scalar_host, n, out, capacity, d_out_len, st);
+    case AG_CMP_NE: return launch_fused_t<T, FCmpNe>(vals, scalar_host, n, out, capacity, d_out_len, st);
+    case AG_CMP_GT: return launch_fused_t<T, FCmpGt>(vals, scalar_host, n, out, capacity, d_out_len, st);
+    case AG_CMP_GE: return launch_fused_t<T, FCmpGe>(vals, scalar_host, n, out, capacity, d_out_len, st);
+    case AG_CMP_LT: return launch_fused_t<T, FCmpLt>(vals, scalar_host, n, out, capacity, d_out_len, st);
+    case AG_CMP_LE: return launch_fused_t<T, FCmpLe>(vals, scalar_host, n, out, capacity, d_out_len, st);
     default: AG_FAIL(AG_ERR_INVALID, "filter_compare: bad operator %d", cmp);
   }
 }
@@ -415,15 +528,13 @@ ag_status filter_compare_scalar_dev(int type, int cmp, const void* vals, const v
   if (!d_out_len || !scalar_host) AG_FAIL(AG_ERR_INVALID, "filter_compare: NULL argument");
   if (n == 0) { AG_CUDA_TRY(cudaMemsetAsync(d_out_len, 0, sizeof(int64_t), st)); return AG_OK; }
   if (!vals || (!out && capacity > 0)) AG_FAIL(AG_ERR_INVALID, "filter_compare: NULL values/output");
-  FilterParams p{};
-  p.vals = vals; p.n = n; p.out = out; p.capacity = capacity; p.out_len = reinterpret_cast<long long*>(d_out_len);
   switch (type) {
-    case AG_TYPE_INT32: return launch_fused_cmp<int32_t>(cmp, p, scalar_host, st);
-    case AG_TYPE_UINT32: return launch_fused_cmp<uint32_t>(cmp, p, scalar_host, st);
-    case AG_TYPE_INT64: return launch_fused_cmp<long long>(cmp, p, scalar_host, st);
-    case AG_TYPE_UINT64: return launch_fused_cmp<unsigned long long>(cmp, p, scalar_host, st);
-    case AG_TYPE_FLOAT32: return launch_fused_cmp<float>(cmp, p, scalar_host, st);
-    case AG_TYPE_FLOAT64: return launch_fused_cmp<double>(cmp, p, scalar_host, st);
+    case AG_TYPE_INT32: return launch_fused_cmp<int32_t>(cmp, vals, scalar_host, n, out, capacity, d_out_len, st);
+    case AG_TYPE_UINT32: return launch_fused_cmp<uint32_t>(cmp, vals, scalar_host, n, out, capacity, d_out_len, st);
+    case AG_TYPE_INT64: return launch_fused_cmp<long long>(cmp, vals, scalar_host, n, out, capacity, d_out_len, st);
+    case AG_TYPE_UINT64: return launch_fused_cmp<unsigned long long>(cmp, vals, scalar_host, n, out, capacity, d_out_len, st);
+    case AG_TYPE_FLOAT32: return launch_fused_cmp<float>(cmp, vals, scalar_host, n, out, capacity, d_out_len, st);
+    case AG_TYPE_FLOAT64: return launch_fused_cmp<double>(cmp, vals, scalar_host, n, out, capacity, d_out_len, st);
     default: AG_FAIL(AG_ERR_NOT_IMPLEMENTED, "filter_compare: fused path covers 32/64-bit types; use compare + filter for type id %d", type);
   }
 }
