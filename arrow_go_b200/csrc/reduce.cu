@@ -21,7 +21,7 @@ namespace ag {
 
 constexpr int kSumThreads = 256;
 constexpr int kSumUnroll = 4;
-constexpr int kSumBlocksPerSM = 8;
+constexpr int kSumBlocksPerSM = 8;  // 1184 blocks (a 888-block single wave measured 25 % slower)
 constexpr int kSumMaxBlocks = 148 * kSumBlocksPerSM;  // fixed: independent of the SM count found
 
 static inline int sum_grid(size_t n_pairs) {

@@ -119,10 +119,12 @@ ag_status get_workspace(cudaStream_t s, Workspace** out) {
   Workspace* ws = new Workspace();
   memset(ws, 0, sizeof(*ws));
   AG_CUDA_TRY(cudaMalloc(&ws->partials, (size_t)kMaxPartials * 16));
+  // Zero the tickets ON THE OWNING STREAM: `s` is a non-blocking stream, so a cudaMemset on the
+  // legacy default stream would not be ordered before the first kernel that reads the ticket.
   AG_CUDA_TRY(cudaMalloc((void**)&ws->ticket, 64 * sizeof(unsigned)));
-  AG_CUDA_TRY(cudaMemset(ws->ticket, 0, 64 * sizeof(unsigned)));
+  AG_CUDA_TRY(cudaMemsetAsync(ws->ticket, 0, 64 * sizeof(unsigned), s));
   AG_CUDA_TRY(cudaMalloc((void**)&ws->scalars, 16 * sizeof(int64_t)));
-  AG_CUDA_TRY(cudaMemset(ws->scalars, 0, 16 * sizeof(int64_t)));
+  AG_CUDA_TRY(cudaMemsetAsync(ws->scalars, 0, 16 * sizeof(int64_t), s));
   AG_CUDA_TRY(cudaHostAlloc((void**)&ws->h_scalars, 16 * sizeof(int64_t), cudaHostAllocDefault));
   ws->tile_status = nullptr;
   ws->tile_status_cap = 0;
