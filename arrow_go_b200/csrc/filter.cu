@@ -114,6 +114,8 @@ struct FCmpLe { template <typename T> static __device__ __forceinline__ bool app
 
 // kMode 0: copy values of type V selected by a bitmap mask.
 // kMode 1: write row indices as V (GetTakeIndices).
+// kMode 2: boolean VALUES: `vals` is an LSB-first bitmap (bit voff+row), `out` a pre-zeroed bitmap;
+//          selected bits are compacted exactly like the validity bits (V is a dummy uint32_t).
 //
 // Tile assignment is STATIC (block b owns tiles b, b+G, ...): a tile only waits on lower tiles,
 // every block walks its tiles in increasing order and the grid is launched cooperatively as ONE
@@ -129,6 +131,8 @@ filter_kernel(const FilterParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const V* __restrict__ vals = reinterpret_cast<const V*>(p.vals) + (kMode == 0 ? p.voff : 0);
   V* __restrict__ out = reinterpret_cast<V*>(p.out);
+  const uint8_t* __restrict__ bvals = reinterpret_cast<const uint8_t*>(p.vals);  // kMode 2
+  uint32_t* __restrict__ bout = reinterpret_cast<uint32_t*>(p.out);             // kMode 2
   const int64_t m_lo = p.moff >> 3, m_hi = (p.moff + p.n + 7) >> 3;
   const long long cap_words = (p.capacity + 31) >> 5;
   for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -213,15 +217,20 @@ filter_kernel(const FilterParams p) {
                 r[u] = __ffs(bits) - 1;
                 bits &= bits - 1;
                 ++cnt;
-                if ((my_sel >> r[u]) & 1) v[u] = (kMode == 1) ? (V)(wrow + r[u]) : __ldcs(vals + wrow + r[u]);
+                if ((my_sel >> r[u]) & 1) {
+                  if (kMode == 1) v[u] = (V)(wrow + r[u]);
+                  else if (kMode == 2) v[u] = (V)bit_is_set(bvals, p.voff + wrow + r[u]);
+                  else v[u] = __ldcs(vals + wrow + r[u]);
+                }
               }
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               if (r[u] >= 0 && (long long)(pos + u) < p.capacity) {
-                out[pos + u] = v[u];
+                if (kMode == 2) { if (v[u]) atomicOr(bout + ((pos + u) >> 5), 1u << ((pos + u) & 31)); }
+                else out[pos + u] = v[u];
                 if (kValidity && ((my_sel >> r[u]) & 1)) {
-                  const bool vb = (kMode == 0 && p.vvalid) ? bit_is_set(p.vvalid, p.voff + wrow + r[u]) : true;
+                  const bool vb = (kMode != 1 && p.vvalid) ? bit_is_set(p.vvalid, p.voff + wrow + r[u]) : true;
                   if (vb) atomicOr(p.out_valid + ((pos + u) >> 5), 1u << ((pos + u) & 31));
                 }
               }
@@ -241,7 +250,11 @@ filter_kernel(const FilterParams p) {
             const uint32_t w_sel = s_sel[j0 + u];
             const int64_t row = trow0 + (int64_t)(j0 + u) * 32 + lane;
             v[u] = V(0);
-            if ((w_sel >> lane) & 1) v[u] = (kMode == 1) ? (V)row : __ldcs(vals + row);  // last use: evict-first
+            if ((w_sel >> lane) & 1) {
+              if (kMode == 1) v[u] = (V)row;
+              else if (kMode == 2) v[u] = (V)bit_is_set(bvals, p.voff + row);
+              else v[u] = __ldcs(vals + row);  // last use: evict-first
+            }
           }
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
@@ -250,11 +263,19 @@ filter_kernel(const FilterParams p) {
             const bool e = (w_emit[u] >> lane) & 1;
             const unsigned rank = __popc(w_emit[u] & ((1u << lane) - 1u));
             const unsigned long long pos = b + rank;
-            if (e && (long long)pos < p.capacity) out[pos] = v[u];
+            if (kMode == 2) {
+              const uint32_t dpat = __reduce_or_sync(0xffffffffu, (e && v[u]) ? (1u << rank) : 0u);
+              if (lane == 0 && dpat) {
+                const unsigned sh = (unsigned)(b & 31);
+                const unsigned long long wi = b >> 5;
+                if ((long long)wi < cap_words) atomicOr(bout + wi, dpat << sh);
+                if (sh && (dpat >> (32 - sh)) && (long long)(wi + 1) < cap_words) atomicOr(bout + wi + 1, dpat >> (32 - sh));
+              }
+            } else if (e && (long long)pos < p.capacity) out[pos] = v[u];
             if (kValidity) {
               const int64_t row = trow0 + (int64_t)(j0 + u) * 32 + lane;
               uint32_t vb = 0;
-              if (e && ((s_sel[j0 + u] >> lane) & 1)) vb = (kMode == 0 && p.vvalid) ? (uint32_t)bit_is_set(p.vvalid, p.voff + row) : 1u;
+              if (e && ((s_sel[j0 + u] >> lane) & 1)) vb = (kMode != 1 && p.vvalid) ? (uint32_t)bit_is_set(p.vvalid, p.voff + row) : 1u;
               const uint32_t pattern = __reduce_or_sync(0xffffffffu, vb << rank);  // rank < 32 whenever vb != 0
               if (lane == 0 && pattern) {
                 const unsigned sh = (unsigned)(b & 31);
@@ -280,6 +301,7 @@ static ag_status launch_filter_t(FilterParams& p, cudaStream_t st) {
   p.status = ws->tile_status;
   AG_CUDA_TRY(cudaMemsetAsync(p.status, 0, (size_t)p.n_tiles * sizeof(unsigned long long), st));
   if (p.out_valid) AG_CUDA_TRY(cudaMemsetAsync(p.out_valid, 0, (size_t)((p.capacity + 31) >> 5) * 4, st));
+  if (kMode == 2 && p.capacity > 0) AG_CUDA_TRY(cudaMemsetAsync(p.out, 0, (size_t)((p.capacity + 31) >> 5) * 4, st));
   void* args[] = {(void*)&p};
   if (p.out_valid)
     AG_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)filter_kernel<V, kMode, true>,
@@ -313,12 +335,15 @@ ag_status filter_primitive_dev(int bit_width, const void* vals, const uint8_t* v
     AG_FAIL(AG_ERR_INVALID, "filter: the output can contain nulls but no output validity buffer was given (vector_selection.go:473)");
   if (n == 0) { AG_CUDA_TRY(cudaMemsetAsync(d_out_len, 0, sizeof(int64_t), st)); return AG_OK; }
   if (!vals || (!out && capacity > 0)) AG_FAIL(AG_ERR_INVALID, "filter: NULL values/output");
-  const uintptr_t am = (uintptr_t)(bit_width / 8 - 1);
-  switch (bit_width) {
-    case 8: case 16: case 32: case 64: break;
-    case 1: AG_FAIL(AG_ERR_NOT_IMPLEMENTED, "filter: boolean values are not implemented (see DESIGN.md: boolFilterWriter.WriteValue, vector_selection.go:433-436)");
-    default: AG_FAIL(AG_ERR_TYPE, "filter: invalid values bit width %d", bit_width);
+  if (bit_width == 1) {
+    // boolean values: the output data bitmap is compacted like the validity bits.  (The reference's
+    // boolFilterWriter.WriteValue never advances its position, vector_selection.go:433-436; we
+    // implement the documented semantics, identical to every other width.)
+    if ((uintptr_t)out & 3) AG_FAIL(AG_ERR_INVALID, "filter: boolean output bitmap must be 4-byte aligned");
+    return launch_filter_t<uint32_t, 2>(p, st);
   }
+  if (bit_width != 8 && bit_width != 16 && bit_width != 32 && bit_width != 64) AG_FAIL(AG_ERR_TYPE, "filter: invalid values bit width %d", bit_width);
+  const uintptr_t am = (uintptr_t)(bit_width / 8 - 1);
   if (((uintptr_t)vals & am) || ((uintptr_t)out & am)) AG_FAIL(AG_ERR_INVALID, "filter: buffers not aligned to the element width");
   switch (bit_width) {
     case 8: return launch_filter_t<uint8_t, 0>(p, st);

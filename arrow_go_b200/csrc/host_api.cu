@@ -478,10 +478,39 @@ ag_status ag_filter_primitive(int bit_width, const void* vals, const uint8_t* vv
   *out_len = 0;
   if (out_nulls) *out_nulls = 0;
   if (n < 0 || moff < 0 || voff < 0) AG_FAIL(AG_ERR_INVALID, "filter: negative length or offset");
-  if (bit_width == 1) AG_FAIL(AG_ERR_NOT_IMPLEMENTED, "filter: boolean values are not implemented");
-  if (bit_width != 8 && bit_width != 16 && bit_width != 32 && bit_width != 64) AG_FAIL(AG_ERR_TYPE, "filter: invalid values bit width %d", bit_width);
+  if (bit_width != 1 && bit_width != 8 && bit_width != 16 && bit_width != 32 && bit_width != 64) AG_FAIL(AG_ERR_TYPE, "filter: invalid values bit width %d", bit_width);
   if (n == 0) return AG_OK;
   if (!vals || !mask) AG_FAIL(AG_ERR_INVALID, "filter: NULL values/mask");
+  if (bit_width == 1) {  // boolean values: bitmap in, bitmap out
+    CallStream cs; AG_TRY(cs.acquire());
+    Temps t(cs);
+    uint8_t *dm, *dmv, *dvv, *dvd; int64_t om, omv, ovv, ovd; int64_t* d_len;
+    AG_TRY(upload_bitmap(t, mask, moff, n, &dm, &om));
+    AG_TRY(upload_bitmap(t, mvalid, moff, n, &dmv, &omv));
+    AG_TRY(upload_bitmap(t, (const uint8_t*)vals, voff, n, &dvd, &ovd));
+    AG_TRY(upload_bitmap(t, vvalid, voff, n, &dvv, &ovv));
+    AG_TRY(t.alloc_t(&d_len, 2 * sizeof(int64_t)));
+    AG_TRY(filter_output_size_dev(dm, dmv, om, n, null_selection, d_len, cs));
+    int64_t len = 0;
+    AG_TRY(d2h(&len, d_len, sizeof(int64_t), cs));
+    AG_TRY(sync(cs));
+    uint8_t *dout, *dov = nullptr;
+    AG_TRY(t.alloc_t(&dout, (size_t)((len + 31) / 32) * 4));
+    if (out_valid) AG_TRY(t.alloc_t(&dov, (size_t)((len + 31) / 32) * 4));
+    // values bitmap and its validity share the row numbering: both copies keep phase voff & 7
+    AG_TRY(filter_primitive_dev(1, dvd, dvv, ovd, dm, dmv, om, n, null_selection, dout, dov, len, d_len + 1, cs));
+    AG_TRY(d2h(out, dout, (size_t)((len + 7) / 8), cs));
+    if (out_valid) AG_TRY(d2h(out_valid, dov, (size_t)((len + 7) / 8), cs));
+    int64_t valid = 0;
+    if (out_valid && out_nulls) {
+      AG_TRY(bitmap_popcount_dev(dov, 0, len, d_len, cs));
+      AG_TRY(d2h(&valid, d_len, sizeof(int64_t), cs));
+    }
+    AG_TRY(sync(cs));
+    *out_len = len;
+    if (out_valid && out_nulls) *out_nulls = len - valid;
+    return AG_OK;
+  }
   const int w = bit_width / 8;
   CallStream cs; AG_TRY(cs.acquire());
   Temps t(cs);
@@ -556,27 +585,35 @@ ag_status ag_take_primitive(int bit_width, const void* vals, const uint8_t* vval
   if (bad_pos) *bad_pos = AG_NO_ERROR_POS;
   if (out_nulls) *out_nulls = 0;
   if (n < 0 || voff < 0 || ioff < 0 || vlen < 0) AG_FAIL(AG_ERR_INVALID, "take: negative length or offset");
-  if (bit_width == 1) AG_FAIL(AG_ERR_NOT_IMPLEMENTED, "take: boolean values are not implemented yet");
-  if (bit_width != 8 && bit_width != 16 && bit_width != 32 && bit_width != 64) AG_FAIL(AG_ERR_INVALID, "take: invalid values byte width for take");
+  if (bit_width != 1 && bit_width != 8 && bit_width != 16 && bit_width != 32 && bit_width != 64) AG_FAIL(AG_ERR_INVALID, "take: invalid values byte width for take");
   if (idx_width != 8 && idx_width != 16 && idx_width != 32 && idx_width != 64) AG_FAIL(AG_ERR_INDEX, "take: invalid indices byte width");
   if (n == 0) return AG_OK;
   if (!idx || !out) AG_FAIL(AG_ERR_INVALID, "take: NULL indices/output");
-  const int w = bit_width / 8, iw = idx_width / 8;
+  const bool is_bool = bit_width == 1;
+  const int w = is_bool ? 0 : bit_width / 8, iw = idx_width / 8;
   CallStream cs; AG_TRY(cs.acquire());
   Temps t(cs);
   void *dv, *di, *dout; uint8_t *dvv, *div; int64_t ovv, oiv; int64_t* d_word;
-  AG_TRY(t.alloc(&dv, (size_t)vlen * w));
-  AG_TRY(h2d(dv, (const char*)vals + voff * w, (size_t)vlen * w, cs));
+  if (is_bool) {
+    uint8_t* dvb; int64_t ovb;
+    AG_TRY(upload_bitmap(t, (const uint8_t*)vals, voff, vlen, &dvb, &ovb));
+    dv = dvb;
+  } else {
+    AG_TRY(t.alloc(&dv, (size_t)vlen * w));
+    AG_TRY(h2d(dv, (const char*)vals + voff * w, (size_t)vlen * w, cs));
+  }
   AG_TRY(upload_bitmap(t, vvalid, voff, vlen, &dvv, &ovv));
+  if (is_bool && !vvalid) ovv = voff & 7;
   AG_TRY(t.alloc(&di, (size_t)n * iw));
   AG_TRY(h2d(di, idx, (size_t)n * iw, cs));
   AG_TRY(upload_bitmap(t, ivalid, ioff, n, &div, &oiv));
-  AG_TRY(t.alloc(&dout, (size_t)n * w));
+  AG_TRY(t.alloc(&dout, is_bool ? (size_t)((n + 31) / 32) * 4 : (size_t)n * w));
   uint8_t* dov = nullptr;
   if (out_valid) AG_TRY(t.alloc_t(&dov, (size_t)((n + 31) / 32) * 4));
   AG_TRY(t.alloc_t(&d_word, 2 * sizeof(int64_t)));
   AG_TRY(error_word_reset(d_word, cs));
-  AG_TRY(take_primitive_dev(bit_width, (const char*)dv - ovv * w, dvv, ovv, vlen, idx_width, idx_signed, di, div, oiv, n,
+  // the device copies start at the slice: element offset becomes the bitmap phase (voff & 7)
+  AG_TRY(take_primitive_dev(bit_width, is_bool ? dv : (void*)((const char*)dv - ovv * w), dvv, ovv, vlen, idx_width, idx_signed, di, div, oiv, n,
                             bounds_check, dout, dov, d_word, cs));
   int64_t bad = AG_NO_ERROR_POS;
   AG_TRY(d2h(&bad, d_word, sizeof(int64_t), cs));
@@ -594,7 +631,7 @@ ag_status ag_take_primitive(int bit_width, const void* vals, const uint8_t* vval
     if (idx_width == 64 && !idx_signed) AG_FAIL(AG_ERR_INDEX, "%llu out of bounds", (unsigned long long)v);
     AG_FAIL(AG_ERR_INDEX, "%lld out of bounds", (long long)v);  // helpers.go:951
   }
-  AG_TRY(d2h(out, dout, (size_t)n * w, cs));
+  AG_TRY(d2h(out, dout, is_bool ? (size_t)((n + 7) / 8) : (size_t)n * w, cs));
   if (out_valid) {
     AG_TRY(d2h(out_valid, dov, (size_t)((n + 7) / 8), cs));
     if (out_nulls) {

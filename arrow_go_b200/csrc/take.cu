@@ -111,6 +111,67 @@ take_kernel(const TakeParams p) {
   }
 }
 
+// booleanTakeImpl (vector_selection.go:990-1074): out bit i = values bit [voff + idx[i]]; same
+// validity and bounds rules.  A warp's 32 rows of one step form one output word (ballot).
+template <typename I>
+__global__ void __launch_bounds__(kTkThreads)
+take_bool_kernel(const TakeParams p) {
+  const uint8_t* __restrict__ vals = reinterpret_cast<const uint8_t*>(p.vals);
+  const I* __restrict__ idx = reinterpret_cast<const I*>(p.idx);
+  uint32_t* __restrict__ out = reinterpret_cast<uint32_t*>(p.out);
+  constexpr I kSignBit = (I)((I)1 << (sizeof(I) * 8 - 1));
+  const int lane = threadIdx.x & 31;
+  const int64_t step = (int64_t)gridDim.x * kTkThreads;
+  long long my_bad = AG_NO_ERROR_POS;
+  for (int64_t base = (int64_t)blockIdx.x * kTkThreads; base < p.n; base += step) {
+    const int64_t i = base + threadIdx.x;
+    bool ok = i < p.n, bit = false;
+    if (ok) {
+      const I ix = idx[i];
+      if (p.ivalid) ok = bit_is_set(p.ivalid, p.ioff + i);
+      if (ok) {
+        const bool oob = (p.idx_signed && (ix & kSignBit)) || (unsigned long long)ix >= p.vlen;
+        if (oob) {
+          ok = false;
+          if (p.bounds_check && (long long)i < my_bad) my_bad = (long long)i;
+        } else {
+          if (p.vvalid) ok = bit_is_set(p.vvalid, p.voff + (int64_t)ix);
+          if (ok) bit = bit_is_set(vals, p.voff + (int64_t)ix);
+        }
+      }
+    }
+    const int64_t w = (base + (threadIdx.x & ~31)) >> 5;
+    const uint32_t dbits = __ballot_sync(0xffffffffu, bit);
+    const uint32_t vbits = __ballot_sync(0xffffffffu, ok);
+    const int64_t rem = p.n - (w << 5);
+    if (lane == 0 && rem > 0) {
+      const uint32_t m = rem >= 32 ? 0xffffffffu : bit_range_mask(0, (int)rem);
+      bitmap_store32_masked(out + w, dbits, m);
+      if (p.out_valid) bitmap_store32_masked(p.out_valid + w, vbits, m);
+    }
+  }
+  if (p.bounds_check) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+      const long long o = __shfl_xor_sync(0xffffffffu, my_bad, m);
+      my_bad = o < my_bad ? o : my_bad;
+    }
+    if (lane == 0 && my_bad != AG_NO_ERROR_POS) atomicMin(p.bad_pos, my_bad);
+  }
+}
+
+static ag_status launch_take_bool(int idx_width, const TakeParams& p, cudaStream_t st) {
+  const int64_t need = (p.n + kTkThreads - 1) / kTkThreads;
+  switch (idx_width) {
+    case 8: take_bool_kernel<uint8_t><<<grid_one_wave(take_bool_kernel<uint8_t>, kTkThreads, need), kTkThreads, 0, st>>>(p); break;
+    case 16: take_bool_kernel<uint16_t><<<grid_one_wave(take_bool_kernel<uint16_t>, kTkThreads, need), kTkThreads, 0, st>>>(p); break;
+    case 32: take_bool_kernel<uint32_t><<<grid_one_wave(take_bool_kernel<uint32_t>, kTkThreads, need), kTkThreads, 0, st>>>(p); break;
+    case 64: take_bool_kernel<unsigned long long><<<grid_one_wave(take_bool_kernel<unsigned long long>, kTkThreads, need), kTkThreads, 0, st>>>(p); break;
+    default: AG_FAIL(AG_ERR_INDEX, "take: invalid indices byte width");
+  }
+  return check_launch("take_bool_kernel");
+}
+
 template <typename V>
 static ag_status launch_take_v(int idx_width, const TakeParams& p, cudaStream_t st) {
   const int64_t need = (p.n + kTkThreads * kTkUnroll - 1) / (kTkThreads * kTkUnroll);
@@ -145,7 +206,9 @@ ag_status take_primitive_dev(int bit_width, const void* vals, const uint8_t* vva
     case 16: return launch_take_v<uint16_t>(idx_width, p, st);
     case 32: return launch_take_v<uint32_t>(idx_width, p, st);
     case 64: return launch_take_v<unsigned long long>(idx_width, p, st);
-    case 1: AG_FAIL(AG_ERR_NOT_IMPLEMENTED, "take: boolean values are not implemented yet");
+    case 1:
+      if (reinterpret_cast<uintptr_t>(out) & 3) AG_FAIL(AG_ERR_INVALID, "take: boolean output bitmap must be 4-byte aligned");
+      return launch_take_bool(idx_width, p, st);
     default: AG_FAIL(AG_ERR_INVALID, "take: invalid values byte width for take");  // vector_selection.go:1190
   }
 }

@@ -864,11 +864,10 @@ Status PrimitiveFilterExec(KernelCtx* ctx, const ExecSpan& batch, ExecResult* ou
   out->nulls = (vn == 0 && (sel == DropNulls || fn == 0)) ? 0 : kUnknownNullCount;  // :464-468
   const bool allocate_validity = vn != 0 || fn != 0;                                  // :473
   const int bw = BitWidth(values.type);
-  if (bw == 1) return Status::NotImplemented("filter on boolean values is not accelerated (see DESIGN.md, reference quirks)");
   // preallocateData (:83-93)
   out->type = values.type; out->len = out_len; out->offset = 0;
   std::shared_ptr<Buffer> data, valid;
-  RETURN_NOT_OK(ctx->Allocate(out_len * (bw / 8), &data));
+  RETURN_NOT_OK(ctx->Allocate(bw == 1 ? ((out_len + 31) / 32) * 4 : out_len * (bw / 8), &data));
   out->buffers[1].buf = data->data(); out->buffers[1].len = data->size(); out->buffers[1].owner = data; out->buffers[1].self_alloc = true;
   if (allocate_validity) {
     RETURN_NOT_OK(ctx->Allocate(((out_len + 31) / 32) * 4, &valid));
@@ -890,11 +889,10 @@ Status PrimitiveTakeExec(KernelCtx* ctx, const ExecSpan& batch, ExecResult* out)
   RETURN_NOT_OK(values.UpdateNullCount(&vn));
   RETURN_NOT_OK(indices.UpdateNullCount(&in_));
   const int bw = BitWidth(values.type);
-  if (bw == 1) return Status::NotImplemented("take on boolean values is not accelerated yet");
   const bool allocate_validity = vn != 0 || in_ != 0;  // :1175
   out->type = values.type; out->len = indices.len; out->offset = 0;
   std::shared_ptr<Buffer> data, valid, word;
-  RETURN_NOT_OK(ctx->Allocate(indices.len * (bw / 8), &data));
+  RETURN_NOT_OK(ctx->Allocate(bw == 1 ? ((indices.len + 31) / 32) * 4 : indices.len * (bw / 8), &data));
   out->buffers[1].buf = data->data(); out->buffers[1].len = data->size(); out->buffers[1].owner = data; out->buffers[1].self_alloc = true;
   if (allocate_validity) {
     RETURN_NOT_OK(ctx->Allocate(((indices.len + 31) / 32) * 4, &valid));

@@ -482,6 +482,31 @@ static inline void copy_elem(void* out, int64_t opos, const void* vals, int64_t 
 int ref_filter_primitive(int bit_width, const void* vals, const uint8_t* vvalid, int64_t voff,
                          const uint8_t* mask, const uint8_t* mvalid, int64_t moff, int64_t n,
                          int null_selection, void* out, uint8_t* out_valid, int64_t* out_len, int64_t* out_nulls) {
+  if (bit_width == 1) {
+    /* boolean values (boolFilterWriter :423-447).  Row rule of the default branch; NB the
+     * reference's WriteValue does not advance its output position (:433-436) — we restate the
+     * documented behaviour (what every other width does), see DESIGN.md "reference quirks". */
+    int64_t opos = 0, nulls = 0;
+    for (int64_t i = 0; i < n; ++i) {
+      const int mv = mvalid ? bit_is_set(mvalid, moff + i) : 1;
+      const int m = bit_is_set(mask, moff + i);
+      if (mv && m) {
+        const int v = vvalid ? bit_is_set(vvalid, voff + i) : 1;
+        if (out_valid) set_bit_to(out_valid, opos, v);
+        nulls += !v;
+        set_bit_to((uint8_t*)out, opos, bit_is_set((const uint8_t*)vals, voff + i));
+        ++opos;
+      } else if (!mv && null_selection == 1) {
+        if (out_valid) set_bit_to(out_valid, opos, 0);
+        set_bit_to((uint8_t*)out, opos, 0);
+        ++nulls;
+        ++opos;
+      }
+    }
+    if (out_len) *out_len = opos;
+    if (out_nulls) *out_nulls = nulls;
+    return REF_OK;
+  }
   if (bit_width != 8 && bit_width != 16 && bit_width != 32 && bit_width != 64) return REF_ERR_TYPE;
   const int w = bit_width / 8;
   int64_t opos = 0, nulls = 0;
@@ -580,9 +605,9 @@ int ref_take_primitive(int bit_width, const void* vals, const uint8_t* vvalid, i
                        int idx_width, int idx_signed, const void* idx, const uint8_t* ivalid, int64_t ioff,
                        int64_t n, int bounds_check, void* out, uint8_t* out_valid,
                        int64_t* out_nulls, int64_t* bad_pos, int64_t* bad_index) {
-  if (bit_width != 8 && bit_width != 16 && bit_width != 32 && bit_width != 64) return REF_ERR_TYPE;
+  if (bit_width != 1 && bit_width != 8 && bit_width != 16 && bit_width != 32 && bit_width != 64) return REF_ERR_TYPE;
   if (idx_width != 8 && idx_width != 16 && idx_width != 32 && idx_width != 64) return REF_ERR_INDEX;
-  const int w = bit_width / 8;
+  const int w = bit_width / 8; /* 0 for boolean values: booleanTakeImpl :990-1074 */
   if (bad_pos) *bad_pos = REF_NO_ERROR_POS;
   if (bounds_check) {
     for (int64_t i = 0; i < n; ++i) {
@@ -609,10 +634,12 @@ int ref_take_primitive(int bit_width, const void* vals, const uint8_t* vvalid, i
       if (vvalid) ok = bit_is_set(vvalid, voff + (int64_t)v);
     }
     if (ok) {
-      copy_elem(out, i, vbase, (int64_t)v, w);
+      if (bit_width == 1) set_bit_to((uint8_t*)out, i, bit_is_set((const uint8_t*)vals, voff + (int64_t)v));
+      else copy_elem(out, i, vbase, (int64_t)v, w);
       if (out_valid) set_bit_to(out_valid, i, 1);
     } else {
-      memset((char*)out + i * w, 0, (size_t)w);
+      if (bit_width == 1) set_bit_to((uint8_t*)out, i, 0);
+      else memset((char*)out + i * w, 0, (size_t)w);
       if (out_valid) set_bit_to(out_valid, i, 0);
       ++nulls;
     }

@@ -282,3 +282,17 @@ def test_kleene_scalar_operands():
                 bcast = pc.Array.from_pylist([sv] * len(arr), pc.BOOL)
                 assert pc.CallFunction(name, [a, pc.Scalar(sv, pc.BOOL)]).to_pylist() == pc.CallFunction(name, [a, bcast]).to_pylist(), (name, sv, "right")
                 assert pc.CallFunction(name, [pc.Scalar(sv, pc.BOOL), a]).to_pylist() == pc.CallFunction(name, [bcast, a]).to_pylist(), (name, sv, "left")
+
+
+def test_boolean_values_filter_take_api():
+    # TestFilterBoolean / TestTakeBoolean-style literals (vector_selection_test.go)
+    T, F, U = True, False, None
+    v = pc.Array.from_pylist([T, F, U, T, F], pc.BOOL)
+    m = pc.Array.from_pylist([T, T, T, U, F], pc.BOOL)
+    assert pc.Filter(v, m, pc.DROP_NULLS).to_pylist() == [T, F, U]
+    assert pc.Filter(v, m, pc.EMIT_NULLS).to_pylist() == [T, F, U, U]
+    assert pc.Take(v, pc.Array.from_pylist([4, 0, 2, None, 1], pc.INT32)).to_pylist() == [F, T, U, U, F]
+    assert pc.Take(pc.Array.from_pylist([T, F, T], pc.BOOL), pc.Array.from_pylist([0, 1, 0], pc.INT8)).to_pylist() == [T, F, T]
+    with pytest.raises(pc.ArrowError) as e:
+        pc.Take(v, pc.Array.from_pylist([0, 5], pc.INT32))
+    assert e.value.sentinel == "ErrIndex"

@@ -205,3 +205,26 @@ def test_filter_100m_rows_config3(ag):
     want = np.zeros(w, dtype=np.int64); wl = C.c_int64()
     assert oracle.cpu().ref_filter_primitive(64, ptr(hv), None, 0, ptr(hm), None, 0, w, 0, ptr(want), None, C.byref(wl), None) == 0
     assert out.buf.to_numpy(np.int64, wl.value).tobytes() == want[: wl.value].tobytes()
+
+
+def test_boolean_values_filter(ag, cpu):
+    rng = np.random.default_rng(21)
+    for n in (1, 31, 32, 33, 1000, 32768, 32769, 200_001):
+        for sel in (0, 1):
+            for p_mask in (0.05, 0.5, 1.0):
+                for p_mnull, p_vnull in ((0, 0), (0.2, 0.2)):
+                    voff, moff = int(rng.integers(0, 13)), int(rng.integers(0, 9))
+                    vals = pack_bits(rng.random(n) < 0.5, voff)
+                    vvalid = pack_bits(rng.random(n) >= p_vnull, voff) if p_vnull else None
+                    mask = pack_bits(rng.random(n) < p_mask, moff)
+                    mvalid = pack_bits(rng.random(n) >= p_mnull, moff) if p_mnull else None
+                    want = np.zeros(n // 8 + 8, dtype=np.uint8); wv = np.zeros(n // 8 + 8, dtype=np.uint8); wl, wn = C.c_int64(), C.c_int64()
+                    assert cpu.ref_filter_primitive(1, ptr(vals), ptr(vvalid), voff, ptr(mask), ptr(mvalid), moff, n, sel, ptr(want), ptr(wv), C.byref(wl), C.byref(wn)) == 0
+                    got = np.zeros(n // 8 + 8, dtype=np.uint8); gv = np.zeros(n // 8 + 8, dtype=np.uint8) if (p_mnull or p_vnull) else None
+                    gl, gn = C.c_int64(), C.c_int64()
+                    ag.call("ag_filter_primitive", 1, ptr(vals), ptr(vvalid), voff, ptr(mask), ptr(mvalid), moff, n, sel, ptr(got), ptr(gv), C.byref(gl), C.byref(gn))
+                    assert gl.value == wl.value
+                    valid = unpack_bits(wv, 0, wl.value) if gv is not None else np.ones(wl.value, bool)
+                    if gv is not None:
+                        assert np.array_equal(unpack_bits(gv, 0, wl.value), valid) and gn.value == wn.value
+                    assert np.array_equal(unpack_bits(got, 0, wl.value)[valid], unpack_bits(want, 0, wl.value)[valid]), (n, sel, p_mask, p_mnull)

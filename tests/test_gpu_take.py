@@ -143,3 +143,26 @@ def test_take_125m_rows_config4_shard(ag):
     ag.call("ag_take_primitive_dev", 64, v.ptr, None, 0, nv, 32, 1, idx.ptr, None, 0, n, 1, out.ptr, None, bad.ptr, None)
     ag.call("ag_stream_sync", None)
     assert bad.get()[0] == 77_777_777
+
+
+def test_boolean_values_take(ag, cpu):
+    rng = np.random.default_rng(22)
+    for vlen in (1, 77, 10_000):
+        for n in (1, 31, 32, 33, 1000, 100_001):
+            for p_inull, p_vnull in ((0, 0), (0.2, 0.2)):
+                voff, ioff = int(rng.integers(0, 13)), int(rng.integers(0, 9))
+                vals = pack_bits(rng.random(vlen) < 0.5, voff)
+                vvalid = pack_bits(rng.random(vlen) >= p_vnull, voff) if p_vnull else None
+                idx = rng.integers(0, vlen, n).astype(np.int32)
+                ivalid = pack_bits(rng.random(n) >= p_inull, ioff) if p_inull else None
+                want = np.zeros(n // 8 + 8, dtype=np.uint8); wv = np.zeros(n // 8 + 8, dtype=np.uint8)
+                wn, wp, wi = C.c_int64(), C.c_int64(), C.c_int64()
+                assert cpu.ref_take_primitive(1, ptr(vals), ptr(vvalid), voff, vlen, 32, 1, ptr(idx), ptr(ivalid), ioff, n, 1, ptr(want), ptr(wv),
+                                              C.byref(wn), C.byref(wp), C.byref(wi)) == 0
+                got = np.zeros(n // 8 + 8, dtype=np.uint8); gv = np.zeros(n // 8 + 8, dtype=np.uint8) if (p_inull or p_vnull) else None
+                gn, gp, gi = C.c_int64(), C.c_int64(), C.c_int64()
+                ag.call("ag_take_primitive", 1, ptr(vals), ptr(vvalid), voff, vlen, 32, 1, ptr(idx), ptr(ivalid), ioff, n, 1, ptr(got), ptr(gv),
+                        C.byref(gn), C.byref(gp), C.byref(gi))
+                assert np.array_equal(unpack_bits(got, 0, n), unpack_bits(want, 0, n)), (vlen, n, p_inull)
+                if gv is not None:
+                    assert np.array_equal(unpack_bits(gv, 0, n), unpack_bits(wv, 0, n)) and gn.value == wn.value

@@ -249,3 +249,37 @@ def test_checked_overflow_cases(cpu, type_id):
         assert int(out[i]) == q
     b2[5] = 0
     assert cpu.ref_arith_checked(type_id, N.OP_DIV_CHECKED, 0, ptr(a), None, 0, ptr(b2), None, 0, ptr(out), n, C.byref(bad)) == 1 and bad.value == 5
+
+
+def test_boolean_values_filter_take_vs_pyarrow(cpu):
+    """bit-width-1 values: boolFilterWriter / booleanTakeImpl (vector_selection.go:423-447, 990-1074)
+    restated with the documented row semantics; pyarrow is the independent check."""
+    rng = np.random.default_rng(9)
+    for n in (1, 9, 64, 65, 1000):
+        vals = rng.random(n) < 0.5
+        vvalid = rng.random(n) < 0.8
+        mask = rng.random(n) < 0.4
+        mvalid = rng.random(n) < 0.85
+        voff, moff = 5, 3
+        bv, bvv, bm, bmv = pack_bits(vals, voff), pack_bits(vvalid, voff), pack_bits(mask, moff), pack_bits(mvalid, moff)
+        for sel, name in ((0, "drop"), (1, "emit_null")):
+            want = pc.filter(pa.array(vals, mask=~vvalid), pa.array(mask, mask=~mvalid), null_selection_behavior=name)
+            out = np.zeros(n // 8 + 2, dtype=np.uint8); ov = np.zeros(n // 8 + 2, dtype=np.uint8); ln, nulls = C.c_int64(), C.c_int64()
+            assert cpu.ref_filter_primitive(1, ptr(bv), ptr(bvv), voff, ptr(bm), ptr(bmv), moff, n, sel, ptr(out), ptr(ov), C.byref(ln), C.byref(nulls)) == 0
+            assert ln.value == len(want) and nulls.value == want.null_count
+            wv = np.array([x.is_valid for x in want], dtype=bool)
+            assert unpack_bits(ov, 0, ln.value).tolist() == wv.tolist()
+            wd = np.array([bool(x.as_py()) if x.is_valid else False for x in want], dtype=bool)
+            assert unpack_bits(out, 0, ln.value)[wv].tolist() == wd[wv].tolist()
+        idx = rng.integers(0, n, 2 * n).astype(np.int32)
+        ivalid = rng.random(2 * n) < 0.9
+        want = pc.take(pa.array(vals, mask=~vvalid), pa.array(idx, mask=~ivalid))
+        out = np.zeros(2 * n // 8 + 2, dtype=np.uint8); ov = np.zeros(2 * n // 8 + 2, dtype=np.uint8)
+        nulls, bp, bi = C.c_int64(), C.c_int64(), C.c_int64()
+        biv = pack_bits(ivalid, 2)
+        assert cpu.ref_take_primitive(1, ptr(bv), ptr(bvv), voff, n, 32, 1, ptr(idx), ptr(biv), 2, 2 * n, 1, ptr(out), ptr(ov),
+                                      C.byref(nulls), C.byref(bp), C.byref(bi)) == 0
+        wv = np.array([x.is_valid for x in want], dtype=bool)
+        assert unpack_bits(ov, 0, 2 * n).tolist() == wv.tolist() and nulls.value == want.null_count
+        wd = np.array([bool(x.as_py()) if x.is_valid else False for x in want], dtype=bool)
+        assert unpack_bits(out, 0, 2 * n)[wv].tolist() == wd[wv].tolist()
