@@ -10,12 +10,14 @@
 // One add per 24 bytes -> no tensor cores, no shared-memory reuse: the job is to keep
 // >= 64 KB of 128-bit loads in flight per SM and to write with full 128-byte lines.
 //
-// Layout: 256-thread blocks, persistent grid of 148 x 8 blocks; each thread moves 4 independent
-// 16-byte vectors per operand per iteration (ld.global.cs / st.global.cs — streaming, evict
-// first: every byte is touched once).  Pointers that are only element-aligned (Arrow slices,
-// Appendix D of SURVEY.md) take the scalar grid-stride path with the same arithmetic.
+// Layout: 256-thread blocks, one resident wave (SMs x occupancy); a block streams contiguous
+// 4096-row tiles, each thread moving 4 independent 16-byte vectors per operand at a time
+// (ld.global.cs / st.global.cs — streaming, evict first: every byte is touched once).  A chunked
+// call is ONE launch over all its aligned spans.  Pointers that are only element-aligned (Arrow
+// slices, Appendix D of SURVEY.md) take the element-wise path with the same arithmetic.
 #include "common.cuh"
 
+#include <stdlib.h>
 #include <type_traits>
 #include <vector>
 
@@ -61,46 +63,6 @@ __device__ __forceinline__ void stv(T* p, int64_t vi, const Vec<T, 16 / sizeof(T
 // ---------------------------------------------------------------- binary -----------
 template <typename T, typename Op, int kShape>
 __global__ void __launch_bounds__(kEwThreads)
-binary_vec_kernel(const T* __restrict__ l, const T* __restrict__ r, T* __restrict__ out, int64_t n, T scalar) {
-  constexpr int N = 16 / sizeof(T);
-  const int64_t nvec = n / N;
-  const int64_t stride = (int64_t)gridDim.x * kEwThreads;
-  int64_t vi = (int64_t)blockIdx.x * kEwThreads + threadIdx.x;
-  for (; vi + (kEwUnroll - 1) * stride < nvec; vi += kEwUnroll * stride) {
-    Vec<T, N> a[kEwUnroll], b[kEwUnroll];
-#pragma unroll
-    for (int k = 0; k < kEwUnroll; ++k) {
-      if (kShape != AG_SHAPE_SA) a[k] = ldv(l, vi + k * stride);
-      if (kShape != AG_SHAPE_AS) b[k] = ldv(r, vi + k * stride);
-    }
-#pragma unroll
-    for (int k = 0; k < kEwUnroll; ++k) {
-      Vec<T, N> o;
-#pragma unroll
-      for (int e = 0; e < N; ++e)
-        o.v[e] = Op::template apply<T>(kShape == AG_SHAPE_SA ? scalar : a[k].v[e], kShape == AG_SHAPE_AS ? scalar : b[k].v[e]);
-      stv(out, vi + k * stride, o);
-    }
-  }
-  for (; vi < nvec; vi += stride) {
-    Vec<T, N> a, b, o;
-    if (kShape != AG_SHAPE_SA) a = ldv(l, vi);
-    if (kShape != AG_SHAPE_AS) b = ldv(r, vi);
-#pragma unroll
-    for (int e = 0; e < N; ++e)
-      o.v[e] = Op::template apply<T>(kShape == AG_SHAPE_SA ? scalar : a.v[e], kShape == AG_SHAPE_AS ? scalar : b.v[e]);
-    stv(out, vi, o);
-  }
-  // tail (< N elements): block 0
-  if (blockIdx.x == 0) {
-    const int64_t i = nvec * N + threadIdx.x;
-    if (i < n)
-      out[i] = Op::template apply<T>(kShape == AG_SHAPE_SA ? scalar : l[i], kShape == AG_SHAPE_AS ? scalar : r[i]);
-  }
-}
-
-template <typename T, typename Op, int kShape>
-__global__ void __launch_bounds__(kEwThreads)
 binary_scalar_kernel(const T* __restrict__ l, const T* __restrict__ r, T* __restrict__ out, int64_t n, T scalar) {
   const int64_t stride = (int64_t)gridDim.x * kEwThreads;
   int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x;
@@ -121,6 +83,9 @@ binary_scalar_kernel(const T* __restrict__ l, const T* __restrict__ r, T* __rest
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 template <typename T, typename Op, int kShape>
+static ag_status launch_single_span(const T* l, const T* r, T* out, int64_t n, T scalar, cudaStream_t st);
+
+template <typename T, typename Op, int kShape>
 static ag_status launch_binary_t(const void* l, const void* r, void* out, int64_t n, const void* scalar_host, cudaStream_t st) {
   T scalar = T(0);
   if (kShape != AG_SHAPE_AA) scalar = *reinterpret_cast<const T*>(scalar_host);
@@ -130,8 +95,7 @@ static ag_status launch_binary_t(const void* l, const void* r, void* out, int64_
   constexpr int N = 16 / sizeof(T);
   const bool vec = aligned16(out) && (kShape == AG_SHAPE_SA || aligned16(l)) && (kShape == AG_SHAPE_AS || aligned16(r));
   if (vec) {
-    const int grid = grid_one_wave(binary_vec_kernel<T, Op, kShape>, kEwThreads, (n / N + kEwThreads * kEwUnroll) / (kEwThreads * kEwUnroll));
-    binary_vec_kernel<T, Op, kShape><<<grid, kEwThreads, 0, st>>>(lp, rp, op, n, scalar);
+    return launch_single_span<T, Op, kShape>(lp, rp, op, n, scalar, st);
   } else {
     const int grid = grid_one_wave(binary_scalar_kernel<T, Op, kShape>, kEwThreads, (n + kEwThreads * kEwUnroll - 1) / (kEwThreads * kEwUnroll));
     binary_scalar_kernel<T, Op, kShape><<<grid, kEwThreads, 0, st>>>(lp, rp, op, n, scalar);
@@ -198,23 +162,27 @@ struct SpanDesc {
   long long first_tile;  // number of tiles before this span
 };
 
-template <typename T, typename Op, int kShape>
+// kSingle: one span passed by value (the contiguous call) — same tile loop, no table, no search.
+template <typename T, typename Op, int kShape, bool kSingle>
 __global__ void __launch_bounds__(kEwThreads)
-binary_spans_kernel(const SpanDesc* __restrict__ spans, int n_spans, long long total_tiles, T scalar) {
+binary_spans_kernel(const SpanDesc* __restrict__ spans, int n_spans, long long total_tiles, T scalar, SpanDesc single) {
   constexpr int N = 16 / sizeof(T);
   __shared__ int s_span;
   for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-    if (threadIdx.x == 0) {
-      int lo = 0, hi = n_spans - 1;  // last span with first_tile <= tile
-      while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (spans[mid].first_tile <= tile) lo = mid; else hi = mid - 1;
+    SpanDesc sp = single;
+    if (!kSingle) {
+      if (threadIdx.x == 0) {
+        int lo = 0, hi = n_spans - 1;  // last span with first_tile <= tile
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (spans[mid].first_tile <= tile) lo = mid; else hi = mid - 1;
+        }
+        s_span = lo;
       }
-      s_span = lo;
+      __syncthreads();
+      sp = spans[s_span];
+      __syncthreads();
     }
-    __syncthreads();
-    const SpanDesc sp = spans[s_span];
-    __syncthreads();
     const long long e0 = (tile - sp.first_tile) * kSpanTile;
     const int len = (int)((sp.n - e0 < kSpanTile) ? (sp.n - e0) : kSpanTile);
     const T* l = reinterpret_cast<const T*>(sp.l) + (kShape == AG_SHAPE_SA ? 0 : e0);
@@ -258,12 +226,23 @@ binary_spans_kernel(const SpanDesc* __restrict__ spans, int n_spans, long long t
   }
 }
 
+// The contiguous call: one span by value through the same tile kernel (contiguous 32 KB tiles per
+// block iteration measured 99.5 % of the HBM copy peak vs 95.5 % for the grid-strided loop).
+template <typename T, typename Op, int kShape>
+static ag_status launch_single_span(const T* l, const T* r, T* out, int64_t n, T scalar, cudaStream_t st) {
+  SpanDesc sp{l, r, out, (long long)n, 0};
+  const long long tiles = (n + kSpanTile - 1) / kSpanTile;
+  const int grid = grid_one_wave(binary_spans_kernel<T, Op, kShape, true>, kEwThreads, tiles);
+  binary_spans_kernel<T, Op, kShape, true><<<grid, kEwThreads, 0, st>>>(nullptr, 1, tiles, scalar, sp);
+  return check_launch("binary_spans_kernel");
+}
+
 template <typename T, typename Op, int kShape>
 static ag_status launch_spans_t(const SpanDesc* d_spans, int n_spans, long long total_tiles, const void* scalar_host, cudaStream_t st) {
   T scalar = T(0);
   if (kShape != AG_SHAPE_AA) scalar = *reinterpret_cast<const T*>(scalar_host);
-  const int grid = grid_one_wave(binary_spans_kernel<T, Op, kShape>, kEwThreads, total_tiles);
-  binary_spans_kernel<T, Op, kShape><<<grid, kEwThreads, 0, st>>>(d_spans, n_spans, total_tiles, scalar);
+  const int grid = grid_one_wave(binary_spans_kernel<T, Op, kShape, false>, kEwThreads, total_tiles);
+  binary_spans_kernel<T, Op, kShape, false><<<grid, kEwThreads, 0, st>>>(d_spans, n_spans, total_tiles, scalar, SpanDesc{});
   return check_launch("binary_spans_kernel");
 }
 template <typename T, typename Op>

@@ -8,27 +8,37 @@
 //
 // Shape of the reduction (fixed => the float64 result is a pure function of (data, n)):
 //   * the input is viewed as PAIRS (x[2j], x[2j+1]); an odd last element is folded in at the end;
-//   * G = sum_grid(n) blocks of 256 threads; thread t of the grid owns pairs t, t+S, t+2S, ...
-//     (S = 256*G), with 4 pair-loads in flight per iteration, each feeding its own two
-//     accumulators (8 independent chains per thread);
+//   * G = sum_grid(n) blocks of 256 threads (at most 148 x 8, a constant); block b streams the
+//     contiguous 2048-pair (32 KB) tiles b, b+G, ...; in a tile thread t owns pairs t, t+256, ...
+//     with 8 pair-loads in flight, load k feeding accumulator pair k % 4 (8 chains per thread);
 //   * thread sum -> warp xor-shuffle tree -> block tree (fixed) -> partials[G];
 //   * the last block to finish (ticket) reduces partials[] with the same fixed tree.
 // 16-byte aligned inputs use 128-bit ld.global.cs; 8-byte aligned ones use two 64-bit loads
 // with the SAME pair->thread mapping, so alignment never changes the result.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace ag {
 
 constexpr int kSumThreads = 256;
-constexpr int kSumUnroll = 4;
-constexpr int kSumBlocksPerSM = 8;  // 1184 blocks (a 888-block single wave measured 25 % slower)
-constexpr int kSumMaxBlocks = 148 * kSumBlocksPerSM;  // fixed: independent of the SM count found
+constexpr int kSumLoads = 8;                                  // 16-byte pair loads in flight per thread
+constexpr int kSumAcc = 4;                                    // accumulator pairs per thread (slot = load % 4)
+constexpr int kSumTilePairs = kSumThreads * kSumLoads;        // 2048 pairs = 32 KB per block iteration
+constexpr int kSumBlocksPerSM = 8;                            // measured at 100M rows: 296..888 blocks 126-135 us, 1184 blocks 123.6 us
+constexpr int kSumMaxBlocks = 148 * kSumBlocksPerSM;          // fixed (not queried): the result must not depend on the device
 
 static inline int sum_grid(size_t n_pairs) {
-  // a block-iteration consumes 256*4 pairs; small inputs get few blocks (latency), big ones 1184
-  size_t want = (n_pairs + (size_t)kSumThreads * kSumUnroll - 1) / ((size_t)kSumThreads * kSumUnroll);
+  // small inputs get few blocks (latency), big ones the fixed one-wave grid
+  size_t want = (n_pairs + kSumTilePairs - 1) / kSumTilePairs;
   if (want < 1) want = 1;
-  if (want > (size_t)kSumMaxBlocks) want = kSumMaxBlocks;
+  static int cap = 0;
+  if (cap == 0) {
+    const char* e = getenv("AG_SUM_BLOCKS");  // experiments only
+    cap = (e && atoi(e) > 0) ? atoi(e) : kSumMaxBlocks;
+    if (cap > kMaxPartials) cap = kMaxPartials;
+  }
+  if (want > (size_t)cap) want = cap;
   return (int)want;
 }
 
@@ -80,27 +90,29 @@ sum_kernel(const T* __restrict__ in, size_t n, T* __restrict__ partials, unsigne
   __shared__ T smem[8];
   __shared__ bool is_last;
   const size_t n_pairs = n >> 1;
-  const size_t stride = (size_t)gridDim.x * kSumThreads;
-  T ax[kSumUnroll], ay[kSumUnroll];
+  const size_t n_tiles = (n_pairs + kSumTilePairs - 1) / kSumTilePairs;
+  T ax[kSumAcc], ay[kSumAcc];
 #pragma unroll
-  for (int k = 0; k < kSumUnroll; ++k) { ax[k] = T(0); ay[k] = T(0); }
-
-  size_t j = (size_t)blockIdx.x * kSumThreads + threadIdx.x;
-  // main loop: all 4 loads in range
-  for (; j + (kSumUnroll - 1) * stride < n_pairs; j += kSumUnroll * stride) {
-    Pair<T> p[kSumUnroll];
+  for (int k = 0; k < kSumAcc; ++k) { ax[k] = T(0); ay[k] = T(0); }
+  // Block b streams the contiguous 32 KB tiles b, b+G, b+2G, ...; inside a tile thread t owns
+  // pairs t, t+256, ... (8 independent 16-byte loads in flight), load k feeds accumulator k % 4.
+  for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const size_t j0 = tile * kSumTilePairs + threadIdx.x;
+    if (j0 + (size_t)(kSumLoads - 1) * kSumThreads < n_pairs) {
+      Pair<T> p[kSumLoads];
 #pragma unroll
-    for (int k = 0; k < kSumUnroll; ++k) p[k] = load_pair<T, kAligned>(in, j + k * stride);
+      for (int k = 0; k < kSumLoads; ++k) p[k] = load_pair<T, kAligned>(in, j0 + (size_t)k * kSumThreads);
 #pragma unroll
-    for (int k = 0; k < kSumUnroll; ++k) { ax[k] = ax[k] + p[k].x; ay[k] = ay[k] + p[k].y; }
-  }
-  // remainder: same accumulator assignment (slot k gets pair j + k*stride)
+      for (int k = 0; k < kSumLoads; ++k) { ax[k % kSumAcc] = ax[k % kSumAcc] + p[k].x; ay[k % kSumAcc] = ay[k % kSumAcc] + p[k].y; }
+    } else {
 #pragma unroll
-  for (int k = 0; k < kSumUnroll; ++k) {
-    const size_t jj = j + k * stride;
-    if (jj < n_pairs) {
-      const Pair<T> p = load_pair<T, kAligned>(in, jj);
-      ax[k] = ax[k] + p.x; ay[k] = ay[k] + p.y;
+      for (int k = 0; k < kSumLoads; ++k) {
+        const size_t jj = j0 + (size_t)k * kSumThreads;
+        if (jj < n_pairs) {
+          const Pair<T> p = load_pair<T, kAligned>(in, jj);
+          ax[k % kSumAcc] = ax[k % kSumAcc] + p.x; ay[k % kSumAcc] = ay[k % kSumAcc] + p.y;
+        }
+      }
     }
   }
   T v = ((ax[0] + ay[0]) + (ax[1] + ay[1])) + ((ax[2] + ay[2]) + (ax[3] + ay[3]));

@@ -44,7 +44,8 @@ def test_reference_known_answers(ag):
     ag.call("ag_sum_i64", ptr(xi), xi.size, C.byref(r))
     assert r.value == 49995000
     ru = C.c_uint64()
-    ag.call("ag_sum_u64", ptr(xi.astype(np.uint64)), xi.size, C.byref(ru))
+    xu = xi.astype(np.uint64)  # keep the buffer alive across the call
+    ag.call("ag_sum_u64", ptr(xu), xu.size, C.byref(ru))
     assert ru.value == 49995000
     # empty (float64_test.go:43-48)
     e = np.zeros(0)

@@ -69,7 +69,8 @@ def test_reference_literal_cases(ag, cpu):
     both(ag, cpu, 32, vals, None, 0, 3, 32, 1, np.array([0, 9, 0], dtype=np.int32), pack_bits([1, 0, 1]), 0, 3)
     # empty
     out = np.zeros(1, dtype=np.uint32)
-    ag.call("ag_take_primitive", 32, ptr(vals), None, 0, 3, 32, 1, ptr(np.zeros(1, dtype=np.int32)), None, 0, 0, 1, ptr(out), None, None, None, None)
+    no_idx = np.zeros(1, dtype=np.int32)
+    ag.call("ag_take_primitive", 32, ptr(vals), None, 0, 3, 32, 1, ptr(no_idx), None, 0, 0, 1, ptr(out), None, None, None, None)
 
 
 @pytest.mark.parametrize("bw", [8, 16, 32, 64])

@@ -20,8 +20,9 @@ def test_sum_known_answers(cpu, ref):
     x = np.arange(10000, dtype=np.float64)
     assert cpu.ref_sum_f64_avx2_order(ptr(x), x.size) == 49995000.0
     assert cpu.ref_sum_f64_sequential(ptr(x), x.size) == 49995000.0
-    assert cpu.ref_sum_i64(ptr(x.astype(np.int64)), x.size) == 49995000
-    assert cpu.ref_sum_u64(ptr(x.astype(np.uint64)), x.size) == 49995000
+    xi, xu = x.astype(np.int64), x.astype(np.uint64)  # keep the buffers alive across the calls
+    assert cpu.ref_sum_i64(ptr(xi), x.size) == 49995000
+    assert cpu.ref_sum_u64(ptr(xu), x.size) == 49995000
     assert cpu.ref_sum_f64_avx2_order(None, 0) == 0.0
     for isa in ISAS:
         r = C.c_double()
@@ -51,7 +52,8 @@ def test_sum_ints_wrap(cpu, ref, n):
         getattr(ref, f"sum_int64_{isa}")(ptr(x), n, C.addressof(r))
         assert cpu.ref_sum_i64(ptr(x), n) == r.value
         ru = C.c_uint64()
-        getattr(ref, f"sum_uint64_{isa}")(ptr(x.view(np.uint64)), n, C.addressof(ru))
+        xu = x.view(np.uint64)
+        getattr(ref, f"sum_uint64_{isa}")(ptr(xu), n, C.addressof(ru))
         assert cpu.ref_sum_u64(ptr(x), n) == ru.value
 
 
