@@ -18,6 +18,7 @@
 #include "common.cuh"
 
 #include <stdlib.h>
+#include <cuda/barrier>
 
 namespace ag {
 
@@ -142,6 +143,104 @@ sum_kernel(const T* __restrict__ in, size_t n, T* __restrict__ partials, unsigne
   }
 }
 
+
+// ---------------------------------------------------------------- TMA-staged variant ---------
+// Same reduction, but the input is staged through shared memory by the TMA engine instead of
+// per-thread loads: one elected thread issues cp.async.bulk (1-D bulk copy, SASS UBLKCP) of a
+// 16 KB chunk into a 4-deep ring of shared-memory stages, completion is signalled on an mbarrier
+// (expect-tx bytes), and the 256 threads read the stage with conflict-free LDS.128.  Bytes in
+// flight per SM no longer depend on registers or occupancy: 3 resident blocks x 4 stages x 16 KB
+// = 192 KB.  Requires a 16-byte aligned input; the (< 2048-element) tail is folded in by the last
+// block.  Fixed shape (444 blocks, static chunk -> block map) => deterministic like sum_kernel.
+namespace cde = cuda::device::experimental;
+using block_barrier = cuda::barrier<cuda::thread_scope_block>;
+
+constexpr int kTmaStages = 4;
+constexpr int kTmaChunkElems = 2048;  // 16 KB of 8-byte elements
+constexpr int kTmaBlocks = 148 * 3;
+
+template <typename T>
+__global__ void __launch_bounds__(kSumThreads)
+sum_tma_kernel(const T* __restrict__ in, size_t n, T* __restrict__ partials, unsigned* __restrict__ ticket, T* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char tma_smem[];
+  T(*buf)[kTmaChunkElems] = reinterpret_cast<T(*)[kTmaChunkElems]>(tma_smem);
+#pragma nv_diag_suppress static_var_with_dynamic_init
+  __shared__ block_barrier bar[kTmaStages];
+  __shared__ T smem[8];
+  __shared__ bool is_last;
+  const size_t n_chunks = n / kTmaChunkElems;
+  constexpr unsigned kBytes = kTmaChunkElems * sizeof(T);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kTmaStages; ++s) init(&bar[s], kSumThreads);
+    cde::fence_proxy_async_shared_cta();
+  }
+  __syncthreads();
+  block_barrier::arrival_token token[kTmaStages];
+  auto issue = [&](int s, size_t chunk) {
+    if (threadIdx.x == 0) {
+      cde::cp_async_bulk_global_to_shared(buf[s], in + chunk * kTmaChunkElems, kBytes, bar[s]);
+      token[s] = cuda::device::barrier_arrive_tx(bar[s], 1, kBytes);
+    } else {
+      token[s] = bar[s].arrive();
+    }
+  };
+#pragma unroll
+  for (int s = 0; s < kTmaStages; ++s) {
+    const size_t chunk = blockIdx.x + (size_t)s * gridDim.x;
+    if (chunk < n_chunks) issue(s, chunk);
+  }
+  T ax[kSumAcc], ay[kSumAcc];
+#pragma unroll
+  for (int k = 0; k < kSumAcc; ++k) { ax[k] = T(0); ay[k] = T(0); }
+  for (size_t base = blockIdx.x; base < n_chunks; base += (size_t)kTmaStages * gridDim.x) {
+#pragma unroll
+    for (int s = 0; s < kTmaStages; ++s) {
+      const size_t chunk = base + (size_t)s * gridDim.x;
+      if (chunk >= n_chunks) break;
+      bar[s].wait(std::move(token[s]));
+      const ulonglong2* v2 = reinterpret_cast<const ulonglong2*>(buf[s]);
+#pragma unroll
+      for (int k = 0; k < kTmaChunkElems / 2 / kSumThreads; ++k) {  // 4 pairs per thread
+        const ulonglong2 v = v2[k * kSumThreads + threadIdx.x];
+        ax[k % kSumAcc] = ax[k % kSumAcc] + *reinterpret_cast<const T*>(&v.x);
+        ay[k % kSumAcc] = ay[k % kSumAcc] + *reinterpret_cast<const T*>(&v.y);
+      }
+      __syncthreads();  // every thread is done with stage s before it is refilled
+      const size_t next = chunk + (size_t)kTmaStages * gridDim.x;
+      if (next < n_chunks) issue(s, next);
+    }
+  }
+  T v = ((ax[0] + ay[0]) + (ax[1] + ay[1])) + ((ax[2] + ay[2]) + (ax[3] + ay[3]));
+  v = block_tree_sum(v, smem);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = v;
+    __threadfence();
+    const unsigned t = atomicAdd(ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  T acc = T(0);
+  for (unsigned i = threadIdx.x; i < gridDim.x; i += kSumThreads) acc = acc + __ldcg(partials + i);
+  acc = block_tree_sum(acc, smem);
+  // tail (< one chunk): thread t takes elements t, t+256, ... of the remainder, fixed tree again
+  T tail = T(0);
+  for (size_t i = n_chunks * kTmaChunkElems + threadIdx.x; i < n; i += kSumThreads) tail = tail + in[i];
+  tail = block_tree_sum(tail, smem);
+  if (threadIdx.x == 0) {
+    *out = acc + tail;
+    *ticket = 0;
+  }
+}
+
+static bool sum_use_tma() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("AG_SUM_TMA"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
 // Reference association order (float64_avx2_amd64.s:36-43,86-174): 32 interleaved serial
 // chains over the first n&~31 elements — lane j of ONE warp owns chain j, so every load is a
 // fully coalesced 256-byte row — combined as (y0+y4)+(y2+y6) + (y1+y5)+(y3+y7) per ymm lane,
@@ -190,8 +289,18 @@ static ag_status launch_sum(const T* d_in, size_t n, T* d_res, cudaStream_t st) 
   if ((reinterpret_cast<uintptr_t>(d_in) & 7) != 0) AG_FAIL(AG_ERR_INVALID, "sum: input is not 8-byte aligned");
   Workspace* ws;
   AG_TRY(get_workspace(st, &ws));
-  const int grid = sum_grid(n >> 1);
   const bool aligned = (reinterpret_cast<uintptr_t>(d_in) & 15) == 0;
+  if (sum_use_tma() && aligned && n >= (size_t)kTmaChunkElems * kTmaBlocks) {
+    constexpr size_t smem = (size_t)kTmaStages * kTmaChunkElems * sizeof(T);
+    static std::atomic<bool> attr{false};
+    if (!attr.load()) {
+      AG_CUDA_TRY(cudaFuncSetAttribute((const void*)sum_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr.store(true);
+    }
+    sum_tma_kernel<T><<<kTmaBlocks, kSumThreads, smem, st>>>(d_in, n, (T*)ws->partials, ws->ticket, d_res);
+    return check_launch("sum_tma_kernel");
+  }
+  const int grid = sum_grid(n >> 1);
   if (aligned)
     sum_kernel<T, true><<<grid, kSumThreads, 0, st>>>(d_in, n, (T*)ws->partials, ws->ticket, d_res);
   else
