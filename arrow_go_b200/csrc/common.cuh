@@ -114,36 +114,6 @@ inline int grid_for(int64_t work_items, int items_per_block, int blocks_per_sm) 
 // ---------------------------------------------------------------- device helpers --
 #ifdef __CUDACC__
 
-// Streaming 128-bit load / store (evict-first: every byte on this path is touched once).
-template <typename V>
-__device__ __forceinline__ V ld_stream(const V* p) { return __ldcs(p); }
-template <typename V>
-__device__ __forceinline__ void st_stream(V* p, V v) { __stcs(p, v); }
-
-// L2 eviction-priority policies (createpolicy) for loads whose line is, or is not, needed again:
-// the fused filter re-reads the selected rows of a tile a few microseconds after streaming it.
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-template <typename T>
-__device__ __forceinline__ T ld_l2_hint(const T* p, uint64_t policy) {
-  T v;
-  if constexpr (sizeof(T) == 8) {
-    unsigned long long r;
-    asm volatile("ld.global.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(r) : "l"(p), "l"(policy));
-    v = *reinterpret_cast<T*>(&r);
-  } else if constexpr (sizeof(T) == 4) {
-    unsigned r;
-    asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(policy));
-    v = *reinterpret_cast<T*>(&r);
-  } else {
-    v = *p;
-  }
-  return v;
-}
-
 // Read 32 bits of an LSB-first bitmap starting at absolute bit position `bit`
 // (relative to byte pointer `base`), touching only bytes in [lo_byte, hi_byte).
 // Bits that fall outside are returned as 0.  Interior reads use aligned 32-bit loads.

@@ -23,7 +23,6 @@
 namespace ag {
 
 constexpr int kCmpThreads = 256;
-constexpr int kCmpBlocksPerSM = 8;
 constexpr int kCmpBatch = 8;   // loads in flight per lane before the votes (16 -> 90 regs, 2 blocks/SM: measured slower)
 
 struct CmpEq { template <typename T> static __device__ __forceinline__ bool apply(T a, T b) { return a == b; } };

@@ -104,7 +104,6 @@ __device__ __forceinline__ unsigned long long lookback(unsigned long long* st, i
   return running;
 }
 
-struct FCmpNone { template <typename T> static __device__ __forceinline__ bool apply(T, T) { return false; } };
 struct FCmpEq { template <typename T> static __device__ __forceinline__ bool apply(T a, T b) { return a == b; } };
 struct FCmpNe { template <typename T> static __device__ __forceinline__ bool apply(T a, T b) { return a != b; } };
 struct FCmpGt { template <typename T> static __device__ __forceinline__ bool apply(T a, T b) { return a > b; } };

@@ -26,7 +26,6 @@ namespace ag {
 
 constexpr int kTkThreads = 256;
 constexpr int kTkUnroll = 4;
-constexpr int kTkBlocksPerSM = 8;
 
 struct TakeParams {
   const void* vals;       // element 0 of the values buffer

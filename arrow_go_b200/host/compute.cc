@@ -828,6 +828,39 @@ exec::ArrayKernelExec KleeneExec(int kop, int plain_bitop) {
   };
 }
 
+// isNullExec / isNotNullExec (scalar_comparisons.go:718-745): NullComputedNoPrealloc, MemNoPrealloc,
+// the output never has a validity bitmap
+Status IsNullExec(KernelCtx* ctx, const ExecSpan& batch, ExecResult* out) {
+  const ArraySpan& in = batch.values[0].array;
+  std::shared_ptr<Buffer> b;
+  RETURN_NOT_OK(ctx->AllocateBitmap(in.len, &b));  // zero-filled: "no validity buffer" means all false
+  if (in.buffers[0].buf) NATIVE(ag_bitmap_invert_dev(in.buffers[0].buf, in.offset, in.len, b->data(), 0, nullptr));
+  out->type = Type::BOOL; out->len = in.len; out->offset = 0; out->nulls = 0;
+  out->buffers[0] = exec::BufferSpan();
+  out->buffers[1].buf = b->data(); out->buffers[1].len = b->size(); out->buffers[1].owner = b; out->buffers[1].self_alloc = true;
+  return Status::OK();
+}
+Status IsNotNullExec(KernelCtx* ctx, const ExecSpan& batch, ExecResult* out) {
+  const ArraySpan& in = batch.values[0].array;
+  std::shared_ptr<Buffer> b;
+  RETURN_NOT_OK(ctx->AllocateBitmap(in.len, &b));
+  if (in.buffers[0].buf) NATIVE(ag_bitmap_copy_dev(in.buffers[0].buf, in.offset, in.len, b->data(), 0, nullptr));
+  else NATIVE(ag_bitmap_set_dev(b->data(), 0, in.len, 1, nullptr));  // memory.Set(0xFF)
+  out->type = Type::BOOL; out->len = in.len; out->offset = 0; out->nulls = 0;
+  out->buffers[0] = exec::BufferSpan();
+  out->buffers[1].buf = b->data(); out->buffers[1].len = b->size(); out->buffers[1].owner = b; out->buffers[1].self_alloc = true;
+  return Status::OK();
+}
+// isNanKernelExec (scalar_comparisons.go:754-765): the NE kernel with the input on both sides;
+// integer inputs are ConstBoolExec(false) (:747-752)
+Status IsNanExec(KernelCtx*, const ExecSpan& batch, ExecResult* out) {
+  const ArraySpan& in = batch.values[0].array;
+  if (!IsFloating(in.type)) { NATIVE(ag_bitmap_set_dev(out->buffers[1].buf, out->offset, batch.len, 0, nullptr)); return Status::OK(); }
+  NATIVE(ag_compare_dev((int)in.type, AG_CMP_NE, AG_SHAPE_AA, ValuesPtr(in), ValuesPtr(in), out->buffers[1].buf + out->offset / 8, batch.len,
+                        (int)(out->offset % 8), nullptr));
+  return Status::OK();
+}
+
 // NotExecKernel (scalar_boolean.go:336-347): invert data, share the validity buffer
 Status NotExec(KernelCtx*, const ExecSpan& batch, ExecResult* out) {
   const ArraySpan& in = batch.values[0].array;
@@ -1048,6 +1081,31 @@ FunctionRegistry* GetFunctionRegistry() {
       k.null_handling = exec::NullHandling::COMPUTED_NO_PREALLOC;
       k.can_write_into_slices = false;
       fn->AddKernel(std::move(k));
+      reg->AddFunction(fn, false);
+    }
+    // scalar_compare.go / scalar_comparisons.go:718-813: is_null, is_not_null, is_nan
+    for (auto& spec : std::vector<std::pair<const char*, exec::ArrayKernelExec>>{{"is_null", IsNullExec}, {"is_not_null", IsNotNullExec}}) {
+      auto fn = std::make_shared<ScalarFunction>(spec.first, 1);
+      exec::ScalarKernel k;
+      k.any_input_type = true;
+      k.out_type = BoolType;
+      k.exec = spec.second;
+      k.null_handling = exec::NullHandling::COMPUTED_NO_PREALLOC;
+      k.mem_alloc = exec::MemAlloc::NO_PREALLOC;
+      k.can_write_into_slices = false;
+      fn->AddKernel(std::move(k));
+      reg->AddFunction(fn, false);
+    }
+    {
+      auto fn = std::make_shared<ScalarFunction>("is_nan", 1);
+      for (Type t : kNumericTypes) {
+        exec::ScalarKernel k;
+        k.in_types = {t};
+        k.out_type = BoolType;
+        k.exec = IsNanExec;
+        k.null_handling = exec::NullHandling::OUTPUT_NOT_NULL;
+        fn->AddKernel(std::move(k));
+      }
       reg->AddFunction(fn, false);
     }
     // selection.go:593-650: array_filter / array_take vector functions + filter / take meta functions

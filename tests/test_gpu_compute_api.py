@@ -296,3 +296,18 @@ def test_boolean_values_filter_take_api():
     with pytest.raises(pc.ArrowError) as e:
         pc.Take(v, pc.Array.from_pylist([0, 5], pc.INT32))
     assert e.value.sentinel == "ErrIndex"
+
+
+def test_is_null_is_not_null_is_nan():
+    # scalar_compare_test.go TestIsNull / TestIsNaN shapes (kernels scalar_comparisons.go:718-813)
+    a = pc.Array.from_pylist([1.5, None, float("nan"), 0.0, None], pc.FLOAT64)
+    assert pc.CallFunction("is_null", [a]).to_pylist() == [False, True, False, False, True]
+    assert pc.CallFunction("is_not_null", [a]).to_pylist() == [True, False, True, True, False]
+    no_nulls = pc.Array.from_pylist([1, 2, 3], pc.INT32)
+    assert pc.CallFunction("is_null", [no_nulls]).to_pylist() == [False, False, False]
+    assert pc.CallFunction("is_not_null", [no_nulls]).to_pylist() == [True, True, True]
+    assert pc.CallFunction("is_nan", [no_nulls]).to_pylist() == [False, False, False]
+    nan = pc.CallFunction("is_nan", [pc.Array.from_pylist([1.5, float("nan"), float("inf"), -0.0], pc.FLOAT64)])
+    assert nan.to_pylist() == [False, True, False, False] and nan.type == pc.BOOL
+    s = pc.Array.from_pylist([None, 1, None, 4, 5, None, 7, 8, 9], pc.INT64).slice(1, 7)
+    assert pc.CallFunction("is_null", [s]).to_pylist() == [False, True, False, False, True, False, False]

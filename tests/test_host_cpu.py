@@ -57,7 +57,7 @@ def test_bench_config_spans():
 def test_registry_has_the_reference_function_names():
     names = set(pc.function_names())
     for n in ("add", "add_unchecked", "sub", "sub_unchecked", "subtract", "subtract_unchecked", "multiply", "multiply_unchecked",
-              "abs_unchecked", "negate_unchecked", "sign", "equal", "not_equal", "greater", "greater_equal", "less", "less_equal",
+              "abs", "abs_unchecked", "negate", "negate_unchecked", "sign", "is_null", "is_not_null", "is_nan", "equal", "not_equal", "greater", "greater_equal", "less", "less_equal",
               "and", "or", "xor", "and_not", "and_kleene", "or_kleene", "and_not_kleene", "not",
               "filter", "array_filter", "take", "array_take"):
         assert n in names, n
