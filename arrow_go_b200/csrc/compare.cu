@@ -23,6 +23,7 @@
 namespace ag {
 
 constexpr int kCmpThreads = 256;
+constexpr int kCmpFastBatch = 16;  // interior tiles: loads in flight per lane before the votes
 constexpr int kCmpBatch = 8;   // loads in flight per lane before the votes (16 -> 90 regs, 2 blocks/SM: measured slower)
 
 struct CmpEq { template <typename T> static __device__ __forceinline__ bool apply(T a, T b) { return a == b; } };
@@ -41,24 +42,46 @@ compare_kernel(const T* __restrict__ l, const T* __restrict__ r, T scalar,
   for (int64_t tile = warp_id; tile < n_tiles; tile += warps_total) {
     const int64_t w0 = tile << 5;
     uint32_t myword = 0;
+    const int64_t e_first = (w0 << 5) - shift;  // row of bit 0 of the tile's first word
+    if (e_first >= 0 && e_first + 1024 <= n) {
+      // interior tile: every row is in range — no per-row bounds tests, pointers advance by 32 rows
+      const T* lp = (kShape != AG_SHAPE_SA) ? l + e_first + lane : nullptr;
+      const T* rp = (kShape != AG_SHAPE_AS) ? r + e_first + lane : nullptr;
 #pragma unroll
-    for (int kb = 0; kb < 32; kb += kCmpBatch) {
-      T a[kCmpBatch], b[kCmpBatch];
-      bool inr[kCmpBatch];
+      for (int kb = 0; kb < 32; kb += kCmpFastBatch) {
+        T a[kCmpFastBatch], b[kCmpFastBatch];
 #pragma unroll
-      for (int u = 0; u < kCmpBatch; ++u) {
-        const int64_t e = ((w0 + kb + u) << 5) + lane - shift;
-        inr[u] = (e >= 0) && (e < n);
-        a[u] = scalar; b[u] = scalar;
-        if (inr[u]) {
-          if (kShape != AG_SHAPE_SA) a[u] = __ldcs(l + e);
-          if (kShape != AG_SHAPE_AS) b[u] = __ldcs(r + e);
+        for (int u = 0; u < kCmpFastBatch; ++u) {
+          a[u] = (kShape != AG_SHAPE_SA) ? __ldcs(lp + (kb + u) * 32) : scalar;
+          b[u] = (kShape != AG_SHAPE_AS) ? __ldcs(rp + (kb + u) * 32) : scalar;
+        }
+        __syncwarp();  // scheduling fence: issue the whole batch of loads before the first vote
+#pragma unroll
+        for (int u = 0; u < kCmpFastBatch; ++u) {
+          const uint32_t bits = __ballot_sync(0xffffffffu, Cmp::template apply<T>(a[u], b[u]));
+          if (lane == kb + u) myword = bits;
         }
       }
+    } else {
 #pragma unroll
-      for (int u = 0; u < kCmpBatch; ++u) {
-        const uint32_t bits = __ballot_sync(0xffffffffu, inr[u] && Cmp::template apply<T>(a[u], b[u]));
-        if (lane == kb + u) myword = bits;
+      for (int kb = 0; kb < 32; kb += kCmpBatch) {
+        T a[kCmpBatch], b[kCmpBatch];
+        bool inr[kCmpBatch];
+#pragma unroll
+        for (int u = 0; u < kCmpBatch; ++u) {
+          const int64_t e = ((w0 + kb + u) << 5) + lane - shift;
+          inr[u] = (e >= 0) && (e < n);
+          a[u] = scalar; b[u] = scalar;
+          if (inr[u]) {
+            if (kShape != AG_SHAPE_SA) a[u] = __ldcs(l + e);
+            if (kShape != AG_SHAPE_AS) b[u] = __ldcs(r + e);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kCmpBatch; ++u) {
+          const uint32_t bits = __ballot_sync(0xffffffffu, inr[u] && Cmp::template apply<T>(a[u], b[u]));
+          if (lane == kb + u) myword = bits;
+        }
       }
     }
     const int64_t w = w0 + lane;
