@@ -51,4 +51,14 @@ timed("greater_i64_scalar", lambda: N.call("ag_compare_dev", N.INT64, N.CMP_GT, 
 timed("filter_i64", lambda: N.call("ag_filter_primitive_dev", 64, b.ptr, None, 0, mask.ptr, None, 0, rows, 0, o.ptr, None, cnt, scal.ptr + 8, None))
 timed("fused_greater_filter_i64", lambda: N.call("ag_filter_compare_scalar_dev", N.INT64, N.CMP_GT, b.ptr, sc.ctypes.data, rows, o.ptr, cnt, scal.ptr + 8, None))
 timed("take_i64_i32", lambda: N.call("ag_take_primitive_dev", 64, b.ptr, None, 0, rows, 32, 1, idx.ptr, None, 0, rows, 1, o.ptr, None, bad.ptr, None))
+# the default compute.Add on integers is the CHECKED kernel (ScalarBinaryNotNull semantics)
+N.call("ag_generate_dev", 1, 0x94378165, -1000, 1000, a.ptr, rows, None)
+valid = DeviceBuffer(rows // 8 + 64)
+N.call("ag_generate_dev", 4, 0x1234, 9, 10, valid.ptr, rows, None)  # 90 % valid
+timed("add_checked_i64_nonull", lambda: N.call("ag_arith_checked_dev", N.INT64, N.OP_ADD_CHECKED, N.SHAPE_AA, a.ptr, None, 0, b.ptr, None, 0, o.ptr, rows, bad.ptr, None))
+timed("add_checked_i64_nulls", lambda: N.call("ag_arith_checked_dev", N.INT64, N.OP_ADD_CHECKED, N.SHAPE_AA, a.ptr, valid.ptr, 0, b.ptr, valid.ptr, 3, o.ptr, rows, bad.ptr, None))
+timed("add_unchecked_i64", lambda: N.call("ag_arith_binary_dev", N.INT64, N.OP_ADD, N.SHAPE_AA, a.ptr, b.ptr, o.ptr, rows, None))
+timed("bitmap_and_100m_bits", lambda: N.call("ag_bitmap_op_dev", N.BITOP_AND, valid.ptr, 0, mask.ptr, 5, o.ptr, 3, rows, None))
+timed("bitmap_popcount_100m_bits", lambda: N.call("ag_bitmap_popcount_dev", valid.ptr, 3, rows - 3, scal.ptr, None))
+timed("abs_f64", lambda: N.call("ag_arith_unary_same_dev", N.FLOAT64, N.OP_ABS, a.ptr, o.ptr, rows, None))
 print("selected rows:", cnt)
