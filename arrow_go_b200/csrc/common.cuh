@@ -116,32 +116,39 @@ inline int grid_for(int64_t work_items, int items_per_block, int blocks_per_sm) 
 
 // Read 32 bits of an LSB-first bitmap starting at absolute bit position `bit`
 // (relative to byte pointer `base`), touching only bytes in [lo_byte, hi_byte).
-// Bits that fall outside are returned as 0.  Interior reads use aligned 32-bit loads.
-__device__ __forceinline__ uint32_t bitmap_load32(const uint8_t* __restrict__ base, int64_t bit,
-                                                  int64_t lo_byte, int64_t hi_byte) {
-  // aligned 4-byte window index relative to the 4-byte aligned address at or below base
-  const uintptr_t addr = reinterpret_cast<uintptr_t>(base);
-  const int64_t mis = (int64_t)(addr & 3);       // base = abase + mis
-  const uint8_t* abase = base - mis;
-  const int64_t abit = bit + mis * 8;            // bit position relative to abase
-  const int64_t w = abit >> 5;                   // aligned word index (floor; abit >= 0 whenever any bit is valid)
-  const int sh = (int)(abit & 31);
-  const int64_t lo = lo_byte + mis, hi = hi_byte + mis;  // valid byte range relative to abase
-  auto load_word = [&](int64_t wi) -> uint32_t {
-    const int64_t b0 = wi * 4;
-    if (b0 >= lo && b0 + 4 <= hi) return *reinterpret_cast<const uint32_t*>(abase + b0);
-    uint32_t v = 0;
+// Bits that fall outside are returned as 0.  Interior windows are two aligned 32-bit loads and
+// a funnel shift; windows that touch the ends of the range go through the (out-of-line) byte-wise
+// path so that no byte outside the caller's buffer is ever read.
+static __device__ __noinline__ uint32_t bitmap_load32_edge(const uint8_t* abase, int64_t w, int sh, int64_t lo, int64_t hi) {
+  uint32_t words[2] = {0u, 0u};
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int64_t b0 = (w + j) * 4;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int64_t b = b0 + k;
-      if (b >= lo && b < hi) v |= (uint32_t)abase[b] << (8 * k);
+      if (b >= lo && b < hi) words[j] |= (uint32_t)abase[b] << (8 * k);
     }
-    return v;
-  };
-  const uint32_t w0 = load_word(w);
-  if (sh == 0) return w0;
-  const uint32_t w1 = load_word(w + 1);
-  return __funnelshift_r(w0, w1, sh);
+  }
+  return sh ? __funnelshift_r(words[0], words[1], sh) : words[0];
+}
+
+__device__ __forceinline__ uint32_t bitmap_load32(const uint8_t* __restrict__ base, int64_t bit,
+                                                  int64_t lo_byte, int64_t hi_byte) {
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(base);
+  const int64_t mis = (int64_t)(addr & 3);       // base = abase + mis, abase 4-byte aligned
+  const uint8_t* abase = base - mis;
+  const int64_t abit = bit + mis * 8;            // bit position relative to abase (floor semantics for negatives)
+  const int64_t w = abit >> 5;
+  const int sh = (int)(abit & 31);
+  const int64_t lo = lo_byte + mis, hi = hi_byte + mis;  // valid byte range relative to abase
+  const int64_t b0 = w * 4;
+  if (b0 >= lo && b0 + 8 <= hi) {
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(abase + b0);
+    const uint32_t w0 = wp[0];
+    return sh ? __funnelshift_r(w0, wp[1], sh) : w0;
+  }
+  return bitmap_load32_edge(abase, w, sh, lo, hi);
 }
 
 // mask with bits [a, b) set, 0 <= a <= b <= 32
