@@ -72,3 +72,58 @@ def test_exact_type_dispatch():
     assert e.value.sentinel == "ErrNotImplemented"
     with pytest.raises(pc.ArrowError):
         pc.dispatch("no_such_function", [pc.INT32])
+
+
+def _model_spans(arg_lens, chunked, max_chunk):
+    """Plain-Python model of iterateExecSpans (executor.go:757-863) to fuzz the C++ restatement."""
+    totals = [sum(l) for l, c in zip(arg_lens, chunked) if l or c]
+    length = totals[0] if totals else 1
+    max_chunk = min(length, max_chunk)
+    idx = [0] * len(arg_lens)
+    posn = [0] * len(arg_lens)
+    out, pos = [], 0
+    while pos != length:
+        it = min(length - pos, max_chunk)
+        for i, (lens, c) in enumerate(zip(arg_lens, chunked)):
+            if not c:
+                continue
+            while posn[i] == lens[idx[i]]:
+                idx[i] += 1
+                posn[i] = 0
+            it = min(it, lens[idx[i]] - posn[i])
+        out.append((pos, it, list(idx)))
+        for i, (lens, c) in enumerate(zip(arg_lens, chunked)):
+            if lens or c:
+                posn[i] += it
+        pos += it
+    return out
+
+
+def test_iterate_exec_spans_fuzz():
+    import random
+    rng = random.Random(0x0FF1CE)
+    for _ in range(300):
+        total = rng.randint(1, 500)
+        nargs = rng.randint(1, 4)
+        arg_lens, chunked = [], []
+        for _a in range(nargs):
+            kind = rng.choice(["array", "chunked", "scalar"])
+            if kind == "scalar":
+                arg_lens.append([]); chunked.append(False)
+            elif kind == "array":
+                arg_lens.append([total]); chunked.append(False)
+            else:
+                cuts = sorted(rng.sample(range(0, total + 1), rng.randint(0, min(6, total))))
+                bounds = [0] + cuts + [total]
+                lens = [b - a for a, b in zip(bounds, bounds[1:])]  # may contain zero-length chunks
+                arg_lens.append(lens); chunked.append(True)
+        if all(not l and not c for l, c in zip(arg_lens, chunked)):
+            continue
+        mc = rng.choice([1 << 62, 7, 64, total])
+        got = pc.iterate_exec_spans(arg_lens, chunked, mc)
+        want = _model_spans(arg_lens, chunked, mc)
+        assert [(p, l) for p, l, _ in got] == [(p, l) for p, l, _ in want], (arg_lens, chunked, mc)
+        for (_, _, gi), (_, _, wi) in zip(got, want):
+            for a in range(nargs):
+                if chunked[a]:
+                    assert gi[a] == wi[a]
