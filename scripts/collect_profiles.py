@@ -15,8 +15,11 @@ os.makedirs(P, exist_ok=True)
 for src, dst in ((f"{tag}_bench.json", "bench_n1.json"), (f"{tag}_bench_ref.json", "bench_reference_arm_n1.json"), (f"{tag}_box.txt", "box.txt"),
                  (f"{tag}_kernels.txt", "kernel_timings_100m.txt"), (f"{tag}_pytest.log", "pytest_gpu.log")):
     shutil.copy(os.path.join(G, src), os.path.join(P, dst))
-subprocess.check_call([sys.executable, "scripts/ncu_summary.py", f"{G}/{tag}_prof_add.ncu-rep", f"{P}/ncu_full_binary_spans_kernel.csv"])
-subprocess.check_call([sys.executable, "scripts/ncu_summary.py", f"{G}/{tag}_prof_kernels.ncu-rep", f"{P}/ncu_full_other_kernels.csv"])
+for src, dst in ((f"{tag}_ncu_add", "ncu_full_binary_spans_kernel.csv"), (f"{tag}_ncu_kernels", "ncu_full_other_kernels.csv")):
+    if os.path.exists(os.path.join(G, src + ".csv")):
+        shutil.copy(os.path.join(G, src + ".csv"), os.path.join(P, dst))
+    else:  # older runs brought the raw report back
+        subprocess.check_call([sys.executable, "scripts/ncu_summary.py", f"{G}/{src.replace('_ncu_', '_prof_')}.ncu-rep", f"{P}/{dst}"])
 rows = list(csv.reader(open(f"{G}/{tag}_launches.csv", errors="replace")))
 hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
 hdr = rows[hi]
