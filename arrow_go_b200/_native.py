@@ -111,6 +111,11 @@ _SIGS = {
     "ag_arith_unary_checked": [_i, _i8, _p, _p, _i64, _pi64],
     "ag_arith_unary_checked_dev": [_i, _i8, _p, _p, _i64, _p, _p],
     "ag_error_word_reset_dev": [_p, _p],
+    # numeric casts
+    "ag_cast_numeric": [_i, _i, _p, _p, _i64],
+    "ag_cast_numeric_dev": [_i, _i, _p, _p, _i64, _p],
+    "ag_cast_numeric_checked": [_i, _i, _p, _p, _i64, _p, _i64, _i, _i, _pi64],
+    "ag_cast_numeric_checked_dev": [_i, _i, _p, _p, _i64, _p, _i64, _i, _i, _p, _p],
     # compare
     "ag_compare": [_i, _i, _i, _p, _p, _p, _i64, _i],
     "ag_compare_dev": [_i, _i, _i, _p, _p, _p, _i64, _i, _p],

@@ -75,6 +75,10 @@ def lib():
         h.agx_iterate_spans.argtypes = [C.POINTER(i64), C.POINTER(i), C.POINTER(i), i, i64, C.POINTER(i64), C.POINTER(i), i, C.POINTER(i)]
         h.agx_function_names.argtypes = [C.c_char_p, i64]
         h.agx_dispatch.argtypes = [C.c_char_p, C.POINTER(i), i]
+        h.agx_dispatch_best.argtypes = [C.c_char_p, C.POINTER(i), i]
+        h.agx_common_numeric.argtypes = [C.POINTER(i), i]
+        h.agx_cast.argtypes = [p, i, i, i, pp]
+        h.agx_scalar_value.argtypes = [p, C.POINTER(i), p]
         _lib = h
     return _lib
 
@@ -246,6 +250,24 @@ def Multiply(l, r, no_check_overflow=False):
     return _arith(2, l, r, no_check_overflow)
 
 
+def Cast(value, to_type, allow_int_overflow=False, allow_float_truncate=False):
+    """compute.CastDatum(ctx, value, &CastOptions{ToType, AllowIntOverflow, AllowFloatTruncate}); the
+    defaults are SafeCastOptions(to_type) — what implicit promotion uses."""
+    out = C.c_void_p()
+    _check(lib().agx_cast(value._h, to_type, int(allow_int_overflow), int(allow_float_truncate), C.byref(out)))
+    return Datum(out)
+
+
+def scalar_value(d):
+    """(python value or None) of a Scalar datum."""
+    valid = C.c_int()
+    raw = np.zeros(8, dtype=np.uint8)
+    _check(lib().agx_scalar_value(d._h, C.byref(valid), raw.ctypes.data))
+    if not valid.value:
+        return None
+    return raw.view(NP_OF[d.type])[0].item()
+
+
 def Filter(values, mask, null_selection=DROP_NULLS):
     return CallFunction("filter", [values, mask], ("filter", null_selection))
 
@@ -296,6 +318,20 @@ def function_names():
     buf = C.create_string_buffer(8192)
     _check(lib().agx_function_names(buf, 8192))
     return [x for x in buf.value.decode().split("\n") if x]
+
+
+def common_numeric(types):
+    """commonNumeric (utils.go:178-240): the promoted type id, or None."""
+    arr = (C.c_int * len(types))(*types)
+    r = lib().agx_common_numeric(arr, len(types))
+    return r or None
+
+
+def dispatch_best(name, types):
+    """The input signature `name` would run with after implicit promotion (DispatchBest)."""
+    arr = (C.c_int * len(types))(*types)
+    _check(lib().agx_dispatch_best(name.encode(), arr, len(types)))
+    return list(arr)
 
 
 def dispatch(name, types):

@@ -28,6 +28,8 @@ ag_status arith_checked_dev(int type, int8_t op, int shape, const void* l, const
                             const void* r, const uint8_t* rvalid, int64_t roff, void* out, int64_t n, int64_t* d_first_bad, cudaStream_t st);
 ag_status error_word_reset(int64_t* d_word, cudaStream_t st);
 ag_status arith_unary_checked_dev(int type, int8_t op, const void* in, void* out, int64_t n, int64_t* d_first_bad, cudaStream_t st);
+ag_status cast_numeric_dev(int itype, int otype, const void* in, const uint8_t* valid, int64_t voff, void* out, int64_t n,
+                           int allow_int_overflow, int allow_float_truncate, int64_t* first_bad, int64_t row_base, cudaStream_t st);
 ag_status compare_dev(int type, int cmp, int shape, const void* l, const void* r, uint8_t* out, int64_t n, int off, cudaStream_t st);
 ag_status bitmap_op_dev(int bitop, const uint8_t* l, int64_t loff, const uint8_t* r, int64_t roff, uint8_t* out, int64_t ooff, int64_t n, cudaStream_t st);
 ag_status bitmap_copy_dev(const uint8_t* src, int64_t soff, int64_t n, uint8_t* dst, int64_t doff, bool invert, cudaStream_t st);
@@ -298,6 +300,57 @@ ag_status ag_arith_unary_checked(int type, int8_t op, const void* in, void* out,
   AG_TRY(sync(cs));
   if (first_bad) *first_bad = bad;
   if (bad != AG_NO_ERROR_POS) AG_FAIL(AG_ERR_INVALID, "overflow");
+  return AG_OK;
+}
+
+// ---- numeric casts -----------------------------------------------------------------
+ag_status ag_cast_numeric(int itype, int otype, const void* in, void* out, int64_t n) {
+  const int wi = type_width(itype), wo = type_width(otype);
+  if (wi == 0 || wo == 0) AG_FAIL(AG_ERR_TYPE, "cast: unsupported type id");
+  if (n < 0) AG_FAIL(AG_ERR_INVALID, "cast: negative length");
+  if (n > 0 && (!in || !out)) AG_FAIL(AG_ERR_INVALID, "cast: NULL operand");
+  const void* ins[1] = {in};
+  const int widths[1] = {wi};
+  return pipelined_rows(n, 1, ins, widths, out, wo, [&](void* const* d_in, void* d_out, int64_t len, cudaStream_t st) {
+    return cast_numeric_dev(itype, otype, d_in[0], nullptr, 0, d_out, len, 1, 1, nullptr, 0, st);
+  });
+}
+
+ag_status ag_cast_numeric_checked(int itype, int otype, const void* in, const uint8_t* valid, int64_t valid_offset,
+                                  void* out, int64_t n, int allow_int_overflow, int allow_float_truncate, int64_t* first_bad) {
+  AG_TRY(ensure_init());
+  if (first_bad) *first_bad = AG_NO_ERROR_POS;
+  const int wi = type_width(itype), wo = type_width(otype);
+  if (wi == 0 || wo == 0) AG_FAIL(AG_ERR_TYPE, "cast: unsupported type id");
+  if (n < 0 || valid_offset < 0) AG_FAIL(AG_ERR_INVALID, "cast: negative length or offset");
+  if (n == 0) return AG_OK;
+  if (!in || !out) AG_FAIL(AG_ERR_INVALID, "cast: NULL operand");
+  CallStream cs; AG_TRY(cs.acquire());
+  Temps t(cs);
+  void *din, *dout; int64_t* d_bad; uint8_t* dvalid = nullptr;
+  AG_TRY(t.alloc(&din, (size_t)n * wi)); AG_TRY(t.alloc(&dout, (size_t)n * wo)); AG_TRY(t.alloc_t(&d_bad, sizeof(int64_t)));
+  AG_TRY(h2d(din, in, (size_t)n * wi, cs));
+  const int64_t vbyte0 = valid_offset >> 3;
+  if (valid) {
+    const size_t vbytes = (size_t)(bytes_for_bits(valid_offset + n) - vbyte0);
+    AG_TRY(t.alloc_t(&dvalid, vbytes));
+    AG_TRY(h2d(dvalid, valid + vbyte0, vbytes, cs));
+  }
+  AG_TRY(error_word_reset(d_bad, cs));
+  AG_TRY(cast_numeric_dev(itype, otype, din, dvalid, valid_offset & 7, dout, n, allow_int_overflow, allow_float_truncate, d_bad, 0, cs));
+  int64_t bad = AG_NO_ERROR_POS;
+  AG_TRY(d2h(&bad, d_bad, sizeof(bad), cs));
+  AG_TRY(d2h(out, dout, (size_t)n * wo, cs));
+  AG_TRY(sync(cs));
+  if (first_bad) *first_bad = bad;
+  if (bad != AG_NO_ERROR_POS) {
+    // numeric_cast.go:614-617 / helpers.go:591-594 wording; the offending element is in the caller's buffer
+    if (type_is_float(itype)) {
+      const double v = itype == AG_TYPE_FLOAT32 ? (double)((const float*)in)[bad] : ((const double*)in)[bad];
+      AG_FAIL(AG_ERR_INVALID, "float value %f was truncated converting to type id %d", v, otype);
+    }
+    AG_FAIL(AG_ERR_INVALID, "integer value not in range (row %lld)", (long long)bad);
+  }
   return AG_OK;
 }
 

@@ -217,6 +217,15 @@ struct TakeOptions : FunctionOptions {  // expression.go:494: default BoundsChec
   const char* TypeName() const override { return "TakeOptions"; }
 };
 
+struct CastOptions : FunctionOptions {  // kernels/cast.go:27-35 (the numeric knobs)
+  Type ToType = Type::NA;
+  bool AllowIntOverflow = false;
+  bool AllowFloatTruncate = false;
+  const char* TypeName() const override { return "CastOptions"; }
+};
+inline CastOptions SafeCastOptions(Type to) { CastOptions o; o.ToType = to; return o; }  // cast.go: SafeCastOptions
+inline CastOptions UnsafeCastOptions(Type to) { CastOptions o; o.ToType = to; o.AllowIntOverflow = o.AllowFloatTruncate = true; return o; }
+
 enum class FuncKind { SCALAR, VECTOR, META };  // functions.go FuncScalar / FuncVector / FuncMeta
 
 class FunctionRegistry;
@@ -245,6 +254,11 @@ class ScalarFunction : public Function {  // functions.go:233-310
   ScalarFunction(std::string name, int arity) : Function(std::move(name), FuncKind::SCALAR, arity) {}
   Status AddKernel(exec::ScalarKernel k);                                        // functions.go:290
   Status DispatchExact(const std::vector<Type>& types, const exec::ScalarKernel** out) const;  // functions.go:204-217 (first match)
+  // arithmeticFunction.DispatchBest (arithmetic.go:112-140) / compareFunction.DispatchBest (scalar_compare.go:37-65):
+  // exact match first; binary functions flagged `promote_numeric` then replace both types by
+  // commonNumeric (utils.go:178-240).  `types` is rewritten to the dispatched signature.
+  Status DispatchBest(std::vector<Type>* types, const exec::ScalarKernel** out) const;
+  bool promote_numeric = false;
   Status Execute(const ExecCtx& ctx, const FunctionOptions* opts, const std::vector<Datum>& args, Datum* out) const override;
  private:
   std::vector<exec::ScalarKernel> kernels_;
@@ -284,6 +298,11 @@ class FunctionRegistry {  // registry.go:30-133
 };
 FunctionRegistry* GetFunctionRegistry();                                       // registry.go:47-62
 std::unique_ptr<FunctionRegistry> NewChildRegistry(FunctionRegistry* parent);  // registry.go:69
+
+// utils.go:178-240; Type::NA when there is no common numeric type
+Type CommonNumeric(const std::vector<Type>& types);
+// cast.go:919-921: CallFunction("cast") — arrays, chunked arrays and scalars between the 10 numeric types
+Status CastDatum(const ExecCtx& ctx, const Datum& val, const CastOptions& opts, Datum* out);
 
 // exec.go:191
 Status CallFunction(const ExecCtx& ctx, const std::string& name, const FunctionOptions* opts, const std::vector<Datum>& args, Datum* out);

@@ -95,6 +95,20 @@ int agx_arith(int which, int no_check_overflow, agx_datum* l, agx_datum* r, agx_
   *out = new agx_datum{res};
   return AG_OK;
 }
+// compute.CastDatum with CastOptions{ToType, AllowIntOverflow, AllowFloatTruncate} (cast.go:919-921)
+int agx_cast(agx_datum* d, int to_type, int allow_int_overflow, int allow_float_truncate, agx_datum** out) {
+  CastOptions o; o.ToType = (Type)to_type; o.AllowIntOverflow = allow_int_overflow != 0; o.AllowFloatTruncate = allow_float_truncate != 0;
+  ExecCtx ctx; Datum res;
+  AGX_TRY(CastDatum(ctx, d->d, o, &res));
+  *out = new agx_datum{res};
+  return AG_OK;
+}
+int agx_scalar_value(agx_datum* d, int* valid, void* value8) {
+  if (d->d.kind != DatumKind::SCALAR) return fail(Status::Invalid("scalar_value: not a scalar"));
+  *valid = d->d.scalar->valid ? 1 : 0;
+  memcpy(value8, d->d.scalar->value, 8);
+  return AG_OK;
+}
 int agx_sum_f64(agx_datum* d, int reference_order, double* out) {
   if (d->d.kind != DatumKind::ARRAY) return fail(Status::Invalid("sum: not an array"));
   AGX_TRY(reference_order ? math::SumFloat64ReferenceOrder(*d->d.array, out) : math::SumFloat64(*d->d.array, out));
@@ -136,6 +150,23 @@ int agx_function_names(char* buf, int64_t buflen) {
   for (auto& n : GetFunctionRegistry()->GetFunctionNames()) all += n + "\n";
   if ((int64_t)all.size() + 1 > buflen) return fail(Status::Invalid("buffer too small"));
   memcpy(buf, all.c_str(), all.size() + 1);
+  return AG_OK;
+}
+int agx_common_numeric(const int* types, int n) {  // commonNumeric, utils.go:178-240 (0 = none)
+  std::vector<Type> t;
+  for (int i = 0; i < n; ++i) t.push_back((Type)types[i]);
+  return (int)CommonNumeric(t);
+}
+// DispatchBest: rewrites `types` to the signature the call would run with (after implicit promotion)
+int agx_dispatch_best(const char* name, int* types, int n) {
+  const Function* f = GetFunctionRegistry()->GetFunction(name);
+  if (!f) return fail(Status::Make(AG_ERR_INVALID, std::string("no function registered with name: ") + name));
+  if (f->Kind() != FuncKind::SCALAR) return fail(Status::Invalid("dispatch_best: scalar functions only"));
+  std::vector<Type> t;
+  for (int i = 0; i < n; ++i) t.push_back((Type)types[i]);
+  const exec::ScalarKernel* k;
+  AGX_TRY(static_cast<const ScalarFunction*>(f)->DispatchBest(&t, &k));
+  for (int i = 0; i < n; ++i) types[i] = (int)t[i];
   return AG_OK;
 }
 // dispatch-only check: does `name` have a kernel for these input types?  (no device work)

@@ -387,6 +387,42 @@ Status ScalarFunction::AddKernel(exec::ScalarKernel k) {
 Status ScalarFunction::DispatchExact(const std::vector<Type>& types, const exec::ScalarKernel** out) const {
   return DispatchFirstMatch(Name(), kernels_, types, out);
 }
+// commonNumeric, utils.go:178-240
+Type CommonNumeric(const std::vector<Type>& types) {
+  for (Type t : types) if (!IsInteger(t) && !IsFloating(t)) return Type::NA;
+  for (Type t : types) if (t == Type::FLOAT64) return Type::FLOAT64;
+  for (Type t : types) if (t == Type::FLOAT32) return Type::FLOAT32;
+  int max_signed = 0, max_unsigned = 0;
+  for (Type t : types) {
+    if (IsSignedInteger(t)) max_signed = std::max(max_signed, BitWidth(t));
+    else max_unsigned = std::max(max_unsigned, BitWidth(t));
+  }
+  if (max_signed == 0) {
+    if (max_unsigned >= 64) return Type::UINT64;
+    if (max_unsigned == 32) return Type::UINT32;
+    if (max_unsigned == 16) return Type::UINT16;
+    return Type::UINT8;
+  }
+  if (max_signed <= max_unsigned) {  // bitutil.NextPowerOf2(maxWidthUnsigned + 1)
+    int w = 1;
+    while (w < max_unsigned + 1) w <<= 1;
+    max_signed = w;
+  }
+  if (max_signed >= 64) return Type::INT64;
+  if (max_signed == 32) return Type::INT32;
+  if (max_signed == 16) return Type::INT16;
+  return Type::INT8;
+}
+
+Status ScalarFunction::DispatchBest(std::vector<Type>* types, const exec::ScalarKernel** out) const {
+  if (DispatchExact(*types, out).ok()) return Status::OK();
+  if (promote_numeric && types->size() == 2) {  // "only promote types for binary funcs", arithmetic.go:127-137
+    const Type common = CommonNumeric(*types);
+    if (common != Type::NA) { (*types)[0] = common; (*types)[1] = common; }
+  }
+  return DispatchExact(*types, out);
+}
+
 Status VectorFunction::AddKernel(exec::VectorKernel k) { kernels_.push_back(std::move(k)); return Status::OK(); }
 Status VectorFunction::DispatchExact(const std::vector<Type>& types, const exec::VectorKernel** out) const {
   return DispatchFirstMatch(Name(), kernels_, types, out);
@@ -410,12 +446,20 @@ struct ErrorWord {  // device int64 "first failing row", reset per call
 
 // scalarExecutor: executor.go:487-728 (Init :435-440, setupPrealloc :658-702, executeSpans :598-623,
 // executeSingleSpan :644-656, emitResult :704-728) + WrapResults :521-580.
-Status ScalarFunction::Execute(const ExecCtx& ectx, const FunctionOptions* opts, const std::vector<Datum>& args, Datum* out) const {
-  RETURN_NOT_OK(CheckArgs(*this, args));
+Status ScalarFunction::Execute(const ExecCtx& ectx, const FunctionOptions* opts, const std::vector<Datum>& args_in, Datum* out) const {
+  RETURN_NOT_OK(CheckArgs(*this, args_in));
   std::vector<Type> in_types;
-  for (auto& a : args) in_types.push_back(a.type());
+  for (auto& a : args_in) in_types.push_back(a.type());
   const exec::ScalarKernel* kernel = nullptr;
-  RETURN_NOT_OK(DispatchExact(in_types, &kernel));  // NB: implicit casts (DispatchBest + CastDatum, exec.go:101-121) are out of scope
+  RETURN_NOT_OK(DispatchBest(&in_types, &kernel));
+  // "cast arguments if necessary" (exec.go:101-121): implicit promotion runs the safe cast
+  std::vector<Datum> cast_args;
+  for (size_t i = 0; i < args_in.size(); ++i) {
+    if (args_in[i].type() == in_types[i]) continue;
+    if (cast_args.empty()) cast_args = args_in;
+    RETURN_NOT_OK(CastDatum(ectx, args_in[i], SafeCastOptions(in_types[i]), &cast_args[i]));
+  }
+  const std::vector<Datum>& args = cast_args.empty() ? args_in : cast_args;
   const Type out_type = kernel->out_type(in_types);
 
   // span iteration metadata
@@ -638,6 +682,12 @@ inline const uint8_t* ValuesPtr(const ArraySpan& a) {  // exec.GetSpanValues: Bu
   return a.buffers[1].buf + a.offset * (BitWidth(a.type) / 8);
 }
 inline uint8_t* ValuesPtr(ExecResult* a) { return a->buffers[1].buf + a->offset * (BitWidth(a->type) / 8); }
+
+const std::vector<Type>& kNumericTypesForCast() {
+  static const std::vector<Type> v = {Type::UINT8, Type::INT8, Type::UINT16, Type::INT16, Type::UINT32, Type::INT32,
+                                      Type::UINT64, Type::INT64, Type::FLOAT32, Type::FLOAT64};
+  return v;
+}
 
 int ShapeOf(const ExecSpan& b) { return b.values[0].IsArray() ? (b.values[1].IsArray() ? AG_SHAPE_AA : AG_SHAPE_AS) : AG_SHAPE_SA; }
 
@@ -862,6 +912,90 @@ Status IsNanExec(KernelCtx*, const ExecSpan& batch, ExecResult* out) {
 }
 
 // NotExecKernel (scalar_boolean.go:336-347): invert data, share the validity buffer
+// ---- numeric casts (kernels/numeric_cast.go:37-71 over cast_numeric.go:101-131) ----------
+// Integer bounds of intsCanFit / checkIntToFloatTrunc, only needed to word the error like the
+// reference ("integer value %d not in range: %d to %d", helpers.go:591-594).
+void SafeIntBounds(Type in, Type out, __int128* lo, __int128* hi) {
+  auto tmin = [](Type t) -> __int128 { return IsSignedInteger(t) ? -((__int128)1 << (BitWidth(t) - 1)) : 0; };
+  auto tmax = [](Type t) -> __int128 { return IsSignedInteger(t) ? ((__int128)1 << (BitWidth(t) - 1)) - 1 : ((__int128)1 << BitWidth(t)) - 1; };
+  if (IsFloating(out)) {
+    const int mant = out == Type::FLOAT32 ? 24 : 53;
+    *hi = (__int128)1 << mant;
+    *lo = IsSignedInteger(in) ? -*hi : 0;
+    return;
+  }
+  *lo = std::max(tmin(in), tmin(out));
+  *hi = std::min(tmax(in), tmax(out));
+}
+std::string Int128ToString(__int128 v) {
+  if (v == 0) return "0";
+  const bool neg = v < 0;
+  unsigned __int128 u = neg ? (unsigned __int128)(-(v + 1)) + 1 : (unsigned __int128)v;
+  std::string r;
+  while (u) { r.insert(r.begin(), (char)('0' + (int)(u % 10))); u /= 10; }
+  return neg ? "-" + r : r;
+}
+
+Status CastNumericExec(KernelCtx* ctx, const ExecSpan& batch, ExecResult* out) {
+  const auto* opts = static_cast<const CastOptions*>(ctx->state);
+  const ArraySpan& in = batch.values[0].array;
+  if (batch.len == 0) return Status::OK();
+  NATIVE(ag_cast_numeric_checked_dev((int)in.type, (int)out->type, ValuesPtr(in), in.buffers[0].buf, in.offset, ValuesPtr(out), batch.len,
+                                     opts->AllowIntOverflow ? 1 : 0, opts->AllowFloatTruncate ? 1 : 0, ctx->error_word, nullptr));
+  // one 8-byte read per span: the error names the offending VALUE, like the reference's does
+  int64_t bad = AG_NO_ERROR_POS;
+  NATIVE(ag_download(&bad, ctx->error_word, sizeof(bad), nullptr));
+  NATIVE(ag_stream_sync(nullptr));
+  if (bad == AG_NO_ERROR_POS) return Status::OK();
+  const int w = BitWidth(in.type) / 8;
+  uint8_t raw[8] = {0};
+  NATIVE(ag_download(raw, ValuesPtr(in) + bad * w, (size_t)w, nullptr));
+  NATIVE(ag_stream_sync(nullptr));
+  if (IsFloating(in.type)) {  // numeric_cast.go:614-617
+    double v;
+    if (in.type == Type::FLOAT32) { float f; memcpy(&f, raw, 4); v = f; } else memcpy(&v, raw, 8);
+    char buf[128];
+    snprintf(buf, sizeof(buf), "float value %f was truncated converting to %s", v, TypeName(out->type));
+    return Status::Invalid(buf);
+  }
+  __int128 v = 0, lo, hi;
+  switch (in.type) {
+    case Type::INT8: v = (int8_t)raw[0]; break;
+    case Type::UINT8: v = raw[0]; break;
+    case Type::INT16: { int16_t t; memcpy(&t, raw, 2); v = t; break; }
+    case Type::UINT16: { uint16_t t; memcpy(&t, raw, 2); v = t; break; }
+    case Type::INT32: { int32_t t; memcpy(&t, raw, 4); v = t; break; }
+    case Type::UINT32: { uint32_t t; memcpy(&t, raw, 4); v = t; break; }
+    case Type::INT64: { int64_t t; memcpy(&t, raw, 8); v = t; break; }
+    default: { uint64_t t; memcpy(&t, raw, 8); v = t; break; }
+  }
+  SafeIntBounds(in.type, out->type, &lo, &hi);
+  return Status::Invalid("integer value " + Int128ToString(v) + " not in range: " + Int128ToString(lo) + " to " + Int128ToString(hi));
+}
+
+const char* CastFunctionName(Type t) {  // cast.go:841-880
+  switch (t) {
+    case Type::INT8: return "cast_int8"; case Type::INT16: return "cast_int16"; case Type::INT32: return "cast_int32";
+    case Type::INT64: return "cast_int64"; case Type::UINT8: return "cast_uint8"; case Type::UINT16: return "cast_uint16";
+    case Type::UINT32: return "cast_uint32"; case Type::UINT64: return "cast_uint64"; case Type::FLOAT32: return "cast_float";
+    case Type::FLOAT64: return "cast_double"; default: return nullptr;
+  }
+}
+
+std::shared_ptr<ScalarFunction> MakeCastTo(Type to) {  // GetCastToInteger / GetCastToFloating, numeric_cast.go:835-906
+  auto fn = std::make_shared<ScalarFunction>(CastFunctionName(to), 1);
+  for (Type t : kNumericTypesForCast()) {
+    exec::ScalarKernel k;
+    k.in_types = {t};
+    k.out_type = [to](const std::vector<Type>&) { return to; };
+    k.exec = CastNumericExec;
+    k.can_fail = true;  // the executor supplies the error word; CastNumericExec words the error itself
+    k.fail_message = "cast failed";
+    fn->AddKernel(std::move(k));
+  }
+  return fn;
+}
+
 Status NotExec(KernelCtx*, const ExecSpan& batch, ExecResult* out) {
   const ArraySpan& in = batch.values[0].array;
   NATIVE(ag_bitmap_invert_dev(in.buffers[1].buf, in.offset, in.len, out->buffers[1].buf, out->offset, nullptr));
@@ -967,6 +1101,7 @@ const Type kNumericTypes[] = {Type::UINT8, Type::INT8, Type::UINT16, Type::INT16
 std::shared_ptr<ScalarFunction> MakeArithBinary(const std::string& name, int8_t unchecked_op, int8_t checked_op, bool checked, const char* fail_msg) {
   // GetArithmeticBinaryKernels (scalar_arithmetic.go:86-95): one [ty,ty]->ty kernel per numeric type
   auto fn = std::make_shared<ScalarFunction>(name, 2);
+  fn->promote_numeric = true;  // arithmeticFunction.DispatchBest, arithmetic.go:112-140
   for (Type t : kNumericTypes) {
     exec::ScalarKernel k;
     k.in_types = {t, t};
@@ -1012,6 +1147,7 @@ std::shared_ptr<ScalarFunction> MakeArithUnaryChecked(const std::string& name, i
 
 std::shared_ptr<ScalarFunction> MakeCompare(const std::string& name, int cmp) {  // CompareKernels, scalar_comparisons.go:654-716
   auto fn = std::make_shared<ScalarFunction>(name, 2);
+  fn->promote_numeric = true;  // compareFunction.DispatchBest, scalar_compare.go:37-65
   for (Type t : kNumericTypes) {
     exec::ScalarKernel k;
     k.in_types = {t, t};
@@ -1108,6 +1244,33 @@ FunctionRegistry* GetFunctionRegistry() {
       }
       reg->AddFunction(fn, false);
     }
+    // cast.go:45-81,841-880: cast_<type> scalar functions for the numeric types + the "cast" meta function
+    for (Type t : kNumericTypes) reg->AddFunction(MakeCastTo(t), false);
+    reg->AddFunction(std::make_shared<MetaFunction>("cast", 1, [](const ExecCtx& ctx, const FunctionOptions* fo, const std::vector<Datum>& args, Datum* out) -> Status {
+      const auto* co = dynamic_cast<const CastOptions*>(fo);
+      if (!co || co->ToType == Type::NA) return Status::Invalid("cast requires that options be passed with a ToType");
+      if (args.size() != 1 || args[0].kind == DatumKind::NONE) return Status::Invalid("cast takes one value argument");
+      if (args[0].type() == co->ToType) { *out = args[0]; return Status::OK(); }
+      const char* fname = CastFunctionName(co->ToType);
+      FunctionRegistry* r = ctx.Registry ? ctx.Registry : GetFunctionRegistry();
+      const Function* fn = fname ? r->GetFunction(fname) : nullptr;
+      if (!fn) return Status::NotImplemented(std::string("unsupported cast to ") + TypeName(co->ToType) + " from " + TypeName(args[0].type()));
+      if (args[0].kind != DatumKind::SCALAR) return fn->Execute(ctx, fo, args, out);
+      // scalar input: a one-element array through the same kernel (the reference promotes scalars to
+      // length-1 arrays for scalar-only execution too, executor.go PromoteExecSpanScalars)
+      const Scalar& sc = *args[0].scalar;
+      auto res = std::make_shared<Scalar>();
+      res->type = co->ToType;
+      if (!sc.valid) { *out = Datum(res); return Status::OK(); }
+      std::shared_ptr<ArrayData> one;
+      RETURN_NOT_OK(ArrayData::FromHost(sc.type, 1, 0, nullptr, sc.value, 0, &one));
+      Datum casted;
+      RETURN_NOT_OK(fn->Execute(ctx, fo, {Datum(one)}, &casted));
+      RETURN_NOT_OK(casted.array->ToHost(res->value, nullptr, nullptr));
+      res->valid = true;
+      *out = Datum(res);
+      return Status::OK();
+    }), false);
     // selection.go:593-650: array_filter / array_take vector functions + filter / take meta functions
     {
       auto fn = std::make_shared<VectorFunction>("array_filter", 2);
@@ -1203,6 +1366,10 @@ Status ConcatenateChunks(const ChunkedArray& c, std::shared_ptr<ArrayData>* out)
 }  // namespace
 
 // arithmetic.go:1090-1142
+Status CastDatum(const ExecCtx& ctx, const Datum& val, const CastOptions& opts, Datum* out) {  // cast.go:919-921
+  return CallFunction(ctx, "cast", &opts, {val}, out);
+}
+
 static Status ArithImpl(const ExecCtx& ctx, const ArithmeticOptions& opts, const char* fn, const Datum& l, const Datum& r, Datum* out) {
   std::string name = fn;
   if (opts.NoCheckOverflow) name += "_unchecked";

@@ -243,6 +243,31 @@ ag_status ag_arith_checked_dev(int type, int8_t op, int shape,
 ag_status ag_error_word_reset_dev(int64_t* d_word, ag_stream_t s);
 
 /* ================================================================================= *
+ * Numeric casts — replaces cast_type_numeric_{avx2,sse4} (_lib/cast_numeric.cc:22-101, Go
+ *   dispatch cast_numeric.go:101-131) for the 10 numeric types, and the checks of
+ *   numeric_cast.go that frame it under safe CastOptions (what implicit promotion uses:
+ *   compute/exec.go:101-121 -> CastDatum(SafeCastOptions)):
+ *     int -> int    intsCanFit/intsInRange (helpers.go:545-653), skipped when AllowIntOverflow
+ *     int -> float  checkIntToFloatTrunc   (numeric_cast.go:698-729): |v| <= 2^24 / 2^53
+ *     float -> int  checkFloatTrunc        (numeric_cast.go:613-660): OutT(v) converted back != v
+ *   the last two skipped when AllowFloatTruncate.  Every slot is converted (nulls too, like
+ *   castNumberToNumberUnsafe, helpers.go:690-703); the checks look only at valid slots.
+ *   Bit-exact with the reference loops for every input whose converted value is representable
+ *   in the output type; out-of-range float -> int is not defined by the reference (its AVX2 body,
+ *   SSE4 body and scalar tail disagree) — here: 64-bit truncation (NaN/overflow -> INT64_MIN)
+ *   then wrap to the output width, the pure-Go amd64 behaviour.
+ *   Checked flavour: AG_ERR_INVALID + lowest failing row in *first_bad (else AG_NO_ERROR_POS).
+ * ================================================================================= */
+ag_status ag_cast_numeric(int itype, int otype, const void* in, void* out, int64_t n);
+ag_status ag_cast_numeric_dev(int itype, int otype, const void* d_in, void* d_out, int64_t n, ag_stream_t s);
+ag_status ag_cast_numeric_checked(int itype, int otype, const void* in, const uint8_t* valid, int64_t valid_offset,
+                                  void* out, int64_t n, int allow_int_overflow, int allow_float_truncate, int64_t* first_bad);
+/* *d_first_bad must hold AG_NO_ERROR_POS (ag_error_word_reset_dev); it is only lowered. */
+ag_status ag_cast_numeric_checked_dev(int itype, int otype, const void* d_in, const uint8_t* d_valid, int64_t valid_offset,
+                                      void* d_out, int64_t n, int allow_int_overflow, int allow_float_truncate,
+                                      int64_t* d_first_bad, ag_stream_t s);
+
+/* ================================================================================= *
  * Comparisons -> bitmap — replaces comparison_{equal,not_equal,greater,greater_equal}
  *   _{arr_arr,arr_scalar,scalar_arr}_{avx2,sse4} (_lib/scalar_comparison.cc:210-256)
  *   and compareKernel (scalar_comparisons.go:199-218).  `out_bits` points at the byte

@@ -344,6 +344,117 @@ int ref_arith_unary_checked(int type, int op, const void* in, void* out, int64_t
 }
 
 /* ====================================================================================== *
+ * Numeric casts: the loop K/cast_numeric.go:101-131 (= K/_lib/cast_numeric.cc:22-101) framed by
+ * the safe-cast checks of K/numeric_cast.go:37-71 —
+ *   int -> int    intsCanFit (K/helpers.go:545-578) bounds from getSafeMinMax* (:496-543),
+ *                 intsInRange (:580-653) incl. its "whole input range fits" early return;
+ *   int -> float  checkIntToFloatTrunc (K/numeric_cast.go:698-729);
+ *   float -> int  checkFloatTrunc / wasTrunc (K/numeric_cast.go:587-660), evaluated AFTER the loop.
+ * Every slot is converted; only valid slots are checked; *first_bad = lowest failing row.
+ * float -> int of an unrepresentable value is undefined in C and varies between the reference's
+ * own AVX2 / SSE4 / scalar-tail code; this restates what Go's conversion does on amd64
+ * (CVTTSD2SQ "integer indefinite" + wrap), which is also what the CUDA path documents.
+ * ====================================================================================== */
+static int64_t cvtt64(double v) {
+  if (!(v >= -9223372036854775808.0 && v < 9223372036854775808.0)) return INT64_MIN;
+  return (int64_t)v;
+}
+static uint64_t f2u64(double v) {
+  if (v >= 9223372036854775808.0) return (uint64_t)cvtt64(v - 9223372036854775808.0) ^ 0x8000000000000000ull;
+  return (uint64_t)cvtt64(v);
+}
+static int cast_is_int(int t) { return t >= T_U8 && t <= T_I64; }
+static int cast_is_signed(int t) { return t == T_I8 || t == T_I16 || t == T_I32 || t == T_I64; }
+static int cast_width(int t) {
+  switch (t) { case T_U8: case T_I8: return 1; case T_U16: case T_I16: return 2;
+               case T_U32: case T_I32: case T_F32: return 4; case T_U64: case T_I64: case T_F64: return 8; default: return 0; }
+}
+typedef __int128 i128;
+static i128 int_min_of(int t) { return cast_is_signed(t) ? -((i128)1 << (8 * cast_width(t) - 1)) : 0; }
+static i128 int_max_of(int t) { return cast_is_signed(t) ? ((i128)1 << (8 * cast_width(t) - 1)) - 1 : ((i128)1 << (8 * cast_width(t))) - 1; }
+
+/* carriers: ints as i128 (exact), floats as double (float32 -> double is exact) */
+static i128 load_int(int t, const void* p, int64_t i) {
+  switch (t) {
+    case T_U8: return ((const uint8_t*)p)[i];   case T_I8: return ((const int8_t*)p)[i];
+    case T_U16: return ((const uint16_t*)p)[i]; case T_I16: return ((const int16_t*)p)[i];
+    case T_U32: return ((const uint32_t*)p)[i]; case T_I32: return ((const int32_t*)p)[i];
+    case T_U64: return ((const uint64_t*)p)[i]; default: return ((const int64_t*)p)[i];
+  }
+}
+static void store_int_bits(int t, void* p, int64_t i, uint64_t bits) {
+  switch (cast_width(t)) {
+    case 1: ((uint8_t*)p)[i] = (uint8_t)bits; break;
+    case 2: ((uint16_t*)p)[i] = (uint16_t)bits; break;
+    case 4: ((uint32_t*)p)[i] = (uint32_t)bits; break;
+    default: ((uint64_t*)p)[i] = bits; break;
+  }
+}
+
+int ref_cast_numeric(int itype, int otype, const void* in, const uint8_t* valid, int64_t voff, void* out, int64_t n,
+                     int allow_int_overflow, int allow_float_truncate, int64_t* first_bad) {
+  int64_t bad = REF_NO_ERROR_POS;
+  if (first_bad) *first_bad = bad;
+  const int wi = cast_width(itype), wo = cast_width(otype);
+  if (wi == 0 || wo == 0) return REF_ERR_TYPE;
+  if (n < 0) return REF_ERR_INVALID;
+  if (itype == otype) { memcpy(out, in, (size_t)n * wi); return REF_OK; }
+  const int iint = cast_is_int(itype), oint = cast_is_int(otype);
+  /* bounds for the integer-input checks */
+  int check_range = 0;
+  i128 lo = 0, hi = 0;
+  if (iint && oint && !allow_int_overflow) {
+    lo = int_min_of(itype); hi = int_max_of(itype);
+    if (cast_is_signed(itype)) {
+      if (cast_is_signed(otype)) { if (wi > wo) { lo = int_min_of(otype); hi = int_max_of(otype); } }
+      else { lo = 0; if (wi > wo) hi = int_max_of(otype); }
+    } else {
+      if (cast_is_signed(otype)) { if (wi >= wo) hi = int_max_of(otype); }
+      else { if (wi > wo) hi = int_max_of(otype); }
+    }
+    check_range = !(lo <= int_min_of(itype) && hi >= int_max_of(itype));
+  } else if (iint && !oint && !allow_float_truncate) {
+    const int mant = (otype == T_F32) ? 24 : 53;
+    if (8 * wi > mant && !(wi == 4 && otype == T_F64)) {  /* int8/16 never; int32/uint32 only -> float32 */
+      hi = (i128)1 << mant; lo = cast_is_signed(itype) ? -hi : 0; check_range = 1;
+    }
+  }
+  const int check_trunc = !iint && oint && !allow_float_truncate;
+  for (int64_t i = 0; i < n; ++i) {
+    const int is_valid = !valid || ((valid[(voff + i) >> 3] >> ((voff + i) & 7)) & 1);
+    if (iint) {
+      const i128 v = load_int(itype, in, i);
+      if (check_range && is_valid && (v < lo || v > hi) && i < bad) bad = i;
+      if (oint) store_int_bits(otype, out, i, (uint64_t)v);
+      else if (otype == T_F32) ((float*)out)[i] = cast_is_signed(itype) ? (float)(int64_t)v : (float)(uint64_t)v;
+      else ((double*)out)[i] = cast_is_signed(itype) ? (double)(int64_t)v : (double)(uint64_t)v;
+    } else {
+      const double d = (itype == T_F32) ? (double)((const float*)in)[i] : ((const double*)in)[i];
+      if (!oint) {
+        if (otype == T_F32) ((float*)out)[i] = (float)d; else ((double*)out)[i] = d;
+      } else {
+        const uint64_t bits = (otype == T_U64) ? f2u64(d) : (uint64_t)cvtt64(d);
+        store_int_bits(otype, out, i, bits);
+        if (check_trunc && is_valid) {
+          const i128 o = load_int(otype, out, i);   /* the stored (wrapped) OutT value */
+          int trunc;
+          if (itype == T_F32) {
+            const float back = cast_is_signed(otype) ? (float)(int64_t)o : (float)(uint64_t)o;
+            trunc = !(back == ((const float*)in)[i]);
+          } else {
+            const double back = cast_is_signed(otype) ? (double)(int64_t)o : (double)(uint64_t)o;
+            trunc = !(back == d);
+          }
+          if (trunc && i < bad) bad = i;
+        }
+      }
+    }
+  }
+  if (first_bad) *first_bad = bad;
+  return bad == REF_NO_ERROR_POS ? REF_OK : REF_ERR_INVALID;
+}
+
+/* ====================================================================================== *
  * Comparisons: K/_lib/scalar_comparison.cc:63-206 (prefix bits up to the next byte boundary,
  * 32-wide batches packed LSB-first, tail bits), driver K/scalar_comparisons.go:199-218,
  * LT/LE by flipping K/../scalar_compare.go:73-99.  Bits outside [offset, offset+n) keep

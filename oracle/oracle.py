@@ -50,6 +50,7 @@ def cpu():
         lib.ref_arith_unary_diff.argtypes = [C.c_int, C.c_int, C.c_int, c_p, c_p, i64]
         lib.ref_arith_checked.argtypes = [C.c_int, C.c_int, C.c_int, c_p, c_p, i64, c_p, c_p, i64, c_p, i64, C.POINTER(i64)]
         lib.ref_arith_unary_checked.argtypes = [C.c_int, C.c_int, c_p, c_p, i64, C.POINTER(i64)]
+        lib.ref_cast_numeric.argtypes = [C.c_int, C.c_int, c_p, c_p, i64, c_p, i64, C.c_int, C.c_int, C.POINTER(i64)]
         lib.ref_compare.argtypes = [C.c_int, C.c_int, C.c_int, c_p, c_p, c_p, i64, C.c_int]
         lib.ref_bitmap_op.argtypes = [C.c_int, c_p, i64, c_p, i64, c_p, i64, i64]
         lib.ref_bitmap_copy.restype = None
@@ -101,6 +102,10 @@ def ref():
                 f = getattr(lib, f"arithmetic_unary_diff_type_{isa}")
                 f.restype = None
                 f.argtypes = [C.c_int, C.c_int, C.c_int8, c_p, c_p, C.c_int]
+                f = getattr(lib, f"cast_type_numeric_{isa}", None)  # (itype, otype, in, out, len)
+                if f is not None:
+                    f.restype = None
+                    f.argtypes = [C.c_int, C.c_int, c_p, c_p, C.c_int]
                 for op in ("equal", "not_equal", "greater", "greater_equal"):
                     for sh in ("arr_arr", "arr_scalar", "scalar_arr"):
                         f = getattr(lib, f"comparison_{op}_{sh}_{isa}")

@@ -61,4 +61,11 @@ timed("add_unchecked_i64", lambda: N.call("ag_arith_binary_dev", N.INT64, N.OP_A
 timed("bitmap_and_100m_bits", lambda: N.call("ag_bitmap_op_dev", N.BITOP_AND, valid.ptr, 0, mask.ptr, 5, o.ptr, 3, rows, None))
 timed("bitmap_popcount_100m_bits", lambda: N.call("ag_bitmap_popcount_dev", valid.ptr, 3, rows - 3, scal.ptr, None))
 timed("abs_f64", lambda: N.call("ag_arith_unary_same_dev", N.FLOAT64, N.OP_ABS, a.ptr, o.ptr, rows, None))
+# numeric casts (implicit promotion): a holds int64 in [-1000, 1000]; idx holds int32
+timed("cast_i32_to_i64", lambda: N.call("ag_cast_numeric_dev", N.INT32, N.INT64, idx.ptr, o.ptr, rows, None))
+timed("cast_i64_to_f64_checked", lambda: N.call("ag_cast_numeric_checked_dev", N.INT64, N.FLOAT64, a.ptr, None, 0, o.ptr, rows, 0, 0, bad.ptr, None))
+timed("cast_i64_to_f64_checked_nulls", lambda: N.call("ag_cast_numeric_checked_dev", N.INT64, N.FLOAT64, a.ptr, valid.ptr, 3, o.ptr, rows, 0, 0, bad.ptr, None))
+timed("cast_i64_to_i32_checked", lambda: N.call("ag_cast_numeric_checked_dev", N.INT64, N.INT32, a.ptr, None, 0, o.ptr, rows, 0, 0, bad.ptr, None))
+timed("cast_i32_to_i8_unsafe", lambda: N.call("ag_cast_numeric_dev", N.INT32, N.INT8, idx.ptr, o.ptr, rows, None))
+timed("cast_f64_to_f32", lambda: N.call("ag_cast_numeric_dev", N.FLOAT64, N.FLOAT32, b.ptr, o.ptr, rows, None))
 print("selected rows:", cnt)

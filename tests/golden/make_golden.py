@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-from helpers import ALL_TYPES, NP_OF, TYPE_NAME, random_values  # noqa: E402
+from helpers import ALL_TYPES, NP_OF, TYPE_NAME, cast_inputs, random_values  # noqa: E402
 from oracle import oracle  # noqa: E402
 
 
@@ -64,6 +64,21 @@ def main():
                 o = np.full(12, 0xA5, dtype=np.uint8)
                 getattr(ref, f"comparison_{cn}_{sn}_avx2")(t, l.ctypes.data, r.ctypes.data, o.ctypes.data, n, 3)
                 out[f"cmp/{TYPE_NAME[t]}/{ci}/{shape}"] = o
+    # numeric casts: every ordered pair of distinct types, n = 67 (vector body + scalar tail),
+    # inputs whose converted value is representable (helpers.cast_inputs)
+    crng = np.random.default_rng(0xCA57)
+    for ti in ALL_TYPES:
+        for to in ALL_TYPES:
+            if ti == to:
+                continue
+            x = cast_inputs(crng, ti, to, n)
+            o = np.empty(n, dtype=NP_OF[to])
+            ref.cast_type_numeric_avx2(ti, to, x.ctypes.data, o.ctypes.data, n)
+            o2 = np.empty(n, dtype=NP_OF[to])
+            ref.cast_type_numeric_sse4(ti, to, x.ctypes.data, o2.ctypes.data, n)
+            assert o.tobytes() == o2.tobytes() or np.dtype(NP_OF[to]).kind == "f", (ti, to)
+            out[f"cast/{TYPE_NAME[ti]}/{TYPE_NAME[to]}/x"] = x
+            out[f"cast/{TYPE_NAME[ti]}/{TYPE_NAME[to]}/o"] = o
     path = os.path.join(HERE, "ref_simd_vectors.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path)} bytes")

@@ -49,6 +49,30 @@ def random_values(rng, type_id, n, small=False):
     return rng.integers(info.min, info.max, n, dtype=dt, endpoint=True)
 
 
+def cast_inputs(rng, itype, otype, n):
+    """Inputs for a numeric cast whose converted value is representable in the output type —
+    the domain on which the reference's AVX2 / SSE4 / scalar code agree (and the only one a
+    safe cast accepts).  int -> anything and float -> float are defined on the whole input
+    range; float -> int is restricted to truncations that fit."""
+    idt, odt = np.dtype(NP_OF[itype]), np.dtype(NP_OF[otype])
+    if idt.kind != "f":
+        return random_values(rng, itype, n)
+    if odt.kind == "f":
+        v = (rng.standard_normal(n) * 10.0 ** rng.integers(-3, 30, n)).astype(idt)
+        if n > 8:
+            v[rng.integers(0, n, 4)] = [np.nan, np.inf, -np.inf, -0.0]
+        return v
+    info = np.iinfo(odt)
+    # stay strictly inside the output range after rounding to the input float type
+    shrink = 1.0 - 2.0 ** -20
+    lo, hi = max(float(info.min), -2.0 ** 62) * shrink, min(float(info.max), 2.0 ** 62) * shrink
+    v = rng.uniform(lo, hi, n)
+    k = rng.integers(0, 4, n)
+    v = np.where(k == 0, np.trunc(v), v)                    # whole numbers (pass the safe check)
+    v = np.where(k == 1, rng.uniform(max(lo, -300.0), min(hi, 300.0), n), v)  # small magnitudes
+    return v.astype(idt)
+
+
 def same_bits(a, b):
     """Bit-exact equality (NaN payloads included)."""
     a = np.ascontiguousarray(a)

@@ -311,3 +311,99 @@ def test_is_null_is_not_null_is_nan():
     assert nan.to_pylist() == [False, True, False, False] and nan.type == pc.BOOL
     s = pc.Array.from_pylist([None, 1, None, 4, 5, None, 7, 8, 9], pc.INT64).slice(1, 7)
     assert pc.CallFunction("is_null", [s]).to_pylist() == [False, True, False, False, True, False, False]
+
+
+# ---------------------------------------------------------------- cast + implicit promotion ----
+def test_cast_reference_vectors():
+    """arrow/compute/cast_test.go:483-629 through compute.CastDatum (tests/golden/cast_numeric.json)."""
+    name_to_id = {"int8": pc.INT8, "int16": pc.INT16, "int32": pc.INT32, "int64": pc.INT64, "uint8": pc.UINT8, "uint16": pc.UINT16,
+                  "uint32": pc.UINT32, "uint64": pc.UINT64, "float32": pc.FLOAT32, "float64": pc.FLOAT64}
+    for case in load("cast_numeric.json")["cases"]:
+        ti, to = name_to_id[case["from"]], name_to_id[case["to"]]
+        vals = list(case["in"])
+        for i in case.get("null_at", []):
+            vals[i] = None
+        arr = pc.Array.from_pylist(vals, ti)
+        if "slice" in case:
+            arr = arr.slice(case["slice"][0], case["slice"][1] - case["slice"][0])
+        kw = dict(allow_int_overflow=bool(case.get("allow_int_overflow")), allow_float_truncate=bool(case.get("allow_float_truncate")))
+        if case.get("fails"):
+            with pytest.raises(pc.ArrowError) as e:
+                pc.Cast(arr, to, **kw)
+            assert e.value.sentinel == "ErrInvalid", case
+            assert ("not in range" in e.value.msg) or ("was truncated" in e.value.msg), e.value.msg
+        else:
+            out = pc.Cast(arr, to, **kw)
+            assert out.type == to and out.to_pylist() == case["out"], case
+    # error wording (helpers.go:591-594, numeric_cast.go:614-617)
+    with pytest.raises(pc.ArrowError) as e:
+        pc.Cast(pc.Array.from_pylist([0, None, 2000, 70000, 2], pc.INT32), pc.INT16)
+    assert "integer value 70000 not in range: -32768 to 32767" in e.value.msg
+    with pytest.raises(pc.ArrowError) as e:
+        pc.Cast(pc.Array.from_pylist([1.0, 2.5], pc.FLOAT64), pc.INT32)
+    assert "float value 2.500000 was truncated converting to int32" in e.value.msg
+
+
+def test_cast_same_type_chunked_scalar():
+    a = pc.Array.from_pylist([1, None, 3], pc.INT32)
+    assert pc.Cast(a, pc.INT32).to_pylist() == [1, None, 3]                      # castMetaFunc: same type returns the input
+    rng = np.random.default_rng(5)
+    x = rng.integers(-1000, 1000, 5000).astype(np.int16)
+    v = rng.random(5000) > 0.2
+    cuts = [0, 1, 999, 1000, 4099, 5000]
+    c = pc.Chunked([pc.Array.from_numpy(x[s:e], v[s:e]) for s, e in zip(cuts, cuts[1:])], pc.INT16)
+    out = pc.Cast(c, pc.FLOAT64)
+    assert out.kind == pc.KIND_CHUNKED and out.type == pc.FLOAT64
+    vals, valid, _ = out.to_numpy()
+    assert np.array_equal(valid, v) and np.array_equal(vals[v], x.astype(np.float64)[v])
+    # sliced input (offset not a multiple of 8) keeps its validity
+    full = pc.Array.from_numpy(x, v)
+    vals, valid, _ = pc.Cast(full.slice(13, 777), pc.INT64).to_numpy()
+    assert np.array_equal(valid, v[13:790]) and np.array_equal(vals[valid], x[13:790].astype(np.int64)[valid])
+    # scalars
+    assert pc.scalar_value(pc.Cast(pc.Scalar(7, pc.INT8), pc.FLOAT32)) == 7.0
+    assert pc.scalar_value(pc.Cast(pc.Scalar(None, pc.INT8), pc.INT64)) is None
+    with pytest.raises(pc.ArrowError):
+        pc.Cast(pc.Scalar(300, pc.INT32), pc.UINT8)
+
+
+@pytest.mark.parametrize("fname", ["add", "sub", "multiply", "add_unchecked"])
+def test_arithmetic_implicit_promotion(fname):
+    """exec.go:101-121: DispatchBest picks the common numeric type and the arguments are cast with
+    SafeCastOptions before the kernel runs (arithmetic_test.go:715-753 names the expected types)."""
+    rng = np.random.default_rng(11)
+    n = 3000
+    npf = {"add": np.add, "sub": np.subtract, "multiply": np.multiply, "add_unchecked": np.add}[fname]
+    combos = [(pc.INT32, pc.INT64, pc.INT64), (pc.INT8, pc.UINT8, pc.INT16), (pc.UINT16, pc.INT32, pc.INT32),
+              (pc.INT32, pc.FLOAT64, pc.FLOAT64), (pc.FLOAT32, pc.INT16, pc.FLOAT32), (pc.UINT8, pc.UINT32, pc.UINT32)]
+    for lt, rt, want_t in combos:
+        l = rng.integers(0, 11, n).astype(pc.NP_OF[lt]) if lt not in (pc.FLOAT32, pc.FLOAT64) else rng.standard_normal(n).astype(pc.NP_OF[lt])
+        r = rng.integers(0, 11, n).astype(pc.NP_OF[rt]) if rt not in (pc.FLOAT32, pc.FLOAT64) else rng.standard_normal(n).astype(pc.NP_OF[rt])
+        lv, rv = rng.random(n) > 0.1, rng.random(n) > 0.1
+        out = pc.CallFunction(fname, [pc.Array.from_numpy(l, lv), pc.Array.from_numpy(r, rv)])
+        assert out.type == want_t, (lt, rt)
+        vals, valid, _ = out.to_numpy()
+        assert np.array_equal(valid, lv & rv)
+        want = npf(l.astype(pc.NP_OF[want_t]), r.astype(pc.NP_OF[want_t]))
+        assert np.array_equal(vals[valid], want[valid]), (fname, lt, rt)
+        # array (op) scalar of another type: the scalar is cast too
+        out = pc.CallFunction(fname, [pc.Array.from_numpy(l, lv), pc.Scalar(r[0].item(), rt)])
+        assert out.type == want_t
+        vals, valid, _ = out.to_numpy()
+        want = npf(l.astype(pc.NP_OF[want_t]), r[:1].astype(pc.NP_OF[want_t]))
+        assert np.array_equal(valid, lv) and np.array_equal(vals[valid], want[valid])
+    # int64 -> float64 promotion is a SAFE cast: values beyond 2^53 make the call fail
+    big = pc.Array.from_pylist([1, (1 << 53) + 1], pc.INT64)
+    with pytest.raises(pc.ArrowError) as e:
+        pc.CallFunction("add", [big, pc.Array.from_pylist([0.5, 0.5], pc.FLOAT64)])
+    assert "not in range" in e.value.msg
+    # compare promotes the same way
+    out = pc.CallFunction("greater", [pc.Array.from_pylist([1, 200, None], pc.UINT8), pc.Array.from_pylist([-1, 300, 5], pc.INT16)])
+    assert out.to_pylist() == [True, False, None]
+    # chunked (op) array of another type
+    l = rng.integers(-100, 100, n).astype(np.int32)
+    r = rng.standard_normal(n)
+    cuts = [0, 7, 1500, n]
+    out = pc.CallFunction(fname, [pc.Chunked([pc.Array.from_numpy(l[s:e]) for s, e in zip(cuts, cuts[1:])], pc.INT32), pc.Array.from_numpy(r)])
+    vals, _, _ = out.to_numpy()
+    assert out.type == pc.FLOAT64 and np.array_equal(vals, npf(l.astype(np.float64), r))

@@ -59,7 +59,8 @@ def test_registry_has_the_reference_function_names():
     for n in ("add", "add_unchecked", "sub", "sub_unchecked", "subtract", "subtract_unchecked", "multiply", "multiply_unchecked",
               "abs", "abs_unchecked", "negate", "negate_unchecked", "sign", "is_null", "is_not_null", "is_nan", "equal", "not_equal", "greater", "greater_equal", "less", "less_equal",
               "and", "or", "xor", "and_not", "and_kleene", "or_kleene", "and_not_kleene", "not",
-              "filter", "array_filter", "take", "array_take"):
+              "filter", "array_filter", "take", "array_take", "cast", "cast_int8", "cast_int16", "cast_int32", "cast_int64",
+              "cast_uint8", "cast_uint16", "cast_uint32", "cast_uint64", "cast_float", "cast_double"):
         assert n in names, n
 
 
@@ -68,10 +69,56 @@ def test_exact_type_dispatch():
     pc.dispatch("greater", [pc.INT64, pc.INT64])
     pc.dispatch("and_kleene", [pc.BOOL, pc.BOOL])
     with pytest.raises(pc.ArrowError) as e:
-        pc.dispatch("add", [pc.INT32, pc.FLOAT64])  # implicit promotion (cast) is out of scope
+        pc.dispatch("add", [pc.INT32, pc.FLOAT64])  # DispatchExact alone does not promote
     assert e.value.sentinel == "ErrNotImplemented"
     with pytest.raises(pc.ArrowError):
         pc.dispatch("no_such_function", [pc.INT32])
+
+
+def test_binary_arithmetic_dispatch_best():
+    """arrow/compute/arithmetic_test.go:715-753 TestBinaryArithmeticDispatchBest (numeric rows) and the
+    compare functions' DispatchBest (scalar_compare.go:37-65)."""
+    rows = [(pc.INT32, pc.INT32, pc.INT32), (pc.INT32, pc.INT8, pc.INT32), (pc.INT32, pc.INT16, pc.INT32),
+            (pc.INT32, pc.INT64, pc.INT64), (pc.INT32, pc.UINT8, pc.INT32), (pc.INT32, pc.UINT16, pc.INT32),
+            (pc.INT32, pc.UINT32, pc.INT64), (pc.INT32, pc.UINT64, pc.INT64), (pc.UINT8, pc.UINT8, pc.UINT8),
+            (pc.UINT8, pc.UINT16, pc.UINT16), (pc.INT32, pc.FLOAT32, pc.FLOAT32), (pc.FLOAT32, pc.INT64, pc.FLOAT32),
+            (pc.FLOAT64, pc.INT32, pc.FLOAT64)]
+    for name in ("add", "sub", "multiply"):
+        for suffix in ("", "_unchecked"):
+            for l, r, want in rows:
+                assert pc.dispatch_best(name + suffix, [l, r]) == [want, want], (name, l, r)
+    for name in ("equal", "not_equal", "greater", "greater_equal", "less", "less_equal"):
+        for l, r, want in rows:
+            assert pc.dispatch_best(name, [l, r]) == [want, want]
+    # unary functions and non-numeric arguments never promote
+    with pytest.raises(pc.ArrowError):
+        pc.dispatch_best("add", [pc.BOOL, pc.INT32])
+    with pytest.raises(pc.ArrowError):
+        pc.dispatch_best("and", [pc.INT8, pc.INT32])
+
+
+def test_common_numeric_table():
+    """commonNumeric (utils.go:178-240) against an independent model: floats win, otherwise the
+    narrowest integer type that holds both ranges, saturating at 64 bits (uint64 + signed -> int64)."""
+    ints = {pc.UINT8: (8, 0), pc.INT8: (8, 1), pc.UINT16: (16, 0), pc.INT16: (16, 1),
+            pc.UINT32: (32, 0), pc.INT32: (32, 1), pc.UINT64: (64, 0), pc.INT64: (64, 1)}
+    by = {v: k for k, v in ints.items()}
+    allt = list(ints) + [pc.FLOAT32, pc.FLOAT64]
+    for a in allt:
+        for b in allt:
+            if pc.FLOAT64 in (a, b):
+                want = pc.FLOAT64
+            elif pc.FLOAT32 in (a, b):
+                want = pc.FLOAT32
+            else:
+                (wa, sa), (wb, sb) = ints[a], ints[b]
+                if sa == sb:
+                    want = by[(max(wa, wb), sa)]
+                else:
+                    ws, wu = (wa, wb) if sa else (wb, wa)
+                    want = by[(min(64, ws if ws > wu else 2 * wu), 1)]
+            assert pc.common_numeric([a, b]) == want, (a, b)
+    assert pc.common_numeric([pc.BOOL, pc.INT8]) is None
 
 
 def _model_spans(arg_lens, chunked, max_chunk):
