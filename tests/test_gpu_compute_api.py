@@ -377,7 +377,8 @@ def test_arithmetic_implicit_promotion(fname):
     combos = [(pc.INT32, pc.INT64, pc.INT64), (pc.INT8, pc.UINT8, pc.INT16), (pc.UINT16, pc.INT32, pc.INT32),
               (pc.INT32, pc.FLOAT64, pc.FLOAT64), (pc.FLOAT32, pc.INT16, pc.FLOAT32), (pc.UINT8, pc.UINT32, pc.UINT32)]
     for lt, rt, want_t in combos:
-        l = rng.integers(0, 11, n).astype(pc.NP_OF[lt]) if lt not in (pc.FLOAT32, pc.FLOAT64) else rng.standard_normal(n).astype(pc.NP_OF[lt])
+        # left operand >= right operand so that checked "sub" on unsigned types stays in range
+        l = rng.integers(20, 31, n).astype(pc.NP_OF[lt]) if lt not in (pc.FLOAT32, pc.FLOAT64) else rng.standard_normal(n).astype(pc.NP_OF[lt])
         r = rng.integers(0, 11, n).astype(pc.NP_OF[rt]) if rt not in (pc.FLOAT32, pc.FLOAT64) else rng.standard_normal(n).astype(pc.NP_OF[rt])
         lv, rv = rng.random(n) > 0.1, rng.random(n) > 0.1
         out = pc.CallFunction(fname, [pc.Array.from_numpy(l, lv), pc.Array.from_numpy(r, rv)])
