@@ -11,6 +11,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libarrowgpu.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "arrowgpu.h")
+CDATA_HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "arrowgpu_cdata.h")
 
 # status codes (include/arrowgpu.h)
 AG_OK, AG_ERR_INVALID, AG_ERR_INDEX, AG_ERR_NOT_IMPLEMENTED, AG_ERR_TYPE, AG_ERR_CUDA, AG_ERR_OOM = range(7)
@@ -150,7 +151,48 @@ for _op in ("eq", "ne", "gt", "ge"):
     for _sh in ("aa", "as", "sa"):
         _SIGS[f"ag_cmp_{_op}_{_sh}"] = [_i, _p, _p, _p, _i64, _i]
 
+# Arrow C Data / C Device Data Interface structs (include/arrowgpu_cdata.h)
+class ArrowSchema(C.Structure):
+    pass
+
+
+ArrowSchema._fields_ = [("format", C.c_char_p), ("name", C.c_char_p), ("metadata", C.c_char_p), ("flags", C.c_int64),
+                        ("n_children", C.c_int64), ("children", C.c_void_p), ("dictionary", C.c_void_p),
+                        ("release", C.CFUNCTYPE(None, C.POINTER(ArrowSchema))), ("private_data", C.c_void_p)]
+
+
+class ArrowArray(C.Structure):
+    pass
+
+
+ArrowArray._fields_ = [("length", C.c_int64), ("null_count", C.c_int64), ("offset", C.c_int64), ("n_buffers", C.c_int64),
+                       ("n_children", C.c_int64), ("buffers", C.POINTER(C.c_void_p)), ("children", C.c_void_p),
+                       ("dictionary", C.c_void_p), ("release", C.CFUNCTYPE(None, C.POINTER(ArrowArray))),
+                       ("private_data", C.c_void_p)]
+
+
+class ArrowDeviceArray(C.Structure):
+    _fields_ = [("array", ArrowArray), ("device_id", C.c_int64), ("device_type", C.c_int32), ("sync_event", C.c_void_p),
+                ("reserved", C.c_int64 * 3)]
+
+
+class ArrayView(C.Structure):  # ag_array_view
+    _fields_ = [("type", C.c_int), ("length", C.c_int64), ("null_count", C.c_int64), ("offset", C.c_int64),
+                ("validity", C.c_void_p), ("values", C.c_void_p), ("device_type", C.c_int32), ("device_id", C.c_int64)]
+
+
+RELEASE_BUFFERS_FN = C.CFUNCTYPE(None, C.c_void_p)
+DEVICE_CPU, DEVICE_CUDA, DEVICE_CUDA_HOST, DEVICE_CUDA_MANAGED = 1, 2, 3, 13
+
+_SIGS.update({
+    "ag_schema_format_to_type": [C.c_char_p, C.POINTER(_i)],
+    "ag_device_array_describe": [C.POINTER(ArrowDeviceArray), C.POINTER(ArrowSchema), C.POINTER(ArrayView)],
+    "ag_export_device_array": [_i, _i64, _i64, _i64, _p, _p, RELEASE_BUFFERS_FN, _p, _p, C.POINTER(ArrowDeviceArray), C.POINTER(ArrowSchema)],
+    "ag_import_device_array": [C.POINTER(ArrowDeviceArray), C.POINTER(ArrowSchema), _p, C.POINTER(ArrayView)],
+})
+
 _SPECIAL = {
+    "ag_type_to_schema_format": (C.c_char_p, [_i]),
     "ag_last_error": (None, [C.c_char_p, _sz]),
     "ag_version": (C.c_char_p, []),
     "ag_kernel_launch_count": (C.c_uint64, []),
@@ -214,8 +256,8 @@ def call_status(name, *args):
 
 
 def declared_symbols():
-    """Every function name declared in include/arrowgpu.h (for the export check)."""
+    """Every function name declared in include/arrowgpu.h and include/arrowgpu_cdata.h (for the export check)."""
     import re
-    text = open(HEADER_PATH).read()
+    text = open(HEADER_PATH).read() + open(CDATA_HEADER_PATH).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(ag_[a-z0-9_]+)\s*\(", text)))

@@ -78,6 +78,8 @@ def lib():
         h.agx_dispatch_best.argtypes = [C.c_char_p, C.POINTER(i), i]
         h.agx_common_numeric.argtypes = [C.POINTER(i), i]
         h.agx_cast.argtypes = [p, i, i, i, pp]
+        h.agx_export_device.argtypes = [p, C.POINTER(N.ArrowDeviceArray), C.POINTER(N.ArrowSchema)]
+        h.agx_import_device.argtypes = [C.POINTER(N.ArrowDeviceArray), C.POINTER(N.ArrowSchema), pp]
         h.agx_scalar_value.argtypes = [p, C.POINTER(i), p]
         _lib = h
     return _lib
@@ -248,6 +250,21 @@ def Subtract(l, r, no_check_overflow=False):
 
 def Multiply(l, r, no_check_overflow=False):
     return _arith(2, l, r, no_check_overflow)
+
+
+def export_device(arr):
+    """Array datum -> (ArrowDeviceArray, ArrowSchema) sharing the device buffers (zero copy).  The
+    consumer (or release_device) must call array.release."""
+    da, sc = N.ArrowDeviceArray(), N.ArrowSchema()
+    _check(lib().agx_export_device(arr._h, C.byref(da), C.byref(sc)))
+    return da, sc
+
+
+def import_device(device_array, schema):
+    """(ArrowDeviceArray, ArrowSchema) -> Array datum; takes ownership of the device array."""
+    out = C.c_void_p()
+    _check(lib().agx_import_device(C.byref(device_array), C.byref(schema), C.byref(out)))
+    return Datum(out)
 
 
 def Cast(value, to_type, allow_int_overflow=False, allow_float_truncate=False):

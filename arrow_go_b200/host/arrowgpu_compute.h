@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "../../include/arrowgpu.h"
+#include "../../include/arrowgpu_cdata.h"
 
 namespace arrowgpu {
 
@@ -65,10 +66,15 @@ class Buffer {
   int64_t size() const { return size_; }
   static Status Allocate(int64_t nbytes, std::shared_ptr<Buffer>* out);          // zero-filled, 64-B padded
   static Status FromHost(const void* host, int64_t nbytes, std::shared_ptr<Buffer>* out);
+  // Foreign device memory (an imported ArrowDeviceArray): not freed, `on_release` runs when the last
+  // reference goes away (memory.Buffer with a custom release, arrow/cdata/cdata.go importedBuffer).
+  static std::shared_ptr<Buffer> Wrap(const void* device_ptr, int64_t nbytes, std::function<void()> on_release);
   Status ToHost(void* host, int64_t nbytes, int64_t byte_offset = 0) const;
  private:
   uint8_t* data_ = nullptr;
   int64_t size_ = 0;
+  bool foreign_ = false;
+  std::function<void()> on_release_;
 };
 
 // arrow.ArrayData for primitive / boolean arrays (arrow/array/data.go:30-42)
@@ -85,6 +91,12 @@ struct ArrayData {
   // Copies the logical [0,length) range out: values (length elements, or ceil(length/8) bytes for BOOL,
   // bit 0 = element 0) and validity (ceil(length/8) bytes; all ones when there is no bitmap).
   Status ToHost(void* values, uint8_t* validity, int64_t* null_count) const;
+  // Arrow C Device Data Interface (include/arrowgpu_cdata.h).  Export shares the buffers: the exported
+  // struct keeps them alive until the consumer calls release.  Import takes ownership of `in`
+  // (moves it; in->array.release is called when the last buffer reference is dropped) and makes the
+  // default stream wait on its sync_event.
+  Status ExportDevice(struct ArrowDeviceArray* out, struct ArrowSchema* out_schema) const;
+  static Status ImportDevice(struct ArrowDeviceArray* in, const struct ArrowSchema* schema, std::shared_ptr<ArrayData>* out);
 };
 
 struct ChunkedArray {  // arrow.Chunked (arrow/table.go:135-143)

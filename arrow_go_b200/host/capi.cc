@@ -125,6 +125,19 @@ int agx_sum_u64(agx_datum* d, uint64_t* out) {
   return AG_OK;
 }
 
+// Arrow C Device Data Interface: export an Array datum / import one (takes ownership of *in)
+int agx_export_device(agx_datum* d, struct ArrowDeviceArray* out, struct ArrowSchema* out_schema) {
+  if (d->d.kind != DatumKind::ARRAY) return fail(Status::Invalid("export: not an array"));
+  AGX_TRY(d->d.array->ExportDevice(out, out_schema));
+  return AG_OK;
+}
+int agx_import_device(struct ArrowDeviceArray* in, const struct ArrowSchema* schema, agx_datum** out) {
+  std::shared_ptr<ArrayData> a;
+  AGX_TRY(ArrayData::ImportDevice(in, schema, &a));
+  *out = new agx_datum{Datum(a)};
+  return AG_OK;
+}
+
 // metadata-only pieces (run without a GPU)
 int agx_iterate_spans(const int64_t* lens_flat, const int* nchunks, const int* is_chunked, int nargs, int64_t max_chunk,
                       int64_t* out_pos_len, int* out_chunk_idx, int cap, int* n_out) {

@@ -51,7 +51,19 @@ static inline int64_t BytesForBits(int64_t n) { return (n + 7) / 8; }
 static inline int64_t DataBytes(Type t, int64_t n) { return t == Type::BOOL ? BytesForBits(n) : n * (BitWidth(t) / 8); }
 
 // ---------------------------------------------------------------- Buffer ------------------
-Buffer::~Buffer() { if (data_) ag_dev_free(data_); }
+Buffer::~Buffer() {
+  if (foreign_) { if (on_release_) on_release_(); }
+  else if (data_) ag_dev_free(data_);
+}
+
+std::shared_ptr<Buffer> Buffer::Wrap(const void* device_ptr, int64_t nbytes, std::function<void()> on_release) {
+  auto b = std::shared_ptr<Buffer>(new Buffer());
+  b->data_ = const_cast<uint8_t*>(static_cast<const uint8_t*>(device_ptr));
+  b->size_ = nbytes;
+  b->foreign_ = true;
+  b->on_release_ = std::move(on_release);
+  return b;
+}
 
 Status Buffer::Allocate(int64_t nbytes, std::shared_ptr<Buffer>* out) {
   auto b = std::shared_ptr<Buffer>(new Buffer());
@@ -79,6 +91,37 @@ Status Buffer::ToHost(void* host, int64_t nbytes, int64_t byte_offset) const {
 }
 
 // ---------------------------------------------------------------- ArrayData ---------------
+namespace {
+struct ExportedBuffers { std::shared_ptr<Buffer> b[2]; };
+void ReleaseExportedBuffers(void* opaque) { delete static_cast<ExportedBuffers*>(opaque); }
+}  // namespace
+
+Status ArrayData::ExportDevice(struct ArrowDeviceArray* out, struct ArrowSchema* out_schema) const {
+  auto* keep = new ExportedBuffers{{buffers[0], buffers[1]}};
+  const int rc = ag_export_device_array((int)type, length, null_count, offset, buffers[0] ? buffers[0]->data() : nullptr,
+                                        buffers[1] ? buffers[1]->data() : nullptr, ReleaseExportedBuffers, keep, nullptr, out, out_schema);
+  if (rc != AG_OK) { delete keep; return Status::FromNative(rc); }
+  return Status::OK();
+}
+
+Status ArrayData::ImportDevice(struct ArrowDeviceArray* in, const struct ArrowSchema* schema, std::shared_ptr<ArrayData>* out) {
+  ag_array_view v;
+  NATIVE(ag_import_device_array(in, schema, nullptr, &v));
+  if (v.type == 0) return Status::Invalid("import: a schema is required");
+  // move the struct: the importer owns it now (C Data Interface "moving an array")
+  auto owned = std::make_shared<ArrowDeviceArray>(*in);
+  in->array.release = nullptr;
+  auto releaser = std::shared_ptr<void>(nullptr, [owned](void*) { if (owned->array.release) owned->array.release(&owned->array); });
+  auto d = std::make_shared<ArrayData>();
+  d->type = (Type)v.type; d->length = v.length; d->offset = v.offset; d->null_count = v.null_count;
+  const int64_t n = v.offset + v.length;
+  if (v.validity) d->buffers[0] = Buffer::Wrap(v.validity, BytesForBits(n), [releaser] {});
+  d->buffers[1] = Buffer::Wrap(v.values, DataBytes((Type)v.type, n), [releaser] {});
+  if (!v.validity) d->null_count = 0;
+  *out = d;
+  return Status::OK();
+}
+
 std::shared_ptr<ArrayData> ArrayData::Slice(int64_t off, int64_t len) const {
   auto d = std::make_shared<ArrayData>(*this);
   d->offset = offset + off;
