@@ -112,6 +112,8 @@ _SIGS = {
     "ag_arith_unary_checked": [_i, _i8, _p, _p, _i64, _pi64],
     "ag_arith_unary_checked_dev": [_i, _i8, _p, _p, _i64, _p, _p],
     "ag_error_word_reset_dev": [_p, _p],
+    "ag_min_max": [_i, _p, _i64, _p, _p],
+    "ag_min_max_dev": [_i, _p, _i64, _p, _p],
     # numeric casts
     "ag_cast_numeric": [_i, _i, _p, _p, _i64],
     "ag_cast_numeric_dev": [_i, _i, _p, _p, _i64, _p],

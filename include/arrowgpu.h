@@ -185,6 +185,17 @@ ag_status ag_sum_u64_dev(const uint64_t* d_buf, size_t n, uint64_t* d_res, ag_st
 ag_status ag_sum_f64_reforder_dev(const double* d_buf, size_t n, double* d_res, ag_stream_t s);
 
 /* ================================================================================= *
+ * Integer min/max — replaces {int,uint}{8,16,32,64}_max_min_{avx2,sse4,neon}
+ *   (internal/utils/_lib/min_max.c:23-125; Go: GetMinMaxInt8 ... GetMinMaxUint64,
+ *   internal/utils/min_max.go) — the reduction behind Parquet column statistics
+ *   (parquet/metadata/statistics_types.gen.go:160-190,464-490).  n == 0 gives the
+ *   reference's initial values (type MAX, type MIN).  The device flavour writes
+ *   {min, max} as two consecutive elements of the value type.
+ * ================================================================================= */
+ag_status ag_min_max(int type, const void* values, int64_t n, void* min_out, void* max_out);
+ag_status ag_min_max_dev(int type, const void* d_values, int64_t n, void* d_min_max, ag_stream_t s);
+
+/* ================================================================================= *
  * Arithmetic — replaces arithmetic_{binary,arr_scalar,scalar_arr,unary_same_types,
  *   unary_diff_type}_{avx2,sse4} (_lib/base_arithmetic.cc:465-483) and the pure-Go
  *   fallbacks of base_arithmetic.go.  Computed for EVERY slot (ScalarBinary

@@ -344,6 +344,29 @@ int ref_arith_unary_checked(int type, int op, const void* in, void* out, int64_t
 }
 
 /* ====================================================================================== *
+ * Integer min/max: internal/utils/min_max.go:25-210 (pure Go) = internal/utils/_lib/min_max.c:23-125.
+ * Initial values (type MAX, type MIN) are what an empty input returns.
+ * ====================================================================================== */
+#define MINMAX_LOOP(T, TMIN, TMAX)                                                      \
+  do { T lo = (TMAX), hi = (TMIN); const T* V = (const T*)in;                            \
+       for (int64_t i = 0; i < n; ++i) { if (lo > V[i]) lo = V[i]; if (hi < V[i]) hi = V[i]; } \
+       *(T*)min_out = lo; *(T*)max_out = hi; } while (0)
+int ref_min_max(int type, const void* in, int64_t n, void* min_out, void* max_out) {
+  switch (type) {
+    case T_I8: MINMAX_LOOP(int8_t, INT8_MIN, INT8_MAX); break;
+    case T_U8: MINMAX_LOOP(uint8_t, 0, UINT8_MAX); break;
+    case T_I16: MINMAX_LOOP(int16_t, INT16_MIN, INT16_MAX); break;
+    case T_U16: MINMAX_LOOP(uint16_t, 0, UINT16_MAX); break;
+    case T_I32: MINMAX_LOOP(int32_t, INT32_MIN, INT32_MAX); break;
+    case T_U32: MINMAX_LOOP(uint32_t, 0, UINT32_MAX); break;
+    case T_I64: MINMAX_LOOP(int64_t, INT64_MIN, INT64_MAX); break;
+    case T_U64: MINMAX_LOOP(uint64_t, 0, UINT64_MAX); break;
+    default: return REF_ERR_TYPE;
+  }
+  return REF_OK;
+}
+
+/* ====================================================================================== *
  * Numeric casts: the loop K/cast_numeric.go:101-131 (= K/_lib/cast_numeric.cc:22-101) framed by
  * the safe-cast checks of K/numeric_cast.go:37-71 —
  *   int -> int    intsCanFit (K/helpers.go:545-578) bounds from getSafeMinMax* (:496-543),

@@ -47,6 +47,9 @@ int ref_arith_checked(int type, int op, int shape,
 
 int ref_arith_unary_checked(int type, int op, const void* in, void* out, int64_t n, int64_t* first_bad);
 
+/* integer min/max */
+int ref_min_max(int type, const void* in, int64_t n, void* min_out, void* max_out);
+
 /* numeric casts (loop + safe-cast checks) */
 int ref_cast_numeric(int itype, int otype, const void* in, const uint8_t* valid, int64_t voff, void* out, int64_t n,
                      int allow_int_overflow, int allow_float_truncate, int64_t* first_bad);

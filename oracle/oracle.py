@@ -50,6 +50,7 @@ def cpu():
         lib.ref_arith_unary_diff.argtypes = [C.c_int, C.c_int, C.c_int, c_p, c_p, i64]
         lib.ref_arith_checked.argtypes = [C.c_int, C.c_int, C.c_int, c_p, c_p, i64, c_p, c_p, i64, c_p, i64, C.POINTER(i64)]
         lib.ref_arith_unary_checked.argtypes = [C.c_int, C.c_int, c_p, c_p, i64, C.POINTER(i64)]
+        lib.ref_min_max.argtypes = [C.c_int, c_p, i64, c_p, c_p]
         lib.ref_cast_numeric.argtypes = [C.c_int, C.c_int, c_p, c_p, i64, c_p, i64, C.c_int, C.c_int, C.POINTER(i64)]
         lib.ref_compare.argtypes = [C.c_int, C.c_int, C.c_int, c_p, c_p, c_p, i64, C.c_int]
         lib.ref_bitmap_op.argtypes = [C.c_int, c_p, i64, c_p, i64, c_p, i64, i64]
@@ -102,6 +103,11 @@ def ref():
                 f = getattr(lib, f"arithmetic_unary_diff_type_{isa}")
                 f.restype = None
                 f.argtypes = [C.c_int, C.c_int, C.c_int8, c_p, c_p, C.c_int]
+                for t in ("int8", "uint8", "int16", "uint16", "int32", "uint32", "int64", "uint64"):
+                    f = getattr(lib, f"{t}_max_min_{isa}", None)  # (values, len, minout, maxout)
+                    if f is not None:
+                        f.restype = None
+                        f.argtypes = [c_p, C.c_int, c_p, c_p]
                 f = getattr(lib, f"cast_type_numeric_{isa}", None)  # (itype, otype, in, out, len)
                 if f is not None:
                     f.restype = None

@@ -68,4 +68,6 @@ timed("cast_i64_to_f64_checked_nulls", lambda: N.call("ag_cast_numeric_checked_d
 timed("cast_i64_to_i32_checked", lambda: N.call("ag_cast_numeric_checked_dev", N.INT64, N.INT32, a.ptr, None, 0, o.ptr, rows, 0, 0, bad.ptr, None))
 timed("cast_i32_to_i8_unsafe", lambda: N.call("ag_cast_numeric_dev", N.INT32, N.INT8, idx.ptr, o.ptr, rows, None))
 timed("cast_f64_to_f32", lambda: N.call("ag_cast_numeric_dev", N.FLOAT64, N.FLOAT32, b.ptr, o.ptr, rows, None))
+timed("min_max_i64", lambda: N.call("ag_min_max_dev", N.INT64, b.ptr, rows, scal.ptr, None))
+timed("min_max_i32", lambda: N.call("ag_min_max_dev", N.INT32, idx.ptr, rows, scal.ptr, None))
 print("selected rows:", cnt)
