@@ -114,6 +114,9 @@ _SIGS = {
     "ag_error_word_reset_dev": [_p, _p],
     "ag_min_max": [_i, _p, _i64, _p, _p],
     "ag_min_max_dev": [_i, _p, _i64, _p, _p],
+    "ag_cumulative_sum": [_i, _p, _p, _i64, _i64, _p, _i, _i, _p, _p, _pi64, _pi64],
+    "ag_cumulative_sum_state_init_dev": [_p, _i, _p, _p],
+    "ag_cumulative_sum_dev": [_i, _p, _p, _i64, _i64, _i, _i, _p, _p, _i64, _p, _p, _p],
     # numeric casts
     "ag_cast_numeric": [_i, _i, _p, _p, _i64],
     "ag_cast_numeric_dev": [_i, _i, _p, _p, _i64, _p],

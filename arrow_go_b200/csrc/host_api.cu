@@ -30,6 +30,9 @@ ag_status error_word_reset(int64_t* d_word, cudaStream_t st);
 ag_status arith_unary_checked_dev(int type, int8_t op, const void* in, void* out, int64_t n, int64_t* d_first_bad, cudaStream_t st);
 ag_status cast_numeric_dev(int itype, int otype, const void* in, const uint8_t* valid, int64_t voff, void* out, int64_t n,
                            int allow_int_overflow, int allow_float_truncate, int64_t* first_bad, int64_t row_base, cudaStream_t st);
+ag_status cumulative_sum_dev(int type, const void* in, const uint8_t* valid, int64_t voff, int64_t n, int skip_nulls, int checked,
+                             void* out, uint8_t* out_valid, int64_t ooff, void* d_state, int64_t* d_first_bad, cudaStream_t st);
+ag_status cumulative_sum_state_init(void* d_state, int type, const void* start_host, cudaStream_t st);
 ag_status compare_dev(int type, int cmp, int shape, const void* l, const void* r, uint8_t* out, int64_t n, int off, cudaStream_t st);
 ag_status bitmap_op_dev(int bitop, const uint8_t* l, int64_t loff, const uint8_t* r, int64_t roff, uint8_t* out, int64_t ooff, int64_t n, cudaStream_t st);
 ag_status bitmap_copy_dev(const uint8_t* src, int64_t soff, int64_t n, uint8_t* dst, int64_t doff, bool invert, cudaStream_t st);
@@ -351,6 +354,61 @@ ag_status ag_cast_numeric_checked(int itype, int otype, const void* in, const ui
     }
     AG_FAIL(AG_ERR_INVALID, "integer value not in range (row %lld)", (long long)bad);
   }
+  return AG_OK;
+}
+
+// ---- cumulative sum ----------------------------------------------------------------
+ag_status ag_cumulative_sum(int type, const void* in, const uint8_t* valid, int64_t valid_offset, int64_t n,
+                            const void* start, int skip_nulls, int checked,
+                            void* out, uint8_t* out_valid, int64_t* null_count, int64_t* first_bad) {
+  AG_TRY(ensure_init());
+  if (first_bad) *first_bad = AG_NO_ERROR_POS;
+  if (null_count) *null_count = 0;
+  const int w = type_width(type);
+  if (w == 0) AG_FAIL(AG_ERR_TYPE, "cumulative_sum: input type must be numeric, got type id %d", type);
+  if (n < 0 || valid_offset < 0) AG_FAIL(AG_ERR_INVALID, "cumulative_sum: negative length or offset");
+  if (n == 0) return AG_OK;
+  if (!in || !out) AG_FAIL(AG_ERR_INVALID, "cumulative_sum: NULL operand");
+  if (valid && !out_valid) AG_FAIL(AG_ERR_INVALID, "cumulative_sum: an input with a validity bitmap needs an output validity bitmap");
+  CallStream cs; AG_TRY(cs.acquire());
+  Temps t(cs);
+  void *din, *dout; int64_t* d_bad; uint8_t *dvalid = nullptr, *dovalid = nullptr; ag_cumsum_state* dstate;
+  AG_TRY(t.alloc(&din, (size_t)n * w)); AG_TRY(t.alloc(&dout, (size_t)n * w)); AG_TRY(t.alloc_t(&d_bad, sizeof(int64_t)));
+  AG_TRY(t.alloc_t(&dstate, sizeof(ag_cumsum_state)));
+  AG_TRY(h2d(din, in, (size_t)n * w, cs));
+  const int64_t vbyte0 = valid_offset >> 3;
+  const size_t obytes = (size_t)bytes_for_bits(n);
+  if (valid) {
+    const size_t vbytes = (size_t)(bytes_for_bits(valid_offset + n) - vbyte0);
+    AG_TRY(t.alloc_t(&dvalid, vbytes));
+    AG_TRY(h2d(dvalid, valid + vbyte0, vbytes, cs));
+  }
+  if (out_valid) {
+    AG_TRY(t.alloc_t(&dovalid, obytes + 4));
+    AG_CUDA_TRY(cudaMemsetAsync(dovalid, 0, obytes + 4, cs));
+  }
+  AG_TRY(error_word_reset(d_bad, cs));
+  AG_TRY(cumulative_sum_state_init(dstate, type, start, cs));
+  AG_TRY(cumulative_sum_dev(type, din, dvalid, valid_offset & 7, n, skip_nulls, checked, dout, dovalid, 0, dstate, d_bad, cs));
+  int64_t bad = AG_NO_ERROR_POS;
+  ag_cumsum_state hs;
+  AG_TRY(d2h(&bad, d_bad, sizeof(bad), cs));
+  AG_TRY(d2h(&hs, dstate, sizeof(hs), cs));
+  AG_TRY(d2h(out, dout, (size_t)n * w, cs));
+  if (out_valid) {
+    // whole bytes except the last, whose bits past n keep the caller's values
+    AG_TRY(sync(cs));
+    std::vector<uint8_t> tmp(obytes);
+    AG_TRY(d2h(tmp.data(), dovalid, obytes, cs));
+    AG_TRY(sync(cs));
+    const int tail = (int)(n & 7);
+    if (tail) { const uint8_t m = (uint8_t)((1u << tail) - 1u); tmp[obytes - 1] = (uint8_t)((tmp[obytes - 1] & m) | (out_valid[obytes - 1] & ~m)); }
+    memcpy(out_valid, tmp.data(), obytes);
+  }
+  AG_TRY(sync(cs));
+  if (first_bad) *first_bad = bad;
+  if (null_count) *null_count = hs.null_count;
+  if (checked && bad != AG_NO_ERROR_POS) AG_FAIL(AG_ERR_INVALID, "overflow");
   return AG_OK;
 }
 

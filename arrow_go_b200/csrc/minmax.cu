@@ -21,7 +21,7 @@ namespace {
 
 constexpr int kMmThreads = 256;
 constexpr int kMmLoads = 8;
-constexpr int kMmMaxBlocks = 148 * 8;
+constexpr int kMmAcc = 4;
 
 template <typename T> struct MinMax { T lo, hi; };
 
@@ -74,28 +74,40 @@ minmax_kernel(const T* __restrict__ in, size_t n, size_t head, unsigned long lon
   constexpr int kTileVecs = kMmThreads * kMmLoads;
   __shared__ T s_lo[8], s_hi[8];
   __shared__ bool is_last;
-  MinMax<T> m{std::numeric_limits<T>::max(), std::numeric_limits<T>::lowest()};
+  MinMax<T> acc[kMmAcc];  // independent chains: a 64-bit min/max is a compare + two selects deep
+#pragma unroll
+  for (int k = 0; k < kMmAcc; ++k) acc[k] = MinMax<T>{std::numeric_limits<T>::max(), std::numeric_limits<T>::lowest()};
   const uint4* body = reinterpret_cast<const uint4*>(in + head);  // 16-byte aligned by construction
   const size_t n_vecs = (n - head) / N;
   const size_t n_tiles = (n_vecs + kTileVecs - 1) / kTileVecs;
   for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const size_t v0 = tile * kTileVecs + threadIdx.x;
     uint4 raw[kMmLoads];
+    if (v0 + (size_t)(kMmLoads - 1) * kMmThreads < n_vecs) {  // full tile: no per-load predicates
 #pragma unroll
-    for (int k = 0; k < kMmLoads; ++k) {
-      const size_t vi = v0 + (size_t)k * kMmThreads;
-      if (vi < n_vecs) raw[k] = __ldcs(body + vi);
-    }
+      for (int k = 0; k < kMmLoads; ++k) raw[k] = __ldcs(body + v0 + (size_t)k * kMmThreads);
 #pragma unroll
-    for (int k = 0; k < kMmLoads; ++k) {
-      const size_t vi = v0 + (size_t)k * kMmThreads;
-      if (vi < n_vecs) {
+      for (int k = 0; k < kMmLoads; ++k) {
         const T* e = reinterpret_cast<const T*>(&raw[k]);
 #pragma unroll
-        for (int j = 0; j < N; ++j) fold(m, e[j]);
+        for (int j = 0; j < N; ++j) fold(acc[(k * N + j) % kMmAcc], e[j]);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < kMmLoads; ++k) {
+        const size_t vi = v0 + (size_t)k * kMmThreads;
+        if (vi < n_vecs) {
+          raw[k] = __ldcs(body + vi);
+          const T* e = reinterpret_cast<const T*>(&raw[k]);
+#pragma unroll
+          for (int j = 0; j < N; ++j) fold(acc[j % kMmAcc], e[j]);
+        }
       }
     }
   }
+  MinMax<T> m = acc[0];
+#pragma unroll
+  for (int k = 1; k < kMmAcc; ++k) { m.lo = acc[k].lo < m.lo ? acc[k].lo : m.lo; m.hi = acc[k].hi > m.hi ? acc[k].hi : m.hi; }
   if (blockIdx.x == 0) {  // element-granular head (before the first 16-byte boundary) and tail
     const size_t tail0 = head + n_vecs * N;
     for (size_t i = threadIdx.x; i < head; i += kMmThreads) fold(m, in[i]);
@@ -144,8 +156,10 @@ ag_status launch_minmax(const void* d_in, size_t n, void* d_out, cudaStream_t st
   const size_t n_vecs = (n - head) / N;
   size_t want = (n_vecs + (size_t)kMmThreads * kMmLoads - 1) / ((size_t)kMmThreads * kMmLoads);
   if (want < 1) want = 1;
-  const size_t cap = kMmMaxBlocks < kMaxPartials / 2 ? kMmMaxBlocks : kMaxPartials / 2;
-  const int grid = (int)(want < cap ? want : cap);
+  // exactly one wave of resident blocks (min/max is order-independent, so the grid may follow the
+  // device): a fixed 1184-block grid ran 1.6 waves at this kernel's 48 registers and lost 30 %
+  int grid = grid_one_wave(minmax_kernel<T>, kMmThreads, (int64_t)want);
+  if (grid > kMaxPartials / 2) grid = kMaxPartials / 2;
   minmax_kernel<T><<<grid, kMmThreads, 0, st>>>((const T*)d_in, n, head, (unsigned long long*)ws->partials, ws->ticket, (T*)d_out);
   return check_launch("minmax_kernel");
 }

@@ -279,6 +279,34 @@ ag_status ag_cast_numeric_checked_dev(int itype, int otype, const void* d_in, co
                                       int64_t* d_first_bad, ag_stream_t s);
 
 /* ================================================================================= *
+ * cumulative_sum / cumulative_sum_checked — replaces cumulativeSum{NoNulls,WithNulls}[Checked]
+ *   (arrow/compute/internal/kernels/vector_cumulative.go:228-330; options CumulativeOptions
+ *   {Start, SkipNulls} :92-99; chunked input = one logical sequence, :385-410).
+ *   out[i] = start + sum of the valid in[j], j <= i.  Null input slot -> null output slot (value 0).
+ *   Without skip_nulls every slot after the first null is null too and nothing accumulates past
+ *   it.  `checked`: AG_ERR_INVALID "overflow" at the first running sum outside the type's range
+ *   (integers only; floats never fail), lowest failing row in *first_bad.
+ *   Integers: bit-exact.  Floats: single-pass parallel scan with a fixed (data- and n-determined)
+ *   association — bit-exact with the reference's left-to-right loop whenever every partial sum
+ *   is exactly representable, otherwise within the usual summation error bound.
+ *
+ *   Device flavour: the running value and the encountered-null flag live in a 32-byte device
+ *   block (ag_cumsum_state) so that the chunks of a chunked column are a chain of launches on
+ *   one stream; initialise it with ag_cumulative_sum_state_init_dev (start_host: pointer to one
+ *   element of `type`, or NULL for zero).  d_out_valid (bit offset out_valid_offset) is required
+ *   when d_valid is given and otherwise optional (pass it for every chunk when any chunk has
+ *   nulls); state.null_count accumulates the null slots written.
+ * ================================================================================= */
+typedef struct ag_cumsum_state { uint64_t lo; int64_t hi; int64_t encountered_null; int64_t null_count; } ag_cumsum_state;
+ag_status ag_cumulative_sum(int type, const void* in, const uint8_t* valid, int64_t valid_offset, int64_t n,
+                            const void* start, int skip_nulls, int checked,
+                            void* out, uint8_t* out_valid, int64_t* null_count, int64_t* first_bad);
+ag_status ag_cumulative_sum_state_init_dev(void* d_state, int type, const void* start_host, ag_stream_t s);
+ag_status ag_cumulative_sum_dev(int type, const void* d_in, const uint8_t* d_valid, int64_t valid_offset, int64_t n,
+                                int skip_nulls, int checked, void* d_out, uint8_t* d_out_valid, int64_t out_valid_offset,
+                                void* d_state, int64_t* d_first_bad, ag_stream_t s);
+
+/* ================================================================================= *
  * Comparisons -> bitmap — replaces comparison_{equal,not_equal,greater,greater_equal}
  *   _{arr_arr,arr_scalar,scalar_arr}_{avx2,sse4} (_lib/scalar_comparison.cc:210-256)
  *   and compareKernel (scalar_comparisons.go:199-218).  `out_bits` points at the byte

@@ -367,6 +367,76 @@ int ref_min_max(int type, const void* in, int64_t n, void* min_out, void* max_ou
 }
 
 /* ====================================================================================== *
+ * cumulative_sum[_checked]: arrow/compute/internal/kernels/vector_cumulative.go —
+ * cumulativeSumNoNulls :228-241, NoNullsChecked :243-261, WithNulls :263-290, WithNullsChecked
+ * :292-324, checkedAddSigned / Unsigned :147-160, state (current, skipNulls, encounteredNull)
+ * :100-106.  `state` = {current value (8 bytes, the type's own representation in the low bytes),
+ * encountered_null}; it carries from chunk to chunk like the reference's kernel state.  Null and
+ * dead slots are left at 0 (the reference's output comes zeroed from ctx.Allocate).  The loop
+ * stops at the first overflow (checked), reporting its row.
+ * ====================================================================================== */
+typedef struct { uint8_t cur[8]; int64_t encountered_null; } ref_cumsum_state;
+#define CUMSUM_INT(T, UT, SIGNED, TMIN, TMAX)                                                    \
+  do { const T* X = (const T*)in; T* O = (T*)out; T cur; memcpy(&cur, st->cur, sizeof(T));       \
+       for (int64_t i = 0; i < n; ++i) {                                                         \
+         const int valid_i = !valid || bit_is_set(valid, voff + i);                              \
+         if (!valid_i || st->encountered_null) {                                                 \
+           if (out_valid) set_bit_to(out_valid, ooff + i, 0);                                    \
+           ++nulls; O[i] = 0;                                                                    \
+           if (!valid_i && !skip_nulls) st->encountered_null = 1;                                \
+           continue;                                                                             \
+         }                                                                                       \
+         const T x = X[i];                                                                       \
+         if (checked) {                                                                          \
+           int ovf;                                                                              \
+           if (SIGNED) ovf = (x > 0 && cur > (T)((TMAX) - x)) || (x < 0 && cur < (T)((TMIN) - x)); \
+           else ovf = cur > (T)((TMAX) - x);                                                     \
+           if (ovf) { bad = i; goto done; }                                                      \
+         }                                                                                       \
+         cur = (T)((UT)cur + (UT)x);                                                             \
+         O[i] = cur;                                                                             \
+         if (out_valid) set_bit_to(out_valid, ooff + i, 1);                                      \
+       }                                                                                         \
+       memcpy(st->cur, &cur, sizeof(T)); } while (0)
+#define CUMSUM_FLT(T)                                                                            \
+  do { const T* X = (const T*)in; T* O = (T*)out; T cur; memcpy(&cur, st->cur, sizeof(T));       \
+       for (int64_t i = 0; i < n; ++i) {                                                         \
+         const int valid_i = !valid || bit_is_set(valid, voff + i);                              \
+         if (!valid_i || st->encountered_null) {                                                 \
+           if (out_valid) set_bit_to(out_valid, ooff + i, 0);                                    \
+           ++nulls; O[i] = 0;                                                                    \
+           if (!valid_i && !skip_nulls) st->encountered_null = 1;                                \
+           continue;                                                                             \
+         }                                                                                       \
+         cur = cur + X[i];                                                                       \
+         O[i] = cur;                                                                             \
+         if (out_valid) set_bit_to(out_valid, ooff + i, 1);                                      \
+       }                                                                                         \
+       memcpy(st->cur, &cur, sizeof(T)); } while (0)
+int ref_cumulative_sum(int type, const void* in, const uint8_t* valid, int64_t voff, int64_t n, int skip_nulls, int checked,
+                       void* out, uint8_t* out_valid, int64_t ooff, void* state, int64_t* null_count, int64_t* first_bad) {
+  ref_cumsum_state* st = (ref_cumsum_state*)state;
+  int64_t nulls = 0, bad = REF_NO_ERROR_POS;
+  switch (type) {
+    case T_I8: CUMSUM_INT(int8_t, uint8_t, 1, INT8_MIN, INT8_MAX); break;
+    case T_U8: CUMSUM_INT(uint8_t, uint8_t, 0, 0, UINT8_MAX); break;
+    case T_I16: CUMSUM_INT(int16_t, uint16_t, 1, INT16_MIN, INT16_MAX); break;
+    case T_U16: CUMSUM_INT(uint16_t, uint16_t, 0, 0, UINT16_MAX); break;
+    case T_I32: CUMSUM_INT(int32_t, uint32_t, 1, INT32_MIN, INT32_MAX); break;
+    case T_U32: CUMSUM_INT(uint32_t, uint32_t, 0, 0, UINT32_MAX); break;
+    case T_I64: CUMSUM_INT(int64_t, uint64_t, 1, INT64_MIN, INT64_MAX); break;
+    case T_U64: CUMSUM_INT(uint64_t, uint64_t, 0, 0, UINT64_MAX); break;
+    case T_F32: CUMSUM_FLT(float); break;
+    case T_F64: CUMSUM_FLT(double); break;
+    default: return REF_ERR_TYPE;
+  }
+done:
+  if (null_count) *null_count = nulls;
+  if (first_bad) *first_bad = bad;
+  return bad == REF_NO_ERROR_POS ? REF_OK : REF_ERR_INVALID;
+}
+
+/* ====================================================================================== *
  * Numeric casts: the loop K/cast_numeric.go:101-131 (= K/_lib/cast_numeric.cc:22-101) framed by
  * the safe-cast checks of K/numeric_cast.go:37-71 —
  *   int -> int    intsCanFit (K/helpers.go:545-578) bounds from getSafeMinMax* (:496-543),

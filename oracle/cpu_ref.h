@@ -47,6 +47,10 @@ int ref_arith_checked(int type, int op, int shape,
 
 int ref_arith_unary_checked(int type, int op, const void* in, void* out, int64_t n, int64_t* first_bad);
 
+/* cumulative_sum[_checked]; state = {8 value bytes, int64 encountered_null} carried between chunks */
+int ref_cumulative_sum(int type, const void* in, const uint8_t* valid, int64_t voff, int64_t n, int skip_nulls, int checked,
+                       void* out, uint8_t* out_valid, int64_t ooff, void* state, int64_t* null_count, int64_t* first_bad);
+
 /* integer min/max */
 int ref_min_max(int type, const void* in, int64_t n, void* min_out, void* max_out);
 

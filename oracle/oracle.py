@@ -50,6 +50,7 @@ def cpu():
         lib.ref_arith_unary_diff.argtypes = [C.c_int, C.c_int, C.c_int, c_p, c_p, i64]
         lib.ref_arith_checked.argtypes = [C.c_int, C.c_int, C.c_int, c_p, c_p, i64, c_p, c_p, i64, c_p, i64, C.POINTER(i64)]
         lib.ref_arith_unary_checked.argtypes = [C.c_int, C.c_int, c_p, c_p, i64, C.POINTER(i64)]
+        lib.ref_cumulative_sum.argtypes = [C.c_int, c_p, c_p, i64, i64, C.c_int, C.c_int, c_p, c_p, i64, c_p, C.POINTER(i64), C.POINTER(i64)]
         lib.ref_min_max.argtypes = [C.c_int, c_p, i64, c_p, c_p]
         lib.ref_cast_numeric.argtypes = [C.c_int, C.c_int, c_p, c_p, i64, c_p, i64, C.c_int, C.c_int, C.POINTER(i64)]
         lib.ref_compare.argtypes = [C.c_int, C.c_int, C.c_int, c_p, c_p, c_p, i64, C.c_int]

@@ -70,4 +70,13 @@ timed("cast_i32_to_i8_unsafe", lambda: N.call("ag_cast_numeric_dev", N.INT32, N.
 timed("cast_f64_to_f32", lambda: N.call("ag_cast_numeric_dev", N.FLOAT64, N.FLOAT32, b.ptr, o.ptr, rows, None))
 timed("min_max_i64", lambda: N.call("ag_min_max_dev", N.INT64, b.ptr, rows, scal.ptr, None))
 timed("min_max_i32", lambda: N.call("ag_min_max_dev", N.INT32, idx.ptr, rows, scal.ptr, None))
+state = DeviceBuffer(64)
+ovalid = DeviceBuffer(rows // 8 + 64)
+def cumsum(t, src, v):
+    N.call("ag_cumulative_sum_state_init_dev", state.ptr, t, None, None)
+    N.call("ag_cumulative_sum_dev", t, src, v, 3, rows, 1, 0, o.ptr, ovalid.ptr if v else None, 0, state.ptr, bad.ptr, None)
+timed("cumsum_i64", lambda: cumsum(N.INT64, a.ptr, None))
+timed("cumsum_i64_nulls_skip", lambda: cumsum(N.INT64, a.ptr, valid.ptr))
+timed("cumsum_f64", lambda: cumsum(N.FLOAT64, b.ptr, None))
+timed("cumsum_i32", lambda: cumsum(N.INT32, idx.ptr, None))
 print("selected rows:", cnt)
