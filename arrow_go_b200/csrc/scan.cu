@@ -119,6 +119,39 @@ struct Pol<T, false> {  // integers
 };
 
 template <typename T>
+struct PolWrap {  // unchecked integers: the sum modulo 2^64 is all the result needs
+  using A = unsigned long long;
+  static constexpr int K = 2;
+  static constexpr bool kSigned = T(-1) < T(0);
+  static __device__ __forceinline__ A zero() { return 0ull; }
+  static __device__ __forceinline__ A add(A a, A b) { return a + b; }
+  static __device__ __forceinline__ A add_elem(A a, T x) { return a + (kSigned ? (A)(long long)x : (A)x); }
+  static __device__ __forceinline__ T value(A a) { return (T)a; }
+  static __device__ __forceinline__ bool out_of_range(A) { return false; }
+  static __device__ __forceinline__ A shfl_up(A a, int d) { return __shfl_up_sync(0xffffffffu, a, d); }
+  static __device__ __forceinline__ A shfl(A a, int src) { return __shfl_sync(0xffffffffu, a, src); }
+  static __device__ __forceinline__ void to_words(A a, unsigned (&w)[3]) { w[0] = (unsigned)a; w[1] = (unsigned)(a >> 32); }
+  static __device__ __forceinline__ A from_words(const unsigned (&w)[3]) { return (A)w[0] | ((A)w[1] << 32); }
+  static __device__ __forceinline__ A from_state(const CumsumState& s) { return s.lo; }
+  static __device__ __forceinline__ void to_state(A a, CumsumState* s) {
+    // keep the exact-sum convention of the state block: hi = sign extension of the wrapped low word is
+    // NOT the exact carry count, so an unchecked call leaves hi consistent with "value = lo" only
+    s->lo = a;
+    s->hi = (kSigned && (long long)a < 0) ? -1 : 0;
+  }
+};
+
+template <typename T, bool kChecked> struct PolSel { using type = Pol<T>; };
+template <> struct PolSel<uint8_t, false> { using type = PolWrap<uint8_t>; };
+template <> struct PolSel<int8_t, false> { using type = PolWrap<int8_t>; };
+template <> struct PolSel<uint16_t, false> { using type = PolWrap<uint16_t>; };
+template <> struct PolSel<int16_t, false> { using type = PolWrap<int16_t>; };
+template <> struct PolSel<uint32_t, false> { using type = PolWrap<uint32_t>; };
+template <> struct PolSel<int32_t, false> { using type = PolWrap<int32_t>; };
+template <> struct PolSel<unsigned long long, false> { using type = PolWrap<unsigned long long>; };
+template <> struct PolSel<long long, false> { using type = PolWrap<long long>; };
+
+template <typename T>
 struct Pol<T, true> {  // float / double: accumulate in the value type
   using A = T;
   static constexpr int K = sizeof(T) == 8 ? 2 : 1;
@@ -184,10 +217,10 @@ __device__ __forceinline__ typename P::A poll_value(const unsigned long long* wo
   return P::from_words(w);
 }
 
-template <typename T, bool kVec, bool kHasValid>
-__global__ void __launch_bounds__(kScThreads, 4)
+template <typename T, bool kVec, bool kHasValid, bool kChecked>
+__global__ void __launch_bounds__(kScThreads, 2)
 cumsum_kernel(const CumsumParams p) {
-  using P = Pol<T>;
+  using P = typename PolSel<T, kChecked>::type;
   using A = typename P::A;
   constexpr int N = 16 / sizeof(T);            // elements per 16-byte vector
   constexpr int kTileRows = kScTileBytes / sizeof(T);
@@ -215,6 +248,27 @@ cumsum_kernel(const CumsumParams p) {
   long long my_bad = AG_NO_ERROR_POS;
   const int64_t vlo = p.voff >> 3, vhi = (p.voff + p.n + 7) >> 3;   // byte range of the validity bitmap
 
+  // Coalesced tile load: row k of a warp's 4 KB segment is 32 consecutive 16-byte vectors.  The
+  // loads of tile t+G are issued while tile t is still waiting on its look-back and being written
+  // out, so HBM stays busy across the only serial part of the algorithm.
+  uint4 q[kScRows];
+  auto load_tile = [&](int64_t tile) {
+    const int64_t r0 = tile * kTileRows + (int64_t)warp * kSegRows;
+#pragma unroll
+    for (int k = 0; k < kScRows; ++k) {
+      const int64_t e0 = r0 + ((int64_t)k * 32 + lane) * N;
+      if (kVec && e0 + N <= p.n) {
+        q[k] = __ldcs(reinterpret_cast<const uint4*>(in + e0));
+      } else {
+        __align__(16) T tmp[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) tmp[j] = (e0 + j < p.n) ? in[e0 + j] : T(0);
+        q[k] = *reinterpret_cast<const uint4*>(tmp);
+      }
+    }
+  };
+  if ((int64_t)blockIdx.x < p.n_tiles) load_tile(blockIdx.x);
+
   for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
     const int64_t row0 = tile * kTileRows + (int64_t)warp * kSegRows;  // first row of this warp's segment
     // ---- load (coalesced): row k of the warp's 4 KB segment is 32 consecutive 16-byte vectors -----
@@ -224,20 +278,10 @@ cumsum_kernel(const CumsumParams p) {
     // touch every bank once per quarter warp.
     uint4* seg = s_tile + warp * (kScRows * 32);
 #pragma unroll
-    for (int k = 0; k < kScRows; ++k) {
+    for (int k = 0; k < kScRows; ++k) {  // q[] was loaded one tile ahead (see the prefetch below)
       const int vi = k * 32 + lane;
-      const int64_t e0 = row0 + (int64_t)vi * N;
-      uint4 q;
-      if (kVec && e0 + N <= p.n) {
-        q = __ldcs(reinterpret_cast<const uint4*>(in + e0));
-      } else {
-        __align__(16) T tmp[N];
-#pragma unroll
-        for (int j = 0; j < N; ++j) tmp[j] = (e0 + j < p.n) ? in[e0 + j] : T(0);
-        q = *reinterpret_cast<const uint4*>(tmp);
-      }
       const int owner = vi >> 3, c = vi & 7;
-      seg[owner * 8 + (c ^ (owner & 7))] = q;
+      seg[owner * 8 + (c ^ (owner & 7))] = q[k];
     }
     __syncwarp();
     uint4 raw[kScRows];  // this lane's E = 8*N consecutive elements, still packed
@@ -286,50 +330,85 @@ cumsum_kernel(const CumsumParams p) {
       tile_total = P::add(tile_total, t);
     }
     // ---- look-back (warp 0): publish the aggregate, gather the exclusive prefix of the tile -----
+    if (warp == 0 && lane == 0) {
+      unsigned w[3] = {0u, 0u, 0u};
+      P::to_words(tile_total, w);
+#pragma unroll
+      for (int k = 0; k < P::K; ++k) st_word(p.agg + tile * P::K + k, w[k]);
+    }
+    if (tile + gridDim.x < p.n_tiles) load_tile(tile + gridDim.x);  // prefetch: in flight during the wait below
     if (warp == 0) {
       const int64_t g = tile / kScGroup;
-      const int q = (int)(tile - g * kScGroup);
-      if (lane == 0) {
-        unsigned w[3] = {0u, 0u, 0u};
-        P::to_words(tile_total, w);
-#pragma unroll
-        for (int k = 0; k < P::K; ++k) st_word(p.agg + tile * P::K + k, w[k]);
-      }
-      // aggregates of the earlier tiles of this group, four per lane, folded in a fixed order
-      A part = P::zero();
+      const int qpos = (int)(tile - g * kScGroup);
+      // Everything this tile needs from earlier tiles, fetched as ONE batch of independent polls
+      // (re-issued only for words whose flag is not up yet): slots 0..3 = aggregates of the earlier
+      // tiles of this group (four per lane), slot 4 = aggregates of the earlier groups of this
+      // super-group (one per lane), slot 5 = the previous super-group's inclusive prefix.
+      const int64_t sg = g / kScSuper;
+      const int gq = (int)(g - sg * kScSuper);
+      constexpr int kSlots = kScGroup / 32 + 2;
+      const unsigned long long* src[kSlots];
+      unsigned need = 0;
 #pragma unroll
       for (int r = 0; r < kScGroup / 32; ++r) {
         const int pos = r * 32 + lane;
-        A a = P::zero();
-        if (pos < q) a = poll_value<P>(p.agg + (g * kScGroup + pos) * P::K);
+        src[r] = p.agg + (g * kScGroup + pos) * P::K;
+        if (pos < qpos) need |= ((1u << P::K) - 1u) << (r * P::K);
+      }
+      src[kSlots - 2] = p.gagg + (sg * kScSuper + lane) * P::K;
+      if (lane < gq) need |= ((1u << P::K) - 1u) << ((kSlots - 2) * P::K);
+      src[kSlots - 1] = p.sincl + (sg > 0 ? sg - 1 : 0) * P::K;
+      if (sg > 0) need |= ((1u << P::K) - 1u) << ((kSlots - 1) * P::K);
+      unsigned val[kSlots][3];
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {  // in-order (scan-style) fold keeps lower tiles on the left
-          const A up = P::shfl_up(a, d);
-          if (lane >= d) a = P::add(up, a);
+      for (int r = 0; r < kSlots; ++r) { val[r][0] = 0u; val[r][1] = 0u; val[r][2] = 0u; }
+      unsigned got = 0;
+      constexpr unsigned kAggMask = (1u << ((kScGroup / 32) * P::K)) - 1u;
+      bool folded = false;
+      A part = P::zero();
+      while (true) {  // warp-uniform loop: the fold below uses shuffles
+        unsigned long long sw[kSlots][3];
+#pragma unroll
+        for (int r = 0; r < kSlots; ++r)
+#pragma unroll
+          for (int k = 0; k < P::K; ++k)
+            sw[r][k] = (((need & ~got) >> (r * P::K + k)) & 1u) ? ld_word(src[r] + k) : 0ull;
+#pragma unroll
+        for (int r = 0; r < kSlots; ++r)
+#pragma unroll
+          for (int k = 0; k < P::K; ++k)
+            if (sw[r][k] & kScFlag) { val[r][k] = (unsigned)sw[r][k]; got |= 1u << (r * P::K + k); }
+        if (!folded && __all_sync(0xffffffffu, ((got ^ need) & kAggMask) == 0u)) {
+          // tile aggregates are in: fold them in a fixed order (lower tiles on the left) and, for the
+          // last tile of a group, publish the group aggregate WITHOUT waiting for anything older
+          folded = true;
+#pragma unroll
+          for (int r = 0; r < kScGroup / 32; ++r) {
+            A a = (r * 32 + lane < qpos) ? P::from_words(val[r]) : P::zero();
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+              const A up = P::shfl_up(a, d);
+              if (lane >= d) a = P::add(up, a);
+            }
+            part = P::add(part, P::shfl(a, 31));
+          }
+          if (qpos == kScGroup - 1 && lane == 0) {
+            unsigned wg[3] = {0u, 0u, 0u};
+            P::to_words(P::add(part, tile_total), wg);
+#pragma unroll
+            for (int k = 0; k < P::K; ++k) st_word(p.gagg + g * P::K + k, wg[k]);
+          }
         }
-        part = P::add(part, P::shfl(a, 31));
+        if (__all_sync(0xffffffffu, got == need)) break;
       }
-      // the group's own aggregate needs no other group: its last tile publishes it at once
-      if (q == kScGroup - 1 && lane == 0) {
-        unsigned wg[3] = {0u, 0u, 0u};
-        P::to_words(P::add(part, tile_total), wg);
-#pragma unroll
-        for (int k = 0; k < P::K; ++k) st_word(p.gagg + g * P::K + k, wg[k]);
-      }
-      // aggregates of the earlier groups of this super-group (one per lane), then the previous
-      // super-group's inclusive prefix: the only serial chain, one step per 4096 tiles
-      const int64_t sg = g / kScSuper;
-      const int gq = (int)(g - sg * kScSuper);
-      A gpart = P::zero();
-      if (lane < gq) gpart = poll_value<P>(p.gagg + (sg * kScSuper + lane) * P::K);
+      A gpart = (lane < gq) ? P::from_words(val[kSlots - 2]) : P::zero();
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         const A up = P::shfl_up(gpart, d);
         if (lane >= d) gpart = P::add(up, gpart);
       }
       gpart = P::shfl(gpart, 31);
-      A base = start;
-      if (sg > 0) base = poll_value<P>(p.sincl + (sg - 1) * P::K);   // every lane polls the same words
+      const A base = (sg > 0) ? P::from_words(val[kSlots - 1]) : start;
       const A excl = P::add(P::add(base, gpart), part);
       if (lane == 0) {
         unsigned w[3] = {0u, 0u, 0u};
@@ -337,7 +416,7 @@ cumsum_kernel(const CumsumParams p) {
         s_excl_lo = (unsigned long long)w[0] | ((unsigned long long)w[1] << 32);
         s_excl_hi = (int)w[2];
         const A incl = P::add(excl, tile_total);
-        if (q == kScGroup - 1 && gq == kScSuper - 1) {
+        if (qpos == kScGroup - 1 && gq == kScSuper - 1) {
           unsigned wi[3] = {0u, 0u, 0u};
           P::to_words(incl, wi);
 #pragma unroll
@@ -367,7 +446,7 @@ cumsum_kernel(const CumsumParams p) {
         if ((vbits[i >> 5] >> (i & 31)) & 1u) {
           run = P::add_elem(run, o[i]);
           o[i] = P::value(run);
-          if (p.checked && P::out_of_range(run) && t0 + i < my_bad) my_bad = t0 + i;
+          if (kChecked && P::out_of_range(run) && t0 + i < my_bad) my_bad = t0 + i;
         } else {
           o[i] = T(0);
         }
@@ -394,7 +473,7 @@ cumsum_kernel(const CumsumParams p) {
     }
     __syncthreads();  // s_warp_* / s_excl_* are rewritten by the next tile
   }
-  if (p.checked) {
+  if (kChecked) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
       const long long o = __shfl_xor_sync(0xffffffffu, my_bad, d);
@@ -460,18 +539,18 @@ cumsum_validity_kernel(const uint8_t* __restrict__ valid, int64_t voff, int64_t 
 
 template <typename T>
 ag_status launch_cumsum(CumsumParams& p, cudaStream_t st) {
-  using P = Pol<T>;
+  constexpr int kStatusK = 3;  // sized for the widest accumulator (exact 96-bit)
   constexpr int kTileRows = kScTileBytes / sizeof(T);
   Workspace* ws;
   AG_TRY(get_workspace(st, &ws));
   p.n_tiles = (p.n + kTileRows - 1) / kTileRows;
   const int64_t n_groups = (p.n_tiles + kScGroup - 1) / kScGroup;
   const int64_t n_super = (n_groups + kScSuper - 1) / kScSuper;
-  const size_t words = (size_t)(p.n_tiles + n_groups + n_super) * P::K;
+  const size_t words = (size_t)(p.n_tiles + n_groups + n_super) * kStatusK;
   AG_TRY(ensure_tile_status(ws, words, st));
   p.agg = ws->tile_status;
-  p.gagg = p.agg + (size_t)p.n_tiles * P::K;
-  p.sincl = p.gagg + (size_t)n_groups * P::K;
+  p.gagg = p.agg + (size_t)p.n_tiles * kStatusK;
+  p.sincl = p.gagg + (size_t)n_groups * kStatusK;
   AG_CUDA_TRY(cudaMemsetAsync(ws->tile_status, 0, words * sizeof(unsigned long long), st));
   if (p.valid) {
     long long* fn = reinterpret_cast<long long*>(ws->scalars) + 8;  // slot 8 of the per-stream scalars
@@ -493,8 +572,14 @@ ag_status launch_cumsum(CumsumParams& p, cudaStream_t st) {
   const bool vec = (reinterpret_cast<uintptr_t>(p.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
   void* args[] = {(void*)&p};
   const void* fn;
-  if (vec) fn = p.valid ? (const void*)cumsum_kernel<T, true, true> : (const void*)cumsum_kernel<T, true, false>;
-  else fn = p.valid ? (const void*)cumsum_kernel<T, false, true> : (const void*)cumsum_kernel<T, false, false>;
+  const bool chk = p.checked && !IsFp<T>::v;  // floats: the checked adder is the plain one
+  if (chk) {
+    if (vec) fn = p.valid ? (const void*)cumsum_kernel<T, true, true, !IsFp<T>::v> : (const void*)cumsum_kernel<T, true, false, !IsFp<T>::v>;
+    else fn = p.valid ? (const void*)cumsum_kernel<T, false, true, !IsFp<T>::v> : (const void*)cumsum_kernel<T, false, false, !IsFp<T>::v>;
+  } else {
+    if (vec) fn = p.valid ? (const void*)cumsum_kernel<T, true, true, false> : (const void*)cumsum_kernel<T, true, false, false>;
+    else fn = p.valid ? (const void*)cumsum_kernel<T, false, true, false> : (const void*)cumsum_kernel<T, false, false, false>;
+  }
   int64_t cap = (int64_t)sm_count() * blocks_per_sm(fn, kScThreads);
   const int grid = (int)(p.n_tiles < cap ? p.n_tiles : cap);
   AG_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kScThreads), args, 0, st));
