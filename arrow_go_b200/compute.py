@@ -78,6 +78,7 @@ def lib():
         h.agx_dispatch_best.argtypes = [C.c_char_p, C.POINTER(i), i]
         h.agx_common_numeric.argtypes = [C.POINTER(i), i]
         h.agx_cast.argtypes = [p, i, i, i, pp]
+        h.agx_cumulative_sum.argtypes = [p, i, i, p, pp]
         h.agx_export_device.argtypes = [p, C.POINTER(N.ArrowDeviceArray), C.POINTER(N.ArrowSchema)]
         h.agx_import_device.argtypes = [C.POINTER(N.ArrowDeviceArray), C.POINTER(N.ArrowSchema), pp]
         h.agx_scalar_value.argtypes = [p, C.POINTER(i), p]
@@ -250,6 +251,14 @@ def Subtract(l, r, no_check_overflow=False):
 
 def Multiply(l, r, no_check_overflow=False):
     return _arith(2, l, r, no_check_overflow)
+
+
+def CumulativeSum(values, start=None, skip_nulls=False, checked=False):
+    """compute.CumulativeSum / CumulativeSumChecked(ctx, CumulativeOptions{Start, SkipNulls}, values);
+    `start` is a Scalar datum (any numeric type: it is safe-cast to the input type) or None."""
+    out = C.c_void_p()
+    _check(lib().agx_cumulative_sum(values._h, int(checked), int(skip_nulls), start._h if start is not None else None, C.byref(out)))
+    return Datum(out)
 
 
 def export_device(arr):

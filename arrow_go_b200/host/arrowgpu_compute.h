@@ -205,6 +205,9 @@ struct ScalarKernel : Kernel {  // kernel.go:632-640
 };
 struct VectorKernel : Kernel {  // kernel.go:693-704
   bool can_execute_chunkwise = true;
+  // ExecChunked (kernel.go:687-691): a non-chunkwise kernel that consumes a whole chunked argument as
+  // ONE logical sequence and produces one output array (cumulative_sum, vector_cumulative.go:385-410)
+  std::function<Status(KernelCtx*, const ChunkedArray&, ExecResult*)> exec_chunked;
 };
 
 }  // namespace exec
@@ -237,6 +240,12 @@ struct CastOptions : FunctionOptions {  // kernels/cast.go:27-35 (the numeric kn
 };
 inline CastOptions SafeCastOptions(Type to) { CastOptions o; o.ToType = to; return o; }  // cast.go: SafeCastOptions
 inline CastOptions UnsafeCastOptions(Type to) { CastOptions o; o.ToType = to; o.AllowIntOverflow = o.AllowFloatTruncate = true; return o; }
+
+struct CumulativeOptions : FunctionOptions {  // kernels/vector_cumulative.go:92-99
+  std::shared_ptr<Scalar> Start;  // nullptr = zero of the input type; a null scalar is invalid
+  bool SkipNulls = false;
+  const char* TypeName() const override { return "CumulativeOptions"; }
+};
 
 enum class FuncKind { SCALAR, VECTOR, META };  // functions.go FuncScalar / FuncVector / FuncMeta
 
@@ -323,6 +332,9 @@ Status CallFunction(const ExecCtx& ctx, const std::string& name, const FunctionO
 Status Add(const ExecCtx& ctx, const ArithmeticOptions& opts, const Datum& l, const Datum& r, Datum* out);
 Status Subtract(const ExecCtx& ctx, const ArithmeticOptions& opts, const Datum& l, const Datum& r, Datum* out);
 Status Multiply(const ExecCtx& ctx, const ArithmeticOptions& opts, const Datum& l, const Datum& r, Datum* out);
+// vector_cumulative.go:96-102
+Status CumulativeSum(const ExecCtx& ctx, const CumulativeOptions& opts, const Datum& values, Datum* out);
+Status CumulativeSumChecked(const ExecCtx& ctx, const CumulativeOptions& opts, const Datum& values, Datum* out);
 // selection.go:657 / :304
 Status Filter(const ExecCtx& ctx, const Datum& values, const Datum& filter, const FilterOptions& opts, Datum* out);
 Status Take(const ExecCtx& ctx, const TakeOptions& opts, const Datum& values, const Datum& indices, Datum* out);

@@ -95,6 +95,15 @@ int agx_arith(int which, int no_check_overflow, agx_datum* l, agx_datum* r, agx_
   *out = new agx_datum{res};
   return AG_OK;
 }
+// compute.CumulativeSum / CumulativeSumChecked with CumulativeOptions{Start, SkipNulls}; start may be NULL
+int agx_cumulative_sum(agx_datum* d, int checked, int skip_nulls, agx_datum* start, agx_datum** out) {
+  CumulativeOptions o; o.SkipNulls = skip_nulls != 0;
+  if (start) { if (start->d.kind != DatumKind::SCALAR) return fail(Status::Invalid("start must be a scalar")); o.Start = start->d.scalar; }
+  ExecCtx ctx; Datum res;
+  AGX_TRY(checked ? CumulativeSumChecked(ctx, o, d->d, &res) : CumulativeSum(ctx, o, d->d, &res));
+  *out = new agx_datum{res};
+  return AG_OK;
+}
 // compute.CastDatum with CastOptions{ToType, AllowIntOverflow, AllowFloatTruncate} (cast.go:919-921)
 int agx_cast(agx_datum* d, int to_type, int allow_int_overflow, int allow_float_truncate, agx_datum** out) {
   CastOptions o; o.ToType = (Type)to_type; o.AllowIntOverflow = allow_int_overflow != 0; o.AllowFloatTruncate = allow_float_truncate != 0;

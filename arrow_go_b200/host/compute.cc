@@ -685,6 +685,11 @@ Status VectorFunction::Execute(const ExecCtx& ectx, const FunctionOptions* opts,
       RETURN_NOT_OK(kernel->exec(&kctx, span, &o));
       results.push_back(o.MakeData());
     }
+  } else if (have_chunked && kernel->exec_chunked && args.size() == 1) {
+    ArraySpan o;
+    o.type = out_type;
+    RETURN_NOT_OK(kernel->exec_chunked(&kctx, *args[0].chunked, &o));
+    results.push_back(o.MakeData());
   } else {
     if (have_chunked) return Status::NotImplemented("non-chunkwise vector kernel on chunked input (resolved by the meta function)");
     ExecSpan span;
@@ -1089,6 +1094,104 @@ Status PrimitiveFilterExec(KernelCtx* ctx, const ExecSpan& batch, ExecResult* ou
   return Status::OK();
 }
 
+// ---- cumulative_sum[_checked] (kernels/vector_cumulative.go:332-410) -------------------------
+// cumulativeStartValue :81-112: nil -> zero, null scalar -> error, other types -> safe cast.
+Status CumulativeStart(const CumulativeOptions* opts, Type t, bool* has_start, uint8_t (&raw)[8]) {
+  *has_start = false;
+  memset(raw, 0, 8);
+  if (!opts || !opts->Start) return Status::OK();
+  if (!opts->Start->valid) return Status::Invalid("cumulative sum start value must be valid");
+  std::shared_ptr<Scalar> sc = opts->Start;
+  if (sc->type != t) {
+    Datum casted;
+    ExecCtx ectx;
+    Status st = CastDatum(ectx, Datum(sc), SafeCastOptions(t), &casted);
+    if (!st.ok()) return Status::Invalid(std::string("cannot cast cumulative sum start value to ") + TypeName(t) + ": " + st.msg);
+    sc = casted.scalar;
+  }
+  memcpy(raw, sc->value, 8);
+  *has_start = true;
+  return Status::OK();
+}
+
+struct CumsumRun {  // device state + error word shared by the chunks of one call
+  std::shared_ptr<Buffer> state, bad;
+  Status Init(Type t, const CumulativeOptions* opts) {
+    bool has_start; uint8_t raw[8];
+    RETURN_NOT_OK(CumulativeStart(opts, t, &has_start, raw));
+    RETURN_NOT_OK(Buffer::Allocate(sizeof(ag_cumsum_state), &state));
+    RETURN_NOT_OK(Buffer::Allocate(8, &bad));
+    NATIVE(ag_cumulative_sum_state_init_dev(state->data(), (int)t, has_start ? raw : nullptr, nullptr));
+    NATIVE(ag_error_word_reset_dev((int64_t*)bad->data(), nullptr));
+    return Status::OK();
+  }
+};
+
+// cumulativeSumSpans: one output array for all input spans; validity only when some span may have nulls
+Status CumulativeSpans(bool checked, const CumulativeOptions* opts, Type t, const std::vector<ArraySpan>& inputs, ExecResult* out) {
+  if (!IsInteger(t) && !IsFloating(t)) return Status::TypeError(std::string("cumulative sum input type must be numeric, got ") + TypeName(t));
+  int64_t total = 0;
+  bool needs_validity = false;
+  for (auto& in : inputs) { total += in.len; needs_validity = needs_validity || (in.buffers[0].buf != nullptr && in.nulls != 0); }
+  out->type = t; out->len = total; out->offset = 0; out->nulls = 0;
+  if (total == 0) return Status::OK();
+  CumsumRun run;
+  RETURN_NOT_OK(run.Init(t, opts));
+  std::shared_ptr<Buffer> data, validity;
+  const int w = BitWidth(t) / 8;
+  RETURN_NOT_OK(Buffer::Allocate(total * w, &data));
+  if (needs_validity) RETURN_NOT_OK(Buffer::Allocate(BytesForBits(total), &validity));
+  int64_t pos = 0;
+  for (auto& in : inputs) {
+    if (in.len == 0) continue;
+    NATIVE(ag_cumulative_sum_dev((int)t, ValuesPtr(in), in.buffers[0].buf, in.offset, in.len, opts && opts->SkipNulls ? 1 : 0, checked ? 1 : 0,
+                                 data->data() + pos * w, validity ? validity->data() : nullptr, pos, run.state->data(), (int64_t*)run.bad->data(), nullptr));
+    pos += in.len;
+  }
+  if (checked) {
+    int64_t bad = 0;
+    RETURN_NOT_OK(run.bad->ToHost(&bad, 8));
+    if (bad != AG_NO_ERROR_POS) return Status::Invalid("overflow");  // errOverflow, base_arithmetic.go:137
+  }
+  out->buffers[1].buf = data->data(); out->buffers[1].len = data->size(); out->buffers[1].owner = data;
+  if (validity) {
+    ag_cumsum_state hs;
+    RETURN_NOT_OK(run.state->ToHost(&hs, sizeof(hs)));
+    out->buffers[0].buf = validity->data(); out->buffers[0].len = validity->size(); out->buffers[0].owner = validity;
+    out->nulls = hs.null_count;
+  }
+  return Status::OK();
+}
+
+exec::ArrayKernelExec CumulativeExec(bool checked) {  // cumulativeSumExec :370-383
+  return [checked](KernelCtx* ctx, const ExecSpan& batch, ExecResult* out) -> Status {
+    const ArraySpan& in = batch.values[0].array;
+    return CumulativeSpans(checked, static_cast<const CumulativeOptions*>(ctx->state), in.type, {in}, out);
+  };
+}
+
+std::function<Status(KernelCtx*, const ChunkedArray&, ExecResult*)> CumulativeExecChunked(bool checked) {  // :385-410
+  return [checked](KernelCtx* ctx, const ChunkedArray& c, ExecResult* out) -> Status {
+    std::vector<ArraySpan> spans(c.chunks.size());
+    for (size_t i = 0; i < c.chunks.size(); ++i) spans[i].SetMembers(*c.chunks[i]);
+    return CumulativeSpans(checked, static_cast<const CumulativeOptions*>(ctx->state), c.type, spans, out);
+  };
+}
+
+std::shared_ptr<VectorFunction> MakeCumulative(const std::string& name, bool checked) {
+  auto fn = std::make_shared<VectorFunction>(name, 1);
+  exec::VectorKernel k;
+  k.any_input_type = true;  // the exec rejects non-numeric inputs with ErrType like the reference's start-value check
+  k.out_type = [](const std::vector<Type>& t) { return t[0]; };
+  k.exec = CumulativeExec(checked);
+  k.exec_chunked = CumulativeExecChunked(checked);
+  k.null_handling = exec::NullHandling::COMPUTED_NO_PREALLOC;
+  k.mem_alloc = exec::MemAlloc::NO_PREALLOC;
+  k.can_execute_chunkwise = false;  // vector_cumulative.go:420-421
+  fn->AddKernel(std::move(k));
+  return fn;
+}
+
 // PrimitiveTake (vector_selection.go:1162-1192)
 Status PrimitiveTakeExec(KernelCtx* ctx, const ExecSpan& batch, ExecResult* out) {
   ArraySpan values = batch.values[0].array, indices = batch.values[1].array;
@@ -1314,6 +1417,9 @@ FunctionRegistry* GetFunctionRegistry() {
       *out = Datum(res);
       return Status::OK();
     }), false);
+    // vector_cumulative.go:75-93
+    reg->AddFunction(MakeCumulative("cumulative_sum", false), false);
+    reg->AddFunction(MakeCumulative("cumulative_sum_checked", true), false);
     // selection.go:593-650: array_filter / array_take vector functions + filter / take meta functions
     {
       auto fn = std::make_shared<VectorFunction>("array_filter", 2);
@@ -1409,6 +1515,20 @@ Status ConcatenateChunks(const ChunkedArray& c, std::shared_ptr<ArrayData>* out)
 }  // namespace
 
 // arithmetic.go:1090-1142
+static Status CumulativeImpl(const ExecCtx& ctx, const char* fn, const CumulativeOptions& opts, const Datum& values, Datum* out) {
+  if (values.kind == DatumKind::SCALAR) {  // the vector executor promotes a scalar argument to a length-1 array
+    if (!values.scalar) return Status::Invalid("cumulative sum: empty datum");
+    std::shared_ptr<ArrayData> one;
+    const uint8_t zero = 0;
+    RETURN_NOT_OK(ArrayData::FromHost(values.scalar->type, 1, 0, values.scalar->valid ? nullptr : &zero, values.scalar->value,
+                                      values.scalar->valid ? 0 : 1, &one));
+    return CallFunction(ctx, fn, &opts, {Datum(one)}, out);
+  }
+  return CallFunction(ctx, fn, &opts, {values}, out);
+}
+Status CumulativeSum(const ExecCtx& ctx, const CumulativeOptions& opts, const Datum& values, Datum* out) { return CumulativeImpl(ctx, "cumulative_sum", opts, values, out); }
+Status CumulativeSumChecked(const ExecCtx& ctx, const CumulativeOptions& opts, const Datum& values, Datum* out) { return CumulativeImpl(ctx, "cumulative_sum_checked", opts, values, out); }
+
 Status CastDatum(const ExecCtx& ctx, const Datum& val, const CastOptions& opts, Datum* out) {  // cast.go:919-921
   return CallFunction(ctx, "cast", &opts, {val}, out);
 }

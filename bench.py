@@ -376,7 +376,23 @@ def main():
         ms = timed(lambda: N.call("ag_take_primitive_dev", 64, vi.ptr, None, 0, rows, 32, 1, idx.ptr, None, 0, rows, 1, dout.ptr, None, bad.ptr, None), W, K)
         others["take_i64_i32idx_random"] = {"rows_per_s": world * rows / ms * 1e3, "gbs_per_gpu": 20.0 * rows / ms / 1e6, "frac": 20.0 * rows / ms / 1e6 / peak, "ms": ms,
                                             "note": "algorithmic 20 B/row; random 8-byte gathers move 32-byte sectors"}
-        idx.free(); bad.free(); scal.free()
+        # rows SURVEY §8(f) marks "next", same device-resident columns: promotion cast, min/max, cumulative sum
+        ms = timed(lambda: N.call("ag_cast_numeric_dev", N.INT32, N.INT64, idx.ptr, dout.ptr, rows, None), W, K)
+        others["cast_i32_to_i64"] = {"rows_per_s": world * rows / ms * 1e3, "gbs_per_gpu": 12.0 * rows / ms / 1e6, "frac": 12.0 * rows / ms / 1e6 / peak, "ms": ms}
+        N.call("ag_error_word_reset_dev", bad.ptr, None)
+        ms = timed(lambda: N.call("ag_cast_numeric_checked_dev", N.INT64, N.FLOAT64, vi.ptr, None, 0, dout.ptr, rows, 0, 0, bad.ptr, None), W, K)
+        others["cast_i64_to_f64_safe"] = {"rows_per_s": world * rows / ms * 1e3, "gbs_per_gpu": 16.0 * rows / ms / 1e6, "frac": 16.0 * rows / ms / 1e6 / peak, "ms": ms}
+        ms = timed(lambda: N.call("ag_min_max_dev", N.INT64, vi.ptr, rows, scal.ptr, None), W, K)
+        others["min_max_i64"] = {"rows_per_s": world * rows / ms * 1e3, "gbs_per_gpu": 8.0 * rows / ms / 1e6, "frac": 8.0 * rows / ms / 1e6 / peak, "ms": ms}
+        cstate = DeviceBuffer(64)
+
+        def cumsum():
+            N.call("ag_cumulative_sum_state_init_dev", cstate.ptr, N.INT64, None, None)
+            N.call("ag_cumulative_sum_dev", N.INT64, vi.ptr, None, 0, rows, 0, 0, dout.ptr, None, 0, cstate.ptr, bad.ptr, None)
+        ms = timed(cumsum, W, K)
+        others["cumulative_sum_i64"] = {"rows_per_s": world * rows / ms * 1e3, "gbs_per_gpu": 16.0 * rows / ms / 1e6, "frac": 16.0 * rows / ms / 1e6 / peak, "ms": ms,
+                                        "note": "single-pass scan, read once + write once (16 B/row)"}
+        cstate.free(); idx.free(); bad.free(); scal.free()
 
     launches_total = N.raw().ag_kernel_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None

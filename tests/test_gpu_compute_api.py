@@ -408,3 +408,55 @@ def test_arithmetic_implicit_promotion(fname):
     out = pc.CallFunction(fname, [pc.Chunked([pc.Array.from_numpy(l[s:e]) for s, e in zip(cuts, cuts[1:])], pc.INT32), pc.Array.from_numpy(r)])
     vals, _, _ = out.to_numpy()
     assert out.type == pc.FLOAT64 and np.array_equal(vals, npf(l.astype(np.float64), r))
+
+
+# ---------------------------------------------------------------- cumulative_sum -------------
+def test_cumulative_sum_reference_vectors():
+    """arrow/compute/vector_cumulative_test.go through compute.CumulativeSum[Checked] (tests/golden/cumulative_sum.json)."""
+    name_to_id = {"int8": pc.INT8, "int16": pc.INT16, "int32": pc.INT32, "int64": pc.INT64, "uint8": pc.UINT8, "uint16": pc.UINT16,
+                  "uint32": pc.UINT32, "uint64": pc.UINT64, "float32": pc.FLOAT32, "float64": pc.FLOAT64}
+    for case in load("cumulative_sum.json")["cases"]:
+        t = name_to_id[case["type"]]
+        chunks = [pc.Array.from_pylist(c, t) for c in case["chunks"]]
+        values = chunks[0] if len(chunks) == 1 else pc.Chunked(chunks, t)
+        start = pc.Scalar(case["start"], pc.INT64) if "start" in case else None   # :268-270: an int64 start for int32 input
+        kw = dict(start=start, skip_nulls=bool(case.get("skip_nulls")), checked=bool(case.get("checked")))
+        if case.get("fails"):
+            with pytest.raises(pc.ArrowError) as e:
+                pc.CumulativeSum(values, **kw)
+            assert e.value.sentinel == "ErrInvalid" and "overflow" in e.value.msg, case
+            continue
+        out = pc.CumulativeSum(values, **kw)
+        assert out.type == t and out.to_pylist() == case["out"], case
+        if len(chunks) > 1:   # TestCumulativeSumChunked: a chunked result with ONE chunk
+            assert out.kind == pc.KIND_CHUNKED and len(out.chunks()) == 1
+    # scalar input (TestCumulativeSumAdditionalInputs :141-147) and a sliced input (:149-160)
+    assert pc.CumulativeSum(pc.Scalar(3, pc.INT32)).to_pylist() == [3]
+    assert pc.CumulativeSum(pc.Array.from_pylist([0, 1, 2, 3], pc.INT32).slice(1, 2)).to_pylist() == [1, 3]
+    # start value: null scalar rejected (:277-301), unsafe start rejected by the safe cast (:303-344)
+    with pytest.raises(pc.ArrowError) as e:
+        pc.CumulativeSum(pc.Array.from_pylist([1], pc.INT32), start=pc.Scalar(None, pc.INT32))
+    assert "must be valid" in e.value.msg
+    with pytest.raises(pc.ArrowError) as e:
+        pc.CumulativeSum(pc.Array.from_pylist([1], pc.INT8), start=pc.Scalar(300, pc.INT32))
+    assert "cannot cast cumulative sum start value" in e.value.msg
+    with pytest.raises(pc.ArrowError) as e:
+        pc.CumulativeSum(pc.Array.from_pylist([True], pc.BOOL))
+    assert e.value.sentinel == "ErrType"
+
+
+def test_cumulative_sum_chunked_random():
+    rng = np.random.default_rng(21)
+    n = 300_000
+    x = rng.integers(-1000, 1000, n).astype(np.int64)
+    valid = rng.random(n) > 0.001
+    cuts = [0, 1, 1, 40_000, 40_001, 250_000, n]
+    c = pc.Chunked([pc.Array.from_numpy(x[a:b], valid[a:b]) for a, b in zip(cuts, cuts[1:])], pc.INT64)
+    out = pc.CumulativeSum(c, skip_nulls=True, start=pc.Scalar(5, pc.INT8))
+    vals, v, nulls = out.to_numpy()
+    want = np.cumsum(np.where(valid, x, 0)) + 5
+    assert np.array_equal(v, valid) and np.array_equal(vals[v], want[v]) and nulls == int((~valid).sum())
+    out = pc.CumulativeSum(c)      # propagate: everything from the first null on is null
+    vals, v, nulls = out.to_numpy()
+    first = int(np.argmin(valid))
+    assert v[:first].all() and not v[first:].any() and np.array_equal(vals[:first], np.cumsum(x[:first])) and nulls == n - first

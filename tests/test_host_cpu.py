@@ -60,7 +60,8 @@ def test_registry_has_the_reference_function_names():
               "abs", "abs_unchecked", "negate", "negate_unchecked", "sign", "is_null", "is_not_null", "is_nan", "equal", "not_equal", "greater", "greater_equal", "less", "less_equal",
               "and", "or", "xor", "and_not", "and_kleene", "or_kleene", "and_not_kleene", "not",
               "filter", "array_filter", "take", "array_take", "cast", "cast_int8", "cast_int16", "cast_int32", "cast_int64",
-              "cast_uint8", "cast_uint16", "cast_uint32", "cast_uint64", "cast_float", "cast_double"):
+              "cast_uint8", "cast_uint16", "cast_uint32", "cast_uint64", "cast_float", "cast_double",
+              "cumulative_sum", "cumulative_sum_checked"):
         assert n in names, n
 
 
