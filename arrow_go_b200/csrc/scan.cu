@@ -127,6 +127,7 @@ struct PolWrap {  // unchecked integers: the sum modulo 2^64 is all the result n
   static __device__ __forceinline__ A add(A a, A b) { return a + b; }
   static __device__ __forceinline__ A add_elem(A a, T x) { return a + (kSigned ? (A)(long long)x : (A)x); }
   static __device__ __forceinline__ T value(A a) { return (T)a; }
+  static __device__ __forceinline__ T offset_add(T off, T local) { return (T)((A)off + (A)local); }  // modulo 2^w
   static __device__ __forceinline__ bool out_of_range(A) { return false; }
   static __device__ __forceinline__ A shfl_up(A a, int d) { return __shfl_up_sync(0xffffffffu, a, d); }
   static __device__ __forceinline__ A shfl(A a, int src) { return __shfl_sync(0xffffffffu, a, src); }
@@ -161,6 +162,7 @@ struct Pol<T, true> {  // float / double: accumulate in the value type
   }
   static __device__ __forceinline__ A add_elem(A a, T x) { return add(a, x); }
   static __device__ __forceinline__ T value(A a) { return a; }
+  static __device__ __forceinline__ T offset_add(T off, T local) { return add(off, local); }
   static __device__ __forceinline__ bool out_of_range(A) { return false; }  // checkedAdder default: plain add
   static __device__ __forceinline__ A shfl_up(A a, int d) { return __shfl_up_sync(0xffffffffu, a, d); }
   static __device__ __forceinline__ A shfl(A a, int src) { return __shfl_sync(0xffffffffu, a, src); }
@@ -337,6 +339,19 @@ cumsum_kernel(const CumsumParams p) {
       for (int k = 0; k < P::K; ++k) st_word(p.agg + tile * P::K + k, w[k]);
     }
     if (tile + gridDim.x < p.n_tiles) load_tile(tile + gridDim.x);  // prefetch: in flight during the wait below
+    // Unchecked flavours: the running sums RELATIVE to the tile start need nothing from other tiles, so
+    // warps 1..7 compute them while warp 0 is in the look-back; after the barrier only the tile's
+    // exclusive prefix is added.  (Checked integers keep the exact 96-bit pass after the barrier.)
+    auto local_pass = [&]() {
+      A run = P::add(warp_excl, lane_excl);
+      T* o = reinterpret_cast<T*>(raw);  // results replace the inputs in place
+#pragma unroll
+      for (int i = 0; i < E; ++i) {
+        if ((vbits[i >> 5] >> (i & 31)) & 1u) { run = P::add_elem(run, o[i]); o[i] = P::value(run); }
+        else o[i] = T(0);
+      }
+    };
+    if (!kChecked && warp != 0) local_pass();
     if (warp == 0) {
       const int64_t g = tile / kScGroup;
       const int qpos = (int)(tile - g * kScGroup);
@@ -436,21 +451,27 @@ cumsum_kernel(const CumsumParams p) {
       const unsigned w[3] = {(unsigned)s_excl_lo, (unsigned)(s_excl_lo >> 32), (unsigned)s_excl_hi};
       tile_excl = P::from_words(w);
     }
-    const A seg_base = P::add(tile_excl, warp_excl);
     // ---- running sums of the valid slots (0 in null slots), back through shared memory, store --
-    {
-      A run = P::add(seg_base, lane_excl);
-      T* o = reinterpret_cast<T*>(raw);  // results replace the inputs in place
+    if constexpr (kChecked) {
+      A run = P::add(P::add(tile_excl, warp_excl), lane_excl);
+      T* o = reinterpret_cast<T*>(raw);
 #pragma unroll
       for (int i = 0; i < E; ++i) {
         if ((vbits[i >> 5] >> (i & 31)) & 1u) {
           run = P::add_elem(run, o[i]);
           o[i] = P::value(run);
-          if (kChecked && P::out_of_range(run) && t0 + i < my_bad) my_bad = t0 + i;
+          if (P::out_of_range(run) && t0 + i < my_bad) my_bad = t0 + i;
         } else {
           o[i] = T(0);
         }
       }
+    } else {
+      if (warp == 0) local_pass();
+      const T off = P::value(tile_excl);  // integers: the sum modulo 2^w; floats: the prefix itself
+      T* o = reinterpret_cast<T*>(raw);
+#pragma unroll
+      for (int i = 0; i < E; ++i)
+        if ((vbits[i >> 5] >> (i & 31)) & 1u) o[i] = P::offset_add(off, o[i]);
     }
     __syncwarp();
 #pragma unroll
