@@ -20,7 +20,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:bina
     python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-others > gpurun_out/${TAG}_ncu_add.log 2>&1
 echo "ncu add rc=$?"
 # every other hot kernel, one capture each
-timeout 900 ncu --set full --clock-control none -k regex:'sum_kernel|compare_kernel|filter_kernel|take_kernel|checked_tile_kernel' -c 14 -o gpurun_out/${TAG}_prof_kernels -f \
+timeout 900 ncu --set full --clock-control none -k regex:'sum_kernel|compare_kernel|filter_kernel|take_kernel|checked_tile_kernel|cast_vec_kernel|minmax_kernel|cumsum_kernel' -c 48 -o gpurun_out/${TAG}_prof_kernels -f \
     python scripts/prof_kernels.py 100000000 1 > gpurun_out/${TAG}_ncu_kernels.log 2>&1
 echo "ncu kernels rc=$?"
 # gpurun brings back at most 64 MiB: keep the compact per-launch CSVs, drop the raw reports
