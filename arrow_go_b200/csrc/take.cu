@@ -22,6 +22,8 @@
 // of 32, so the output validity word is one __ballot_sync.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace ag {
 
 constexpr int kTkThreads = 256;
@@ -41,7 +43,29 @@ struct TakeParams {
   void* out;
   uint32_t* out_valid;    // 4-byte aligned, offset 0 (may be NULL)
   long long* bad_pos;     // lowered with atomicMin (may be NULL when !bounds_check)
+  int gather_mode;        // experiments (AG_TAKE_GATHER): cache / L2-prefetch-size hint of the random load
 };
+
+// The random 8-byte read is the whole cost of take (DRAM moves ~118 B per gathered row with the default
+// load): these variants ask L2 for a smaller prefetch granule or keep the line out of L1.
+template <typename V>
+__device__ __forceinline__ V gather_load(const V* p, int mode) {
+  if constexpr (sizeof(V) == 8) {
+    unsigned long long r;
+    switch (mode) {
+      case 1: asm volatile("ld.global.L2::64B.u64 %0, [%1];" : "=l"(r) : "l"(p)); break;
+      case 2: asm volatile("ld.global.L2::128B.u64 %0, [%1];" : "=l"(r) : "l"(p)); break;
+      case 3: asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(r) : "l"(p)); break;
+      case 4: asm volatile("ld.global.nc.L1::no_allocate.L2::64B.u64 %0, [%1];" : "=l"(r) : "l"(p)); break;
+      case 5: asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(r) : "l"(p)); break;
+      case 6: asm volatile("ld.global.L2::256B.u64 %0, [%1];" : "=l"(r) : "l"(p)); break;
+      default: return *p;
+    }
+    return *reinterpret_cast<V*>(&r);
+  } else {
+    return *p;
+  }
+}
 
 template <typename V, typename I>
 __global__ void __launch_bounds__(kTkThreads)
@@ -81,7 +105,7 @@ take_kernel(const TakeParams p) {
           }
         } else {
           if (p.vvalid) ok[k] = bit_is_set(p.vvalid, p.voff + (int64_t)ix[k]);
-          if (ok[k]) v[k] = vals[ix[k]];
+          if (ok[k]) v[k] = gather_load(vals + ix[k], p.gather_mode);
         }
       }
     }
@@ -200,6 +224,7 @@ ag_status take_primitive_dev(int bit_width, const void* vals, const uint8_t* vva
   p.idx = idx; p.ivalid = ivalid; p.ioff = ioff; p.n = n;
   p.idx_signed = idx_signed; p.bounds_check = bounds_check;
   p.out = out; p.out_valid = reinterpret_cast<uint32_t*>(out_valid); p.bad_pos = reinterpret_cast<long long*>(d_bad_pos);
+  { static int mode = -1; if (mode < 0) { const char* e = getenv("AG_TAKE_GATHER"); mode = e ? atoi(e) : 0; } p.gather_mode = mode; }
   switch (bit_width) {
     case 8: return launch_take_v<uint8_t>(idx_width, p, st);
     case 16: return launch_take_v<uint16_t>(idx_width, p, st);
