@@ -243,9 +243,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
     if world > 1:
-        # keep stdout to the ONE JSON line: NCCL prints its version banner there at VERSION/INFO
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # keep stdout to the ONE JSON line: NCCL writes its version banner / debug lines to stdout by
+        # default; send them to stderr instead (the level the caller asked for is left alone)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
