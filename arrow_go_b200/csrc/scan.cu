@@ -35,6 +35,7 @@
 // rounding of the same order as the reference's own otherwise.
 #include "common.cuh"
 
+#include <stdlib.h>
 #include <limits>
 
 namespace ag {
@@ -219,6 +220,93 @@ __device__ __forceinline__ typename P::A poll_value(const unsigned long long* wo
   return P::from_words(w);
 }
 
+// The look-back of one tile, executed by a whole warp.  Returns the tile's exclusive prefix (all lanes)
+// after publishing whatever this tile owes the others (its group aggregate, the super-group prefix).
+template <typename P>
+__device__ __forceinline__ typename P::A scan_lookback(const CumsumParams& p, int64_t tile, typename P::A tile_total,
+                                                       typename P::A start, int lane) {
+  using A = typename P::A;
+    const int64_t g = tile / kScGroup;
+    const int qpos = (int)(tile - g * kScGroup);
+    // Everything this tile needs from earlier tiles, fetched as ONE batch of independent polls
+    // (re-issued only for words whose flag is not up yet): slots 0..3 = aggregates of the earlier
+    // tiles of this group (four per lane), slot 4 = aggregates of the earlier groups of this
+    // super-group (one per lane), slot 5 = the previous super-group's inclusive prefix.
+    const int64_t sg = g / kScSuper;
+    const int gq = (int)(g - sg * kScSuper);
+    constexpr int kSlots = kScGroup / 32 + 2;
+    const unsigned long long* src[kSlots];
+    unsigned need = 0;
+#pragma unroll
+    for (int r = 0; r < kScGroup / 32; ++r) {
+      const int pos = r * 32 + lane;
+      src[r] = p.agg + (g * kScGroup + pos) * P::K;
+      if (pos < qpos) need |= ((1u << P::K) - 1u) << (r * P::K);
+    }
+    src[kSlots - 2] = p.gagg + (sg * kScSuper + lane) * P::K;
+    if (lane < gq) need |= ((1u << P::K) - 1u) << ((kSlots - 2) * P::K);
+    src[kSlots - 1] = p.sincl + (sg > 0 ? sg - 1 : 0) * P::K;
+    if (sg > 0) need |= ((1u << P::K) - 1u) << ((kSlots - 1) * P::K);
+    unsigned val[kSlots][3];
+#pragma unroll
+    for (int r = 0; r < kSlots; ++r) { val[r][0] = 0u; val[r][1] = 0u; val[r][2] = 0u; }
+    unsigned got = 0;
+    constexpr unsigned kAggMask = (1u << ((kScGroup / 32) * P::K)) - 1u;
+    bool folded = false;
+    A part = P::zero();
+    while (true) {  // warp-uniform loop: the fold below uses shuffles
+      unsigned long long sw[kSlots][3];
+#pragma unroll
+      for (int r = 0; r < kSlots; ++r)
+#pragma unroll
+        for (int k = 0; k < P::K; ++k)
+          sw[r][k] = (((need & ~got) >> (r * P::K + k)) & 1u) ? ld_word(src[r] + k) : 0ull;
+#pragma unroll
+      for (int r = 0; r < kSlots; ++r)
+#pragma unroll
+        for (int k = 0; k < P::K; ++k)
+          if (sw[r][k] & kScFlag) { val[r][k] = (unsigned)sw[r][k]; got |= 1u << (r * P::K + k); }
+      if (!folded && __all_sync(0xffffffffu, ((got ^ need) & kAggMask) == 0u)) {
+        // tile aggregates are in: fold them in a fixed order (lower tiles on the left) and, for the
+        // last tile of a group, publish the group aggregate WITHOUT waiting for anything older
+        folded = true;
+#pragma unroll
+        for (int r = 0; r < kScGroup / 32; ++r) {
+          A a = (r * 32 + lane < qpos) ? P::from_words(val[r]) : P::zero();
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const A up = P::shfl_up(a, d);
+            if (lane >= d) a = P::add(up, a);
+          }
+          part = P::add(part, P::shfl(a, 31));
+        }
+        if (qpos == kScGroup - 1 && lane == 0) {
+          unsigned wg[3] = {0u, 0u, 0u};
+          P::to_words(P::add(part, tile_total), wg);
+#pragma unroll
+          for (int k = 0; k < P::K; ++k) st_word(p.gagg + g * P::K + k, wg[k]);
+        }
+      }
+      if (__all_sync(0xffffffffu, got == need)) break;
+    }
+    A gpart = (lane < gq) ? P::from_words(val[kSlots - 2]) : P::zero();
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const A up = P::shfl_up(gpart, d);
+      if (lane >= d) gpart = P::add(up, gpart);
+    }
+    gpart = P::shfl(gpart, 31);
+    const A base = (sg > 0) ? P::from_words(val[kSlots - 1]) : start;
+    const A excl = P::add(P::add(base, gpart), part);
+    if (lane == 0 && qpos == kScGroup - 1 && gq == kScSuper - 1) {
+      unsigned wi[3] = {0u, 0u, 0u};
+      P::to_words(P::add(excl, tile_total), wi);
+#pragma unroll
+      for (int k = 0; k < P::K; ++k) st_word(p.sincl + sg * P::K + k, wi[k]);
+    }
+    return excl;
+}
+
 template <typename T, bool kVec, bool kHasValid, bool kChecked>
 __global__ void __launch_bounds__(kScThreads, 2)
 cumsum_kernel(const CumsumParams p) {
@@ -353,90 +441,13 @@ cumsum_kernel(const CumsumParams p) {
     };
     if (!kChecked && warp != 0) local_pass();
     if (warp == 0) {
-      const int64_t g = tile / kScGroup;
-      const int qpos = (int)(tile - g * kScGroup);
-      // Everything this tile needs from earlier tiles, fetched as ONE batch of independent polls
-      // (re-issued only for words whose flag is not up yet): slots 0..3 = aggregates of the earlier
-      // tiles of this group (four per lane), slot 4 = aggregates of the earlier groups of this
-      // super-group (one per lane), slot 5 = the previous super-group's inclusive prefix.
-      const int64_t sg = g / kScSuper;
-      const int gq = (int)(g - sg * kScSuper);
-      constexpr int kSlots = kScGroup / 32 + 2;
-      const unsigned long long* src[kSlots];
-      unsigned need = 0;
-#pragma unroll
-      for (int r = 0; r < kScGroup / 32; ++r) {
-        const int pos = r * 32 + lane;
-        src[r] = p.agg + (g * kScGroup + pos) * P::K;
-        if (pos < qpos) need |= ((1u << P::K) - 1u) << (r * P::K);
-      }
-      src[kSlots - 2] = p.gagg + (sg * kScSuper + lane) * P::K;
-      if (lane < gq) need |= ((1u << P::K) - 1u) << ((kSlots - 2) * P::K);
-      src[kSlots - 1] = p.sincl + (sg > 0 ? sg - 1 : 0) * P::K;
-      if (sg > 0) need |= ((1u << P::K) - 1u) << ((kSlots - 1) * P::K);
-      unsigned val[kSlots][3];
-#pragma unroll
-      for (int r = 0; r < kSlots; ++r) { val[r][0] = 0u; val[r][1] = 0u; val[r][2] = 0u; }
-      unsigned got = 0;
-      constexpr unsigned kAggMask = (1u << ((kScGroup / 32) * P::K)) - 1u;
-      bool folded = false;
-      A part = P::zero();
-      while (true) {  // warp-uniform loop: the fold below uses shuffles
-        unsigned long long sw[kSlots][3];
-#pragma unroll
-        for (int r = 0; r < kSlots; ++r)
-#pragma unroll
-          for (int k = 0; k < P::K; ++k)
-            sw[r][k] = (((need & ~got) >> (r * P::K + k)) & 1u) ? ld_word(src[r] + k) : 0ull;
-#pragma unroll
-        for (int r = 0; r < kSlots; ++r)
-#pragma unroll
-          for (int k = 0; k < P::K; ++k)
-            if (sw[r][k] & kScFlag) { val[r][k] = (unsigned)sw[r][k]; got |= 1u << (r * P::K + k); }
-        if (!folded && __all_sync(0xffffffffu, ((got ^ need) & kAggMask) == 0u)) {
-          // tile aggregates are in: fold them in a fixed order (lower tiles on the left) and, for the
-          // last tile of a group, publish the group aggregate WITHOUT waiting for anything older
-          folded = true;
-#pragma unroll
-          for (int r = 0; r < kScGroup / 32; ++r) {
-            A a = (r * 32 + lane < qpos) ? P::from_words(val[r]) : P::zero();
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-              const A up = P::shfl_up(a, d);
-              if (lane >= d) a = P::add(up, a);
-            }
-            part = P::add(part, P::shfl(a, 31));
-          }
-          if (qpos == kScGroup - 1 && lane == 0) {
-            unsigned wg[3] = {0u, 0u, 0u};
-            P::to_words(P::add(part, tile_total), wg);
-#pragma unroll
-            for (int k = 0; k < P::K; ++k) st_word(p.gagg + g * P::K + k, wg[k]);
-          }
-        }
-        if (__all_sync(0xffffffffu, got == need)) break;
-      }
-      A gpart = (lane < gq) ? P::from_words(val[kSlots - 2]) : P::zero();
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const A up = P::shfl_up(gpart, d);
-        if (lane >= d) gpart = P::add(up, gpart);
-      }
-      gpart = P::shfl(gpart, 31);
-      const A base = (sg > 0) ? P::from_words(val[kSlots - 1]) : start;
-      const A excl = P::add(P::add(base, gpart), part);
+      const A excl = scan_lookback<P>(p, tile, tile_total, start, lane);
       if (lane == 0) {
         unsigned w[3] = {0u, 0u, 0u};
         P::to_words(excl, w);
         s_excl_lo = (unsigned long long)w[0] | ((unsigned long long)w[1] << 32);
         s_excl_hi = (int)w[2];
         const A incl = P::add(excl, tile_total);
-        if (qpos == kScGroup - 1 && gq == kScSuper - 1) {
-          unsigned wi[3] = {0u, 0u, 0u};
-          P::to_words(incl, wi);
-#pragma unroll
-          for (int k = 0; k < P::K; ++k) st_word(p.sincl + sg * P::K + k, wi[k]);
-        }
         if (tile == p.n_tiles - 1) {  // carry to the next chunk (null_count was advanced by cumsum_validity_kernel)
           CumsumState ns = s_state;
           P::to_state(incl, &ns);
@@ -494,6 +505,277 @@ cumsum_kernel(const CumsumParams p) {
     }
     __syncthreads();  // s_warp_* / s_excl_* are rewritten by the next tile
   }
+  if (kChecked) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const long long o = __shfl_xor_sync(0xffffffffu, my_bad, d);
+      my_bad = o < my_bad ? o : my_bad;
+    }
+    if (lane == 0 && my_bad != AG_NO_ERROR_POS) atomicMin(p.first_bad, my_bad);
+  }
+}
+
+// ---------------------------------------------------------------- TMA-fed variant -----------
+// Same scan, but tiles travel through a ring of shared-memory stages moved by the TMA engine
+// (cp.async.bulk, mbarrier complete_tx; SASS UBLKCP): loads are issued kTmaStages-1 tiles ahead
+// of the tile being scanned, results go back into the stage in place and leave with ONE bulk
+// store per tile.  Nothing the threads do — the scans, the look-back wait, the barrier — stops
+// HBM traffic any more, and no registers are spent on staging.  The stage holds the tile exactly
+// as it lies in memory; lane l owns bytes [l*128, l*128+128) of its warp's 4 KB segment and reads
+// the eight 16-byte chunks in the rotated order (c + l) & 7, which touches every bank once per
+// quarter warp without a swizzled copy; chunk sums are put back in order with 8x8 predicated adds.
+// 4- and 8-byte types with 16-byte aligned operands; everything else uses cumsum_kernel.
+// Opt-in (AG_SCAN_TMA=1): it measured the same as the register-prefetch kernel (see launch_cumsum).
+constexpr int kTmaScanStages = 3;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@!p bra WAIT_%=;\n"
+      "}\n" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* sdst, const void* gsrc, unsigned bytes, unsigned long long* b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)), "l"(gsrc),
+               "r"(bytes), "r"(smem_u32(b))
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_1d(void* gdst, const void* ssrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int kPending>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <typename T, bool kHasValid, bool kChecked>
+__global__ void __launch_bounds__(kScThreads, 2)
+cumsum_tma_kernel(const CumsumParams p) {
+  using P = typename PolSel<T, kChecked>::type;
+  using A = typename P::A;
+  constexpr int N = 16 / sizeof(T);
+  constexpr int kTileRows = kScTileBytes / sizeof(T);
+  constexpr int kSegRows = kTileRows / kScWarps;
+  constexpr int E = kScRows * N;  // <= 32 for the types routed here
+  static_assert(E <= 32, "the TMA variant keeps a lane's validity bits in one word");
+  extern __shared__ __align__(128) unsigned char s_ring[];  // kTmaScanStages x 32 KB
+  __shared__ unsigned long long s_bar[kTmaScanStages];
+  __shared__ unsigned long long s_warp_lo[kScWarps];
+  __shared__ int s_warp_hi[kScWarps];
+  __shared__ unsigned long long s_excl_lo;
+  __shared__ int s_excl_hi;
+  __shared__ CumsumState s_state;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const T* __restrict__ in = reinterpret_cast<const T*>(p.in);
+  T* __restrict__ out = reinterpret_cast<T*>(p.out);
+
+  if (threadIdx.x == 0) {
+    s_state = *p.state;
+#pragma unroll
+    for (int s = 0; s < kTmaScanStages; ++s) mbar_init(&s_bar[s], 1);
+    fence_async_smem();
+  }
+  __syncthreads();
+  const bool dead = !p.skip_nulls && s_state.encountered_null != 0;
+  int64_t limit = p.n;
+  if (dead) limit = 0;
+  else if (kHasValid && !p.skip_nulls) limit = *p.first_null;
+  const A start = P::from_state(s_state);
+  long long my_bad = AG_NO_ERROR_POS;
+  const int64_t vlo = p.voff >> 3, vhi = (p.voff + p.n + 7) >> 3;
+  const int64_t full_tiles = p.n / kTileRows;  // tiles below this index are complete: TMA moves them
+
+  auto issue_load = [&](int64_t it) {  // thread 0 only
+    const int64_t tile = blockIdx.x + it * (int64_t)gridDim.x;
+    if (tile < full_tiles) {
+      const int s = (int)(it % kTmaScanStages);
+      mbar_expect_tx(&s_bar[s], kScTileBytes);
+      tma_load_1d(s_ring + (size_t)s * kScTileBytes, in + tile * kTileRows, kScTileBytes, &s_bar[s]);
+    }
+  };
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int j = 0; j < kTmaScanStages - 1; ++j) issue_load(j);
+  }
+
+  int64_t it = 0;
+  for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+    const int s = (int)(it % kTmaScanStages);
+    unsigned char* stage = s_ring + (size_t)s * kScTileBytes;
+    const bool full = tile < full_tiles;
+    const int64_t row0 = tile * kTileRows + (int64_t)warp * kSegRows;
+    const int64_t t0 = row0 + (int64_t)lane * E;
+    if (full) {
+      mbar_wait(&s_bar[s], (unsigned)((it / kTmaScanStages) & 1));
+    } else {  // the last, partial tile: plain loads into the stage (zero-padded)
+      T* st = reinterpret_cast<T*>(stage);
+      for (int i = threadIdx.x; i < kTileRows; i += kScThreads) {
+        const int64_t r = tile * kTileRows + i;
+        st[i] = r < p.n ? in[r] : T(0);
+      }
+      __syncthreads();
+    }
+    // ---- this lane's 128 bytes, chunk (c + lane) & 7 at step c: conflict-free on the linear tile ----
+    uint4* seg = reinterpret_cast<uint4*>(stage) + warp * (kScRows * 32);
+    uint4 raw[kScRows];
+#pragma unroll
+    for (int c = 0; c < kScRows; ++c) raw[c] = seg[lane * 8 + ((c + lane) & 7)];
+    unsigned vb = 0xffffffffu;
+    if (kHasValid) vb = (t0 < p.n) ? bitmap_load32(p.valid, p.voff + t0, vlo, vhi) : 0u;
+    {
+      const int64_t room = limit - t0;
+      if (room < 32) vb &= (room <= 0) ? 0u : ((1u << (int)room) - 1u);
+      if (E < 32) vb &= (1u << (E & 31)) - 1u;
+    }
+    // ---- chunk sums (rotated order), lane total, one warp scan ------------------------------------
+    A csum[kScRows];
+    A tot = P::zero();
+#pragma unroll
+    for (int c = 0; c < kScRows; ++c) {
+      const unsigned cb = (vb >> (((c + lane) & 7) * N)) & ((1u << N) - 1u);
+      A a = P::zero();
+#pragma unroll
+      for (int e = 0; e < N; ++e) if ((cb >> e) & 1u) a = P::add_elem(a, reinterpret_cast<const T*>(&raw[c])[e]);
+      csum[c] = a;
+      tot = P::add(tot, a);
+    }
+    A incl = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const A up = P::shfl_up(incl, d);
+      if (lane >= d) incl = P::add(up, incl);
+    }
+    A lane_excl = P::shfl_up(incl, 1);
+    if (lane == 0) lane_excl = P::zero();
+    const A carry = P::shfl(incl, 31);
+    {
+      unsigned w[3] = {0u, 0u, 0u};
+      P::to_words(carry, w);
+      if (lane == 0) { s_warp_lo[warp] = (unsigned long long)w[0] | ((unsigned long long)w[1] << 32); s_warp_hi[warp] = (int)w[2]; }
+    }
+    __syncthreads();
+    A warp_excl = P::zero(), tile_total = P::zero();
+#pragma unroll
+    for (int wi = 0; wi < kScWarps; ++wi) {
+      const unsigned w[3] = {(unsigned)s_warp_lo[wi], (unsigned)(s_warp_lo[wi] >> 32), (unsigned)s_warp_hi[wi]};
+      const A t = P::from_words(w);
+      if (wi == warp) warp_excl = tile_total;
+      tile_total = P::add(tile_total, t);
+    }
+    if (warp == 0 && lane == 0) {
+      unsigned w[3] = {0u, 0u, 0u};
+      P::to_words(tile_total, w);
+#pragma unroll
+      for (int k = 0; k < P::K; ++k) st_word(p.agg + tile * P::K + k, w[k]);
+    }
+    // exclusive offset of each chunk inside the lane: the sums of the chunks that precede it in memory
+    A coff[kScRows];
+#pragma unroll
+    for (int c = 0; c < kScRows; ++c) {
+      A a = P::zero();
+#pragma unroll
+      for (int c2 = 0; c2 < kScRows; ++c2)
+        if (((c2 + lane) & 7) < ((c + lane) & 7)) a = P::add(a, csum[c2]);
+      coff[c] = a;
+    }
+    // running sums relative to the tile start (unchecked) while warp 0 is in the look-back
+    auto local_pass = [&]() {
+      const A lbase = P::add(warp_excl, lane_excl);
+#pragma unroll
+      for (int c = 0; c < kScRows; ++c) {
+        const unsigned cb = (vb >> (((c + lane) & 7) * N)) & ((1u << N) - 1u);
+        A run = P::add(lbase, coff[c]);
+        T* o = reinterpret_cast<T*>(&raw[c]);
+#pragma unroll
+        for (int e = 0; e < N; ++e) {
+          if ((cb >> e) & 1u) { run = P::add_elem(run, o[e]); o[e] = P::value(run); }
+          else o[e] = T(0);
+        }
+      }
+    };
+    if (!kChecked && warp != 0) local_pass();
+    if (warp == 0) {
+      const A excl = scan_lookback<P>(p, tile, tile_total, start, lane);
+      if (lane == 0) {
+        unsigned w[3] = {0u, 0u, 0u};
+        P::to_words(excl, w);
+        s_excl_lo = (unsigned long long)w[0] | ((unsigned long long)w[1] << 32);
+        s_excl_hi = (int)w[2];
+        if (tile == p.n_tiles - 1) {
+          CumsumState ns = s_state;
+          P::to_state(P::add(excl, tile_total), &ns);
+          if (kHasValid && *p.first_null < p.n) ns.encountered_null = 1;
+          *p.state = ns;
+        }
+      }
+    }
+    __syncthreads();
+    A tile_excl;
+    {
+      const unsigned w[3] = {(unsigned)s_excl_lo, (unsigned)(s_excl_lo >> 32), (unsigned)s_excl_hi};
+      tile_excl = P::from_words(w);
+    }
+    if constexpr (kChecked) {
+      const A lbase = P::add(P::add(tile_excl, warp_excl), lane_excl);
+#pragma unroll
+      for (int c = 0; c < kScRows; ++c) {
+        const int j = (c + lane) & 7;
+        const unsigned cb = (vb >> (j * N)) & ((1u << N) - 1u);
+        A run = P::add(lbase, coff[c]);
+        T* o = reinterpret_cast<T*>(&raw[c]);
+#pragma unroll
+        for (int e = 0; e < N; ++e) {
+          if ((cb >> e) & 1u) {
+            run = P::add_elem(run, o[e]);
+            o[e] = P::value(run);
+            const long long row = t0 + j * N + e;
+            if (P::out_of_range(run) && row < my_bad) my_bad = row;
+          } else {
+            o[e] = T(0);
+          }
+        }
+      }
+    } else {
+      if (warp == 0) local_pass();
+      const T off = P::value(tile_excl);
+#pragma unroll
+      for (int c = 0; c < kScRows; ++c) {
+        const unsigned cb = (vb >> (((c + lane) & 7) * N)) & ((1u << N) - 1u);
+        T* o = reinterpret_cast<T*>(&raw[c]);
+#pragma unroll
+        for (int e = 0; e < N; ++e) if ((cb >> e) & 1u) o[e] = P::offset_add(off, o[e]);
+      }
+    }
+    // ---- results back into the stage (same places), one bulk store for the tile -------------------
+#pragma unroll
+    for (int c = 0; c < kScRows; ++c) seg[lane * 8 + ((c + lane) & 7)] = raw[c];
+    if (full) {
+      fence_async_smem();  // make the generic-proxy writes visible to the TMA engine
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        tma_store_1d(out + tile * kTileRows, stage, kScTileBytes);
+        tma_store_wait_read<1>();   // every store but this one has released its stage
+        issue_load(it + kTmaScanStages - 1);  // refill the stage of the previous tile
+      }
+    } else {
+      __syncthreads();
+      const T* st = reinterpret_cast<const T*>(stage);
+      for (int i = threadIdx.x; i < kTileRows; i += kScThreads) {
+        const int64_t r = tile * kTileRows + i;
+        if (r < p.n) out[r] = st[i];
+      }
+    }
+  }
+  if (threadIdx.x == 0) tma_store_wait_read<0>();  // shared memory must outlive the last bulk store
   if (kChecked) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -601,9 +883,30 @@ ag_status launch_cumsum(CumsumParams& p, cudaStream_t st) {
     if (vec) fn = p.valid ? (const void*)cumsum_kernel<T, true, true, false> : (const void*)cumsum_kernel<T, true, false, false>;
     else fn = p.valid ? (const void*)cumsum_kernel<T, false, true, false> : (const void*)cumsum_kernel<T, false, false, false>;
   }
-  int64_t cap = (int64_t)sm_count() * blocks_per_sm(fn, kScThreads);
+  size_t dyn_smem = 0;
+  if constexpr (sizeof(T) >= 4) {
+    // opt-in (AG_SCAN_TMA=1, read per call so a test can flip it): measured 433 us vs 437 us for the
+    // register-prefetch kernel at 100M int64 rows — the scan is bound by the look-back dependency between
+    // concurrently running tiles, not by the load path, so the simpler kernel stays the default
+    const char* e = getenv("AG_SCAN_TMA");
+    const bool use_tma = e && e[0] == '1';
+    if (vec && use_tma) {
+      if (chk) fn = p.valid ? (const void*)cumsum_tma_kernel<T, true, !IsFp<T>::v> : (const void*)cumsum_tma_kernel<T, false, !IsFp<T>::v>;
+      else fn = p.valid ? (const void*)cumsum_tma_kernel<T, true, false> : (const void*)cumsum_tma_kernel<T, false, false>;
+      dyn_smem = (size_t)kTmaScanStages * kScTileBytes;
+      AG_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+    }
+  }
+  int per_sm = 0;
+  if (dyn_smem) {
+    AG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kScThreads, dyn_smem));
+    if (per_sm < 1) AG_FAIL(AG_ERR_CUDA, "cumulative_sum: the TMA scan kernel does not fit on an SM");
+  } else {
+    per_sm = blocks_per_sm(fn, kScThreads);
+  }
+  const int64_t cap = (int64_t)sm_count() * per_sm;
   const int grid = (int)(p.n_tiles < cap ? p.n_tiles : cap);
-  AG_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kScThreads), args, 0, st));
+  AG_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kScThreads), args, dyn_smem, st));
   return check_launch("cumsum_kernel");
 }
 
