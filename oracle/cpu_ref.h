@@ -9,10 +9,12 @@
  * Pinning: tests/test_oracle_*.py check this restatement against
  *   (1) the reference's own instruction stream, oracle/_ref/libarrowgo_ref.so (assembled
  *       from the reference's checked-in _lib .s files; oracle/Makefile) for every function
- *       that has a native counterpart (sum, arithmetic, comparisons, aligned bitmap ops),
+ *       that has a native counterpart (sum, arithmetic, comparisons, aligned bitmap ops,
+ *       numeric casts, integer min/max),
  *   (2) the literal known-answer vectors of the reference's Go tests, restated in
  *       tests/golden/ (arithmetic_test.go, scalar_compare_test.go, scalar_bool_test.go,
- *       vector_selection_test.go, arrow/math/{float64,int64,uint64}_test.go, bitmaps_test.go),
+ *       vector_selection_test.go, arrow/math/{float64,int64,uint64}_test.go, bitmaps_test.go,
+ *       cast_test.go, vector_cumulative_test.go),
  *   (3) pyarrow (an independent implementation of the same Arrow semantics) for the
  *       Go-only logic (filter, take, Kleene).
  */
