@@ -219,7 +219,7 @@ def run_reference_arm(args):
         "e2e": {"value": one, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": wall,
     }
-    print(json.dumps(line))
+    _emit(line)
 
 
 # ------------------------------------------------------------------ our arm ---------------
@@ -234,6 +234,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    _claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -451,9 +452,26 @@ def main():
             "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches_timed), "gpu_launches_total": int(launches_total),
             "clocks": clocks, "others": others,
         }
-        print(json.dumps(line))
+        _emit(line)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def _emit(line):
+    """The ONE JSON line, on the process's original stdout."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
+def _claim_stdout():
+    """Everything any library prints (NCCL's version banner, torch notices) goes to stderr: file
+    descriptor 1 is pointed at stderr for the whole run and only _emit() writes to the real stdout."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
 
 
 if __name__ == "__main__":
