@@ -201,7 +201,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = 16_000_000
+    sample = int(os.environ.get("AG_BENCH_REF_SAMPLE", "16000000"))  # rows per step of the bounded sample (tests shrink it)
     t0 = time.perf_counter()
     for _ in range(max(args.warmup, 1) - 1):
         pass

@@ -175,3 +175,22 @@ def test_iterate_exec_spans_fuzz():
             for a in range(nargs):
                 if chunked[a]:
                     assert gi[a] == wi[a]
+
+
+def test_reference_arm_prints_exactly_one_json_line():
+    """bench.py contract: rank 0 prints ONE JSON line on stdout (everything else goes to stderr).  The
+    reference arm runs on the CPU, so the contract can be checked here."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--rows", "1000000", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=300, env=dict(os.environ, AG_BENCH_REF_SAMPLE="500000"))
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout[:500]
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["e2e"]["h2d_bytes_per_step"] == 0
