@@ -50,3 +50,37 @@ def filter_output_offsets(local_count, dist, device="cpu"):
     dist.all_gather(counts, torch.tensor([local_count], dtype=torch.int64, device=device))
     counts = [int(c.item()) for c in counts]
     return sum(counts[: dist.get_rank()]), sum(counts)
+
+
+def global_min_max(local_min, local_max, dist, device="cpu"):
+    """min/max of the per-rank (min, max) pairs (ag_min_max per GPU + two 8-byte all-reduces).  Values
+    travel as int64; uint64 callers pass their values through int(np.int64(np.uint64(v))) ^ (1 << 63) style
+    order-preserving maps if they exceed 2^63 (not needed for the Parquet physical types, which are signed)."""
+    import torch
+    lo = torch.tensor([int(local_min)], dtype=torch.int64, device=device)
+    hi = torch.tensor([int(local_max)], dtype=torch.int64, device=device)
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    return int(lo.item()), int(hi.item())
+
+
+def cumulative_sum_carry(local_total, local_has_null, dist, skip_nulls=False, device="cpu"):
+    """What a row-range-sharded cumulative_sum needs from the other ranks: the wrapping int64 sum of every
+    LOWER rank's shard (its start value: pass it to ag_cumulative_sum_state_init_dev) and whether a lower
+    rank met a null (without skip_nulls this rank's whole output is then null).  Each rank first runs the
+    scan once with start 0 (or just Sum over its valid rows up to its first null) to get `local_total`;
+    G x 9 bytes cross the wire."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    mine = torch.tensor([np.int64(np.uint64(local_total % (1 << 64)).astype(np.int64)), int(bool(local_has_null))], dtype=torch.int64, device=device)
+    parts = [torch.zeros(2, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    start, dead = 0, False
+    for r in range(rank):
+        if not skip_nulls and dead:
+            break
+        start = (start + int(parts[r][0].item())) % (1 << 64)
+        dead = dead or bool(parts[r][1].item())
+    if start >= 1 << 63:
+        start -= 1 << 64
+    return start, (dead and not skip_nulls)

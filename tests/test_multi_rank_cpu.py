@@ -48,6 +48,22 @@ def _worker(rank, world, port, q):
     with np.errstate(over="ignore"):
         want_i = int(xi.sum(dtype=np.int64))
     ok = (gi == want_i) and (gf == float(xf.sum())) and (off == int(mask[:a].sum())) and (total == int(mask.sum()))
+    # min/max and the cumulative-sum carry: per-rank partials from numpy, plumbing under test
+    lo, hi = sharding.global_min_max(int(xi[a:b].min()), int(xi[a:b].max()), dist)
+    ok = ok and (lo, hi) == (int(xi.min()), int(xi.max()))
+    valid = np.ones(n, dtype=bool)
+    valid[700_001] = False                      # one null, in the last shard for world=2
+    for skip in (False, True):
+        v = valid[a:b]
+        first = int(np.argmin(v)) if not v.all() else len(v)
+        contrib = xi[a:b][v] if skip else xi[a:b][:first]
+        with np.errstate(over="ignore"):
+            local_total = int(contrib.sum(dtype=np.int64))
+        start, dead = sharding.cumulative_sum_carry(local_total, not v.all(), dist, skip_nulls=skip)
+        with np.errstate(over="ignore"):
+            want_start = int(xi[:a][valid[:a]].sum(dtype=np.int64)) if skip else int(xi[:min(a, 700_001)].sum(dtype=np.int64))
+        want_dead = (not skip) and (not valid[:a].all())
+        ok = ok and start == want_start and dead == want_dead
     q.put((rank, ok, gi, want_i))
     dist.destroy_process_group()
 
