@@ -811,6 +811,246 @@ cumsum_tma_kernel(const CumsumParams p) {
   }
 }
 
+// ---------------------------------------------------------------- two-phase pipelined variant --
+// cumsum_tma_kernel with each tile's work split in two phases that a block interleaves ACROSS tiles:
+//   A(k): wait for the tile, per-lane / warp / block totals, publish the tile aggregate, remember the
+//         lane's offset inside the tile;
+//   B(k): look-back (the aggregates it needs were published a whole A-phase ago, so the first batch of
+//         polls normally finds them all), running sums, bulk store.
+// The block runs A(k), refills the ring, then B(k-1): the publish -> poll round trip through L2 — the
+// one thing every tile has to sit through — is covered by the next tile's A phase instead of a barrier
+// with seven idle warps (ncu on the single-phase kernels: 45-50 % of stall samples there).  The tile
+// stays in its shared-memory stage between the phases; B re-derives the chunk sums from it.
+constexpr int kPipeStages = 3;
+
+template <typename T, bool kHasValid, bool kChecked>
+__global__ void __launch_bounds__(kScThreads, 2)
+cumsum_pipe_kernel(const CumsumParams p) {
+  using P = typename PolSel<T, kChecked>::type;
+  using A = typename P::A;
+  constexpr int N = 16 / sizeof(T);
+  constexpr int kTileRows = kScTileBytes / sizeof(T);
+  constexpr int kSegRows = kTileRows / kScWarps;
+  constexpr int E = kScRows * N;
+  static_assert(E <= 32, "a lane's validity bits live in one word");
+  extern __shared__ __align__(128) unsigned char s_ring[];  // kPipeStages x 32 KB
+  __shared__ unsigned long long s_bar[kPipeStages];
+  __shared__ unsigned long long s_base_lo[kPipeStages][kScThreads];  // lane offset inside the tile (phase A -> B)
+  __shared__ int s_base_hi[kPipeStages][kScThreads];
+  __shared__ unsigned s_vb[kPipeStages][kScThreads];
+  __shared__ unsigned long long s_tot_lo[kPipeStages];
+  __shared__ int s_tot_hi[kPipeStages];
+  __shared__ unsigned long long s_warp_lo[kScWarps];
+  __shared__ int s_warp_hi[kScWarps];
+  __shared__ unsigned long long s_excl_lo;
+  __shared__ int s_excl_hi;
+  __shared__ CumsumState s_state;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const T* __restrict__ in = reinterpret_cast<const T*>(p.in);
+  T* __restrict__ out = reinterpret_cast<T*>(p.out);
+
+  if (threadIdx.x == 0) {
+    s_state = *p.state;
+#pragma unroll
+    for (int s = 0; s < kPipeStages; ++s) mbar_init(&s_bar[s], 1);
+    fence_async_smem();
+  }
+  __syncthreads();
+  const bool dead = !p.skip_nulls && s_state.encountered_null != 0;
+  int64_t limit = p.n;
+  if (dead) limit = 0;
+  else if (kHasValid && !p.skip_nulls) limit = *p.first_null;
+  const A start = P::from_state(s_state);
+  long long my_bad = AG_NO_ERROR_POS;
+  const int64_t vlo = p.voff >> 3, vhi = (p.voff + p.n + 7) >> 3;
+  const int64_t full_tiles = p.n / kTileRows;
+  const int64_t n_my = (p.n_tiles - 1 - (int64_t)blockIdx.x) / (int64_t)gridDim.x + 1;  // tiles of this block (>= 1)
+
+  auto issue_load = [&](int64_t k) {  // thread 0 only
+    const int64_t tile = blockIdx.x + k * (int64_t)gridDim.x;
+    if (k < n_my && tile < full_tiles) {
+      const int s = (int)(k % kPipeStages);
+      mbar_expect_tx(&s_bar[s], kScTileBytes);
+      tma_load_1d(s_ring + (size_t)s * kScTileBytes, in + tile * kTileRows, kScTileBytes, &s_bar[s]);
+    }
+  };
+  if (threadIdx.x == 0) issue_load(0);
+
+  for (int64_t k = 0; k <= n_my; ++k) {
+    // ================================ phase A of tile k ===========================================
+    if (k < n_my) {
+      const int64_t tile = blockIdx.x + k * (int64_t)gridDim.x;
+      const int s = (int)(k % kPipeStages);
+      unsigned char* stage = s_ring + (size_t)s * kScTileBytes;
+      const int64_t t0 = tile * kTileRows + (int64_t)warp * kSegRows + (int64_t)lane * E;
+      if (tile < full_tiles) {
+        mbar_wait(&s_bar[s], (unsigned)((k / kPipeStages) & 1));
+      } else {
+        T* st = reinterpret_cast<T*>(stage);
+        for (int i = threadIdx.x; i < kTileRows; i += kScThreads) {
+          const int64_t r = tile * kTileRows + i;
+          st[i] = r < p.n ? in[r] : T(0);
+        }
+        __syncthreads();
+      }
+      const uint4* seg = reinterpret_cast<const uint4*>(stage) + warp * (kScRows * 32);
+      unsigned vb = 0xffffffffu;
+      if (kHasValid) vb = (t0 < p.n) ? bitmap_load32(p.valid, p.voff + t0, vlo, vhi) : 0u;
+      {
+        const int64_t room = limit - t0;
+        if (room < 32) vb &= (room <= 0) ? 0u : ((1u << (int)room) - 1u);
+        if (E < 32) vb &= (1u << (E & 31)) - 1u;
+      }
+      A tot = P::zero();
+#pragma unroll
+      for (int c = 0; c < kScRows; ++c) {
+        const uint4 q = seg[lane * 8 + ((c + lane) & 7)];
+        const unsigned cb = (vb >> (((c + lane) & 7) * N)) & ((1u << N) - 1u);
+#pragma unroll
+        for (int e = 0; e < N; ++e) if ((cb >> e) & 1u) tot = P::add_elem(tot, reinterpret_cast<const T*>(&q)[e]);
+      }
+      A incl = tot;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const A up = P::shfl_up(incl, d);
+        if (lane >= d) incl = P::add(up, incl);
+      }
+      A lane_excl = P::shfl_up(incl, 1);
+      if (lane == 0) lane_excl = P::zero();
+      {
+        unsigned w[3] = {0u, 0u, 0u};
+        P::to_words(P::shfl(incl, 31), w);
+        if (lane == 0) { s_warp_lo[warp] = (unsigned long long)w[0] | ((unsigned long long)w[1] << 32); s_warp_hi[warp] = (int)w[2]; }
+      }
+      __syncthreads();
+      A warp_excl = P::zero(), tile_total = P::zero();
+#pragma unroll
+      for (int wi = 0; wi < kScWarps; ++wi) {
+        const unsigned w[3] = {(unsigned)s_warp_lo[wi], (unsigned)(s_warp_lo[wi] >> 32), (unsigned)s_warp_hi[wi]};
+        const A t = P::from_words(w);
+        if (wi == warp) warp_excl = tile_total;
+        tile_total = P::add(tile_total, t);
+      }
+      {
+        unsigned w[3] = {0u, 0u, 0u};
+        P::to_words(tile_total, w);
+        if (threadIdx.x == 0) {
+#pragma unroll
+          for (int kk = 0; kk < P::K; ++kk) st_word(p.agg + tile * P::K + kk, w[kk]);
+          s_tot_lo[s] = (unsigned long long)w[0] | ((unsigned long long)w[1] << 32);
+          s_tot_hi[s] = (int)w[2];
+        }
+        unsigned wb[3] = {0u, 0u, 0u};
+        P::to_words(P::add(warp_excl, lane_excl), wb);
+        s_base_lo[s][threadIdx.x] = (unsigned long long)wb[0] | ((unsigned long long)wb[1] << 32);
+        s_base_hi[s][threadIdx.x] = (int)wb[2];
+        s_vb[s][threadIdx.x] = vb;
+      }
+      __syncthreads();  // s_warp_* may be rewritten by the next phase A; s_tot_* is read by warp 0 in phase B
+    }
+    // ================================ refill the ring ==============================================
+    // tile k+1 goes into the stage tile k-2 used; its bulk store was issued a whole phase A ago
+    if (threadIdx.x == 0) {
+      tma_store_wait_read<0>();
+      issue_load(k + 1);
+    }
+    // ================================ phase B of tile k-1 ==========================================
+    if (k >= 1) {
+      const int64_t j = k - 1;
+      const int64_t tile = blockIdx.x + j * (int64_t)gridDim.x;
+      const int s = (int)(j % kPipeStages);
+      unsigned char* stage = s_ring + (size_t)s * kScTileBytes;
+      const bool full = tile < full_tiles;
+      const int64_t t0 = tile * kTileRows + (int64_t)warp * kSegRows + (int64_t)lane * E;
+      A tile_total;
+      {
+        const unsigned w[3] = {(unsigned)s_tot_lo[s], (unsigned)(s_tot_lo[s] >> 32), (unsigned)s_tot_hi[s]};
+        tile_total = P::from_words(w);
+      }
+      if (warp == 0) {
+        const A excl = scan_lookback<P>(p, tile, tile_total, start, lane);
+        if (lane == 0) {
+          unsigned w[3] = {0u, 0u, 0u};
+          P::to_words(excl, w);
+          s_excl_lo = (unsigned long long)w[0] | ((unsigned long long)w[1] << 32);
+          s_excl_hi = (int)w[2];
+          if (tile == p.n_tiles - 1) {
+            CumsumState ns = s_state;
+            P::to_state(P::add(excl, tile_total), &ns);
+            if (kHasValid && *p.first_null < p.n) ns.encountered_null = 1;
+            *p.state = ns;
+          }
+        }
+      }
+      __syncthreads();
+      A tile_excl, lbase;
+      {
+        const unsigned w[3] = {(unsigned)s_excl_lo, (unsigned)(s_excl_lo >> 32), (unsigned)s_excl_hi};
+        tile_excl = P::from_words(w);
+        const unsigned wb[3] = {(unsigned)s_base_lo[s][threadIdx.x], (unsigned)(s_base_lo[s][threadIdx.x] >> 32), (unsigned)s_base_hi[s][threadIdx.x]};
+        lbase = P::add(tile_excl, P::from_words(wb));
+      }
+      const unsigned vb = s_vb[s][threadIdx.x];
+      uint4* seg = reinterpret_cast<uint4*>(stage) + warp * (kScRows * 32);
+      uint4 raw[kScRows];
+      A csum[kScRows];
+#pragma unroll
+      for (int c = 0; c < kScRows; ++c) {
+        raw[c] = seg[lane * 8 + ((c + lane) & 7)];
+        const unsigned cb = (vb >> (((c + lane) & 7) * N)) & ((1u << N) - 1u);
+        A a = P::zero();
+#pragma unroll
+        for (int e = 0; e < N; ++e) if ((cb >> e) & 1u) a = P::add_elem(a, reinterpret_cast<const T*>(&raw[c])[e]);
+        csum[c] = a;
+      }
+#pragma unroll
+      for (int c = 0; c < kScRows; ++c) {
+        const int jj = (c + lane) & 7;
+        A run = lbase;  // + the sums of the chunks that precede chunk jj in memory
+#pragma unroll
+        for (int c2 = 0; c2 < kScRows; ++c2)
+          if (((c2 + lane) & 7) < jj) run = P::add(run, csum[c2]);
+        const unsigned cb = (vb >> (jj * N)) & ((1u << N) - 1u);
+        T* o = reinterpret_cast<T*>(&raw[c]);
+#pragma unroll
+        for (int e = 0; e < N; ++e) {
+          if ((cb >> e) & 1u) {
+            run = P::add_elem(run, o[e]);
+            o[e] = P::value(run);
+            if (kChecked) { const long long row = t0 + jj * N + e; if (P::out_of_range(run) && row < my_bad) my_bad = row; }
+          } else {
+            o[e] = T(0);
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < kScRows; ++c) seg[lane * 8 + ((c + lane) & 7)] = raw[c];
+      if (full) {
+        fence_async_smem();
+        __syncthreads();
+        if (threadIdx.x == 0) tma_store_1d(out + tile * kTileRows, stage, kScTileBytes);
+      } else {
+        __syncthreads();
+        const T* st = reinterpret_cast<const T*>(stage);
+        for (int i = threadIdx.x; i < kTileRows; i += kScThreads) {
+          const int64_t r = tile * kTileRows + i;
+          if (r < p.n) out[r] = st[i];
+        }
+        __syncthreads();
+      }
+    }
+  }
+  if (threadIdx.x == 0) tma_store_wait_read<0>();
+  if (kChecked) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const long long o = __shfl_xor_sync(0xffffffffu, my_bad, d);
+      my_bad = o < my_bad ? o : my_bad;
+    }
+    if (lane == 0 && my_bad != AG_NO_ERROR_POS) atomicMin(p.first_bad, my_bad);
+  }
+}
+
 // first 0 bit of validity[voff, voff+n): one thread per 32 rows, atomicMin into *first_null (pre-set to n)
 __global__ void __launch_bounds__(256)
 first_null_kernel(const uint8_t* __restrict__ valid, int64_t voff, int64_t n, long long* first_null) {
@@ -915,7 +1155,13 @@ ag_status launch_cumsum(CumsumParams& p, cudaStream_t st) {
     // concurrently running tiles, not by the load path, so the simpler kernel stays the default
     const char* e = getenv("AG_SCAN_TMA");
     const bool use_tma = e && e[0] == '1';
-    if (vec && use_tma) {
+    const bool use_pipe = e && e[0] == '2';
+    if (vec && use_pipe) {
+      if (chk) fn = p.valid ? (const void*)cumsum_pipe_kernel<T, true, !IsFp<T>::v> : (const void*)cumsum_pipe_kernel<T, false, !IsFp<T>::v>;
+      else fn = p.valid ? (const void*)cumsum_pipe_kernel<T, true, false> : (const void*)cumsum_pipe_kernel<T, false, false>;
+      dyn_smem = (size_t)kPipeStages * kScTileBytes;
+      AG_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+    } else if (vec && use_tma) {
       if (chk) fn = p.valid ? (const void*)cumsum_tma_kernel<T, true, !IsFp<T>::v> : (const void*)cumsum_tma_kernel<T, false, !IsFp<T>::v>;
       else fn = p.valid ? (const void*)cumsum_tma_kernel<T, true, false> : (const void*)cumsum_tma_kernel<T, false, false>;
       dyn_smem = (size_t)kTmaScanStages * kScTileBytes;

@@ -238,9 +238,11 @@ def test_gpu_large_crosses_super_group(ag, cpu, t):
 
 
 @gpu
-def test_gpu_tma_variant(ag, cpu, monkeypatch):
-    """The TMA-fed kernel (AG_SCAN_TMA=1: cp.async.bulk ring, bulk stores) gives the same bits."""
-    monkeypatch.setenv("AG_SCAN_TMA", "1")
+@pytest.mark.parametrize("variant", ["1", "2"], ids=["tma", "tma-two-phase"])
+def test_gpu_tma_variant(ag, cpu, monkeypatch, variant):
+    """The TMA-fed kernels (AG_SCAN_TMA=1: cp.async.bulk ring + bulk stores; =2: the same with each tile's
+    work split in two phases interleaved across tiles) give the same bits as the default kernel."""
+    monkeypatch.setenv("AG_SCAN_TMA", variant)
     rng = np.random.default_rng(31)
     for t in (N.INT64, N.INT32, N.FLOAT64, N.FLOAT32, N.UINT64):
         for n in (1, 4096, 4097, 100_003, (1 << 20) + 13):
