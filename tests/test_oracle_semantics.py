@@ -283,3 +283,113 @@ def test_boolean_values_filter_take_vs_pyarrow(cpu):
         assert unpack_bits(ov, 0, 2 * n).tolist() == wv.tolist() and nulls.value == want.null_count
         wd = np.array([bool(x.as_py()) if x.is_valid else False for x in want], dtype=bool)
         assert unpack_bits(out, 0, 2 * n)[wv].tolist() == wd[wv].tolist()
+
+
+# ---------------------------------------------------------------- casts / cumulative sum vs pyarrow ----
+PA_OF = {N.UINT8: pa.uint8(), N.INT8: pa.int8(), N.UINT16: pa.uint16(), N.INT16: pa.int16(), N.UINT32: pa.uint32(), N.INT32: pa.int32(),
+         N.UINT64: pa.uint64(), N.INT64: pa.int64(), N.FLOAT32: pa.float32(), N.FLOAT64: pa.float64()}
+
+
+def _oracle_cast(cpu, ti, to, x, valid, aio, aft):
+    out = np.zeros(x.size, dtype=NP_OF[to])
+    bad = C.c_int64(-1)
+    bm = pack_bits(valid, offset=3) if valid is not None else None
+    st = cpu.ref_cast_numeric(ti, to, ptr(x), ptr(bm) if bm is not None else None, 3, ptr(out), x.size, int(aio), int(aft), C.byref(bad))
+    return st, out, bad.value
+
+
+def test_safe_cast_accept_reject_vs_pyarrow(cpu):
+    """Arrow C++ (pyarrow) is an independent implementation of the same safe-cast rules the Go code ports
+    (int range, |int| <= 2^24 / 2^53 for floats, float -> int truncation): for boundary and random inputs the
+    restatement must accept / reject exactly the same calls, and agree on the values of the accepted ones."""
+    rng = np.random.default_rng(2024)
+    all_t = list(PA_OF)
+    for ti in all_t:
+        for to in all_t:
+            if ti == to:
+                continue
+            idt, odt = np.dtype(NP_OF[ti]), np.dtype(NP_OF[to])
+            cands = []
+            if idt.kind != "f":
+                ii = np.iinfo(idt)
+                pts = {ii.min, ii.max, 0, 1}
+                if odt.kind != "f":
+                    oi = np.iinfo(odt)
+                    pts |= {v for v in (oi.min, oi.max, oi.min - 1, oi.max + 1) if ii.min <= v <= ii.max}
+                else:
+                    m = 24 if odt.itemsize == 4 else 53
+                    pts |= {v for v in ((1 << m), (1 << m) + 1, -(1 << m), -(1 << m) - 1) if ii.min <= v <= ii.max}
+                cands = [np.array([0, p, 0], dtype=idt) for p in sorted(pts)]
+            else:
+                oi = np.iinfo(odt) if odt.kind != "f" else None
+                vals = [0.0, 1.0, -1.0, 1.5, -0.5, 255.0, 256.0, -129.0, 65535.0, 3e9, -3e9, 1e19, float("nan")] if oi else [0.0, 1.5, 1e39, -1e39, float("inf"), float("nan")]
+                with np.errstate(over="ignore"):  # 1e39 -> float32 is inf on purpose
+                    cands = [np.array([0, v, 0], dtype=idt) for v in vals]
+            for x in cands:
+                for valid in (None, np.array([True, False, True])):
+                    arr = pa.array(x, type=PA_OF[ti], mask=None if valid is None else ~valid)
+                    try:
+                        want = pc.cast(arr, PA_OF[to], safe=True)
+                        pa_ok = True
+                    except pa.ArrowInvalid:
+                        pa_ok = False
+                    st, out, bad = _oracle_cast(cpu, ti, to, x, valid, False, False)
+                    if idt.kind == "f" and odt.kind == "f":
+                        assert st == 0   # float -> float never fails in either implementation
+                        continue
+                    assert (st == 0) == pa_ok, (TYPE_NAME[ti], TYPE_NAME[to], x.tolist(), None if valid is None else valid.tolist(), st, pa_ok)
+                    if pa_ok:
+                        ok = np.ones(3, dtype=bool) if valid is None else valid
+                        wv = want.to_numpy(zero_copy_only=False)
+                        got, exp = out[ok], np.asarray(wv[ok], dtype=NP_OF[to])
+                        assert np.array_equal(got, exp, equal_nan=(odt.kind == "f")), (TYPE_NAME[ti], TYPE_NAME[to], x.tolist())
+                    else:
+                        assert bad == 1
+    # unsafe integer casts wrap identically
+    for ti, to in ((N.INT32, N.UINT8), (N.INT64, N.INT16), (N.UINT32, N.INT8), (N.UINT64, N.INT32)):
+        x = random_values(rng, ti, 1000)
+        st, out, _ = _oracle_cast(cpu, ti, to, x, None, True, True)
+        want = pc.cast(pa.array(x), PA_OF[to], safe=False).to_numpy()
+        assert st == 0 and np.array_equal(out, want)
+
+
+def test_cumulative_sum_vs_pyarrow(cpu):
+    """pyarrow's cumulative_sum[_checked] (start, skip_nulls) against the restatement of vector_cumulative.go."""
+    rng = np.random.default_rng(77)
+
+    class St(C.Structure):
+        _fields_ = [("cur", C.c_uint8 * 8), ("enc", C.c_int64)]
+
+    for t in (N.INT8, N.UINT16, N.INT32, N.INT64, N.UINT64, N.FLOAT64):
+        dt = np.dtype(NP_OF[t])
+        for n in (0, 1, 17, 500):
+            for skip in (False, True):
+                for checked in (False, True):
+                    x = rng.integers(-3, 4, n).astype(dt) if dt.kind != "u" else rng.integers(0, 4, n).astype(dt)
+                    valid = rng.random(n) > 0.2
+                    start = 2
+                    st_ = St()
+                    for i, b in enumerate(np.array([start], dtype=dt).tobytes()):
+                        st_.cur[i] = b
+                    out = np.zeros(n, dtype=dt)
+                    ov = np.zeros(n // 8 + 2, dtype=np.uint8)
+                    nulls, bad = C.c_int64(), C.c_int64()
+                    bm = pack_bits(valid, offset=0)
+                    rc = cpu.ref_cumulative_sum(t, ptr(x), ptr(bm), 0, n, int(skip), int(checked), ptr(out), ptr(ov), 0, C.byref(st_), C.byref(nulls), C.byref(bad))
+                    arr = pa.array(x, type=PA_OF[t], mask=~valid)
+                    fn = pc.cumulative_sum_checked if checked else pc.cumulative_sum
+                    want = fn(arr, start=pa.scalar(start, type=PA_OF[t]), skip_nulls=skip)
+                    assert rc == 0
+                    wv = np.array([v is not None for v in want.to_pylist()], dtype=bool)
+                    assert np.array_equal(unpack_bits(ov, 0, n).astype(bool), wv), (TYPE_NAME[t], n, skip)
+                    wvals = np.array([0 if v is None else v for v in want.to_pylist()], dtype=dt)
+                    assert np.array_equal(out[wv], wvals[wv]) and nulls.value == int((~wv).sum())
+    # overflow: checked fails in both, unchecked wraps in both
+    x = np.array([127, 1], dtype=np.int8)
+    with pytest.raises(pa.ArrowInvalid):
+        pc.cumulative_sum_checked(pa.array(x))
+    st_ = St()
+    out = np.zeros(2, dtype=np.int8)
+    bad = C.c_int64()
+    assert cpu.ref_cumulative_sum(N.INT8, ptr(x), None, 0, 2, 0, 1, ptr(out), None, 0, C.byref(st_), None, C.byref(bad)) != 0 and bad.value == 1
+    assert pc.cumulative_sum(pa.array(x)).to_pylist() == [127, -128]
