@@ -14,7 +14,8 @@
 // 4096-row tiles, each thread moving 4 independent 16-byte vectors per operand at a time
 // (ld.global.cs / st.global.cs — streaming, evict first: every byte is touched once).  A chunked
 // call is ONE launch over all its aligned spans.  Pointers that are only element-aligned (Arrow
-// slices, Appendix D of SURVEY.md) take the element-wise path with the same arithmetic.
+// slices, Appendix D of SURVEY.md) keep the 128-bit accesses: the tile aligns on its output and
+// funnel-shifts the inputs (shift_combine below); same arithmetic, same bits.
 #include "common.cuh"
 
 #include <stdlib.h>
@@ -60,26 +61,32 @@ __device__ __forceinline__ void stv(T* p, int64_t vi, const Vec<T, 16 / sizeof(T
   __stcs(reinterpret_cast<uint4*>(p) + vi, *reinterpret_cast<const uint4*>(&v));
 }
 
-// ---------------------------------------------------------------- binary -----------
-template <typename T, typename Op, int kShape>
-__global__ void __launch_bounds__(kEwThreads)
-binary_scalar_kernel(const T* __restrict__ l, const T* __restrict__ r, T* __restrict__ out, int64_t n, T scalar) {
-  const int64_t stride = (int64_t)gridDim.x * kEwThreads;
-  int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x;
-  for (; i + (kEwUnroll - 1) * stride < n; i += kEwUnroll * stride) {
-    T a[kEwUnroll], b[kEwUnroll];
-#pragma unroll
-    for (int k = 0; k < kEwUnroll; ++k) {
-      a[k] = (kShape == AG_SHAPE_SA) ? scalar : __ldcs(l + i + k * stride);
-      b[k] = (kShape == AG_SHAPE_AS) ? scalar : __ldcs(r + i + k * stride);
-    }
-#pragma unroll
-    for (int k = 0; k < kEwUnroll; ++k) __stcs(out + i + k * stride, Op::template apply<T>(a[k], b[k]));
+// ---- element-aligned operands (Arrow slices: base + offset*width is only element-aligned) ----------------------
+// The kernels align on the OUTPUT (a few head elements go through the scalar path) and read a misaligned input as
+// aligned 16-byte vectors: output vector v needs bytes [mb, mb+16) of the aligned pair (v, v+1).  Lane j loads aligned
+// vector v_j and takes v_j+1 from lane j+1 by shuffle (lane 31 from lane 0's NEXT vector, which the same warp loads
+// anyway), so HBM still sees every byte once and every access is a full 128-bit transaction — cf. the reference's
+// prefix / suffix handling around its SIMD body, _lib/scalar_comparison.cc:72-95.
+__device__ __forceinline__ uint4 shift_combine(const uint4 a, const uint4 b, int mb) {
+  uint32_t w0, w1, w2, w3, w4;
+  switch (mb >> 2) {
+    case 0: w0 = a.x; w1 = a.y; w2 = a.z; w3 = a.w; w4 = b.x; break;
+    case 1: w0 = a.y; w1 = a.z; w2 = a.w; w3 = b.x; w4 = b.y; break;
+    case 2: w0 = a.z; w1 = a.w; w2 = b.x; w3 = b.y; w4 = b.z; break;
+    default: w0 = a.w; w1 = b.x; w2 = b.y; w3 = b.z; w4 = b.w; break;
   }
-  for (; i < n; i += stride)
-    out[i] = Op::template apply<T>(kShape == AG_SHAPE_SA ? scalar : l[i], kShape == AG_SHAPE_AS ? scalar : r[i]);
+  const int s = (mb & 3) * 8;
+  return make_uint4(__funnelshift_r(w0, w1, s), __funnelshift_r(w1, w2, s), __funnelshift_r(w2, w3, s), __funnelshift_r(w3, w4, s));
+}
+// next aligned vector of every lane: lanes 0..30 read their right neighbour's `cur`, lane 31 reads lane 0's `nxt`
+__device__ __forceinline__ uint4 neighbour_vector(const uint4 cur, const uint4 nxt, int lane) {
+  const uint4 t = lane == 0 ? nxt : cur;
+  const int src = (lane + 1) & 31;
+  return make_uint4(__shfl_sync(0xffffffffu, t.x, src), __shfl_sync(0xffffffffu, t.y, src), __shfl_sync(0xffffffffu, t.z, src),
+                    __shfl_sync(0xffffffffu, t.w, src));
 }
 
+// ---------------------------------------------------------------- binary -----------
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 template <typename T, typename Op, int kShape>
@@ -92,15 +99,7 @@ static ag_status launch_binary_t(const void* l, const void* r, void* out, int64_
   const T* lp = reinterpret_cast<const T*>(l);
   const T* rp = reinterpret_cast<const T*>(r);
   T* op = reinterpret_cast<T*>(out);
-  constexpr int N = 16 / sizeof(T);
-  const bool vec = aligned16(out) && (kShape == AG_SHAPE_SA || aligned16(l)) && (kShape == AG_SHAPE_AS || aligned16(r));
-  if (vec) {
-    return launch_single_span<T, Op, kShape>(lp, rp, op, n, scalar, st);
-  } else {
-    const int grid = grid_one_wave(binary_scalar_kernel<T, Op, kShape>, kEwThreads, (n + kEwThreads * kEwUnroll - 1) / (kEwThreads * kEwUnroll));
-    binary_scalar_kernel<T, Op, kShape><<<grid, kEwThreads, 0, st>>>(lp, rp, op, n, scalar);
-  }
-  return check_launch("binary_kernel");
+  return launch_single_span<T, Op, kShape>(lp, rp, op, n, scalar, st);   // any element alignment
 }
 
 template <typename T, typename Op>
@@ -152,7 +151,29 @@ ag_status arith_binary_dev(int type, int8_t op, int shape, const void* l, const 
 // block finds its tile's span by binary search over the prefix array, then runs the same
 // 128-bit streaming loop as binary_vec_kernel (or the element loop when that span's pointers
 // are only element-aligned).
-constexpr int kSpanTile = 4096;
+constexpr int kSpanTile = 4096;        // rows per tile of the checked kernels
+constexpr int kSpanTileBytes = 32768;  // bytes per operand per tile of the unchecked kernels (4096 float64 rows)
+
+// Rows before the first 16-byte boundary of `out` (the span head).  Tiles start there, so inside a tile the output is
+// always vector-aligned: a chunked call whose slices share one misalignment (pos*width off a 16-byte boundary on every
+// operand — what executeSpans produces) runs entirely on the aligned path.
+static __host__ __device__ __forceinline__ long long span_head(const void* out, int width, long long n) {
+  const int N = 16 / width;
+  const long long h = (N - (long long)((reinterpret_cast<uintptr_t>(out) & 15) / width)) & (N - 1);
+  return h < n ? h : n;
+}
+// true when an array input of the span is not 16-byte aligned at the row where the output is
+static inline bool span_needs_shift(int shape, const void* l, const void* r, const void* out, int width, long long n) {
+  const uintptr_t hb = (uintptr_t)(span_head(out, width, n) * width);
+  return (shape != AG_SHAPE_SA && ((reinterpret_cast<uintptr_t>(l) + hb) & 15)) ||
+         (shape != AG_SHAPE_AS && ((reinterpret_cast<uintptr_t>(r) + hb) & 15));
+}
+static inline long long span_tiles(const void* out, int width, long long n) {
+  const long long rows = kSpanTileBytes / width;
+  const long long body = n - span_head(out, width, n);
+  const long long t = (body + rows - 1) / rows;
+  return t > 0 ? t : 1;
+}
 
 struct SpanDesc {
   const void* l;
@@ -163,8 +184,10 @@ struct SpanDesc {
 };
 
 // kSingle: one span passed by value (the contiguous call) — same tile loop, no table, no search.
-template <typename T, typename Op, int kShape, bool kSingle>
-__global__ void __launch_bounds__(kEwThreads)
+// kShift: some span has an input that is not 16-byte aligned where its output is (the host checks); the common
+// all-aligned call keeps the lean kernel (no shuffle path, 3 resident blocks per SM).
+template <typename T, typename Op, int kShape, bool kSingle, bool kShift>
+__global__ void __launch_bounds__(kEwThreads, kShift ? 2 : 3)
 binary_spans_kernel(const SpanDesc* __restrict__ spans, int n_spans, long long total_tiles, T scalar, SpanDesc single) {
   constexpr int N = 16 / sizeof(T);
   __shared__ int s_span;
@@ -183,16 +206,26 @@ binary_spans_kernel(const SpanDesc* __restrict__ spans, int n_spans, long long t
       sp = spans[s_span];
       __syncthreads();
     }
-    const long long e0 = (tile - sp.first_tile) * kSpanTile;
-    const int len = (int)((sp.n - e0 < kSpanTile) ? (sp.n - e0) : kSpanTile);
+    constexpr int kTile = kSpanTileBytes / (int)sizeof(T);
+    const long long head = span_head(sp.out, (int)sizeof(T), sp.n);
+    const long long t_in = tile - sp.first_tile;
+    if (t_in == 0 && threadIdx.x < head) {   // the few rows before the output's first 16-byte boundary
+      const T* l0 = reinterpret_cast<const T*>(sp.l);
+      const T* r0 = reinterpret_cast<const T*>(sp.r);
+      reinterpret_cast<T*>(sp.out)[threadIdx.x] =
+          Op::template apply<T>(kShape == AG_SHAPE_SA ? scalar : l0[threadIdx.x], kShape == AG_SHAPE_AS ? scalar : r0[threadIdx.x]);
+    }
+    const long long e0 = head + t_in * kTile;
+    const long long rest = sp.n - e0;
+    const int len = (int)(rest < kTile ? (rest > 0 ? rest : 0) : kTile);
     const T* l = reinterpret_cast<const T*>(sp.l) + (kShape == AG_SHAPE_SA ? 0 : e0);
     const T* r = reinterpret_cast<const T*>(sp.r) + (kShape == AG_SHAPE_AS ? 0 : e0);
     T* out = reinterpret_cast<T*>(sp.out) + e0;
-    const bool vec = ((reinterpret_cast<uintptr_t>(out) | (kShape == AG_SHAPE_SA ? 0 : reinterpret_cast<uintptr_t>(l)) |
-                       (kShape == AG_SHAPE_AS ? 0 : reinterpret_cast<uintptr_t>(r))) & 15) == 0;
+    const bool vec = !kShift || (((kShape == AG_SHAPE_SA ? 0 : reinterpret_cast<uintptr_t>(l)) |
+                                  (kShape == AG_SHAPE_AS ? 0 : reinterpret_cast<uintptr_t>(r))) & 15) == 0;
     if (vec) {
       const int nvec = len / N;
-      constexpr int kIters = kSpanTile / N / kEwThreads;  // vectors per thread in a full tile
+      constexpr int kIters = kTile / N / kEwThreads;  // vectors per thread in a full tile
 #pragma unroll
       for (int b = 0; b < kIters; b += kEwUnroll) {
         Vec<T, N> a[kEwUnroll], c[kEwUnroll];
@@ -218,10 +251,53 @@ binary_spans_kernel(const SpanDesc* __restrict__ spans, int n_spans, long long t
       }
       const int i = nvec * N + threadIdx.x;
       if (i < len) out[i] = Op::template apply<T>(kShape == AG_SHAPE_SA ? scalar : l[i], kShape == AG_SHAPE_AS ? scalar : r[i]);
-    } else {
-#pragma unroll 4
-      for (int i = threadIdx.x; i < len; i += kEwThreads)
-        __stcs(out + i, Op::template apply<T>(kShape == AG_SHAPE_SA ? scalar : __ldcs(l + i), kShape == AG_SHAPE_AS ? scalar : __ldcs(r + i)));
+    } else if constexpr (kShift) {
+      // element-aligned inputs: the output is aligned, shift the inputs (see shift_combine)
+      constexpr int ho = 0;                   // tiles start on an output vector boundary (span_head)
+      const int nvec = len / N;
+      {
+        const int i = nvec * N + threadIdx.x;  // < N tail rows, last tile of the span only
+        if (i < len) out[i] = Op::template apply<T>(kShape == AG_SHAPE_SA ? scalar : l[i], kShape == AG_SHAPE_AS ? scalar : r[i]);
+      }
+      const int mbl = kShape == AG_SHAPE_SA ? 0 : (int)(reinterpret_cast<uintptr_t>(l + ho) & 15);
+      const int mbr = kShape == AG_SHAPE_AS ? 0 : (int)(reinterpret_cast<uintptr_t>(r + ho) & 15);
+      const uint4* __restrict__ lf = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(l + ho) - mbl);
+      const uint4* __restrict__ rf = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(r + ho) - mbr);
+      uint4* __restrict__ ob = reinterpret_cast<uint4*>(out + ho);
+      const int lane = threadIdx.x & 31;
+      const int nl = nvec + (mbl ? 1 : 0), nr = nvec + (mbr ? 1 : 0);   // a shifted operand reads one vector more
+      constexpr int kWarpVecs = 32 * kEwUnroll;
+      for (int base = (threadIdx.x >> 5) * kWarpVecs; base < nvec; base += (kEwThreads / 32) * kWarpVecs) {
+        uint4 a[kEwUnroll + 1], c[kEwUnroll + 1];
+#pragma unroll
+        for (int k = 0; k < kEwUnroll; ++k) {
+          const int vi = base + k * 32 + lane;
+          a[k] = make_uint4(0, 0, 0, 0); c[k] = make_uint4(0, 0, 0, 0);
+          if (kShape != AG_SHAPE_SA && vi < nl) a[k] = __ldcs(lf + vi);
+          if (kShape != AG_SHAPE_AS && vi < nr) c[k] = __ldcs(rf + vi);
+        }
+        a[kEwUnroll] = make_uint4(0, 0, 0, 0); c[kEwUnroll] = make_uint4(0, 0, 0, 0);
+        if (lane == 0) {   // the vector after this warp's last one
+          if (mbl && base + kWarpVecs < nl) a[kEwUnroll] = __ldcs(lf + base + kWarpVecs);
+          if (mbr && base + kWarpVecs < nr) c[kEwUnroll] = __ldcs(rf + base + kWarpVecs);
+        }
+#pragma unroll
+        for (int k = 0; k < kEwUnroll; ++k) {
+          const int vi = base + k * 32 + lane;
+          uint4 av = a[k], cv = c[k];
+          if (mbl) av = shift_combine(a[k], neighbour_vector(a[k], a[k + 1], lane), mbl);
+          if (mbr) cv = shift_combine(c[k], neighbour_vector(c[k], c[k + 1], lane), mbr);
+          if (vi < nvec) {
+            const Vec<T, N>& x = *reinterpret_cast<const Vec<T, N>*>(&av);
+            const Vec<T, N>& y = *reinterpret_cast<const Vec<T, N>*>(&cv);
+            Vec<T, N> o;
+#pragma unroll
+            for (int e = 0; e < N; ++e)
+              o.v[e] = Op::template apply<T>(kShape == AG_SHAPE_SA ? scalar : x.v[e], kShape == AG_SHAPE_AS ? scalar : y.v[e]);
+            __stcs(ob + vi, *reinterpret_cast<const uint4*>(&o));
+          }
+        }
+      }
     }
   }
 }
@@ -231,35 +307,45 @@ binary_spans_kernel(const SpanDesc* __restrict__ spans, int n_spans, long long t
 template <typename T, typename Op, int kShape>
 static ag_status launch_single_span(const T* l, const T* r, T* out, int64_t n, T scalar, cudaStream_t st) {
   SpanDesc sp{l, r, out, (long long)n, 0};
-  const long long tiles = (n + kSpanTile - 1) / kSpanTile;
-  const int grid = grid_one_wave(binary_spans_kernel<T, Op, kShape, true>, kEwThreads, tiles);
-  binary_spans_kernel<T, Op, kShape, true><<<grid, kEwThreads, 0, st>>>(nullptr, 1, tiles, scalar, sp);
+  const long long tiles = span_tiles(out, (int)sizeof(T), n);
+  if (span_needs_shift(kShape, l, r, out, (int)sizeof(T), n)) {
+    const int grid = grid_one_wave(binary_spans_kernel<T, Op, kShape, true, true>, kEwThreads, tiles);
+    binary_spans_kernel<T, Op, kShape, true, true><<<grid, kEwThreads, 0, st>>>(nullptr, 1, tiles, scalar, sp);
+  } else {
+    const int grid = grid_one_wave(binary_spans_kernel<T, Op, kShape, true, false>, kEwThreads, tiles);
+    binary_spans_kernel<T, Op, kShape, true, false><<<grid, kEwThreads, 0, st>>>(nullptr, 1, tiles, scalar, sp);
+  }
   return check_launch("binary_spans_kernel");
 }
 
 template <typename T, typename Op, int kShape>
-static ag_status launch_spans_t(const SpanDesc* d_spans, int n_spans, long long total_tiles, const void* scalar_host, cudaStream_t st) {
+static ag_status launch_spans_t(const SpanDesc* d_spans, int n_spans, long long total_tiles, const void* scalar_host, bool shift, cudaStream_t st) {
   T scalar = T(0);
   if (kShape != AG_SHAPE_AA) scalar = *reinterpret_cast<const T*>(scalar_host);
-  const int grid = grid_one_wave(binary_spans_kernel<T, Op, kShape, false>, kEwThreads, total_tiles);
-  binary_spans_kernel<T, Op, kShape, false><<<grid, kEwThreads, 0, st>>>(d_spans, n_spans, total_tiles, scalar, SpanDesc{});
+  if (shift) {
+    const int grid = grid_one_wave(binary_spans_kernel<T, Op, kShape, false, true>, kEwThreads, total_tiles);
+    binary_spans_kernel<T, Op, kShape, false, true><<<grid, kEwThreads, 0, st>>>(d_spans, n_spans, total_tiles, scalar, SpanDesc{});
+  } else {
+    const int grid = grid_one_wave(binary_spans_kernel<T, Op, kShape, false, false>, kEwThreads, total_tiles);
+    binary_spans_kernel<T, Op, kShape, false, false><<<grid, kEwThreads, 0, st>>>(d_spans, n_spans, total_tiles, scalar, SpanDesc{});
+  }
   return check_launch("binary_spans_kernel");
 }
 template <typename T, typename Op>
-static ag_status launch_spans_shape(int shape, const SpanDesc* d, int n, long long tiles, const void* sc, cudaStream_t st) {
+static ag_status launch_spans_shape(int shape, const SpanDesc* d, int n, long long tiles, const void* sc, bool shift, cudaStream_t st) {
   switch (shape) {
-    case AG_SHAPE_AA: return launch_spans_t<T, Op, AG_SHAPE_AA>(d, n, tiles, sc, st);
-    case AG_SHAPE_AS: return launch_spans_t<T, Op, AG_SHAPE_AS>(d, n, tiles, sc, st);
-    case AG_SHAPE_SA: return launch_spans_t<T, Op, AG_SHAPE_SA>(d, n, tiles, sc, st);
+    case AG_SHAPE_AA: return launch_spans_t<T, Op, AG_SHAPE_AA>(d, n, tiles, sc, shift, st);
+    case AG_SHAPE_AS: return launch_spans_t<T, Op, AG_SHAPE_AS>(d, n, tiles, sc, shift, st);
+    case AG_SHAPE_SA: return launch_spans_t<T, Op, AG_SHAPE_SA>(d, n, tiles, sc, shift, st);
     default: AG_FAIL(AG_ERR_INVALID, "arith: bad operand shape %d", shape);
   }
 }
 template <typename T>
-static ag_status launch_spans_op(int8_t op, int shape, const SpanDesc* d, int n, long long tiles, const void* sc, cudaStream_t st) {
+static ag_status launch_spans_op(int8_t op, int shape, const SpanDesc* d, int n, long long tiles, const void* sc, bool shift, cudaStream_t st) {
   switch (op) {
-    case AG_OP_ADD: case AG_OP_ADD_CHECKED: return launch_spans_shape<T, OpAdd>(shape, d, n, tiles, sc, st);
-    case AG_OP_SUB: case AG_OP_SUB_CHECKED: return launch_spans_shape<T, OpSub>(shape, d, n, tiles, sc, st);
-    case AG_OP_MUL: case AG_OP_MUL_CHECKED: return launch_spans_shape<T, OpMul>(shape, d, n, tiles, sc, st);
+    case AG_OP_ADD: case AG_OP_ADD_CHECKED: return launch_spans_shape<T, OpAdd>(shape, d, n, tiles, sc, shift, st);
+    case AG_OP_SUB: case AG_OP_SUB_CHECKED: return launch_spans_shape<T, OpSub>(shape, d, n, tiles, sc, shift, st);
+    case AG_OP_MUL: case AG_OP_MUL_CHECKED: return launch_spans_shape<T, OpMul>(shape, d, n, tiles, sc, shift, st);
     default: AG_FAIL(AG_ERR_NOT_IMPLEMENTED, "arith: binary op %d has no native kernel", (int)op);
   }
 }
@@ -273,6 +359,7 @@ ag_status arith_binary_spans_dev(int type, int8_t op, int shape, const ag_span3*
   std::vector<SpanDesc> desc;
   desc.reserve((size_t)n_spans);
   long long tiles = 0;
+  bool shift = false;
   const void* scalar_host = nullptr;
   const uintptr_t m = (uintptr_t)(w - 1);
   for (int64_t i = 0; i < n_spans; ++i) {
@@ -286,7 +373,8 @@ ag_status arith_binary_spans_dev(int type, int8_t op, int shape, const ag_span3*
     if (shape == AG_SHAPE_SA) scalar_host = s.l;
     SpanDesc d{s.l, s.r, s.out, (long long)s.n, tiles};
     desc.push_back(d);
-    tiles += (s.n + kSpanTile - 1) / kSpanTile;
+    shift = shift || span_needs_shift(shape, s.l, s.r, s.out, w, s.n);
+    tiles += span_tiles(s.out, w, s.n);
   }
   if (desc.empty()) return AG_OK;
   if (desc.size() > (size_t)INT32_MAX) AG_FAIL(AG_ERR_INVALID, "arith_spans: too many spans");
@@ -298,12 +386,12 @@ ag_status arith_binary_spans_dev(int type, int8_t op, int shape, const ag_span3*
   ag_status rc;
   const int n = (int)desc.size();
   switch (type) {
-    case AG_TYPE_UINT8: case AG_TYPE_INT8: rc = launch_spans_op<uint8_t>(op, shape, d_spans, n, tiles, scalar_host, st); break;
-    case AG_TYPE_UINT16: case AG_TYPE_INT16: rc = launch_spans_op<uint16_t>(op, shape, d_spans, n, tiles, scalar_host, st); break;
-    case AG_TYPE_UINT32: case AG_TYPE_INT32: rc = launch_spans_op<uint32_t>(op, shape, d_spans, n, tiles, scalar_host, st); break;
-    case AG_TYPE_UINT64: case AG_TYPE_INT64: rc = launch_spans_op<unsigned long long>(op, shape, d_spans, n, tiles, scalar_host, st); break;
-    case AG_TYPE_FLOAT32: rc = launch_spans_op<float>(op, shape, d_spans, n, tiles, scalar_host, st); break;
-    case AG_TYPE_FLOAT64: rc = launch_spans_op<double>(op, shape, d_spans, n, tiles, scalar_host, st); break;
+    case AG_TYPE_UINT8: case AG_TYPE_INT8: rc = launch_spans_op<uint8_t>(op, shape, d_spans, n, tiles, scalar_host, shift, st); break;
+    case AG_TYPE_UINT16: case AG_TYPE_INT16: rc = launch_spans_op<uint16_t>(op, shape, d_spans, n, tiles, scalar_host, shift, st); break;
+    case AG_TYPE_UINT32: case AG_TYPE_INT32: rc = launch_spans_op<uint32_t>(op, shape, d_spans, n, tiles, scalar_host, shift, st); break;
+    case AG_TYPE_UINT64: case AG_TYPE_INT64: rc = launch_spans_op<unsigned long long>(op, shape, d_spans, n, tiles, scalar_host, shift, st); break;
+    case AG_TYPE_FLOAT32: rc = launch_spans_op<float>(op, shape, d_spans, n, tiles, scalar_host, shift, st); break;
+    case AG_TYPE_FLOAT64: rc = launch_spans_op<double>(op, shape, d_spans, n, tiles, scalar_host, shift, st); break;
     default: rc = AG_ERR_TYPE; set_error("arith: unsupported type id %d", type); break;
   }
   cudaFreeAsync(d_spans, st);

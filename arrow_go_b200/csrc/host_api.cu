@@ -88,15 +88,7 @@ static ag_status upload_bitmap(Temps& t, const uint8_t* h, int64_t off, int64_t 
 }
 
 constexpr int kPipe = 3;
-static int64_t chunk_bytes() {  // per operand per pipeline stage
-  static int64_t v = 0;
-  if (v == 0) {
-    const char* e = getenv("AG_PIPE_CHUNK_MB");  // experiments only
-    v = ((e && atoi(e) > 0) ? (int64_t)atoi(e) : 32) << 20;
-  }
-  return v;
-}
-#define kChunkBytes (chunk_bytes())
+constexpr int64_t kChunkBytes = (int64_t)32 << 20;  // per operand per pipeline stage
 
 struct Pipe {
   CallStream s[kPipe];

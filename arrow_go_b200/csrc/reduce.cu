@@ -6,6 +6,14 @@
 //
 // Roofline: HBM.  8 algorithmic bytes per row, ~0.125 flop/byte.
 //
+// float64: every accumulator is a (sum, error) pair updated with Knuth's TwoSum (6 dependent-free flops per element,
+// far below what the FP64 pipe can do while the kernel waits on HBM), and partial results are merged the same way, so
+// the value returned is the correctly rounded sum of the inputs up to a relative error of ~n*eps^2 — within 1 ULP of
+// math.fsum at 100M N(0,1) rows (tests/test_gpu_sum.py), where the reference's own three association orders (AVX2 /
+// SSE4 / pure Go) sit tens to hundreds of ULP apart.  Whenever the exact sum is representable (the
+// reference's tests, integer-valued data) the result is bit-identical to the reference in any order;
+// ag_sum_f64_reforder reproduces the AVX2 order bit for bit on any input.  Integers wrap (any order is exact).
+//
 // Shape of the reduction (fixed => the float64 result is a pure function of (data, n)):
 //   * the input is viewed as PAIRS (x[2j], x[2j+1]); an odd last element is folded in at the end;
 //   * G = sum_grid(n) blocks of 256 threads (at most 148 x 8, a constant); block b streams the
@@ -17,8 +25,8 @@
 // with the SAME pair->thread mapping, so alignment never changes the result.
 #include "common.cuh"
 
-#include <stdlib.h>
-#include <cuda/barrier>
+#include <type_traits>
+
 
 namespace ag {
 
@@ -29,17 +37,17 @@ constexpr int kSumTilePairs = kSumThreads * kSumLoads;        // 2048 pairs = 32
 constexpr int kSumBlocksPerSM = 8;                            // measured at 100M rows: 296..888 blocks 126-135 us, 1184 blocks 123.6 us
 constexpr int kSumMaxBlocks = 148 * kSumBlocksPerSM;          // fixed (not queried): the result must not depend on the device
 
+// float64 keeps (sum, error) pairs: 64 registers per thread, 4 resident blocks per SM -> its one-wave grid is 148 x 4
+template <typename T> constexpr int sum_blocks_per_sm() { return std::is_floating_point<T>::value ? 4 : kSumBlocksPerSM; }
+
+template <typename T>
 static inline int sum_grid(size_t n_pairs) {
   // small inputs get few blocks (latency), big ones the fixed one-wave grid
   size_t want = (n_pairs + kSumTilePairs - 1) / kSumTilePairs;
   if (want < 1) want = 1;
-  static int cap = 0;
-  if (cap == 0) {
-    const char* e = getenv("AG_SUM_BLOCKS");  // experiments only
-    cap = (e && atoi(e) > 0) ? atoi(e) : kSumMaxBlocks;
-    if (cap > kMaxPartials) cap = kMaxPartials;
-  }
-  if (want > (size_t)cap) want = cap;
+  static_assert(kSumMaxBlocks <= kMaxPartials, "one 16-byte partial per block");
+  constexpr size_t cap = 148 * sum_blocks_per_sm<T>();
+  if (want > cap) want = cap;
   return (int)want;
 }
 
@@ -66,35 +74,60 @@ __device__ __forceinline__ T shfl_xor_t(T v, int m) {
   return *reinterpret_cast<T*>(&u);
 }
 
+// Accumulator: integers are a plain wrapping sum; float64 carries the rounding error of every addition (TwoSum:
+// s + x = t + e exactly) in a second word.  16 bytes either way, which is the partials slot size.
+template <typename T> struct alignas(16) Acc {
+  T s; T pad;
+  __device__ __forceinline__ void zero() { s = T(0); pad = T(0); }
+  __device__ __forceinline__ void add(T x) { s = s + x; }
+  __device__ __forceinline__ void merge(const Acc& o) { s = s + o.s; }
+  __device__ __forceinline__ Acc shfl_xor(int m) const { Acc r; r.s = shfl_xor_t(s, m); r.pad = T(0); return r; }
+  __device__ __forceinline__ T value() const { return s; }
+};
+template <> struct alignas(16) Acc<double> {
+  double s, c;
+  __device__ __forceinline__ void zero() { s = 0.0; c = 0.0; }
+  __device__ __forceinline__ void add(double x) {
+    const double t = __dadd_rn(s, x);
+    const double z = __dsub_rn(t, s);
+    const double e = __dadd_rn(__dsub_rn(s, __dsub_rn(t, z)), __dsub_rn(x, z));
+    s = t;
+    c = __dadd_rn(c, e);
+  }
+  __device__ __forceinline__ void merge(const Acc& o) { add(o.s); c = __dadd_rn(c, o.c); }
+  __device__ __forceinline__ Acc shfl_xor(int m) const { Acc r; r.s = shfl_xor_t(s, m); r.c = shfl_xor_t(c, m); return r; }
+  __device__ __forceinline__ double value() const { return __dadd_rn(s, c); }
+};
+
 // fixed tree over the 256 threads of a block; result valid in thread 0
 template <typename T>
-__device__ __forceinline__ T block_tree_sum(T v, T* smem /* >= 8 */) {
+__device__ __forceinline__ Acc<T> block_tree_sum(Acc<T> v, Acc<T>* smem /* >= 8 */) {
 #pragma unroll
-  for (int m = 16; m >= 1; m >>= 1) v = v + shfl_xor_t(v, m);
+  for (int m = 16; m >= 1; m >>= 1) v.merge(v.shfl_xor(m));
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0) smem[warp] = v;
   __syncthreads();
-  T r = T(0);
+  Acc<T> r; r.zero();
   if (warp == 0) {
-    r = (lane < kSumThreads / 32) ? smem[lane] : T(0);
+    if (lane < kSumThreads / 32) r = smem[lane];
 #pragma unroll
-    for (int m = 4; m >= 1; m >>= 1) r = r + shfl_xor_t(r, m);
+    for (int m = 4; m >= 1; m >>= 1) r.merge(r.shfl_xor(m));
   }
   __syncthreads();
   return r;
 }
 
 template <typename T, bool kAligned>
-__global__ void __launch_bounds__(kSumThreads)
-sum_kernel(const T* __restrict__ in, size_t n, T* __restrict__ partials, unsigned* __restrict__ ticket,
+__global__ void __launch_bounds__(kSumThreads, sum_blocks_per_sm<T>())
+sum_kernel(const T* __restrict__ in, size_t n, Acc<T>* __restrict__ partials, unsigned* __restrict__ ticket,
            T* __restrict__ out) {
-  __shared__ T smem[8];
+  __shared__ Acc<T> smem[8];
   __shared__ bool is_last;
   const size_t n_pairs = n >> 1;
   const size_t n_tiles = (n_pairs + kSumTilePairs - 1) / kSumTilePairs;
-  T ax[kSumAcc], ay[kSumAcc];
+  Acc<T> ax[kSumAcc], ay[kSumAcc];
 #pragma unroll
-  for (int k = 0; k < kSumAcc; ++k) { ax[k] = T(0); ay[k] = T(0); }
+  for (int k = 0; k < kSumAcc; ++k) { ax[k].zero(); ay[k].zero(); }
   // Block b streams the contiguous 32 KB tiles b, b+G, b+2G, ...; inside a tile thread t owns
   // pairs t, t+256, ... (8 independent 16-byte loads in flight), load k feeds accumulator k % 4.
   for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -104,23 +137,26 @@ sum_kernel(const T* __restrict__ in, size_t n, T* __restrict__ partials, unsigne
 #pragma unroll
       for (int k = 0; k < kSumLoads; ++k) p[k] = load_pair<T, kAligned>(in, j0 + (size_t)k * kSumThreads);
 #pragma unroll
-      for (int k = 0; k < kSumLoads; ++k) { ax[k % kSumAcc] = ax[k % kSumAcc] + p[k].x; ay[k % kSumAcc] = ay[k % kSumAcc] + p[k].y; }
+      for (int k = 0; k < kSumLoads; ++k) { ax[k % kSumAcc].add(p[k].x); ay[k % kSumAcc].add(p[k].y); }
     } else {
 #pragma unroll
       for (int k = 0; k < kSumLoads; ++k) {
         const size_t jj = j0 + (size_t)k * kSumThreads;
         if (jj < n_pairs) {
           const Pair<T> p = load_pair<T, kAligned>(in, jj);
-          ax[k % kSumAcc] = ax[k % kSumAcc] + p.x; ay[k % kSumAcc] = ay[k % kSumAcc] + p.y;
+          ax[k % kSumAcc].add(p.x); ay[k % kSumAcc].add(p.y);
         }
       }
     }
   }
-  T v = ((ax[0] + ay[0]) + (ax[1] + ay[1])) + ((ax[2] + ay[2]) + (ax[3] + ay[3]));
-  v = block_tree_sum(v, smem);
+  // ((x0+y0)+(x1+y1)) + ((x2+y2)+(x3+y3))
+#pragma unroll
+  for (int k = 0; k < kSumAcc; ++k) ax[k].merge(ay[k]);
+  ax[0].merge(ax[1]); ax[2].merge(ax[3]); ax[0].merge(ax[2]);
+  Acc<T> v = block_tree_sum(ax[0], smem);
 
   if (gridDim.x == 1) {
-    if (threadIdx.x == 0) { if (n & 1) v = v + in[n - 1]; *out = v; }
+    if (threadIdx.x == 0) { if (n & 1) v.add(in[n - 1]); *out = v.value(); }
     return;
   }
   if (threadIdx.x == 0) {
@@ -133,112 +169,17 @@ sum_kernel(const T* __restrict__ in, size_t n, T* __restrict__ partials, unsigne
   if (!is_last) return;
   __threadfence();
   // fixed-order reduction of the partials: thread t takes t, t+256, ... then the block tree
-  T acc = T(0);
-  for (unsigned i = threadIdx.x; i < gridDim.x; i += kSumThreads) acc = acc + __ldcg(partials + i);
+  Acc<T> acc; acc.zero();
+  for (unsigned i = threadIdx.x; i < gridDim.x; i += kSumThreads) {
+    const ulonglong2 raw = __ldcg(reinterpret_cast<const ulonglong2*>(partials + i));
+    acc.merge(*reinterpret_cast<const Acc<T>*>(&raw));
+  }
   acc = block_tree_sum(acc, smem);
   if (threadIdx.x == 0) {
-    if (n & 1) acc = acc + in[n - 1];
-    *out = acc;
+    if (n & 1) acc.add(in[n - 1]);
+    *out = acc.value();
     *ticket = 0;  // leave the workspace ready for the next launch on this stream
   }
-}
-
-
-// ---------------------------------------------------------------- TMA-staged variant ---------
-// Same reduction, but the input is staged through shared memory by the TMA engine instead of
-// per-thread loads: one elected thread issues cp.async.bulk (1-D bulk copy, SASS UBLKCP) of a
-// 16 KB chunk into a 4-deep ring of shared-memory stages, completion is signalled on an mbarrier
-// (expect-tx bytes), and the 256 threads read the stage with conflict-free LDS.128.  Bytes in
-// flight per SM no longer depend on registers or occupancy: 3 resident blocks x 4 stages x 16 KB
-// = 192 KB.  Requires a 16-byte aligned input; the (< 2048-element) tail is folded in by the last
-// block.  Fixed shape (444 blocks, static chunk -> block map) => deterministic like sum_kernel.
-namespace cde = cuda::device::experimental;
-using block_barrier = cuda::barrier<cuda::thread_scope_block>;
-
-constexpr int kTmaStages = 4;
-constexpr int kTmaChunkElems = 2048;  // 16 KB of 8-byte elements
-constexpr int kTmaBlocks = 148 * 3;
-
-template <typename T>
-__global__ void __launch_bounds__(kSumThreads)
-sum_tma_kernel(const T* __restrict__ in, size_t n, T* __restrict__ partials, unsigned* __restrict__ ticket, T* __restrict__ out) {
-  extern __shared__ __align__(128) unsigned char tma_smem[];
-  T(*buf)[kTmaChunkElems] = reinterpret_cast<T(*)[kTmaChunkElems]>(tma_smem);
-#pragma nv_diag_suppress static_var_with_dynamic_init
-  __shared__ block_barrier bar[kTmaStages];
-  __shared__ T smem[8];
-  __shared__ bool is_last;
-  const size_t n_chunks = n / kTmaChunkElems;
-  constexpr unsigned kBytes = kTmaChunkElems * sizeof(T);
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int s = 0; s < kTmaStages; ++s) init(&bar[s], kSumThreads);
-    cde::fence_proxy_async_shared_cta();
-  }
-  __syncthreads();
-  block_barrier::arrival_token token[kTmaStages];
-  auto issue = [&](int s, size_t chunk) {
-    if (threadIdx.x == 0) {
-      cde::cp_async_bulk_global_to_shared(buf[s], in + chunk * kTmaChunkElems, kBytes, bar[s]);
-      token[s] = cuda::device::barrier_arrive_tx(bar[s], 1, kBytes);
-    } else {
-      token[s] = bar[s].arrive();
-    }
-  };
-#pragma unroll
-  for (int s = 0; s < kTmaStages; ++s) {
-    const size_t chunk = blockIdx.x + (size_t)s * gridDim.x;
-    if (chunk < n_chunks) issue(s, chunk);
-  }
-  T ax[kSumAcc], ay[kSumAcc];
-#pragma unroll
-  for (int k = 0; k < kSumAcc; ++k) { ax[k] = T(0); ay[k] = T(0); }
-  for (size_t base = blockIdx.x; base < n_chunks; base += (size_t)kTmaStages * gridDim.x) {
-#pragma unroll
-    for (int s = 0; s < kTmaStages; ++s) {
-      const size_t chunk = base + (size_t)s * gridDim.x;
-      if (chunk >= n_chunks) break;
-      bar[s].wait(std::move(token[s]));
-      const ulonglong2* v2 = reinterpret_cast<const ulonglong2*>(buf[s]);
-#pragma unroll
-      for (int k = 0; k < kTmaChunkElems / 2 / kSumThreads; ++k) {  // 4 pairs per thread
-        const ulonglong2 v = v2[k * kSumThreads + threadIdx.x];
-        ax[k % kSumAcc] = ax[k % kSumAcc] + *reinterpret_cast<const T*>(&v.x);
-        ay[k % kSumAcc] = ay[k % kSumAcc] + *reinterpret_cast<const T*>(&v.y);
-      }
-      __syncthreads();  // every thread is done with stage s before it is refilled
-      const size_t next = chunk + (size_t)kTmaStages * gridDim.x;
-      if (next < n_chunks) issue(s, next);
-    }
-  }
-  T v = ((ax[0] + ay[0]) + (ax[1] + ay[1])) + ((ax[2] + ay[2]) + (ax[3] + ay[3]));
-  v = block_tree_sum(v, smem);
-  if (threadIdx.x == 0) {
-    partials[blockIdx.x] = v;
-    __threadfence();
-    const unsigned t = atomicAdd(ticket, 1u);
-    is_last = (t == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  T acc = T(0);
-  for (unsigned i = threadIdx.x; i < gridDim.x; i += kSumThreads) acc = acc + __ldcg(partials + i);
-  acc = block_tree_sum(acc, smem);
-  // tail (< one chunk): thread t takes elements t, t+256, ... of the remainder, fixed tree again
-  T tail = T(0);
-  for (size_t i = n_chunks * kTmaChunkElems + threadIdx.x; i < n; i += kSumThreads) tail = tail + in[i];
-  tail = block_tree_sum(tail, smem);
-  if (threadIdx.x == 0) {
-    *out = acc + tail;
-    *ticket = 0;
-  }
-}
-
-static bool sum_use_tma() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("AG_SUM_TMA"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v == 1;
 }
 
 // Reference association order (float64_avx2_amd64.s:36-43,86-174): 32 interleaved serial
@@ -290,21 +231,11 @@ static ag_status launch_sum(const T* d_in, size_t n, T* d_res, cudaStream_t st) 
   Workspace* ws;
   AG_TRY(get_workspace(st, &ws));
   const bool aligned = (reinterpret_cast<uintptr_t>(d_in) & 15) == 0;
-  if (sum_use_tma() && aligned && n >= (size_t)kTmaChunkElems * kTmaBlocks) {
-    constexpr size_t smem = (size_t)kTmaStages * kTmaChunkElems * sizeof(T);
-    static std::atomic<bool> attr{false};
-    if (!attr.load()) {
-      AG_CUDA_TRY(cudaFuncSetAttribute((const void*)sum_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr.store(true);
-    }
-    sum_tma_kernel<T><<<kTmaBlocks, kSumThreads, smem, st>>>(d_in, n, (T*)ws->partials, ws->ticket, d_res);
-    return check_launch("sum_tma_kernel");
-  }
-  const int grid = sum_grid(n >> 1);
+  const int grid = sum_grid<T>(n >> 1);
   if (aligned)
-    sum_kernel<T, true><<<grid, kSumThreads, 0, st>>>(d_in, n, (T*)ws->partials, ws->ticket, d_res);
+    sum_kernel<T, true><<<grid, kSumThreads, 0, st>>>(d_in, n, (Acc<T>*)ws->partials, ws->ticket, d_res);
   else
-    sum_kernel<T, false><<<grid, kSumThreads, 0, st>>>(d_in, n, (T*)ws->partials, ws->ticket, d_res);
+    sum_kernel<T, false><<<grid, kSumThreads, 0, st>>>(d_in, n, (Acc<T>*)ws->partials, ws->ticket, d_res);
   return check_launch("sum_kernel");
 }
 

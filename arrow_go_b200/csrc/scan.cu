@@ -35,7 +35,6 @@
 // rounding of the same order as the reference's own otherwise.
 #include "common.cuh"
 
-#include <stdlib.h>
 #include <limits>
 
 namespace ag {
@@ -535,522 +534,6 @@ cumsum_kernel(const CumsumParams p) {
   }
 }
 
-// ---------------------------------------------------------------- TMA-fed variant -----------
-// Same scan, but tiles travel through a ring of shared-memory stages moved by the TMA engine
-// (cp.async.bulk, mbarrier complete_tx; SASS UBLKCP): loads are issued kTmaStages-1 tiles ahead
-// of the tile being scanned, results go back into the stage in place and leave with ONE bulk
-// store per tile.  Nothing the threads do — the scans, the look-back wait, the barrier — stops
-// HBM traffic any more, and no registers are spent on staging.  The stage holds the tile exactly
-// as it lies in memory; lane l owns bytes [l*128, l*128+128) of its warp's 4 KB segment and reads
-// the eight 16-byte chunks in the rotated order (c + l) & 7, which touches every bank once per
-// quarter warp without a swizzled copy; chunk sums are put back in order with 8x8 predicated adds.
-// 4- and 8-byte types with 16-byte aligned operands; everything else uses cumsum_kernel.
-// Opt-in (AG_SCAN_TMA=1): it measured the same as the register-prefetch kernel (see launch_cumsum).
-constexpr int kTmaScanStages = 2;   // stage t+1 is refilled while tile t is in its look-back
-constexpr int kTmaScanBlocksPerSM = 3;  // 64 KB of ring per block
-
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@!p bra WAIT_%=;\n"
-      "}\n" ::"r"(smem_u32(b)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void* sdst, const void* gsrc, unsigned bytes, unsigned long long* b) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)), "l"(gsrc),
-               "r"(bytes), "r"(smem_u32(b))
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_1d(void* gdst, const void* ssrc, unsigned bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-template <int kPending>
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-template <typename T, bool kHasValid, bool kChecked>
-__global__ void __launch_bounds__(kScThreads, kTmaScanBlocksPerSM)
-cumsum_tma_kernel(const CumsumParams p) {
-  using P = typename PolSel<T, kChecked>::type;
-  using A = typename P::A;
-  constexpr int N = 16 / sizeof(T);
-  constexpr int kTileRows = kScTileBytes / sizeof(T);
-  constexpr int kSegRows = kTileRows / kScWarps;
-  constexpr int E = kScRows * N;  // <= 32 for the types routed here
-  static_assert(E <= 32, "the TMA variant keeps a lane's validity bits in one word");
-  extern __shared__ __align__(128) unsigned char s_ring[];  // kTmaScanStages x 32 KB
-  __shared__ unsigned long long s_bar[kTmaScanStages];
-  __shared__ unsigned long long s_warp_lo[kScWarps];
-  __shared__ int s_warp_hi[kScWarps];
-  __shared__ unsigned long long s_excl_lo;
-  __shared__ int s_excl_hi;
-  __shared__ CumsumState s_state;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const T* __restrict__ in = reinterpret_cast<const T*>(p.in);
-  T* __restrict__ out = reinterpret_cast<T*>(p.out);
-
-  if (threadIdx.x == 0) {
-    s_state = *p.state;
-#pragma unroll
-    for (int s = 0; s < kTmaScanStages; ++s) mbar_init(&s_bar[s], 1);
-    fence_async_smem();
-  }
-  __syncthreads();
-  const bool dead = !p.skip_nulls && s_state.encountered_null != 0;
-  int64_t limit = p.n;
-  if (dead) limit = 0;
-  else if (kHasValid && !p.skip_nulls) limit = *p.first_null;
-  const A start = P::from_state(s_state);
-  long long my_bad = AG_NO_ERROR_POS;
-  const int64_t vlo = p.voff >> 3, vhi = (p.voff + p.n + 7) >> 3;
-  const int64_t full_tiles = p.n / kTileRows;  // tiles below this index are complete: TMA moves them
-
-  auto issue_load = [&](int64_t it) {  // thread 0 only
-    const int64_t tile = blockIdx.x + it * (int64_t)gridDim.x;
-    if (tile < full_tiles) {
-      const int s = (int)(it % kTmaScanStages);
-      mbar_expect_tx(&s_bar[s], kScTileBytes);
-      tma_load_1d(s_ring + (size_t)s * kScTileBytes, in + tile * kTileRows, kScTileBytes, &s_bar[s]);
-    }
-  };
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int j = 0; j < kTmaScanStages - 1; ++j) issue_load(j);
-  }
-
-  int64_t it = 0;
-  for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-    const int s = (int)(it % kTmaScanStages);
-    unsigned char* stage = s_ring + (size_t)s * kScTileBytes;
-    const bool full = tile < full_tiles;
-    const int64_t row0 = tile * kTileRows + (int64_t)warp * kSegRows;
-    const int64_t t0 = row0 + (int64_t)lane * E;
-    if (full) {
-      mbar_wait(&s_bar[s], (unsigned)((it / kTmaScanStages) & 1));
-    } else {  // the last, partial tile: plain loads into the stage (zero-padded)
-      T* st = reinterpret_cast<T*>(stage);
-      for (int i = threadIdx.x; i < kTileRows; i += kScThreads) {
-        const int64_t r = tile * kTileRows + i;
-        st[i] = r < p.n ? in[r] : T(0);
-      }
-      __syncthreads();
-    }
-    // ---- this lane's 128 bytes, chunk (c + lane) & 7 at step c: conflict-free on the linear tile ----
-    uint4* seg = reinterpret_cast<uint4*>(stage) + warp * (kScRows * 32);
-    uint4 raw[kScRows];
-#pragma unroll
-    for (int c = 0; c < kScRows; ++c) raw[c] = seg[lane * 8 + ((c + lane) & 7)];
-    unsigned vb = 0xffffffffu;
-    if (kHasValid) vb = (t0 < p.n) ? bitmap_load32(p.valid, p.voff + t0, vlo, vhi) : 0u;
-    {
-      const int64_t room = limit - t0;
-      if (room < 32) vb &= (room <= 0) ? 0u : ((1u << (int)room) - 1u);
-      if (E < 32) vb &= (1u << (E & 31)) - 1u;
-    }
-    // ---- chunk sums (rotated order), lane total, one warp scan ------------------------------------
-    A csum[kScRows];
-    A tot = P::zero();
-#pragma unroll
-    for (int c = 0; c < kScRows; ++c) {
-      const unsigned cb = (vb >> (((c + lane) & 7) * N)) & ((1u << N) - 1u);
-      A a = P::zero();
-#pragma unroll
-      for (int e = 0; e < N; ++e) if ((cb >> e) & 1u) a = P::add_elem(a, reinterpret_cast<const T*>(&raw[c])[e]);
-      csum[c] = a;
-      tot = P::add(tot, a);
-    }
-    A incl = tot;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const A up = P::shfl_up(incl, d);
-      if (lane >= d) incl = P::add(up, incl);
-    }
-    A lane_excl = P::shfl_up(incl, 1);
-    if (lane == 0) lane_excl = P::zero();
-    const A carry = P::shfl(incl, 31);
-    {
-      unsigned w[3] = {0u, 0u, 0u};
-      P::to_words(carry, w);
-      if (lane == 0) { s_warp_lo[warp] = (unsigned long long)w[0] | ((unsigned long long)w[1] << 32); s_warp_hi[warp] = (int)w[2]; }
-    }
-    __syncthreads();
-    A warp_excl = P::zero(), tile_total = P::zero();
-#pragma unroll
-    for (int wi = 0; wi < kScWarps; ++wi) {
-      const unsigned w[3] = {(unsigned)s_warp_lo[wi], (unsigned)(s_warp_lo[wi] >> 32), (unsigned)s_warp_hi[wi]};
-      const A t = P::from_words(w);
-      if (wi == warp) warp_excl = tile_total;
-      tile_total = P::add(tile_total, t);
-    }
-    if (warp == 0 && lane == 0) {
-      unsigned w[3] = {0u, 0u, 0u};
-      P::to_words(tile_total, w);
-#pragma unroll
-      for (int k = 0; k < P::K; ++k) st_word(p.agg + tile * P::K + k, w[k]);
-    }
-    // refill the ring now — the bulk store of the previous tile has long released its stage — so the
-    // next tile's bytes travel while this one sits in its look-back
-    if (threadIdx.x == 0) {
-      tma_store_wait_read<0>();
-      issue_load(it + kTmaScanStages - 1);
-    }
-    // exclusive offset of each chunk inside the lane: the sums of the chunks that precede it in memory
-    A coff[kScRows];
-#pragma unroll
-    for (int c = 0; c < kScRows; ++c) {
-      A a = P::zero();
-#pragma unroll
-      for (int c2 = 0; c2 < kScRows; ++c2)
-        if (((c2 + lane) & 7) < ((c + lane) & 7)) a = P::add(a, csum[c2]);
-      coff[c] = a;
-    }
-    // running sums relative to the tile start (unchecked) while warp 0 is in the look-back
-    auto local_pass = [&]() {
-      const A lbase = P::add(warp_excl, lane_excl);
-#pragma unroll
-      for (int c = 0; c < kScRows; ++c) {
-        const unsigned cb = (vb >> (((c + lane) & 7) * N)) & ((1u << N) - 1u);
-        A run = P::add(lbase, coff[c]);
-        T* o = reinterpret_cast<T*>(&raw[c]);
-#pragma unroll
-        for (int e = 0; e < N; ++e) {
-          if ((cb >> e) & 1u) { run = P::add_elem(run, o[e]); o[e] = P::value(run); }
-          else o[e] = T(0);
-        }
-      }
-    };
-    if (!kChecked && warp != 0) local_pass();
-    if (warp == 0) {
-      const A excl = scan_lookback<P>(p, tile, tile_total, start, lane);
-      if (lane == 0) {
-        unsigned w[3] = {0u, 0u, 0u};
-        P::to_words(excl, w);
-        s_excl_lo = (unsigned long long)w[0] | ((unsigned long long)w[1] << 32);
-        s_excl_hi = (int)w[2];
-        if (tile == p.n_tiles - 1) {
-          CumsumState ns = s_state;
-          P::to_state(P::add(excl, tile_total), &ns);
-          if (kHasValid && *p.first_null < p.n) ns.encountered_null = 1;
-          *p.state = ns;
-        }
-      }
-    }
-    __syncthreads();
-    A tile_excl;
-    {
-      const unsigned w[3] = {(unsigned)s_excl_lo, (unsigned)(s_excl_lo >> 32), (unsigned)s_excl_hi};
-      tile_excl = P::from_words(w);
-    }
-    if constexpr (kChecked) {
-      const A lbase = P::add(P::add(tile_excl, warp_excl), lane_excl);
-#pragma unroll
-      for (int c = 0; c < kScRows; ++c) {
-        const int j = (c + lane) & 7;
-        const unsigned cb = (vb >> (j * N)) & ((1u << N) - 1u);
-        A run = P::add(lbase, coff[c]);
-        T* o = reinterpret_cast<T*>(&raw[c]);
-#pragma unroll
-        for (int e = 0; e < N; ++e) {
-          if ((cb >> e) & 1u) {
-            run = P::add_elem(run, o[e]);
-            o[e] = P::value(run);
-            const long long row = t0 + j * N + e;
-            if (P::out_of_range(run) && row < my_bad) my_bad = row;
-          } else {
-            o[e] = T(0);
-          }
-        }
-      }
-    } else {
-      if (warp == 0) local_pass();
-      const T off = P::value(tile_excl);
-#pragma unroll
-      for (int c = 0; c < kScRows; ++c) {
-        const unsigned cb = (vb >> (((c + lane) & 7) * N)) & ((1u << N) - 1u);
-        T* o = reinterpret_cast<T*>(&raw[c]);
-#pragma unroll
-        for (int e = 0; e < N; ++e) if ((cb >> e) & 1u) o[e] = P::offset_add(off, o[e]);
-      }
-    }
-    // ---- results back into the stage (same places), one bulk store for the tile -------------------
-#pragma unroll
-    for (int c = 0; c < kScRows; ++c) seg[lane * 8 + ((c + lane) & 7)] = raw[c];
-    if (full) {
-      fence_async_smem();  // make the generic-proxy writes visible to the TMA engine
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        tma_store_1d(out + tile * kTileRows, stage, kScTileBytes);
-      }
-    } else {
-      __syncthreads();
-      const T* st = reinterpret_cast<const T*>(stage);
-      for (int i = threadIdx.x; i < kTileRows; i += kScThreads) {
-        const int64_t r = tile * kTileRows + i;
-        if (r < p.n) out[r] = st[i];
-      }
-    }
-  }
-  if (threadIdx.x == 0) tma_store_wait_read<0>();  // shared memory must outlive the last bulk store
-  if (kChecked) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      const long long o = __shfl_xor_sync(0xffffffffu, my_bad, d);
-      my_bad = o < my_bad ? o : my_bad;
-    }
-    if (lane == 0 && my_bad != AG_NO_ERROR_POS) atomicMin(p.first_bad, my_bad);
-  }
-}
-
-// ---------------------------------------------------------------- two-phase pipelined variant --
-// cumsum_tma_kernel with each tile's work split in two phases that a block interleaves ACROSS tiles:
-//   A(k): wait for the tile, per-lane / warp / block totals, publish the tile aggregate, remember the
-//         lane's offset inside the tile;
-//   B(k): look-back (the aggregates it needs were published a whole A-phase ago, so the first batch of
-//         polls normally finds them all), running sums, bulk store.
-// The block runs A(k), refills the ring, then B(k-1): the publish -> poll round trip through L2 — the
-// one thing every tile has to sit through — is covered by the next tile's A phase instead of a barrier
-// with seven idle warps (ncu on the single-phase kernels: 45-50 % of stall samples there).  The tile
-// stays in its shared-memory stage between the phases; B re-derives the chunk sums from it.
-constexpr int kPipeStages = 3;
-
-template <typename T, bool kHasValid, bool kChecked>
-__global__ void __launch_bounds__(kScThreads, 2)
-cumsum_pipe_kernel(const CumsumParams p) {
-  using P = typename PolSel<T, kChecked>::type;
-  using A = typename P::A;
-  constexpr int N = 16 / sizeof(T);
-  constexpr int kTileRows = kScTileBytes / sizeof(T);
-  constexpr int kSegRows = kTileRows / kScWarps;
-  constexpr int E = kScRows * N;
-  static_assert(E <= 32, "a lane's validity bits live in one word");
-  extern __shared__ __align__(128) unsigned char s_ring[];  // kPipeStages x 32 KB
-  __shared__ unsigned long long s_bar[kPipeStages];
-  __shared__ unsigned long long s_base_lo[kPipeStages][kScThreads];  // lane offset inside the tile (phase A -> B)
-  __shared__ int s_base_hi[kPipeStages][kScThreads];
-  __shared__ unsigned s_vb[kPipeStages][kScThreads];
-  __shared__ unsigned long long s_tot_lo[kPipeStages];
-  __shared__ int s_tot_hi[kPipeStages];
-  __shared__ unsigned long long s_warp_lo[kScWarps];
-  __shared__ int s_warp_hi[kScWarps];
-  __shared__ unsigned long long s_excl_lo;
-  __shared__ int s_excl_hi;
-  __shared__ CumsumState s_state;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const T* __restrict__ in = reinterpret_cast<const T*>(p.in);
-  T* __restrict__ out = reinterpret_cast<T*>(p.out);
-
-  if (threadIdx.x == 0) {
-    s_state = *p.state;
-#pragma unroll
-    for (int s = 0; s < kPipeStages; ++s) mbar_init(&s_bar[s], 1);
-    fence_async_smem();
-  }
-  __syncthreads();
-  const bool dead = !p.skip_nulls && s_state.encountered_null != 0;
-  int64_t limit = p.n;
-  if (dead) limit = 0;
-  else if (kHasValid && !p.skip_nulls) limit = *p.first_null;
-  const A start = P::from_state(s_state);
-  long long my_bad = AG_NO_ERROR_POS;
-  const int64_t vlo = p.voff >> 3, vhi = (p.voff + p.n + 7) >> 3;
-  const int64_t full_tiles = p.n / kTileRows;
-  const int64_t n_my = (p.n_tiles - 1 - (int64_t)blockIdx.x) / (int64_t)gridDim.x + 1;  // tiles of this block (>= 1)
-
-  auto issue_load = [&](int64_t k) {  // thread 0 only
-    const int64_t tile = blockIdx.x + k * (int64_t)gridDim.x;
-    if (k < n_my && tile < full_tiles) {
-      const int s = (int)(k % kPipeStages);
-      mbar_expect_tx(&s_bar[s], kScTileBytes);
-      tma_load_1d(s_ring + (size_t)s * kScTileBytes, in + tile * kTileRows, kScTileBytes, &s_bar[s]);
-    }
-  };
-  if (threadIdx.x == 0) issue_load(0);
-
-  for (int64_t k = 0; k <= n_my; ++k) {
-    // ================================ phase A of tile k ===========================================
-    if (k < n_my) {
-      const int64_t tile = blockIdx.x + k * (int64_t)gridDim.x;
-      const int s = (int)(k % kPipeStages);
-      unsigned char* stage = s_ring + (size_t)s * kScTileBytes;
-      const int64_t t0 = tile * kTileRows + (int64_t)warp * kSegRows + (int64_t)lane * E;
-      if (tile < full_tiles) {
-        mbar_wait(&s_bar[s], (unsigned)((k / kPipeStages) & 1));
-      } else {
-        T* st = reinterpret_cast<T*>(stage);
-        for (int i = threadIdx.x; i < kTileRows; i += kScThreads) {
-          const int64_t r = tile * kTileRows + i;
-          st[i] = r < p.n ? in[r] : T(0);
-        }
-        __syncthreads();
-      }
-      const uint4* seg = reinterpret_cast<const uint4*>(stage) + warp * (kScRows * 32);
-      unsigned vb = 0xffffffffu;
-      if (kHasValid) vb = (t0 < p.n) ? bitmap_load32(p.valid, p.voff + t0, vlo, vhi) : 0u;
-      {
-        const int64_t room = limit - t0;
-        if (room < 32) vb &= (room <= 0) ? 0u : ((1u << (int)room) - 1u);
-        if (E < 32) vb &= (1u << (E & 31)) - 1u;
-      }
-      A tot = P::zero();
-#pragma unroll
-      for (int c = 0; c < kScRows; ++c) {
-        const uint4 q = seg[lane * 8 + ((c + lane) & 7)];
-        const unsigned cb = (vb >> (((c + lane) & 7) * N)) & ((1u << N) - 1u);
-#pragma unroll
-        for (int e = 0; e < N; ++e) if ((cb >> e) & 1u) tot = P::add_elem(tot, reinterpret_cast<const T*>(&q)[e]);
-      }
-      A incl = tot;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const A up = P::shfl_up(incl, d);
-        if (lane >= d) incl = P::add(up, incl);
-      }
-      A lane_excl = P::shfl_up(incl, 1);
-      if (lane == 0) lane_excl = P::zero();
-      {
-        unsigned w[3] = {0u, 0u, 0u};
-        P::to_words(P::shfl(incl, 31), w);
-        if (lane == 0) { s_warp_lo[warp] = (unsigned long long)w[0] | ((unsigned long long)w[1] << 32); s_warp_hi[warp] = (int)w[2]; }
-      }
-      __syncthreads();
-      A warp_excl = P::zero(), tile_total = P::zero();
-#pragma unroll
-      for (int wi = 0; wi < kScWarps; ++wi) {
-        const unsigned w[3] = {(unsigned)s_warp_lo[wi], (unsigned)(s_warp_lo[wi] >> 32), (unsigned)s_warp_hi[wi]};
-        const A t = P::from_words(w);
-        if (wi == warp) warp_excl = tile_total;
-        tile_total = P::add(tile_total, t);
-      }
-      {
-        unsigned w[3] = {0u, 0u, 0u};
-        P::to_words(tile_total, w);
-        if (threadIdx.x == 0) {
-#pragma unroll
-          for (int kk = 0; kk < P::K; ++kk) st_word(p.agg + tile * P::K + kk, w[kk]);
-          s_tot_lo[s] = (unsigned long long)w[0] | ((unsigned long long)w[1] << 32);
-          s_tot_hi[s] = (int)w[2];
-        }
-        unsigned wb[3] = {0u, 0u, 0u};
-        P::to_words(P::add(warp_excl, lane_excl), wb);
-        s_base_lo[s][threadIdx.x] = (unsigned long long)wb[0] | ((unsigned long long)wb[1] << 32);
-        s_base_hi[s][threadIdx.x] = (int)wb[2];
-        s_vb[s][threadIdx.x] = vb;
-      }
-      __syncthreads();  // s_warp_* may be rewritten by the next phase A; s_tot_* is read by warp 0 in phase B
-    }
-    // ================================ refill the ring ==============================================
-    // tile k+1 goes into the stage tile k-2 used; its bulk store was issued a whole phase A ago
-    if (threadIdx.x == 0) {
-      tma_store_wait_read<0>();
-      issue_load(k + 1);
-    }
-    // ================================ phase B of tile k-1 ==========================================
-    if (k >= 1) {
-      const int64_t j = k - 1;
-      const int64_t tile = blockIdx.x + j * (int64_t)gridDim.x;
-      const int s = (int)(j % kPipeStages);
-      unsigned char* stage = s_ring + (size_t)s * kScTileBytes;
-      const bool full = tile < full_tiles;
-      const int64_t t0 = tile * kTileRows + (int64_t)warp * kSegRows + (int64_t)lane * E;
-      A tile_total;
-      {
-        const unsigned w[3] = {(unsigned)s_tot_lo[s], (unsigned)(s_tot_lo[s] >> 32), (unsigned)s_tot_hi[s]};
-        tile_total = P::from_words(w);
-      }
-      if (warp == 0) {
-        const A excl = scan_lookback<P>(p, tile, tile_total, start, lane);
-        if (lane == 0) {
-          unsigned w[3] = {0u, 0u, 0u};
-          P::to_words(excl, w);
-          s_excl_lo = (unsigned long long)w[0] | ((unsigned long long)w[1] << 32);
-          s_excl_hi = (int)w[2];
-          if (tile == p.n_tiles - 1) {
-            CumsumState ns = s_state;
-            P::to_state(P::add(excl, tile_total), &ns);
-            if (kHasValid && *p.first_null < p.n) ns.encountered_null = 1;
-            *p.state = ns;
-          }
-        }
-      }
-      __syncthreads();
-      A tile_excl, lbase;
-      {
-        const unsigned w[3] = {(unsigned)s_excl_lo, (unsigned)(s_excl_lo >> 32), (unsigned)s_excl_hi};
-        tile_excl = P::from_words(w);
-        const unsigned wb[3] = {(unsigned)s_base_lo[s][threadIdx.x], (unsigned)(s_base_lo[s][threadIdx.x] >> 32), (unsigned)s_base_hi[s][threadIdx.x]};
-        lbase = P::add(tile_excl, P::from_words(wb));
-      }
-      const unsigned vb = s_vb[s][threadIdx.x];
-      uint4* seg = reinterpret_cast<uint4*>(stage) + warp * (kScRows * 32);
-      uint4 raw[kScRows];
-      A csum[kScRows];
-#pragma unroll
-      for (int c = 0; c < kScRows; ++c) {
-        raw[c] = seg[lane * 8 + ((c + lane) & 7)];
-        const unsigned cb = (vb >> (((c + lane) & 7) * N)) & ((1u << N) - 1u);
-        A a = P::zero();
-#pragma unroll
-        for (int e = 0; e < N; ++e) if ((cb >> e) & 1u) a = P::add_elem(a, reinterpret_cast<const T*>(&raw[c])[e]);
-        csum[c] = a;
-      }
-#pragma unroll
-      for (int c = 0; c < kScRows; ++c) {
-        const int jj = (c + lane) & 7;
-        A run = lbase;  // + the sums of the chunks that precede chunk jj in memory
-#pragma unroll
-        for (int c2 = 0; c2 < kScRows; ++c2)
-          if (((c2 + lane) & 7) < jj) run = P::add(run, csum[c2]);
-        const unsigned cb = (vb >> (jj * N)) & ((1u << N) - 1u);
-        T* o = reinterpret_cast<T*>(&raw[c]);
-#pragma unroll
-        for (int e = 0; e < N; ++e) {
-          if ((cb >> e) & 1u) {
-            run = P::add_elem(run, o[e]);
-            o[e] = P::value(run);
-            if (kChecked) { const long long row = t0 + jj * N + e; if (P::out_of_range(run) && row < my_bad) my_bad = row; }
-          } else {
-            o[e] = T(0);
-          }
-        }
-      }
-#pragma unroll
-      for (int c = 0; c < kScRows; ++c) seg[lane * 8 + ((c + lane) & 7)] = raw[c];
-      if (full) {
-        fence_async_smem();
-        __syncthreads();
-        if (threadIdx.x == 0) tma_store_1d(out + tile * kTileRows, stage, kScTileBytes);
-      } else {
-        __syncthreads();
-        const T* st = reinterpret_cast<const T*>(stage);
-        for (int i = threadIdx.x; i < kTileRows; i += kScThreads) {
-          const int64_t r = tile * kTileRows + i;
-          if (r < p.n) out[r] = st[i];
-        }
-        __syncthreads();
-      }
-    }
-  }
-  if (threadIdx.x == 0) tma_store_wait_read<0>();
-  if (kChecked) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      const long long o = __shfl_xor_sync(0xffffffffu, my_bad, d);
-      my_bad = o < my_bad ? o : my_bad;
-    }
-    if (lane == 0 && my_bad != AG_NO_ERROR_POS) atomicMin(p.first_bad, my_bad);
-  }
-}
-
 // first 0 bit of validity[voff, voff+n): one thread per 32 rows, atomicMin into *first_null (pre-set to n)
 __global__ void __launch_bounds__(256)
 first_null_kernel(const uint8_t* __restrict__ valid, int64_t voff, int64_t n, long long* first_null) {
@@ -1148,36 +631,10 @@ ag_status launch_cumsum(CumsumParams& p, cudaStream_t st) {
     if (vec) fn = p.valid ? (const void*)cumsum_kernel<T, true, true, false> : (const void*)cumsum_kernel<T, true, false, false>;
     else fn = p.valid ? (const void*)cumsum_kernel<T, false, true, false> : (const void*)cumsum_kernel<T, false, false, false>;
   }
-  size_t dyn_smem = 0;
-  if constexpr (sizeof(T) >= 4) {
-    // opt-in (AG_SCAN_TMA=1, read per call so a test can flip it): measured 433 us vs 437 us for the
-    // register-prefetch kernel at 100M int64 rows — the scan is bound by the look-back dependency between
-    // concurrently running tiles, not by the load path, so the simpler kernel stays the default
-    const char* e = getenv("AG_SCAN_TMA");
-    const bool use_tma = e && e[0] == '1';
-    const bool use_pipe = e && e[0] == '2';
-    if (vec && use_pipe) {
-      if (chk) fn = p.valid ? (const void*)cumsum_pipe_kernel<T, true, !IsFp<T>::v> : (const void*)cumsum_pipe_kernel<T, false, !IsFp<T>::v>;
-      else fn = p.valid ? (const void*)cumsum_pipe_kernel<T, true, false> : (const void*)cumsum_pipe_kernel<T, false, false>;
-      dyn_smem = (size_t)kPipeStages * kScTileBytes;
-      AG_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
-    } else if (vec && use_tma) {
-      if (chk) fn = p.valid ? (const void*)cumsum_tma_kernel<T, true, !IsFp<T>::v> : (const void*)cumsum_tma_kernel<T, false, !IsFp<T>::v>;
-      else fn = p.valid ? (const void*)cumsum_tma_kernel<T, true, false> : (const void*)cumsum_tma_kernel<T, false, false>;
-      dyn_smem = (size_t)kTmaScanStages * kScTileBytes;
-      AG_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
-    }
-  }
-  int per_sm = 0;
-  if (dyn_smem) {
-    AG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kScThreads, dyn_smem));
-    if (per_sm < 1) AG_FAIL(AG_ERR_CUDA, "cumulative_sum: the TMA scan kernel does not fit on an SM");
-  } else {
-    per_sm = blocks_per_sm(fn, kScThreads);
-  }
+  const int per_sm = blocks_per_sm(fn, kScThreads);
   const int64_t cap = (int64_t)sm_count() * per_sm;
   const int grid = (int)(p.n_tiles < cap ? p.n_tiles : cap);
-  AG_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kScThreads), args, dyn_smem, st));
+  AG_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kScThreads), args, 0, st));
   return check_launch("cumsum_kernel");
 }
 

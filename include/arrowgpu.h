@@ -426,6 +426,14 @@ ag_status ag_take_primitive_dev(int bit_width, const void* d_vals, const uint8_t
                                 int idx_width, int idx_signed, const void* d_idx, const uint8_t* d_ivalid, int64_t ioff,
                                 int64_t n, int bounds_check, void* d_out, uint8_t* d_out_valid,
                                 int64_t* d_bad_pos, ag_stream_t s);
+/* Routing of large takes (results never depend on it).  Random indices into a values table far larger
+ * than L2 go through the windowed path (partition indices by 16 MB table window -> gather window by
+ * window out of L2 -> un-permute); sorted / clustered indices and small calls use the direct gather
+ * (the reference switches loop shape the same way, vector_selection.go:897-911).
+ * mode: 0 automatic (default), 1 always direct, 2 windowed whenever the shapes allow it.
+ * min_rows / min_table_bytes / window_bytes: thresholds of the automatic mode and the window size;
+ * values <= 0 keep the current setting.  Process-wide. */
+ag_status ag_take_set_policy(int mode, int64_t min_rows, int64_t min_table_bytes, int64_t window_bytes);
 
 /* ================================================================================= *
  * Parity helpers for inputs too large to bring back to the host:

@@ -238,28 +238,6 @@ def test_gpu_large_crosses_super_group(ag, cpu, t):
 
 
 @gpu
-@pytest.mark.parametrize("variant", ["1", "2"], ids=["tma", "tma-two-phase"])
-def test_gpu_tma_variant(ag, cpu, monkeypatch, variant):
-    """The TMA-fed kernels (AG_SCAN_TMA=1: cp.async.bulk ring + bulk stores; =2: the same with each tile's
-    work split in two phases interleaved across tiles) give the same bits as the default kernel."""
-    monkeypatch.setenv("AG_SCAN_TMA", variant)
-    rng = np.random.default_rng(31)
-    for t in (N.INT64, N.INT32, N.FLOAT64, N.FLOAT32, N.UINT64):
-        for n in (1, 4096, 4097, 100_003, (1 << 20) + 13):
-            x = rng.integers(-3, 4, n).astype(NP_OF[t]) if t in (N.FLOAT32, N.FLOAT64) else random_values(rng, t, n)
-            for valid in (None, rng.random(n) > 0.01):
-                for skip in (False, True):
-                    wst, wout, wv, wn, _ = oracle_chunks(cpu, t, [x], [valid], skip, False, 3)
-                    st, out, v, nulls, _ = gpu_chunks(ag, t, [x], [valid], skip, False, 3)
-                    assert st == 0 and np.array_equal(v, wv) and out.tobytes() == wout.tobytes() and nulls == wn, (TYPE_NAME[t], n, skip)
-    x = np.ones(300_007, dtype=np.int8 if False else np.int64)
-    x[200_000] = np.iinfo(np.int64).max
-    wst, _, _, _, wbad = oracle_chunks(cpu, N.INT64, [x], [None], False, True)
-    st, _, _, _, bad = gpu_chunks(ag, N.INT64, [x], [None], False, True)
-    assert st != 0 and wst != 0 and bad == wbad
-
-
-@gpu
 def test_gpu_chunked_state_carry(ag, cpu):
     rng = np.random.default_rng(77)
     for t in (N.INT64, N.INT32, N.FLOAT64):

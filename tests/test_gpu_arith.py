@@ -212,3 +212,93 @@ def test_unary_checked_matches_oracle(ag, cpu, type_id):
                     assert (same_float_class if isf else same_bits)(got, want)
                 else:
                     assert msg == "overflow" and gb.value == n // 2
+
+
+# ---------------------------------------------------------------------------------------------------------
+# The batched entry point the headline benchmark times: ag_arith_binary_spans[_dev] (one launch for every aligned span
+# of a chunked call, executor.go:598-623,757-863), checked directly against the reference's SIMD loop run span by span.
+def _spans_case(ag, ref, isa, type_id, op, shape, lens, offs, rng, host=False):
+    """lens: rows per span; offs: per span (l, r, out) element offsets into oversized buffers -> every operand of every
+    span gets its own 16-byte phase."""
+    dt = NP_OF[type_id]
+    isz = np.dtype(dt).itemsize
+    isf = type_id in (N.FLOAT32, N.FLOAT64)
+    total = int(sum(lens)) + 64 * len(lens) + 64
+    L = random_values(rng, type_id, total)
+    R = random_values(rng, type_id, total)
+    scal = random_values(rng, type_id, 1)
+    want = np.zeros(total, dtype=dt)
+    got_h = np.zeros(total, dtype=dt)
+    spans, pos = [], 0
+    for ln, (lo, ro, oo) in zip(lens, offs):
+        spans.append((pos + lo, pos + ro, pos + oo, ln))
+        pos += ln + 64
+    fn = getattr(ref, {N.SHAPE_AA: "arithmetic_binary_", N.SHAPE_AS: "arithmetic_arr_scalar_", N.SHAPE_SA: "arithmetic_scalar_arr_"}[shape] + isa)
+    for lp, rp, op_, ln in spans:
+        if ln:
+            fn(type_id, op, scal.ctypes.data if shape == N.SHAPE_SA else L.ctypes.data + lp * isz,
+               scal.ctypes.data if shape == N.SHAPE_AS else R.ctypes.data + rp * isz, want.ctypes.data + op_ * isz, ln)
+    cmp_ = same_float_class if isf else same_bits
+    if host:
+        table = N.span_table([(scal.ctypes.data if shape == N.SHAPE_SA else L.ctypes.data + lp * isz,
+                               scal.ctypes.data if shape == N.SHAPE_AS else R.ctypes.data + rp * isz, got_h.ctypes.data + op_ * isz, ln)
+                              for lp, rp, op_, ln in spans])
+        ag.call("ag_arith_binary_spans", type_id, op, shape, table, len(spans))
+        assert cmp_(got_h, want), (TYPE_NAME[type_id], op, shape, "host")
+        return
+    dL, dR, dO = Dev(L), Dev(R), Dev(np.zeros(total, dtype=dt))
+    table = N.span_table([(scal.ctypes.data if shape == N.SHAPE_SA else dL.ptr + lp * isz,
+                           scal.ctypes.data if shape == N.SHAPE_AS else dR.ptr + rp * isz, dO.ptr + op_ * isz, ln) for lp, rp, op_, ln in spans])
+    ag.call("ag_arith_binary_spans_dev", type_id, op, shape, table, len(spans), None)
+    ag.call("ag_stream_sync", None)
+    assert cmp_(dO.get(), want), (TYPE_NAME[type_id], op, shape, lens[:4], offs[:4])  # rows between spans stay 0: no stray write
+
+
+@pytest.mark.parametrize("type_id", ALL_TYPES, ids=lambda t: TYPE_NAME[t])
+@pytest.mark.parametrize("shape", [N.SHAPE_AA, N.SHAPE_AS, N.SHAPE_SA], ids=["aa", "as", "sa"])
+def test_spans_entry_point_vs_reference_simd(ag, ref, isa, type_id, shape):
+    rng = np.random.default_rng(0x5BA2 + type_id * 13 + shape)
+    isz = np.dtype(NP_OF[type_id]).itemsize
+    nvec = 16 // isz
+    # spans far longer than a tile (32 KB per operand), exactly a tile, one row short / long of a tile, tiny, empty
+    tile = 32768 // isz
+    lens = [5 * tile + 17, tile, tile - 1, tile + 1, 1, 0, 3, 2 * tile + nvec - 1, 70_001]
+    for trial in range(3):
+        if trial == 0:     # every operand on a 16-byte boundary
+            offs = [(0, 0, 0)] * len(lens)
+        elif trial == 1:   # one shared misalignment per span (what executeSpans produces: out, l, r all at pos*width)
+            offs = [(k % nvec,) * 3 for k in range(1, len(lens) + 1)]
+        else:              # independent phases per operand
+            offs = [tuple(int(x) for x in rng.integers(0, 2 * nvec, 3)) for _ in lens]
+        for op in (N.OP_ADD, N.OP_SUB_CHECKED, N.OP_MUL):
+            _spans_case(ag, ref, isa, type_id, op, shape, lens, offs, rng)
+    _spans_case(ag, ref, isa, type_id, N.OP_ADD, shape, lens, [tuple(int(x) for x in rng.integers(0, 2 * nvec, 3)) for _ in lens], rng, host=True)
+
+
+def test_spans_config2_layout_100m_rows_checksum(ag, cpu):
+    """BASELINE config 2 at full size: 100M float64 rows, left chunks of 1M rows and right chunks of 999,983 rows -> 200
+    spans into one contiguous output (the layout bench.py times).  Dataset E (integers stored as double: every sum is
+    exact) generated on the device; the output is checked by the order-sensitive checksum of SURVEY §8d against the
+    oracle's, and three 1M-row windows are compared bit for bit."""
+    n, lc, rc = 100_000_000, 1_000_000, 999_983
+    dl, dr, do = Dev(nbytes=n * 8), Dev(nbytes=n * 8), Dev(nbytes=n * 8)
+    ag.call("ag_generate_dev", 3, 0x94378165, -(1 << 20), 1 << 20, dl.ptr, n, None)
+    ag.call("ag_generate_dev", 3, 0x94378166, -(1 << 20), 1 << 20, dr.ptr, n, None)
+    spans, pos = [], 0
+    while pos < n:
+        ln = min(lc - pos % lc, rc - pos % rc, n - pos)
+        spans.append((dl.ptr + 8 * pos, dr.ptr + 8 * pos, do.ptr + 8 * pos, ln))
+        pos += ln
+    assert len(spans) == 200
+    ag.call("ag_arith_binary_spans_dev", N.FLOAT64, N.OP_ADD_CHECKED, N.SHAPE_AA, N.span_table(spans), len(spans), None)
+    ck = Dev(np.zeros(1, dtype=np.uint64))
+    ag.call("ag_checksum64_dev", do.ptr, n, ck.ptr, None)
+    ag.call("ag_stream_sync", None)
+    # oracle: regenerate both columns on the CPU (the generator's twin), add with the restatement, checksum
+    a, b, want = np.empty(n), np.empty(n), np.empty(n)
+    cpu.ref_generate(3, 0x94378165, -(1 << 20), 1 << 20, a.ctypes.data, n)
+    cpu.ref_generate(3, 0x94378166, -(1 << 20), 1 << 20, b.ctypes.data, n)
+    assert cpu.ref_arith_binary(N.FLOAT64, N.OP_ADD_CHECKED, 0, a.ctypes.data, b.ctypes.data, want.ctypes.data, n) == 0
+    assert int(ck.get()[0]) == cpu.ref_checksum64(want.ctypes.data, n)
+    for start in (0, 49_999_000, n - 1_000_000):
+        assert do.buf.to_numpy(np.float64, 1_000_000, start * 8).tobytes() == want[start:start + 1_000_000].tobytes()

@@ -81,23 +81,59 @@ def test_f64_reference_order_mode_bit_exact_on_general_data(ag, cpu, ref, n):
 
 
 @pytest.mark.parametrize("n", [8192, 100003, 1 << 20, 10_000_000])
-@pytest.mark.parametrize("dist", ["normal", "uniform"])
+@pytest.mark.parametrize("dist", ["normal", "uniform", "cancelling"])
 def test_f64_general_data_accuracy(ag, cpu, n, dist):
-    """Dataset G: tolerance stated in SURVEY §8d — the GPU tree must be within 2 ULP of the
-    exactly rounded sum (math.fsum) and no farther from the reference than the reference is from
-    exact (+2 ULP)."""
+    """Dataset G, SURVEY §8d acceptance: the GPU sum is within 1 ULP of the exactly rounded sum (math.fsum) and no
+    farther from the reference-order result than the reference is from exact (+1 ULP).  The kernel carries the
+    rounding error of every addition (TwoSum), so this holds whatever the condition number — "cancelling" is N(0,1)
+    data followed by its own negation plus a small tail (sum|x| / |sum x| ~ 1e9)."""
     rng = np.random.default_rng(0x94378165)
-    x = rng.standard_normal(n) if dist == "normal" else rng.random(n)
+    if dist == "normal":
+        x = rng.standard_normal(n)
+    elif dist == "uniform":
+        x = rng.random(n)
+    else:
+        h = rng.standard_normal(n // 2)
+        x = np.concatenate([h, -h[::-1], rng.standard_normal(n - 2 * (n // 2) + 0) * 1e-3])[:n]
+        x[-1] = 1e-3
     exact = math.fsum(x)
     refv = cpu.ref_sum_f64_avx2_order(ptr(x), n)
     got = gpu_sum_f64_dev(ag, x)
     assert got == gpu_sum_f64(ag, x), "host and device flavours must agree bit for bit"
     assert got == gpu_sum_f64_dev(ag, x, off_elems=1), "alignment must not change the result"
-    # condition number matters for N(0,1): scale the bound by sum|x| / |sum x|
-    cond = max(1.0, math.fsum(np.abs(x)) / max(abs(exact), 1e-300))
-    tol_ulp = 4 + 0.02 * min(cond, 1e6)
-    assert ulp_dist(got, exact) <= tol_ulp, (got, exact, ulp_dist(got, exact), tol_ulp)
-    assert ulp_dist(got, refv) <= ulp_dist(refv, exact) + tol_ulp
+    assert ulp_dist(got, exact) <= 1, (got, exact, ulp_dist(got, exact))
+    assert ulp_dist(got, refv) <= ulp_dist(refv, exact) + 1
+
+
+def test_f64_dataset_g_100m_rows_reports_ulp(ag, cpu, record_property):
+    """BASELINE config size, dataset G (N(0,1), seed 0x94378165): report the ULP distance of the GPU sum to the exactly
+    rounded sum and to the reference-order (AVX2) result, and of the reference to exact (SURVEY §8d asks for the
+    numbers); accept on <= 1 ULP from exact.  The reference-order mode must reproduce the AVX2 bits at this size too."""
+    n = 100_000_000
+    x = np.random.default_rng(0x94378165).standard_normal(n)
+    exact = math.fsum(x)
+    refv = cpu.ref_sum_f64_avx2_order(ptr(x), n)
+    d = Dev(x)
+    out = Dev(np.zeros(2))
+    ag.call("ag_sum_f64_dev", d.ptr, n, out.ptr, None)
+    ag.call("ag_sum_f64_reforder_dev", d.ptr, n, out.ptr + 8, None)
+    ag.call("ag_stream_sync", None)
+    got, got_ref_order = (float(v) for v in out.get())
+    report = {"rows": n, "gpu_vs_exact_ulp": ulp_dist(got, exact), "gpu_vs_reference_order_ulp": ulp_dist(got, refv),
+              "reference_order_vs_exact_ulp": ulp_dist(refv, exact), "reforder_mode_bit_exact": got_ref_order == refv,
+              "exact": exact, "gpu": got, "reference_order": refv}
+    for k, v in report.items():
+        record_property(k, v)
+    print("\nsum f64 dataset G 100M:", report)
+    try:
+        import json, os
+        os.makedirs("gpurun_out", exist_ok=True)
+        json.dump(report, open("gpurun_out/sum_f64_ulp_100m.json", "w"), indent=1)
+    except OSError:
+        pass
+    assert got_ref_order == refv
+    assert ulp_dist(got, exact) <= 1
+    assert ulp_dist(got, refv) <= ulp_dist(refv, exact) + 1
 
 
 def test_f64_deterministic(ag):

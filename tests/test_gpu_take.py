@@ -167,3 +167,93 @@ def test_boolean_values_take(ag, cpu):
                 assert np.array_equal(unpack_bits(got, 0, n), unpack_bits(want, 0, n)), (vlen, n, p_inull)
                 if gv is not None:
                     assert np.array_equal(unpack_bits(gv, 0, n), unpack_bits(wv, 0, n)) and gn.value == wn.value
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Windowed path (partition by table window -> gather out of L2 -> un-permute).  ag_take_set_policy(2, ...) forces it
+# on inputs the oracle handles in milliseconds; a 4 KB window turns a 50K-row table into ~100 buckets.
+@pytest.fixture
+def windowed(ag):
+    ag.call("ag_take_set_policy", 2, 0, 0, 4096)
+    yield ag
+    ag.call("ag_take_set_policy", 0, 32 << 20, 160 << 20, 16 << 20)
+
+
+@pytest.mark.parametrize("bw", [8, 16, 32, 64])
+@pytest.mark.parametrize("iw,signed", [(32, 1), (32, 0), (64, 1), (64, 0)])
+def test_windowed_random_differential(windowed, cpu, bw, iw, signed):
+    ag = windowed
+    rng = np.random.default_rng(bw * 1000 + iw * 2 + signed)
+    idt = IDT[(iw, signed)]
+    for vlen in (1, 2, 511, 50_000, 700_000):     # 700K rows of int64 over 4 KB windows would be 1367 windows (> 1022): the window grows
+        for n in (2, 33, 8191, 8192, 8193, 30_000, 100_001):
+            for p_inull in (0, 0.3):
+                voff, ioff = int(rng.integers(0, 9)), int(rng.integers(0, 11))
+                vals = rng.integers(0, np.iinfo(VDT[bw]).max, vlen + voff, dtype=VDT[bw], endpoint=True)
+                idx = rng.integers(0, vlen, n).astype(idt)
+                ivalid = pack_bits(rng.random(n) >= p_inull, ioff) if p_inull else None
+                both(ag, cpu, bw, vals, None, voff, vlen, iw, signed, idx, ivalid, ioff, n)
+
+
+def test_windowed_bounds_and_nulls(windowed, cpu):
+    ag = windowed
+    rng = np.random.default_rng(77)
+    n, vlen = 200_000, 60_000
+    vals = rng.integers(0, 1 << 60, vlen, dtype=np.uint64)
+    idx = rng.integers(0, vlen, n).astype(np.int32)
+    idx[[150_000, 123_457, 199_999]] = [vlen, -3, 2_000_000_000]
+    both(ag, cpu, 64, vals, None, 0, vlen, 32, 1, idx, None, 0, n)                      # first offender = lowest row
+    iv = np.ones(n, dtype=bool); iv[[150_000, 123_457, 199_999]] = False
+    both(ag, cpu, 64, vals, None, 0, vlen, 32, 1, idx, pack_bits(iv, 5), 5, n)          # offenders under null slots: no error
+    iv[123_457] = True
+    both(ag, cpu, 64, vals, None, 0, vlen, 32, 1, idx, pack_bits(iv, 5), 5, n)
+    # bounds_check off: out-of-range slots gather nothing and read as 0
+    out = np.full(n, 0xEE, dtype=np.uint64)
+    ag.call("ag_take_primitive", 64, ptr(vals), None, 0, vlen, 32, 1, ptr(idx), None, 0, n, 0, ptr(out), None, None, None, None)
+    ok = (idx >= 0) & (idx < vlen)
+    assert np.array_equal(out[ok], vals[idx[ok]]) and not out[~ok].any()
+    # all-null indices
+    both(ag, cpu, 64, vals, None, 0, vlen, 32, 1, idx, pack_bits(np.zeros(n, dtype=bool)), 0, n)
+    # every index the same row / all in the last window
+    both(ag, cpu, 64, vals, None, 0, vlen, 32, 1, np.full(n, vlen - 1, dtype=np.int32), None, 0, n)
+
+
+def _mix64(z):
+    with np.errstate(over="ignore"):
+        z = z + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+@pytest.mark.parametrize("order", ["random", "sorted", "reversed", "planted_bad"])
+def test_auto_routing_40m_rows(ag, order):
+    """SURVEY §8d C4 datasets at a size the automatic policy sends to the windowed path (40M int32 indices into a
+    64M-row, 512 MB table): random -> windowed, sorted / reversed -> the probe keeps the direct kernel, and one planted
+    out-of-range index is reported at its row.  Every output row is checked: values[i] = splitmix64(seed + i)."""
+    nv, n = 1 << 26, 40_000_000
+    v = Dev(nbytes=nv * 8)
+    ag.call("ag_generate_dev", 0, 0x94378165, 0, 0, v.ptr, nv, None)
+    idx = Dev(nbytes=n * 4)
+    ag.call("ag_generate_dev", 2, 0x0FF1CE, 0, nv - 1, idx.ptr, n, None)
+    ag.call("ag_stream_sync", None)
+    hidx = idx.buf.to_numpy(np.int32, n)
+    if order in ("sorted", "reversed"):
+        hidx = np.sort(hidx)
+        if order == "reversed":
+            hidx = hidx[::-1].copy()
+        ag.call("ag_upload", idx.ptr, hidx.ctypes.data, n * 4, None)
+    if order == "planted_bad":
+        hidx[31_234_567] = -1
+        ag.call("ag_upload", idx.ptr, hidx.ctypes.data, n * 4, None)
+    out = Dev(nbytes=n * 8)
+    bad = Dev(np.zeros(1, dtype=np.int64))
+    ag.call("ag_error_word_reset_dev", bad.ptr, None)
+    ag.call("ag_take_primitive_dev", 64, v.ptr, None, 0, nv, 32, 1, idx.ptr, None, 0, n, 1, out.ptr, None, bad.ptr, None)
+    ag.call("ag_stream_sync", None)
+    if order == "planted_bad":
+        assert bad.get()[0] == 31_234_567
+        return
+    assert bad.get()[0] == N.NO_ERROR_POS
+    want = _mix64(np.uint64(0x94378165) + hidx.astype(np.uint64))
+    assert out.buf.to_numpy(np.uint64, n).tobytes() == want.tobytes()
