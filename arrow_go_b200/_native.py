@@ -64,6 +64,9 @@ _pi64 = C.POINTER(C.c_int64)
 # name -> argtypes.  Every function returns ag_status (int) unless listed in _SPECIAL.
 _SIGS = {
     "ag_init": [_i],
+    "ag_init_all": [C.POINTER(_i)],
+    "ag_set_device": [_i],
+    "ag_get_device": [C.POINTER(_i)],
     "ag_shutdown": [],
     "ag_device_count": [C.POINTER(_i)],
     "ag_device_info": [C.POINTER(_i), C.POINTER(_i), C.POINTER(_sz), C.POINTER(_i), C.POINTER(_i)],
@@ -96,6 +99,19 @@ _SIGS = {
     "ag_sum_i64_dev": [_p, _sz, _p, _p],
     "ag_sum_u64_dev": [_p, _sz, _p, _p],
     "ag_sum_f64_reforder_dev": [_p, _sz, _p, _p],
+    # multi-GPU
+    "ag_shard_range": [_i64, _i, _i, _pi64, _pi64],
+    "ag_comm_local_handle": [_i, _p],
+    "ag_comm_create": [C.POINTER(_p), _i, _i, _p],
+    "ag_comm_create_local": [C.POINTER(_p), _i, C.POINTER(_i)],
+    "ag_comm_unique_id": [_p],
+    "ag_comm_attach_nccl": [_p, _p],
+    "ag_comm_info": [_p, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)],
+    "ag_comm_destroy": [_p],
+    "ag_sum_i64_global_dev": [_p, _p, _sz, _p, _p],
+    "ag_sum_u64_global_dev": [_p, _p, _sz, _p, _p],
+    "ag_sum_f64_global_dev": [_p, _p, _sz, _p, _p],
+    "ag_sum_i64_global_nccl_dev": [_p, _p, _sz, _p, _p],
     # arithmetic
     "ag_arith_binary": [_i, _i8, _p, _p, _p, _i64],
     "ag_arith_arr_scalar": [_i, _i8, _p, _p, _p, _i64],

@@ -155,7 +155,7 @@ extern "C" ag_status ag_import_device_array(struct ArrowDeviceArray* in, const s
       int dev = 0;
       cudaGetDevice(&dev);
       if (in->device_id != dev)
-        AG_FAIL(AG_ERR_INVALID, "cdata: array lives on CUDA device %lld, this process drives device %d (one process per GPU)", (long long)in->device_id, dev);
+        AG_FAIL(AG_ERR_INVALID, "cdata: array lives on CUDA device %lld, the calling thread works on device %d (ag_set_device first)", (long long)in->device_id, dev);
       break;
     }
     case ARROW_DEVICE_CUDA_HOST:

@@ -7,6 +7,7 @@
 #include <stddef.h>
 #include <stdio.h>
 #include <atomic>
+#include <mutex>
 
 #include "../../include/arrowgpu.h"
 
@@ -47,6 +48,14 @@ struct Workspace {
   size_t tile_status_cap;  // in elements
   // pinned host mirror of `scalars` for cheap readback
   int64_t* h_scalars;
+  // Held by an entry point from get_workspace until its last launch is enqueued: two threads that share a stream
+  // (e.g. both pass NULL) may interleave their CALLS but never the launches of one call with another's, so ticket /
+  // scalar slots / tile status are always used by one kernel sequence at a time (the stream orders the rest).
+  std::mutex* seq_mu;
+};
+struct WorkspaceLock {
+  std::unique_lock<std::mutex> lk;
+  explicit WorkspaceLock(Workspace* ws) : lk(*ws->seq_mu) {}
 };
 
 constexpr int kMaxPartials = 4096;
@@ -54,6 +63,8 @@ constexpr int kMaxPartials = 4096;
 ag_status ensure_init();
 int sm_count();
 cudaStream_t resolve_stream(ag_stream_t s);
+int current_device();
+int device_count();
 ag_status get_workspace(cudaStream_t s, Workspace** ws);
 ag_status ensure_tile_status(Workspace* ws, size_t n_tiles, cudaStream_t s);
 void count_launch(int n = 1);
@@ -73,6 +84,17 @@ struct CallStream {
 // Device temp allocation (stream-ordered pool).
 ag_status dev_alloc_async(void** p, size_t nbytes, cudaStream_t s);
 ag_status dev_free_async(void* p, cudaStream_t s);
+
+// ---------------------------------------------------------------- cross-GPU exchange (comm.cu, reduce.cu) ----
+struct alignas(32) MailSlot { unsigned long long flag; unsigned long long pad; unsigned long long s; unsigned long long c; };
+struct SumExchange {
+  MailSlot* const* peers;   // device array [world]: base of every rank's mailbox as addressable from this device
+  MailSlot* local;          // this rank's mailbox
+  int world, rank;
+  unsigned long long epoch; // >= 1, same value on every rank for one collective
+};
+ag_status comm_next_exchange(ag_comm_t comm, SumExchange* x);   // bumps the communicator's epoch
+ag_status comm_nccl_allreduce_sum_i64(ag_comm_t comm, void* d_buf, size_t count, cudaStream_t st);
 
 // ---------------------------------------------------------------- type helpers ----
 inline int type_width(int type) {

@@ -295,6 +295,7 @@ template <typename V, int kMode>
 static ag_status launch_filter_t(FilterParams& p, cudaStream_t st) {
   Workspace* ws;
   AG_TRY(get_workspace(st, &ws));
+  WorkspaceLock ws_lock(ws);
   p.n_tiles = (p.n + kFTileRows - 1) / kFTileRows;
   AG_TRY(ensure_tile_status(ws, (size_t)p.n_tiles, st));
   p.status = ws->tile_status;
@@ -507,6 +508,7 @@ static ag_status launch_fused_t(const void* vals, const void* scalar_host, int64
                                 int64_t* d_out_len, cudaStream_t st) {
   Workspace* ws;
   AG_TRY(get_workspace(st, &ws));
+  WorkspaceLock ws_lock(ws);
   const int64_t n_tiles = (n + kFTileRows - 1) / kFTileRows;
   AG_TRY(ensure_tile_status(ws, (size_t)n_tiles, st));
   AG_CUDA_TRY(cudaMemsetAsync(ws->tile_status, 0, (size_t)n_tiles * sizeof(unsigned long long), st));

@@ -153,6 +153,7 @@ ag_status launch_minmax(const void* d_in, size_t n, void* d_out, cudaStream_t st
   if (head > n) head = n;
   Workspace* ws;
   AG_TRY(get_workspace(st, &ws));
+  WorkspaceLock ws_lock(ws);
   const size_t n_vecs = (n - head) / N;
   size_t want = (n_vecs + (size_t)kMmThreads * kMmLoads - 1) / ((size_t)kMmThreads * kMmLoads);
   if (want < 1) want = 1;

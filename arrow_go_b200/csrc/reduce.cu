@@ -83,6 +83,8 @@ template <typename T> struct alignas(16) Acc {
   __device__ __forceinline__ void merge(const Acc& o) { s = s + o.s; }
   __device__ __forceinline__ Acc shfl_xor(int m) const { Acc r; r.s = shfl_xor_t(s, m); r.pad = T(0); return r; }
   __device__ __forceinline__ T value() const { return s; }
+  __device__ __forceinline__ T& pad_or_c() { return pad; }
+  __device__ __forceinline__ const T& pad_or_c() const { return pad; }
 };
 template <> struct alignas(16) Acc<double> {
   double s, c;
@@ -97,7 +99,46 @@ template <> struct alignas(16) Acc<double> {
   __device__ __forceinline__ void merge(const Acc& o) { add(o.s); c = __dadd_rn(c, o.c); }
   __device__ __forceinline__ Acc shfl_xor(int m) const { Acc r; r.s = shfl_xor_t(s, m); r.c = shfl_xor_t(c, m); return r; }
   __device__ __forceinline__ double value() const { return __dadd_rn(s, c); }
+  __device__ __forceinline__ double& pad_or_c() { return c; }
+  __device__ __forceinline__ const double& pad_or_c() const { return c; }
 };
+
+// ---- cross-GPU exchange fused into the reduction (multi-GPU global Sum) -------------------------
+// Every rank owns a MAILBOX in its HBM: 2 buffers (epoch parity) x world slots of {flag, sum, error}.  The thread that
+// holds a rank's final (sum, error) pair stores it straight into slot[rank] of EVERY rank's mailbox (peer stores over
+// NVLink), publishes the epoch as the flag behind a system-scope fence, then waits for the world's flags in its own
+// mailbox and folds the pairs in RANK ORDER — so the collective costs one NVLink store + one poll inside the kernel
+// that computed the sum: no second launch, no host synchronisation, identical bits on every rank.  A rank can be at
+// most one epoch ahead of the slowest one (it cannot finish epoch e before everyone has written e), hence two buffers.
+template <typename T>
+__device__ __forceinline__ Acc<T> exchange_sum(Acc<T> mine, const SumExchange& x) {
+  const int buf = (int)(x.epoch & 1ull);
+  for (int r = 0; r < x.world; ++r) {
+    MailSlot* m = x.peers[r] + buf * x.world + x.rank;
+    m->s = *reinterpret_cast<const unsigned long long*>(&mine.s);
+    m->c = *reinterpret_cast<const unsigned long long*>(&mine.pad_or_c());
+  }
+  __threadfence_system();
+  for (int r = 0; r < x.world; ++r) {
+    MailSlot* m = x.peers[r] + buf * x.world + x.rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&m->flag), "l"(x.epoch) : "memory");
+  }
+  Acc<T> g; g.zero();
+  for (int r = 0; r < x.world; ++r) {
+    MailSlot* m = x.local + buf * x.world + r;
+    unsigned long long f;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(&m->flag) : "memory");
+    } while (f != x.epoch);
+    Acc<T> o;
+    const unsigned long long vs = *reinterpret_cast<volatile unsigned long long*>(&m->s);
+    const unsigned long long vc = *reinterpret_cast<volatile unsigned long long*>(&m->c);
+    o.s = *reinterpret_cast<const T*>(&vs);
+    o.pad_or_c() = *reinterpret_cast<const T*>(&vc);
+    g.merge(o);
+  }
+  return g;
+}
 
 // fixed tree over the 256 threads of a block; result valid in thread 0
 template <typename T>
@@ -120,7 +161,7 @@ __device__ __forceinline__ Acc<T> block_tree_sum(Acc<T> v, Acc<T>* smem /* >= 8 
 template <typename T, bool kAligned>
 __global__ void __launch_bounds__(kSumThreads, sum_blocks_per_sm<T>())
 sum_kernel(const T* __restrict__ in, size_t n, Acc<T>* __restrict__ partials, unsigned* __restrict__ ticket,
-           T* __restrict__ out) {
+           T* __restrict__ out, const SumExchange xch) {
   __shared__ Acc<T> smem[8];
   __shared__ bool is_last;
   const size_t n_pairs = n >> 1;
@@ -156,7 +197,11 @@ sum_kernel(const T* __restrict__ in, size_t n, Acc<T>* __restrict__ partials, un
   Acc<T> v = block_tree_sum(ax[0], smem);
 
   if (gridDim.x == 1) {
-    if (threadIdx.x == 0) { if (n & 1) v.add(in[n - 1]); *out = v.value(); }
+    if (threadIdx.x == 0) {
+      if (n & 1) v.add(in[n - 1]);
+      if (xch.world > 1) v = exchange_sum(v, xch);
+      *out = v.value();
+    }
     return;
   }
   if (threadIdx.x == 0) {
@@ -177,8 +222,9 @@ sum_kernel(const T* __restrict__ in, size_t n, Acc<T>* __restrict__ partials, un
   acc = block_tree_sum(acc, smem);
   if (threadIdx.x == 0) {
     if (n & 1) acc.add(in[n - 1]);
-    *out = acc.value();
     *ticket = 0;  // leave the workspace ready for the next launch on this stream
+    if (xch.world > 1) acc = exchange_sum(acc, xch);
+    *out = acc.value();
   }
 }
 
@@ -221,21 +267,35 @@ __global__ void __launch_bounds__(32) sum_f64_reforder_kernel(const double* __re
   }
 }
 
+// n == 0 with an exchange: the rank still has to take part, with a zero pair
+__global__ void sum_exchange_only_kernel(unsigned long long* out, const SumExchange xch, int is_f64) {
+  if (is_f64) { Acc<double> z; z.zero(); z = exchange_sum(z, xch); *reinterpret_cast<double*>(out) = z.value(); }
+  else { Acc<unsigned long long> z; z.zero(); z = exchange_sum(z, xch); *out = z.value(); }
+}
+
 template <typename T>
-static ag_status launch_sum(const T* d_in, size_t n, T* d_res, cudaStream_t st) {
+ag_status launch_sum(const T* d_in, size_t n, T* d_res, cudaStream_t st, const SumExchange* xch) {
+  SumExchange x{};
+  x.world = 1;
+  if (xch) x = *xch;
   if (n == 0) {
+    if (x.world > 1) {
+      sum_exchange_only_kernel<<<1, 1, 0, st>>>(reinterpret_cast<unsigned long long*>(d_res), x, std::is_floating_point<T>::value ? 1 : 0);
+      return check_launch("sum_exchange_only_kernel");
+    }
     AG_CUDA_TRY(cudaMemsetAsync(d_res, 0, sizeof(T), st));
     return AG_OK;
   }
   if ((reinterpret_cast<uintptr_t>(d_in) & 7) != 0) AG_FAIL(AG_ERR_INVALID, "sum: input is not 8-byte aligned");
   Workspace* ws;
   AG_TRY(get_workspace(st, &ws));
+  WorkspaceLock ws_lock(ws);
   const bool aligned = (reinterpret_cast<uintptr_t>(d_in) & 15) == 0;
   const int grid = sum_grid<T>(n >> 1);
   if (aligned)
-    sum_kernel<T, true><<<grid, kSumThreads, 0, st>>>(d_in, n, (Acc<T>*)ws->partials, ws->ticket, d_res);
+    sum_kernel<T, true><<<grid, kSumThreads, 0, st>>>(d_in, n, (Acc<T>*)ws->partials, ws->ticket, d_res, x);
   else
-    sum_kernel<T, false><<<grid, kSumThreads, 0, st>>>(d_in, n, (Acc<T>*)ws->partials, ws->ticket, d_res);
+    sum_kernel<T, false><<<grid, kSumThreads, 0, st>>>(d_in, n, (Acc<T>*)ws->partials, ws->ticket, d_res, x);
   return check_launch("sum_kernel");
 }
 
@@ -287,32 +347,58 @@ extern "C" {
 
 ag_status ag_sum_f64_dev(const double* d, size_t n, double* d_res, ag_stream_t s) {
   AG_TRY(ensure_init());
-  return launch_sum<double>(d, n, d_res, resolve_stream(s));
+  return launch_sum<double>(d, n, d_res, resolve_stream(s), nullptr);
 }
 ag_status ag_sum_i64_dev(const int64_t* d, size_t n, int64_t* d_res, ag_stream_t s) {
   AG_TRY(ensure_init());
   // wrapping two's-complement sum == unsigned sum (int64.c:21-27)
-  return launch_sum<unsigned long long>((const unsigned long long*)d, n, (unsigned long long*)d_res, resolve_stream(s));
+  return launch_sum<unsigned long long>((const unsigned long long*)d, n, (unsigned long long*)d_res, resolve_stream(s), nullptr);
 }
 ag_status ag_sum_u64_dev(const uint64_t* d, size_t n, uint64_t* d_res, ag_stream_t s) {
   AG_TRY(ensure_init());
-  return launch_sum<unsigned long long>((const unsigned long long*)d, n, (unsigned long long*)d_res, resolve_stream(s));
+  return launch_sum<unsigned long long>((const unsigned long long*)d, n, (unsigned long long*)d_res, resolve_stream(s), nullptr);
 }
 ag_status ag_sum_f64_reforder_dev(const double* d, size_t n, double* d_res, ag_stream_t s) {
   AG_TRY(ensure_init());
   return launch_reforder(d, n, d_res, resolve_stream(s));
 }
 
+// ---- global Sum over the ranks of a communicator (comm.cu): the local reduction and the cross-GPU fold are ONE kernel
+ag_status ag_sum_i64_global_dev(ag_comm_t comm, const int64_t* d, size_t n, int64_t* d_res, ag_stream_t s) {
+  AG_TRY(ensure_init());
+  cudaStream_t st = resolve_stream(s);
+  SumExchange x;
+  AG_TRY(comm_next_exchange(comm, &x));
+  return launch_sum<unsigned long long>((const unsigned long long*)d, n, (unsigned long long*)d_res, st, &x);
+}
+ag_status ag_sum_u64_global_dev(ag_comm_t comm, const uint64_t* d, size_t n, uint64_t* d_res, ag_stream_t s) {
+  return ag_sum_i64_global_dev(comm, (const int64_t*)d, n, (int64_t*)d_res, s);
+}
+ag_status ag_sum_f64_global_dev(ag_comm_t comm, const double* d, size_t n, double* d_res, ag_stream_t s) {
+  AG_TRY(ensure_init());
+  cudaStream_t st = resolve_stream(s);
+  SumExchange x;
+  AG_TRY(comm_next_exchange(comm, &x));
+  return launch_sum<double>(d, n, d_res, st, &x);
+}
+// the north_star's literal form: per-GPU Sum, then ncclAllReduce of the 8-byte result on the same stream (no host sync)
+ag_status ag_sum_i64_global_nccl_dev(ag_comm_t comm, const int64_t* d, size_t n, int64_t* d_res, ag_stream_t s) {
+  AG_TRY(ensure_init());
+  cudaStream_t st = resolve_stream(s);
+  AG_TRY(launch_sum<unsigned long long>((const unsigned long long*)d, n, (unsigned long long*)d_res, st, nullptr));
+  return comm_nccl_allreduce_sum_i64(comm, d_res, 1, st);
+}
+
 ag_status ag_sum_f64(const double* buf, size_t n, double* res) {
-  return host_sum<double>(buf, n, res, [](const double* d, size_t m, double* r, cudaStream_t st) { return launch_sum<double>(d, m, r, st); });
+  return host_sum<double>(buf, n, res, [](const double* d, size_t m, double* r, cudaStream_t st) { return launch_sum<double>(d, m, r, st, nullptr); });
 }
 ag_status ag_sum_i64(const int64_t* buf, size_t n, int64_t* res) {
   return host_sum<unsigned long long>((const unsigned long long*)buf, n, (unsigned long long*)res,
-      [](const unsigned long long* d, size_t m, unsigned long long* r, cudaStream_t st) { return launch_sum<unsigned long long>(d, m, r, st); });
+      [](const unsigned long long* d, size_t m, unsigned long long* r, cudaStream_t st) { return launch_sum<unsigned long long>(d, m, r, st, nullptr); });
 }
 ag_status ag_sum_u64(const uint64_t* buf, size_t n, uint64_t* res) {
   return host_sum<unsigned long long>((const unsigned long long*)buf, n, (unsigned long long*)res,
-      [](const unsigned long long* d, size_t m, unsigned long long* r, cudaStream_t st) { return launch_sum<unsigned long long>(d, m, r, st); });
+      [](const unsigned long long* d, size_t m, unsigned long long* r, cudaStream_t st) { return launch_sum<unsigned long long>(d, m, r, st, nullptr); });
 }
 ag_status ag_sum_f64_reforder(const double* buf, size_t n, double* res) {
   return host_sum<double>(buf, n, res, [](const double* d, size_t m, double* r, cudaStream_t st) { return launch_reforder(d, m, r, st); });

@@ -34,20 +34,33 @@ ag_status cuda_fail(cudaError_t e, const char* what, const char* file, int line)
 }
 
 // ---------------------------------------------------------------- state -----------
+// One Runtime per device.  A thread works on its CURRENT device: the one it chose with ag_set_device, else the
+// process default (first ag_init / LOCAL_RANK / device 0).  One process per GPU (torchrun) uses exactly one entry;
+// a single process that drives the whole box (a Go program: one process, many goroutines) calls ag_init_all and
+// then ag_set_device per worker thread / per shard.  Streams remember their device, so an entry point that is
+// handed a stream always runs on that stream's device whatever the thread's current device is.
+constexpr int kMaxDevices = 16;
 struct Runtime {
   bool ready = false;
   int device = -1;
   int sms = 0;
   cudaStream_t default_stream = nullptr;
   std::mutex mu;
-  std::unordered_map<cudaStream_t, Workspace*> workspaces;
   std::vector<cudaStream_t> free_streams;   // pooled streams for the host-pointer entry points
   std::vector<cudaStream_t> all_streams;
   void* flush_buf = nullptr;
   size_t flush_bytes = 0;
+  int numa_state = 0;                        // 0 unknown, 1 have cpu set, -1 unavailable
+  cpu_set_t numa_cpus;
 };
-static Runtime g_rt;
+static Runtime g_dev[kMaxDevices];
+static int g_default_device = -1;            // set by the first successful init
+static int g_device_count = -1;
+static thread_local int tls_device = -1;     // ag_set_device; -1 = process default
 static std::mutex g_init_mu;
+static std::mutex g_ws_mu;                   // workspaces + stream -> device registry (streams are unique process-wide)
+static std::unordered_map<cudaStream_t, Workspace*> g_workspaces;
+static std::unordered_map<cudaStream_t, int> g_stream_device;
 static std::atomic<uint64_t> g_launches{0};
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
@@ -62,60 +75,93 @@ ag_status check_launch(const char* what) {
   return AG_OK;
 }
 
-static ag_status init_locked(int device) {
-  if (g_rt.ready) {
-    // one process per GPU: re-binding the calling thread is all that is needed
-    AG_CUDA_TRY(cudaSetDevice(g_rt.device));
-    return AG_OK;
-  }
-  int count = 0;
-  cudaError_t e = cudaGetDeviceCount(&count);
-  if (e != cudaSuccess || count == 0) {
-    cudaGetLastError();
-    AG_FAIL(AG_ERR_CUDA, "no CUDA device available (%s); libarrowgpu has no CPU fallback",
-            e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+static int current_device_index() { return tls_device >= 0 ? tls_device : g_default_device; }
+static Runtime& cur() { return g_dev[current_device_index()]; }
+
+static void register_stream(cudaStream_t st, int device) {
+  std::lock_guard<std::mutex> lk(g_ws_mu);
+  g_stream_device[st] = device;
+}
+
+// g_init_mu held
+static ag_status init_device_locked(int device) {
+  if (g_device_count < 0) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+      cudaGetLastError();
+      AG_FAIL(AG_ERR_CUDA, "no CUDA device available (%s); libarrowgpu has no CPU fallback",
+              e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    g_device_count = count < kMaxDevices ? count : kMaxDevices;
   }
   if (device < 0) {
-    const char* lr = getenv("LOCAL_RANK");
+    const char* lr = getenv("LOCAL_RANK");   // torchrun: one process per GPU
     device = lr ? atoi(lr) : 0;
   }
-  if (device >= count) AG_FAIL(AG_ERR_INVALID, "device %d out of range (have %d)", device, count);
+  if (device >= g_device_count) AG_FAIL(AG_ERR_INVALID, "device %d out of range (have %d)", device, g_device_count);
+  Runtime& rt = g_dev[device];
   AG_CUDA_TRY(cudaSetDevice(device));
+  if (rt.ready) return AG_OK;
   cudaDeviceProp prop;
   AG_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   if (prop.major < 10)
     AG_FAIL(AG_ERR_CUDA, "device %d is sm_%d%d; libarrowgpu is built for sm_100a only", device, prop.major, prop.minor);
-  g_rt.device = device;
-  g_rt.sms = prop.multiProcessorCount;
-  AG_CUDA_TRY(cudaStreamCreateWithFlags(&g_rt.default_stream, cudaStreamNonBlocking));
-  // keep freed blocks cached in the stream-ordered pool (temp buffers of the host entry points)
+  rt.device = device;
+  rt.sms = prop.multiProcessorCount;
+  AG_CUDA_TRY(cudaStreamCreateWithFlags(&rt.default_stream, cudaStreamNonBlocking));
+  register_stream(rt.default_stream, device);
+  // keep freed blocks cached in the stream-ordered pool (temp buffers of the host entry points, take's scratch)
   cudaMemPool_t pool;
   AG_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
   uint64_t thresh = UINT64_MAX;
   AG_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
-  g_rt.ready = true;
+  rt.ready = true;
+  if (g_default_device < 0) g_default_device = device;
   return AG_OK;
 }
 
 ag_status ensure_init() {
-  if (g_rt.ready) {
+  const int want = current_device_index();
+  if (want >= 0 && g_dev[want].ready) {
     // cgo calls arrive on arbitrary OS threads: bind the device for this thread.
-    int cur = -1;
-    if (cudaGetDevice(&cur) != cudaSuccess || cur != g_rt.device) AG_CUDA_TRY(cudaSetDevice(g_rt.device));
+    int c = -1;
+    if (cudaGetDevice(&c) != cudaSuccess || c != want) AG_CUDA_TRY(cudaSetDevice(want));
     return AG_OK;
   }
   std::lock_guard<std::mutex> lk(g_init_mu);
-  return init_locked(-1);
+  return init_device_locked(want);
 }
 
-int sm_count() { return g_rt.sms > 0 ? g_rt.sms : 148; }
+int sm_count() {
+  const int d = current_device_index();
+  return (d >= 0 && g_dev[d].sms > 0) ? g_dev[d].sms : 148;
+}
+int current_device() { return current_device_index(); }
+int device_count() { return g_device_count; }
 
-cudaStream_t resolve_stream(ag_stream_t s) { return s ? (cudaStream_t)s : g_rt.default_stream; }
+// NULL -> the current device's default stream.  A stream created by this library runs on ITS device: the calling
+// thread is switched to it (kernel launches and stream-ordered allocations follow the current device).
+cudaStream_t resolve_stream(ag_stream_t s) {
+  if (!s) return cur().default_stream;
+  cudaStream_t st = (cudaStream_t)s;
+  int dev = -1;
+  {
+    std::lock_guard<std::mutex> lk(g_ws_mu);
+    auto it = g_stream_device.find(st);
+    if (it != g_stream_device.end()) dev = it->second;
+  }
+  if (dev >= 0 && dev != current_device_index()) {
+    tls_device = dev;
+    cudaSetDevice(dev);
+  }
+  return st;
+}
 
 ag_status get_workspace(cudaStream_t s, Workspace** out) {
-  std::lock_guard<std::mutex> lk(g_rt.mu);
-  auto it = g_rt.workspaces.find(s);
-  if (it != g_rt.workspaces.end()) { *out = it->second; return AG_OK; }
+  std::lock_guard<std::mutex> lk(g_ws_mu);
+  auto it = g_workspaces.find(s);
+  if (it != g_workspaces.end()) { *out = it->second; return AG_OK; }
   Workspace* ws = new Workspace();
   memset(ws, 0, sizeof(*ws));
   AG_CUDA_TRY(cudaMalloc(&ws->partials, (size_t)kMaxPartials * 16));
@@ -126,13 +172,13 @@ ag_status get_workspace(cudaStream_t s, Workspace** out) {
   AG_CUDA_TRY(cudaMalloc((void**)&ws->scalars, 16 * sizeof(int64_t)));
   AG_CUDA_TRY(cudaMemsetAsync(ws->scalars, 0, 16 * sizeof(int64_t), s));
   AG_CUDA_TRY(cudaHostAlloc((void**)&ws->h_scalars, 16 * sizeof(int64_t), cudaHostAllocDefault));
-  ws->tile_status = nullptr;
-  ws->tile_status_cap = 0;
-  g_rt.workspaces[s] = ws;
+  ws->seq_mu = new std::mutex();
+  g_workspaces[s] = ws;
   *out = ws;
   return AG_OK;
 }
 
+// Caller holds WorkspaceLock(ws): growth cannot race with another call's launches on the same stream.
 ag_status ensure_tile_status(Workspace* ws, size_t n_tiles, cudaStream_t s) {
   if (ws->tile_status_cap >= n_tiles) return AG_OK;
   size_t cap = ws->tile_status_cap ? ws->tile_status_cap : 4096;
@@ -150,21 +196,35 @@ ag_status ensure_tile_status(Workspace* ws, size_t n_tiles, cudaStream_t s) {
 }
 
 ag_status acquire_call_stream(cudaStream_t* out) {
-  std::lock_guard<std::mutex> lk(g_rt.mu);
-  if (!g_rt.free_streams.empty()) {
-    *out = g_rt.free_streams.back();
-    g_rt.free_streams.pop_back();
-    return AG_OK;
+  Runtime& rt = cur();
+  {
+    std::lock_guard<std::mutex> lk(rt.mu);
+    if (!rt.free_streams.empty()) {
+      *out = rt.free_streams.back();
+      rt.free_streams.pop_back();
+      return AG_OK;
+    }
   }
   cudaStream_t st;
   AG_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  g_rt.all_streams.push_back(st);
+  register_stream(st, rt.device);
+  {
+    std::lock_guard<std::mutex> lk(rt.mu);
+    rt.all_streams.push_back(st);
+  }
   *out = st;
   return AG_OK;
 }
 void release_call_stream(cudaStream_t st) {
-  std::lock_guard<std::mutex> lk(g_rt.mu);
-  g_rt.free_streams.push_back(st);
+  int dev = -1;
+  {
+    std::lock_guard<std::mutex> lk(g_ws_mu);
+    auto it = g_stream_device.find(st);
+    if (it != g_stream_device.end()) dev = it->second;
+  }
+  Runtime& rt = dev >= 0 ? g_dev[dev] : cur();
+  std::lock_guard<std::mutex> lk(rt.mu);
+  rt.free_streams.push_back(st);
 }
 
 // Resident blocks per SM for a kernel (cudaOccupancyMaxActiveBlocksPerMultiprocessor), cached per
@@ -201,33 +261,95 @@ extern "C" {
 
 ag_status ag_init(int device) {
   std::lock_guard<std::mutex> lk(g_init_mu);
-  if (g_rt.ready && device >= 0 && device != g_rt.device)
-    AG_FAIL(AG_ERR_INVALID, "ag_init(%d): process already bound to device %d (one process per GPU)", device, g_rt.device);
-  return init_locked(device);
+  AG_TRY(init_device_locked(device));
+  int d = -1;
+  cudaGetDevice(&d);
+  // the first ag_init names the process default; a later ag_init(other) initialises that device too and makes it
+  // the calling thread's current device (same as ag_set_device)
+  if (d >= 0 && d != g_default_device) tls_device = d;
+  return AG_OK;
+}
+
+ag_status ag_init_all(int* n_devices) {
+  std::lock_guard<std::mutex> lk(g_init_mu);
+  AG_TRY(init_device_locked(g_default_device >= 0 ? g_default_device : 0));
+  for (int d = 0; d < g_device_count; ++d) AG_TRY(init_device_locked(d));
+  // peer access between every pair: the sharded reductions read the other devices' partial results directly
+  for (int a = 0; a < g_device_count; ++a) {
+    AG_CUDA_TRY(cudaSetDevice(a));
+    for (int b = 0; b < g_device_count; ++b) {
+      if (a == b) continue;
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, a, b) == cudaSuccess && can) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(b, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+        cudaGetLastError();
+      }
+    }
+  }
+  AG_CUDA_TRY(cudaSetDevice(current_device_index()));
+  if (n_devices) *n_devices = g_device_count;
+  return AG_OK;
+}
+
+ag_status ag_set_device(int device) {
+  {
+    std::lock_guard<std::mutex> lk(g_init_mu);
+    AG_TRY(init_device_locked(device));
+  }
+  int d = -1;
+  AG_CUDA_TRY(cudaGetDevice(&d));
+  tls_device = d;
+  return AG_OK;
+}
+
+ag_status ag_get_device(int* device) {
+  if (!device) AG_FAIL(AG_ERR_INVALID, "ag_get_device: NULL argument");
+  AG_TRY(ensure_init());
+  *device = current_device_index();
+  return AG_OK;
 }
 
 ag_status ag_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_init_mu);
-  if (!g_rt.ready) return AG_OK;
-  cudaDeviceSynchronize();
+  if (g_default_device < 0) return AG_OK;
+  for (int d = 0; d < kMaxDevices; ++d) {
+    if (!g_dev[d].ready) continue;
+    cudaSetDevice(d);
+    cudaDeviceSynchronize();
+  }
   {
-    std::lock_guard<std::mutex> lk2(g_rt.mu);
-    for (auto& kv : g_rt.workspaces) {
+    std::lock_guard<std::mutex> lk2(g_ws_mu);
+    for (auto& kv : g_workspaces) {
       Workspace* ws = kv.second;
+      auto it = g_stream_device.find(kv.first);
+      if (it != g_stream_device.end()) cudaSetDevice(it->second);
       cudaFree(ws->partials); cudaFree(ws->ticket); cudaFree(ws->scalars);
       if (ws->tile_status) cudaFree(ws->tile_status);
       cudaFreeHost(ws->h_scalars);
+      delete ws->seq_mu;
       delete ws;
     }
-    g_rt.workspaces.clear();
-    for (cudaStream_t st : g_rt.all_streams) cudaStreamDestroy(st);
-    g_rt.all_streams.clear();
-    g_rt.free_streams.clear();
-    if (g_rt.flush_buf) { cudaFree(g_rt.flush_buf); g_rt.flush_buf = nullptr; }
+    g_workspaces.clear();
+    g_stream_device.clear();
   }
-  cudaStreamDestroy(g_rt.default_stream);
-  g_rt.default_stream = nullptr;
-  g_rt.ready = false;
+  for (int d = 0; d < kMaxDevices; ++d) {
+    Runtime& rt = g_dev[d];
+    if (!rt.ready) continue;
+    cudaSetDevice(d);
+    {
+      std::lock_guard<std::mutex> lk2(rt.mu);
+      for (cudaStream_t st : rt.all_streams) cudaStreamDestroy(st);
+      rt.all_streams.clear();
+      rt.free_streams.clear();
+      if (rt.flush_buf) { cudaFree(rt.flush_buf); rt.flush_buf = nullptr; }
+    }
+    cudaStreamDestroy(rt.default_stream);
+    rt.default_stream = nullptr;
+    rt.ready = false;
+  }
+  g_default_device = -1;
+  tls_device = -1;
   return AG_OK;
 }
 
@@ -241,8 +363,8 @@ ag_status ag_device_count(int* count) {
 ag_status ag_device_info(int* device, int* sms, size_t* hbm_bytes, int* cc_major, int* cc_minor) {
   AG_TRY(ensure_init());
   cudaDeviceProp prop;
-  AG_CUDA_TRY(cudaGetDeviceProperties(&prop, g_rt.device));
-  if (device) *device = g_rt.device;
+  AG_CUDA_TRY(cudaGetDeviceProperties(&prop, cur().device));
+  if (device) *device = cur().device;
   if (sms) *sms = prop.multiProcessorCount;
   if (hbm_bytes) *hbm_bytes = prop.totalGlobalMem;
   if (cc_major) *cc_major = prop.major;
@@ -263,14 +385,12 @@ uint64_t ag_kernel_launch_count(void) { return g_launches.load(std::memory_order
 // CPUs of the NUMA node the GPU hangs off (sysfs); empty when unknown.  Pinned buffers are
 // allocated and first-touched from one of those CPUs so DMA does not cross the socket link.
 static bool gpu_node_cpus(cpu_set_t* set) {
-  static int state = 0;  // 0 unknown, 1 have set, -1 unavailable
-  static cpu_set_t cached;
-  static std::mutex mu;
-  std::lock_guard<std::mutex> lk(mu);
-  if (state == 0) {
-    state = -1;
+  Runtime& rt = cur();
+  std::lock_guard<std::mutex> lk(rt.mu);
+  if (rt.numa_state == 0) {
+    rt.numa_state = -1;
     char bus[32] = {0};
-    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), g_rt.device) == cudaSuccess) {
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), rt.device) == cudaSuccess) {
       for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
       char path[128];
       snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
@@ -279,24 +399,24 @@ static bool gpu_node_cpus(cpu_set_t* set) {
       if (node >= 0) {
         snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
         if (FILE* f = fopen(path, "r")) {
-          CPU_ZERO(&cached);
+          CPU_ZERO(&rt.numa_cpus);
           int a, b; char sep;
           bool any = false;
           while (fscanf(f, "%d", &a) == 1) {
             b = a;
             if (fscanf(f, "%c", &sep) == 1 && sep == '-') { if (fscanf(f, "%d", &b) != 1) b = a; if (fscanf(f, "%c", &sep) != 1) sep = 0; }
-            for (int c = a; c <= b && c < CPU_SETSIZE; ++c) { CPU_SET(c, &cached); any = true; }
+            for (int c = a; c <= b && c < CPU_SETSIZE; ++c) { CPU_SET(c, &rt.numa_cpus); any = true; }
             if (sep != ',') break;
           }
           fclose(f);
-          if (any) state = 1;
+          if (any) rt.numa_state = 1;
         }
       }
     } else {
       cudaGetLastError();
     }
   }
-  if (state == 1) { *set = cached; return true; }
+  if (rt.numa_state == 1) { *set = rt.numa_cpus; return true; }
   return false;
 }
 
@@ -351,8 +471,8 @@ ag_status ag_dev_alloc(void** dptr, size_t nbytes) {
   size_t sz = nbytes ? ((nbytes + 63) & ~(size_t)63) : 64;  // Arrow padding: 64-byte multiples
   cudaError_t e = cudaMalloc(dptr, sz);
   if (e != cudaSuccess) { *dptr = nullptr; return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__); }
-  AG_CUDA_TRY(cudaMemsetAsync(*dptr, 0, sz, g_rt.default_stream));
-  AG_CUDA_TRY(cudaStreamSynchronize(g_rt.default_stream));
+  AG_CUDA_TRY(cudaMemsetAsync(*dptr, 0, sz, cur().default_stream));
+  AG_CUDA_TRY(cudaStreamSynchronize(cur().default_stream));
   return AG_OK;
 }
 ag_status ag_dev_free(void* dptr) {
@@ -388,25 +508,28 @@ ag_status ag_stream_create(ag_stream_t* s) {
   AG_TRY(ensure_init());
   cudaStream_t st;
   AG_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  register_stream(st, cur().device);
   *s = (ag_stream_t)st;
   return AG_OK;
 }
 ag_status ag_stream_destroy(ag_stream_t s) {
   if (!s) return AG_OK;
   AG_TRY(ensure_init());
-  cudaStream_t st = (cudaStream_t)s;
+  cudaStream_t st = resolve_stream(s);
   AG_CUDA_TRY(cudaStreamSynchronize(st));
   {
-    std::lock_guard<std::mutex> lk(g_rt.mu);
-    auto it = g_rt.workspaces.find(st);
-    if (it != g_rt.workspaces.end()) {
+    std::lock_guard<std::mutex> lk(g_ws_mu);
+    auto it = g_workspaces.find(st);
+    if (it != g_workspaces.end()) {
       Workspace* ws = it->second;
       cudaFree(ws->partials); cudaFree(ws->ticket); cudaFree(ws->scalars);
       if (ws->tile_status) cudaFree(ws->tile_status);
       cudaFreeHost(ws->h_scalars);
+      delete ws->seq_mu;
       delete ws;
-      g_rt.workspaces.erase(it);
+      g_workspaces.erase(it);
     }
+    g_stream_device.erase(st);
   }
   AG_CUDA_TRY(cudaStreamDestroy(st));
   return AG_OK;
@@ -444,14 +567,16 @@ ag_status ag_event_elapsed_ms(ag_event_t a, ag_event_t b, float* ms) {
 
 ag_status ag_flush_l2(ag_stream_t s) {
   AG_TRY(ensure_init());
+  cudaStream_t st = resolve_stream(s);
+  Runtime& rt = cur();
   {
-    std::lock_guard<std::mutex> lk(g_rt.mu);
-    if (!g_rt.flush_buf) {
-      g_rt.flush_bytes = (size_t)256 << 20;  // 256 MiB > 126 MB L2
-      AG_CUDA_TRY(cudaMalloc(&g_rt.flush_buf, g_rt.flush_bytes));
+    std::lock_guard<std::mutex> lk(rt.mu);
+    if (!rt.flush_buf) {
+      rt.flush_bytes = (size_t)256 << 20;  // 256 MiB > 126 MB L2
+      AG_CUDA_TRY(cudaMalloc(&rt.flush_buf, rt.flush_bytes));
     }
   }
-  AG_CUDA_TRY(cudaMemsetAsync(g_rt.flush_buf, 0x5a, g_rt.flush_bytes, resolve_stream(s)));
+  AG_CUDA_TRY(cudaMemsetAsync(rt.flush_buf, 0x5a, rt.flush_bytes, st));
   return AG_OK;
 }
 

@@ -594,6 +594,7 @@ ag_status launch_cumsum(CumsumParams& p, cudaStream_t st) {
   constexpr int kTileRows = kScTileBytes / sizeof(T);
   Workspace* ws;
   AG_TRY(get_workspace(st, &ws));
+  WorkspaceLock ws_lock(ws);
   p.n_tiles = (p.n + kTileRows - 1) / kTileRows;
   const int64_t n_groups = (p.n_tiles + kScGroup - 1) / kScGroup;
   const int64_t n_super = (n_groups + kScSuper - 1) / kScSuper;

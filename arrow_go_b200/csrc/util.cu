@@ -44,6 +44,8 @@ generate_kernel(int kind, unsigned long long seed, long long lo, long long hi, v
         case 2: ((int*)out)[i] = (int)(lo + (long long)k); break;
         case 3: ((double*)out)[i] = (double)(lo + (long long)k); break;
         case 4: byte |= (unsigned)((((z >> 32) * (unsigned long long)hi) >> 32) < (unsigned long long)lo) << e; break;
+        case 5: ((int*)out)[i] = (int)(lo + (long long)(((unsigned __int128)i * span) / n)); break;              // sorted ramp over [lo, hi]
+        case 6: ((int*)out)[i] = (int)(lo + (long long)(((unsigned __int128)(n - 1 - i) * span) / n)); break;  // reverse-sorted
         default: break;
       }
     }
@@ -70,7 +72,7 @@ ag_status ag_checksum64_dev(const void* d_buf, size_t n_words, uint64_t* d_res, 
 
 ag_status ag_generate_dev(int kind, uint64_t seed, int64_t lo, int64_t hi, void* d_out, size_t n, ag_stream_t s) {
   AG_TRY(ensure_init());
-  if (kind < 0 || kind > 4) AG_FAIL(AG_ERR_INVALID, "generate: bad kind %d", kind);
+  if (kind < 0 || kind > 6) AG_FAIL(AG_ERR_INVALID, "generate: bad kind %d", kind);
   if (kind != 0 && (hi < lo || (kind != 4 && (uint64_t)(hi - lo) >= (1ull << 32)))) AG_FAIL(AG_ERR_INVALID, "generate: need lo <= hi and hi-lo < 2^32");
   if (n == 0) return AG_OK;
   const int grid = grid_for((int64_t)((n + 7) / 8), kUtThreads * 2, 8);

@@ -84,3 +84,45 @@ def cumulative_sum_carry(local_total, local_has_null, dist, skip_nulls=False, de
     if start >= 1 << 63:
         start -= 1 << 64
     return start, (dead and not skip_nulls)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# The product's own communicator (include/arrowgpu.h "Multi-GPU"): HBM mailboxes written over NVLink by the Sum kernel
+# itself.  torch.distributed is only the out-of-band channel that all-gathers the 64-byte IPC handles at start-up.
+def create_comm(dist=None, device="cpu"):
+    """One rank's ag_comm_t.  world 1 (dist None): a self-contained communicator.  Otherwise every rank exports its
+    mailbox handle, the handles are all-gathered through `dist` (any backend), and the peers' mailboxes are mapped."""
+    import ctypes as C
+
+    from . import _native as N
+    comm = C.c_void_p()
+    if dist is None or dist.get_world_size() == 1:
+        N.call("ag_comm_create", C.byref(comm), 1, 0, None)
+        return comm
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    h = (C.c_ubyte * 64)()
+    N.call("ag_comm_local_handle", world, h)
+    mine = torch.tensor(list(bytes(h)), dtype=torch.uint8, device=device)
+    parts = [torch.zeros(64, dtype=torch.uint8, device=device) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    table = b"".join(bytes(p.cpu().numpy().tobytes()) for p in parts)
+    buf = (C.c_ubyte * (64 * world)).from_buffer_copy(table)
+    N.call("ag_comm_create", C.byref(comm), world, rank, buf)
+    return comm
+
+
+def attach_nccl(comm, dist, device="cpu"):
+    """Optional: give the communicator an NCCL handle (rank 0 draws the id, `dist` broadcasts its 128 bytes)."""
+    import ctypes as C
+
+    import torch
+
+    from . import _native as N
+    ident = (C.c_ubyte * 128)()
+    if dist.get_rank() == 0:
+        N.call("ag_comm_unique_id", ident)
+    t = torch.tensor(list(bytes(ident)), dtype=torch.uint8, device=device)
+    dist.broadcast(t, src=0)
+    ident = (C.c_ubyte * 128).from_buffer_copy(bytes(t.cpu().numpy().tobytes()))
+    N.call("ag_comm_attach_nccl", comm, ident)

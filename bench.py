@@ -19,8 +19,11 @@ ONE JSON line on rank 0 (contract in the task statement):
             checked-in assembly) on a bounded sample of the same workload, 1 thread — what a
             reference CallFunction uses (arrow/compute/exec.go:164-170) — plus an all-cores
             row-sharded figure for context
-  others    kernel-only numbers for Sum / Greater / Filter / fused / Take at 100M rows
-`--impl reference` times the reference's CPU path alone (same metric, same config).
+  others    kernel-only numbers for Sum / Greater / Filter / fused / Take at 100M rows, Add on sliced (element-aligned)
+            operands, the reference-order Sum mode, the global Sum (mailbox and NCCL forms), BASELINE configs 4 and 5
+            at their full 1B rows split over the ranks (values asserted), PCIe peaks and the config-3 resident pipeline
+`--impl reference` times the reference's CPU path alone (same metric, same config): the full 100M-row chunked Add per
+step, one pinned core, span loop and clock in C (oracle/bench_cpu.c).
 """
 import argparse
 import ctypes as C
@@ -142,84 +145,244 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ reference / CPU arm -----
-def cpu_reference_add(rows_sample, reps, threads):
-    """The reference's own inner loop for this config: _arithmetic_binary_avx2(FLOAT64, OpAddChecked,
-    l, r, out, len) (base_arithmetic_avx2_amd64.go:35-39), called once per span like
-    executeSpans does (executor.go:598-623).  Returns rows/s."""
-    from oracle import oracle
-    ref = oracle.ref()
-    isa = oracle.host_isa()
-    if ref is not None:
-        fn = getattr(ref, f"arithmetic_binary_{isa}")
-        kind = "reference"
+def bench_config(rows, world):
+    """The `config` object, identical for both arms."""
+    return {"workload": "compute.Add(float64,float64) on a 100M-row chunked array per GPU (BASELINE.json configs[1])",
+            "rows_per_gpu": rows, "chunks": f"left {L_CHUNK}-row chunks, right {R_CHUNK}-row chunks -> {len(spans_for(rows, L_CHUNK, R_CHUNK))} spans, one contiguous output",
+            "l2": "inputs (1.6 GB) + output (0.8 GB) per step exceed the 126 MB L2 (and every CPU cache); no flush needed",
+            "parallelism": f"row-range x{world}"}
 
-        def run(l, r, o, n):
-            fn(12, 21, l, r, o, n)
-    else:
-        cpu = oracle.cpu()
-        kind = "port"
 
-        def run(l, r, o, n):
-            cpu.ref_arith_binary(12, 21, 0, l, r, o, n)
-    rng = np.random.default_rng(0x94378165)
-    a = rng.integers(-(1 << 20), 1 << 20, rows_sample).astype(np.float64)
-    b = rng.integers(-(1 << 20), 1 << 20, rows_sample).astype(np.float64)
-    out = np.empty(rows_sample)
-    spans = spans_for(rows_sample, L_CHUNK, R_CHUNK)
+class CpuAdd:
+    """The reference's own inner loop for this config — _arithmetic_binary_avx2(FLOAT64, OpAddChecked, l, r, out, len)
+    (base_arithmetic_avx2_amd64.go:35-39) called once per span like executeSpans does (executor.go:598-623) — timed by
+    the C harness oracle/bench_cpu.c: span loop and clock_gettime in C, the thread pinned to one core."""
 
-    def shard(lo, hi):
-        for pos, ln in spans:
-            s, e = max(pos, lo), min(pos + ln, hi)
-            if e > s:
-                run(a.ctypes.data + 8 * s, b.ctypes.data + 8 * s, out.ctypes.data + 8 * s, e - s)
-
-    def step():
-        if threads == 1:
-            shard(0, rows_sample)
+    def __init__(self, rows):
+        from oracle import oracle
+        self.rows = rows
+        self.h = oracle.bench()
+        ref = oracle.ref()
+        self.isa = oracle.host_isa()
+        if ref is not None:
+            self.fn = C.cast(getattr(ref, f"arithmetic_binary_{self.isa}"), C.c_void_p)
+            self.kind = "reference"
         else:
-            cuts = np.linspace(0, rows_sample, threads + 1).astype(np.int64)
-            list(pool.map(lambda i: shard(int(cuts[i]), int(cuts[i + 1])), range(threads)))
+            self.fn = C.cast(oracle.cpu().ref_arith_binary_native_abi, C.c_void_p)
+            self.kind = "port"
+        rng = np.random.default_rng(0x94378165)   # dataset E: integers stored as double
+        self.a = rng.integers(-(1 << 20), 1 << 20, rows).astype(np.float64)
+        self.b = rng.integers(-(1 << 20), 1 << 20, rows).astype(np.float64)
+        self.out = np.zeros(rows)
+        try:
+            self.cores = sorted(os.sched_getaffinity(0))
+        except AttributeError:
+            self.cores = list(range(os.cpu_count() or 1))
 
-    pool = ThreadPoolExecutor(threads) if threads > 1 else None
-    step()  # warm-up (page faults)
-    best = float("inf")
-    tot = 0.0
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        step()
-        dt = time.perf_counter() - t0
-        best = min(best, dt)
-        tot += dt
-    if pool:
-        pool.shutdown()
-    assert np.array_equal(out[:1000], a[:1000] + b[:1000])
-    return rows_sample * reps / tot, rows_sample / best, kind, isa
+    def _run(self, lo, hi, warmup, steps, core):
+        times = (C.c_double * steps)()
+        if core is not None:
+            self.h.bench_pin_to_core(core)
+        self.h.bench_add_f64_chunked(self.fn, 12, 21, self.a.ctypes.data, self.b.ctypes.data, self.out.ctypes.data, lo, hi,
+                                     L_CHUNK, R_CHUNK, warmup, steps, times)
+        return list(times)
+
+    def one_core(self, warmup, steps):
+        """rows/s over exactly `steps` timed full-size steps on one pinned core (what a reference CallFunction uses,
+        arrow/compute/exec.go:164-170)."""
+        saved = os.sched_getaffinity(0)
+        try:
+            t = self._run(0, self.rows, warmup, steps, self.cores[len(self.cores) // 2])
+        finally:
+            os.sched_setaffinity(0, saved)
+        assert np.array_equal(self.out[:1000], self.a[:1000] + self.b[:1000]) and np.array_equal(self.out[-1000:], self.a[-1000:] + self.b[-1000:])
+        return self.rows * steps / sum(t), self.rows / min(t), sum(t) / steps
+
+    def all_cores(self, warmup, steps):
+        """Context only (NOT a reference feature): the same loop row-range sharded over every host core, one pinned
+        thread per core, wall clock around the whole pool."""
+        T = len(self.cores)
+        cuts = np.linspace(0, self.rows, T + 1).astype(np.int64)
+        with ThreadPoolExecutor(T) as pool:
+            list(pool.map(lambda i: self._run(int(cuts[i]), int(cuts[i + 1]), 1, 1, self.cores[i]), range(T)))   # page faults, pin
+            t0 = time.perf_counter()
+            list(pool.map(lambda i: self._run(int(cuts[i]), int(cuts[i + 1]), 0, steps, self.cores[i]), range(T)))
+            dt = time.perf_counter() - t0
+        return self.rows * steps / dt, T
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    sample = int(os.environ.get("AG_BENCH_REF_SAMPLE", "16000000"))  # rows per step of the bounded sample (tests shrink it)
+    rows = int(os.environ.get("AG_BENCH_REF_ROWS", str(args.rows)))   # the CPU tests shrink it
+    W, K = max(args.warmup, 1), max(args.steps, 1)
     t0 = time.perf_counter()
-    for _ in range(max(args.warmup, 1) - 1):
-        pass
-    one, one_best, kind, isa = cpu_reference_add(sample, max(args.steps, 3), 1)
-    allc, allc_best, _, _ = cpu_reference_add(sample * 4, max(args.steps, 3), cores)
+    cpu = CpuAdd(rows)
+    one, one_best, s_per_step = cpu.one_core(min(W, 3), K)
+    allc, T = cpu.all_cores(1, max(2, min(K, 5)))
     wall = time.perf_counter() - t0
     line = {
-        "impl": "reference", "metric": METRIC, "value": one, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ROWS / one * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "compute.Add(float64,float64), 100M-row chunked array (1M-row x 999,983-row chunks), 1 call = 1 goroutine",
-                   "rows": ROWS, "timing": "wall clock, host resident"},
-        "cpu_baseline": {"value": one, "unit": "rows/s", "cores": 1, "kind": kind, "isa": isa,
-                         "sample": f"{sample} rows x {max(args.steps, 3)} steps of the same chunked Add (the reference executes a CallFunction's spans on one goroutine, exec.go:164-170)",
-                         "all_cores": {"value": allc, "unit": "rows/s", "cores": cores, "note": "row-range sharded over every host core; NOT a reference feature, context only"}},
+        "impl": "reference", "metric": METRIC, "value": one, "unit": "rows/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
+        "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": bench_config(rows, args.gpus),
+        "cpu_baseline": {"value": one, "unit": "rows/s", "cores": 1, "kind": cpu.kind, "isa": cpu.isa, "best_step": one_best,
+                         "sample": f"the full workload: {rows} rows x {K} steps, span loop + clock_gettime in C (oracle/bench_cpu.c), thread pinned to core "
+                                   f"{cpu.cores[len(cpu.cores) // 2]}; the reference executes a CallFunction's spans on one goroutine (exec.go:164-170)",
+                         "all_cores": {"value": allc, "unit": "rows/s", "cores": T, "note": "row-range sharded over every host core, one pinned thread each; NOT a reference feature, context only"}},
         "e2e": {"value": one, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0, "wall_s": wall,
+        "gpu_launches": 0, "wall_s": wall, "timing": "clock_gettime(CLOCK_MONOTONIC) per step inside the C harness, host resident",
     }
     _emit(line)
+
+
+# ------------------------------------------------------------------ helpers of our arm -----
+def _mix64_np(z):
+    with np.errstate(over="ignore"):
+        z = z + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def full_size_configs(N, comm, dist, rank, world, peak, timed, DeviceBuffer, total_rows):
+    """BASELINE configs[3] and [4]: Take(int64 values, int32 indices) with the 1B-row (8 GB) values table replicated on
+    every GPU and 1B random indices sharded by row range; Int64 Sum over 1B rows sharded by row range with the global
+    fold.  The results are ASSERTED: the Sum against the oracle's generator twin + wrapping sum of every rank's shard,
+    the Take element by element on sampled windows (values[i] = mix64(i)), by cross-checking the windowed path's whole
+    output against the direct path's through the order-sensitive device checksum, and through a planted bad index."""
+    from oracle import oracle
+    cpu = oracle.cpu()
+    out = {}
+    a, b = C.c_int64(), C.c_int64()
+    N.call("ag_shard_range", total_rows, rank, world, C.byref(a), C.byref(b))
+    lo, n = a.value, b.value - a.value
+    scal = DeviceBuffer(64)
+    # ---- C5: Int64 Sum, column = mix64(seed + global row) (full range, wraps)
+    col = DeviceBuffer(max(n, 1) * 8)
+    N.call("ag_generate_dev", 0, 0x94378165 + lo, 0, 0, col.ptr, n, None)
+    ms_local = timed(lambda: N.call("ag_sum_i64_dev", col.ptr, n, scal.ptr, None), 3, 10)
+    ms = timed(lambda: N.call("ag_sum_i64_global_dev", comm, col.ptr, n, scal.ptr, None), 3, 10)
+    N.call("ag_stream_sync", None)
+    got = int(scal.to_numpy(np.int64, 1)[0])
+    want, chunk = 0, 1 << 26
+    tmp = np.empty(chunk, dtype=np.uint64)
+    for off in range(0, n, chunk):
+        m = min(chunk, n - off)
+        cpu.ref_generate(0, 0x94378165 + lo + off, 0, 0, tmp.ctypes.data, m)
+        want = (want + cpu.ref_sum_i64(tmp.ctypes.data, m)) % (1 << 64)
+    if dist is not None:
+        import torch
+        t = torch.tensor([want - (1 << 64) if want >= 1 << 63 else want], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)   # wrapping int64 sum of the per-rank expected values (verification plumbing only)
+        want = int(t.item()) % (1 << 64)
+    assert got % (1 << 64) == want, f"config 5: global Sum {got} != expected {want}"
+    out["config5_sum_i64_1b_rows"] = {"total_rows": total_rows, "rows_per_gpu": n, "ranks": world, "ms": ms, "ms_local_sum_only": ms_local,
+                                      "rows_per_s": total_rows / ms * 1e3, "gbs_per_gpu": 8.0 * n / ms / 1e6, "frac": 8.0 * n / ms / 1e6 / peak,
+                                      "verified": "global value == wrapping sum of the oracle's generator twin over all 1B rows",
+                                      "note": "row-range shards (ag_shard_range), Sum + cross-GPU fold in one kernel (ag_sum_i64_global_dev)"}
+    col.free()
+    # ---- C4: Take
+    table_rows = total_rows
+    table = DeviceBuffer(table_rows * 8); idx = DeviceBuffer(max(n, 1) * 4); o = DeviceBuffer(max(n, 1) * 8); bad = DeviceBuffer(64); ck = DeviceBuffer(64)
+    N.call("ag_generate_dev", 0, 0, 0, 0, table.ptr, table_rows, None)                                   # values[i] = mix64(i)
+    N.call("ag_generate_dev", 2, 0x0FF1CE + lo, 0, min(table_rows, 1 << 31) - 1, idx.ptr, n, None)      # uniform in [0, table_rows)
+    N.call("ag_error_word_reset_dev", bad.ptr, None)
+    take = lambda: N.call("ag_take_primitive_dev", 64, table.ptr, None, 0, table_rows, 32, 1, idx.ptr, None, 0, n, 1, o.ptr, None, bad.ptr, None)
+    ms = timed(take, 2, 5)
+    N.call("ag_checksum64_dev", o.ptr, n, ck.ptr, None)
+    N.call("ag_stream_sync", None)
+    ck_windowed = int(ck.to_numpy(np.uint64, 1)[0])
+    win, checked = min(4_000_000, n), 0
+    for start in (0, n // 3, n - win):
+        ii = idx.to_numpy(np.int32, win, start * 4)
+        oo = o.to_numpy(np.uint64, win, start * 8)
+        assert np.array_equal(oo, _mix64_np(ii.astype(np.uint64))), f"config 4: take mismatch in the window at row {lo + start}"
+        checked += win
+    assert int(bad.to_numpy(np.int64, 1)[0]) == (1 << 63) - 1
+    N.call("ag_take_set_policy", 1, 0, 0, 0)       # the one-pass gather on the same inputs: whole-output cross-check
+    ms_direct = timed(take, 1, 2)
+    N.call("ag_take_set_policy", 0, 0, 0, 0)
+    N.call("ag_checksum64_dev", o.ptr, n, ck.ptr, None)
+    N.call("ag_stream_sync", None)
+    assert int(ck.to_numpy(np.uint64, 1)[0]) == ck_windowed, "config 4: windowed and direct paths disagree"
+    pos = n // 2 + 17
+    N.call("ag_upload", idx.ptr + pos * 4, np.array([-1], dtype=np.int32).ctypes.data, 4, None)
+    take()
+    N.call("ag_stream_sync", None)
+    assert int(bad.to_numpy(np.int64, 1)[0]) == pos, "config 4: planted out-of-range index not reported at its row"
+    out["config4_take_1b_rows"] = {"total_rows": total_rows, "rows_per_gpu": n, "table_rows": table_rows, "ranks": world, "ms": ms, "ms_direct_path": ms_direct,
+                                   "rows_per_s": total_rows / ms * 1e3, "gbs_per_gpu": 20.0 * n / ms / 1e6, "frac": 20.0 * n / ms / 1e6 / peak,
+                                   "verified": f"{checked} rows per rank element by element (values[i] = mix64(i)); whole output: checksum(windowed) == checksum(direct); planted bad index found at its row",
+                                   "note": "8 GB values table replicated per GPU, indices row-range sharded, no collective (SURVEY 8e)"}
+    for buf in (table, idx, o, bad, ck, scal):
+        buf.free()
+    return out
+
+
+def link_peaks(N, h_src, h_dst, d_a, d_b, nbytes, Event, barrier, max_over_ranks):
+    """Pinned-host <-> HBM copy rates of THIS box, measured beside the e2e number: H2D alone, D2H alone, both at once
+    on two streams (what the host-pointer pipeline does).  Every rank copies at the same time, so at N > 1 these are
+    the per-GPU rates under contention for the host's root complexes."""
+    from arrow_go_b200.device import Stream
+    s1, s2 = Stream(), Stream()
+
+    def run(h2d, d2h, reps=3):
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            if h2d:
+                N.call("ag_upload", d_a.ptr, h_src.ptr, nbytes, s1.handle)
+            if d2h:
+                N.call("ag_download", h_dst.ptr, d_b.ptr, nbytes, s2.handle)
+        s1.sync(); s2.sync()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        return (int(h2d) + int(d2h)) * nbytes * reps / dt / 1e9
+    run(True, True, 1)
+    out = {"h2d_gbs": run(True, False), "d2h_gbs": run(False, True), "bidirectional_gbs": run(True, True), "bytes_per_copy": nbytes}
+    s1.close(); s2.close()
+    return out
+
+
+def c3_pipeline(N, h_vals, h_out, d_vals, d_out, rows, rank, Event, barrier, max_over_ranks):
+    """BASELINE config 3 end to end the way the design intends it: the int64 column is uploaded ONCE (pinned host ->
+    HBM), Greater(v, 89) + Filter run fused on the resident column, only the ~10 % selected rows (80 MB) come back.
+    Reported: the one-off upload, and the steady-state step (kernel + D2H of the result) on the resident column."""
+    scal = None
+    from arrow_go_b200.device import DeviceBuffer
+    scal = DeviceBuffer(64)
+    N.call("ag_generate_dev", 1, 0x0FF1CE + rank * rows, 0, 99, d_vals.ptr, rows, None)
+    N.call("ag_download", h_vals.ptr, d_vals.ptr, rows * 8, None)
+    N.call("ag_stream_sync", None)
+    sc = np.array([89], dtype=np.int64)
+    barrier()
+    t0 = time.perf_counter()
+    N.call("ag_upload", d_vals.ptr, h_vals.ptr, rows * 8, None)
+    N.call("ag_stream_sync", None)
+    t_up = max_over_ranks(time.perf_counter() - t0)
+
+    def step():
+        N.call("ag_filter_compare_scalar_dev", N.INT64, N.CMP_GT, d_vals.ptr, sc.ctypes.data, rows, d_out.ptr, rows, scal.ptr, None)
+        N.call("ag_stream_sync", None)
+        cnt = int(scal.to_numpy(np.int64, 1)[0])
+        N.call("ag_download", h_out.ptr, d_out.ptr, cnt * 8, None)
+        N.call("ag_stream_sync", None)
+        return cnt
+    cnt = step()
+    barrier()
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        cnt = step()
+    t_step = max_over_ranks(time.perf_counter() - t0) / reps
+    hv = np.frombuffer((C.c_char * (rows * 8)).from_address(h_vals.ptr), dtype=np.int64, count=1 << 20)
+    ho = np.frombuffer((C.c_char * (rows * 8)).from_address(h_out.ptr), dtype=np.int64, count=int((hv > 89).sum()))
+    assert np.array_equal(ho, hv[hv > 89]), "config 3 pipeline: filtered rows differ"
+    scal.free()
+    return {"rows": rows, "selected_rows": cnt, "upload_once_ms": t_up * 1e3, "upload_gbs": rows * 8 / t_up / 1e9,
+            "resident_step_ms": t_step * 1e3, "resident_rows_per_s": rows / t_step, "d2h_bytes_per_step": cnt * 8,
+            "first_call_ms": (t_up + t_step) * 1e3, "first_call_rows_per_s": rows / (t_up + t_step),
+            "note": "Greater(int64, 89) + Filter fused (ag_filter_compare_scalar_dev) on the resident column; wall clock incl. the count readback and the D2H of the selected rows"}
 
 
 # ------------------------------------------------------------------ our arm ---------------
@@ -233,6 +396,8 @@ def main():
     ap.add_argument("--no-others", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-full-configs", action="store_true", help="skip BASELINE configs 4/5 at 1B rows")
+    ap.add_argument("--full-rows", type=int, default=1_000_000_000, help="total rows of configs 4/5 (split over the ranks)")
     args = ap.parse_args()
     _claim_stdout()
     if args.impl == "reference":
@@ -256,6 +421,15 @@ def main():
     from arrow_go_b200.device import DeviceBuffer, Event, PinnedArray
 
     N.call("ag_init", local_rank)
+    from arrow_go_b200 import sharding
+    comm = sharding.create_comm(dist, device="cuda") if dist is not None else sharding.create_comm(None)
+    have_nccl = False
+    if dist is not None:
+        try:
+            sharding.attach_nccl(comm, dist, device="cuda")
+            have_nccl = True
+        except Exception as e:  # no libnccl.so.2 the product can dlopen: the mailbox form still runs
+            print(f"rank {rank}: NCCL attach failed: {e}", file=sys.stderr)
     rows = args.rows
     W, K = max(args.warmup, 3), max(args.steps, 1)
     peak, peak_kind = peaks()
@@ -335,24 +509,24 @@ def main():
         others["sum_f64"] = {"rows_per_s": world * rows / ms * 1e3, "gbs_per_gpu": 8.0 * rows / ms / 1e6, "frac": 8.0 * rows / ms / 1e6 / peak, "ms": ms}
         ms = timed(lambda: N.call("ag_sum_i64_dev", dl.ptr, rows, scal.ptr, None), W, K)
         others["sum_i64"] = {"rows_per_s": world * rows / ms * 1e3, "gbs_per_gpu": 8.0 * rows / ms / 1e6, "frac": 8.0 * rows / ms / 1e6 / peak, "ms": ms}
-        if dist is not None:
-            import torch
-            t = torch.zeros(1, dtype=torch.int64, device="cuda")
-
-            def sum_allreduce():
-                N.call("ag_sum_i64_dev", dl.ptr, rows, scal.ptr, None)
-                N.call("ag_copy_dev", t.data_ptr(), scal.ptr, 8, None)
-                N.call("ag_stream_sync", None)
-                dist.all_reduce(t)
-            for _ in range(W):
-                sum_allreduce()
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(K):
-                sum_allreduce()
-            torch.cuda.synchronize()
-            ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / K
-            others["sum_i64_global_nccl"] = {"rows_per_s": world * rows / ms * 1e3, "ms": ms, "note": "per-GPU Sum + 8-byte NCCL all-reduce, wall clock"}
+        # reference-order mode (bit-exact AVX2 association, one warp, latency-bound by design) next to the default
+        ms = timed(lambda: N.call("ag_sum_f64_reforder_dev", dl.ptr, 8192, scal.ptr, None), W, K)
+        ms_def = timed(lambda: N.call("ag_sum_f64_dev", dl.ptr, 8192, scal.ptr, None), W, K)
+        others["sum_f64_8192_rows"] = {"mode_default_ms": ms_def, "mode_reference_order_ms": ms, "note": "BASELINE configs[0] size; launch-bound (the reference's cache-resident loop: ~0.7-2 us)"}
+        ms = timed(lambda: N.call("ag_sum_f64_reforder_dev", dl.ptr, rows, scal.ptr, None), 1, 2)
+        others["sum_f64_reference_order_mode"] = {"rows_per_s": world * rows / ms * 1e3, "gbs_per_gpu": 8.0 * rows / ms / 1e6, "frac": 8.0 * rows / ms / 1e6 / peak, "ms": ms,
+                                                  "note": "ag_sum_f64_reforder: 32 serial chains = the AVX2 order bit for bit; n/32 dependent adds, a parity tool not a fast path"}
+        others["sum_f64"]["mode"] = "default: compensated (TwoSum) fixed tree, <= 1 ULP from the exactly rounded sum"
+        # global Sum over the ranks: the fold is fused into the Sum kernel (HBM mailboxes over NVLink); NCCL form beside it
+        ms = timed(lambda: N.call("ag_sum_i64_global_dev", comm, dl.ptr, rows, scal.ptr, None), W, K)
+        others["sum_i64_global_mailbox"] = {"rows_per_s": world * rows / ms * 1e3, "ms": ms, "ranks": world,
+                                            "note": "per-GPU Sum + cross-GPU fold in ONE kernel (peer stores into HBM mailboxes, rank-order fold); CUDA events, max over ranks, no host sync"}
+        ms = timed(lambda: N.call("ag_sum_f64_global_dev", comm, dl.ptr, rows, scal.ptr, None), W, K)
+        others["sum_f64_global_mailbox"] = {"rows_per_s": world * rows / ms * 1e3, "ms": ms, "ranks": world}
+        if have_nccl:
+            ms = timed(lambda: N.call("ag_sum_i64_global_nccl_dev", comm, dl.ptr, rows, scal.ptr, None), W, K)
+            others["sum_i64_global_nccl"] = {"rows_per_s": world * rows / ms * 1e3, "ms": ms, "ranks": world,
+                                             "note": "per-GPU Sum + ncclAllReduce(8 bytes) issued by libarrowgpu on the same stream; CUDA events, max over ranks, no host sync"}
         # Greater(int64, 89) -> mask ; Filter ; fused ; Take
         vi = dr  # reuse: regenerate as int64 uniform [0,100)
         N.call("ag_generate_dev", 1, 0x0FF1CE + rank * rows, 0, 99, vi.ptr, rows, None)
@@ -376,7 +550,25 @@ def main():
         N.call("ag_error_word_reset_dev", bad.ptr, None)
         ms = timed(lambda: N.call("ag_take_primitive_dev", 64, vi.ptr, None, 0, rows, 32, 1, idx.ptr, None, 0, rows, 1, dout.ptr, None, bad.ptr, None), W, K)
         others["take_i64_i32idx_random"] = {"rows_per_s": world * rows / ms * 1e3, "gbs_per_gpu": 20.0 * rows / ms / 1e6, "frac": 20.0 * rows / ms / 1e6 / peak, "ms": ms,
-                                            "note": "algorithmic 20 B/row; random 8-byte gathers move 32-byte sectors"}
+                                            "path": "windowed (partition by 16 MB table window -> L2-resident gather -> un-permute), chosen by the on-device probe",
+                                            "note": "algorithmic 20 B/row; 100M random int32 indices into a 100M-row int64 table (800 MB); L2 flushed by the 2 GB the call itself moves"}
+        N.call("ag_take_set_policy", 1, 0, 0, 0)
+        ms = timed(lambda: N.call("ag_take_primitive_dev", 64, vi.ptr, None, 0, rows, 32, 1, idx.ptr, None, 0, rows, 1, dout.ptr, None, bad.ptr, None), 3, max(3, K // 4))
+        N.call("ag_take_set_policy", 0, 0, 0, 0)
+        others["take_i64_i32idx_random_direct_path"] = {"ms": ms, "frac": 20.0 * rows / ms / 1e6 / peak, "note": "same call forced onto the one-pass gather (round 1's kernel): one DRAM line per gathered row"}
+        # sorted indices: the probe keeps the direct kernel, which then streams the table (vector_selection.go:897-911)
+        N.call("ag_generate_dev", 5, 0, 0, rows - 1, idx.ptr, rows, None)
+        ms = timed(lambda: N.call("ag_take_primitive_dev", 64, vi.ptr, None, 0, rows, 32, 1, idx.ptr, None, 0, rows, 1, dout.ptr, None, bad.ptr, None), W, K)
+        others["take_i64_i32idx_sorted"] = {"rows_per_s": world * rows / ms * 1e3, "gbs_per_gpu": 20.0 * rows / ms / 1e6, "frac": 20.0 * rows / ms / 1e6 / peak, "ms": ms,
+                                            "path": "direct (probe: adjacent indices are neighbours)"}
+        N.call("ag_generate_dev", 2, 0x0FF1CE + 7 + rank * rows, 0, rows - 1, idx.ptr, rows, None)
+        # Add on sliced operands (Arrow slices are only element-aligned): l.slice(1, n) + r.slice(0, n)
+        N.call("ag_generate_dev", 3, 0x94378166 + rank * rows, -(1 << 20), 1 << 20, vi.ptr, rows, None)
+        ms = timed(lambda: N.call("ag_arith_binary_dev", N.FLOAT64, N.OP_ADD_CHECKED, N.SHAPE_AA, dl.ptr + 8, vi.ptr, dout.ptr, rows - 1, None), W, K)
+        others["add_f64_left_sliced_by_1"] = {"ms": ms, "frac": 24.0 * (rows - 1) / ms / 1e6 / peak, "note": "left operand 8 bytes off a 16-byte boundary: aligned 128-bit loads + shuffle/funnel shift"}
+        ms = timed(lambda: N.call("ag_arith_binary_dev", N.FLOAT64, N.OP_ADD_CHECKED, N.SHAPE_AA, dl.ptr + 8, vi.ptr + 8, dout.ptr + 8, rows - 1, None), W, K)
+        others["add_f64_all_sliced_by_1"] = {"ms": ms, "frac": 24.0 * (rows - 1) / ms / 1e6 / peak, "note": "all three operands share the misalignment (what executeSpans produces): one head row, then the aligned path"}
+        N.call("ag_generate_dev", 1, 0x0FF1CE + rank * rows, 0, 99, vi.ptr, rows, None)
         # rows SURVEY §8(f) marks "next", same device-resident columns: promotion cast, min/max, cumulative sum
         ms = timed(lambda: N.call("ag_cast_numeric_dev", N.INT32, N.INT64, idx.ptr, dout.ptr, rows, None), W, K)
         others["cast_i32_to_i64"] = {"rows_per_s": world * rows / ms * 1e3, "gbs_per_gpu": 12.0 * rows / ms / 1e6, "frac": 12.0 * rows / ms / 1e6 / peak, "ms": ms}
@@ -394,6 +586,13 @@ def main():
         others["cumulative_sum_i64"] = {"rows_per_s": world * rows / ms * 1e3, "gbs_per_gpu": 16.0 * rows / ms / 1e6, "frac": 16.0 * rows / ms / 1e6 / peak, "ms": ms,
                                         "note": "single-pass scan, read once + write once (16 B/row)"}
         cstate.free(); idx.free(); bad.free(); scal.free()
+
+    # ---- BASELINE configs 4 and 5 at their full 1B rows, split over the ranks by ag_shard_range; values asserted ----
+    if not args.no_full_configs:
+        dl.free(); dr.free(); dout.free()
+        others.update(full_size_configs(N, comm, dist, rank, world, peak, timed, DeviceBuffer, args.full_rows))
+        dl, dr, dout = DeviceBuffer(rows * 8), DeviceBuffer(rows * 8), DeviceBuffer(rows * 8)
+        N.call("ag_generate_dev", 3, 0x94378165 + rank * rows, -(1 << 20), 1 << 20, dl.ptr, rows, None)
 
     launches_total = N.raw().ag_kernel_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
@@ -422,29 +621,34 @@ def main():
         dt = max_over_ranks(time.perf_counter() - t0)
         barrier()
         assert np.array_equal(ho.array[:4096], ha.array[:4096] + hb.array[:4096])
+        link = link_peaks(N, ha, ho, dl, dout, e_rows * 8, Event, barrier, max_over_ranks)
         e2e = {"value": world * e_rows * ke / dt, "unit": "rows/s", "h2d_bytes_per_step": 16 * e_rows, "d2h_bytes_per_step": 8 * e_rows,
-               "ms_per_step": dt / ke * 1e3, "link_gbs": 24.0 * e_rows * ke / dt / 1e9,
-               "how": "ag_arith_binary_spans(host ptrs) over the same 200-span chunked layout on ag_host_alloc (pinned) buffers; synchronous API timed by wall clock, max over ranks"}
+               "ms_per_step": dt / ke * 1e3, "link_gbs": 24.0 * e_rows * ke / dt / 1e9, "link_peak": link,
+               "frac_of_link_peak": (24.0 * e_rows * ke / dt / 1e9) / link["bidirectional_gbs"] if link.get("bidirectional_gbs") else None,
+               "how": "ag_arith_binary_spans(host ptrs) over the same 200-span chunked layout on ag_host_alloc (pinned) buffers; synchronous API timed by wall clock, max over ranks; "
+                      "link_peak = pinned cudaMemcpyAsync of 800 MB each way measured in this run (per GPU, all ranks copying at once)"}
+        e2e["config3_upload_once_pipeline"] = c3_pipeline(N, ha, ho, dl, dout, e_rows, rank, Event, barrier, max_over_ranks)
         ha.free(); hb.free(); ho.free()
 
     # ---- CPU baseline (rank 0, N=1 only) ----
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cores = os.cpu_count() or 1
-        one, _, kind, isa = cpu_reference_add(16_000_000, 5, 1)
-        allc, _, _, _ = cpu_reference_add(64_000_000, 5, cores)
-        cpu_baseline = {"value": one, "unit": "rows/s", "cores": 1, "kind": kind, "isa": isa,
-                        "sample": "16M rows x 5 steps of the same chunked Add through the reference's arithmetic_binary_avx2 (1 goroutine per CallFunction, exec.go:164-170)",
-                        "all_cores": {"value": allc, "unit": "rows/s", "cores": cores, "note": "row-range sharded over all host cores; not a reference feature"}}
+        cpu = CpuAdd(rows)
+        one, one_best, _ = cpu.one_core(2, 5)
+        allc, T = cpu.all_cores(1, 3)
+        cpu_baseline = {"value": one, "unit": "rows/s", "cores": 1, "kind": cpu.kind, "isa": cpu.isa, "best_step": one_best,
+                        "sample": f"the full workload ({rows} rows, 200 spans) x 5 steps through the reference's arithmetic_binary_{cpu.isa}, C harness pinned to one core "
+                                  "(1 goroutine per CallFunction, exec.go:164-170)",
+                        "all_cores": {"value": allc, "unit": "rows/s", "cores": T, "note": "row-range sharded over all host cores, one pinned thread each; not a reference feature"}}
+        del cpu
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_chunked,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "compute.Add(float64,float64) on a 100M-row chunked array per GPU (BASELINE.json configs[1])",
-                       "rows_per_gpu": rows, "chunks": f"left {L_CHUNK}-row chunks, right {R_CHUNK}-row chunks -> {len(spans)} spans, one contiguous output",
-                       "l2": "inputs (1.6 GB) + output (0.8 GB) per step exceed the 126 MB L2; no flush needed", "parallelism": f"row-range x{world}",
-                       "contiguous_ms_per_step": ms_contig, "per_span_launch_ms_per_step": ms_per_span},
+            "impl": "ours", "config": bench_config(rows, world),
+            "detail": {"contiguous_ms_per_step": ms_contig, "per_span_launch_ms_per_step": ms_per_span,
+                       "timing": "CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_bytes(),
                          "traffic_note": "bytes per launch, dram__bytes_read+write from profiles/r1/ncu_full_binary_spans_kernel.csv (same kernel, same shape)",
                          "peak_kind": peak_kind, "algorithmic_bytes_per_row": 24, "kernel": "binary_spans_kernel<double,OpAdd,AA>",

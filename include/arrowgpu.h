@@ -114,18 +114,27 @@ typedef int ag_status;
 /* sentinel written to *first_bad / *bad_pos when no element failed */
 #define AG_NO_ERROR_POS INT64_MAX
 
-typedef void* ag_stream_t; /* opaque (a CUDA stream); NULL = the library's default stream */
+typedef void* ag_stream_t; /* opaque (a CUDA stream); NULL = the current device's default stream */
 typedef void* ag_event_t;  /* opaque (a CUDA event) */
+typedef void* ag_comm_t;   /* opaque: one rank of a multi-GPU communicator */
 
 /* ================================================================================= *
  * Runtime, residency, streams
  * ================================================================================= */
 
-/* Bind the calling process to one device (one process per GPU) and create the stream
- * pool.  device < 0 selects LOCAL_RANK from the environment, else device 0.
- * Idempotent.  Every compute call initialises lazily with device -1 if this was never
- * called. */
+/* Initialise one device and its stream pool.  The first call names the process DEFAULT device
+ * (device < 0: LOCAL_RANK from the environment, else 0) — all a one-process-per-GPU rank needs.
+ * Idempotent; every compute call initialises lazily with device -1 if this was never called.
+ * A later ag_init(other) behaves like ag_set_device(other). */
 ag_status ag_init(int device);
+/* One process driving the whole box (the reference is ONE Go process whose take/filter fan out over
+ * goroutines, arrow/compute/selection.go:127-150): initialise every visible device and enable peer
+ * access between all pairs.  Then each worker thread picks its device with ag_set_device; streams,
+ * pinned and device allocations, and NULL-stream calls follow the calling thread's current device,
+ * and a call that is handed a stream always runs on that stream's device. */
+ag_status ag_init_all(int* n_devices);
+ag_status ag_set_device(int device);
+ag_status ag_get_device(int* device);
 ag_status ag_shutdown(void);
 ag_status ag_device_count(int* count);
 ag_status ag_device_info(int* device, int* sm_count, size_t* hbm_bytes, int* cc_major, int* cc_minor);
@@ -183,6 +192,41 @@ ag_status ag_sum_f64_dev(const double* d_buf, size_t n, double* d_res, ag_stream
 ag_status ag_sum_i64_dev(const int64_t* d_buf, size_t n, int64_t* d_res, ag_stream_t s);
 ag_status ag_sum_u64_dev(const uint64_t* d_buf, size_t n, uint64_t* d_res, ag_stream_t s);
 ag_status ag_sum_f64_reforder_dev(const double* d_buf, size_t n, double* d_res, ag_stream_t s);
+
+/* ================================================================================= *
+ * Multi-GPU: row-range shards, no data-path collective except the global Sum.
+ *   Sharding rule: ag_shard_range — ceil-balanced, cuts at multiples of 64 rows (no two shards
+ *   share a bitmap word).  Add / compare / filter / take run per shard with no exchange (take
+ *   replicates `values`); a bounds / overflow error is the minimum of the shards' error words.
+ *   Global Sum: ag_sum_*_global_dev runs the shard's reduction AND the fold over the ranks as
+ *   one kernel — the final (sum, error) pair is stored into every rank's HBM mailbox over
+ *   NVLink and folded in rank order, so every rank's *d_res holds the same bits, with no
+ *   second launch and no host synchronisation.  Every rank of the communicator must make the
+ *   call (in the same order when several are in flight).
+ *   Setting up the mailboxes:
+ *     one process per GPU : ag_comm_local_handle(world, h) on every rank; all-gather the
+ *                           AG_COMM_HANDLE_BYTES handles with the caller's own plumbing (MPI,
+ *                           torch.distributed, a socket); ag_comm_create(&c, world, rank, handles)
+ *     one process, n GPUs : ag_init_all; ag_comm_create_local(comms, n, devices)
+ *   NCCL (optional): ag_comm_unique_id on rank 0, broadcast the AG_COMM_ID_BYTES, then
+ *   ag_comm_attach_nccl on every rank; ag_sum_i64_global_nccl_dev = per-GPU Sum followed by
+ *   ncclAllReduce of the 8-byte result on the same stream.  libnccl.so.2 is dlopen'ed on
+ *   first use (AG_ERR_NOT_IMPLEMENTED when the process has none).
+ * ================================================================================= */
+#define AG_COMM_HANDLE_BYTES 64
+#define AG_COMM_ID_BYTES 128
+ag_status ag_shard_range(int64_t n_rows, int shard, int n_shards, int64_t* start, int64_t* stop);
+ag_status ag_comm_local_handle(int world, void* handle64);
+ag_status ag_comm_create(ag_comm_t* comm, int world, int rank, const void* all_handles);
+ag_status ag_comm_create_local(ag_comm_t* comms, int n, const int* devices);
+ag_status ag_comm_unique_id(void* id128);
+ag_status ag_comm_attach_nccl(ag_comm_t comm, const void* id128);
+ag_status ag_comm_info(ag_comm_t comm, int* world, int* rank, int* device);
+ag_status ag_comm_destroy(ag_comm_t comm);
+ag_status ag_sum_i64_global_dev(ag_comm_t comm, const int64_t* d_buf, size_t n, int64_t* d_res, ag_stream_t s);
+ag_status ag_sum_u64_global_dev(ag_comm_t comm, const uint64_t* d_buf, size_t n, uint64_t* d_res, ag_stream_t s);
+ag_status ag_sum_f64_global_dev(ag_comm_t comm, const double* d_buf, size_t n, double* d_res, ag_stream_t s);
+ag_status ag_sum_i64_global_nccl_dev(ag_comm_t comm, const int64_t* d_buf, size_t n, int64_t* d_res, ag_stream_t s);
 
 /* ================================================================================= *
  * Integer min/max — replaces {int,uint}{8,16,32,64}_max_min_{avx2,sse4,neon}
@@ -444,7 +488,8 @@ ag_status ag_take_set_policy(int mode, int64_t min_rows, int64_t min_table_bytes
 ag_status ag_checksum64_dev(const void* d_buf, size_t n_words, uint64_t* d_res, ag_stream_t s);
 /* kind: 0 = splitmix64(seed + i) as u64; 1 = uniform int64 in [lo, hi] (hi-lo+1 <= 2^32, via
  * multiply-shift on the high 32 bits); 2 = uniform int32 in [lo, hi]; 3 = double(k) with k
- * uniform integer in [lo, hi]; 4 = bitmap with P(bit)=lo/hi (n = bits). */
+ * uniform integer in [lo, hi]; 4 = bitmap with P(bit)=lo/hi (n = bits); 5 / 6 = sorted / reverse-sorted int32
+ * ramp over [lo, hi] (the sorted index datasets of SURVEY §8d). */
 ag_status ag_generate_dev(int kind, uint64_t seed, int64_t lo, int64_t hi, void* d_out, size_t n, ag_stream_t s);
 
 #ifdef __cplusplus

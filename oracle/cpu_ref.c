@@ -127,6 +127,12 @@ int ref_arith_binary(int type, int op, int shape, const void* l, const void* r, 
   }
 }
 
+/* same loop behind the reference's native signature (base_arithmetic.cc:465: type, op, l, r, out, len) so the C
+ * bench harness can time the restatement when oracle/_ref was never built */
+void ref_arith_binary_native_abi(int type, int8_t op, const void* l, const void* r, void* out, int len) {
+  (void)ref_arith_binary(type, op, 0, l, r, out, len);
+}
+
 /* unary: AbsoluteValue :160-176, Negate :194-205, NegateChecked :207-219 (unsigned -> 0),
  * Sign :221-234.  Float abs clears the sign bit (NaN payload preserved); float negate
  * is a sign flip (-x). */
@@ -885,6 +891,8 @@ void ref_generate(int kind, uint64_t seed, int64_t lo, int64_t hi, void* out, si
         b[i >> 3] |= (uint8_t)(bit << (i & 7));
         break;
       }
+      case 5: ((int32_t*)out)[i] = (int32_t)(lo + (int64_t)(((unsigned __int128)i * span) / n)); break;
+      case 6: ((int32_t*)out)[i] = (int32_t)(lo + (int64_t)(((unsigned __int128)(n - 1 - i) * span) / n)); break;
       default: return;
     }
   }

@@ -39,6 +39,7 @@ uint64_t ref_sum_u64(const uint64_t* buf, size_t n);
 
 /* arithmetic (all slots) */
 int ref_arith_binary(int type, int op, int shape, const void* l, const void* r, void* out, int64_t n);
+void ref_arith_binary_native_abi(int type, int8_t op, const void* l, const void* r, void* out, int len);
 int ref_arith_unary_same(int type, int op, const void* in, void* out, int64_t n);
 int ref_arith_unary_diff(int itype, int otype, int op, const void* in, void* out, int64_t n);
 /* checked integer arithmetic with ScalarBinaryNotNull / ScalarBinary slot semantics */

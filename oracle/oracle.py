@@ -30,6 +30,24 @@ def build(quiet=True):
         print(out.stdout)
 
 
+_bench = None
+
+
+def bench():
+    """oracle/libbench_cpu.so: the C timing harness of bench.py's CPU legs (pinning, span loop, clock_gettime)."""
+    global _bench
+    if _bench is None:
+        path = os.path.join(_HERE, "libbench_cpu.so")
+        if not os.path.exists(path):
+            build()
+        lib = C.CDLL(path)
+        lib.bench_pin_to_core.argtypes = [C.c_int]
+        lib.bench_add_f64_chunked.restype = i64
+        lib.bench_add_f64_chunked.argtypes = [c_p, C.c_int, C.c_int, c_p, c_p, c_p, i64, i64, i64, i64, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        _bench = lib
+    return _bench
+
+
 def cpu():
     global _cpu
     if _cpu is None:

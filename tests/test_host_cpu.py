@@ -186,7 +186,7 @@ def test_reference_arm_prints_exactly_one_json_line():
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--rows", "1000000", "--steps", "1", "--warmup", "0"],
-                         capture_output=True, text=True, timeout=300, env=dict(os.environ, AG_BENCH_REF_SAMPLE="500000"))
+                         capture_output=True, text=True, timeout=300, env=dict(os.environ, AG_BENCH_REF_ROWS="1000000"))
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, out.stdout[:500]
