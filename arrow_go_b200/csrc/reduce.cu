@@ -76,17 +76,17 @@ __device__ __forceinline__ T shfl_xor_t(T v, int m) {
 
 // Accumulator: integers are a plain wrapping sum; float64 carries the rounding error of every addition (TwoSum:
 // s + x = t + e exactly) in a second word.  16 bytes either way, which is the partials slot size.
-template <typename T> struct alignas(16) Acc {
-  T s; T pad;
-  __device__ __forceinline__ void zero() { s = T(0); pad = T(0); }
+template <typename T> struct Acc {
+  T s;
+  __device__ __forceinline__ void zero() { s = T(0); }
   __device__ __forceinline__ void add(T x) { s = s + x; }
   __device__ __forceinline__ void merge(const Acc& o) { s = s + o.s; }
-  __device__ __forceinline__ Acc shfl_xor(int m) const { Acc r; r.s = shfl_xor_t(s, m); r.pad = T(0); return r; }
+  __device__ __forceinline__ Acc shfl_xor(int m) const { Acc r; r.s = shfl_xor_t(s, m); return r; }
   __device__ __forceinline__ T value() const { return s; }
-  __device__ __forceinline__ T& pad_or_c() { return pad; }
-  __device__ __forceinline__ const T& pad_or_c() const { return pad; }
+  __device__ __forceinline__ ulonglong2 raw() const { return make_ulonglong2(*reinterpret_cast<const unsigned long long*>(&s), 0ull); }
+  static __device__ __forceinline__ Acc from_raw(const ulonglong2 v) { Acc r; r.s = *reinterpret_cast<const T*>(&v.x); return r; }
 };
-template <> struct alignas(16) Acc<double> {
+template <> struct Acc<double> {
   double s, c;
   __device__ __forceinline__ void zero() { s = 0.0; c = 0.0; }
   __device__ __forceinline__ void add(double x) {
@@ -99,8 +99,8 @@ template <> struct alignas(16) Acc<double> {
   __device__ __forceinline__ void merge(const Acc& o) { add(o.s); c = __dadd_rn(c, o.c); }
   __device__ __forceinline__ Acc shfl_xor(int m) const { Acc r; r.s = shfl_xor_t(s, m); r.c = shfl_xor_t(c, m); return r; }
   __device__ __forceinline__ double value() const { return __dadd_rn(s, c); }
-  __device__ __forceinline__ double& pad_or_c() { return c; }
-  __device__ __forceinline__ const double& pad_or_c() const { return c; }
+  __device__ __forceinline__ ulonglong2 raw() const { return make_ulonglong2((unsigned long long)__double_as_longlong(s), (unsigned long long)__double_as_longlong(c)); }
+  static __device__ __forceinline__ Acc from_raw(const ulonglong2 v) { Acc r; r.s = __longlong_as_double((long long)v.x); r.c = __longlong_as_double((long long)v.y); return r; }
 };
 
 // ---- cross-GPU exchange fused into the reduction (multi-GPU global Sum) -------------------------
@@ -113,10 +113,11 @@ template <> struct alignas(16) Acc<double> {
 template <typename T>
 __device__ __forceinline__ Acc<T> exchange_sum(Acc<T> mine, const SumExchange& x) {
   const int buf = (int)(x.epoch & 1ull);
+  const ulonglong2 me = mine.raw();
   for (int r = 0; r < x.world; ++r) {
     MailSlot* m = x.peers[r] + buf * x.world + x.rank;
-    m->s = *reinterpret_cast<const unsigned long long*>(&mine.s);
-    m->c = *reinterpret_cast<const unsigned long long*>(&mine.pad_or_c());
+    m->s = me.x;
+    m->c = me.y;
   }
   __threadfence_system();
   for (int r = 0; r < x.world; ++r) {
@@ -130,12 +131,10 @@ __device__ __forceinline__ Acc<T> exchange_sum(Acc<T> mine, const SumExchange& x
     do {
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(&m->flag) : "memory");
     } while (f != x.epoch);
-    Acc<T> o;
-    const unsigned long long vs = *reinterpret_cast<volatile unsigned long long*>(&m->s);
-    const unsigned long long vc = *reinterpret_cast<volatile unsigned long long*>(&m->c);
-    o.s = *reinterpret_cast<const T*>(&vs);
-    o.pad_or_c() = *reinterpret_cast<const T*>(&vc);
-    g.merge(o);
+    ulonglong2 v;
+    v.x = *reinterpret_cast<volatile unsigned long long*>(&m->s);
+    v.y = *reinterpret_cast<volatile unsigned long long*>(&m->c);
+    g.merge(Acc<T>::from_raw(v));
   }
   return g;
 }
@@ -159,8 +158,8 @@ __device__ __forceinline__ Acc<T> block_tree_sum(Acc<T> v, Acc<T>* smem /* >= 8 
 }
 
 template <typename T, bool kAligned>
-__global__ void __launch_bounds__(kSumThreads, sum_blocks_per_sm<T>())
-sum_kernel(const T* __restrict__ in, size_t n, Acc<T>* __restrict__ partials, unsigned* __restrict__ ticket,
+__global__ void __launch_bounds__(kSumThreads, std::is_floating_point<T>::value ? 4 : 5)
+sum_kernel(const T* __restrict__ in, size_t n, ulonglong2* __restrict__ partials, unsigned* __restrict__ ticket,
            T* __restrict__ out, const SumExchange xch) {
   __shared__ Acc<T> smem[8];
   __shared__ bool is_last;
@@ -205,7 +204,7 @@ sum_kernel(const T* __restrict__ in, size_t n, Acc<T>* __restrict__ partials, un
     return;
   }
   if (threadIdx.x == 0) {
-    partials[blockIdx.x] = v;
+    partials[blockIdx.x] = v.raw();
     __threadfence();
     const unsigned t = atomicAdd(ticket, 1u);
     is_last = (t == gridDim.x - 1);
@@ -216,8 +215,7 @@ sum_kernel(const T* __restrict__ in, size_t n, Acc<T>* __restrict__ partials, un
   // fixed-order reduction of the partials: thread t takes t, t+256, ... then the block tree
   Acc<T> acc; acc.zero();
   for (unsigned i = threadIdx.x; i < gridDim.x; i += kSumThreads) {
-    const ulonglong2 raw = __ldcg(reinterpret_cast<const ulonglong2*>(partials + i));
-    acc.merge(*reinterpret_cast<const Acc<T>*>(&raw));
+    acc.merge(Acc<T>::from_raw(__ldcg(partials + i)));
   }
   acc = block_tree_sum(acc, smem);
   if (threadIdx.x == 0) {
@@ -293,9 +291,9 @@ ag_status launch_sum(const T* d_in, size_t n, T* d_res, cudaStream_t st, const S
   const bool aligned = (reinterpret_cast<uintptr_t>(d_in) & 15) == 0;
   const int grid = sum_grid<T>(n >> 1);
   if (aligned)
-    sum_kernel<T, true><<<grid, kSumThreads, 0, st>>>(d_in, n, (Acc<T>*)ws->partials, ws->ticket, d_res, x);
+    sum_kernel<T, true><<<grid, kSumThreads, 0, st>>>(d_in, n, (ulonglong2*)ws->partials, ws->ticket, d_res, x);
   else
-    sum_kernel<T, false><<<grid, kSumThreads, 0, st>>>(d_in, n, (Acc<T>*)ws->partials, ws->ticket, d_res, x);
+    sum_kernel<T, false><<<grid, kSumThreads, 0, st>>>(d_in, n, (ulonglong2*)ws->partials, ws->ticket, d_res, x);
   return check_launch("sum_kernel");
 }
 
