@@ -363,6 +363,8 @@ ag_status take_indices_dev(int index_width, const uint8_t* mask, const uint8_t* 
   p.out_len = reinterpret_cast<long long*>(d_out_len);
   AG_TRY(check_filter_args(p, "take_indices"));
   if (n > 0 && !mask) AG_FAIL(AG_ERR_INVALID, "take_indices: NULL mask");
+  if (p.emit_nulls && !out_valid && capacity > 0)
+    AG_FAIL(AG_ERR_INVALID, "take_indices: EMIT_NULLS with a mask validity bitmap needs an output validity bitmap (a null mask slot would otherwise read as row 0)");
   if (n == 0) { AG_CUDA_TRY(cudaMemsetAsync(d_out_len, 0, sizeof(int64_t), st)); return AG_OK; }
   if (index_width == 16) {
     if (n >= 65535) AG_FAIL(AG_ERR_INVALID, "take_indices: uint16 indices need n < 65535 (vector_selection.go:229-231)");

@@ -61,6 +61,10 @@ struct Temps {
   }
   template <typename T> ag_status alloc_t(T** p, size_t nbytes) { return alloc(reinterpret_cast<void**>(p), nbytes); }
   ~Temps() {
+    // An early (error) return may leave H2D / D2H copies of CALLER memory in flight on this pooled stream: wait for
+    // them before the function returns and before the stream goes back to the pool.  On the success paths the
+    // stream is already idle and this costs a few microseconds.
+    cudaStreamSynchronize(st);
     for (void* p : ptrs) cudaFreeAsync(p, st);
   }
 };
