@@ -140,45 +140,81 @@ static ag_status pipelined_rows(int64_t n, int n_in, const void* const* in, cons
   return rc != AG_OK ? rc : rs;
 }
 
-// Host flavour of the batched-span call: every (span, sub-chunk) becomes one stage of the same
-// 3-deep H2D / kernel / D2H pipeline, so consecutive spans of a chunked call overlap exactly like
-// the chunks of one long span do.
+// Host flavour of the batched-span call.  Spans are cut into pieces of at most one stage (32 MB per operand), pieces
+// that continue each other in host memory on every operand are merged (slices of one allocation: a chunked array built
+// from NewSlice views), and pieces are PACKED into stages of up to 32 MB: each piece is copied to the next 16-byte
+// aligned offset of the stage's device buffers, ONE kernel runs over the packed range (the few padding rows between
+// pieces compute garbage nobody reads), and each piece is copied back from the same offset.  So a chunked call with
+// 8 MB chunks runs the same 3-deep H2D / kernel / D2H pipeline, with the same stage size, as one contiguous column
+// (measured on 100M float64 rows in 200 spans: 38.4 ms per call with one stage per span, 32 ms packed = the contiguous
+// call; scripts/e2e_probe.py).
 static ag_status host_arith_binary_spans(int type, int8_t op, int shape, const ag_span3* spans, int64_t n_spans) {
   AG_TRY(ensure_init());
   const int w = type_width(type);
   if (w == 0) AG_FAIL(AG_ERR_TYPE, "arith: unsupported type id %d", type);
   if (n_spans < 0 || (n_spans > 0 && !spans)) AG_FAIL(AG_ERR_INVALID, "arith_spans: bad span table");
-  int64_t max_n = 0;
+  const bool la = shape != AG_SHAPE_SA, ra = shape != AG_SHAPE_AS;
+  const int64_t chunk = (kChunkBytes / w) & ~(int64_t)1023;   // rows per stage
+  const int64_t pad = 16 / w;                                   // pieces start on 16-byte boundaries of the stage
+  struct Piece { const char* l; const char* r; char* out; int64_t n; };
+  std::vector<Piece> pieces;
+  const void* scalar_l = nullptr; const void* scalar_r = nullptr;
   for (int64_t i = 0; i < n_spans; ++i) {
-    if (spans[i].n < 0) AG_FAIL(AG_ERR_INVALID, "arith_spans: negative length");
-    if (spans[i].n > 0 && (!spans[i].l || !spans[i].r || !spans[i].out)) AG_FAIL(AG_ERR_INVALID, "arith_spans: NULL operand");
-    if (spans[i].n > max_n) max_n = spans[i].n;
+    const ag_span3& sp = spans[i];
+    if (sp.n < 0) AG_FAIL(AG_ERR_INVALID, "arith_spans: negative length");
+    if (sp.n == 0) continue;
+    if (!sp.l || !sp.r || !sp.out) AG_FAIL(AG_ERR_INVALID, "arith_spans: NULL operand");
+    if (!la) scalar_l = sp.l;
+    if (!ra) scalar_r = sp.r;
+    for (int64_t r0 = 0; r0 < sp.n; r0 += chunk) {
+      Piece p{(const char*)sp.l + (la ? r0 * w : 0), (const char*)sp.r + (ra ? r0 * w : 0), (char*)sp.out + r0 * w, sp.n - r0 < chunk ? sp.n - r0 : chunk};
+      if (!pieces.empty()) {
+        Piece& q = pieces.back();
+        const bool cont = (!la || q.l + q.n * w == p.l) && (!ra || q.r + q.n * w == p.r) && q.out + q.n * w == p.out;
+        if (cont && q.n + p.n <= chunk) { q.n += p.n; continue; }
+      }
+      pieces.push_back(p);
+    }
   }
-  if (max_n == 0) return AG_OK;
+  if (pieces.empty()) return AG_OK;
   Pipe pipe;
   AG_TRY(pipe.acquire());
-  int64_t chunk = (kChunkBytes / w) & ~(int64_t)1023;
-  if (chunk > max_n) chunk = max_n;
-  const bool la = shape != AG_SHAPE_SA, ra = shape != AG_SHAPE_AS;
   void* d_l[kPipe] = {}; void* d_r[kPipe] = {}; void* d_o[kPipe] = {};
   ag_status rc = AG_OK;
+  const size_t stage_bytes = (size_t)(chunk + pad) * w + 64;
   for (int sl = 0; sl < kPipe && rc == AG_OK; ++sl) {
-    if (la) rc = dev_alloc_async(&d_l[sl], (size_t)chunk * w + 64, pipe.s[sl]);
-    if (rc == AG_OK && ra) rc = dev_alloc_async(&d_r[sl], (size_t)chunk * w + 64, pipe.s[sl]);
-    if (rc == AG_OK) rc = dev_alloc_async(&d_o[sl], (size_t)chunk * w + 64, pipe.s[sl]);
+    if (la) rc = dev_alloc_async(&d_l[sl], stage_bytes, pipe.s[sl]);
+    if (rc == AG_OK && ra) rc = dev_alloc_async(&d_r[sl], stage_bytes, pipe.s[sl]);
+    if (rc == AG_OK) rc = dev_alloc_async(&d_o[sl], stage_bytes, pipe.s[sl]);
   }
   int64_t ci = 0;
-  for (int64_t i = 0; i < n_spans && rc == AG_OK; ++i) {
-    const ag_span3& sp = spans[i];
-    for (int64_t r0 = 0; r0 < sp.n && rc == AG_OK; r0 += chunk, ++ci) {
-      const int sl = (int)(ci % kPipe);
-      const int64_t len = (sp.n - r0 < chunk) ? (sp.n - r0) : chunk;
-      cudaStream_t st = pipe.s[sl];
-      if (la) rc = h2d(d_l[sl], (const char*)sp.l + r0 * w, (size_t)len * w, st);
-      if (rc == AG_OK && ra) rc = h2d(d_r[sl], (const char*)sp.r + r0 * w, (size_t)len * w, st);
-      if (rc == AG_OK) rc = arith_binary_dev(type, op, shape, la ? d_l[sl] : sp.l, ra ? d_r[sl] : sp.r, d_o[sl], len, st);
-      if (rc == AG_OK) rc = d2h((char*)sp.out + r0 * w, d_o[sl], (size_t)len * w, st);
+  for (size_t first = 0; first < pieces.size() && rc == AG_OK; ++ci) {
+    const int sl = (int)(ci % kPipe);
+    cudaStream_t st = pipe.s[sl];
+    // pieces [first, last) of this stage, each at a 16-byte aligned row offset
+    size_t last = first;
+    int64_t rows = 0;
+    while (last < pieces.size()) {
+      const int64_t at = (rows + pad - 1) / pad * pad;
+      if (last > first && at + pieces[last].n > chunk) break;
+      rows = at + pieces[last].n;
+      ++last;
     }
+    int64_t at = 0;
+    for (size_t k = first; k < last && rc == AG_OK; ++k) {
+      at = (at + pad - 1) / pad * pad;
+      if (la) rc = h2d((char*)d_l[sl] + at * w, pieces[k].l, (size_t)pieces[k].n * w, st);
+      if (rc == AG_OK && ra) rc = h2d((char*)d_r[sl] + at * w, pieces[k].r, (size_t)pieces[k].n * w, st);
+      at += pieces[k].n;
+    }
+    if (rc == AG_OK) rc = arith_binary_dev(type, op, shape, la ? d_l[sl] : scalar_l, ra ? d_r[sl] : scalar_r, d_o[sl], rows, st);
+    at = 0;
+    for (size_t k = first; k < last && rc == AG_OK; ++k) {
+      at = (at + pad - 1) / pad * pad;
+      rc = d2h(pieces[k].out, (const char*)d_o[sl] + at * w, (size_t)pieces[k].n * w, st);
+      at += pieces[k].n;
+    }
+    first = last;
   }
   for (int sl = 0; sl < kPipe; ++sl) {
     if (d_l[sl]) cudaFreeAsync(d_l[sl], pipe.s[sl]);
