@@ -45,6 +45,12 @@ ag_status filter_primitive_dev(int bit_width, const void* vals, const uint8_t* v
                                int64_t moff, int64_t n, int null_selection, void* out, uint8_t* out_valid, int64_t capacity, int64_t* d_out_len, cudaStream_t st);
 ag_status take_indices_dev(int index_width, const uint8_t* mask, const uint8_t* mvalid, int64_t moff, int64_t n, int null_selection,
                            void* out_idx, uint8_t* out_valid, int64_t capacity, int64_t* d_out_len, cudaStream_t st);
+ag_status is_in_dev(int bit_width, const void* vals, const uint8_t* valid, int64_t off, int64_t n, const void* set, const uint8_t* set_valid,
+                    int64_t set_off, int64_t set_n, int null_behavior, uint8_t* out_data, uint8_t* out_valid, int64_t* d_null_count, cudaStream_t st);
+ag_status unique_dev(int bit_width, const void* vals, const uint8_t* valid, int64_t off, int64_t n, void* out, uint8_t* out_valid, int64_t capacity,
+                     int64_t* d_out_len, cudaStream_t st);
+ag_status sort_indices_dev(int type, const void* vals, const uint8_t* valid, int64_t voff, int64_t n, int order, int null_placement,
+                           uint64_t* d_out, int64_t* nulls_out, int64_t* nans_out, cudaStream_t st);
 ag_status take_primitive_dev(int bit_width, const void* vals, const uint8_t* vvalid, int64_t voff, int64_t vlen, int idx_width, int idx_signed,
                              const void* idx, const uint8_t* ivalid, int64_t ioff, int64_t n, int bounds_check, void* out, uint8_t* out_valid,
                              int64_t* d_bad_pos, cudaStream_t st);
@@ -796,6 +802,106 @@ ag_status ag_take_primitive(int bit_width, const void* vals, const uint8_t* vval
     }
   }
   return sync(cs);
+}
+
+ag_status ag_sort_indices(int type, const void* vals, const uint8_t* valid, int64_t offset, int64_t n, int order,
+                          int null_placement, uint64_t* out, int64_t* null_count, int64_t* nan_count) {
+  AG_TRY(ensure_init());
+  if (null_count) *null_count = 0;
+  if (nan_count) *nan_count = 0;
+  const int w = type_width(type);
+  if (w == 0) AG_FAIL(AG_ERR_NOT_IMPLEMENTED, "sort_indices: unsupported type id %d (fixed-width numeric columns only)", type);
+  if (n < 0 || offset < 0) AG_FAIL(AG_ERR_INVALID, "sort_indices: negative length or offset");
+  if (n == 0) return AG_OK;
+  if (!vals || !out) AG_FAIL(AG_ERR_INVALID, "sort_indices: NULL values/output");
+  CallStream cs; AG_TRY(cs.acquire());
+  Temps t(cs);
+  void* dv; uint8_t* dvalid; int64_t ov; uint64_t* dout;
+  AG_TRY(t.alloc(&dv, (size_t)n * w));
+  AG_TRY(h2d(dv, (const char*)vals + offset * w, (size_t)n * w, cs));
+  AG_TRY(upload_bitmap(t, valid, offset, n, &dvalid, &ov));
+  AG_TRY(t.alloc_t(&dout, (size_t)n * 8));
+  // the device copy starts at the slice: the element offset becomes the bitmap phase (offset & 7)
+  AG_TRY(sort_indices_dev(type, (const char*)dv - ov * w, dvalid, ov, n, order, null_placement, dout, null_count, nan_count, cs));
+  AG_TRY(d2h(out, dout, (size_t)n * 8, cs));
+  return sync(cs);
+}
+
+ag_status ag_is_in(int bit_width, const void* vals, const uint8_t* valid, int64_t offset, int64_t n, const void* set_vals,
+                   const uint8_t* set_valid, int64_t set_offset, int64_t set_n, int null_behavior, uint8_t* out_data, uint8_t* out_valid,
+                   int64_t* out_nulls) {
+  AG_TRY(ensure_init());
+  if (out_nulls) *out_nulls = 0;
+  if (bit_width != 8 && bit_width != 16 && bit_width != 32 && bit_width != 64) AG_FAIL(AG_ERR_NOT_IMPLEMENTED, "is_in: fixed-width values of 1/2/4/8 bytes only");
+  if (n < 0 || set_n < 0 || offset < 0 || set_offset < 0) AG_FAIL(AG_ERR_INVALID, "is_in: negative length or offset");
+  if (n == 0) return AG_OK;
+  if (!vals || !out_data || (set_n > 0 && !set_vals)) AG_FAIL(AG_ERR_INVALID, "is_in: NULL values / value set / output");
+  const int w = bit_width / 8;
+  CallStream cs; AG_TRY(cs.acquire());
+  Temps t(cs);
+  void *dv, *ds = nullptr; uint8_t *dvv, *dsv = nullptr, *dod, *dov; int64_t ov, os = 0; int64_t* d_nulls;
+  AG_TRY(t.alloc(&dv, (size_t)n * w));
+  AG_TRY(h2d(dv, (const char*)vals + offset * w, (size_t)n * w, cs));
+  AG_TRY(upload_bitmap(t, valid, offset, n, &dvv, &ov));
+  if (set_n > 0) {
+    AG_TRY(t.alloc(&ds, (size_t)set_n * w));
+    AG_TRY(h2d(ds, (const char*)set_vals + set_offset * w, (size_t)set_n * w, cs));
+    AG_TRY(upload_bitmap(t, set_valid, set_offset, set_n, &dsv, &os));
+  }
+  const size_t bm = (size_t)((n + 31) / 32) * 4;
+  AG_TRY(t.alloc_t(&dod, bm));
+  AG_TRY(t.alloc_t(&dov, bm));
+  AG_TRY(t.alloc_t(&d_nulls, 8));
+  AG_TRY(is_in_dev(bit_width, (const char*)dv - ov * w, dvv, ov, n, ds ? (const char*)ds - os * w : nullptr, dsv, os, set_n, null_behavior, dod,
+                   out_valid ? dov : nullptr, d_nulls, cs));
+  AG_TRY(d2h(out_data, dod, (size_t)((n + 7) / 8), cs));
+  if (out_valid) AG_TRY(d2h(out_valid, dov, (size_t)((n + 7) / 8), cs));
+  int64_t nulls = 0;
+  AG_TRY(d2h(&nulls, d_nulls, 8, cs));
+  AG_TRY(sync(cs));
+  if (out_nulls) *out_nulls = nulls;
+  return AG_OK;
+}
+
+ag_status ag_unique(int bit_width, const void* vals, const uint8_t* valid, int64_t offset, int64_t n, void* out, uint8_t* out_valid,
+                    int64_t* out_len, int64_t* out_nulls) {
+  AG_TRY(ensure_init());
+  if (!out_len) AG_FAIL(AG_ERR_INVALID, "unique: NULL out_len");
+  *out_len = 0;
+  if (out_nulls) *out_nulls = 0;
+  if (bit_width != 8 && bit_width != 16 && bit_width != 32 && bit_width != 64) AG_FAIL(AG_ERR_NOT_IMPLEMENTED, "unique: fixed-width values of 1/2/4/8 bytes only");
+  if (n < 0 || offset < 0) AG_FAIL(AG_ERR_INVALID, "unique: negative length or offset");
+  if (n == 0) return AG_OK;
+  if (!vals || !out) AG_FAIL(AG_ERR_INVALID, "unique: NULL values/output");
+  if (valid && !out_valid) AG_FAIL(AG_ERR_INVALID, "unique: an input with a validity bitmap needs an output validity bitmap");
+  const int w = bit_width / 8;
+  CallStream cs; AG_TRY(cs.acquire());
+  Temps t(cs);
+  void *dv, *dout; uint8_t *dvv, *dov = nullptr; int64_t ov; int64_t* d_len;
+  AG_TRY(t.alloc(&dv, (size_t)n * w));
+  AG_TRY(h2d(dv, (const char*)vals + offset * w, (size_t)n * w, cs));
+  AG_TRY(upload_bitmap(t, valid, offset, n, &dvv, &ov));
+  AG_TRY(t.alloc(&dout, (size_t)n * w));
+  if (valid) AG_TRY(t.alloc_t(&dov, (size_t)((n + 31) / 32) * 4));
+  AG_TRY(t.alloc_t(&d_len, 16));
+  AG_TRY(unique_dev(bit_width, (const char*)dv - ov * w, dvv, ov, n, dout, dov, n, d_len, cs));
+  int64_t len = 0;
+  AG_TRY(d2h(&len, d_len, 8, cs));
+  AG_TRY(sync(cs));
+  AG_TRY(d2h(out, dout, (size_t)len * w, cs));
+  if (dov && out_valid) {
+    AG_TRY(d2h(out_valid, dov, (size_t)((len + 7) / 8), cs));
+    if (out_nulls) {
+      AG_TRY(bitmap_popcount_dev(dov, 0, len, d_len + 1, cs));
+      int64_t v = 0;
+      AG_TRY(d2h(&v, d_len + 1, 8, cs));
+      AG_TRY(sync(cs));
+      *out_nulls = len - v;
+    }
+  }
+  AG_TRY(sync(cs));
+  *out_len = len;
+  return AG_OK;
 }
 
 }  // extern "C"

@@ -1,0 +1,431 @@
+// sort.cu — sort_indices for one fixed-width column on sm_100a.
+//
+// Replaces kernels.SortIndices for a single key (arrow/compute/internal/kernels/vector_sort.go:385-481,
+// arraySortOneColumnRange vector_sort_internal.go:250-300): a STABLE permutation of 0..n-1 laid out as
+//     NullsAtEnd   : [ finite values in key order | NaNs in row order | nulls in row order ]
+//     NullsAtStart : [ nulls in row order | NaNs in row order | finite values in key order ]
+// (partitionNullsOnly + partitionNullLikes, vector_sort_internal.go:36-150, then a stable sort of the finite range
+// with compareOrdered: ascending or descending, ties keep row order, -0.0 == +0.0; vector_sort_physical.go,
+// vector_sort_support.go:100-170).  Output: uint64 row indices, like the reference.
+//
+// Algorithm: least-significant-digit radix sort over (key', row) pairs, 8-bit digits.
+//   key' is an order-preserving unsigned image of the value (sign bias for signed ints; floats: flip all bits of
+//   negatives, set the sign bit of the rest, -0.0 folded onto +0.0), complemented for Descending so that an ascending
+//   stable sort of key' gives the descending order with ties still in row order.
+//   K0  one pass over the column: per-digit global histograms of the finite rows + class counts (finite / NaN / null)
+//       -> read back (2 KB) so the host can lay out the three regions and SKIP every digit on which all keys agree
+//       (a column of small integers needs one or two passes instead of eight);
+//   K1  class pass: stable 3-way partition of the rows into the region order above, materialising the pairs;
+//   K2+ one pass per remaining digit on the finite region: tile histogram (shared-memory atomics) -> per-bin scan over
+//       the tiles -> scatter with a stable in-tile rank (warp __match_any_sync groups + per-warp digit counters);
+//   K3  the row indices of the final pair buffer are widened to uint64 into `out`.
+// Roofline: HBM; per executed digit pass 8 (histogram read) + 12 + 12 bytes/row for 64-bit keys; the gathers are
+// never random (pairs move with their rows).  The API is synchronous in one spot: the 2 KB read-back after K0.
+#include "common.cuh"
+
+#include <string.h>
+#include <type_traits>
+#include <vector>
+
+namespace ag {
+
+constexpr int kSoThreads = 256;
+constexpr int kSoPerThread = 16;
+constexpr int kSoTile = kSoThreads * kSoPerThread;   // 4096 rows per tile
+constexpr int kSoWarps = kSoThreads / 32;
+constexpr int kSoWarpRows = kSoTile / kSoWarps;      // 512 consecutive rows per warp
+
+struct SortSource {
+  const void* vals;        // element 0 of the values buffer
+  const uint8_t* valid;    // validity bitmap (may be NULL)
+  int64_t voff;            // element offset of the slice (values and bitmap)
+  int64_t n;
+  int descending;
+  int nulls_first;
+};
+
+// order-preserving unsigned image of a value; *cls = 0 finite, 1 NaN
+template <typename T, typename K>
+__device__ __forceinline__ K sort_key(T v, int descending, int* cls) {
+  K k;
+  *cls = 0;
+  if constexpr (std::is_same<T, float>::value) {
+    uint32_t b = __float_as_uint(v);
+    if ((b & 0x7fffffffu) > 0x7f800000u) *cls = 1;
+    if (b == 0x80000000u) b = 0;                        // -0.0 == +0.0 (compareOrdered)
+    k = (K)((b & 0x80000000u) ? ~b : (b | 0x80000000u));
+  } else if constexpr (std::is_same<T, double>::value) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    if ((b & 0x7fffffffffffffffull) > 0x7ff0000000000000ull) *cls = 1;
+    if (b == 0x8000000000000000ull) b = 0;
+    k = (K)((b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull));
+  } else if constexpr (std::is_signed<T>::value) {
+    using U = typename std::make_unsigned<T>::type;
+    k = (K)(U)((U)v ^ (U)((U)1 << (sizeof(T) * 8 - 1)));
+  } else {
+    k = (K)v;
+  }
+  if (descending) {
+    // complement inside the value's own width so narrower types keep their zero high bits
+    if constexpr (sizeof(T) < sizeof(K)) k = (K)(~k & (((K)1 << (sizeof(T) * 8)) - 1));
+    else k = (K)~k;
+  }
+  return k;
+}
+
+// region index of a row class under the null placement: the class pass sorts by this "digit"
+__device__ __forceinline__ int class_digit(int cls /*0 finite,1 NaN,2 null*/, int nulls_first) { return nulls_first ? 2 - cls : cls; }
+
+// ---------------------------------------------------------------- K0: global histograms
+// hist layout: [sizeof(K)][256] digit counts of the FINITE rows, then 3 class counts (finite, NaN, null).
+template <typename T, typename K>
+__global__ void __launch_bounds__(kSoThreads)
+sort_prep_hist_kernel(const SortSource src, unsigned long long* __restrict__ hist) {
+  constexpr int ND = (int)sizeof(K);
+  __shared__ unsigned s_hist[ND * 256 + 4];
+  for (int i = threadIdx.x; i < ND * 256 + 4; i += kSoThreads) s_hist[i] = 0;
+  __syncthreads();
+  const T* __restrict__ vals = reinterpret_cast<const T*>(src.vals) + src.voff;
+  for (int64_t i = (int64_t)blockIdx.x * kSoThreads + threadIdx.x; i < src.n; i += (int64_t)gridDim.x * kSoThreads) {
+    int cls;
+    const K k = sort_key<T, K>(__ldcs(vals + i), src.descending, &cls);
+    if (src.valid && !bit_is_set(src.valid, src.voff + i)) cls = 2;
+    atomicAdd(&s_hist[ND * 256 + cls], 1u);
+    if (cls == 0) {
+#pragma unroll
+      for (int d = 0; d < ND; ++d) atomicAdd(&s_hist[d * 256 + (int)((k >> (8 * d)) & 0xff)], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ND * 256 + 3; i += kSoThreads)
+    if (s_hist[i]) atomicAdd(&hist[i], (unsigned long long)s_hist[i]);
+}
+
+// ---------------------------------------------------------------- shared pieces of a pass
+// tile_hist layout: [bin][tile] (one contiguous row per bin, scanned by one block per bin)
+__global__ void __launch_bounds__(kSoThreads)
+sort_scan_bins_kernel(unsigned* __restrict__ tile_hist, int64_t ntiles, const unsigned long long* __restrict__ bin_base) {
+  __shared__ unsigned long long s_w[kSoWarps];
+  unsigned* row = tile_hist + (int64_t)blockIdx.x * ntiles;
+  const int64_t per = (ntiles + kSoThreads - 1) / kSoThreads;
+  const int64_t lo = (int64_t)threadIdx.x * per, hi = lo + per < ntiles ? lo + per : ntiles;
+  unsigned long long sum = 0;
+  for (int64_t i = lo; i < hi; ++i) sum += row[i];
+  unsigned long long inc = sum;
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) s_w[threadIdx.x >> 5] = inc;
+  __syncthreads();
+  unsigned long long base = bin_base[blockIdx.x];
+  for (int w = 0; w < (threadIdx.x >> 5); ++w) base += s_w[w];
+  unsigned long long run = base + inc - sum;
+  for (int64_t i = lo; i < hi; ++i) {
+    const unsigned c = row[i];
+    row[i] = (unsigned)run;     // positions fit 32 bits (n < 2^32)
+    run += c;
+  }
+}
+
+// Stable rank of every element of a tile inside its digit: warp w owns rows [512w, 512w+512) of the tile and walks them
+// 32 at a time; lanes with equal digits form a group (__match_any_sync), the group's lowest lane advances the warp's
+// counter of that digit, and a lane's rank is the counter before the step plus its position inside the group.  After
+// the walk the 8 warp counters of a digit are turned into exclusive offsets (thread b handles digit b).
+// digits[e] for e = 0..15 are the digits of rows 512w + 32e + lane; rank[e] receives the rank inside (warp, digit).
+// s_cnt: [kSoWarps][256] counters; on return s_cnt[w][b] = rows of digit b in warps < w, tile_count[b] in s_tot.
+__device__ __forceinline__ void tile_rank(const int (&digits)[kSoPerThread], const bool (&live)[kSoPerThread], unsigned (&rank)[kSoPerThread],
+                                          unsigned* s_cnt, unsigned* s_tot, int nbins) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < kSoWarps * 256; i += kSoThreads) s_cnt[i] = 0;
+  __syncthreads();
+  unsigned* mine = s_cnt + warp * 256;
+  const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int e = 0; e < kSoPerThread; ++e) {
+    const int d = live[e] ? digits[e] : 256 + lane;          // dead rows match nobody
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    unsigned old = 0;
+    const int leader = __ffs(peers) - 1;
+    if (live[e] && lane == leader) { old = mine[d]; mine[d] = old + __popc(peers); }
+    old = __shfl_sync(0xffffffffu, old, leader);
+    rank[e] = old + __popc(peers & lt);
+    __syncwarp();
+  }
+  __syncthreads();
+  if (threadIdx.x < nbins) {
+    unsigned run = 0;
+#pragma unroll
+    for (int w = 0; w < kSoWarps; ++w) {
+      const unsigned c = s_cnt[w * 256 + threadIdx.x];
+      s_cnt[w * 256 + threadIdx.x] = run;
+      run += c;
+    }
+    s_tot[threadIdx.x] = run;
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------- K1: class pass (source arrays -> pairs)
+template <typename T, typename K>
+__global__ void __launch_bounds__(kSoThreads)
+sort_class_hist_kernel(const SortSource src, unsigned* __restrict__ tile_hist, int64_t ntiles) {
+  __shared__ unsigned s_c[4];
+  const T* __restrict__ vals = reinterpret_cast<const T*>(src.vals) + src.voff;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    if (threadIdx.x < 4) s_c[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned c[3] = {0, 0, 0};
+#pragma unroll 4
+    for (int e = 0; e < kSoPerThread; ++e) {
+      const int64_t i = tile * kSoTile + e * kSoThreads + threadIdx.x;
+      if (i < src.n) {
+        int cls;
+        (void)sort_key<T, K>(vals[i], 0, &cls);
+        if (src.valid && !bit_is_set(src.valid, src.voff + i)) cls = 2;
+        ++c[class_digit(cls, src.nulls_first)];
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      unsigned v = c[b];
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+      if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_c[b], v);
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) tile_hist[(int64_t)threadIdx.x * ntiles + tile] = s_c[threadIdx.x];
+    __syncthreads();
+  }
+}
+
+template <typename T, typename K>
+__global__ void __launch_bounds__(kSoThreads)
+sort_class_scatter_kernel(const SortSource src, const unsigned* __restrict__ tile_off, int64_t ntiles, K* __restrict__ keys_out,
+                          unsigned* __restrict__ idx_out) {
+  __shared__ unsigned s_cnt[kSoWarps * 256];
+  __shared__ unsigned s_tot[256];
+  __shared__ unsigned s_base[4];
+  const T* __restrict__ vals = reinterpret_cast<const T*>(src.vals) + src.voff;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int digits[kSoPerThread];
+    bool live[kSoPerThread];
+    unsigned rank[kSoPerThread];
+    K key[kSoPerThread];
+    const int64_t row0 = tile * kSoTile + warp * kSoWarpRows + lane;
+#pragma unroll
+    for (int e = 0; e < kSoPerThread; ++e) {
+      const int64_t i = row0 + e * 32;
+      live[e] = i < src.n;
+      digits[e] = 0; key[e] = 0;
+      if (live[e]) {
+        int cls;
+        key[e] = sort_key<T, K>(__ldcs(vals + i), src.descending, &cls);
+        if (src.valid && !bit_is_set(src.valid, src.voff + i)) cls = 2;
+        if (cls) key[e] = 0;
+        digits[e] = class_digit(cls, src.nulls_first);
+      }
+    }
+    if (threadIdx.x < 3) s_base[threadIdx.x] = tile_off[(int64_t)threadIdx.x * ntiles + tile];
+    tile_rank(digits, live, rank, s_cnt, s_tot, 3);
+#pragma unroll
+    for (int e = 0; e < kSoPerThread; ++e) {
+      if (live[e]) {
+        const unsigned pos = s_base[digits[e]] + s_cnt[warp * 256 + digits[e]] + rank[e];
+        keys_out[pos] = key[e];
+        idx_out[pos] = (unsigned)(row0 + e * 32);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------- K2: digit passes on the pair buffers
+template <typename K>
+__global__ void __launch_bounds__(kSoThreads)
+sort_digit_hist_kernel(const K* __restrict__ keys, int64_t lo, int64_t n, int shift, unsigned* __restrict__ tile_hist, int64_t ntiles) {
+  __shared__ unsigned s_h[256];
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    s_h[threadIdx.x] = 0;
+    __syncthreads();
+#pragma unroll 4
+    for (int e = 0; e < kSoPerThread; ++e) {
+      const int64_t i = tile * kSoTile + e * kSoThreads + threadIdx.x;
+      if (i < n) atomicAdd(&s_h[(int)((__ldcs(keys + lo + i) >> shift) & 0xff)], 1u);
+    }
+    __syncthreads();
+    tile_hist[(int64_t)threadIdx.x * ntiles + tile] = s_h[threadIdx.x];
+    __syncthreads();
+  }
+}
+
+template <typename K>
+__global__ void __launch_bounds__(kSoThreads)
+sort_digit_scatter_kernel(const K* __restrict__ keys_in, const unsigned* __restrict__ idx_in, int64_t lo, int64_t n, int shift,
+                          const unsigned* __restrict__ tile_off, int64_t ntiles, K* __restrict__ keys_out, unsigned* __restrict__ idx_out) {
+  __shared__ unsigned s_cnt[kSoWarps * 256];
+  __shared__ unsigned s_tot[256];
+  __shared__ unsigned s_base[256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int digits[kSoPerThread];
+    bool live[kSoPerThread];
+    unsigned rank[kSoPerThread];
+    K key[kSoPerThread];
+    unsigned idx[kSoPerThread];
+    const int64_t row0 = tile * kSoTile + warp * kSoWarpRows + lane;
+#pragma unroll
+    for (int e = 0; e < kSoPerThread; ++e) {
+      const int64_t i = row0 + e * 32;
+      live[e] = i < n;
+      key[e] = 0; idx[e] = 0; digits[e] = 0;
+      if (live[e]) {
+        key[e] = __ldcs(keys_in + lo + i);
+        idx[e] = __ldcs(idx_in + lo + i);
+        digits[e] = (int)((key[e] >> shift) & 0xff);
+      }
+    }
+    s_base[threadIdx.x] = tile_off[(int64_t)threadIdx.x * ntiles + tile];
+    tile_rank(digits, live, rank, s_cnt, s_tot, 256);
+#pragma unroll
+    for (int e = 0; e < kSoPerThread; ++e) {
+      if (live[e]) {
+        const int64_t pos = lo + s_base[digits[e]] + s_cnt[warp * 256 + digits[e]] + rank[e];
+        keys_out[pos] = key[e];
+        idx_out[pos] = idx[e];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kSoThreads)
+sort_widen_kernel(const unsigned* __restrict__ idx, int64_t n, unsigned long long* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * kSoThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kSoThreads) out[i] = idx[i];
+}
+__global__ void __launch_bounds__(kSoThreads)
+sort_copy_u32_kernel(const unsigned* __restrict__ src, unsigned* __restrict__ dst, int64_t lo, int64_t hi) {
+  for (int64_t i = lo + (int64_t)blockIdx.x * kSoThreads + threadIdx.x; i < hi; i += (int64_t)gridDim.x * kSoThreads) dst[i] = src[i];
+}
+
+template <typename T, typename K>
+static ag_status sort_indices_t(const SortSource& src, unsigned long long* d_out, int64_t* nulls_out, int64_t* nans_out, cudaStream_t st) {
+  constexpr int ND = (int)sizeof(K);
+  const int64_t n = src.n;
+  const int64_t ntiles = (n + kSoTile - 1) / kSoTile;
+  const size_t hist_words = (size_t)ND * 256 + 3;
+  const size_t key_bytes = ((size_t)n * sizeof(K) + 255) & ~(size_t)255;
+  const size_t idx_bytes = ((size_t)n * 4 + 255) & ~(size_t)255;
+  const size_t th_bytes = ((size_t)256 * ntiles * 4 + 255) & ~(size_t)255;
+  const size_t head = (hist_words * 8 + 256 * 8 + 255) & ~(size_t)255;
+  void* scratch = nullptr;
+  AG_TRY(dev_alloc_async(&scratch, head + 2 * key_bytes + 2 * idx_bytes + th_bytes, st));
+  char* base = reinterpret_cast<char*>(scratch);
+  unsigned long long* d_hist = reinterpret_cast<unsigned long long*>(base);
+  unsigned long long* d_binbase = d_hist + hist_words;
+  K* keys[2] = {reinterpret_cast<K*>(base + head), reinterpret_cast<K*>(base + head + key_bytes)};
+  unsigned* idx[2] = {reinterpret_cast<unsigned*>(base + head + 2 * key_bytes), reinterpret_cast<unsigned*>(base + head + 2 * key_bytes + idx_bytes)};
+  unsigned* tile_hist = reinterpret_cast<unsigned*>(base + head + 2 * key_bytes + 2 * idx_bytes);
+  ag_status rc = AG_OK;
+  std::vector<unsigned long long> h((size_t)hist_words);
+  do {
+    if (cudaMemsetAsync(d_hist, 0, hist_words * 8, st) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "memset", __FILE__, __LINE__); break; }
+    const int grid = grid_for(n, kSoTile, 8);
+    sort_prep_hist_kernel<T, K><<<grid, kSoThreads, 0, st>>>(src, d_hist);
+    if ((rc = check_launch("sort_prep_hist_kernel")) != AG_OK) break;
+    if (cudaMemcpyAsync(h.data(), d_hist, hist_words * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "histogram read-back", __FILE__, __LINE__); break; }
+    const unsigned long long n_fin = h[(size_t)ND * 256], n_nan = h[(size_t)ND * 256 + 1], n_null = h[(size_t)ND * 256 + 2];
+    if (nulls_out) *nulls_out = (int64_t)n_null;
+    if (nans_out) *nans_out = (int64_t)n_nan;
+    // region layout in class-digit order
+    unsigned long long cls_cnt[3];
+    cls_cnt[src.nulls_first ? 2 : 0] = n_fin; cls_cnt[1] = n_nan; cls_cnt[src.nulls_first ? 0 : 2] = n_null;
+    unsigned long long bb[256] = {0};
+    bb[0] = 0; bb[1] = cls_cnt[0]; bb[2] = cls_cnt[0] + cls_cnt[1];
+    const int64_t fin_lo = (int64_t)(src.nulls_first ? n_null + n_nan : 0);
+    // ---- K1: class pass -> pairs in buffer 0
+    if (cudaMemcpyAsync(d_binbase, bb, 3 * 8, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "bin bases", __FILE__, __LINE__); break; }
+    sort_class_hist_kernel<T, K><<<grid, kSoThreads, 0, st>>>(src, tile_hist, ntiles);
+    if ((rc = check_launch("sort_class_hist_kernel")) != AG_OK) break;
+    sort_scan_bins_kernel<<<3, kSoThreads, 0, st>>>(tile_hist, ntiles, d_binbase);
+    if ((rc = check_launch("sort_scan_bins_kernel")) != AG_OK) break;
+    sort_class_scatter_kernel<T, K><<<grid, kSoThreads, 0, st>>>(src, tile_hist, ntiles, keys[0], idx[0]);
+    if ((rc = check_launch("sort_class_scatter_kernel")) != AG_OK) break;
+    // ---- K2: digit passes over the finite region, skipping digits on which every finite key agrees
+    int cur = 0;
+    const int64_t fn = (int64_t)n_fin;
+    const int64_t ftiles = (fn + kSoTile - 1) / kSoTile;
+    for (int d = 0; d < ND && fn > 1; ++d) {
+      bool trivial = false;
+      unsigned long long run = 0;
+      for (int b = 0; b < 256; ++b) {
+        if (h[(size_t)d * 256 + b] == n_fin) trivial = true;
+        bb[b] = run;
+        run += h[(size_t)d * 256 + b];
+      }
+      if (trivial) continue;
+      // cudaMemcpyAsync from pageable memory is staged before it returns, so `bb` may be reused next iteration
+      if (cudaMemcpyAsync(d_binbase, bb, 256 * 8, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "bin bases", __FILE__, __LINE__); break; }
+      const int fgrid = grid_for(fn, kSoTile, 8);
+      sort_digit_hist_kernel<K><<<fgrid, kSoThreads, 0, st>>>(keys[cur], fin_lo, fn, 8 * d, tile_hist, ftiles);
+      if ((rc = check_launch("sort_digit_hist_kernel")) != AG_OK) break;
+      sort_scan_bins_kernel<<<256, kSoThreads, 0, st>>>(tile_hist, ftiles, d_binbase);
+      if ((rc = check_launch("sort_scan_bins_kernel")) != AG_OK) break;
+      sort_digit_scatter_kernel<K><<<fgrid, kSoThreads, 0, st>>>(keys[cur], idx[cur], fin_lo, fn, 8 * d, tile_hist, ftiles, keys[cur ^ 1], idx[cur ^ 1]);
+      if ((rc = check_launch("sort_digit_scatter_kernel")) != AG_OK) break;
+      cur ^= 1;
+    }
+    if (rc != AG_OK) break;
+    // NaN / null rows stayed in buffer 0
+    if (cur == 1 && (n_nan + n_null) > 0) {
+      const int64_t olo = src.nulls_first ? 0 : fn, ohi = src.nulls_first ? fin_lo : n;
+      sort_copy_u32_kernel<<<grid_for(ohi - olo, kSoThreads * 8, 8), kSoThreads, 0, st>>>(idx[0], idx[1], olo, ohi);
+      if ((rc = check_launch("sort_copy_u32_kernel")) != AG_OK) break;
+    }
+    sort_widen_kernel<<<grid_for(n, kSoThreads * 8, 8), kSoThreads, 0, st>>>(idx[cur], n, d_out);
+    rc = check_launch("sort_widen_kernel");
+  } while (0);
+  const ag_status frc = dev_free_async(scratch, st);
+  return rc != AG_OK ? rc : frc;
+}
+
+ag_status sort_indices_dev(int type, const void* vals, const uint8_t* valid, int64_t voff, int64_t n, int order, int null_placement,
+                           uint64_t* d_out, int64_t* nulls_out, int64_t* nans_out, cudaStream_t st) {
+  if (n < 0 || voff < 0) AG_FAIL(AG_ERR_INVALID, "sort_indices: negative length or offset");
+  if (order != 0 && order != 1) AG_FAIL(AG_ERR_INVALID, "sort_indices: order must be 0 (ascending) or 1 (descending)");
+  if (null_placement != 0 && null_placement != 1) AG_FAIL(AG_ERR_INVALID, "sort_indices: null placement must be 0 (at end) or 1 (at start)");
+  if (nulls_out) *nulls_out = 0;
+  if (nans_out) *nans_out = 0;
+  if (n == 0) return AG_OK;
+  if (!vals || !d_out) AG_FAIL(AG_ERR_INVALID, "sort_indices: NULL values/output");
+  if (n >= (1ll << 32)) AG_FAIL(AG_ERR_NOT_IMPLEMENTED, "sort_indices: more than 2^32-1 rows per call");
+  SortSource src{vals, valid, voff, n, order, null_placement};
+  unsigned long long* out = reinterpret_cast<unsigned long long*>(d_out);
+  switch (type) {
+    case AG_TYPE_INT8: return sort_indices_t<int8_t, uint32_t>(src, out, nulls_out, nans_out, st);
+    case AG_TYPE_UINT8: return sort_indices_t<uint8_t, uint32_t>(src, out, nulls_out, nans_out, st);
+    case AG_TYPE_INT16: return sort_indices_t<int16_t, uint32_t>(src, out, nulls_out, nans_out, st);
+    case AG_TYPE_UINT16: return sort_indices_t<uint16_t, uint32_t>(src, out, nulls_out, nans_out, st);
+    case AG_TYPE_INT32: return sort_indices_t<int32_t, uint32_t>(src, out, nulls_out, nans_out, st);
+    case AG_TYPE_UINT32: return sort_indices_t<uint32_t, uint32_t>(src, out, nulls_out, nans_out, st);
+    case AG_TYPE_FLOAT32: return sort_indices_t<float, uint32_t>(src, out, nulls_out, nans_out, st);
+    case AG_TYPE_INT64: return sort_indices_t<long long, unsigned long long>(src, out, nulls_out, nans_out, st);
+    case AG_TYPE_UINT64: return sort_indices_t<unsigned long long, unsigned long long>(src, out, nulls_out, nans_out, st);
+    case AG_TYPE_FLOAT64: return sort_indices_t<double, unsigned long long>(src, out, nulls_out, nans_out, st);
+    default: AG_FAIL(AG_ERR_NOT_IMPLEMENTED, "sort_indices: unsupported type id %d (fixed-width numeric columns only)", type);
+  }
+}
+
+}  // namespace ag
+
+using namespace ag;
+
+extern "C" ag_status ag_sort_indices_dev(int type, const void* d_vals, const uint8_t* d_valid, int64_t offset, int64_t n, int order,
+                                         int null_placement, uint64_t* d_out, int64_t* null_count, int64_t* nan_count, ag_stream_t s) {
+  AG_TRY(ensure_init());
+  return sort_indices_dev(type, d_vals, d_valid, offset, n, order, null_placement, d_out, null_count, nan_count, resolve_stream(s));
+}

@@ -480,6 +480,50 @@ ag_status ag_take_primitive_dev(int bit_width, const void* d_vals, const uint8_t
 ag_status ag_take_set_policy(int mode, int64_t min_rows, int64_t min_table_bytes, int64_t window_bytes);
 
 /* ================================================================================= *
+ * is_in / unique for fixed-width values of 1/2/4/8 bytes — the memo-table kernels of
+ *   kernels/scalar_set_lookup.go:112-413 and kernels/vector_hash.go.  Values are compared by their RAW
+ *   BYTES like the reference's memo tables (floats: NaN == NaN of the same payload, -0.0 != +0.0).
+ *   is_in: out_data / out_valid are bitmaps at bit offset 0 (4-byte aligned); per row
+ *     valid value: in the set -> (true, valid); else INCONCLUSIVE and the set holds a null -> (false, null);
+ *                  else (false, valid)
+ *     null       : MATCH and the set holds a null -> (true, valid); SKIP, or MATCH without one -> (false, valid);
+ *                  else (false, null)                                   (isInKernelExec :373-413)
+ *   unique: the distinct values in order of first appearance, a null kept once where it first appears;
+ *     *out_len receives the count (capacity n is always enough).
+ *   `offset` / `set_offset` are element offsets into both the values buffer and the validity bitmap.
+ * ================================================================================= */
+#define AG_NULL_MATCH        0
+#define AG_NULL_SKIP         1
+#define AG_NULL_EMIT_NULL    2
+#define AG_NULL_INCONCLUSIVE 3
+ag_status ag_is_in(int bit_width, const void* vals, const uint8_t* valid, int64_t offset, int64_t n,
+                   const void* set_vals, const uint8_t* set_valid, int64_t set_offset, int64_t set_n, int null_behavior,
+                   uint8_t* out_data, uint8_t* out_valid, int64_t* out_nulls);
+ag_status ag_is_in_dev(int bit_width, const void* d_vals, const uint8_t* d_valid, int64_t offset, int64_t n,
+                       const void* d_set_vals, const uint8_t* d_set_valid, int64_t set_offset, int64_t set_n, int null_behavior,
+                       uint8_t* d_out_data, uint8_t* d_out_valid, int64_t* d_null_count, ag_stream_t s);
+ag_status ag_unique(int bit_width, const void* vals, const uint8_t* valid, int64_t offset, int64_t n,
+                    void* out, uint8_t* out_valid, int64_t* out_len, int64_t* out_nulls);
+ag_status ag_unique_dev(int bit_width, const void* d_vals, const uint8_t* d_valid, int64_t offset, int64_t n,
+                        void* d_out, uint8_t* d_out_valid, int64_t capacity, int64_t* d_out_len, ag_stream_t s);
+
+/* ================================================================================= *
+ * sort_indices, one fixed-width column — replaces kernels.SortIndices for a single
+ *   key (vector_sort.go:385-481, vector_sort_internal.go:36-150,250-300): a STABLE permutation of
+ *   0..n-1 as uint64 row indices,
+ *     null_placement 0 (NullsAtEnd)  : [finite in key order | NaN in row order | null in row order]
+ *     null_placement 1 (NullsAtStart): [null in row order | NaN in row order | finite in key order]
+ *   order 0 ascending / 1 descending (ties keep row order either way; -0.0 == +0.0).
+ *   `offset` is the slice's element offset into both the values buffer and the validity bitmap.
+ *   The device flavour synchronises the stream once (a 2 KB histogram read-back decides which radix
+ *   passes can be skipped).  n < 2^32 rows per call.
+ * ================================================================================= */
+ag_status ag_sort_indices(int type, const void* vals, const uint8_t* valid, int64_t offset, int64_t n, int order,
+                          int null_placement, uint64_t* out_indices, int64_t* null_count, int64_t* nan_count);
+ag_status ag_sort_indices_dev(int type, const void* d_vals, const uint8_t* d_valid, int64_t offset, int64_t n, int order,
+                              int null_placement, uint64_t* d_out_indices, int64_t* null_count, int64_t* nan_count, ag_stream_t s);
+
+/* ================================================================================= *
  * Parity helpers for inputs too large to bring back to the host:
  * order-sensitive 64-bit checksum  sum_i mix64(i) * word_i  (mod 2^64)  over a buffer
  * viewed as little-endian uint64 words (n_words = nbytes/8), and a counter-based

@@ -11,6 +11,7 @@
 
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 
 /* arrow.Type ids, arrow/datatype.go:36-72 */
 enum { T_BOOL = 1, T_U8 = 2, T_I8 = 3, T_U16 = 4, T_I16 = 5, T_U32 = 6, T_I32 = 7, T_U64 = 8, T_I64 = 9, T_F32 = 11, T_F64 = 12 };
@@ -896,4 +897,181 @@ void ref_generate(int kind, uint64_t seed, int64_t lo, int64_t hi, void* out, si
       default: return;
     }
   }
+}
+
+
+/* ------------------------------------------------------------------------------------------------------------
+ * sort_indices, single fixed-width column (kernels.SortIndices for one key: arrow/compute/internal/kernels/
+ * vector_sort.go:385-481; arraySortOneColumnRange vector_sort_internal.go:250-300 = partitionNullsOnly :36-87 +
+ * partitionNullLikes :89-150 + slices.SortStableFunc over the finite range with compareRowsForKey
+ * (vector_sort_physical.go: compareKeyedNulls / compareFloatNaNs / compareOrdered, vector_sort_support.go:100-170)).
+ *   NullsAtEnd  : [finite in key order | NaN in row order | null in row order]
+ *   NullsAtStart: [null in row order | NaN in row order | finite in key order]
+ * Stable; Descending reverses the key order only (ties stay in row order); -0.0 == +0.0.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct { int type; const void* vals; int64_t voff; int desc; } sort_ctx_t;
+
+static int sort_is_nan(const sort_ctx_t* c, uint64_t i) {
+  if (c->type == T_F32) { float v = ((const float*)c->vals)[c->voff + (int64_t)i]; return v != v; }
+  if (c->type == T_F64) { double v = ((const double*)c->vals)[c->voff + (int64_t)i]; return v != v; }
+  return 0;
+}
+
+/* compareOrdered on two finite rows */
+static int sort_cmp(const sort_ctx_t* c, uint64_t a, uint64_t b) {
+  int r = 0;
+#define CMP_AS(T) { const T x = ((const T*)c->vals)[c->voff + (int64_t)a], y = ((const T*)c->vals)[c->voff + (int64_t)b]; r = x < y ? -1 : (x > y ? 1 : 0); }
+  switch (c->type) {
+    case T_I8: CMP_AS(int8_t) break;   case T_U8: CMP_AS(uint8_t) break;
+    case T_I16: CMP_AS(int16_t) break; case T_U16: CMP_AS(uint16_t) break;
+    case T_I32: CMP_AS(int32_t) break; case T_U32: CMP_AS(uint32_t) break;
+    case T_I64: CMP_AS(int64_t) break; case T_U64: CMP_AS(uint64_t) break;
+    case T_F32: CMP_AS(float) break;   case T_F64: CMP_AS(double) break;
+    default: break;
+  }
+#undef CMP_AS
+  return c->desc ? -r : r;
+}
+
+/* stable merge sort of idx[lo,hi) (slices.SortStableFunc) */
+static void sort_merge(const sort_ctx_t* c, uint64_t* idx, uint64_t* tmp, int64_t lo, int64_t hi) {
+  if (hi - lo < 2) return;
+  if (hi - lo <= 16) { /* insertion sort: stable */
+    for (int64_t i = lo + 1; i < hi; ++i) {
+      const uint64_t v = idx[i];
+      int64_t j = i;
+      while (j > lo && sort_cmp(c, idx[j - 1], v) > 0) { idx[j] = idx[j - 1]; --j; }
+      idx[j] = v;
+    }
+    return;
+  }
+  const int64_t mid = lo + (hi - lo) / 2;
+  sort_merge(c, idx, tmp, lo, mid);
+  sort_merge(c, idx, tmp, mid, hi);
+  int64_t i = lo, j = mid, k = lo;
+  while (i < mid && j < hi) tmp[k++] = (sort_cmp(c, idx[j], idx[i]) < 0) ? idx[j++] : idx[i++];  /* ties take the left run */
+  while (i < mid) tmp[k++] = idx[i++];
+  while (j < hi) tmp[k++] = idx[j++];
+  for (k = lo; k < hi; ++k) idx[k] = tmp[k];
+}
+
+int ref_sort_indices(int type, const void* vals, const uint8_t* valid, int64_t voff, int64_t n, int order, int null_placement, uint64_t* out,
+                     int64_t* null_count, int64_t* nan_count) {
+  if (n < 0 || voff < 0 || (order != 0 && order != 1) || (null_placement != 0 && null_placement != 1)) return REF_ERR_INVALID;
+  sort_ctx_t c = {type, vals, voff, order};
+  int64_t n_null = 0, n_nan = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    if (valid && !bit_is_set(valid, voff + i)) ++n_null;
+    else if (sort_is_nan(&c, (uint64_t)i)) ++n_nan;
+  }
+  const int64_t n_fin = n - n_null - n_nan;
+  int64_t pf = null_placement ? n_null + n_nan : 0, pn = null_placement ? n_null : n_fin, pz = null_placement ? 0 : n_fin + n_nan;
+  const int64_t fin_lo = pf;
+  for (int64_t i = 0; i < n; ++i) {
+    if (valid && !bit_is_set(valid, voff + i)) out[pz++] = (uint64_t)i;
+    else if (sort_is_nan(&c, (uint64_t)i)) out[pn++] = (uint64_t)i;
+    else out[pf++] = (uint64_t)i;
+  }
+  uint64_t* tmp = (uint64_t*)malloc((size_t)(n > 0 ? n : 1) * sizeof(uint64_t));
+  if (!tmp) return REF_ERR_INVALID;
+  sort_merge(&c, out, tmp, fin_lo, fin_lo + n_fin);
+  free(tmp);
+  if (null_count) *null_count = n_null;
+  if (nan_count) *nan_count = n_nan;
+  return REF_OK;
+}
+
+
+/* ------------------------------------------------------------------------------------------------------------
+ * is_in / unique for fixed-width values, keyed by raw bytes (kernels/scalar_set_lookup.go:112-413: SetLookupState
+ * over uint8/16/32/64 memo tables, isInKernelExec :373-413; kernels/vector_hash.go: unique = distinct values in
+ * order of first appearance, null kept once).  Restated with a sort-free quadratic-safe approach: an open hash of
+ * the raw 64-bit keys (test sizes are small).
+ * ------------------------------------------------------------------------------------------------------------ */
+static uint64_t raw_key_at(int bit_width, const void* vals, int64_t i) {
+  switch (bit_width) {
+    case 8: return ((const uint8_t*)vals)[i];
+    case 16: return ((const uint16_t*)vals)[i];
+    case 32: return ((const uint32_t*)vals)[i];
+    default: return ((const uint64_t*)vals)[i];
+  }
+}
+typedef struct { uint64_t* keys; int64_t* first; uint8_t* used; uint64_t mask; } rset_t;
+static int rset_init(rset_t* s, int64_t entries) {
+  uint64_t slots = 16;
+  while (slots < (uint64_t)entries * 2 + 2) slots <<= 1;
+  s->keys = (uint64_t*)calloc(slots, 8); s->first = (int64_t*)calloc(slots, 8); s->used = (uint8_t*)calloc(slots, 1); s->mask = slots - 1;
+  return s->keys && s->first && s->used;
+}
+static void rset_free(rset_t* s) { free(s->keys); free(s->first); free(s->used); }
+static int64_t rset_find(const rset_t* s, uint64_t key) { /* first row or -1 */
+  uint64_t h = mix64(key) & s->mask;
+  while (s->used[h]) { if (s->keys[h] == key) return s->first[h]; h = (h + 1) & s->mask; }
+  return -1;
+}
+static void rset_add(rset_t* s, uint64_t key, int64_t row) {
+  uint64_t h = mix64(key) & s->mask;
+  while (s->used[h]) { if (s->keys[h] == key) return; h = (h + 1) & s->mask; }
+  s->used[h] = 1; s->keys[h] = key; s->first[h] = row;
+}
+
+int ref_is_in(int bit_width, const void* vals, const uint8_t* valid, int64_t off, int64_t n, const void* set, const uint8_t* set_valid,
+              int64_t set_off, int64_t set_n, int null_behavior, uint8_t* out_data, uint8_t* out_valid, int64_t* out_nulls) {
+  if (bit_width != 8 && bit_width != 16 && bit_width != 32 && bit_width != 64) return REF_ERR_NOT_IMPLEMENTED;
+  rset_t s;
+  if (!rset_init(&s, set_n)) return REF_ERR_INVALID;
+  int has_null = 0;
+  for (int64_t i = 0; i < set_n; ++i) {
+    if (set_valid && !bit_is_set(set_valid, set_off + i)) has_null = 1;
+    else rset_add(&s, raw_key_at(bit_width, set, set_off + i), i);
+  }
+  int64_t nulls = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    int d = 0, v = 1;
+    if (valid && !bit_is_set(valid, off + i)) {
+      if (null_behavior == 0 && has_null) d = 1;                                        /* MATCH */
+      else if (null_behavior == 1 || (null_behavior == 0 && !has_null)) d = 0;          /* SKIP */
+      else v = 0;
+    } else if (rset_find(&s, raw_key_at(bit_width, vals, off + i)) >= 0) {
+      d = 1;
+    } else if (null_behavior == 3 && has_null) {                                        /* INCONCLUSIVE */
+      v = 0;
+    }
+    if (d) out_data[i >> 3] |= (uint8_t)(1u << (i & 7)); else out_data[i >> 3] &= (uint8_t)~(1u << (i & 7));
+    if (out_valid) { if (v) out_valid[i >> 3] |= (uint8_t)(1u << (i & 7)); else out_valid[i >> 3] &= (uint8_t)~(1u << (i & 7)); }
+    nulls += !v;
+  }
+  rset_free(&s);
+  if (out_nulls) *out_nulls = nulls;
+  return REF_OK;
+}
+
+int ref_unique(int bit_width, const void* vals, const uint8_t* valid, int64_t off, int64_t n, void* out, uint8_t* out_valid, int64_t* out_len,
+               int64_t* out_nulls) {
+  if (bit_width != 8 && bit_width != 16 && bit_width != 32 && bit_width != 64) return REF_ERR_NOT_IMPLEMENTED;
+  rset_t s;
+  if (!rset_init(&s, n)) return REF_ERR_INVALID;
+  const int w = bit_width / 8;
+  int64_t k = 0, nulls = 0;
+  int seen_null = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    if (valid && !bit_is_set(valid, off + i)) {
+      if (seen_null) continue;
+      seen_null = 1;
+      memset((char*)out + k * w, 0, (size_t)w);
+      if (out_valid) out_valid[k >> 3] &= (uint8_t)~(1u << (k & 7));
+      ++nulls; ++k;
+      continue;
+    }
+    const uint64_t key = raw_key_at(bit_width, vals, off + i);
+    if (rset_find(&s, key) >= 0) continue;
+    rset_add(&s, key, i);
+    memcpy((char*)out + k * w, (const char*)vals + (off + i) * w, (size_t)w);
+    if (out_valid) out_valid[k >> 3] |= (uint8_t)(1u << (k & 7));
+    ++k;
+  }
+  rset_free(&s);
+  *out_len = k;
+  if (out_nulls) *out_nulls = nulls;
+  return REF_OK;
 }

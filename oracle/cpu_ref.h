@@ -88,6 +88,12 @@ int ref_take_primitive(int bit_width, const void* vals, const uint8_t* vvalid, i
                        int64_t* out_nulls, int64_t* bad_pos, int64_t* bad_index);
 
 /* parity helpers (same definitions as the device versions) */
+int ref_is_in(int bit_width, const void* vals, const uint8_t* valid, int64_t off, int64_t n, const void* set, const uint8_t* set_valid,
+              int64_t set_off, int64_t set_n, int null_behavior, uint8_t* out_data, uint8_t* out_valid, int64_t* out_nulls);
+int ref_unique(int bit_width, const void* vals, const uint8_t* valid, int64_t off, int64_t n, void* out, uint8_t* out_valid, int64_t* out_len,
+               int64_t* out_nulls);
+int ref_sort_indices(int type, const void* vals, const uint8_t* valid, int64_t voff, int64_t n, int order, int null_placement, uint64_t* out,
+                     int64_t* null_count, int64_t* nan_count);
 uint64_t ref_checksum64(const void* buf, size_t n_words);
 void     ref_generate(int kind, uint64_t seed, int64_t lo, int64_t hi, void* out, size_t n);
 

@@ -89,6 +89,9 @@ def cpu():
         lib.ref_take_indices.argtypes = [C.c_int, c_p, c_p, i64, i64, C.c_int, c_p, c_p, C.POINTER(i64)]
         lib.ref_take_primitive.argtypes = [C.c_int, c_p, c_p, i64, i64, C.c_int, C.c_int, c_p, c_p, i64, i64,
                                            C.c_int, c_p, c_p, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
+        lib.ref_is_in.argtypes = [C.c_int, c_p, c_p, i64, i64, c_p, c_p, i64, i64, C.c_int, c_p, c_p, C.POINTER(i64)]
+        lib.ref_unique.argtypes = [C.c_int, c_p, c_p, i64, i64, c_p, c_p, C.POINTER(i64), C.POINTER(i64)]
+        lib.ref_sort_indices.argtypes = [C.c_int, c_p, c_p, i64, i64, C.c_int, C.c_int, c_p, C.POINTER(i64), C.POINTER(i64)]
         lib.ref_checksum64.restype = C.c_uint64
         lib.ref_checksum64.argtypes = [c_p, C.c_size_t]
         lib.ref_generate.restype = None
