@@ -171,6 +171,12 @@ _SIGS = {
     "ag_unique_dev": [_i, _p, _p, _i64, _i64, _p, _p, _i64, _p, _p],
     "ag_sort_indices": [_i, _p, _p, _i64, _i64, _i, _i, _p, _pi64, _pi64],
     "ag_sort_indices_dev": [_i, _p, _p, _i64, _i64, _i, _i, _p, _pi64, _pi64, _p],
+    "ag_parquet_unpack32": [_p, _p, _i64, _i, _pi64],
+    "ag_parquet_unpack32_dev": [_p, _p, _i64, _i, _pi64, _p],
+    "ag_parquet_bytes_to_bools": [_p, _i64, _p, _i64],
+    "ag_parquet_bytes_to_bools_dev": [_p, _i64, _p, _i64, _p],
+    "ag_parquet_def_levels_to_bitmap": [_p, _i64, _i, _i, _p, _i64, _i64, _pi64, _pi64],
+    "ag_parquet_def_levels_to_bitmap_dev": [_p, _i64, _i, _i, _p, _i64, _i64, _p, _p],
     # parity helpers
     "ag_checksum64_dev": [_p, _sz, _p, _p],
     "ag_generate_dev": [_i, _u64, _i64, _i64, _p, _sz, _p],

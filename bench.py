@@ -57,9 +57,11 @@ def peaks():
 
 def ncu_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the Add kernel from the committed
-    `ncu --set full` capture (profiles/r1/ncu_full_binary_spans_kernel.csv), or None."""
+    `ncu --set full` capture (profiles/r2/ncu_full_bench_kernels.csv), or None."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r1", "ncu_full_binary_spans_kernel.csv")
+    path = os.path.join(ROOT, "profiles", "r2", "ncu_full_bench_kernels.csv")
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "r1", "ncu_full_binary_spans_kernel.csv")
     try:
         rows = list(csv.reader(open(path)))
         h = rows[0]
@@ -585,6 +587,26 @@ def main():
         ms = timed(cumsum, W, K)
         others["cumulative_sum_i64"] = {"rows_per_s": world * rows / ms * 1e3, "gbs_per_gpu": 16.0 * rows / ms / 1e6, "frac": 16.0 * rows / ms / 1e6 / peak, "ms": ms,
                                         "note": "single-pass scan, read once + write once (16 B/row)"}
+        # SURVEY 8f rank 3, same columns: sort_indices (stable radix sort), is_in (1000-value set), unique (100 distinct values)
+        N.call("ag_generate_dev", 1, 0x5027 + rank * rows, -(1 << 31), (1 << 31) - 1, vi.ptr, rows, None)
+        nn, na = C.c_int64(), C.c_int64()
+        ms = timed(lambda: N.call("ag_sort_indices_dev", N.INT64, vi.ptr, None, 0, rows, 0, 0, dout.ptr, C.byref(nn), C.byref(na), None), 1, 3)
+        others["sort_indices_i64"] = {"rows_per_s": world * rows / ms * 1e3, "ms": ms, "gbs_per_gpu": 16.0 * rows / ms / 1e6, "frac": 16.0 * rows / ms / 1e6 / peak,
+                                      "note": "keys uniform in [-2^31, 2^31): 4 of 8 radix digits vary -> class pass + 4 digit passes; algorithmic 8 B key in + 8 B index out per row; one host sync inside (2 KB histogram)"}
+        N.call("ag_generate_dev", 1, 0x15 + rank * rows, 0, 99_999, vi.ptr, rows, None)
+        sset = DeviceBuffer(8000)
+        hs = np.arange(0, 100_000, 100, dtype=np.int64)
+        N.call("ag_upload", sset.ptr, hs.ctypes.data, 8000, None)
+        bm1, bm2 = DeviceBuffer(rows // 8 + 64), DeviceBuffer(rows // 8 + 64)
+        ms = timed(lambda: N.call("ag_is_in_dev", 64, vi.ptr, None, 0, rows, sset.ptr, None, 0, 1000, 0, bm1.ptr, bm2.ptr, scal.ptr, None), W, K)
+        others["is_in_i64_1000_values"] = {"rows_per_s": world * rows / ms * 1e3, "ms": ms, "gbs_per_gpu": 8.25 * rows / ms / 1e6, "frac": 8.25 * rows / ms / 1e6 / peak,
+                                           "note": "8 B value in + 2 bitmap bits out per row; the 1000-entry hash table stays in L1/L2"}
+        N.call("ag_generate_dev", 1, 0x16 + rank * rows, 0, 99, vi.ptr, rows, None)
+        ms = timed(lambda: N.call("ag_unique_dev", 64, vi.ptr, None, 0, rows, dout.ptr, None, rows, scal.ptr, None), 1, 3)
+        others["unique_i64_100_distinct"] = {"rows_per_s": world * rows / ms * 1e3, "ms": ms,
+                                             "note": "insert (atomicCAS / atomicMin first row) + mark + compaction; table sized for n distinct rows (3.2 GB memset included)"}
+        sset.free(); bm1.free(); bm2.free()
+        N.call("ag_generate_dev", 1, 0x0FF1CE + rank * rows, 0, 99, vi.ptr, rows, None)
         cstate.free(); idx.free(); bad.free(); scal.free()
 
     # ---- BASELINE configs 4 and 5 at their full 1B rows, split over the ranks by ag_shard_range; values asserted ----
@@ -650,7 +672,7 @@ def main():
             "detail": {"contiguous_ms_per_step": ms_contig, "per_span_launch_ms_per_step": ms_per_span,
                        "timing": "CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_bytes(),
-                         "traffic_note": "bytes per launch, dram__bytes_read+write from profiles/r1/ncu_full_binary_spans_kernel.csv (same kernel, same shape)",
+                         "traffic_note": "bytes per launch, dram__bytes_read+write from profiles/r2/ncu_full_bench_kernels.csv (ncu --set full of this command's Add kernel)",
                          "peak_kind": peak_kind, "algorithmic_bytes_per_row": 24, "kernel": "binary_spans_kernel<double,OpAdd,AA>",
                          "contiguous_frac": 24.0 * rows / (ms_contig * 1e-3) / 1e9 / peak},
             "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches_timed), "gpu_launches_total": int(launches_total),

@@ -524,6 +524,32 @@ ag_status ag_sort_indices_dev(int type, const void* d_vals, const uint8_t* d_val
                               int null_placement, uint64_t* d_out_indices, int64_t* null_count, int64_t* nan_count, ag_stream_t s);
 
 /* ================================================================================= *
+ * Parquet decode primitives (the feeder side) — the SIMD leaf loops arrow-go links under
+ *   parquet/internal, so pages can be decoded into device-resident Arrow buffers.
+ *   ag_parquet_unpack32 ↔ unpack32_avx2 (parquet/internal/utils/_lib/bit_packing_avx2.c:1772): values of
+ *     num_bits (0..32) bits, LSB-first, 32 per group -> uint32; only whole groups are unpacked
+ *     (batch_size/32*32, returned in *unpacked) — the caller handles the tail like BitReader.GetBatch.
+ *     d_in 4-byte aligned, d_out 16-byte aligned.
+ *   ag_parquet_bytes_to_bools ↔ bytes_to_bools (utils/_lib/unpack_bool.c:21): bit j of byte i -> out[8i+j] (0/1).
+ *   ag_parquet_def_levels_to_bitmap ↔ DefLevelsToBitmap (parquet/file/level_conversion.go:134-184 over
+ *     levels_to_bitmap / extract_bits, bmi/_lib/bitmap_bmi2.c:24-47): appends validity bits at
+ *     valid_bits_offset.  repeated_ancestor_def_level < 0: no repeated parent — bit i = def[i] >= def_level,
+ *     values_read = n (error if n > read_upper_bound).  Otherwise only slots with def >= the ancestor level
+ *     produce a bit.  *null_count is INCREMENTED by values_read - set bits (like the reference); the device
+ *     flavour returns {values_read, set bits} in d_counts[2].  n == 0 leaves valid_bits untouched.
+ * ================================================================================= */
+ag_status ag_parquet_unpack32(const uint32_t* in, uint32_t* out, int64_t batch_size, int num_bits, int64_t* unpacked);
+ag_status ag_parquet_unpack32_dev(const uint32_t* d_in, uint32_t* d_out, int64_t batch_size, int num_bits, int64_t* unpacked, ag_stream_t s);
+ag_status ag_parquet_bytes_to_bools(const uint8_t* bytes, int64_t len, uint8_t* out, int64_t outlen);
+ag_status ag_parquet_bytes_to_bools_dev(const uint8_t* d_bytes, int64_t len, uint8_t* d_out, int64_t outlen, ag_stream_t s);
+ag_status ag_parquet_def_levels_to_bitmap(const int16_t* def_levels, int64_t n, int def_level, int repeated_ancestor_def_level,
+                                          uint8_t* valid_bits, int64_t valid_bits_offset, int64_t read_upper_bound,
+                                          int64_t* values_read, int64_t* null_count);
+ag_status ag_parquet_def_levels_to_bitmap_dev(const int16_t* d_def_levels, int64_t n, int def_level, int repeated_ancestor_def_level,
+                                              uint8_t* d_valid_bits, int64_t valid_bits_offset, int64_t read_upper_bound,
+                                              int64_t* d_counts, ag_stream_t s);
+
+/* ================================================================================= *
  * Parity helpers for inputs too large to bring back to the host:
  * order-sensitive 64-bit checksum  sum_i mix64(i) * word_i  (mod 2^64)  over a buffer
  * viewed as little-endian uint64 words (n_words = nbytes/8), and a counter-based
