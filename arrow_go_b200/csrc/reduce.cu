@@ -110,31 +110,46 @@ template <> struct Acc<double> {
 // mailbox and folds the pairs in RANK ORDER — so the collective costs one NVLink store + one poll inside the kernel
 // that computed the sum: no second launch, no host synchronisation, identical bits on every rank.  A rank can be at
 // most one epoch ahead of the slowest one (it cannot finish epoch e before everyone has written e), hence two buffers.
+// Called by every lane of warp 0 of the block that holds the final pair (valid in lane 0).  Lane r talks to rank r:
+// the world's stores, flag releases and polls are in flight together (one NVLink round trip, not `world` of them); the
+// fold itself stays sequential in rank order so every rank computes the same bits.  Returns the total in every lane.
 template <typename T>
 __device__ __forceinline__ Acc<T> exchange_sum(Acc<T> mine, const SumExchange& x) {
+  const int lane = threadIdx.x & 31;
   const int buf = (int)(x.epoch & 1ull);
-  const ulonglong2 me = mine.raw();
-  for (int r = 0; r < x.world; ++r) {
-    MailSlot* m = x.peers[r] + buf * x.world + x.rank;
-    m->s = me.x;
-    m->c = me.y;
-  }
-  __threadfence_system();
-  for (int r = 0; r < x.world; ++r) {
-    MailSlot* m = x.peers[r] + buf * x.world + x.rank;
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&m->flag), "l"(x.epoch) : "memory");
-  }
+  ulonglong2 me = mine.raw();
+  me.x = __shfl_sync(0xffffffffu, me.x, 0);
+  me.y = __shfl_sync(0xffffffffu, me.y, 0);
   Acc<T> g; g.zero();
-  for (int r = 0; r < x.world; ++r) {
-    MailSlot* m = x.local + buf * x.world + r;
-    unsigned long long f;
-    do {
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(&m->flag) : "memory");
-    } while (f != x.epoch);
-    ulonglong2 v;
-    v.x = *reinterpret_cast<volatile unsigned long long*>(&m->s);
-    v.y = *reinterpret_cast<volatile unsigned long long*>(&m->c);
-    g.merge(Acc<T>::from_raw(v));
+  for (int r0 = 0; r0 < x.world; r0 += 32) {
+    const int r = r0 + lane;
+    if (r < x.world) {
+      MailSlot* m = x.peers[r] + buf * x.world + x.rank;
+      m->s = me.x;
+      m->c = me.y;
+      __threadfence_system();
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&m->flag), "l"(x.epoch) : "memory");
+    }
+  }
+  for (int r0 = 0; r0 < x.world; r0 += 32) {
+    const int r = r0 + lane;
+    ulonglong2 v = make_ulonglong2(0ull, 0ull);
+    if (r < x.world) {
+      MailSlot* m = x.local + buf * x.world + r;
+      unsigned long long f;
+      do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(&m->flag) : "memory");
+      } while (f != x.epoch);
+      v.x = *reinterpret_cast<volatile unsigned long long*>(&m->s);
+      v.y = *reinterpret_cast<volatile unsigned long long*>(&m->c);
+    }
+    const int cnt = x.world - r0 < 32 ? x.world - r0 : 32;
+    for (int k = 0; k < cnt; ++k) {   // rank order
+      ulonglong2 o;
+      o.x = __shfl_sync(0xffffffffu, v.x, k);
+      o.y = __shfl_sync(0xffffffffu, v.y, k);
+      g.merge(Acc<T>::from_raw(o));
+    }
   }
   return g;
 }
@@ -196,10 +211,10 @@ sum_kernel(const T* __restrict__ in, size_t n, ulonglong2* __restrict__ partials
   Acc<T> v = block_tree_sum(ax[0], smem);
 
   if (gridDim.x == 1) {
-    if (threadIdx.x == 0) {
-      if (n & 1) v.add(in[n - 1]);
+    if (threadIdx.x < 32) {
+      if (threadIdx.x == 0 && (n & 1)) v.add(in[n - 1]);
       if (xch.world > 1) v = exchange_sum(v, xch);
-      *out = v.value();
+      if (threadIdx.x == 0) *out = v.value();
     }
     return;
   }
@@ -218,11 +233,13 @@ sum_kernel(const T* __restrict__ in, size_t n, ulonglong2* __restrict__ partials
     acc.merge(Acc<T>::from_raw(__ldcg(partials + i)));
   }
   acc = block_tree_sum(acc, smem);
-  if (threadIdx.x == 0) {
-    if (n & 1) acc.add(in[n - 1]);
-    *ticket = 0;  // leave the workspace ready for the next launch on this stream
+  if (threadIdx.x < 32) {
+    if (threadIdx.x == 0) {
+      if (n & 1) acc.add(in[n - 1]);
+      *ticket = 0;  // leave the workspace ready for the next launch on this stream
+    }
     if (xch.world > 1) acc = exchange_sum(acc, xch);
-    *out = acc.value();
+    if (threadIdx.x == 0) *out = acc.value();
   }
 }
 
@@ -266,9 +283,9 @@ __global__ void __launch_bounds__(32) sum_f64_reforder_kernel(const double* __re
 }
 
 // n == 0 with an exchange: the rank still has to take part, with a zero pair
-__global__ void sum_exchange_only_kernel(unsigned long long* out, const SumExchange xch, int is_f64) {
-  if (is_f64) { Acc<double> z; z.zero(); z = exchange_sum(z, xch); *reinterpret_cast<double*>(out) = z.value(); }
-  else { Acc<unsigned long long> z; z.zero(); z = exchange_sum(z, xch); *out = z.value(); }
+__global__ void sum_exchange_only_kernel(unsigned long long* out, const SumExchange xch, int is_f64) {   // <<<1, 32>>>
+  if (is_f64) { Acc<double> z; z.zero(); z = exchange_sum(z, xch); if (threadIdx.x == 0) *reinterpret_cast<double*>(out) = z.value(); }
+  else { Acc<unsigned long long> z; z.zero(); z = exchange_sum(z, xch); if (threadIdx.x == 0) *out = z.value(); }
 }
 
 template <typename T>
@@ -278,7 +295,7 @@ ag_status launch_sum(const T* d_in, size_t n, T* d_res, cudaStream_t st, const S
   if (xch) x = *xch;
   if (n == 0) {
     if (x.world > 1) {
-      sum_exchange_only_kernel<<<1, 1, 0, st>>>(reinterpret_cast<unsigned long long*>(d_res), x, std::is_floating_point<T>::value ? 1 : 0);
+      sum_exchange_only_kernel<<<1, 32, 0, st>>>(reinterpret_cast<unsigned long long*>(d_res), x, std::is_floating_point<T>::value ? 1 : 0);
       return check_launch("sum_exchange_only_kernel");
     }
     AG_CUDA_TRY(cudaMemsetAsync(d_res, 0, sizeof(T), st));
