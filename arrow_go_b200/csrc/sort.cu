@@ -29,11 +29,12 @@
 
 namespace ag {
 
-constexpr int kSoThreads = 256;
-constexpr int kSoPerThread = 16;
+constexpr int kSoThreads = 512;
+constexpr int kSoPerThread = 8;
 constexpr int kSoTile = kSoThreads * kSoPerThread;   // 4096 rows per tile
 constexpr int kSoWarps = kSoThreads / 32;
-constexpr int kSoWarpRows = kSoTile / kSoWarps;      // 512 consecutive rows per warp
+constexpr int kSoWarpRows = kSoTile / kSoWarps;      // 256 consecutive rows per warp
+constexpr int kSoBins = 256;
 
 struct SortSource {
   const void* vals;        // element 0 of the values buffer
@@ -247,9 +248,9 @@ sort_class_scatter_kernel(const SortSource src, const unsigned* __restrict__ til
 template <typename K>
 __global__ void __launch_bounds__(kSoThreads)
 sort_digit_hist_kernel(const K* __restrict__ keys, int64_t lo, int64_t n, int shift, unsigned* __restrict__ tile_hist, int64_t ntiles) {
-  __shared__ unsigned s_h[256];
+  __shared__ unsigned s_h[kSoBins];
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    s_h[threadIdx.x] = 0;
+    if (threadIdx.x < kSoBins) s_h[threadIdx.x] = 0;
     __syncthreads();
 #pragma unroll 4
     for (int e = 0; e < kSoPerThread; ++e) {
@@ -257,18 +258,27 @@ sort_digit_hist_kernel(const K* __restrict__ keys, int64_t lo, int64_t n, int sh
       if (i < n) atomicAdd(&s_h[(int)((__ldcs(keys + lo + i) >> shift) & 0xff)], 1u);
     }
     __syncthreads();
-    tile_hist[(int64_t)threadIdx.x * ntiles + tile] = s_h[threadIdx.x];
+    if (threadIdx.x < kSoBins) tile_hist[(int64_t)threadIdx.x * ntiles + tile] = s_h[threadIdx.x];
     __syncthreads();
   }
 }
 
+// The scatter stages the tile in shared memory in digit order first (position = exclusive bin offset inside the tile +
+// rows of the digit in earlier warps + rank), then walks the staged tile with consecutive threads: rows of one digit
+// are consecutive there AND consecutive in the destination, so the global writes are contiguous runs issued by
+// neighbouring lanes instead of 16 isolated 8-byte stores per bin.
 template <typename K>
 __global__ void __launch_bounds__(kSoThreads)
 sort_digit_scatter_kernel(const K* __restrict__ keys_in, const unsigned* __restrict__ idx_in, int64_t lo, int64_t n, int shift,
                           const unsigned* __restrict__ tile_off, int64_t ntiles, K* __restrict__ keys_out, unsigned* __restrict__ idx_out) {
-  __shared__ unsigned s_cnt[kSoWarps * 256];
-  __shared__ unsigned s_tot[256];
-  __shared__ unsigned s_base[256];
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  K* s_key = reinterpret_cast<K*>(s_dyn);                                   // [kSoTile] staged keys, digit order
+  unsigned* s_idx = reinterpret_cast<unsigned*>(s_dyn + sizeof(K) * kSoTile);  // [kSoTile]
+  unsigned* s_cnt = s_idx + kSoTile;                                        // [kSoWarps][256]
+  __shared__ unsigned s_tot[kSoBins];
+  __shared__ unsigned s_excl[kSoBins];     // exclusive offset of a digit inside the staged tile
+  __shared__ unsigned s_base[kSoBins];     // global position of the tile's first row of a digit
+  __shared__ unsigned s_w[kSoBins / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     int digits[kSoPerThread];
@@ -277,6 +287,7 @@ sort_digit_scatter_kernel(const K* __restrict__ keys_in, const unsigned* __restr
     K key[kSoPerThread];
     unsigned idx[kSoPerThread];
     const int64_t row0 = tile * kSoTile + warp * kSoWarpRows + lane;
+    const int len = (int)(n - tile * kSoTile < kSoTile ? n - tile * kSoTile : kSoTile);
 #pragma unroll
     for (int e = 0; e < kSoPerThread; ++e) {
       const int64_t i = row0 + e * 32;
@@ -288,15 +299,41 @@ sort_digit_scatter_kernel(const K* __restrict__ keys_in, const unsigned* __restr
         digits[e] = (int)((key[e] >> shift) & 0xff);
       }
     }
-    s_base[threadIdx.x] = tile_off[(int64_t)threadIdx.x * ntiles + tile];
-    tile_rank(digits, live, rank, s_cnt, s_tot, 256);
+    if (threadIdx.x < kSoBins) s_base[threadIdx.x] = tile_off[(int64_t)threadIdx.x * ntiles + tile];
+    tile_rank(digits, live, rank, s_cnt, s_tot, kSoBins);
+    // exclusive scan of the 256 digit totals of the tile (one digit per thread of the first 8 warps)
+    {
+      const unsigned c = threadIdx.x < kSoBins ? s_tot[threadIdx.x] : 0u;
+      unsigned inc = c;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+      }
+      if (lane == 31 && warp < kSoBins / 32) s_w[warp] = inc;
+      __syncthreads();
+      if (threadIdx.x < kSoBins) {
+        unsigned wb = 0;
+        for (int w = 0; w < warp; ++w) wb += s_w[w];
+        s_excl[threadIdx.x] = wb + inc - c;
+      }
+    }
+    __syncthreads();
 #pragma unroll
     for (int e = 0; e < kSoPerThread; ++e) {
       if (live[e]) {
-        const int64_t pos = lo + s_base[digits[e]] + s_cnt[warp * 256 + digits[e]] + rank[e];
-        keys_out[pos] = key[e];
-        idx_out[pos] = idx[e];
+        const unsigned p = s_excl[digits[e]] + s_cnt[warp * 256 + digits[e]] + rank[e];
+        s_key[p] = key[e];
+        s_idx[p] = idx[e];
       }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < len; j += kSoThreads) {
+      const K k = s_key[j];
+      const int d = (int)((k >> shift) & 0xff);
+      const int64_t pos = lo + s_base[d] + (unsigned)(j - (int)s_excl[d]);
+      keys_out[pos] = k;
+      idx_out[pos] = s_idx[j];
     }
     __syncthreads();
   }
@@ -314,6 +351,12 @@ sort_copy_u32_kernel(const unsigned* __restrict__ src, unsigned* __restrict__ ds
 template <typename T, typename K>
 static ag_status sort_indices_t(const SortSource& src, unsigned long long* d_out, int64_t* nulls_out, int64_t* nans_out, cudaStream_t st) {
   constexpr int ND = (int)sizeof(K);
+  constexpr size_t kScatterSmem = (sizeof(K) + 4) * (size_t)kSoTile + (size_t)kSoWarps * 256 * 4;
+  static std::atomic<bool> attr_set{false};   // per K
+  if (!attr_set.load(std::memory_order_acquire)) {
+    AG_CUDA_TRY(cudaFuncSetAttribute(sort_digit_scatter_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScatterSmem));
+    attr_set.store(true, std::memory_order_release);
+  }
   const int64_t n = src.n;
   const int64_t ntiles = (n + kSoTile - 1) / kSoTile;
   const size_t hist_words = (size_t)ND * 256 + 3;
@@ -375,7 +418,7 @@ static ag_status sort_indices_t(const SortSource& src, unsigned long long* d_out
       if ((rc = check_launch("sort_digit_hist_kernel")) != AG_OK) break;
       sort_scan_bins_kernel<<<256, kSoThreads, 0, st>>>(tile_hist, ftiles, d_binbase);
       if ((rc = check_launch("sort_scan_bins_kernel")) != AG_OK) break;
-      sort_digit_scatter_kernel<K><<<fgrid, kSoThreads, 0, st>>>(keys[cur], idx[cur], fin_lo, fn, 8 * d, tile_hist, ftiles, keys[cur ^ 1], idx[cur ^ 1]);
+      sort_digit_scatter_kernel<K><<<fgrid, kSoThreads, kScatterSmem, st>>>(keys[cur], idx[cur], fin_lo, fn, 8 * d, tile_hist, ftiles, keys[cur ^ 1], idx[cur ^ 1]);
       if ((rc = check_launch("sort_digit_scatter_kernel")) != AG_OK) break;
       cur ^= 1;
     }
