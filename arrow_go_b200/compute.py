@@ -82,6 +82,9 @@ def lib():
         h.agx_export_device.argtypes = [p, C.POINTER(N.ArrowDeviceArray), C.POINTER(N.ArrowSchema)]
         h.agx_import_device.argtypes = [C.POINTER(N.ArrowDeviceArray), C.POINTER(N.ArrowSchema), pp]
         h.agx_scalar_value.argtypes = [p, C.POINTER(i), p]
+        h.agx_sort_indices.argtypes = [p, i, i, pp]
+        h.agx_unique.argtypes = [p, pp]
+        h.agx_is_in.argtypes = [p, p, i, pp]
         _lib = h
     return _lib
 
@@ -300,6 +303,32 @@ def Filter(values, mask, null_selection=DROP_NULLS):
 
 def Take(values, indices, bounds_check=True):
     return CallFunction("take", [values, indices], ("take", bounds_check))
+
+
+ASCENDING, DESCENDING = 0, 1
+NULLS_AT_END, NULLS_AT_START = 0, 1
+NULL_MATCH, NULL_SKIP, NULL_EMIT_NULL, NULL_INCONCLUSIVE = 0, 1, 2, 3
+
+
+def SortIndices(values, order=ASCENDING, null_placement=NULLS_AT_END):
+    """compute.SortIndices(ctx, input, SortOptions): uint64 row indices (arrow/compute/vector_sort.go:205-211)."""
+    out = C.c_void_p()
+    _check(lib().agx_sort_indices(values._h, int(order), int(null_placement), C.byref(out)))
+    return Datum(out)
+
+
+def Unique(values):
+    """compute.Unique: distinct values in order of first appearance (arrow/compute/vector_hash.go)."""
+    out = C.c_void_p()
+    _check(lib().agx_unique(values._h, C.byref(out)))
+    return Datum(out)
+
+
+def IsIn(values, value_set, null_behavior=NULL_MATCH):
+    """compute.IsIn(ctx, SetOptions{ValueSet, NullBehavior}, values) (arrow/compute/scalar_set_lookup.go)."""
+    out = C.c_void_p()
+    _check(lib().agx_is_in(values._h, value_set._h, int(null_behavior), C.byref(out)))
+    return Datum(out)
 
 
 class math:

@@ -247,6 +247,21 @@ struct CumulativeOptions : FunctionOptions {  // kernels/vector_cumulative.go:92
   const char* TypeName() const override { return "CumulativeOptions"; }
 };
 
+enum SortOrder { Ascending = 0, Descending = 1 };            // kernels/vector_sort.go:30-36
+enum NullPlacement { NullsAtEnd = 0, NullsAtStart = 1 };     // :38-44
+struct SortOptions : FunctionOptions {                        // :46-50 (single key: ColumnIndex is meaningless for an array)
+  SortOrder Order = Ascending;
+  NullPlacement Placement = NullsAtEnd;
+  const char* TypeName() const override { return "SortOptions"; }
+};
+enum NullMatchingBehavior { NullMatchingMatch = 0, NullMatchingSkip = 1, NullMatchingEmitNull = 2, NullMatchingInconclusive = 3 };
+struct Datum;
+struct SetLookupOptions : FunctionOptions {                   // compute/scalar_set_lookup.go (ValueSet, NullBehavior)
+  std::shared_ptr<ArrayData> ValueSet;
+  NullMatchingBehavior NullBehavior = NullMatchingMatch;
+  const char* TypeName() const override { return "SetLookupOptions"; }
+};
+
 enum class FuncKind { SCALAR, VECTOR, META };  // functions.go FuncScalar / FuncVector / FuncMeta
 
 class FunctionRegistry;
@@ -338,6 +353,10 @@ Status CumulativeSumChecked(const ExecCtx& ctx, const CumulativeOptions& opts, c
 // selection.go:657 / :304
 Status Filter(const ExecCtx& ctx, const Datum& values, const Datum& filter, const FilterOptions& opts, Datum* out);
 Status Take(const ExecCtx& ctx, const TakeOptions& opts, const Datum& values, const Datum& indices, Datum* out);
+// compute.SortIndices (vector_sort.go:205-211), compute.Unique (vector_hash.go), compute.IsIn (scalar_set_lookup.go)
+Status SortIndices(const ExecCtx& ctx, const Datum& input, const SortOptions& opts, Datum* out);
+Status Unique(const ExecCtx& ctx, const Datum& values, Datum* out);
+Status IsIn(const ExecCtx& ctx, const SetLookupOptions& opts, const Datum& values, Datum* out);
 
 // ---- executor internals exposed for tests (exec_internals_test.go exercises the same pieces) ----
 struct SpanPiece { int64_t pos; int64_t len; std::vector<int> chunk_index; std::vector<int64_t> chunk_pos; };

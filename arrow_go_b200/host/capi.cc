@@ -112,6 +112,28 @@ int agx_cast(agx_datum* d, int to_type, int allow_int_overflow, int allow_float_
   *out = new agx_datum{res};
   return AG_OK;
 }
+// compute.SortIndices(SortOptions{Order, NullPlacement}) / compute.Unique / compute.IsIn(SetLookupOptions{ValueSet, NullBehavior})
+int agx_sort_indices(agx_datum* d, int order, int null_placement, agx_datum** out) {
+  SortOptions o; o.Order = (SortOrder)order; o.Placement = (NullPlacement)null_placement;
+  ExecCtx ctx; Datum res;
+  AGX_TRY(CallFunction(ctx, "sort_indices", &o, {d->d}, &res));
+  *out = new agx_datum{res};
+  return AG_OK;
+}
+int agx_unique(agx_datum* d, agx_datum** out) {
+  ExecCtx ctx; Datum res;
+  AGX_TRY(CallFunction(ctx, "unique", nullptr, {d->d}, &res));
+  *out = new agx_datum{res};
+  return AG_OK;
+}
+int agx_is_in(agx_datum* d, agx_datum* value_set, int null_behavior, agx_datum** out) {
+  if (value_set->d.kind != DatumKind::ARRAY) return fail(Status::Invalid("is_in: the value set must be an array"));
+  SetLookupOptions o; o.ValueSet = value_set->d.array; o.NullBehavior = (NullMatchingBehavior)null_behavior;
+  ExecCtx ctx; Datum res;
+  AGX_TRY(CallFunction(ctx, "is_in", &o, {d->d}, &res));
+  *out = new agx_datum{res};
+  return AG_OK;
+}
 int agx_scalar_value(agx_datum* d, int* valid, void* value8) {
   if (d->d.kind != DatumKind::SCALAR) return fail(Status::Invalid("scalar_value: not a scalar"));
   *valid = d->d.scalar->valid ? 1 : 0;

@@ -1420,6 +1420,22 @@ FunctionRegistry* GetFunctionRegistry() {
       *out = Datum(res);
       return Status::OK();
     }), false);
+    // vector_sort.go:383-390, vector_hash.go, scalar_set_lookup.go: registry names bound to the GPU kernels
+    reg->AddFunction(std::make_shared<MetaFunction>("sort_indices", 1, [](const ExecCtx& ctx, const FunctionOptions* fo, const std::vector<Datum>& args, Datum* out) -> Status {
+      const auto* so = dynamic_cast<const SortOptions*>(fo);
+      if (args.size() != 1) return Status::Invalid("sort_indices takes one argument");
+      return SortIndices(ctx, args[0], so ? *so : SortOptions(), out);
+    }), false);
+    reg->AddFunction(std::make_shared<MetaFunction>("unique", 1, [](const ExecCtx& ctx, const FunctionOptions*, const std::vector<Datum>& args, Datum* out) -> Status {
+      if (args.size() != 1) return Status::Invalid("unique takes one argument");
+      return Unique(ctx, args[0], out);
+    }), false);
+    reg->AddFunction(std::make_shared<MetaFunction>("is_in", 1, [](const ExecCtx& ctx, const FunctionOptions* fo, const std::vector<Datum>& args, Datum* out) -> Status {
+      const auto* so = dynamic_cast<const SetLookupOptions*>(fo);
+      if (!so) return Status::Invalid("is_in requires SetLookupOptions");
+      if (args.size() != 1) return Status::Invalid("is_in takes one argument");
+      return IsIn(ctx, *so, args[0], out);
+    }), false);
     // vector_cumulative.go:75-93
     reg->AddFunction(MakeCumulative("cumulative_sum", false), false);
     reg->AddFunction(MakeCumulative("cumulative_sum_checked", true), false);
@@ -1544,6 +1560,72 @@ static Status ArithImpl(const ExecCtx& ctx, const ArithmeticOptions& opts, const
 Status Add(const ExecCtx& ctx, const ArithmeticOptions& o, const Datum& l, const Datum& r, Datum* out) { return ArithImpl(ctx, o, "add", l, r, out); }
 Status Subtract(const ExecCtx& ctx, const ArithmeticOptions& o, const Datum& l, const Datum& r, Datum* out) { return ArithImpl(ctx, o, "sub", l, r, out); }
 Status Multiply(const ExecCtx& ctx, const ArithmeticOptions& o, const Datum& l, const Datum& r, Datum* out) { return ArithImpl(ctx, o, "multiply", l, r, out); }
+// ---- sort_indices / unique / is_in: single fixed-width column, anything else is ErrNotImplemented
+// like the reference's type switches (vector_sort.go:183-185, scalar_set_lookup.go:270-272) ------------------------
+static Status OneArray(const Datum& d, const char* fn, std::shared_ptr<ArrayData>* out) {
+  if (d.kind == DatumKind::ARRAY) { *out = d.array; return Status::OK(); }
+  if (d.kind == DatumKind::CHUNKED && d.chunked->chunks.size() == 1) { *out = d.chunked->chunks[0]; return Status::OK(); }
+  return Status::NotImplemented(std::string(fn) + ": the GPU kernel takes one array (a multi-chunk input is merged by the parent registry's function)");
+}
+static Status MakeOut(Type t, int64_t len, std::shared_ptr<Buffer> data, std::shared_ptr<Buffer> valid, int64_t nulls, Datum* out) {
+  auto a = std::make_shared<ArrayData>();
+  a->type = t; a->length = len; a->offset = 0; a->null_count = nulls;
+  a->buffers[0] = valid; a->buffers[1] = data;
+  *out = Datum(a);
+  return Status::OK();
+}
+
+Status SortIndices(const ExecCtx& ctx, const Datum& input, const SortOptions& opts, Datum* out) {
+  std::shared_ptr<ArrayData> a;
+  RETURN_NOT_OK(OneArray(input, "sort_indices", &a));
+  if (!IsInteger(a->type) && !IsFloating(a->type)) return Status::NotImplemented(std::string("unsupported type for sort_indices operation: ") + TypeName(a->type));
+  std::shared_ptr<Buffer> idx;
+  RETURN_NOT_OK(Buffer::Allocate(std::max<int64_t>(a->length, 1) * 8, &idx));
+  int64_t nulls = 0, nans = 0;
+  const uint8_t* valid = (a->buffers[0] && a->null_count != 0) ? a->buffers[0]->data() : nullptr;
+  NATIVE(ag_sort_indices_dev((int)a->type, a->buffers[1] ? a->buffers[1]->data() : nullptr, valid, a->offset, a->length, (int)opts.Order, (int)opts.Placement,
+                             (uint64_t*)idx->data(), &nulls, &nans, nullptr));
+  return MakeOut(Type::UINT64, a->length, idx, nullptr, 0, out);
+}
+
+Status Unique(const ExecCtx& ctx, const Datum& values, Datum* out) {
+  std::shared_ptr<ArrayData> a;
+  RETURN_NOT_OK(OneArray(values, "unique", &a));
+  const int bw = BitWidth(a->type);
+  if (bw != 8 && bw != 16 && bw != 32 && bw != 64) return Status::NotImplemented(std::string("unique: unsupported type ") + TypeName(a->type));
+  const bool has_valid = a->buffers[0] && a->null_count != 0;
+  std::shared_ptr<Buffer> data, valid, len;
+  RETURN_NOT_OK(Buffer::Allocate(std::max<int64_t>(a->length, 1) * (bw / 8), &data));
+  if (has_valid) RETURN_NOT_OK(Buffer::Allocate(((a->length + 31) / 32) * 4 + 4, &valid));
+  RETURN_NOT_OK(Buffer::Allocate(16, &len));
+  NATIVE(ag_unique_dev(bw, a->buffers[1] ? a->buffers[1]->data() : nullptr, has_valid ? a->buffers[0]->data() : nullptr, a->offset, a->length, data->data(),
+                       has_valid ? valid->data() : nullptr, a->length, (int64_t*)len->data(), nullptr));
+  int64_t k = 0;
+  RETURN_NOT_OK(len->ToHost(&k, 8));
+  return MakeOut(a->type, k, data, valid, has_valid ? kUnknownNullCount : 0, out);
+}
+
+Status IsIn(const ExecCtx& ctx, const SetLookupOptions& opts, const Datum& values, Datum* out) {
+  std::shared_ptr<ArrayData> a;
+  RETURN_NOT_OK(OneArray(values, "is_in", &a));
+  if (!opts.ValueSet) return Status::Invalid("is_in: SetLookupOptions.ValueSet is required");
+  if (opts.ValueSet->type != a->type) return Status::NotImplemented("is_in: the value set must have the input's type (casts are left to the parent registry)");
+  const int bw = BitWidth(a->type);
+  if (bw != 8 && bw != 16 && bw != 32 && bw != 64) return Status::Invalid(std::string("unsupported type ") + TypeName(a->type) + " for is_in function");
+  const ArrayData& s = *opts.ValueSet;
+  std::shared_ptr<Buffer> data, valid, cnt;
+  const int64_t bm = ((a->length + 31) / 32) * 4 + 4;
+  RETURN_NOT_OK(Buffer::Allocate(bm, &data));
+  RETURN_NOT_OK(Buffer::Allocate(bm, &valid));
+  RETURN_NOT_OK(Buffer::Allocate(8, &cnt));
+  NATIVE(ag_is_in_dev(bw, a->buffers[1] ? a->buffers[1]->data() : nullptr, (a->buffers[0] && a->null_count != 0) ? a->buffers[0]->data() : nullptr, a->offset, a->length,
+                      s.buffers[1] ? s.buffers[1]->data() : nullptr, (s.buffers[0] && s.null_count != 0) ? s.buffers[0]->data() : nullptr, s.offset, s.length,
+                      (int)opts.NullBehavior, data->data(), valid->data(), (int64_t*)cnt->data(), nullptr));
+  int64_t nulls = 0;
+  RETURN_NOT_OK(cnt->ToHost(&nulls, 8));
+  return MakeOut(Type::BOOL, a->length, data, nulls ? valid : nullptr, nulls, out);
+}
+
 Status Filter(const ExecCtx& ctx, const Datum& values, const Datum& filter, const FilterOptions& opts, Datum* out) {
   return CallFunction(ctx, "filter", &opts, {values, filter}, out);
 }

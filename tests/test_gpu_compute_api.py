@@ -460,3 +460,43 @@ def test_cumulative_sum_chunked_random():
     vals, v, nulls = out.to_numpy()
     first = int(np.argmin(valid))
     assert v[:first].all() and not v[first:].any() and np.array_equal(vals[:first], np.cumsum(x[:first])) and nulls == n - first
+
+
+# ---------------------------------------------------------------- sort_indices / unique / is_in ---
+TYPE_BY_NAME = {"int32": pc.INT32, "uint64": pc.UINT64, "float64": pc.FLOAT64}
+
+
+def test_sort_indices_reference_cases():
+    """TestSortIndices (vector_sort_test.go:40-325), the fixed-width numeric cases, through compute.SortIndices."""
+    for case in load("sort_indices.json")["cases"]:
+        t = TYPE_BY_NAME[case["type"]]
+        vals = [None if v is None else (float("nan") if v == "NaN" else v) for v in case["values"]]
+        if not vals:
+            continue
+        out = pc.SortIndices(pc.Array.from_pylist(vals, t), order=case["order"], null_placement=case["null_placement"])
+        assert out.type == pc.UINT64 and out.to_pylist() == case["expected"], case["name"]
+    # registry name, default options (Ascending, NullsAtEnd)
+    assert pc.CallFunction("sort_indices", [pc.Array.from_pylist([3, None, 1], pc.INT64)]).to_pylist() == [2, 0, 1]
+    # sliced input: offsets apply to values and validity alike
+    a = pc.Array.from_pylist([9, 3, None, 1, 2, 8], pc.INT16).slice(1, 4)
+    assert pc.SortIndices(a, order=pc.DESCENDING, null_placement=pc.NULLS_AT_START).to_pylist() == [1, 0, 3, 2]
+
+
+@pytest.mark.parametrize("t", NUMERIC)
+def test_is_in_and_unique_reference_cases(t):
+    """TestIsInPrimitive (scalar_set_lookup_test.go:104-167) and PrimitiveHashKernelSuite.TestUnique
+    (vector_hash_test.go:236-255) for every numeric type."""
+    g = load("set_lookup.json")
+    for case in g["is_in"]:
+        if not case["input"]:
+            continue
+        for matching, expected in case["cases"]:
+            out = pc.IsIn(pc.Array.from_pylist(case["input"], t), pc.Array.from_pylist(case["set"], t), null_behavior=matching)
+            assert out.type == pc.BOOL and out.to_pylist() == expected, (case["name"], matching)
+    for case in g["unique"]:
+        out = pc.Unique(pc.Array.from_pylist(case["input"], t))
+        assert out.type == t and out.to_pylist() == case["expected"]
+    a = pc.Array.from_pylist([1, 2, None, 3, 2, None], t).slice(1, 4)   # vector_hash_test.go:244-254
+    assert pc.Unique(a).to_pylist() == [2, None, 3]
+    with pytest.raises(pc.ArrowError):
+        pc.IsIn(pc.Array.from_pylist([1], t), pc.Array.from_pylist([1], pc.BOOL))
