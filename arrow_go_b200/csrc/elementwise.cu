@@ -436,42 +436,58 @@ struct USign {
   }
 };
 
-// Same tile loop as binary_spans_kernel: a block streams contiguous kUnaryTile-row tiles, each
-// thread moving 4 independent 16-byte vectors at a time.
-constexpr int kUnaryTile = 4096;
-template <typename T, typename Op>
+// Same shape as binary_spans_kernel: tiles of 32 KB that start on the output's first 16-byte boundary; a warp owns 128
+// consecutive vectors of a tile (4 x 16-byte loads in flight per lane); kShift adds the shuffle / funnel-shift read of an
+// input that is not 16-byte aligned where the output is (an Arrow slice).
+template <typename T, typename Op, bool kShift>
 __global__ void __launch_bounds__(kEwThreads)
 unary_vec_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t n) {
   constexpr int N = 16 / sizeof(T);
-  const int64_t n_tiles = (n + kUnaryTile - 1) / kUnaryTile;
+  constexpr int kTile = kSpanTileBytes / (int)sizeof(T);
+  const long long head = span_head(out, (int)sizeof(T), n);
+  if (blockIdx.x == 0 && threadIdx.x < head) out[threadIdx.x] = Op::template apply<T, T>(in[threadIdx.x]);
+  const int64_t body = n - head;
+  const int64_t n_tiles = (body + kTile - 1) / kTile;
+  const int lane = threadIdx.x & 31;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t e0 = tile * kUnaryTile;
-    const int len = (int)((n - e0 < kUnaryTile) ? (n - e0) : kUnaryTile);
+    const int64_t e0 = head + tile * kTile;
+    const int len = (int)((n - e0 < kTile) ? (n - e0) : kTile);
     const T* ip = in + e0;
     T* op = out + e0;
     const int nvec = len / N;
-    constexpr int kIters = (kUnaryTile / N + kEwThreads - 1) / kEwThreads;
-#pragma unroll
-    for (int b = 0; b < kIters; b += kEwUnroll) {
-      Vec<T, N> a[kEwUnroll];
+    {
+      const int i = nvec * N + threadIdx.x;   // < N tail rows, last tile only
+      if (i < len) op[i] = Op::template apply<T, T>(ip[i]);
+    }
+    const int mb = kShift ? (int)(reinterpret_cast<uintptr_t>(ip) & 15) : 0;
+    const uint4* __restrict__ vf = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(ip) - mb);
+    uint4* __restrict__ ob = reinterpret_cast<uint4*>(op);
+    const int nin = nvec + (mb ? 1 : 0);
+    constexpr int kWarpVecs = 32 * kEwUnroll;
+    for (int base = (threadIdx.x >> 5) * kWarpVecs; base < nvec; base += (kEwThreads / 32) * kWarpVecs) {
+      uint4 a[kEwUnroll + 1];
 #pragma unroll
       for (int k = 0; k < kEwUnroll; ++k) {
-        const int vi = (b + k) * kEwThreads + threadIdx.x;
-        if (vi < nvec) a[k] = ldv(ip, vi);
+        const int vi = base + k * 32 + lane;
+        a[k] = make_uint4(0, 0, 0, 0);
+        if (vi < nin) a[k] = __ldcs(vf + vi);
       }
+      a[kEwUnroll] = make_uint4(0, 0, 0, 0);
+      if (kShift && mb && lane == 0 && base + kWarpVecs < nin) a[kEwUnroll] = __ldcs(vf + base + kWarpVecs);
 #pragma unroll
       for (int k = 0; k < kEwUnroll; ++k) {
-        const int vi = (b + k) * kEwThreads + threadIdx.x;
+        const int vi = base + k * 32 + lane;
+        uint4 av = a[k];
+        if (kShift && mb) av = shift_combine(a[k], neighbour_vector(a[k], a[k + 1], lane), mb);
         if (vi < nvec) {
+          const Vec<T, N>& x = *reinterpret_cast<const Vec<T, N>*>(&av);
           Vec<T, N> o;
 #pragma unroll
-          for (int e = 0; e < N; ++e) o.v[e] = Op::template apply<T, T>(a[k].v[e]);
-          stv(op, vi, o);
+          for (int e = 0; e < N; ++e) o.v[e] = Op::template apply<T, T>(x.v[e]);
+          __stcs(ob + vi, *reinterpret_cast<const uint4*>(&o));
         }
       }
     }
-    const int i = nvec * N + threadIdx.x;
-    if (i < len) op[i] = Op::template apply<T, T>(ip[i]);
   }
 }
 
@@ -485,13 +501,13 @@ unary_scalar_kernel(const TI* __restrict__ in, TO* __restrict__ out, int64_t n) 
 
 template <typename T, typename Op>
 static ag_status launch_unary_same_t(const void* in, void* out, int64_t n, cudaStream_t st) {
-  constexpr int N = 16 / sizeof(T);
-  if (aligned16(in) && aligned16(out)) {
-    const int grid = grid_one_wave(unary_vec_kernel<T, Op>, kEwThreads, (n + kUnaryTile - 1) / kUnaryTile);
-    unary_vec_kernel<T, Op><<<grid, kEwThreads, 0, st>>>((const T*)in, (T*)out, n);
+  const int64_t tiles = span_tiles(out, (int)sizeof(T), n);
+  if (span_needs_shift(AG_SHAPE_AS, in, nullptr, out, (int)sizeof(T), n)) {   // "array op scalar" = one array input
+    const int grid = grid_one_wave(unary_vec_kernel<T, Op, true>, kEwThreads, tiles);
+    unary_vec_kernel<T, Op, true><<<grid, kEwThreads, 0, st>>>((const T*)in, (T*)out, n);
   } else {
-    const int grid = grid_for(n, kEwThreads * kEwUnroll, kEwBlocksPerSM);
-    unary_scalar_kernel<T, T, Op><<<grid, kEwThreads, 0, st>>>((const T*)in, (T*)out, n);
+    const int grid = grid_one_wave(unary_vec_kernel<T, Op, false>, kEwThreads, tiles);
+    unary_vec_kernel<T, Op, false><<<grid, kEwThreads, 0, st>>>((const T*)in, (T*)out, n);
   }
   return check_launch("unary_kernel");
 }

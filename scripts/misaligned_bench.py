@@ -37,5 +37,13 @@ for tname, tid, w in (("f64", N.FLOAT64, 8), ("i32", N.INT32, 4), ("u8", N.UINT8
         print(f"add_{tname}_{name:16s} {ms:8.4f} ms  frac {3.0 * w * n / ms / 1e6 / PEAK:.3f}", flush=True)
     for b in (l, r, o):
         b.free()
+# unary Abs on a sliced input
+n8 = n
+x, o = DeviceBuffer(n8 * 8 + 256), DeviceBuffer(n8 * 8 + 256)
+N.call("ag_dev_memset", x.ptr, 1, n8 * 8 + 256, None)
+for name, (io, oo) in {"aligned": (0, 0), "in+1": (1, 0), "out+1": (0, 1), "both+1": (1, 1)}.items():
+    ms = timed(lambda: N.call("ag_arith_unary_same_dev", N.FLOAT64, N.OP_ABS, x.ptr + io * 8, o.ptr + oo * 8, n8, None))
+    res[f"abs_f64_{name}"] = {"ms": round(ms, 4), "frac": round(16.0 * n8 / ms / 1e6 / PEAK, 4)}
+    print(f"abs_f64_{name:20s} {ms:8.4f} ms  frac {16.0 * n8 / ms / 1e6 / PEAK:.3f}", flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open("gpurun_out/misaligned_bench.json", "w"), indent=1)
