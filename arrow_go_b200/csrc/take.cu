@@ -248,141 +248,166 @@ __global__ void __launch_bounds__(1024) take_probe_kernel(const I* __restrict__ 
 // memory atomics (the returned old value is the row's rank inside its bucket), exclusive-scan the <= 1024 counters,
 // scatter window-local indices into bucket order in shared memory, write them out coalesced.  The bounds check of
 // checkIndexBounds is fused here (valid slots only).
+struct PartitionShared {
+  uint32_t hist[kWinMaxBuckets + 2];
+  alignas(16) uint32_t sorted[kWinTile];
+  uint32_t wsum[kWinAThreads / 32];
+};
+
+// One tile.  kFull: 8192 rows and a 16-byte aligned index pointer -> no per-row range tests, 128-bit loads.
+// All per-row arithmetic is 32-bit: lim32 = min(limit, 2^32 - 1) (a 64-bit index is first tested against the 64-bit
+// limit and then narrowed, since a row that passes is < 2^32 only when the table is; otherwise the window-local index
+// and the bucket come from the 64-bit value).
+template <typename I, bool kValid, bool kFull>
+__device__ __forceinline__ void partition_tile(const TakeParams& p, const TakeWindowPlan& w, PartitionShared& sh, const I* __restrict__ idx,
+                                               int64_t tile, unsigned long long limit, uint32_t* __restrict__ sorted, uint16_t* __restrict__ perm,
+                                               uint16_t* __restrict__ off, uint32_t& bad_local) {
+  constexpr int QUADS = kWinTile / (4 * kWinAThreads);
+  constexpr int SPER = (kWinMaxBuckets + 2 + kWinAThreads - 1) / kWinAThreads;
+  const int lane = threadIdx.x & 31;
+  const int64_t base = tile * kWinTile;
+  const int len = kFull ? kWinTile : (int)min((int64_t)kWinTile, p.n - base);
+  const uint32_t nb = (uint32_t)w.nb;
+  const int shift = w.shift;
+  const bool all_fit = limit > 0xffffffffull;                 // every 32-bit index is in range
+  const uint32_t lim32 = all_fit ? 0xffffffffu : (uint32_t)limit;
+  for (int b = threadIdx.x; b < w.nslots; b += kWinAThreads) sh.hist[b] = 0;
+  __syncthreads();
+  I ix[QUADS][4];
+  uint32_t bk[QUADS][4];   // bucket << 13 | rank within the bucket  (bucket <= 1023: 10 bits)
+#pragma unroll
+  for (int q = 0; q < QUADS; ++q) {
+    const int r0 = q * (4 * kWinAThreads) + 4 * threadIdx.x;
+    if (kFull) {
+      const I* src = idx + base + r0;
+      if constexpr (sizeof(I) == 4) {
+        const uint4 v = __ldcs(reinterpret_cast<const uint4*>(src));
+        ix[q][0] = v.x; ix[q][1] = v.y; ix[q][2] = v.z; ix[q][3] = v.w;
+      } else {
+        const ulonglong2 v0 = __ldcs(reinterpret_cast<const ulonglong2*>(src));
+        const ulonglong2 v1 = __ldcs(reinterpret_cast<const ulonglong2*>(src) + 1);
+        ix[q][0] = v0.x; ix[q][1] = v0.y; ix[q][2] = v1.x; ix[q][3] = v1.y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ix[q][j] = r0 + j < len ? idx[base + r0 + j] : (I)0;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < QUADS; ++q) {
+    const int r0 = q * (4 * kWinAThreads) + 4 * threadIdx.x;
+    uint32_t vbits = 0xfu;
+    if (kValid) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if ((!kFull && r0 + j >= len) || !bit_is_set(p.ivalid, p.ioff + base + r0 + j)) vbits &= ~(1u << j);
+    } else if (!kFull) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (r0 + j >= len) vbits &= ~(1u << j);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool live = (!kValid && kFull) ? true : (bool)((vbits >> j) & 1u);   // row exists and its index slot is valid
+      bool oob;
+      uint32_t b;
+      if constexpr (sizeof(I) == 4) {
+        oob = (uint32_t)ix[q][j] >= lim32 && !all_fit;        // one 32-bit compare
+        b = shift < 32 ? (uint32_t)ix[q][j] >> shift : 0u;
+      } else {
+        oob = (unsigned long long)ix[q][j] >= limit;
+        b = (uint32_t)((unsigned long long)ix[q][j] >> shift);
+      }
+      if (live && oob) bad_local = min(bad_local, (uint32_t)(r0 + j));
+      if (!live || oob) b = nb;
+      bk[q][j] = 0;
+      if (kFull || r0 + j < len) bk[q][j] = (b << 13) | atomicAdd(&sh.hist[b], 1u);
+    }
+  }
+  __syncthreads();
+  {
+    uint32_t loc[SPER];
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < SPER; ++j) {
+      const int b = threadIdx.x * SPER + j;
+      loc[j] = b < w.nslots ? sh.hist[b] : 0u;
+      s += loc[j];
+    }
+    uint32_t inc = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    if (lane == 31) sh.wsum[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    uint32_t wbase = 0;
+    for (int q = 0; q < (threadIdx.x >> 5); ++q) wbase += sh.wsum[q];
+    uint32_t run = wbase + inc - s;
+#pragma unroll
+    for (int j = 0; j < SPER; ++j) {
+      const int b = threadIdx.x * SPER + j;
+      if (b < w.nslots) sh.hist[b] = run;
+      run += loc[j];
+    }
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < w.nslots; b += kWinAThreads) off[tile * w.nslots + b] = (uint16_t)sh.hist[b];
+  const uint32_t wmask32 = shift < 32 ? ((1u << shift) - 1u) : 0xffffffffu;
+#pragma unroll
+  for (int q = 0; q < QUADS; ++q) {
+    const int r0 = q * (4 * kWinAThreads) + 4 * threadIdx.x;
+    uint32_t pos[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      pos[j] = 0;
+      if (kFull || r0 + j < len) {
+        pos[j] = sh.hist[bk[q][j] >> 13] + (bk[q][j] & 8191u);
+        sh.sorted[pos[j]] = (uint32_t)ix[q][j] & wmask32;    // low 32 bits hold the whole window-local index (shift <= 32)
+      }
+    }
+    if (kFull || r0 + 4 <= len) {
+      *reinterpret_cast<uint2*>(perm + base + r0) = make_uint2(pos[0] | (pos[1] << 16), pos[2] | (pos[3] << 16));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (r0 + j < len) perm[base + r0 + j] = (uint16_t)pos[j];
+    }
+  }
+  __syncthreads();
+  {
+    const int nv = len >> 2;
+    uint4* dst = reinterpret_cast<uint4*>(sorted + base);        // scratch: 256-byte aligned, base is a multiple of 8192
+    const uint4* src = reinterpret_cast<const uint4*>(sh.sorted);
+    for (int i = threadIdx.x; i < nv; i += kWinAThreads) dst[i] = src[i];
+    const int r = (nv << 2) + threadIdx.x;
+    if (!kFull && r < len) sorted[base + r] = sh.sorted[r];
+  }
+  __syncthreads();
+}
+
 template <typename I, bool kValid>
 __global__ void __launch_bounds__(kWinAThreads, 2)
 take_partition_kernel(const TakeParams p, const TakeWindowPlan w, uint32_t* __restrict__ sorted, uint16_t* __restrict__ perm,
                       uint16_t* __restrict__ off) {
   // thread t owns rows 4t..4t+3 of each 2048-row quarter of the tile: 128-bit index loads, 64-bit perm stores
-  constexpr int QUADS = kWinTile / (4 * kWinAThreads);
-  constexpr int SPER = (kWinMaxBuckets + 2 + kWinAThreads - 1) / kWinAThreads;
-  __shared__ uint32_t hist[kWinMaxBuckets + 2];
-  __shared__ __align__(16) uint32_t s_sorted[kWinTile];
-  __shared__ uint32_t wsum[kWinAThreads / 32];
+  __shared__ PartitionShared sh;
   if (*p.route != kRouteWindowed) return;
   const I* __restrict__ idx = reinterpret_cast<const I*>(p.idx);
-  const int lane = threadIdx.x & 31;
-  const unsigned long long wmask = (1ull << w.shift) - 1ull;
   // one unsigned compare does the whole bounds check: a negative signed index is >= 2^(bits-1) as unsigned
   unsigned long long limit = p.vlen;
   if (p.idx_signed && sizeof(I) < 8 && limit > (1ull << (sizeof(I) * 8 - 1))) limit = 1ull << (sizeof(I) * 8 - 1);
   if (p.idx_signed && sizeof(I) == 8 && limit > (1ull << 63)) limit = 1ull << 63;
-  const uint32_t nb = (uint32_t)w.nb;
-  const int shift = w.shift;
   const bool vec_ok = (reinterpret_cast<uintptr_t>(idx) & 15) == 0;
   long long my_bad = AG_NO_ERROR_POS;
   for (int64_t tile = blockIdx.x; tile < w.ntiles; tile += gridDim.x) {
-    const int64_t base = tile * kWinTile;
-    const int len = (int)min((int64_t)kWinTile, p.n - base);
-    const bool full = len == kWinTile && vec_ok;
-    for (int b = threadIdx.x; b < w.nslots; b += kWinAThreads) hist[b] = 0;
-    __syncthreads();
-    I ix[QUADS][4];
-    uint32_t bk[QUADS][4];   // bucket << 13 | rank within the bucket  (bucket <= 1023: 10 bits)
-    if (full) {
-#pragma unroll
-      for (int q = 0; q < QUADS; ++q) {
-        const I* src = idx + base + q * (4 * kWinAThreads) + 4 * threadIdx.x;
-        if constexpr (sizeof(I) == 4) {
-          const uint4 v = __ldcs(reinterpret_cast<const uint4*>(src));
-          ix[q][0] = v.x; ix[q][1] = v.y; ix[q][2] = v.z; ix[q][3] = v.w;
-        } else {
-          const ulonglong2 v0 = __ldcs(reinterpret_cast<const ulonglong2*>(src));
-          const ulonglong2 v1 = __ldcs(reinterpret_cast<const ulonglong2*>(src) + 1);
-          ix[q][0] = v0.x; ix[q][1] = v0.y; ix[q][2] = v1.x; ix[q][3] = v1.y;
-        }
-      }
-    } else {
-#pragma unroll
-      for (int q = 0; q < QUADS; ++q)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int r = q * (4 * kWinAThreads) + 4 * threadIdx.x + j;
-          ix[q][j] = r < len ? idx[base + r] : (I)0;
-        }
-    }
-#pragma unroll
-    for (int q = 0; q < QUADS; ++q) {
-      const int r0 = q * (4 * kWinAThreads) + 4 * threadIdx.x;
-      uint32_t vbits = 0xfu;
-      if (kValid) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (r0 + j >= len || !bit_is_set(p.ivalid, p.ioff + base + r0 + j)) vbits &= ~(1u << j);
-      } else if (!full) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) if (r0 + j >= len) vbits &= ~(1u << j);
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const bool live = (vbits >> j) & 1u;                       // row exists and its index slot is valid
-        const bool oob = (unsigned long long)ix[q][j] >= limit;
-        if (live && oob && p.bounds_check && base + r0 + j < my_bad) my_bad = base + r0 + j;
-        const uint32_t b = (live && !oob) ? (uint32_t)((unsigned long long)ix[q][j] >> shift) : nb;
-        bk[q][j] = 0;
-        if (full || r0 + j < len) bk[q][j] = (b << 13) | atomicAdd(&hist[b], 1u);
-      }
-    }
-    __syncthreads();
-    {
-      uint32_t loc[SPER];
-      uint32_t s = 0;
-#pragma unroll
-      for (int j = 0; j < SPER; ++j) {
-        const int b = threadIdx.x * SPER + j;
-        loc[j] = b < w.nslots ? hist[b] : 0u;
-        s += loc[j];
-      }
-      uint32_t inc = s;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += o;
-      }
-      if (lane == 31) wsum[threadIdx.x >> 5] = inc;
-      __syncthreads();
-      uint32_t wbase = 0;
-      for (int q = 0; q < (threadIdx.x >> 5); ++q) wbase += wsum[q];
-      uint32_t run = wbase + inc - s;
-#pragma unroll
-      for (int j = 0; j < SPER; ++j) {
-        const int b = threadIdx.x * SPER + j;
-        if (b < w.nslots) hist[b] = run;
-        run += loc[j];
-      }
-    }
-    __syncthreads();
-    for (int b = threadIdx.x; b < w.nslots; b += kWinAThreads) off[tile * w.nslots + b] = (uint16_t)hist[b];
-#pragma unroll
-    for (int q = 0; q < QUADS; ++q) {
-      const int r0 = q * (4 * kWinAThreads) + 4 * threadIdx.x;
-      uint32_t pos[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        pos[j] = 0;
-        if (full || r0 + j < len) {
-          pos[j] = hist[bk[q][j] >> 13] + (bk[q][j] & 8191u);
-          s_sorted[pos[j]] = (uint32_t)((unsigned long long)ix[q][j] & wmask);
-        }
-      }
-      if (full || r0 + 4 <= len) {
-        *reinterpret_cast<uint2*>(perm + base + r0) = make_uint2(pos[0] | (pos[1] << 16), pos[2] | (pos[3] << 16));
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) if (r0 + j < len) perm[base + r0 + j] = (uint16_t)pos[j];
-      }
-    }
-    __syncthreads();
-    {
-      const int nv = len >> 2;
-      uint4* dst = reinterpret_cast<uint4*>(sorted + base);        // scratch: 256-byte aligned, base is a multiple of 8192
-      const uint4* src = reinterpret_cast<const uint4*>(s_sorted);
-      for (int i = threadIdx.x; i < nv; i += kWinAThreads) dst[i] = src[i];
-      const int r = (nv << 2) + threadIdx.x;
-      if (r < len) sorted[base + r] = s_sorted[r];
-    }
-    __syncthreads();
+    uint32_t bad_local = 0xffffffffu;
+    const bool full = vec_ok && (tile + 1) * (int64_t)kWinTile <= p.n;
+    if (full) partition_tile<I, kValid, true>(p, w, sh, idx, tile, limit, sorted, perm, off, bad_local);
+    else partition_tile<I, kValid, false>(p, w, sh, idx, tile, limit, sorted, perm, off, bad_local);
+    if (bad_local != 0xffffffffu && tile * kWinTile + bad_local < my_bad) my_bad = tile * kWinTile + bad_local;
   }
   if (p.bounds_check) {
+    const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) {
       const long long o = __shfl_xor_sync(0xffffffffu, my_bad, m);
