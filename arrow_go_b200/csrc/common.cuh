@@ -117,6 +117,16 @@ inline bool type_is_float(int type) { return type == AG_TYPE_FLOAT32 || type == 
 inline int64_t bytes_for_bits(int64_t nbits) { return (nbits + 7) >> 3; }
 
 int blocks_per_sm(const void* kernel, int threads);
+int lab_knob(int key);   // experiment switches (ag_lab_set); 0 = shipped behaviour
+// Opt a kernel into `bytes` of dynamic shared memory on the calling thread's device, once per device
+// (`done` = the caller's per-instantiation bit set; the attribute is per function per context).
+inline ag_status ensure_dynamic_smem(const void* kernel, int bytes, std::atomic<unsigned>* done) {
+  const unsigned bit = 1u << (current_device() & 31);
+  if (done->load(std::memory_order_acquire) & bit) return AG_OK;
+  AG_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done->fetch_or(bit, std::memory_order_release);
+  return AG_OK;
+}
 // One-wave grid for a grid-stride kernel: min(blocks needed, SMs x resident blocks per SM).
 template <typename K>
 inline int grid_one_wave(K kernel, int threads, int64_t blocks_needed) {

@@ -18,8 +18,8 @@
 //     loads; fused compare: the values are streamed once and __ballot_sync packs the predicate);
 //   * block scan of the word popcounts -> tile aggregate published in a 64-bit status word
 //     (2 flag bits + 62-bit count, one store => a reader never sees a flag without its value);
-//     warp 0 looks back 32 tiles at a time until it meets an inclusive prefix.  The chain moves
-//     32 tiles per L2 round trip, so tiles must be large: 32 x 32768 rows per ~0.7 us;
+//     warp 0 resolves the tile's exclusive prefix with a two-level look-back (`lookback` below): two
+//     or three dependent L2 round trips whatever the number of tiles in flight;
 //   * phase 2 is warp-cooperative: for each word, lane j owns row 32k+j; the lanes whose bit is
 //     set load (8 words in flight per lane) and store to out[base_k + rank], rank = popc of the
 //     lower set bits, so the writes of one step are contiguous.  Only the sectors of selected
@@ -64,34 +64,55 @@ struct FilterParams {
   uint32_t* out_valid;       // 4-byte aligned, pre-zeroed for ceil(capacity/32) words (may be NULL)
   int64_t capacity;          // rows the output buffers can hold
   unsigned long long* status;  // one status word per tile
+  unsigned long long* gstatus; // one status word per group of 32 tiles
   long long* out_len;
   int64_t n_tiles;
 };
 
-// One warp.  Returns the exclusive prefix of `tile` (rows emitted by all earlier tiles) and
-// publishes this tile's inclusive prefix.  One 64-bit word carries flag + count, so a reader
-// never sees a flag without its value.  Throughput of the chain is 32 tiles per L2 round trip,
-// which is why tiles are 32K rows: 32 x 32768 rows / ~0.7 us >> the HBM rate of any width.
-__device__ __forceinline__ unsigned long long lookback(unsigned long long* st, int64_t tile, unsigned long long total, int lane) {
-  if (tile == 0) {
-    if (lane == 0) st_status(st, kFlagIncl | total);
-    return 0;
-  }
-  if (lane == 0) st_status(st + tile, kFlagAgg | total);
+// One warp.  Returns the exclusive prefix of `tile` (rows emitted by all earlier tiles).
+//
+// Two levels, so the number of DEPENDENT L2 round trips does not grow with the number of tiles in
+// flight.  (A flat 32-wide look-back needs about q/64 hops for the q-th tile of a wave: with 450-740
+// resident blocks in lockstep the last tiles of a wave waited 7-10 hops, ~5-9 us per wave, while HBM
+// idled: profiles/r2/fused_filter_experiments.txt.)
+//   level 1: tiles form groups of 32.  A tile publishes its AGGREGATE in st[tile] (written once) and
+//            reads the aggregates of the earlier tiles of its own group: one batch of <= 31 polls;
+//   level 2: the last tile of a group publishes the GROUP aggregate in gst[g] and, after its own
+//            look-back, the group's INCLUSIVE prefix in the same word; every tile looks back over the
+//            groups before its own, 32 at a time, until it meets an inclusive prefix.  Fewer than 32
+//            groups (1024 tiles) are ever in flight, so that is one hop.
+// One 64-bit word carries flag + count, so a reader never sees a flag without its value.  A tile waits
+// only on lower tiles, which the static tile order + one resident wave guarantee are running or done.
+template <bool kPublish = true>   // false: the caller has already published the tile's aggregate
+__device__ __forceinline__ unsigned long long lookback(unsigned long long* st, unsigned long long* gst, int64_t tile,
+                                                       unsigned long long total, int lane) {
+  const int64_t g = tile >> 5;
+  const int q = (int)(tile & 31);
+  if (kPublish && lane == 0) st_status(st + tile, kFlagAgg | total);
+  // level 1
+  unsigned long long s = (lane < q) ? 0ull : kFlagAgg;  // lanes >= q: nothing to wait for
+  do {
+    if ((s >> kFlagShift) == 0) s = ld_status(st + (g << 5) + lane);
+  } while (__any_sync(0xffffffffu, (s >> kFlagShift) == 0));
+  unsigned long long part = (lane < q) ? (s & kValMask) : 0ull;
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
+  const bool leader = q == 31;
+  if (leader && lane == 0) st_status(gst + g, kFlagAgg | (part + total));
+  // level 2
   unsigned long long running = 0;
-  int64_t look = tile - 1;
-  while (true) {
+  int64_t look = g - 1;
+  while (look >= 0) {
     const int64_t idx = look - lane;
-    unsigned long long s;
     unsigned flag;
     do {
-      s = (idx >= 0) ? ld_status(st + idx) : kFlagIncl;  // before tile 0: inclusive prefix 0
+      s = (idx >= 0) ? ld_status(gst + idx) : kFlagIncl;  // before group 0: inclusive prefix 0
       flag = (unsigned)(s >> kFlagShift);
     } while (__any_sync(0xffffffffu, flag == 0));
     const unsigned incl = __ballot_sync(0xffffffffu, flag == 2);
     unsigned long long v = s & kValMask;
     if (incl) {
-      const int first = __ffs(incl) - 1;  // closest tile that already knows its inclusive prefix
+      const int first = __ffs(incl) - 1;  // closest group that already knows its inclusive prefix
       if (lane > first) v = 0;
     }
 #pragma unroll
@@ -100,8 +121,8 @@ __device__ __forceinline__ unsigned long long lookback(unsigned long long* st, i
     if (incl) break;
     look -= 32;
   }
-  if (lane == 0) st_status(st + tile, kFlagIncl | (running + total));
-  return running;
+  if (leader && lane == 0) st_status(gst + g, kFlagIncl | (running + part + total));
+  return running + part;
 }
 
 struct FCmpEq { template <typename T> static __device__ __forceinline__ bool apply(T a, T b) { return a == b; } };
@@ -181,7 +202,7 @@ filter_kernel(const FilterParams p) {
 #pragma unroll
     for (int k = 0; k < kFWordsPerThread; ++k) { s_base[threadIdx.x * kFWordsPerThread + k] = run; run += cnt[k]; }
     if (warp == 0) {
-      const unsigned long long excl = lookback(p.status, tile, tile_total, lane);
+      const unsigned long long excl = lookback(p.status, p.gstatus, tile, tile_total, lane);
       if (lane == 0) {
         s_tile_base = excl;
         if (tile == p.n_tiles - 1) *p.out_len = (long long)(excl + tile_total);
@@ -297,9 +318,11 @@ static ag_status launch_filter_t(FilterParams& p, cudaStream_t st) {
   AG_TRY(get_workspace(st, &ws));
   WorkspaceLock ws_lock(ws);
   p.n_tiles = (p.n + kFTileRows - 1) / kFTileRows;
-  AG_TRY(ensure_tile_status(ws, (size_t)p.n_tiles, st));
+  const size_t n_status = (size_t)p.n_tiles + (size_t)((p.n_tiles + 31) >> 5);
+  AG_TRY(ensure_tile_status(ws, n_status, st));
   p.status = ws->tile_status;
-  AG_CUDA_TRY(cudaMemsetAsync(p.status, 0, (size_t)p.n_tiles * sizeof(unsigned long long), st));
+  p.gstatus = p.status + p.n_tiles;
+  AG_CUDA_TRY(cudaMemsetAsync(p.status, 0, n_status * sizeof(unsigned long long), st));
   if (p.out_valid) AG_CUDA_TRY(cudaMemsetAsync(p.out_valid, 0, (size_t)((p.capacity + 31) >> 5) * 4, st));
   if (kMode == 2 && p.capacity > 0) AG_CUDA_TRY(cudaMemsetAsync(p.out, 0, (size_t)((p.capacity + 31) >> 5) * 4, st));
   void* args[] = {(void*)&p};
@@ -381,127 +404,183 @@ ag_status take_indices_dev(int index_width, const uint8_t* mask, const uint8_t* 
 // Greater/…(values, scalar) -> Filter in ONE kernel (config 3 of BASELINE.json): no intermediate
 // mask in HBM and every value is read from HBM exactly once (8 + 8s bytes/row).
 //
-// A 32K-row block tile is 32 "segments" of 1024 rows (4 sub-tiles x 8 warps).  Phase 1, per
-// segment: lane j loads rows 32k+j (32 coalesced 256-byte requests in flight), __ballot_sync
-// packs the predicate words, a warp scan of their popcounts gives every selected value its slot,
-// and the values go straight from registers into the segment's staging area in SHARED memory.
-// Then: block scan of the 32 segment counts, look-back for the tile base, and phase 2 copies each
-// staged segment to out[] with fully coalesced stores.  A segment that selects more rows than its
-// staging area holds (kSegCap, > 21 % of 1024) is flagged and compacted by re-reading its rows.
-// Measured at 100M int64 rows, 10 % selected: 190 us (two-step compare + filter: 285 us; the
-// first fused version, which re-read selected rows through L2: 210 us; 512-row segments with the
-// same shared-memory budget: 198 us).
+// A 16K-row block tile is 16 "segments" of 1024 rows (2 per compute warp).  Phase 1, per segment: lane j
+// loads rows 32k+j (32 coalesced 256-byte requests in flight, requested one segment AHEAD of the votes,
+// across tile boundaries too), __ballot_sync packs the predicate words, every lane tracks the running count
+// from the ballots and the selected values go straight from registers into the segment's staging area in
+// SHARED memory.  Phase 2 copies each staged segment to out[] with fully coalesced stores.  A segment that
+// selects more rows than its staging area holds (kSegCap, > 21 % of 1024) is compacted by re-reading it.
+//
+// Schedule (round 2; history in profiles/r2/fused_filter_experiments.txt).  The block-synchronous shape —
+// 8 warps stream a tile, meet, warp 0 resolves the look-back, all copy out — left every resident block in
+// the same phase, so nothing covered the look-back: 186 us = 0.72 of the roofline whatever the occupancy,
+// the look-back width or the tile claiming order.  Here the look-back is off the critical path:
+//   * a block = 8 compute warps + 1 LOOK-BACK warp, staging areas double-buffered;
+//   * iteration j: the compute warps run phase 1 of tile j and then phase 2 of tile j-1, while the look-back
+//     warp resolves the prefix of tile j-1; one block barrier per tile joins them;
+//   * a tile's aggregate is published by the LAST compute warp to finish its segments (shared-memory counter):
+//     other blocks see it a whole phase-2 + look-back ahead of the moment they need it.
 constexpr int kSegRows = 1024;
-constexpr int kSegsPerTile = kFTileRows / kSegRows;  // 32
-constexpr int kSegCap = 224;                         // staged values per segment
+constexpr int kSegCap = 224;                              // staged values per segment
+constexpr int kFuTileRows = 16384;
+constexpr int kFuSegs = kFuTileRows / kSegRows;           // 16
+constexpr int kFuSegsPerWarp = kFuSegs / kFWarps;         // 2
+constexpr int kFuThreads = kFThreads + 32;                // + the look-back warp
+constexpr int kFuEmitWords = kFuTileRows / 32;            // 512
+
+template <typename T>
+struct FusedBuffers {   // one of the two staging buffers (dynamic shared memory)
+  uint32_t emit[kFuEmitWords];   // predicate words (overflow path only)
+  uint32_t cnt[kFuSegs];         // rows selected per segment
+  uint32_t excl[kFuSegs];        // exclusive offsets inside the tile
+  T stage[kFuSegs][kSegCap];
+};
 
 template <typename T, typename Cmp>
-__global__ void __launch_bounds__(kFThreads, 3)
+__global__ void __launch_bounds__(kFuThreads, 2)
 fused_filter_kernel(const T* __restrict__ vals, T scalar, int64_t n, T* __restrict__ out, int64_t capacity,
-                    unsigned long long* status, long long* out_len, int64_t n_tiles) {
+                    unsigned long long* status, unsigned long long* gstatus, long long* out_len, int64_t n_tiles) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint32_t* s_emit = reinterpret_cast<uint32_t*>(smem_raw);            // [1024] predicate words
-  uint32_t* s_cnt = s_emit + kFTileWords;                              // [32] rows selected per segment
-  uint32_t* s_excl = s_cnt + kSegsPerTile;                             // [32] exclusive offsets inside the tile
-  T* s_stage = reinterpret_cast<T*>(s_excl + kSegsPerTile);            // [32][kSegCap]
-  __shared__ unsigned long long s_tile_base;
+  FusedBuffers<T>* bufs = reinterpret_cast<FusedBuffers<T>*>(smem_raw);   // [2]
+  __shared__ unsigned long long s_tile_base[2];
+  __shared__ uint32_t s_total[2];
+  __shared__ unsigned s_arrived[2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool looker = warp == kFWarps;
+  if (threadIdx.x < 2) s_arrived[threadIdx.x] = 0u;
+  __syncthreads();
 
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t trow0 = tile * kFTileRows;
-    // ---- phase 1: stream, predicate, stage --------------------------------------------------
-#pragma unroll 1
-    for (int sub = 0; sub < kSegsPerTile / kFWarps; ++sub) {
-      const int seg = sub * kFWarps + warp;
-      const int64_t wrow0 = trow0 + (int64_t)seg * kSegRows;
-      T v[32];
-      if (wrow0 + kSegRows <= n) {
+  T v[32];
+  auto issue = [&](int64_t t, int sub) {
+    const int64_t wrow0 = t * kFuTileRows + (int64_t)(sub * kFWarps + warp) * kSegRows;
+    if (wrow0 + kSegRows <= n) {
 #pragma unroll
-        for (int k = 0; k < 32; ++k) v[k] = __ldcs(vals + wrow0 + k * 32 + lane);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const int64_t row = wrow0 + k * 32 + lane;
-          v[k] = (row < n) ? __ldcs(vals + row) : scalar;
-        }
-      }
-      __syncwarp();  // keep every load ahead of the first vote
-      // Every lane sees every ballot, so each lane tracks the running count itself: the slot of a
-      // selected row is (rows selected in earlier words) + (selected rows below it in its word).
-      // No scan and no shuffles; values go from registers straight into the staging area (slots
-      // past kSegCap are dropped — such a segment is flagged and compacted by re-reading).
-      T* stage = s_stage + seg * kSegCap;
-      uint32_t myword = 0;
-      unsigned running = 0;
-      const uint32_t lt = (1u << lane) - 1u;
+      for (int k = 0; k < 32; ++k) v[k] = __ldcs(vals + wrow0 + k * 32 + lane);
+    } else {
 #pragma unroll
       for (int k = 0; k < 32; ++k) {
         const int64_t row = wrow0 + k * 32 + lane;
-        const bool pr = row < n && Cmp::template apply<T>(v[k], scalar);
-        const uint32_t bits = __ballot_sync(0xffffffffu, pr);
-        if (lane == k) myword = bits;
-        const unsigned pos = running + __popc(bits & lt);
-        if (pr && pos < kSegCap) stage[pos] = v[k];
-        running += __popc(bits);
-      }
-      s_emit[seg * 32 + lane] = myword;
-      if (lane == 0) s_cnt[seg] = running;
-    }
-    __syncthreads();
-    // ---- block scan of the 32 segment counts + look-back (warp 0) -----------------------------
-    if (warp == 0) {
-      const unsigned c = s_cnt[lane];
-      unsigned incl = c;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
-      }
-      s_excl[lane] = incl - c;
-      const unsigned tile_total = __shfl_sync(0xffffffffu, incl, 31);
-      const unsigned long long excl = lookback(status, tile, tile_total, lane);
-      if (lane == 0) {
-        s_tile_base = excl;
-        if (tile == n_tiles - 1) *out_len = (long long)(excl + tile_total);
+        v[k] = (row < n) ? __ldcs(vals + row) : scalar;
       }
     }
-    __syncthreads();
-    // ---- phase 2: staged segments -> out[] with coalesced stores --------------------------------
-    const unsigned long long tbase = s_tile_base;
+  };
+  const int64_t G = gridDim.x;
+  const int64_t mine = ((int64_t)blockIdx.x < n_tiles) ? (n_tiles - blockIdx.x + G - 1) / G : 0;
+  if (!looker && mine > 0) issue(blockIdx.x, 0);
+  // iteration j: phase 1 of tile j (j < mine); look-back + phase 2 of tile j-1 (j >= 1)
+  for (int64_t j = 0; j <= mine; ++j) {
+    const int64_t tile_r = blockIdx.x + j * G, tile_f = tile_r - G;
+    const int br = (int)(j & 1), bf = br ^ 1;
+    if (!looker) {
+      if (j < mine) {
+        FusedBuffers<T>& B = bufs[br];
+        const int64_t trow0 = tile_r * kFuTileRows;
 #pragma unroll 1
-    for (int sub = 0; sub < kSegsPerTile / kFWarps; ++sub) {
-      const int seg = sub * kFWarps + warp;
-      const unsigned total = s_cnt[seg];
-      if (total == 0) continue;
-      const unsigned long long base = tbase + s_excl[seg];
-      if (total <= kSegCap) {
-        const T* stage = s_stage + seg * kSegCap;
-        for (unsigned i = lane; i < total; i += 32)
-          if ((long long)(base + i) < capacity) out[base + i] = stage[i];
-      } else {
-        // overflow: re-read the segment's selected rows (they are at worst in L2)
-        const uint32_t myword = s_emit[seg * 32 + lane];
-        const unsigned cnt = __popc(myword);
-        unsigned incl = cnt;
+        for (int sub = 0; sub < kFuSegsPerWarp; ++sub) {
+          const int seg = sub * kFWarps + warp;
+          const int64_t wrow0 = trow0 + (int64_t)seg * kSegRows;
+          __syncwarp();  // keep every load ahead of the first vote
+          // Every lane sees every ballot, so each lane tracks the running count itself: the slot of a selected row is
+          // (rows selected in earlier words) + (selected rows below it in its word).  No scan and no shuffles; values
+          // go from registers straight into the staging area (slots past kSegCap are dropped: overflow path).
+          T* stage = B.stage[seg];
+          uint32_t myword = 0;
+          unsigned running = 0;
+          const uint32_t lt = (1u << lane) - 1u;
+          if (wrow0 + kSegRows <= n) {  // interior segment: no per-row range test
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
-          if (lane >= d) incl += t;
+            for (int k = 0; k < 32; ++k) {
+              const bool pr = Cmp::template apply<T>(v[k], scalar);
+              const uint32_t bits = __ballot_sync(0xffffffffu, pr);
+              if (lane == k) myword = bits;
+              const unsigned pos = running + __popc(bits & lt);
+              if (pr && pos < kSegCap) stage[pos] = v[k];
+              running += __popc(bits);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              const int64_t row = wrow0 + k * 32 + lane;
+              const bool pr = row < n && Cmp::template apply<T>(v[k], scalar);
+              const uint32_t bits = __ballot_sync(0xffffffffu, pr);
+              if (lane == k) myword = bits;
+              const unsigned pos = running + __popc(bits & lt);
+              if (pr && pos < kSegCap) stage[pos] = v[k];
+              running += __popc(bits);
+            }
+          }
+          B.emit[seg * 32 + lane] = myword;
+          if (lane == 0) B.cnt[seg] = running;
+          if (sub + 1 < kFuSegsPerWarp) issue(tile_r, sub + 1);
+          else if (j + 1 < mine) issue(tile_r + G, 0);
         }
-        const unsigned my_excl = incl - cnt;
-        const int64_t wrow0 = trow0 + (int64_t)seg * kSegRows;
-#pragma unroll 4
-        for (int k = 0; k < 32; ++k) {
-          const uint32_t w = __shfl_sync(0xffffffffu, myword, k);
-          const unsigned off = __shfl_sync(0xffffffffu, my_excl, k);
-          if ((w >> lane) & 1) {
-            const unsigned long long pos = base + off + __popc(w & ((1u << lane) - 1u));
-            if ((long long)pos < capacity) out[pos] = __ldcs(vals + wrow0 + k * 32 + lane);
+        if (lane == 0) {
+          // last warp in: segment offsets, tile total, aggregate published (no barrier on the way)
+          __threadfence_block();
+          if (atomicAdd(&s_arrived[br], 1u) == kFWarps - 1) {
+            __threadfence_block();
+            s_arrived[br] = 0u;
+            uint32_t run = 0;
+#pragma unroll
+            for (int sg = 0; sg < kFuSegs; ++sg) {
+              const uint32_t c = reinterpret_cast<volatile uint32_t*>(B.cnt)[sg];
+              B.excl[sg] = run;
+              run += c;
+            }
+            s_total[br] = run;
+            st_status(status + tile_r, kFlagAgg | (unsigned long long)run);
           }
         }
       }
+    } else if (j >= 1) {
+      const unsigned long long total = s_total[bf];
+      const unsigned long long excl = lookback<false>(status, gstatus, tile_f, total, lane);
+      if (lane == 0) {
+        s_tile_base[bf] = excl;
+        if (tile_f == n_tiles - 1) *out_len = (long long)(excl + total);
+      }
     }
-    __syncthreads();  // shared arrays are rewritten by the next tile
+    __syncthreads();
+    if (!looker && j >= 1) {
+      // ---- phase 2: staged segments -> out[] with coalesced stores --------------------------------
+      FusedBuffers<T>& B = bufs[bf];
+      const int64_t trow0 = tile_f * kFuTileRows;
+      const unsigned long long tbase = s_tile_base[bf];
+#pragma unroll 1
+      for (int sub = 0; sub < kFuSegsPerWarp; ++sub) {
+        const int seg = sub * kFWarps + warp;
+        const unsigned total = B.cnt[seg];
+        if (total == 0) continue;
+        const unsigned long long base = tbase + B.excl[seg];
+        if (total <= kSegCap) {
+          const T* stage = B.stage[seg];
+          for (unsigned i = lane; i < total; i += 32)
+            if ((long long)(base + i) < capacity) out[base + i] = stage[i];
+        } else {
+          // overflow: re-read the segment's selected rows (they are at worst in L2)
+          const uint32_t myword = B.emit[seg * 32 + lane];
+          const unsigned cnt = __popc(myword);
+          unsigned incl = cnt;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+          }
+          const unsigned my_excl = incl - cnt;
+          const int64_t wrow0 = trow0 + (int64_t)seg * kSegRows;
+#pragma unroll 4
+          for (int k = 0; k < 32; ++k) {
+            const uint32_t w = __shfl_sync(0xffffffffu, myword, k);
+            const unsigned off = __shfl_sync(0xffffffffu, my_excl, k);
+            if ((w >> lane) & 1) {
+              const unsigned long long pos = base + off + __popc(w & ((1u << lane) - 1u));
+              if ((long long)pos < capacity) out[pos] = __ldcs(vals + wrow0 + k * 32 + lane);
+            }
+          }
+        }
+      }
+      __syncwarp();  // this warp's staging areas of buffer bf are rewritten two iterations from now
+    }
   }
 }
 
@@ -511,17 +590,16 @@ static ag_status launch_fused_t(const void* vals, const void* scalar_host, int64
   Workspace* ws;
   AG_TRY(get_workspace(st, &ws));
   WorkspaceLock ws_lock(ws);
-  const int64_t n_tiles = (n + kFTileRows - 1) / kFTileRows;
-  AG_TRY(ensure_tile_status(ws, (size_t)n_tiles, st));
-  AG_CUDA_TRY(cudaMemsetAsync(ws->tile_status, 0, (size_t)n_tiles * sizeof(unsigned long long), st));
-  const size_t smem = (kFTileWords + 2 * kSegsPerTile) * sizeof(uint32_t) + (size_t)kSegsPerTile * kSegCap * sizeof(T);
-  static std::atomic<bool> attr_set{false};  // per instantiation
-  if (!attr_set.load()) {
-    AG_CUDA_TRY(cudaFuncSetAttribute((const void*)fused_filter_kernel<T, Cmp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set.store(true);
-  }
+  const int64_t n_tiles = (n + kFuTileRows - 1) / kFuTileRows;
+  const size_t n_status = (size_t)n_tiles + (size_t)((n_tiles + 31) >> 5);
+  AG_TRY(ensure_tile_status(ws, n_status, st));
+  AG_CUDA_TRY(cudaMemsetAsync(ws->tile_status, 0, n_status * sizeof(unsigned long long), st));
+  const size_t smem = 2 * sizeof(FusedBuffers<T>);
+  static std::atomic<unsigned> attr_set{0u};  // per instantiation, one bit per device
+  const void* fn = (const void*)fused_filter_kernel<T, Cmp>;
+  AG_TRY(ensure_dynamic_smem(fn, (int)smem, &attr_set));
   int per_sm = 0;
-  AG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_filter_kernel<T, Cmp>, kFThreads, smem));
+  AG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kFuThreads, smem));
   if (per_sm < 1) per_sm = 1;
   int64_t grid = (int64_t)sm_count() * per_sm;
   if (grid > n_tiles) grid = n_tiles;
@@ -529,10 +607,11 @@ static ag_status launch_fused_t(const void* vals, const void* scalar_host, int64
   T a_scalar = *(const T*)scalar_host;
   T* a_out = (T*)out;
   unsigned long long* a_status = ws->tile_status;
+  unsigned long long* a_gstatus = ws->tile_status + n_tiles;
   long long* a_len = (long long*)d_out_len;
   int64_t a_n = n, a_cap = capacity, a_tiles = n_tiles;
-  void* args[] = {&a_vals, &a_scalar, &a_n, &a_out, &a_cap, &a_status, &a_len, &a_tiles};
-  AG_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)fused_filter_kernel<T, Cmp>, dim3((unsigned)grid), dim3(kFThreads), args, smem, st));
+  void* args[] = {&a_vals, &a_scalar, &a_n, &a_out, &a_cap, &a_status, &a_gstatus, &a_len, &a_tiles};
+  AG_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(kFuThreads), args, smem, st));
   return check_launch("fused_filter_kernel");
 }
 

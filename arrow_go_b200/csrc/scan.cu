@@ -534,6 +534,317 @@ cumsum_kernel(const CumsumParams p) {
   }
 }
 
+// ---- streaming flavour: no validity bitmap, unchecked, 16-byte aligned operands ------------------
+// ncu on the block-synchronous shape (general kernel above, and a first streaming kernel with the same
+// schedule; profiles/r2/scan_stream_history.txt): 67 % of all warp samples sit at the barrier behind the
+// look-back and warp 0 spends 92 % of its time inside it (half waiting for flags of tiles that other
+// blocks are reducing at the same moment, half in ~600 dependent instructions of one warp) — every
+// resident block is in the same phase, so nothing on the SM covers that wait: 7.2 us per 32 KB tile per
+// block against 4.4 us of HBM time.  This kernel takes the look-back off the critical path:
+//   * a block = 8 compute warps + 1 LOOK-BACK warp.  In iteration j the compute warps reduce tile j
+//     and finalize tile j-1 while the look-back warp resolves the prefix of tile j-1 (whose aggregate,
+//     and those of its predecessors in other blocks, were published an iteration ago: the polls hit);
+//     one block barrier per tile joins them;
+//   * tiles arrive by cp.async (16 bytes per thread, no staging registers) straight into the SWIZZLED
+//     position of a 3-stage shared-memory ring (loading / being reduced / waiting for its prefix); a
+//     warp only ever touches its own 4 KB segment of a stage, so the ring needs __syncwarp only;
+//   * the look-back reads a whole 16-byte status entry per load, issues all its polls as one batch
+//     and folds them with interleaved warp scans: ~1 L2 round trip + ~150 instructions;
+//   * interior tiles run a branch-free body (base pointer + immediate offsets).
+// Same tiles, same status words, same fold order as cumsum_kernel: results are bit-identical to it
+// (floats included), so the two kernels can be mixed inside one chunked sequence.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, int bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
+
+// One status entry = K flagged 64-bit words, fetched with ONE volatile load (K = 2: 128 bits; every word carries its own
+// flag, so it does not matter whether the two halves are observed at the same instant).
+template <int K> struct StatusEntry;
+template <> struct StatusEntry<1> {
+  unsigned long long w0;
+  __device__ __forceinline__ void load(const unsigned long long* p) { asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w0) : "l"(p) : "memory"); }
+  __device__ __forceinline__ bool ready() const { return (w0 & kScFlag) != 0; }
+  __device__ __forceinline__ void words(unsigned (&w)[3]) const { w[0] = (unsigned)w0; w[1] = 0u; w[2] = 0u; }
+  __device__ __forceinline__ void set_ready_zero() { w0 = kScFlag; }
+};
+template <> struct StatusEntry<2> {
+  unsigned long long w0, w1;
+  __device__ __forceinline__ void load(const unsigned long long* p) {
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+  }
+  __device__ __forceinline__ bool ready() const { return ((w0 & w1) & kScFlag) != 0; }
+  __device__ __forceinline__ void words(unsigned (&w)[3]) const { w[0] = (unsigned)w0; w[1] = (unsigned)w1; w[2] = 0u; }
+  __device__ __forceinline__ void set_ready_zero() { w0 = kScFlag; w1 = kScFlag; }
+};
+
+// scan_lookback with the same three levels, the same words and the same fold order, built for latency: whole entries per
+// load, every poll of a level in one batch, the four tile-aggregate scans interleaved.  Entries must be 16-byte aligned.
+template <typename P>
+__device__ __forceinline__ typename P::A scan_lookback_lean(const CumsumParams& p, int64_t tile, typename P::A tile_total,
+                                                            typename P::A start, int lane) {
+  using A = typename P::A;
+  constexpr int K = P::K;
+  static_assert(K <= 2, "lean look-back: float / double / wrapped 64-bit accumulators");
+  constexpr int R = kScGroup / 32;
+  const int64_t g = tile / kScGroup;
+  const int qpos = (int)(tile - g * kScGroup);
+  const int64_t sg = g / kScSuper;
+  const int gq = (int)(g - sg * kScSuper);
+  const unsigned long long* a_src = p.agg + (g * kScGroup + lane) * K;
+  const unsigned long long* g_src = p.gagg + (sg * kScSuper + lane) * K;
+  const unsigned long long* s_src = p.sincl + (sg > 0 ? sg - 1 : 0) * K;
+  StatusEntry<K> ea[R], eg, es;
+  bool need_a[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) need_a[r] = r * 32 + lane < qpos;
+  const bool need_g = lane < gq, need_s = sg > 0;
+  // first batch: everything at once (one L2 round trip when all flags are up, the common case)
+#pragma unroll
+  for (int r = 0; r < R; ++r) { if (need_a[r]) ea[r].load(a_src + r * 32 * K); else ea[r].set_ready_zero(); }
+  if (need_g) eg.load(g_src); else eg.set_ready_zero();
+  if (need_s) es.load(s_src); else es.set_ready_zero();
+  while (true) {
+    bool ok = true;
+#pragma unroll
+    for (int r = 0; r < R; ++r) ok = ok && ea[r].ready();
+    if (__all_sync(0xffffffffu, ok)) break;
+#pragma unroll
+    for (int r = 0; r < R; ++r) if (need_a[r] && !ea[r].ready()) ea[r].load(a_src + r * 32 * K);
+  }
+  A x[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    unsigned w[3];
+    ea[r].words(w);
+    x[r] = need_a[r] ? P::from_words(w) : P::zero();
+  }
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const A up = P::shfl_up(x[r], d);
+      if (lane >= d) x[r] = P::add(up, x[r]);
+    }
+  }
+  A part = P::zero();
+#pragma unroll
+  for (int r = 0; r < R; ++r) part = P::add(part, P::shfl(x[r], 31));
+  if (qpos == kScGroup - 1 && lane == 0) {  // group aggregate: needs nothing older than this group
+    unsigned wg[3] = {0u, 0u, 0u};
+    P::to_words(P::add(part, tile_total), wg);
+#pragma unroll
+    for (int k = 0; k < K; ++k) st_word(p.gagg + g * K + k, wg[k]);
+  }
+  while (!__all_sync(0xffffffffu, eg.ready() && es.ready())) {
+    if (need_g && !eg.ready()) eg.load(g_src);
+    if (need_s && !es.ready()) es.load(s_src);
+  }
+  unsigned w[3];
+  eg.words(w);
+  A gpart = need_g ? P::from_words(w) : P::zero();
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const A up = P::shfl_up(gpart, d);
+    if (lane >= d) gpart = P::add(up, gpart);
+  }
+  gpart = P::shfl(gpart, 31);
+  es.words(w);
+  const A base = need_s ? P::from_words(w) : start;
+  const A excl = P::add(P::add(base, gpart), part);
+  if (lane == 0 && qpos == kScGroup - 1 && gq == kScSuper - 1) {
+    unsigned wi[3] = {0u, 0u, 0u};
+    P::to_words(P::add(excl, tile_total), wi);
+#pragma unroll
+    for (int k = 0; k < K; ++k) st_word(p.sincl + sg * K + k, wi[k]);
+  }
+  return excl;
+}
+
+constexpr int kScStreamThreads = kScThreads + 32;  // 8 compute warps + the look-back warp
+constexpr int kScStreamStages = 3;
+constexpr int kScStreamBlocksPerSm = 2;            // 2 x (3 x 32 KB) of the SM's 227 KB
+
+template <typename T>
+__global__ void __launch_bounds__(kScStreamThreads, kScStreamBlocksPerSm)
+cumsum_stream_kernel(const CumsumParams p) {
+  using P = typename PolSel<T, false>::type;
+  using A = typename P::A;
+  constexpr int N = 16 / sizeof(T);
+  constexpr int E = kScRows * N;                  // rows owned by one lane (128 contiguous bytes)
+  extern __shared__ __align__(128) unsigned char s_ring[];  // 3 stages x 32 KB
+  __shared__ A s_warp[2][kScWarps];
+  __shared__ A s_excl[2];
+  __shared__ unsigned s_arrived[2];
+  __shared__ CumsumState s_state;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool looker = warp == kScWarps;
+  if (threadIdx.x < 2) s_arrived[threadIdx.x] = 0u;
+  const unsigned char* __restrict__ in = reinterpret_cast<const unsigned char*>(p.in);
+  unsigned char* __restrict__ out = reinterpret_cast<unsigned char*>(p.out);
+  const int64_t n_bytes = p.n * (int64_t)sizeof(T);
+
+  if (threadIdx.x == 0) s_state = *p.state;
+  __syncthreads();
+  const A start = P::from_state(s_state);
+  if (!p.skip_nulls && s_state.encountered_null != 0) {
+    // an earlier chunk of the sequence met a null: every slot of this call is null (value 0) and the
+    // carried state stays as it is (cumsum_kernel's limit = 0 case)
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (int64_t b = ((int64_t)blockIdx.x * kScStreamThreads + threadIdx.x) * 16; b < n_bytes; b += (int64_t)gridDim.x * kScStreamThreads * 16) {
+      if (b + 16 <= n_bytes) __stcs(reinterpret_cast<uint4*>(out + b), z);
+      else for (int64_t j = b; j < n_bytes; ++j) out[j] = 0;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { CumsumState ns = s_state; P::to_state(start, &ns); *p.state = ns; }
+    return;
+  }
+
+  // byte offsets of this lane inside a 4 KB warp segment
+  //   striped (coalesced) vector k:  logical (k*32 + lane) * 16, parked at its owner's row, chunk ^ (owner & 7)
+  //   blocked chunk c of row `lane`: lane*128 + ((c ^ (lane & 7)) << 4)
+  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(s_ring);
+  const uint32_t seg_off = (uint32_t)(warp & (kScWarps - 1)) * 4096u;
+  const uint32_t str_even = (uint32_t)(((lane & ~7) | ((lane & 7) ^ (lane >> 3))) << 4);  // k even; k odd: ^ 64; + k*512
+  const uint32_t blk_row = (uint32_t)lane * 128u;
+  const uint32_t blk_x = (uint32_t)(lane & 7) << 4;
+
+  auto prefetch = [&](int64_t tile, int stage) {
+    const uint32_t dst0 = ring + (uint32_t)stage * kScTileBytes + seg_off;
+    const int64_t g0 = tile * kScTileBytes + seg_off + (int64_t)lane * 16;
+    if (g0 - (int64_t)lane * 16 + 4096 <= n_bytes) {
+#pragma unroll
+      for (int k = 0; k < kScRows; ++k) cp_async16(dst0 + (str_even ^ ((k & 1) << 6)) + k * 512, in + g0 + k * 512);
+    } else {  // the segment crosses the end of the input: zero-fill what is not there
+#pragma unroll
+      for (int k = 0; k < kScRows; ++k) {
+        const int64_t g = g0 + k * 512;
+        const int64_t room = n_bytes - g;
+        const int bytes = room >= 16 ? 16 : (room > 0 ? (int)room : 0);
+        cp_async16_zfill(dst0 + (str_even ^ ((k & 1) << 6)) + k * 512, bytes > 0 ? in + g : in, bytes);
+      }
+    }
+  };
+
+  const int64_t G = gridDim.x;
+  const int64_t mine = ((int64_t)blockIdx.x < p.n_tiles) ? (p.n_tiles - blockIdx.x + G - 1) / G : 0;  // tiles of this block
+  if (!looker) { if (mine > 0) prefetch(blockIdx.x, 0); cp_async_commit(); }
+  A lane_excl_cur = P::zero(), warp_excl_cur = P::zero();
+  int st_r = 0, st_f = kScStreamStages - 1;   // stage of the tile being reduced (j % 3) / finalized ((j-1) % 3)
+  // iteration j: reduce tile j (j < mine), look-back + finalize tile j-1 (j >= 1)
+  for (int64_t j = 0; j <= mine; ++j) {
+    const int64_t tile_r = blockIdx.x + j * G, tile_f = tile_r - G;
+    const int br = (int)(j & 1), bf = br ^ 1;
+    A lane_excl_next = P::zero();
+    if (!looker) {
+      const int st_n = st_r + 1 == kScStreamStages ? 0 : st_r + 1;
+      if (j + 1 < mine) prefetch(tile_r + G, st_n);  // that stage held tile j-2: finalized, by this warp, an iteration ago
+      cp_async_commit();
+      if (j < mine) {
+        cp_async_wait<1>();
+        __syncwarp();
+        const unsigned char* seg = s_ring + st_r * kScTileBytes + seg_off;
+        uint4 raw[kScRows];
+#pragma unroll
+        for (int c = 0; c < kScRows; ++c) raw[c] = *reinterpret_cast<const uint4*>(seg + blk_row + (((uint32_t)c << 4) ^ blk_x));
+        const T* o = reinterpret_cast<const T*>(raw);
+        A tot = P::zero();
+#pragma unroll
+        for (int i = 0; i < E; ++i) tot = P::add_elem(tot, o[i]);
+        A incl = tot;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const A up = P::shfl_up(incl, d);
+          if (lane >= d) incl = P::add(up, incl);
+        }
+        lane_excl_next = P::shfl_up(incl, 1);
+        if (lane == 0) lane_excl_next = P::zero();
+        if (lane == 31) {
+          // the LAST warp to deliver its total publishes the tile aggregate: no barrier between a tile's reduction
+          // and the moment other blocks can see it (their look-backs wait on exactly this word)
+          s_warp[br][warp] = incl;
+          __threadfence_block();
+          if (atomicAdd(&s_arrived[br], 1u) == kScWarps - 1) {
+            __threadfence_block();
+            s_arrived[br] = 0u;
+            A tile_total = P::zero();
+#pragma unroll
+            for (int wi = 0; wi < kScWarps; ++wi) tile_total = P::add(tile_total, reinterpret_cast<volatile A*>(s_warp[br])[wi]);
+            unsigned w[3] = {0u, 0u, 0u};
+            P::to_words(tile_total, w);
+#pragma unroll
+            for (int k = 0; k < P::K; ++k) st_word(p.agg + tile_r * P::K + k, w[k]);
+          }
+        }
+      }
+    } else if (j >= 1) {
+      A tile_total = P::zero();
+#pragma unroll
+      for (int wi = 0; wi < kScWarps; ++wi) tile_total = P::add(tile_total, s_warp[bf][wi]);
+      const A excl = scan_lookback_lean<P>(p, tile_f, tile_total, start, lane);
+      if (lane == 0) {
+        s_excl[bf] = excl;
+        if (tile_f == p.n_tiles - 1) {
+          CumsumState ns = s_state;
+          P::to_state(P::add(excl, tile_total), &ns);
+          *p.state = ns;
+        }
+      }
+    }
+    __syncthreads();
+    if (!looker) {
+      A warp_excl_next = P::zero();
+      if (j < mine) {
+        A tile_total = P::zero();
+#pragma unroll
+        for (int wi = 0; wi < kScWarps; ++wi) {
+          if (wi == warp) warp_excl_next = tile_total;
+          tile_total = P::add(tile_total, s_warp[br][wi]);
+        }
+      }
+      if (j >= 1) {
+        unsigned char* seg = s_ring + st_f * kScTileBytes + seg_off;
+        uint4 raw[kScRows];
+#pragma unroll
+        for (int c = 0; c < kScRows; ++c) raw[c] = *reinterpret_cast<const uint4*>(seg + blk_row + (((uint32_t)c << 4) ^ blk_x));
+        T* o = reinterpret_cast<T*>(raw);
+        A run = P::add(warp_excl_cur, lane_excl_cur);
+        const T off = P::value(s_excl[bf]);
+#pragma unroll
+        for (int i = 0; i < E; ++i) { run = P::add_elem(run, o[i]); o[i] = P::offset_add(off, P::value(run)); }
+#pragma unroll
+        for (int c = 0; c < kScRows; ++c) *reinterpret_cast<uint4*>(seg + blk_row + (((uint32_t)c << 4) ^ blk_x)) = raw[c];
+        __syncwarp();
+        const int64_t g0 = tile_f * kScTileBytes + seg_off + (int64_t)lane * 16;
+        if (g0 - (int64_t)lane * 16 + 4096 <= n_bytes) {
+#pragma unroll
+          for (int k = 0; k < kScRows; ++k)
+            __stcs(reinterpret_cast<uint4*>(out + g0 + k * 512), *reinterpret_cast<const uint4*>(seg + (str_even ^ ((k & 1) << 6)) + k * 512));
+        } else {
+#pragma unroll
+          for (int k = 0; k < kScRows; ++k) {
+            const int64_t g = g0 + k * 512;
+            const uint4 v = *reinterpret_cast<const uint4*>(seg + (str_even ^ ((k & 1) << 6)) + k * 512);
+            if (g + 16 <= n_bytes) __stcs(reinterpret_cast<uint4*>(out + g), v);
+            else {
+              const unsigned char* vb = reinterpret_cast<const unsigned char*>(&v);
+              for (int q = 0; q < 16; ++q) if (g + q < n_bytes) out[g + q] = vb[q];
+            }
+          }
+        }
+        __syncwarp();  // the segment is refilled (cp.async) two iterations from now, by this warp
+      }
+      lane_excl_cur = lane_excl_next;
+      warp_excl_cur = warp_excl_next;
+    }
+    st_f = st_r;
+    st_r = st_r + 1 == kScStreamStages ? 0 : st_r + 1;
+  }
+}
+
 // first 0 bit of validity[voff, voff+n): one thread per 32 rows, atomicMin into *first_null (pre-set to n)
 __global__ void __launch_bounds__(256)
 first_null_kernel(const uint8_t* __restrict__ valid, int64_t voff, int64_t n, long long* first_null) {
@@ -598,11 +909,13 @@ ag_status launch_cumsum(CumsumParams& p, cudaStream_t st) {
   p.n_tiles = (p.n + kTileRows - 1) / kTileRows;
   const int64_t n_groups = (p.n_tiles + kScGroup - 1) / kScGroup;
   const int64_t n_super = (n_groups + kScSuper - 1) / kScSuper;
-  const size_t words = (size_t)(p.n_tiles + n_groups + n_super) * kStatusK;
+  // every level starts on a 16-byte boundary (the streaming kernel fetches whole entries with 128-bit loads)
+  const size_t agg_words = ((size_t)p.n_tiles * kStatusK + 1) & ~(size_t)1, gagg_words = ((size_t)n_groups * kStatusK + 1) & ~(size_t)1;
+  const size_t words = agg_words + gagg_words + (size_t)n_super * kStatusK;
   AG_TRY(ensure_tile_status(ws, words, st));
   p.agg = ws->tile_status;
-  p.gagg = p.agg + (size_t)p.n_tiles * kStatusK;
-  p.sincl = p.gagg + (size_t)n_groups * kStatusK;
+  p.gagg = p.agg + agg_words;
+  p.sincl = p.gagg + gagg_words;
   AG_CUDA_TRY(cudaMemsetAsync(ws->tile_status, 0, words * sizeof(unsigned long long), st));
   if (p.valid) {
     long long* fn = reinterpret_cast<long long*>(ws->scalars) + 8;  // slot 8 of the per-stream scalars
@@ -625,6 +938,18 @@ ag_status launch_cumsum(CumsumParams& p, cudaStream_t st) {
   void* args[] = {(void*)&p};
   const void* fn;
   const bool chk = p.checked && !IsFp<T>::v;  // floats: the checked adder is the plain one
+  if (vec && !chk && !p.valid) {
+    constexpr int kRing = kScStreamStages * kScTileBytes;
+    static std::atomic<unsigned> attr_set{0u};  // per instantiation, one bit per device
+    AG_TRY(ensure_dynamic_smem((const void*)cumsum_stream_kernel<T>, kRing, &attr_set));
+    int per_sm = 0;
+    AG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cumsum_stream_kernel<T>, kScStreamThreads, kRing));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t cap = (int64_t)sm_count() * per_sm;
+    const int grid = (int)(p.n_tiles < cap ? p.n_tiles : cap);
+    AG_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)cumsum_stream_kernel<T>, dim3(grid), dim3(kScStreamThreads), args, kRing, st));
+    return check_launch("cumsum_stream_kernel");
+  }
   if (chk) {
     if (vec) fn = p.valid ? (const void*)cumsum_kernel<T, true, true, !IsFp<T>::v> : (const void*)cumsum_kernel<T, true, false, !IsFp<T>::v>;
     else fn = p.valid ? (const void*)cumsum_kernel<T, false, true, !IsFp<T>::v> : (const void*)cumsum_kernel<T, false, false, !IsFp<T>::v>;

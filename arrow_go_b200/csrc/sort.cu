@@ -352,11 +352,8 @@ template <typename T, typename K>
 static ag_status sort_indices_t(const SortSource& src, unsigned long long* d_out, int64_t* nulls_out, int64_t* nans_out, cudaStream_t st) {
   constexpr int ND = (int)sizeof(K);
   constexpr size_t kScatterSmem = (sizeof(K) + 4) * (size_t)kSoTile + (size_t)kSoWarps * 256 * 4;
-  static std::atomic<bool> attr_set{false};   // per K
-  if (!attr_set.load(std::memory_order_acquire)) {
-    AG_CUDA_TRY(cudaFuncSetAttribute(sort_digit_scatter_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScatterSmem));
-    attr_set.store(true, std::memory_order_release);
-  }
+  static std::atomic<unsigned> attr_set{0u};   // per K, one bit per device
+  AG_TRY(ensure_dynamic_smem((const void*)sort_digit_scatter_kernel<K>, (int)kScatterSmem, &attr_set));
   const int64_t n = src.n;
   const int64_t ntiles = (n + kSoTile - 1) / kSoTile;
   const size_t hist_words = (size_t)ND * 256 + 3;

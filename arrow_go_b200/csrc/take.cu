@@ -214,7 +214,6 @@ constexpr int kWinTile = 8192;        // rows per tile: positions fit 13 bits, o
 constexpr int kWinMaxBuckets = 1022;  // + the no-gather bucket + the end slot = 1024 shared-memory counters
 constexpr int kWinAThreads = 512;
 constexpr int kWinBThreads = 256;
-constexpr int kWinCThreads = 1024;
 
 struct TakeWindowPlan {
   int shift;        // log2(rows per window)
@@ -525,8 +524,8 @@ take_window_gather_kernel(const TakeParams p, const TakeWindowPlan w, const uint
 
 // Pass C.  out[row] = gathered[perm[row]] inside each tile, in place (the whole tile sits in shared memory between the
 // read and the write).  Rows of the no-gather bucket (position >= its start) get value 0 and validity 0.
-template <typename V>
-__global__ void __launch_bounds__(kWinCThreads, 2)
+template <typename V, int kWinCThreads, int kPerSm>
+__global__ void __launch_bounds__(kWinCThreads, kPerSm)
 take_unpermute_kernel(const TakeParams p, const TakeWindowPlan w, const uint16_t* __restrict__ perm, const uint16_t* __restrict__ off) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   V* s_vals = reinterpret_cast<V*>(s_raw);
@@ -635,14 +634,17 @@ static ag_status launch_window_gather(const TakeParams& p, const TakeWindowPlan&
 
 template <typename V>
 static ag_status launch_unpermute(const TakeParams& p, const TakeWindowPlan& w, const uint16_t* perm, const uint16_t* off, cudaStream_t st) {
-  static std::atomic<bool> attr_set{false};
+  static std::atomic<unsigned> attr_set{0u}, attr_set3{0u};  // one bit per device
   const int smem = kWinTile * (int)sizeof(V);
-  if (!attr_set.load(std::memory_order_acquire)) {
-    AG_CUDA_TRY(cudaFuncSetAttribute(take_unpermute_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set.store(true, std::memory_order_release);
+  if (lab_knob(0) == 1) {  // experiment: 3 x 512 threads per SM instead of 2 x 1024
+    AG_TRY(ensure_dynamic_smem((const void*)take_unpermute_kernel<V, 512, 3>, smem, &attr_set3));
+    const int64_t cap = (int64_t)sm_count() * 3;
+    take_unpermute_kernel<V, 512, 3><<<(int)(w.ntiles < cap ? w.ntiles : cap), 512, smem, st>>>(p, w, perm, off);
+    return check_launch("take_unpermute_kernel");
   }
+  AG_TRY(ensure_dynamic_smem((const void*)take_unpermute_kernel<V, 1024, 2>, smem, &attr_set));
   const int64_t cap = (int64_t)sm_count() * 2;
-  take_unpermute_kernel<V><<<(int)(w.ntiles < cap ? w.ntiles : cap), kWinCThreads, smem, st>>>(p, w, perm, off);
+  take_unpermute_kernel<V, 1024, 2><<<(int)(w.ntiles < cap ? w.ntiles : cap), 1024, smem, st>>>(p, w, perm, off);
   return check_launch("take_unpermute_kernel");
 }
 

@@ -273,3 +273,22 @@ def test_gpu_general_floats_bounded_and_deterministic(ag, cpu):
     ref_err = np.abs(ref_out.astype(np.longdouble) - exact)
     assert (gpu_err <= 64 * eps * scale).all()          # log-depth tree: far inside the n*eps bound
     assert gpu_err.max() <= max(ref_err.max(), eps) * 4  # and no worse than the sequential loop in practice
+
+
+@gpu
+def test_gpu_streaming_and_general_kernels_share_one_sequence(ag, cpu):
+    """Chunks without a bitmap (16-byte aligned: the streaming kernel) and chunks with one (the general
+    kernel) alternate inside one sequence; once a null was met (no skip) a later bitmap-free chunk is
+    all null and leaves the carried value alone."""
+    rng = np.random.default_rng(78)
+    for t in (N.INT64, N.INT16, N.FLOAT64, N.FLOAT32):
+        cuts = [0, 4096 * 16, 4096 * 16 + 48_000, 300_000 + 16, 300_000 + 16 + 70_000 + 32, 500_000]
+        n = cuts[-1]
+        x = rng.integers(-3, 4, n).astype(NP_OF[t])
+        for skip in (False, True):
+            valids = [None, None, rng.random(cuts[3] - cuts[2]) > 0.001, None, None]
+            valids[2][:100] = True
+            chunks = [x[a:b] for a, b in zip(cuts, cuts[1:])]
+            wst, wout, wv, wn, _ = oracle_chunks(cpu, t, chunks, valids, skip, False, 3)
+            st, out, v, nulls, _ = gpu_chunks(ag, t, chunks, valids, skip, False, 3)
+            assert st == 0 and np.array_equal(v, wv) and out.tobytes() == wout.tobytes() and nulls == wn, (TYPE_NAME[t], skip)
