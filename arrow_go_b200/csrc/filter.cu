@@ -492,11 +492,33 @@ fused_filter_kernel(const T* __restrict__ vals, T scalar, int64_t n, T* __restri
   FusedBuffers<T>* bufs = reinterpret_cast<FusedBuffers<T>*>(smem_raw);   // [2]
   __shared__ unsigned long long s_tile_base[2];
   __shared__ uint32_t s_total[2];
-  __shared__ unsigned s_arrived[2];
+  __shared__ unsigned s_arrived[2], s_ready[2], s_done[2];   // sequence-numbered: tile j of this block <-> j + 1
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool looker = warp == kFWarps;
-  if (threadIdx.x < 2) s_arrived[threadIdx.x] = 0u;
+  if (threadIdx.x < 2) { s_arrived[threadIdx.x] = 0u; s_ready[threadIdx.x] = 0u; s_done[threadIdx.x] = 0u; }
   __syncthreads();
+  const int64_t G = gridDim.x;
+  const int64_t mine = ((int64_t)blockIdx.x < n_tiles) ? (n_tiles - blockIdx.x + G - 1) / G : 0;
+  // No block barrier from here on: compute warps and the look-back warp meet through s_ready (a tile's total is in)
+  // and s_done (its base is out), so a warp that is ahead is never held back by one that is behind.
+  if (looker) {
+    for (int64_t j = 0; j < mine; ++j) {
+      const int64_t tile = blockIdx.x + j * G;
+      const int b = (int)(j & 1);
+      if (lane == 0) { while (*reinterpret_cast<volatile unsigned*>(&s_ready[b]) != (unsigned)(j + 1)) {} }
+      __syncwarp();
+      __threadfence_block();
+      const unsigned long long total = *reinterpret_cast<volatile uint32_t*>(&s_total[b]);
+      const unsigned long long excl = lookback<false>(status, gstatus, tile, total, lane);
+      if (lane == 0) {
+        s_tile_base[b] = excl;
+        if (tile == n_tiles - 1) *out_len = (long long)(excl + total);
+        __threadfence_block();
+        *reinterpret_cast<volatile unsigned*>(&s_done[b]) = (unsigned)(j + 1);
+      }
+    }
+    return;
+  }
 
   T v[32];
   auto issue = [&](int64_t t, int sub) {
@@ -512,14 +534,12 @@ fused_filter_kernel(const T* __restrict__ vals, T scalar, int64_t n, T* __restri
       }
     }
   };
-  const int64_t G = gridDim.x;
-  const int64_t mine = ((int64_t)blockIdx.x < n_tiles) ? (n_tiles - blockIdx.x + G - 1) / G : 0;
-  if (!looker && mine > 0) issue(blockIdx.x, 0);
-  // iteration j: phase 1 of tile j (j < mine); look-back + phase 2 of tile j-1 (j >= 1)
+  if (mine > 0) issue(blockIdx.x, 0);
+  // iteration j: phase 1 of tile j (j < mine); phase 2 of tile j-1 (j >= 1)
   for (int64_t j = 0; j <= mine; ++j) {
     const int64_t tile_r = blockIdx.x + j * G, tile_f = tile_r - G;
     const int br = (int)(j & 1), bf = br ^ 1;
-    if (!looker) {
+    {
       if (j < mine) {
         FusedBuffers<T>& B = bufs[br];
         const int64_t trow0 = tile_r * kFuTileRows;
@@ -577,29 +597,26 @@ fused_filter_kernel(const T* __restrict__ vals, T scalar, int64_t n, T* __restri
             }
             s_total[br] = run;
             st_status(status + tile_r, kFlagAgg | (unsigned long long)run);
+            __threadfence_block();
+            *reinterpret_cast<volatile unsigned*>(&s_ready[br]) = (unsigned)(j + 1);
           }
         }
       }
-    } else if (j >= 1) {
-      const unsigned long long total = s_total[bf];
-      const unsigned long long excl = lookback<false>(status, gstatus, tile_f, total, lane);
-      if (lane == 0) {
-        s_tile_base[bf] = excl;
-        if (tile_f == n_tiles - 1) *out_len = (long long)(excl + total);
-      }
     }
-    __syncthreads();
-    if (!looker && j >= 1) {
+    if (j >= 1) {
       // ---- phase 2: staged segments -> out[] with coalesced stores --------------------------------
+      if (lane == 0) { while (*reinterpret_cast<volatile unsigned*>(&s_done[bf]) != (unsigned)j) {} }
+      __syncwarp();
+      __threadfence_block();
       FusedBuffers<T>& B = bufs[bf];
       const int64_t trow0 = tile_f * kFuTileRows;
-      const unsigned long long tbase = s_tile_base[bf];
+      const unsigned long long tbase = *reinterpret_cast<volatile unsigned long long*>(&s_tile_base[bf]);
 #pragma unroll 1
       for (int sub = 0; sub < kFuSegsPerWarp; ++sub) {
         const int seg = sub * kFWarps + warp;
         const unsigned total = B.cnt[seg];
         if (total == 0) continue;
-        const unsigned long long base = tbase + B.excl[seg];
+        const unsigned long long base = tbase + reinterpret_cast<volatile uint32_t*>(B.excl)[seg];
         if (total <= kSegCap) {
           const T* stage = B.stage[seg];
           for (unsigned i = lane; i < total; i += 32)
