@@ -117,7 +117,6 @@ inline bool type_is_float(int type) { return type == AG_TYPE_FLOAT32 || type == 
 inline int64_t bytes_for_bits(int64_t nbits) { return (nbits + 7) >> 3; }
 
 int blocks_per_sm(const void* kernel, int threads);
-int lab_knob(int key);   // experiment switches (ag_lab_set); 0 = shipped behaviour
 // Opt a kernel into `bytes` of dynamic shared memory on the calling thread's device, once per device
 // (`done` = the caller's per-instantiation bit set; the attribute is per function per context).
 inline ag_status ensure_dynamic_smem(const void* kernel, int bytes, std::atomic<unsigned>* done) {

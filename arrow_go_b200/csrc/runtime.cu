@@ -138,8 +138,7 @@ int sm_count() {
   return (d >= 0 && g_dev[d].sms > 0) ? g_dev[d].sms : 148;
 }
 int current_device() { return current_device_index(); }
-static std::atomic<int> g_lab[8];
-int lab_knob(int key) { return (key >= 0 && key < 8) ? g_lab[key].load(std::memory_order_relaxed) : 0; }
+
 int device_count() { return g_device_count; }
 
 // NULL -> the current device's default stream.  A stream created by this library runs on ITS device: the calling
@@ -583,6 +582,3 @@ ag_status ag_flush_l2(ag_stream_t s) {
 }
 
 }  // extern "C"
-
-// Experiment switches for scripts/lab (not part of the ABI in include/arrowgpu.h; every knob defaults to the shipped path).
-extern "C" void ag_lab_set(int key, int value) { if (key >= 0 && key < 8) ag::g_lab[key].store(value); }

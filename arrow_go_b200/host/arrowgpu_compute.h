@@ -381,4 +381,41 @@ Status SumUint64(const ArrayData& a, uint64_t* out);   // Uint64Funcs.Sum
 Status SumFloat64ReferenceOrder(const ArrayData& a, double* out);
 }  // namespace math
 
+// ======================================================================================
+// ipc: Arrow IPC file -> device-resident record batches (arrow/ipc/file_reader.go), and the
+// ArrowDeviceArrayStream hand-off of whole batches (arrow/cdata/abi.h:170-200)
+// ======================================================================================
+namespace ipc {
+struct Field { std::string name; Type type = Type::NA; bool nullable = false; };   // arrow.Field of a numeric / boolean column
+// Where a column's buffers sit inside its record batch body (offsets relative to the body; -1 = no buffer).
+struct ColumnLayout { int64_t length, null_count, validity_offset, validity_length, data_offset, data_length; };
+struct RecordBatch { int64_t num_rows = 0; std::vector<std::shared_ptr<ArrayData>> columns; };
+
+class FileReader {
+ public:
+  ~FileReader();
+  // NewMappedFileReader (file_reader.go:231-250): `data` (a memory map or a pinned slab) must outlive the reader.
+  static Status Open(const uint8_t* data, int64_t size, std::unique_ptr<FileReader>* out);
+  const std::vector<Field>& schema() const;   // FileReader.Schema :383
+  int NumRecords() const;                     // :394
+  int version() const;                        // MetadataVersion :398
+  // Metadata of record batch i only — no device work: the checks of validateFileBlock :68-99,
+  // validateFileBlockMetadata (metadata.go:78-109) and newRecordBatch's buffer walk :523-575, 732-780.
+  Status Layout(int i, int64_t* num_rows, int64_t* body_offset, int64_t* body_length, std::vector<ColumnLayout>* cols) const;
+  // RecordBatchAt :451-480.  The batch body crosses the link ONCE (one H2D copy); columns are views into it.
+  Status RecordBatchAt(int i, RecordBatch* out) const;
+ private:
+  FileReader();
+  struct Impl;
+  Impl* impl_;
+};
+
+// Producer: every get_next reads the next record batch of `reader` (one H2D copy) and hands it over as a struct-typed
+// ArrowDeviceArray {ARROW_DEVICE_CUDA, current device} whose children are the columns.  The stream owns the reader.
+Status ExportDeviceStream(std::shared_ptr<FileReader> reader, struct ArrowDeviceArrayStream* out);
+// Consumer: drains a device stream (ours or another producer's) into record batches; columns keep the producer's
+// arrays alive until the last reference goes (release is called then).  Calls stream->release at the end.
+Status ImportDeviceStream(struct ArrowDeviceArrayStream* stream, std::vector<Field>* schema, std::vector<RecordBatch>* out);
+}  // namespace ipc
+
 }  // namespace arrowgpu

@@ -224,4 +224,64 @@ int agx_dispatch(const char* name, const int* types, int n) {
   return AG_OK;
 }
 
+// ---- ipc: file reader + device streams -------------------------------------------------------------------------
+typedef struct agx_ipc_reader { std::shared_ptr<ipc::FileReader> r; } agx_ipc_reader;
+
+int agx_ipc_open(const uint8_t* data, int64_t size, agx_ipc_reader** out) {
+  std::unique_ptr<ipc::FileReader> r;
+  AGX_TRY(ipc::FileReader::Open(data, size, &r));
+  *out = new agx_ipc_reader{std::shared_ptr<ipc::FileReader>(std::move(r))};
+  return AG_OK;
+}
+void agx_ipc_close(agx_ipc_reader* h) { delete h; }
+int agx_ipc_num_fields(agx_ipc_reader* h) { return (int)h->r->schema().size(); }
+int agx_ipc_num_records(agx_ipc_reader* h) { return h->r->NumRecords(); }
+int agx_ipc_version(agx_ipc_reader* h) { return h->r->version(); }
+int agx_ipc_field(agx_ipc_reader* h, int i, char* name, int64_t cap, int* type, int* nullable) {
+  if (i < 0 || i >= (int)h->r->schema().size()) return fail(Status::Invalid("ipc: field index out of range"));
+  const ipc::Field& f = h->r->schema()[(size_t)i];
+  if ((int64_t)f.name.size() + 1 > cap) return fail(Status::Invalid("ipc: name buffer too small"));
+  memcpy(name, f.name.c_str(), f.name.size() + 1);
+  *type = (int)f.type;
+  *nullable = f.nullable ? 1 : 0;
+  return AG_OK;
+}
+// cols: 6 int64 per field {length, null_count, validity_offset, validity_length, data_offset, data_length}
+int agx_ipc_layout(agx_ipc_reader* h, int i, int64_t* rows, int64_t* body_offset, int64_t* body_length, int64_t* cols) {
+  std::vector<ipc::ColumnLayout> L;
+  AGX_TRY(h->r->Layout(i, rows, body_offset, body_length, &L));
+  for (size_t c = 0; c < L.size(); ++c) {
+    int64_t* o = cols + 6 * c;
+    o[0] = L[c].length; o[1] = L[c].null_count; o[2] = L[c].validity_offset; o[3] = L[c].validity_length; o[4] = L[c].data_offset; o[5] = L[c].data_length;
+  }
+  return AG_OK;
+}
+int agx_ipc_read_batch(agx_ipc_reader* h, int i, int64_t* rows, agx_datum** cols) {
+  ipc::RecordBatch rb;
+  AGX_TRY(h->r->RecordBatchAt(i, &rb));
+  *rows = rb.num_rows;
+  for (size_t c = 0; c < rb.columns.size(); ++c) cols[c] = new agx_datum{Datum(rb.columns[c])};
+  return AG_OK;
+}
+int agx_ipc_export_stream(agx_ipc_reader* h, struct ArrowDeviceArrayStream* out) {
+  AGX_TRY(ipc::ExportDeviceStream(h->r, out));
+  return AG_OK;
+}
+// Drains `stream`; batches come back column-major: cols[b * nfields + c].  *nbatches in: capacity, out: count.
+int agx_ipc_import_stream(struct ArrowDeviceArrayStream* stream, int* nfields, int* types, int max_fields,
+                          int* nbatches, int64_t* rows, agx_datum** cols) {
+  std::vector<ipc::Field> schema;
+  std::vector<ipc::RecordBatch> batches;
+  AGX_TRY(ipc::ImportDeviceStream(stream, &schema, &batches));
+  if ((int)schema.size() > max_fields || (int)batches.size() > *nbatches) return fail(Status::Invalid("ipc: output arrays too small"));
+  *nfields = (int)schema.size();
+  for (size_t c = 0; c < schema.size(); ++c) types[c] = (int)schema[c].type;
+  *nbatches = (int)batches.size();
+  for (size_t b = 0; b < batches.size(); ++b) {
+    rows[b] = batches[b].num_rows;
+    for (size_t c = 0; c < schema.size(); ++c) cols[b * schema.size() + c] = new agx_datum{Datum(batches[b].columns[c])};
+  }
+  return AG_OK;
+}
+
 }  // extern "C"

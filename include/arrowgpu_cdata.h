@@ -78,6 +78,23 @@ struct ArrowDeviceArray {
 
 #endif /* ARROW_C_DEVICE_DATA_INTERFACE */
 
+#ifndef ARROW_C_DEVICE_STREAM_INTERFACE
+#define ARROW_C_DEVICE_STREAM_INTERFACE
+
+/* A stream of ArrowDeviceArrays on ONE device (arrow/cdata/abi.h:170-200 of the reference; the published Arrow C
+ * Device Stream ABI).  Callbacks return 0 or an errno-compatible code; get_next marks the end of the stream with a
+ * released array (out->array.release == NULL).  Every array must be released independently of the stream. */
+struct ArrowDeviceArrayStream {
+  ArrowDeviceType device_type;
+  int (*get_schema)(struct ArrowDeviceArrayStream* self, struct ArrowSchema* out);
+  int (*get_next)(struct ArrowDeviceArrayStream* self, struct ArrowDeviceArray* out);
+  const char* (*get_last_error)(struct ArrowDeviceArrayStream* self);
+  void (*release)(struct ArrowDeviceArrayStream* self);
+  void* private_data;
+};
+
+#endif /* ARROW_C_DEVICE_STREAM_INTERFACE */
+
 /* What an array looks like to the *_dev entry points of arrowgpu.h. */
 typedef struct ag_array_view {
   int type;             /* AG_TYPE_* (0 when no schema / type was given) */

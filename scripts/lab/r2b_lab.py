@@ -13,7 +13,7 @@ from arrow_go_b200.device import DeviceBuffer, Event  # noqa: E402
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000_000
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 N.call("ag_init", 0)
-lab = N.raw().ag_lab_set
+lab = getattr(N.raw(), "ag_lab_set", lambda k, v: None)   # experiment switches existed only in lab builds
 a, b, o = DeviceBuffer(rows * 8), DeviceBuffer(rows * 8), DeviceBuffer(rows * 8)
 N.call("ag_generate_dev", 1, 0x94378165, -1000, 1000, a.ptr, rows, None)
 N.call("ag_generate_dev", 1, 0x0FF1CE, 0, 99, b.ptr, rows, None)
