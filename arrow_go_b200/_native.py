@@ -22,6 +22,7 @@ NULL, BOOL, UINT8, INT8, UINT16, INT16, UINT32, INT32, UINT64, INT64, FLOAT16, F
 # ArithmeticOp
 OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_ABS, OP_NEGATE = 0, 1, 2, 3, 4, 5
 OP_SIGN, OP_ADD_CHECKED, OP_SUB_CHECKED, OP_MUL_CHECKED, OP_DIV_CHECKED, OP_ABS_CHECKED, OP_NEGATE_CHECKED = 20, 21, 22, 23, 24, 25, 26
+OP_BIT_AND, OP_BIT_OR, OP_BIT_XOR, OP_BIT_NOT, OP_SHIFT_LEFT, OP_SHIFT_RIGHT, OP_SHIFT_LEFT_CHECKED, OP_SHIFT_RIGHT_CHECKED = 64, 65, 66, 67, 68, 69, 70, 71
 # CompareOperator
 CMP_EQ, CMP_NE, CMP_GT, CMP_GE, CMP_LT, CMP_LE = range(6)
 SHAPE_AA, SHAPE_AS, SHAPE_SA = range(3)

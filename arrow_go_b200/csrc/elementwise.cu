@@ -42,6 +42,11 @@ struct OpMul {
   }
 };
 // explicit round-to-nearest intrinsics: no FMA contraction, no reassociation
+// bitwiseKernelOp (scalar_arithmetic.go:191-243): the reference runs BitmapAnd/Or/Xor over the value buffers, i.e. the
+// plain bitwise op on every slot; integer types only (the float instantiations are never dispatched).
+struct OpBitAnd { template <typename T> static __device__ __forceinline__ T apply(T a, T b) { if constexpr (std::is_integral<T>::value) return (T)(a & b); else return a; } };
+struct OpBitOr { template <typename T> static __device__ __forceinline__ T apply(T a, T b) { if constexpr (std::is_integral<T>::value) return (T)(a | b); else return a; } };
+struct OpBitXor { template <typename T> static __device__ __forceinline__ T apply(T a, T b) { if constexpr (std::is_integral<T>::value) return (T)(a ^ b); else return a; } };
 template <> __device__ __forceinline__ double OpAdd::apply<double>(double a, double b) { return __dadd_rn(a, b); }
 template <> __device__ __forceinline__ float OpAdd::apply<float>(float a, float b) { return __fadd_rn(a, b); }
 template <> __device__ __forceinline__ double OpSub::apply<double>(double a, double b) { return __dsub_rn(a, b); }
@@ -120,6 +125,14 @@ static ag_status launch_binary_op(int8_t op, int shape, const void* l, const voi
     case AG_OP_ADD: case AG_OP_ADD_CHECKED: return launch_binary_shape<T, OpAdd>(shape, l, r, out, n, st);
     case AG_OP_SUB: case AG_OP_SUB_CHECKED: return launch_binary_shape<T, OpSub>(shape, l, r, out, n, st);
     case AG_OP_MUL: case AG_OP_MUL_CHECKED: return launch_binary_shape<T, OpMul>(shape, l, r, out, n, st);
+    case AG_OP_BIT_AND: case AG_OP_BIT_OR: case AG_OP_BIT_XOR:
+      if constexpr (std::is_integral<T>::value) {
+        if (op == AG_OP_BIT_AND) return launch_binary_shape<T, OpBitAnd>(shape, l, r, out, n, st);
+        if (op == AG_OP_BIT_OR) return launch_binary_shape<T, OpBitOr>(shape, l, r, out, n, st);
+        return launch_binary_shape<T, OpBitXor>(shape, l, r, out, n, st);
+      } else {
+        AG_FAIL(AG_ERR_TYPE, "arith: bitwise ops take integer types");
+      }
     default: AG_FAIL(AG_ERR_NOT_IMPLEMENTED, "arith: binary op %d has no native kernel (the reference has none either)", (int)op);
   }
 }
@@ -346,6 +359,14 @@ static ag_status launch_spans_op(int8_t op, int shape, const SpanDesc* d, int n,
     case AG_OP_ADD: case AG_OP_ADD_CHECKED: return launch_spans_shape<T, OpAdd>(shape, d, n, tiles, sc, shift, st);
     case AG_OP_SUB: case AG_OP_SUB_CHECKED: return launch_spans_shape<T, OpSub>(shape, d, n, tiles, sc, shift, st);
     case AG_OP_MUL: case AG_OP_MUL_CHECKED: return launch_spans_shape<T, OpMul>(shape, d, n, tiles, sc, shift, st);
+    case AG_OP_BIT_AND: case AG_OP_BIT_OR: case AG_OP_BIT_XOR:
+      if constexpr (std::is_integral<T>::value) {
+        if (op == AG_OP_BIT_AND) return launch_spans_shape<T, OpBitAnd>(shape, d, n, tiles, sc, shift, st);
+        if (op == AG_OP_BIT_OR) return launch_spans_shape<T, OpBitOr>(shape, d, n, tiles, sc, shift, st);
+        return launch_spans_shape<T, OpBitXor>(shape, d, n, tiles, sc, shift, st);
+      } else {
+        AG_FAIL(AG_ERR_TYPE, "arith: bitwise ops take integer types");
+      }
     default: AG_FAIL(AG_ERR_NOT_IMPLEMENTED, "arith: binary op %d has no native kernel", (int)op);
   }
 }
@@ -424,6 +445,11 @@ struct UNegChecked {  // identical to UNeg except unsigned -> 0 (base_arithmetic
   template <typename TO, typename T> static __device__ __forceinline__ TO apply(T x) {
     if constexpr (std::is_unsigned<T>::value) return 0;
     else return UNeg::apply<TO, T>(x);
+  }
+};
+struct UBitNot {  // bitwiseNot, scalar_arithmetic.go:257-259 (integer types; floats are refused before the launch)
+  template <typename TO, typename T> static __device__ __forceinline__ TO apply(T x) {
+    if constexpr (std::is_integral<T>::value) return (TO)(T)~x; else return (TO)x;
   }
 };
 struct USign {
@@ -519,6 +545,9 @@ static ag_status launch_unary_same_op(int8_t op, const void* in, void* out, int6
     case AG_OP_NEGATE: return launch_unary_same_t<T, UNeg>(in, out, n, st);
     case AG_OP_NEGATE_CHECKED: return launch_unary_same_t<T, UNegChecked>(in, out, n, st);
     case AG_OP_SIGN: return launch_unary_same_t<T, USign>(in, out, n, st);
+    case AG_OP_BIT_NOT:
+      if constexpr (std::is_integral<T>::value) return launch_unary_same_t<T, UBitNot>(in, out, n, st);
+      else AG_FAIL(AG_ERR_TYPE, "arith: bit_wise_not takes integer types");
     default: AG_FAIL(AG_ERR_NOT_IMPLEMENTED, "arith: unary op %d has no native kernel", (int)op);
   }
 }
@@ -626,6 +655,28 @@ template <typename ST> struct ChkDiv {
       if (a == tmin && b == (ST)-1) return a;
     }
     return (ST)(a / b);
+  }
+};
+
+// shiftKernelSignedImpl / UnsignedImpl (scalar_arithmetic.go:293-379): an amount outside [0, maxShift) leaves lhs as it
+// is and, in the checked flavour, fails the call; maxShift = bits - 1 for SIGNED types, bits for unsigned.
+template <typename ST, bool kLeft, bool kChecked> struct ChkShift {
+  static __device__ __forceinline__ ST apply(ST a, ST b, bool& bad) {
+    using U = typename std::make_unsigned<ST>::type;
+    constexpr int max_shift = (int)sizeof(ST) * 8 - (std::is_signed<ST>::value ? 1 : 0);
+    const bool invalid = (std::is_signed<ST>::value && b < 0) || (unsigned long long)b >= (unsigned long long)max_shift;
+    bad = kChecked && invalid;
+    if (invalid) return a;
+    if (kLeft) return (ST)((U)a << (int)b);
+    return (ST)(a >> (int)b);
+  }
+};
+// floating point Div / DivChecked (base_arithmetic.go:386-397): IEEE quotient; the checked op fails on a zero divisor
+template <typename FT, bool kChecked> struct ChkFDiv {
+  static __device__ __forceinline__ FT apply(FT a, FT b, bool& bad) {
+    bad = kChecked && b == FT(0);
+    if (bad) return FT(0);
+    if constexpr (sizeof(FT) == 8) return __ddiv_rn(a, b); else return __fdiv_rn(a, b);
   }
 };
 
@@ -821,7 +872,22 @@ static ag_status launch_checked_op(int8_t op, int shape, const void* l, const ui
     case AG_OP_SUB_CHECKED: return launch_checked_shape<ST, ChkSub<ST>, true>(shape, l, lvalid, loff, r, rvalid, roff, out, n, d_first_bad, st);
     case AG_OP_MUL_CHECKED: return launch_checked_shape<ST, ChkMul<ST>, false>(shape, l, lvalid, loff, r, rvalid, roff, out, n, d_first_bad, st);
     case AG_OP_DIV: case AG_OP_DIV_CHECKED: return launch_checked_shape<ST, ChkDiv<ST>, true>(shape, l, lvalid, loff, r, rvalid, roff, out, n, d_first_bad, st);
+    case AG_OP_SHIFT_LEFT: return launch_checked_shape<ST, ChkShift<ST, true, false>, true>(shape, l, lvalid, loff, r, rvalid, roff, out, n, d_first_bad, st);
+    case AG_OP_SHIFT_RIGHT: return launch_checked_shape<ST, ChkShift<ST, false, false>, true>(shape, l, lvalid, loff, r, rvalid, roff, out, n, d_first_bad, st);
+    case AG_OP_SHIFT_LEFT_CHECKED: return launch_checked_shape<ST, ChkShift<ST, true, true>, true>(shape, l, lvalid, loff, r, rvalid, roff, out, n, d_first_bad, st);
+    case AG_OP_SHIFT_RIGHT_CHECKED: return launch_checked_shape<ST, ChkShift<ST, false, true>, true>(shape, l, lvalid, loff, r, rvalid, roff, out, n, d_first_bad, st);
     default: AG_FAIL(AG_ERR_NOT_IMPLEMENTED, "arith_checked: op %d is not a checked integer op", (int)op);
+  }
+}
+
+template <typename FT>
+static ag_status launch_checked_fdiv(int8_t op, int shape, const void* l, const uint8_t* lvalid, int64_t loff,
+                                     const void* r, const uint8_t* rvalid, int64_t roff,
+                                     void* out, int64_t n, int64_t* d_first_bad, cudaStream_t st) {
+  switch (op) {
+    case AG_OP_DIV: return launch_checked_shape<FT, ChkFDiv<FT, false>, true>(shape, l, lvalid, loff, r, rvalid, roff, out, n, d_first_bad, st);
+    case AG_OP_DIV_CHECKED: return launch_checked_shape<FT, ChkFDiv<FT, true>, true>(shape, l, lvalid, loff, r, rvalid, roff, out, n, d_first_bad, st);
+    default: AG_FAIL(AG_ERR_NOT_IMPLEMENTED, "arith_checked: op %d on a floating point type (only DIV / DIV_CHECKED have NotNull float kernels)", (int)op);
   }
 }
 
@@ -841,7 +907,9 @@ ag_status arith_checked_dev(int type, int8_t op, int shape, const void* l, const
     case AG_TYPE_UINT16: return launch_checked_op<uint16_t>(op, shape, l, lvalid, loff, r, rvalid, roff, out, n, d_first_bad, st);
     case AG_TYPE_UINT32: return launch_checked_op<uint32_t>(op, shape, l, lvalid, loff, r, rvalid, roff, out, n, d_first_bad, st);
     case AG_TYPE_UINT64: return launch_checked_op<unsigned long long>(op, shape, l, lvalid, loff, r, rvalid, roff, out, n, d_first_bad, st);
-    default: AG_FAIL(AG_ERR_TYPE, "arith_checked: type id %d is not an integer type", type);
+    case AG_TYPE_FLOAT32: return launch_checked_fdiv<float>(op, shape, l, lvalid, loff, r, rvalid, roff, out, n, d_first_bad, st);
+    case AG_TYPE_FLOAT64: return launch_checked_fdiv<double>(op, shape, l, lvalid, loff, r, rvalid, roff, out, n, d_first_bad, st);
+    default: AG_FAIL(AG_ERR_TYPE, "arith_checked: type id %d is not a numeric type", type);
   }
 }
 

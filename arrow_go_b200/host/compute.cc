@@ -1268,6 +1268,57 @@ std::shared_ptr<ScalarFunction> MakeArithBinary(const std::string& name, int8_t 
   return fn;
 }
 
+// divide / divide_unchecked (arithmetic.go:782-785; kernels base_arithmetic.go:154-161,287-294,386-397): every kernel is
+// ScalarBinaryNotNull.  Integers fail on a zero divisor in BOTH flavours; floats only in the checked one.
+std::shared_ptr<ScalarFunction> MakeDivide(const std::string& name, bool checked) {
+  auto fn = std::make_shared<ScalarFunction>(name, 2);
+  fn->promote_numeric = true;
+  for (Type t : kNumericTypes) {
+    exec::ScalarKernel k;
+    k.in_types = {t, t};
+    k.out_type = FirstType;
+    k.exec = ArithCheckedExec(checked ? AG_OP_DIV_CHECKED : AG_OP_DIV);
+    k.can_fail = true;   // the NotNull entry point always takes an error word; the unchecked float op never raises it
+    k.fail_message = "divide by zero";
+    fn->AddKernel(std::move(k));
+  }
+  return fn;
+}
+
+const Type kIntTypes[] = {Type::UINT8, Type::INT8, Type::UINT16, Type::INT16, Type::UINT32, Type::INT32, Type::UINT64, Type::INT64};
+
+// bit_wise_and / or / xor (arithmetic.go:944-961, GetBitwiseBinaryKernels scalar_arithmetic.go:245-255): integer types,
+// every slot; validity by intersection
+std::shared_ptr<ScalarFunction> MakeBitwiseBinary(const std::string& name, int8_t op) {
+  auto fn = std::make_shared<ScalarFunction>(name, 2);
+  fn->promote_numeric = true;
+  for (Type t : kIntTypes) {
+    exec::ScalarKernel k;
+    k.in_types = {t, t};
+    k.out_type = FirstType;
+    k.exec = ArithBinaryExec(op);
+    k.exec_batch = ArithBinaryBatchExec(op);
+    fn->AddKernel(std::move(k));
+  }
+  return fn;
+}
+
+// shift_left / shift_right (+ _unchecked) (arithmetic.go:970-996, GetShiftKernels scalar_arithmetic.go:401-412)
+std::shared_ptr<ScalarFunction> MakeShift(const std::string& name, int8_t op, bool checked) {
+  auto fn = std::make_shared<ScalarFunction>(name, 2);
+  fn->promote_numeric = true;
+  for (Type t : kIntTypes) {
+    exec::ScalarKernel k;
+    k.in_types = {t, t};
+    k.out_type = FirstType;
+    k.exec = ArithCheckedExec(op);
+    k.can_fail = true;   // error word always supplied; only the checked ops raise it
+    k.fail_message = "shift amount must be >= 0 and less than precision of type";
+    fn->AddKernel(std::move(k));
+  }
+  return fn;
+}
+
 std::shared_ptr<ScalarFunction> MakeArithUnary(const std::string& name, int8_t op) {
   auto fn = std::make_shared<ScalarFunction>(name, 1);
   for (Type t : kNumericTypes) {
@@ -1342,6 +1393,26 @@ FunctionRegistry* GetFunctionRegistry() {
     reg->AddFunction(MakeArithUnary("sign", AG_OP_SIGN), false);
     reg->AddFunction(MakeArithUnaryChecked("abs", AG_OP_ABS_CHECKED, false), false);       // arithmetic.go:822-823
     reg->AddFunction(MakeArithUnaryChecked("negate", AG_OP_NEGATE_CHECKED, true), false);  // arithmetic.go:839-846
+    reg->AddFunction(MakeDivide("divide", true), false);                                   // arithmetic.go:784-785
+    reg->AddFunction(MakeDivide("divide_unchecked", false), false);
+    reg->AddFunction(MakeBitwiseBinary("bit_wise_and", AG_OP_BIT_AND), false);             // arithmetic.go:949-951
+    reg->AddFunction(MakeBitwiseBinary("bit_wise_or", AG_OP_BIT_OR), false);
+    reg->AddFunction(MakeBitwiseBinary("bit_wise_xor", AG_OP_BIT_XOR), false);
+    {
+      auto fn = std::make_shared<ScalarFunction>("bit_wise_not", 1);                       // arithmetic.go:965-972
+      for (Type t : kIntTypes) {
+        exec::ScalarKernel k;
+        k.in_types = {t};
+        k.out_type = FirstType;
+        k.exec = ArithUnaryExec(AG_OP_BIT_NOT);
+        fn->AddKernel(std::move(k));
+      }
+      reg->AddFunction(fn, false);
+    }
+    reg->AddFunction(MakeShift("shift_left", AG_OP_SHIFT_LEFT_CHECKED, true), false);      // arithmetic.go:980-983
+    reg->AddFunction(MakeShift("shift_left_unchecked", AG_OP_SHIFT_LEFT, false), false);
+    reg->AddFunction(MakeShift("shift_right", AG_OP_SHIFT_RIGHT_CHECKED, true), false);
+    reg->AddFunction(MakeShift("shift_right_unchecked", AG_OP_SHIFT_RIGHT, false), false);
     // scalar_compare.go:102-153
     reg->AddFunction(MakeCompare("equal", AG_CMP_EQ), false);
     reg->AddFunction(MakeCompare("not_equal", AG_CMP_NE), false);

@@ -82,6 +82,21 @@ typedef int ag_status;
 #define AG_OP_DIV_CHECKED    24
 #define AG_OP_ABS_CHECKED    25
 #define AG_OP_NEGATE_CHECKED 26
+/* Not ArithmeticOp values: the reference keeps these in separate enums (BitwiseOp scalar_arithmetic.go:183-189,
+ * ShiftDir :286-291); one op space here so that they ride the same entry points.
+ *   BIT_AND / BIT_OR / BIT_XOR: ag_arith_binary* on the integer types (every slot, like a3: bitwiseKernelOp :191-243
+ *     runs the bitmap op over the value buffers); BIT_NOT: ag_arith_unary_same (bitwiseNot :257-259).
+ *   SHIFT_*: ag_arith_checked* (ScalarBinaryNotNull slots).  An invalid amount (rhs < 0 or rhs >= bits for unsigned,
+ *     rhs >= bits - 1 for SIGNED types — maxShift of shiftKernelSignedImpl :293-296) leaves lhs unchanged; the
+ *     _CHECKED flavours also fail the call ("shift amount must be >= 0 and less than precision of type"). */
+#define AG_OP_BIT_AND        64
+#define AG_OP_BIT_OR         65
+#define AG_OP_BIT_XOR        66
+#define AG_OP_BIT_NOT        67
+#define AG_OP_SHIFT_LEFT     68
+#define AG_OP_SHIFT_RIGHT    69
+#define AG_OP_SHIFT_LEFT_CHECKED  70
+#define AG_OP_SHIFT_RIGHT_CHECKED 71
 
 /* ---- kernels.CompareOperator (kernels/types.go:62-71) ---------------------------- */
 #define AG_CMP_EQ 0

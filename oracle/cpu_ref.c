@@ -17,7 +17,8 @@
 enum { T_BOOL = 1, T_U8 = 2, T_I8 = 3, T_U16 = 4, T_I16 = 5, T_U32 = 6, T_I32 = 7, T_U64 = 8, T_I64 = 9, T_F32 = 11, T_F64 = 12 };
 /* ArithmeticOp, K/base_arithmetic.go:37-82 */
 enum { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2, OP_DIV = 3, OP_ABS = 4, OP_NEG = 5, OP_SIGN = 20,
-       OP_ADD_C = 21, OP_SUB_C = 22, OP_MUL_C = 23, OP_DIV_C = 24, OP_ABS_C = 25, OP_NEG_C = 26 };
+       OP_ADD_C = 21, OP_SUB_C = 22, OP_MUL_C = 23, OP_DIV_C = 24, OP_ABS_C = 25, OP_NEG_C = 26,
+       OP_BIT_AND = 64, OP_BIT_OR = 65, OP_BIT_XOR = 66, OP_BIT_NOT = 67, OP_SHL = 68, OP_SHR = 69, OP_SHL_C = 70, OP_SHR_C = 71 };
 enum { SH_AA = 0, SH_AS = 1, SH_SA = 2 };
 enum { CMP_EQ = 0, CMP_NE = 1, CMP_GT = 2, CMP_GE = 3, CMP_LT = 4, CMP_LE = 5 };
 
@@ -106,6 +107,10 @@ uint64_t ref_sum_u64(const uint64_t* buf, size_t n) {
     case OP_ADD: case OP_ADD_C: BIN_LOOP(UT, (UT)(a + b)); return REF_OK;               \
     case OP_SUB: case OP_SUB_C: BIN_LOOP(UT, (UT)(a - b)); return REF_OK;               \
     case OP_MUL: case OP_MUL_C: BIN_LOOP(UT, (UT)((uint64_t)a * (uint64_t)b)); return REF_OK; \
+    /* bitwiseKernelOp K/scalar_arithmetic.go:191-243: BitmapAnd/Or/Xor over the value buffers */ \
+    case OP_BIT_AND: BIN_LOOP(UT, (UT)(a & b)); return REF_OK;                          \
+    case OP_BIT_OR: BIN_LOOP(UT, (UT)(a | b)); return REF_OK;                           \
+    case OP_BIT_XOR: BIN_LOOP(UT, (UT)(a ^ b)); return REF_OK;                          \
     default: return REF_ERR_NOT_IMPLEMENTED;                                            \
   }
 #define BIN_FLT(FT)                                                                     \
@@ -148,6 +153,7 @@ void ref_arith_binary_native_abi(int type, int8_t op, const void* l, const void*
     case OP_ABS: case OP_ABS_C: UN_LOOP(ST, ST, (ST)(((UT)x + (UT)(x >> (sizeof(ST) * 8 - 1))) ^ (UT)(x >> (sizeof(ST) * 8 - 1)))); return REF_OK; \
     case OP_NEG: case OP_NEG_C: UN_LOOP(ST, ST, (ST)(0 - (UT)x)); return REF_OK;        \
     case OP_SIGN: UN_LOOP(ST, ST, x > 0 ? 1 : (x ? -1 : 0)); return REF_OK;             \
+    case OP_BIT_NOT: UN_LOOP(ST, ST, (ST)~x); return REF_OK;  /* bitwiseNot K/scalar_arithmetic.go:257-259 */ \
     default: return REF_ERR_NOT_IMPLEMENTED;                                            \
   }
 #define UN_UINT(UT)                                                                     \
@@ -156,6 +162,7 @@ void ref_arith_binary_native_abi(int type, int8_t op, const void* l, const void*
     case OP_NEG: UN_LOOP(UT, UT, (UT)(~x + 1)); return REF_OK;                          \
     case OP_NEG_C: UN_LOOP(UT, UT, 0); return REF_OK;                                   \
     case OP_SIGN: UN_LOOP(UT, UT, x > 0 ? 1 : 0); return REF_OK;                        \
+    case OP_BIT_NOT: UN_LOOP(UT, UT, (UT)~x); return REF_OK;                            \
     default: return REF_ERR_NOT_IMPLEMENTED;                                            \
   }
 
@@ -294,8 +301,32 @@ int ref_arith_unary_diff(int itype, int otype, int op, const void* in, void* out
     }                                                                                   \
   } while (0)
 
+/* shiftKernelSignedImpl / UnsignedImpl K/scalar_arithmetic.go:293-379 under ScalarBinaryNotNull: an amount outside
+ * [0, maxShift) leaves lhs as it is (and fails the call in the checked flavour); maxShift = bits - 1 for SIGNED types
+ * (so int32 << 31 is refused), bits for unsigned.  Left shifts go through the unsigned type, right shifts are
+ * arithmetic for signed operands. */
+#define CHK_SHIFT(ST, UT, IS_SIGNED, LEFT, CHECKED)                                     \
+  do {                                                                                  \
+    const ST* L = (const ST*)l; const ST* R = (const ST*)r; ST* O = (ST*)out;           \
+    const int max_shift = (int)sizeof(ST) * 8 - ((IS_SIGNED) ? 1 : 0);                  \
+    for (int64_t i = 0; i < n; ++i) {                                                   \
+      if (!CHK_SLOT_VALID(i)) { O[i] = 0; continue; }                                   \
+      const ST a = (shape == SH_SA) ? L[0] : L[i];                                      \
+      const ST b = (shape == SH_AS) ? R[0] : R[i];                                      \
+      if (((IS_SIGNED) && b < 0) || (uint64_t)b >= (uint64_t)max_shift) {               \
+        if ((CHECKED) && i < bad) bad = i;                                              \
+        O[i] = a;                                                                       \
+      } else if (LEFT) O[i] = (ST)((UT)a << (int)b);                                    \
+      else O[i] = (ST)(a >> (int)b);                                                    \
+    }                                                                                   \
+  } while (0)
+
 #define CHK_TYPE(ST, UT, IS_SIGNED, TMIN, TMAX)                                         \
   switch (op) {                                                                         \
+    case OP_SHL: CHK_SHIFT(ST, UT, IS_SIGNED, 1, 0); break;                             \
+    case OP_SHR: CHK_SHIFT(ST, UT, IS_SIGNED, 0, 0); break;                             \
+    case OP_SHL_C: CHK_SHIFT(ST, UT, IS_SIGNED, 1, 1); break;                           \
+    case OP_SHR_C: CHK_SHIFT(ST, UT, IS_SIGNED, 0, 1); break;                           \
     case OP_ADD_C: CHK_ADDSUB(ST, IS_SIGNED, (ST)(a & b) | ((ST)(a | b) & (ST)~o), (UT)a + (UT)b); break;      \
     case OP_SUB_C: CHK_ADDSUB(ST, IS_SIGNED, (ST)((ST)~a & b) | ((ST)~(ST)(a ^ b) & o), (UT)a - (UT)b); break; \
     case OP_MUL_C: CHK_MUL(ST, UT, TMIN, TMAX); break;                                  \
@@ -303,6 +334,19 @@ int ref_arith_unary_diff(int itype, int otype, int op, const void* in, void* out
     default: return REF_ERR_NOT_IMPLEMENTED;                                            \
   }                                                                                     \
   break;
+
+#define CHK_FDIV(FT)                                                                    \
+  if (op != OP_DIV && op != OP_DIV_C) return REF_ERR_NOT_IMPLEMENTED;                   \
+  do {                                                                                  \
+    const FT* L = (const FT*)l; const FT* R = (const FT*)r; FT* O = (FT*)out;           \
+    for (int64_t i = 0; i < n; ++i) {                                                   \
+      if (!CHK_SLOT_VALID(i)) { O[i] = 0; continue; }                                   \
+      const FT a = (shape == SH_SA) ? L[0] : L[i];                                      \
+      const FT b = (shape == SH_AS) ? R[0] : R[i];                                      \
+      if (op == OP_DIV_C && b == 0) { if (i < bad) bad = i; O[i] = 0; }                 \
+      else O[i] = a / b;                                                                \
+    }                                                                                   \
+  } while (0);
 
 int ref_arith_checked(int type, int op, int shape,
                       const void* l, const uint8_t* lvalid, int64_t loff,
@@ -321,6 +365,10 @@ int ref_arith_checked(int type, int op, int shape,
     case T_U16: CHK_TYPE(uint16_t, uint16_t, 0, 0, UINT16_MAX)
     case T_U32: CHK_TYPE(uint32_t, uint32_t, 0, 0, UINT32_MAX)
     case T_U64: CHK_TYPE(uint64_t, uint64_t, 0, 0, UINT64_MAX)
+    /* floating point Div / DivChecked, K/base_arithmetic.go:386-397 under ScalarBinaryNotNull: the unchecked op is
+     * the IEEE quotient (x/0 = +-Inf or NaN), the checked one fails on a zero divisor (slot value 0) */
+    case T_F32: CHK_FDIV(float) break;
+    case T_F64: CHK_FDIV(double) break;
     default: return REF_ERR_TYPE;
   }
   if (first_bad) *first_bad = bad;
