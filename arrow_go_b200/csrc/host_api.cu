@@ -290,7 +290,9 @@ ag_status ag_arith_checked(int type, int8_t op, int shape, const void* l, const 
   AG_TRY(ensure_init());
   if (first_bad) *first_bad = AG_NO_ERROR_POS;
   const int w = type_width(type);
-  if (w == 0 || type_is_float(type)) AG_FAIL(AG_ERR_TYPE, "arith_checked: type id %d is not an integer type", type);
+  if (w == 0) AG_FAIL(AG_ERR_TYPE, "arith_checked: type id %d is not a numeric type", type);
+  if (type_is_float(type) && op != AG_OP_DIV && op != AG_OP_DIV_CHECKED)
+    AG_FAIL(AG_ERR_TYPE, "arith_checked: type id %d is not an integer type (floating point types have NotNull kernels for DIV / DIV_CHECKED only)", type);
   if (n < 0) AG_FAIL(AG_ERR_INVALID, "arith_checked: negative length");
   if (n == 0) return AG_OK;
   if ((shape == AG_SHAPE_SA && !l) || (shape == AG_SHAPE_AS && !r)) return AG_OK;  // null scalar
@@ -315,6 +317,8 @@ ag_status ag_arith_checked(int type, int8_t op, int shape, const void* l, const 
   if (first_bad) *first_bad = bad;
   if (bad != AG_NO_ERROR_POS) {
     if (op == AG_OP_DIV || op == AG_OP_DIV_CHECKED) AG_FAIL(AG_ERR_INVALID, "divide by zero");  // errDivByZero, base_arithmetic.go:139
+    if (op == AG_OP_SHIFT_LEFT_CHECKED || op == AG_OP_SHIFT_RIGHT_CHECKED)
+      AG_FAIL(AG_ERR_INVALID, "shift amount must be >= 0 and less than precision of type");     // errShift, scalar_arithmetic.go:294
     AG_FAIL(AG_ERR_INVALID, "overflow");                                                        // errOverflow,  base_arithmetic.go:138
   }
   return AG_OK;

@@ -587,6 +587,46 @@ def main():
         ms = timed(cumsum, W, K)
         others["cumulative_sum_i64"] = {"rows_per_s": world * rows / ms * 1e3, "gbs_per_gpu": 16.0 * rows / ms / 1e6, "frac": 16.0 * rows / ms / 1e6 / peak, "ms": ms,
                                         "note": "single-pass scan, read once + write once (16 B/row)"}
+        vmask = DeviceBuffer(rows // 8 + 64)
+        N.call("ag_generate_dev", 4, 0x1234 + rank, 9, 10, vmask.ptr, rows, None)   # 90 % valid
+        ovalid = DeviceBuffer(rows // 8 + 64)
+
+        def cumsum_nulls():
+            N.call("ag_cumulative_sum_state_init_dev", cstate.ptr, N.INT64, None, None)
+            N.call("ag_cumulative_sum_dev", N.INT64, vi.ptr, vmask.ptr, 3, rows, 1, 0, dout.ptr, ovalid.ptr, 0, cstate.ptr, bad.ptr, None)
+        ms = timed(cumsum_nulls, W, K)
+        others["cumulative_sum_i64_nulls_skip"] = {"rows_per_s": world * rows / ms * 1e3, "gbs_per_gpu": 16.25 * rows / ms / 1e6, "frac": 16.25 * rows / ms / 1e6 / peak, "ms": ms,
+                                                   "note": "10 % nulls, skip_nulls: the general scan kernel (block-synchronous look-back) + validity pass"}
+        # shift_left (checked), bit_wise_xor, divide (checked float NotNull kernel) on resident columns.  vi IS dr (int64 in
+        # [0, 100)); dout gets the shift amounts, dl takes the integer results and is regenerated afterwards
+        N.call("ag_generate_dev", 1, 0x51F7 + rank, 0, 62, dout.ptr, rows, None)
+        N.call("ag_error_word_reset_dev", bad.ptr, None)
+        ms = timed(lambda: N.call("ag_arith_checked_dev", N.INT64, N.OP_SHIFT_LEFT_CHECKED, N.SHAPE_AA, vi.ptr, None, 0, dout.ptr, None, 0, dl.ptr, rows, bad.ptr, None), W, K)
+        others["shift_left_i64_checked"] = {"rows_per_s": world * rows / ms * 1e3, "gbs_per_gpu": 24.0 * rows / ms / 1e6, "frac": 24.0 * rows / ms / 1e6 / peak, "ms": ms}
+        ms = timed(lambda: N.call("ag_arith_binary_dev", N.INT64, N.OP_BIT_XOR, N.SHAPE_AA, vi.ptr, dout.ptr, dl.ptr, rows, None), W, K)
+        others["bit_wise_xor_i64"] = {"rows_per_s": world * rows / ms * 1e3, "gbs_per_gpu": 24.0 * rows / ms / 1e6, "frac": 24.0 * rows / ms / 1e6 / peak, "ms": ms}
+        N.call("ag_generate_dev", 3, 0x94378165 + rank * rows, -(1 << 20), 1 << 20, dl.ptr, rows, None)
+        N.call("ag_generate_dev", 3, 0x0D1F + rank * rows, 1, 1 << 20, dout.ptr, rows, None)       # divisors >= 1: no error raised
+        ms = timed(lambda: N.call("ag_arith_checked_dev", N.FLOAT64, N.OP_DIV_CHECKED, N.SHAPE_AA, dl.ptr, None, 0, dout.ptr, None, 0, dr.ptr, rows, bad.ptr, None), W, K)
+        others["divide_f64_checked"] = {"rows_per_s": world * rows / ms * 1e3, "gbs_per_gpu": 24.0 * rows / ms / 1e6, "frac": 24.0 * rows / ms / 1e6 / peak, "ms": ms,
+                                        "note": "ScalarBinaryNotNull float kernel with the zero-divisor test per valid slot"}
+        # Parquet decode primitives: bit-unpack 100M 13-bit values, bytes -> bools, def levels -> validity
+        nb = 13
+        unp = C.c_int64()
+        ms = timed(lambda: N.call("ag_parquet_unpack32_dev", vi.ptr, dout.ptr, rows, nb, C.byref(unp), None), W, K)
+        ub = rows * nb / 8.0 + rows * 4.0
+        others["parquet_unpack32_13bit"] = {"values_per_s": world * rows / ms * 1e3, "gbs_per_gpu": ub / ms / 1e6, "frac": ub / ms / 1e6 / peak, "ms": ms,
+                                            "note": "13/8 B in + 4 B out per value"}
+        ms = timed(lambda: N.call("ag_parquet_bytes_to_bools_dev", vi.ptr, rows // 8, dout.ptr, rows, None), W, K)
+        others["parquet_bytes_to_bools"] = {"values_per_s": world * rows / ms * 1e3, "gbs_per_gpu": 1.125 * rows / ms / 1e6, "frac": 1.125 * rows / ms / 1e6 / peak, "ms": ms,
+                                            "note": "1/8 B in + 1 B out per value"}
+        N.call("ag_generate_dev", 2, 0xDEF + rank, 0, 1, dr.ptr, rows, None)   # int32 lanes -> int16 levels in {0, 1} pairs
+        counts = DeviceBuffer(64)
+        ms = timed(lambda: N.call("ag_parquet_def_levels_to_bitmap_dev", dr.ptr, rows, 1, -1, ovalid.ptr, 0, rows, counts.ptr, None), W, K)
+        others["parquet_def_levels_to_bitmap"] = {"values_per_s": world * rows / ms * 1e3, "gbs_per_gpu": 2.125 * rows / ms / 1e6, "frac": 2.125 * rows / ms / 1e6 / peak, "ms": ms,
+                                                  "note": "flat column: 2 B level in + 1 bit out per value (compare_kernel int16 >= scalar)"}
+        counts.free(); vmask.free(); ovalid.free()
+        N.call("ag_generate_dev", 3, 0x94378166 + rank * rows, -(1 << 20), 1 << 20, dr.ptr, rows, None)
         # SURVEY 8f rank 3, same columns: sort_indices (stable radix sort), is_in (1000-value set), unique (100 distinct values)
         N.call("ag_generate_dev", 1, 0x5027 + rank * rows, -(1 << 31), (1 << 31) - 1, vi.ptr, rows, None)
         nn, na = C.c_int64(), C.c_int64()

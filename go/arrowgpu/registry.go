@@ -22,6 +22,9 @@ var numericTypes = []arrow.DataType{
 	arrow.PrimitiveTypes.Float32, arrow.PrimitiveTypes.Float64,
 }
 
+// intTypes of the reference's bitwise / shift kernel lists (scalar_arithmetic.go:245-255,401-412)
+var integerTypes = numericTypes[:8]
+
 // delegating is a compute.Function that runs the GPU ScalarFunction when its kernels match the argument types exactly
 // and hands every other call (promotions, decimals, temporal types, dictionary inputs ...) to the function of the same
 // name in the parent registry.  This is forced by the reference: dispatch is first-match over an unexported kernel
@@ -102,14 +105,44 @@ func NewRegistry() compute.FunctionRegistry {
 			addScalar(reg, parent, fn)
 		}
 	}
-	// ---- divide (integers: checked form reports "divide by zero" / overflow, base_arithmetic.go:154-161,287-294)
+	// ---- divide / divide_unchecked: every kernel is ScalarBinaryNotNull (base_arithmetic.go:154-161,287-294 integers —
+	// a zero divisor fails in BOTH flavours —, :386-397 floats — only the checked one fails)
 	for name, op := range map[string]C.int8_t{"divide": C.AG_OP_DIV_CHECKED, "divide_unchecked": C.AG_OP_DIV} {
 		fn := compute.NewScalarFunction(name, compute.Binary(), compute.EmptyFuncDoc)
 		for _, ty := range numericTypes {
-			if arrow.IsInteger(ty.ID()) {
-				if err := fn.AddKernel(binaryKernel(ty, ty, checkedExec(op), exec.NullIntersection)); err != nil {
-					panic(err)
-				}
+			if err := fn.AddKernel(binaryKernel(ty, ty, checkedExec(op), exec.NullIntersection)); err != nil {
+				panic(err)
+			}
+		}
+		addScalar(reg, parent, fn)
+	}
+	// ---- bit_wise_and / or / xor (every slot, like the arithmetic loops) and bit_wise_not (arithmetic.go:944-972)
+	for name, op := range map[string]C.int8_t{"bit_wise_and": C.AG_OP_BIT_AND, "bit_wise_or": C.AG_OP_BIT_OR, "bit_wise_xor": C.AG_OP_BIT_XOR} {
+		fn := compute.NewScalarFunction(name, compute.Binary(), compute.EmptyFuncDoc)
+		for _, ty := range integerTypes {
+			if err := fn.AddKernel(binaryKernel(ty, ty, arithExec(op), exec.NullIntersection)); err != nil {
+				panic(err)
+			}
+		}
+		addScalar(reg, parent, fn)
+	}
+	{
+		fn := compute.NewScalarFunction("bit_wise_not", compute.Unary(), compute.EmptyFuncDoc)
+		for _, ty := range integerTypes {
+			k := exec.NewScalarKernel([]exec.InputType{exec.NewExactInput(ty)}, exec.NewOutputType(ty), unaryExec(C.AG_OP_BIT_NOT), nil)
+			if err := fn.AddKernel(k); err != nil {
+				panic(err)
+			}
+		}
+		addScalar(reg, parent, fn)
+	}
+	// ---- shift_left / shift_right (+ _unchecked), arithmetic.go:974-996, kernels scalar_arithmetic.go:293-412
+	for name, op := range map[string]C.int8_t{"shift_left": C.AG_OP_SHIFT_LEFT_CHECKED, "shift_left_unchecked": C.AG_OP_SHIFT_LEFT,
+		"shift_right": C.AG_OP_SHIFT_RIGHT_CHECKED, "shift_right_unchecked": C.AG_OP_SHIFT_RIGHT} {
+		fn := compute.NewScalarFunction(name, compute.Binary(), compute.EmptyFuncDoc)
+		for _, ty := range integerTypes {
+			if err := fn.AddKernel(binaryKernel(ty, ty, checkedExec(op), exec.NullIntersection)); err != nil { // errShift worded by the library
+				panic(err)
 			}
 		}
 		addScalar(reg, parent, fn)
