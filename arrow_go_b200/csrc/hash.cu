@@ -45,7 +45,13 @@ __device__ __forceinline__ void table_insert(const HashTable& t, unsigned long l
   while (true) {
     unsigned long long cur = t.keys[h];
     if (cur == kEmptyKey) cur = atomicCAS(&t.keys[h], kEmptyKey, key);
-    if (cur == kEmptyKey || cur == key) { atomicMin(&t.first[h], row); return; }
+    if (cur == kEmptyKey || cur == key) {
+      // rows arrive roughly in increasing order, so after a key's first few rows the slot already holds a lower row:
+      // a plain load then replaces the atomic (100M rows over 100 distinct keys would otherwise serialise 100M
+      // atomicMin on 100 addresses)
+      if (*reinterpret_cast<volatile unsigned*>(&t.first[h]) > row) atomicMin(&t.first[h], row);
+      return;
+    }
     h = (h + 1) & t.mask;
   }
 }
@@ -73,36 +79,71 @@ hash_insert_kernel(const V* __restrict__ vals, const uint8_t* __restrict__ valid
 // isInKernelExec (scalar_set_lookup.go:373-413), per row:
 //   valid value : in the set -> (true, valid); else INCONCLUSIVE with a null in the set -> (false, null); else (false, valid)
 //   null        : MATCH with a null in the set -> (true, valid); SKIP, or MATCH without one -> (false, valid); else (false, null)
-template <typename V>
+constexpr int kIsInSmemSlots = 4096;   // 32 KB of keys: value sets up to 2048 entries are probed in shared memory
+constexpr int kIsInUnroll = 4;
+
+template <typename V, bool kSmem>
 __global__ void __launch_bounds__(kHThreads)
 is_in_kernel(const V* __restrict__ vals, const uint8_t* __restrict__ valid, int64_t off, int64_t n, const HashTable t, int null_behavior,
              uint32_t* __restrict__ out_data, uint32_t* __restrict__ out_valid, unsigned long long* __restrict__ null_count) {
+  __shared__ unsigned long long s_keys[kSmem ? kIsInSmemSlots : 1];
+  if (kSmem) {
+    // the column streams through L1 and would keep evicting a table that lives in global memory
+    for (unsigned i = threadIdx.x; i <= (unsigned)t.mask; i += kHThreads) s_keys[i] = t.keys[i];
+    __syncthreads();
+  }
   const bool set_has_null = t.special[1] != kNoRow;
+  const bool set_has_ones = t.special[0] != kNoRow;
+  auto member = [&](unsigned long long key) -> bool {
+    if (key == kEmptyKey) return set_has_ones;
+    unsigned long long h = mix64(key) & t.mask;
+    while (true) {
+      const unsigned long long cur = kSmem ? s_keys[h] : t.keys[h];
+      if (cur == key) return true;
+      if (cur == kEmptyKey) return false;
+      h = (h + 1) & t.mask;
+    }
+  };
   const int lane = threadIdx.x & 31;
   const int64_t n_words = (n + 31) >> 5;
+  const int64_t warp0 = ((int64_t)blockIdx.x * kHThreads + threadIdx.x) >> 5;
+  const int64_t warps = ((int64_t)gridDim.x * kHThreads) >> 5;
   unsigned long long nulls = 0;
-  for (int64_t w = ((int64_t)blockIdx.x * kHThreads + threadIdx.x) >> 5; w < n_words; w += ((int64_t)gridDim.x * kHThreads) >> 5) {
-    const int64_t i = (w << 5) + lane;
-    bool d = false, v = true;
-    if (i < n) {
-      if (valid && !bit_is_set(valid, off + i)) {
-        if (null_behavior == AG_NULL_MATCH && set_has_null) d = true;
-        else if (null_behavior == AG_NULL_SKIP || (null_behavior == AG_NULL_MATCH && !set_has_null)) d = false;
-        else v = false;
-      } else if (table_first_row(t, raw_key(vals + off, i)) != kNoRow) {
-        d = true;
-      } else if (null_behavior == AG_NULL_INCONCLUSIVE && set_has_null) {
-        v = false;
-      }
+  for (int64_t w0 = warp0 * kIsInUnroll; w0 < n_words; w0 += warps * kIsInUnroll) {
+    V x[kIsInUnroll];
+    bool have[kIsInUnroll], isnull[kIsInUnroll];
+#pragma unroll
+    for (int k = 0; k < kIsInUnroll; ++k) {   // independent loads first: 4 rows in flight per lane
+      const int64_t i = ((w0 + k) << 5) + lane;
+      have[k] = i < n;
+      isnull[k] = have[k] && valid && !bit_is_set(valid, off + i);
+      x[k] = (have[k] && !isnull[k]) ? __ldcs(vals + off + i) : V(0);
     }
-    const uint32_t dbits = __ballot_sync(0xffffffffu, d);
-    const uint32_t vbits = __ballot_sync(0xffffffffu, v);
-    if (lane == 0) {
-      const int64_t rem = n - (w << 5);
-      const uint32_t m = rem >= 32 ? 0xffffffffu : bit_range_mask(0, (int)rem);
-      bitmap_store32_masked(out_data + w, dbits, m);
-      if (out_valid) bitmap_store32_masked(out_valid + w, vbits, m);
-      nulls += __popc(~vbits & m);
+#pragma unroll
+    for (int k = 0; k < kIsInUnroll; ++k) {
+      const int64_t w = w0 + k;
+      if (w >= n_words) break;   // warp-uniform
+      bool d = false, v = true;
+      if (have[k]) {
+        if (isnull[k]) {
+          if (null_behavior == AG_NULL_MATCH && set_has_null) d = true;
+          else if (null_behavior == AG_NULL_SKIP || (null_behavior == AG_NULL_MATCH && !set_has_null)) d = false;
+          else v = false;
+        } else if (member((unsigned long long)x[k])) {
+          d = true;
+        } else if (null_behavior == AG_NULL_INCONCLUSIVE && set_has_null) {
+          v = false;
+        }
+      }
+      const uint32_t dbits = __ballot_sync(0xffffffffu, d);
+      const uint32_t vbits = __ballot_sync(0xffffffffu, v);
+      if (lane == 0) {
+        const int64_t rem = n - (w << 5);
+        const uint32_t m = rem >= 32 ? 0xffffffffu : bit_range_mask(0, (int)rem);
+        bitmap_store32_masked(out_data + w, dbits, m);
+        if (out_valid) bitmap_store32_masked(out_valid + w, vbits, m);
+        nulls += __popc(~vbits & m);
+      }
     }
   }
   if (lane == 0 && nulls && null_count) atomicAdd(null_count, nulls);
@@ -157,9 +198,14 @@ static ag_status is_in_t(const void* vals, const uint8_t* valid, int64_t off, in
       if ((rc = check_launch("hash_insert_kernel")) != AG_OK) break;
     }
     if (d_null_count && cudaMemsetAsync(d_null_count, 0, 8, st) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "memset", __FILE__, __LINE__); break; }
-    is_in_kernel<V><<<grid_for(n, kHThreads * 4, 8), kHThreads, 0, st>>>(reinterpret_cast<const V*>(vals), valid, off, n, tm.t, null_behavior,
-                                                                         reinterpret_cast<uint32_t*>(out_data), reinterpret_cast<uint32_t*>(out_valid),
-                                                                         reinterpret_cast<unsigned long long*>(d_null_count));
+    if (tm.t.mask < (unsigned long long)kIsInSmemSlots)
+      is_in_kernel<V, true><<<grid_for(n, kHThreads * 4, 6), kHThreads, 0, st>>>(reinterpret_cast<const V*>(vals), valid, off, n, tm.t, null_behavior,
+                                                                                 reinterpret_cast<uint32_t*>(out_data), reinterpret_cast<uint32_t*>(out_valid),
+                                                                                 reinterpret_cast<unsigned long long*>(d_null_count));
+    else
+      is_in_kernel<V, false><<<grid_for(n, kHThreads * 4, 8), kHThreads, 0, st>>>(reinterpret_cast<const V*>(vals), valid, off, n, tm.t, null_behavior,
+                                                                                  reinterpret_cast<uint32_t*>(out_data), reinterpret_cast<uint32_t*>(out_valid),
+                                                                                  reinterpret_cast<unsigned long long*>(d_null_count));
     rc = check_launch("is_in_kernel");
   } while (0);
   tm.release(st);

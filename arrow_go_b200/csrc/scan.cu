@@ -669,13 +669,16 @@ constexpr int kScStreamThreads = kScThreads + 32;  // 8 compute warps + the look
 constexpr int kScStreamStages = 3;
 constexpr int kScStreamBlocksPerSm = 2;            // 2 x (3 x 32 KB) of the SM's 227 KB
 
-template <typename T>
+template <typename T, bool kHasValid>
 __global__ void __launch_bounds__(kScStreamThreads, kScStreamBlocksPerSm)
 cumsum_stream_kernel(const CumsumParams p) {
   using P = typename PolSel<T, false>::type;
   using A = typename P::A;
   constexpr int N = 16 / sizeof(T);
   constexpr int E = kScRows * N;                  // rows owned by one lane (128 contiguous bytes)
+  constexpr int kTileRows = kScTileBytes / sizeof(T);
+  constexpr int kSegRows = kTileRows / kScWarps;
+  constexpr int VW = (E + 31) / 32;               // validity words per lane
   extern __shared__ __align__(128) unsigned char s_ring[];  // 3 stages x 32 KB
   __shared__ A s_warp[2][kScWarps];
   __shared__ A s_excl[2];
@@ -702,6 +705,29 @@ cumsum_stream_kernel(const CumsumParams p) {
     if (blockIdx.x == 0 && threadIdx.x == 0) { CumsumState ns = s_state; P::to_state(start, &ns); *p.state = ns; }
     return;
   }
+
+  // validity of the E rows a lane owns, 32 at a time: rows at or past `limit` (the first null when nulls are not
+  // skipped) and past n contribute nothing — cumsum_kernel's rule.  Returns whether every row counts (the common case).
+  int64_t limit = p.n;
+  if (kHasValid && !p.skip_nulls) limit = *p.first_null;
+  const int64_t vlo = p.voff >> 3, vhi = (p.voff + p.n + 7) >> 3;
+  auto lane_validity = [&](int64_t tile, unsigned (&vbits)[VW]) -> bool {
+    if (!kHasValid) return true;
+    const int64_t t0 = tile * kTileRows + (int64_t)(warp & (kScWarps - 1)) * kSegRows + (int64_t)lane * E;
+    bool dense = true;
+#pragma unroll
+    for (int w = 0; w < VW; ++w) {
+      const int64_t e0 = t0 + w * 32;
+      unsigned m = (e0 < p.n) ? bitmap_load32(p.valid, p.voff + e0, vlo, vhi) : 0u;
+      const int64_t room = limit - e0;
+      if (room < 32) m &= (room <= 0) ? 0u : ((1u << (int)room) - 1u);
+      constexpr unsigned kFull = (E >= 32) ? 0xffffffffu : ((1u << (E & 31)) - 1u);
+      m &= kFull;
+      vbits[w] = m;
+      dense = dense && m == kFull;
+    }
+    return dense;
+  };
 
   // byte offsets of this lane inside a 4 KB warp segment
   //   striped (coalesced) vector k:  logical (k*32 + lane) * 16, parked at its owner's row, chunk ^ (owner & 7)
@@ -752,8 +778,14 @@ cumsum_stream_kernel(const CumsumParams p) {
         for (int c = 0; c < kScRows; ++c) raw[c] = *reinterpret_cast<const uint4*>(seg + blk_row + (((uint32_t)c << 4) ^ blk_x));
         const T* o = reinterpret_cast<const T*>(raw);
         A tot = P::zero();
+        unsigned vbits[VW];
+        if (lane_validity(tile_r, vbits)) {
 #pragma unroll
-        for (int i = 0; i < E; ++i) tot = P::add_elem(tot, o[i]);
+          for (int i = 0; i < E; ++i) tot = P::add_elem(tot, o[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < E; ++i) if ((vbits[i >> 5] >> (i & 31)) & 1u) tot = P::add_elem(tot, o[i]);
+        }
         A incl = tot;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -790,6 +822,7 @@ cumsum_stream_kernel(const CumsumParams p) {
         if (tile_f == p.n_tiles - 1) {
           CumsumState ns = s_state;
           P::to_state(P::add(excl, tile_total), &ns);
+          if (kHasValid && *p.first_null < p.n) ns.encountered_null = 1;
           *p.state = ns;
         }
       }
@@ -813,8 +846,17 @@ cumsum_stream_kernel(const CumsumParams p) {
         T* o = reinterpret_cast<T*>(raw);
         A run = P::add(warp_excl_cur, lane_excl_cur);
         const T off = P::value(s_excl[bf]);
+        unsigned vbits[VW];
+        if (lane_validity(tile_f, vbits)) {
 #pragma unroll
-        for (int i = 0; i < E; ++i) { run = P::add_elem(run, o[i]); o[i] = P::offset_add(off, P::value(run)); }
+          for (int i = 0; i < E; ++i) { run = P::add_elem(run, o[i]); o[i] = P::offset_add(off, P::value(run)); }
+        } else {
+#pragma unroll
+          for (int i = 0; i < E; ++i) {
+            if ((vbits[i >> 5] >> (i & 31)) & 1u) { run = P::add_elem(run, o[i]); o[i] = P::offset_add(off, P::value(run)); }
+            else o[i] = T(0);
+          }
+        }
 #pragma unroll
         for (int c = 0; c < kScRows; ++c) *reinterpret_cast<uint4*>(seg + blk_row + (((uint32_t)c << 4) ^ blk_x)) = raw[c];
         __syncwarp();
@@ -938,16 +980,18 @@ ag_status launch_cumsum(CumsumParams& p, cudaStream_t st) {
   void* args[] = {(void*)&p};
   const void* fn;
   const bool chk = p.checked && !IsFp<T>::v;  // floats: the checked adder is the plain one
-  if (vec && !chk && !p.valid) {
+  if (vec && !chk) {
     constexpr int kRing = kScStreamStages * kScTileBytes;
     static std::atomic<unsigned> attr_set{0u};  // per instantiation, one bit per device
-    AG_TRY(ensure_dynamic_smem((const void*)cumsum_stream_kernel<T>, kRing, &attr_set));
+    const void* sfn = p.valid ? (const void*)cumsum_stream_kernel<T, true> : (const void*)cumsum_stream_kernel<T, false>;
+    static std::atomic<unsigned> attr_set_v{0u};
+    AG_TRY(ensure_dynamic_smem(sfn, kRing, p.valid ? &attr_set_v : &attr_set));
     int per_sm = 0;
-    AG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cumsum_stream_kernel<T>, kScStreamThreads, kRing));
+    AG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sfn, kScStreamThreads, kRing));
     if (per_sm < 1) per_sm = 1;
     const int64_t cap = (int64_t)sm_count() * per_sm;
     const int grid = (int)(p.n_tiles < cap ? p.n_tiles : cap);
-    AG_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)cumsum_stream_kernel<T>, dim3(grid), dim3(kScStreamThreads), args, kRing, st));
+    AG_CUDA_TRY(cudaLaunchCooperativeKernel(sfn, dim3(grid), dim3(kScStreamThreads), args, kRing, st));
     return check_launch("cumsum_stream_kernel");
   }
   if (chk) {

@@ -77,4 +77,13 @@ for k in (0, 1):
     timed(f"take_i64_i32 random knob0={k}", lambda: N.call("ag_take_primitive_dev", 64, b.ptr, None, 0, rows, 32, 1, idx.ptr, None, 0, rows, 1, o.ptr, None, bad.ptr, None), rows * 20)
 lab(0, 0)
 timed("greater_i64_scalar", lambda: N.call("ag_compare_dev", N.INT64, N.CMP_GT, N.SHAPE_AS, b.ptr, sc.ctypes.data, mask.ptr, rows, 0, None), rows * 8 + rows // 8)
+# set lookup / unique
+N.call("ag_generate_dev", 1, 0x15, 0, 99_999, a.ptr, rows, None)
+sset = DeviceBuffer(8000)
+hs = np.arange(0, 100_000, 100, dtype=np.int64)
+N.call("ag_upload", sset.ptr, hs.ctypes.data, 8000, None)
+bm1, bm2 = DeviceBuffer(rows // 8 + 64), DeviceBuffer(rows // 8 + 64)
+timed("is_in_i64 (1000-value set)", lambda: N.call("ag_is_in_dev", 64, a.ptr, None, 0, rows, sset.ptr, None, 0, 1000, 0, bm1.ptr, bm2.ptr, scal.ptr, None), rows * 8.25)
+N.call("ag_generate_dev", 1, 0x16, 0, 99, a.ptr, rows, None)
+timed("unique_i64 (100 distinct)", lambda: N.call("ag_unique_dev", 64, a.ptr, None, 0, rows, o.ptr, None, rows, scal.ptr, None), rows * 8.0)
 print("selected rows:", cnt)
