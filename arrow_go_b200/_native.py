@@ -166,6 +166,7 @@ _SIGS = {
     "ag_take_primitive": [_i, _p, _p, _i64, _i64, _i, _i, _p, _p, _i64, _i64, _i, _p, _p, _pi64, _pi64, _pi64],
     "ag_take_primitive_dev": [_i, _p, _p, _i64, _i64, _i, _i, _p, _p, _i64, _i64, _i, _p, _p, _p, _p],
     "ag_take_set_policy": [_i, _i64, _i64, _i64],
+    "ag_unique_set_policy": [_i64, _i64],
     "ag_is_in": [_i, _p, _p, _i64, _i64, _p, _p, _i64, _i64, _i, _p, _p, _pi64],
     "ag_is_in_dev": [_i, _p, _p, _i64, _i64, _p, _p, _i64, _i64, _i, _p, _p, _p, _p],
     "ag_unique": [_i, _p, _p, _i64, _i64, _p, _p, _pi64, _pi64],

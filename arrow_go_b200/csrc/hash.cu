@@ -7,14 +7,22 @@
 //           NullMatchingBehavior table restated in is_in_kernel below);
 //   unique  arrow/compute/internal/kernels/vector_hash.go (the distinct values in order of FIRST appearance, a null
 //           kept once at the position of its first appearance).
-// Both sit on the same open-addressing table in HBM: 64-bit keys (the value's bytes, zero-extended), linear probing,
-// load factor <= 0.5, inserted with atomicCAS; every slot also keeps the lowest row that carried its key (atomicMin),
-// which is all `unique` needs: a row is emitted iff it is the first row of its key, and the emitted rows are compacted
-// in row order by the filter kernel (filter.cu) — so the output order is the reference's and does not depend on the
-// order in which threads reached the table.
-// Roofline: the probe is take's access pattern (one random 8-byte read per row into a table that is L2-resident for
-// value sets up to a few million entries); `unique` on n rows sizes its table by n (2n slots rounded up to a power of
-// two, 12 bytes per slot).
+// Both sit on the same open-addressing table: 16-byte slots {64-bit key = the value's bytes zero-extended, lowest row
+// that carried the key}, linear probing from an even slot (so a probe can always look at an aligned pair), load factor
+// <= 0.5, keys inserted with atomicCAS, first rows with atomicMin.  The first row is all `unique` needs: a row is
+// emitted iff it is the first row of its key, and the emitted rows are compacted in row order by the filter kernel
+// (filter.cu) — so the output order is the reference's and does not depend on the order in which threads reached the
+// table.
+//   is_in : value sets up to 4096 entries are probed in shared memory (8192 key slots = 64 KB, load factor <= 1/8 for
+//           the usual few-hundred-value set, two slots per 128-bit read); 1- and 2-byte values skip hashing altogether:
+//           the set becomes a 256 / 65536-bit membership bitmap.  Larger sets are probed in HBM / L2.
+//   unique: a column of more than 2M rows first runs against a 4M-slot table that stays L2-resident (64 MB); only when
+//           more than 2M distinct values turn up does the insert raise an overflow word, and the full-size table
+//           (2n slots) is cleared and filled by kernels that test that word first — the choice is made on the device,
+//           the call stays stream-ordered.  Each warp also keeps the last keys it met in a small shared-memory cache:
+//           a key met at a lower row of the same warp cannot be a first appearance, so low-cardinality columns
+//           (the usual dictionary-encoding case) hardly touch the table at all.
+// Roofline: HBM, 8 B/row read once per pass (is_in: one pass; unique: insert + mark + compaction).
 #include "common.cuh"
 
 namespace ag {
@@ -24,84 +32,185 @@ ag_status filter_primitive_dev(int bit_width, const void* vals, const uint8_t* v
                                int64_t capacity, int64_t* d_out_len, cudaStream_t st);
 
 constexpr int kHThreads = 256;
+constexpr int kHWarps = kHThreads / 32;
+constexpr int kHUnroll = 4;                 // 32-row groups a warp has in flight
 constexpr unsigned long long kEmptyKey = 0xffffffffffffffffull;
 constexpr unsigned kNoRow = 0xffffffffu;
+constexpr unsigned kNoCap = 0xffffffffu;
+
+struct alignas(16) Slot { unsigned long long key; unsigned first; unsigned pad; };
 
 struct HashTable {
-  unsigned long long* keys;   // [slots], kEmptyKey = free
-  unsigned* first;            // [slots] lowest row that carried the key
+  Slot* slots;                // cleared to all-ones: key = kEmptyKey (free), first = kNoRow
   unsigned long long mask;    // slots - 1
-  unsigned* special;          // [2]: lowest row whose key is the all-ones pattern (cannot live in `keys`), lowest NULL row
+  int shift;                  // 64 - log2(slots)
+  unsigned cap;               // distinct keys after which an insert raises special[3] and stops (kNoCap: never)
+  unsigned* special;          // [0] lowest row whose key is the all-ones pattern (cannot live in `slots`), [1] lowest NULL row,
+                              // [2] distinct keys inserted, [3] overflow word (0xffffffff after the clear = not raised)
 };
+
+// multiplicative (Fibonacci) hash of the folded key, forced even: every probe sequence starts on an aligned slot pair
+__device__ __forceinline__ unsigned long long hash_slot(unsigned long long key, int shift) {
+  const unsigned long long x = key ^ (key >> 32);
+  return ((x * 0x9E3779B97F4A7C15ull) >> shift) & ~1ull;
+}
+__device__ __forceinline__ bool overflowed(const HashTable& t) { return *reinterpret_cast<volatile unsigned*>(&t.special[3]) == 1u; }
 
 template <typename V>
 __device__ __forceinline__ unsigned long long raw_key(const V* __restrict__ vals, int64_t i) {
   return (unsigned long long)vals[i];
 }
 
+// lower `*p` to `row` (rows arrive roughly in increasing order, so after the first few rows of a key the word already
+// holds a lower row and a plain load replaces the atomic: 100M rows over 100 keys would otherwise serialise 100M atomics
+// on 100 addresses)
+__device__ __forceinline__ void lower_row(unsigned* p, unsigned seen, unsigned row) {
+  if (seen > row) atomicMin(p, row);
+}
+
 __device__ __forceinline__ void table_insert(const HashTable& t, unsigned long long key, unsigned row) {
-  if (key == kEmptyKey) { atomicMin(&t.special[0], row); return; }
-  unsigned long long h = mix64(key) & t.mask;
+  unsigned long long h = hash_slot(key, t.shift);
+  unsigned probes = 0;
   while (true) {
-    unsigned long long cur = t.keys[h];
-    if (cur == kEmptyKey) cur = atomicCAS(&t.keys[h], kEmptyKey, key);
-    if (cur == kEmptyKey || cur == key) {
-      // rows arrive roughly in increasing order, so after a key's first few rows the slot already holds a lower row:
-      // a plain load then replaces the atomic (100M rows over 100 distinct keys would otherwise serialise 100M
-      // atomicMin on 100 addresses)
-      if (*reinterpret_cast<volatile unsigned*>(&t.first[h]) > row) atomicMin(&t.first[h], row);
-      return;
+    Slot* s = t.slots + h;
+    const ulonglong2 raw = __ldcg(reinterpret_cast<const ulonglong2*>(s));   // key and first row in one L2 request
+    unsigned long long cur = raw.x;
+    unsigned seen = (unsigned)raw.y;
+    if (cur == kEmptyKey) {
+      cur = atomicCAS(&s->key, kEmptyKey, key);
+      if (cur == kEmptyKey) {
+        seen = kNoRow;
+        // special[2] is cleared to 0xffffffff: old + 2 (mod 2^32) is the number of keys now in the table
+        if (t.cap != kNoCap && atomicAdd(&t.special[2], 1u) + 2u > t.cap) *reinterpret_cast<volatile unsigned*>(&t.special[3]) = 1u;
+        cur = key;
+      } else if (cur == key) {
+        seen = kNoRow;     // somebody else created it just now: its first row is not in `raw`
+      }
     }
+    if (cur == key) { lower_row(&s->first, seen, row); return; }
     h = (h + 1) & t.mask;
+    // a capped table can fill up completely while the inserts that were in flight when the cap was crossed finish:
+    // the overflow word is raised before that can happen (cap = half the slots), so a long probe checks it and gives up
+    if (t.cap != kNoCap && ((++probes & 7u) == 0u) && overflowed(t)) return;
   }
 }
-// lowest row that carried `key`, kNoRow when absent
+// lowest row that carried `key`, kNoRow when absent (the table is complete: plain cached loads)
 __device__ __forceinline__ unsigned table_first_row(const HashTable& t, unsigned long long key) {
-  if (key == kEmptyKey) return t.special[0];
-  unsigned long long h = mix64(key) & t.mask;
+  unsigned long long h = hash_slot(key, t.shift);
   while (true) {
-    const unsigned long long cur = t.keys[h];
-    if (cur == key) return t.first[h];
-    if (cur == kEmptyKey) return kNoRow;
+    const ulonglong2 raw = *reinterpret_cast<const ulonglong2*>(t.slots + h);
+    if (raw.x == key) return (unsigned)raw.y;
+    if (raw.x == kEmptyKey) return kNoRow;
     h = (h + 1) & t.mask;
   }
 }
 
+// Per-warp cache of keys already met (direct-mapped, 256 entries).  A warp walks its rows in increasing order, so a hit
+// means: this key sits at a lower row that this warp has already sent to the table.
+constexpr int kWarpCacheSlots = 256;
+__device__ __forceinline__ int warp_cache_slot(unsigned long long key) {
+  return (int)(((key ^ (key >> 32)) * 0x9E3779B97F4A7C15ull) >> 56);
+}
+
+// `run_if`: NULL, or a device word the kernel tests first (the full-size pass of `unique` runs only after an overflow)
 template <typename V>
 __global__ void __launch_bounds__(kHThreads)
-hash_insert_kernel(const V* __restrict__ vals, const uint8_t* __restrict__ valid, int64_t off, int64_t n, const HashTable t) {
-  for (int64_t i = (int64_t)blockIdx.x * kHThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kHThreads) {
-    if (valid && !bit_is_set(valid, off + i)) atomicMin(&t.special[1], (unsigned)i);
-    else table_insert(t, raw_key(vals + off, i), (unsigned)i);
+hash_insert_kernel(const V* __restrict__ vals, const uint8_t* __restrict__ valid, int64_t off, int64_t n, const HashTable t,
+                   const unsigned* __restrict__ run_if) {
+  __shared__ unsigned long long s_cache[kHWarps][kWarpCacheSlots];
+  if (run_if && *run_if != 1u) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long* cache = s_cache[warp];
+  for (int i = lane; i < kWarpCacheSlots; i += 32) cache[i] = kEmptyKey;
+  __syncwarp();
+  const int64_t n_words = (n + 31) >> 5;
+  const int64_t warp0 = ((int64_t)blockIdx.x * kHThreads + threadIdx.x) >> 5;
+  const int64_t warps = ((int64_t)gridDim.x * kHThreads) >> 5;
+  for (int64_t w0 = warp0 * kHUnroll; w0 < n_words; w0 += warps * kHUnroll) {
+    if (__any_sync(0xffffffffu, t.cap != kNoCap && overflowed(t))) return;   // the small table is being abandoned (warp-uniform exit)
+    V x[kHUnroll];
+    int kind[kHUnroll];                                  // 0 nothing, 1 value, 2 null
+#pragma unroll
+    for (int k = 0; k < kHUnroll; ++k) {
+      const int64_t i = ((w0 + k) << 5) + lane;
+      kind[k] = i < n ? ((valid && !bit_is_set(valid, off + i)) ? 2 : 1) : 0;
+      x[k] = kind[k] == 1 ? __ldcs(vals + off + i) : V(0);
+    }
+#pragma unroll
+    for (int k = 0; k < kHUnroll; ++k) {
+      const unsigned row = (unsigned)(((w0 + k) << 5) + lane);
+      const unsigned long long key = (unsigned long long)x[k];
+      const int cs = warp_cache_slot(key);
+      if (kind[k] == 2) lower_row(&t.special[1], *reinterpret_cast<volatile unsigned*>(&t.special[1]), row);
+      else if (kind[k] == 1 && key == kEmptyKey) lower_row(&t.special[0], *reinterpret_cast<volatile unsigned*>(&t.special[0]), row);
+      const bool go = kind[k] == 1 && key != kEmptyKey && cache[cs] != key;
+      __syncwarp();
+      if (go) { table_insert(t, key, row); cache[cs] = key; }
+      __syncwarp();
+    }
   }
+}
+
+__global__ void __launch_bounds__(kHThreads)
+table_clear_kernel(uint4* __restrict__ p, int64_t n16, const unsigned* __restrict__ run_if) {
+  if (run_if && *run_if != 1u) return;
+  const uint4 ones = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+  for (int64_t i = (int64_t)blockIdx.x * kHThreads + threadIdx.x; i < n16; i += (int64_t)gridDim.x * kHThreads) p[i] = ones;
 }
 
 // isInKernelExec (scalar_set_lookup.go:373-413), per row:
 //   valid value : in the set -> (true, valid); else INCONCLUSIVE with a null in the set -> (false, null); else (false, valid)
 //   null        : MATCH with a null in the set -> (true, valid); SKIP, or MATCH without one -> (false, valid); else (false, null)
-constexpr int kIsInSmemSlots = 4096;   // 32 KB of keys: value sets up to 2048 entries are probed in shared memory
-constexpr int kIsInUnroll = 4;
+constexpr int kIsInSmemSlots = 8192;   // 64 KB of keys
+enum { kMemberTable = 0, kMemberSmem = 1, kMemberBitmap = 2 };
 
-template <typename V, bool kSmem>
+// membership bitmap of a 1- or 2-byte value set: bit v of `bits`; a null in the set lowers special[1]
+template <typename V>
 __global__ void __launch_bounds__(kHThreads)
-is_in_kernel(const V* __restrict__ vals, const uint8_t* __restrict__ valid, int64_t off, int64_t n, const HashTable t, int null_behavior,
-             uint32_t* __restrict__ out_data, uint32_t* __restrict__ out_valid, unsigned long long* __restrict__ null_count) {
-  __shared__ unsigned long long s_keys[kSmem ? kIsInSmemSlots : 1];
-  if (kSmem) {
+set_bitmap_kernel(const V* __restrict__ set, const uint8_t* __restrict__ valid, int64_t off, int64_t n, unsigned* __restrict__ bits,
+                  unsigned* __restrict__ special) {
+  for (int64_t i = (int64_t)blockIdx.x * kHThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kHThreads) {
+    if (valid && !bit_is_set(valid, off + i)) atomicMin(&special[1], (unsigned)i);
+    else { const unsigned v = (unsigned)set[off + i]; atomicOr(&bits[v >> 5], 1u << (v & 31)); }
+  }
+}
+
+template <typename V, int kMember>
+__global__ void __launch_bounds__(kHThreads)
+is_in_kernel(const V* __restrict__ vals, const uint8_t* __restrict__ valid, int64_t off, int64_t n, const HashTable t,
+             const unsigned* __restrict__ set_bits, int null_behavior, uint32_t* __restrict__ out_data, uint32_t* __restrict__ out_valid,
+             unsigned long long* __restrict__ null_count) {
+  extern __shared__ __align__(16) unsigned long long s_keys[];   // kMemberSmem: the table's keys; kMemberBitmap: the bitmap words
+  constexpr int kBitWords = sizeof(V) == 1 ? 8 : 2048;
+  if (kMember == kMemberSmem) {
     // the column streams through L1 and would keep evicting a table that lives in global memory
-    for (unsigned i = threadIdx.x; i <= (unsigned)t.mask; i += kHThreads) s_keys[i] = t.keys[i];
+    for (unsigned i = threadIdx.x; i <= (unsigned)t.mask; i += kHThreads) s_keys[i] = t.slots[i].key;
+    __syncthreads();
+  } else if (kMember == kMemberBitmap) {
+    unsigned* sb = reinterpret_cast<unsigned*>(s_keys);
+    for (int i = threadIdx.x; i < kBitWords; i += kHThreads) sb[i] = set_bits[i];
     __syncthreads();
   }
   const bool set_has_null = t.special[1] != kNoRow;
   const bool set_has_ones = t.special[0] != kNoRow;
   auto member = [&](unsigned long long key) -> bool {
+    if (kMember == kMemberBitmap) {
+      const unsigned* sb = reinterpret_cast<const unsigned*>(s_keys);
+      return (sb[(unsigned)key >> 5] >> ((unsigned)key & 31)) & 1u;
+    }
     if (key == kEmptyKey) return set_has_ones;
-    unsigned long long h = mix64(key) & t.mask;
+    unsigned long long h = hash_slot(key, t.shift);
     while (true) {
-      const unsigned long long cur = kSmem ? s_keys[h] : t.keys[h];
-      if (cur == key) return true;
-      if (cur == kEmptyKey) return false;
-      h = (h + 1) & t.mask;
+      unsigned long long k0, k1;
+      if (kMember == kMemberSmem) {
+        const ulonglong2 pr = *reinterpret_cast<const ulonglong2*>(s_keys + h);   // h is even: one aligned pair
+        k0 = pr.x; k1 = pr.y;
+      } else {
+        k0 = t.slots[h].key; k1 = t.slots[h + 1].key;                             // same 32-byte sector
+      }
+      if (k0 == key || k1 == key) return true;
+      if (k0 == kEmptyKey || k1 == kEmptyKey) return false;
+      h = (h + 2) & t.mask;
     }
   };
   const int lane = threadIdx.x & 31;
@@ -109,18 +218,18 @@ is_in_kernel(const V* __restrict__ vals, const uint8_t* __restrict__ valid, int6
   const int64_t warp0 = ((int64_t)blockIdx.x * kHThreads + threadIdx.x) >> 5;
   const int64_t warps = ((int64_t)gridDim.x * kHThreads) >> 5;
   unsigned long long nulls = 0;
-  for (int64_t w0 = warp0 * kIsInUnroll; w0 < n_words; w0 += warps * kIsInUnroll) {
-    V x[kIsInUnroll];
-    bool have[kIsInUnroll], isnull[kIsInUnroll];
+  for (int64_t w0 = warp0 * kHUnroll; w0 < n_words; w0 += warps * kHUnroll) {
+    V x[kHUnroll];
+    bool have[kHUnroll], isnull[kHUnroll];
 #pragma unroll
-    for (int k = 0; k < kIsInUnroll; ++k) {   // independent loads first: 4 rows in flight per lane
+    for (int k = 0; k < kHUnroll; ++k) {   // independent loads first: 4 rows in flight per lane
       const int64_t i = ((w0 + k) << 5) + lane;
       have[k] = i < n;
       isnull[k] = have[k] && valid && !bit_is_set(valid, off + i);
       x[k] = (have[k] && !isnull[k]) ? __ldcs(vals + off + i) : V(0);
     }
 #pragma unroll
-    for (int k = 0; k < kIsInUnroll; ++k) {
+    for (int k = 0; k < kHUnroll; ++k) {
       const int64_t w = w0 + k;
       if (w >= n_words) break;   // warp-uniform
       bool d = false, v = true;
@@ -149,39 +258,81 @@ is_in_kernel(const V* __restrict__ vals, const uint8_t* __restrict__ valid, int6
   if (lane == 0 && nulls && null_count) atomicAdd(null_count, nulls);
 }
 
-// unique: row i is kept iff it is the first row of its key (or the first null row)
+// unique: row i is kept iff it is the first row of its key (or the first null row).  `big` is the full-size table of an
+// overflowed call (slots == NULL when the call has only one table).
 template <typename V>
 __global__ void __launch_bounds__(kHThreads)
-unique_mark_kernel(const V* __restrict__ vals, const uint8_t* __restrict__ valid, int64_t off, int64_t n, const HashTable t,
-                   uint32_t* __restrict__ keep) {
-  const int lane = threadIdx.x & 31;
+unique_mark_kernel(const V* __restrict__ vals, const uint8_t* __restrict__ valid, int64_t off, int64_t n, const HashTable small_t,
+                   const HashTable big_t, uint32_t* __restrict__ keep) {
+  __shared__ unsigned long long s_cache[kHWarps][kWarpCacheSlots];
+  const bool use_big = big_t.slots && overflowed(small_t);
+  HashTable t;
+  t.slots = use_big ? big_t.slots : small_t.slots;
+  t.mask = use_big ? big_t.mask : small_t.mask;
+  t.shift = use_big ? big_t.shift : small_t.shift;
+  t.cap = kNoCap;
+  t.special = use_big ? big_t.special : small_t.special;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long* cache = s_cache[warp];
+  for (int i = lane; i < kWarpCacheSlots; i += 32) cache[i] = kEmptyKey;
+  __syncwarp();
+  const unsigned first_ones = t.special[0], first_null = t.special[1];
   const int64_t n_words = (n + 31) >> 5;
-  for (int64_t w = ((int64_t)blockIdx.x * kHThreads + threadIdx.x) >> 5; w < n_words; w += ((int64_t)gridDim.x * kHThreads) >> 5) {
-    const int64_t i = (w << 5) + lane;
-    bool k = false;
-    if (i < n) {
-      if (valid && !bit_is_set(valid, off + i)) k = t.special[1] == (unsigned)i;
-      else k = table_first_row(t, raw_key(vals + off, i)) == (unsigned)i;
+  const int64_t warp0 = ((int64_t)blockIdx.x * kHThreads + threadIdx.x) >> 5;
+  const int64_t warps = ((int64_t)gridDim.x * kHThreads) >> 5;
+  for (int64_t w0 = warp0 * kHUnroll; w0 < n_words; w0 += warps * kHUnroll) {
+    V x[kHUnroll];
+    int kind[kHUnroll];
+#pragma unroll
+    for (int k = 0; k < kHUnroll; ++k) {
+      const int64_t i = ((w0 + k) << 5) + lane;
+      kind[k] = i < n ? ((valid && !bit_is_set(valid, off + i)) ? 2 : 1) : 0;
+      x[k] = kind[k] == 1 ? __ldcs(vals + off + i) : V(0);
     }
-    const uint32_t bits = __ballot_sync(0xffffffffu, k);
-    if (lane == 0) keep[w] = bits;
+#pragma unroll
+    for (int k = 0; k < kHUnroll; ++k) {
+      const int64_t w = w0 + k;
+      if (w >= n_words) break;   // warp-uniform
+      const unsigned row = (unsigned)((w << 5) + lane);
+      const unsigned long long key = (unsigned long long)x[k];
+      const int cs = warp_cache_slot(key);
+      bool kp = false;
+      if (kind[k] == 2) kp = first_null == row;
+      else if (kind[k] == 1 && key == kEmptyKey) kp = first_ones == row;
+      const bool go = kind[k] == 1 && key != kEmptyKey && cache[cs] != key;   // a cached key sits at a lower row: not first
+      __syncwarp();
+      if (go) { kp = table_first_row(t, key) == row; cache[cs] = key; }
+      __syncwarp();
+      const uint32_t bits = __ballot_sync(0xffffffffu, kp);
+      if (lane == 0) keep[w] = bits;
+    }
   }
 }
 
 struct TableMem {
   void* block = nullptr;
+  size_t bytes = 0;
   HashTable t{};
-  ag_status alloc(int64_t entries, cudaStream_t st) {
+  // slots = the power of two >= max(2 * entries, min_slots)
+  ag_status alloc(int64_t entries, unsigned long long min_slots, unsigned cap, cudaStream_t st) {
     unsigned long long slots = 1024;
-    while (slots < (unsigned long long)entries * 2) slots <<= 1;
-    const size_t kb = slots * 8, fb = slots * 4;
-    AG_TRY(dev_alloc_async(&block, kb + fb + 64, st));
-    t.keys = reinterpret_cast<unsigned long long*>(block);
-    t.first = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(block) + kb);
-    t.special = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(block) + kb + fb);
+    while (slots < (unsigned long long)entries * 2 || slots < min_slots) slots <<= 1;
+    int bits = 0;
+    while ((1ull << bits) < slots) ++bits;
+    bytes = slots * sizeof(Slot) + 64;
+    AG_TRY(dev_alloc_async(&block, bytes, st));
+    t.slots = reinterpret_cast<Slot*>(block);
+    t.special = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(block) + slots * sizeof(Slot));
     t.mask = slots - 1;
-    AG_CUDA_TRY(cudaMemsetAsync(block, 0xff, kb + fb + 64, st));   // every key free, every first row = none
+    t.shift = 64 - bits;
+    t.cap = cap;
     return AG_OK;
+  }
+  // every key free, every first row = none, special = {none, none, 0xffffffff (the counter: +1 per key wraps to 0 first), not raised}
+  ag_status clear(cudaStream_t st, const unsigned* run_if = nullptr) {
+    if (!run_if) { AG_CUDA_TRY(cudaMemsetAsync(block, 0xff, bytes, st)); return AG_OK; }
+    table_clear_kernel<<<grid_for((int64_t)(bytes / 16), kHThreads * 8, 8), kHThreads, 0, st>>>(reinterpret_cast<uint4*>(block), (int64_t)(bytes / 16), run_if);
+    return check_launch("table_clear_kernel");
   }
   void release(cudaStream_t st) { if (block) cudaFreeAsync(block, st); block = nullptr; }
 };
@@ -189,23 +340,39 @@ struct TableMem {
 template <typename V>
 static ag_status is_in_t(const void* vals, const uint8_t* valid, int64_t off, int64_t n, const void* set, const uint8_t* set_valid, int64_t set_off,
                          int64_t set_n, int null_behavior, uint8_t* out_data, uint8_t* out_valid, int64_t* d_null_count, cudaStream_t st) {
+  constexpr bool kSmall = sizeof(V) <= 2;
   TableMem tm;
-  AG_TRY(tm.alloc(set_n, st));
-  ag_status rc = AG_OK;
+  // 1-/2-byte values: a 1024-slot block whose first 8 KB hold the membership bitmap (zeroed), `special` behind it as usual
+  // others: load factor <= 1/8 while the table still fits the shared-memory copy, <= 1/2 beyond
+  unsigned long long min_slots = 1024;
+  if (!kSmall) { while (min_slots < (unsigned long long)set_n * 8 && min_slots < (unsigned long long)kIsInSmemSlots) min_slots <<= 1; }
+  AG_TRY(tm.alloc(kSmall ? 0 : set_n, min_slots, kNoCap, st));
+  ag_status rc = tm.clear(st);
+  unsigned* bits = reinterpret_cast<unsigned*>(tm.block);
   do {
+    if (rc != AG_OK) break;
+    if (kSmall && cudaMemsetAsync(bits, 0, 8192, st) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "memset", __FILE__, __LINE__); break; }
     if (set_n > 0) {
-      hash_insert_kernel<V><<<grid_for(set_n, kHThreads * 4, 8), kHThreads, 0, st>>>(reinterpret_cast<const V*>(set), set_valid, set_off, set_n, tm.t);
-      if ((rc = check_launch("hash_insert_kernel")) != AG_OK) break;
+      if constexpr (kSmall) set_bitmap_kernel<V><<<grid_for(set_n, kHThreads, 8), kHThreads, 0, st>>>(reinterpret_cast<const V*>(set), set_valid, set_off, set_n, bits, tm.t.special);
+      else hash_insert_kernel<V><<<grid_for(set_n, kHThreads * kHUnroll, 8), kHThreads, 0, st>>>(reinterpret_cast<const V*>(set), set_valid, set_off, set_n, tm.t, nullptr);
+      if ((rc = check_launch("is_in set kernel")) != AG_OK) break;
     }
     if (d_null_count && cudaMemsetAsync(d_null_count, 0, 8, st) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "memset", __FILE__, __LINE__); break; }
-    if (tm.t.mask < (unsigned long long)kIsInSmemSlots)
-      is_in_kernel<V, true><<<grid_for(n, kHThreads * 4, 6), kHThreads, 0, st>>>(reinterpret_cast<const V*>(vals), valid, off, n, tm.t, null_behavior,
-                                                                                 reinterpret_cast<uint32_t*>(out_data), reinterpret_cast<uint32_t*>(out_valid),
-                                                                                 reinterpret_cast<unsigned long long*>(d_null_count));
-    else
-      is_in_kernel<V, false><<<grid_for(n, kHThreads * 4, 8), kHThreads, 0, st>>>(reinterpret_cast<const V*>(vals), valid, off, n, tm.t, null_behavior,
-                                                                                  reinterpret_cast<uint32_t*>(out_data), reinterpret_cast<uint32_t*>(out_valid),
-                                                                                  reinterpret_cast<unsigned long long*>(d_null_count));
+    uint32_t* od = reinterpret_cast<uint32_t*>(out_data);
+    uint32_t* ov = reinterpret_cast<uint32_t*>(out_valid);
+    unsigned long long* nc = reinterpret_cast<unsigned long long*>(d_null_count);
+    const V* v = reinterpret_cast<const V*>(vals);
+    if constexpr (kSmall) {
+      is_in_kernel<V, kMemberBitmap><<<grid_for(n, kHThreads * kHUnroll, 8), kHThreads, 8192, st>>>(v, valid, off, n, tm.t, bits, null_behavior, od, ov, nc);
+    } else if (tm.t.mask < (unsigned long long)kIsInSmemSlots) {
+      const int smem = (int)((tm.t.mask + 1) * 8);
+      static std::atomic<unsigned> attr_set{0u};   // per V, one bit per device
+      if ((rc = ensure_dynamic_smem((const void*)is_in_kernel<V, kMemberSmem>, kIsInSmemSlots * 8, &attr_set)) != AG_OK) break;
+      const int per_sm = smem > 32768 ? 3 : (smem > 16384 ? 6 : 8);
+      is_in_kernel<V, kMemberSmem><<<grid_for(n, kHThreads * kHUnroll, per_sm), kHThreads, smem, st>>>(v, valid, off, n, tm.t, nullptr, null_behavior, od, ov, nc);
+    } else {
+      is_in_kernel<V, kMemberTable><<<grid_for(n, kHThreads * kHUnroll, 8), kHThreads, 0, st>>>(v, valid, off, n, tm.t, nullptr, null_behavior, od, ov, nc);
+    }
     rc = check_launch("is_in_kernel");
   } while (0);
   tm.release(st);
@@ -229,28 +396,46 @@ ag_status is_in_dev(int bit_width, const void* vals, const uint8_t* valid, int64
   }
 }
 
+// columns above `small_rows` try a table of `small_slots` slots (4M x 16 B = 64 MB: L2-resident) first
+static std::atomic<long long> g_unique_small_rows{1ll << 21};
+static std::atomic<long long> g_unique_small_slots{1ll << 22};
+
 template <typename V>
 static ag_status unique_t(int bit_width, const void* vals, const uint8_t* valid, int64_t off, int64_t n, void* out, uint8_t* out_valid,
                           int64_t capacity, int64_t* d_out_len, cudaStream_t st) {
-  TableMem tm;
-  AG_TRY(tm.alloc(n, st));
+  const bool two = n > g_unique_small_rows.load(std::memory_order_relaxed);
+  const unsigned long long small_slots = (unsigned long long)g_unique_small_slots.load(std::memory_order_relaxed);
+  TableMem small_t, big_t;
   uint32_t* keep = nullptr;
-  ag_status rc = dev_alloc_async((void**)&keep, (size_t)((n + 31) / 32) * 4 + 64, st);
-  if (rc == AG_OK) {
-    do {
-      hash_insert_kernel<V><<<grid_for(n, kHThreads * 4, 8), kHThreads, 0, st>>>(reinterpret_cast<const V*>(vals), valid, off, n, tm.t);
+  ag_status rc = AG_OK;
+  do {
+    if (two) rc = small_t.alloc(0, small_slots, (unsigned)(small_slots / 2), st);
+    else rc = small_t.alloc(n, 1024, kNoCap, st);
+    if (rc != AG_OK) break;
+    if ((rc = small_t.clear(st)) != AG_OK) break;
+    if (two && (rc = big_t.alloc(n, 1024, kNoCap, st)) != AG_OK) break;
+    if ((rc = dev_alloc_async((void**)&keep, (size_t)((n + 31) / 32) * 4 + 64, st)) != AG_OK) break;
+    const V* v = reinterpret_cast<const V*>(vals);
+    const int grid = grid_for(n, kHThreads * kHUnroll, 8);
+    hash_insert_kernel<V><<<grid, kHThreads, 0, st>>>(v, valid, off, n, small_t.t, nullptr);
+    if ((rc = check_launch("hash_insert_kernel")) != AG_OK) break;
+    if (two) {
+      const unsigned* raised = small_t.t.special + 3;
+      if ((rc = big_t.clear(st, raised)) != AG_OK) break;
+      hash_insert_kernel<V><<<grid, kHThreads, 0, st>>>(v, valid, off, n, big_t.t, raised);
       if ((rc = check_launch("hash_insert_kernel")) != AG_OK) break;
-      unique_mark_kernel<V><<<grid_for(n, kHThreads * 4, 8), kHThreads, 0, st>>>(reinterpret_cast<const V*>(vals), valid, off, n, tm.t, keep);
-      if ((rc = check_launch("unique_mark_kernel")) != AG_OK) break;
-      if (out_valid) {
-        if (cudaMemsetAsync(out_valid, 0, (size_t)((capacity + 31) / 32) * 4, st) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "memset", __FILE__, __LINE__); break; }
-      }
-      rc = filter_primitive_dev(bit_width, vals, valid, off, reinterpret_cast<const uint8_t*>(keep), nullptr, 0, n, AG_DROP_NULLS, out, out_valid,
-                                capacity, d_out_len, st);
-    } while (0);
-    cudaFreeAsync(keep, st);
-  }
-  tm.release(st);
+    }
+    unique_mark_kernel<V><<<grid, kHThreads, 0, st>>>(v, valid, off, n, small_t.t, big_t.t, keep);
+    if ((rc = check_launch("unique_mark_kernel")) != AG_OK) break;
+    if (out_valid) {
+      if (cudaMemsetAsync(out_valid, 0, (size_t)((capacity + 31) / 32) * 4, st) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "memset", __FILE__, __LINE__); break; }
+    }
+    rc = filter_primitive_dev(bit_width, vals, valid, off, reinterpret_cast<const uint8_t*>(keep), nullptr, 0, n, AG_DROP_NULLS, out, out_valid,
+                              capacity, d_out_len, st);
+  } while (0);
+  if (keep) cudaFreeAsync(keep, st);
+  small_t.release(st);
+  big_t.release(st);
   return rc;
 }
 
@@ -281,6 +466,15 @@ extern "C" ag_status ag_is_in_dev(int bit_width, const void* d_vals, const uint8
   AG_TRY(ensure_init());
   return is_in_dev(bit_width, d_vals, d_valid, offset, n, d_set, d_set_valid, set_offset, set_n, null_behavior, d_out_data, d_out_valid, d_null_count,
                    resolve_stream(s));
+}
+
+extern "C" ag_status ag_unique_set_policy(int64_t small_rows, int64_t small_slots) {
+  if (small_rows < 0 || small_slots < 0) AG_FAIL(AG_ERR_INVALID, "ag_unique_set_policy: negative argument");
+  if (small_slots && (small_slots < 1024 || small_slots > (1ll << 31) || (small_slots & (small_slots - 1))))
+    AG_FAIL(AG_ERR_INVALID, "ag_unique_set_policy: small_slots must be a power of two in [1024, 2^31]");
+  g_unique_small_rows.store(small_rows ? small_rows : (1ll << 21), std::memory_order_relaxed);
+  g_unique_small_slots.store(small_slots ? small_slots : (1ll << 22), std::memory_order_relaxed);
+  return AG_OK;
 }
 
 extern "C" ag_status ag_unique_dev(int bit_width, const void* d_vals, const uint8_t* d_valid, int64_t offset, int64_t n, void* d_out,

@@ -8,19 +8,23 @@
 // with compareOrdered: ascending or descending, ties keep row order, -0.0 == +0.0; vector_sort_physical.go,
 // vector_sort_support.go:100-170).  Output: uint64 row indices, like the reference.
 //
-// Algorithm: least-significant-digit radix sort over (key', row) pairs, 8-bit digits.
+// Algorithm: least-significant-digit radix sort over (key, row) pairs, 8-bit digits.
 //   key' is an order-preserving unsigned image of the value (sign bias for signed ints; floats: flip all bits of
 //   negatives, set the sign bit of the rest, -0.0 folded onto +0.0), complemented for Descending so that an ascending
-//   stable sort of key' gives the descending order with ties still in row order.
-//   K0  one pass over the column: per-digit global histograms of the finite rows + class counts (finite / NaN / null)
-//       -> read back (2 KB) so the host can lay out the three regions and SKIP every digit on which all keys agree
-//       (a column of small integers needs one or two passes instead of eight);
-//   K1  class pass: stable 3-way partition of the rows into the region order above, materialising the pairs;
-//   K2+ one pass per remaining digit on the finite region: tile histogram (shared-memory atomics) -> per-bin scan over
-//       the tiles -> scatter with a stable in-tile rank (warp __match_any_sync groups + per-warp digit counters);
-//   K3  the row indices of the final pair buffer are widened to uint64 into `out`.
-// Roofline: HBM; per executed digit pass 8 (histogram read) + 12 + 12 bytes/row for 64-bit keys; the gathers are
-// never random (pairs move with their rows).  The API is synchronous in one spot: the 2 KB read-back after K0.
+//   stable sort of key' gives the descending order with ties still in row order.  The sorted key is
+//       key = (key' - min key') >> tz,   tz = trailing bits on which every finite key' agrees,
+//   still order preserving, and only ceil(bits(max - min) - tz) / 8) digits can differ: a column of small integers
+//   (whatever their sign), or of doubles holding integers, needs one to four passes instead of eight.
+//   K0  one pass over the column: min / max / OR of differences of key' over the finite rows + NaN and null counts
+//       -> read back (40 bytes) so the host can lay out the three regions and pick the digits;
+//   K1  class pass, only when the column has NaNs or nulls: stable 3-way partition of the rows into the region order
+//       above, materialising the pairs (a column without them feeds the first digit pass straight from the source);
+//   K2+ one pass per digit on the finite region: tile histogram (shared-memory atomics) -> per-bin scan over the tiles
+//       -> scatter with a stable in-tile rank (warp __match_any_sync groups + per-warp digit counters); the last
+//       pass writes the uint64 row indices straight into `out`.
+// Roofline: HBM; per digit pass 8 (histogram read) + 12 + 12 bytes/row for 64-bit keys (first pass from the source:
+// 8 + 8 + 12; last pass: 8 + 12 + 8); the gathers are never random (pairs move with their rows).  The API is synchronous
+// in one spot: the 40-byte read-back after K0.
 #include "common.cuh"
 
 #include <string.h>
@@ -77,36 +81,68 @@ __device__ __forceinline__ K sort_key(T v, int descending, int* cls) {
 // region index of a row class under the null placement: the class pass sorts by this "digit"
 __device__ __forceinline__ int class_digit(int cls /*0 finite,1 NaN,2 null*/, int nulls_first) { return nulls_first ? 2 - cls : cls; }
 
-// ---------------------------------------------------------------- K0: global histograms
-// hist layout: [sizeof(K)][256] digit counts of the FINITE rows, then 3 class counts (finite, NaN, null).
+// key = (key' - kmin) >> tz
+struct SortXform { unsigned long long kmin; int tz; };
+
+// ---------------------------------------------------------------- K0: statistics of key'
+// stats: [0] min, [1] max, [2] OR of (key' ^ key' of row 0) over the FINITE rows; [3] NaN rows, [4] null rows.
+// (Row 0 as the reference even when it is not finite: a bit then merely looks varying, which costs a pass, not a result.)
 template <typename T, typename K>
 __global__ void __launch_bounds__(kSoThreads)
-sort_prep_hist_kernel(const SortSource src, unsigned long long* __restrict__ hist) {
-  constexpr int ND = (int)sizeof(K);
-  __shared__ unsigned s_hist[ND * 256 + 4];
-  for (int i = threadIdx.x; i < ND * 256 + 4; i += kSoThreads) s_hist[i] = 0;
-  __syncthreads();
+sort_prep_kernel(const SortSource src, unsigned long long* __restrict__ stats) {
   const T* __restrict__ vals = reinterpret_cast<const T*>(src.vals) + src.voff;
+  int c0;
+  const K ref = sort_key<T, K>(vals[0], src.descending, &c0);
+  K mn = (K)~(K)0, mx = 0, vr = 0;
+  unsigned n_nan = 0, n_null = 0;
+#pragma unroll 4
   for (int64_t i = (int64_t)blockIdx.x * kSoThreads + threadIdx.x; i < src.n; i += (int64_t)gridDim.x * kSoThreads) {
     int cls;
     const K k = sort_key<T, K>(__ldcs(vals + i), src.descending, &cls);
     if (src.valid && !bit_is_set(src.valid, src.voff + i)) cls = 2;
-    atomicAdd(&s_hist[ND * 256 + cls], 1u);
-    if (cls == 0) {
-#pragma unroll
-      for (int d = 0; d < ND; ++d) atomicAdd(&s_hist[d * 256 + (int)((k >> (8 * d)) & 0xff)], 1u);
-    }
+    if (cls == 0) { mn = k < mn ? k : mn; mx = k > mx ? k : mx; vr |= k ^ ref; }
+    n_nan += cls == 1;
+    n_null += cls == 2;
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < ND * 256 + 3; i += kSoThreads)
-    if (s_hist[i]) atomicAdd(&hist[i], (unsigned long long)s_hist[i]);
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) {
+    const K omn = __shfl_xor_sync(0xffffffffu, mn, m), omx = __shfl_xor_sync(0xffffffffu, mx, m);
+    mn = omn < mn ? omn : mn; mx = omx > mx ? omx : mx;
+    vr |= __shfl_xor_sync(0xffffffffu, vr, m);
+    n_nan += __shfl_xor_sync(0xffffffffu, n_nan, m);
+    n_null += __shfl_xor_sync(0xffffffffu, n_null, m);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (mn <= mx) {
+      atomicMin(&stats[0], (unsigned long long)mn);
+      atomicMax(&stats[1], (unsigned long long)mx);
+      if (vr) atomicOr(&stats[2], (unsigned long long)vr);
+    }
+    if (n_nan) atomicAdd(&stats[3], (unsigned long long)n_nan);
+    if (n_null) atomicAdd(&stats[4], (unsigned long long)n_null);
+  }
 }
 
 // ---------------------------------------------------------------- shared pieces of a pass
 // tile_hist layout: [bin][tile] (one contiguous row per bin, scanned by one block per bin)
 __global__ void __launch_bounds__(kSoThreads)
-sort_scan_bins_kernel(unsigned* __restrict__ tile_hist, int64_t ntiles, const unsigned long long* __restrict__ bin_base) {
+sort_scan_bins_kernel(unsigned* __restrict__ tile_hist, int64_t ntiles, const unsigned* __restrict__ tot) {
   __shared__ unsigned long long s_w[kSoWarps];
+  __shared__ unsigned long long s_base;
+  // first position of this bin = rows of all lower bins (tot: per-bin totals of the pass, at most 256 of them)
+  {
+    unsigned long long v = (threadIdx.x < blockIdx.x) ? (unsigned long long)tot[threadIdx.x] : 0ull;   // blockIdx.x <= 255 < kSoThreads
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long b = 0;
+      for (int w = 0; w < kSoWarps; ++w) b += s_w[w];
+      s_base = b;
+    }
+    __syncthreads();
+  }
   unsigned* row = tile_hist + (int64_t)blockIdx.x * ntiles;
   const int64_t per = (ntiles + kSoThreads - 1) / kSoThreads;
   const int64_t lo = (int64_t)threadIdx.x * per, hi = lo + per < ntiles ? lo + per : ntiles;
@@ -121,7 +157,7 @@ sort_scan_bins_kernel(unsigned* __restrict__ tile_hist, int64_t ntiles, const un
   }
   if (lane == 31) s_w[threadIdx.x >> 5] = inc;
   __syncthreads();
-  unsigned long long base = bin_base[blockIdx.x];
+  unsigned long long base = s_base;
   for (int w = 0; w < (threadIdx.x >> 5); ++w) base += s_w[w];
   unsigned long long run = base + inc - sum;
   for (int64_t i = lo; i < hi; ++i) {
@@ -204,7 +240,7 @@ sort_class_hist_kernel(const SortSource src, unsigned* __restrict__ tile_hist, i
 
 template <typename T, typename K>
 __global__ void __launch_bounds__(kSoThreads)
-sort_class_scatter_kernel(const SortSource src, const unsigned* __restrict__ tile_off, int64_t ntiles, K* __restrict__ keys_out,
+sort_class_scatter_kernel(const SortSource src, const SortXform xf, const unsigned* __restrict__ tile_off, int64_t ntiles, K* __restrict__ keys_out,
                           unsigned* __restrict__ idx_out) {
   __shared__ unsigned s_cnt[kSoWarps * 256];
   __shared__ unsigned s_tot[256];
@@ -226,7 +262,7 @@ sort_class_scatter_kernel(const SortSource src, const unsigned* __restrict__ til
         int cls;
         key[e] = sort_key<T, K>(__ldcs(vals + i), src.descending, &cls);
         if (src.valid && !bit_is_set(src.valid, src.voff + i)) cls = 2;
-        if (cls) key[e] = 0;
+        key[e] = cls ? (K)0 : (K)((key[e] - (K)xf.kmin) >> xf.tz);
         digits[e] = class_digit(cls, src.nulls_first);
       }
     }
@@ -244,33 +280,56 @@ sort_class_scatter_kernel(const SortSource src, const unsigned* __restrict__ til
   }
 }
 
-// ---------------------------------------------------------------- K2: digit passes on the pair buffers
-template <typename K>
+// ---------------------------------------------------------------- K2: digit passes
+// kFromSource: the pass reads the column itself (no NaN / null rows: pair i is (key(vals[i]), i)), otherwise the pair
+// buffers of the previous pass.  T is only used with kFromSource.
+template <typename T, typename K, bool kFromSource>
+__device__ __forceinline__ K pass_key(const SortSource& src, const SortXform& xf, const K* __restrict__ keys, int64_t lo, int64_t i) {
+  if constexpr (kFromSource) {
+    int cls;
+    const K k = sort_key<T, K>(__ldcs(reinterpret_cast<const T*>(src.vals) + src.voff + i), src.descending, &cls);
+    return (K)((k - (K)xf.kmin) >> xf.tz);
+  } else {
+    return __ldcs(keys + lo + i);
+  }
+}
+
+// tot[256]: per-bin totals of the pass (zeroed by the host), accumulated per block and flushed once
+template <typename T, typename K, bool kFromSource>
 __global__ void __launch_bounds__(kSoThreads)
-sort_digit_hist_kernel(const K* __restrict__ keys, int64_t lo, int64_t n, int shift, unsigned* __restrict__ tile_hist, int64_t ntiles) {
+sort_digit_hist_kernel(const SortSource src, const SortXform xf, const K* __restrict__ keys, int64_t lo, int64_t n, int shift,
+                       unsigned* __restrict__ tile_hist, int64_t ntiles, unsigned* __restrict__ tot) {
   __shared__ unsigned s_h[kSoBins];
+  unsigned acc = 0;                      // thread b < 256: rows of digit b in this block's tiles
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     if (threadIdx.x < kSoBins) s_h[threadIdx.x] = 0;
     __syncthreads();
 #pragma unroll 4
     for (int e = 0; e < kSoPerThread; ++e) {
       const int64_t i = tile * kSoTile + e * kSoThreads + threadIdx.x;
-      if (i < n) atomicAdd(&s_h[(int)((__ldcs(keys + lo + i) >> shift) & 0xff)], 1u);
+      if (i < n) atomicAdd(&s_h[(int)((pass_key<T, K, kFromSource>(src, xf, keys, lo, i) >> shift) & 0xff)], 1u);
     }
     __syncthreads();
-    if (threadIdx.x < kSoBins) tile_hist[(int64_t)threadIdx.x * ntiles + tile] = s_h[threadIdx.x];
+    if (threadIdx.x < kSoBins) {
+      const unsigned c = s_h[threadIdx.x];
+      tile_hist[(int64_t)threadIdx.x * ntiles + tile] = c;
+      acc += c;
+    }
     __syncthreads();
   }
+  if (threadIdx.x < kSoBins && acc) atomicAdd(&tot[threadIdx.x], acc);
 }
 
 // The scatter stages the tile in shared memory in digit order first (position = exclusive bin offset inside the tile +
 // rows of the digit in earlier warps + rank), then walks the staged tile with consecutive threads: rows of one digit
 // are consecutive there AND consecutive in the destination, so the global writes are contiguous runs issued by
 // neighbouring lanes instead of 16 isolated 8-byte stores per bin.
-template <typename K>
+// kLast: the final pass writes the uint64 row indices into `out64` (positions are absolute) and drops the keys.
+template <typename T, typename K, bool kFromSource, bool kLast>
 __global__ void __launch_bounds__(kSoThreads)
-sort_digit_scatter_kernel(const K* __restrict__ keys_in, const unsigned* __restrict__ idx_in, int64_t lo, int64_t n, int shift,
-                          const unsigned* __restrict__ tile_off, int64_t ntiles, K* __restrict__ keys_out, unsigned* __restrict__ idx_out) {
+sort_digit_scatter_kernel(const SortSource src, const SortXform xf, const K* __restrict__ keys_in, const unsigned* __restrict__ idx_in, int64_t lo,
+                          int64_t n, int shift, const unsigned* __restrict__ tile_off, int64_t ntiles, K* __restrict__ keys_out,
+                          unsigned* __restrict__ idx_out, unsigned long long* __restrict__ out64) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   K* s_key = reinterpret_cast<K*>(s_dyn);                                   // [kSoTile] staged keys, digit order
   unsigned* s_idx = reinterpret_cast<unsigned*>(s_dyn + sizeof(K) * kSoTile);  // [kSoTile]
@@ -294,8 +353,8 @@ sort_digit_scatter_kernel(const K* __restrict__ keys_in, const unsigned* __restr
       live[e] = i < n;
       key[e] = 0; idx[e] = 0; digits[e] = 0;
       if (live[e]) {
-        key[e] = __ldcs(keys_in + lo + i);
-        idx[e] = __ldcs(idx_in + lo + i);
+        key[e] = pass_key<T, K, kFromSource>(src, xf, keys_in, lo, i);
+        idx[e] = kFromSource ? (unsigned)i : __ldcs(idx_in + lo + i);
         digits[e] = (int)((key[e] >> shift) & 0xff);
       }
     }
@@ -332,8 +391,12 @@ sort_digit_scatter_kernel(const K* __restrict__ keys_in, const unsigned* __restr
       const K k = s_key[j];
       const int d = (int)((k >> shift) & 0xff);
       const int64_t pos = lo + s_base[d] + (unsigned)(j - (int)s_excl[d]);
-      keys_out[pos] = k;
-      idx_out[pos] = s_idx[j];
+      if constexpr (kLast) {
+        __stcs(out64 + pos, (unsigned long long)s_idx[j]);
+      } else {
+        keys_out[pos] = k;
+        idx_out[pos] = s_idx[j];
+      }
     }
     __syncthreads();
   }
@@ -344,90 +407,111 @@ sort_widen_kernel(const unsigned* __restrict__ idx, int64_t n, unsigned long lon
   for (int64_t i = (int64_t)blockIdx.x * kSoThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kSoThreads) out[i] = idx[i];
 }
 __global__ void __launch_bounds__(kSoThreads)
-sort_copy_u32_kernel(const unsigned* __restrict__ src, unsigned* __restrict__ dst, int64_t lo, int64_t hi) {
-  for (int64_t i = lo + (int64_t)blockIdx.x * kSoThreads + threadIdx.x; i < hi; i += (int64_t)gridDim.x * kSoThreads) dst[i] = src[i];
+sort_iota_kernel(int64_t n, unsigned long long* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * kSoThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kSoThreads) out[i] = (unsigned long long)i;
+}
+
+template <typename T, typename K, bool kFromSource>
+static ag_status launch_digit_pass(const SortSource& src, const SortXform& xf, const K* keys_in, const unsigned* idx_in, int64_t lo, int64_t fn, int shift,
+                                   unsigned* tile_hist, unsigned* tot, K* keys_out, unsigned* idx_out, unsigned long long* out64, bool last,
+                                   cudaStream_t st) {
+  constexpr size_t kScatterSmem = (sizeof(K) + 4) * (size_t)kSoTile + (size_t)kSoWarps * 256 * 4;
+  static std::atomic<unsigned> attr_a{0u}, attr_b{0u};   // per instantiation, one bit per device
+  AG_TRY(ensure_dynamic_smem((const void*)sort_digit_scatter_kernel<T, K, kFromSource, false>, (int)kScatterSmem, &attr_a));
+  AG_TRY(ensure_dynamic_smem((const void*)sort_digit_scatter_kernel<T, K, kFromSource, true>, (int)kScatterSmem, &attr_b));
+  const int64_t ftiles = (fn + kSoTile - 1) / kSoTile;
+  const int fgrid = grid_for(fn, kSoTile, 8);
+  sort_digit_hist_kernel<T, K, kFromSource><<<fgrid, kSoThreads, 0, st>>>(src, xf, keys_in, lo, fn, shift, tile_hist, ftiles, tot);
+  AG_TRY(check_launch("sort_digit_hist_kernel"));
+  sort_scan_bins_kernel<<<256, kSoThreads, 0, st>>>(tile_hist, ftiles, tot);
+  AG_TRY(check_launch("sort_scan_bins_kernel"));
+  if (last)
+    sort_digit_scatter_kernel<T, K, kFromSource, true><<<fgrid, kSoThreads, kScatterSmem, st>>>(src, xf, keys_in, idx_in, lo, fn, shift, tile_hist, ftiles, keys_out, idx_out, out64);
+  else
+    sort_digit_scatter_kernel<T, K, kFromSource, false><<<fgrid, kSoThreads, kScatterSmem, st>>>(src, xf, keys_in, idx_in, lo, fn, shift, tile_hist, ftiles, keys_out, idx_out, out64);
+  return check_launch("sort_digit_scatter_kernel");
 }
 
 template <typename T, typename K>
 static ag_status sort_indices_t(const SortSource& src, unsigned long long* d_out, int64_t* nulls_out, int64_t* nans_out, cudaStream_t st) {
   constexpr int ND = (int)sizeof(K);
-  constexpr size_t kScatterSmem = (sizeof(K) + 4) * (size_t)kSoTile + (size_t)kSoWarps * 256 * 4;
-  static std::atomic<unsigned> attr_set{0u};   // per K, one bit per device
-  AG_TRY(ensure_dynamic_smem((const void*)sort_digit_scatter_kernel<K>, (int)kScatterSmem, &attr_set));
   const int64_t n = src.n;
   const int64_t ntiles = (n + kSoTile - 1) / kSoTile;
-  const size_t hist_words = (size_t)ND * 256 + 3;
   const size_t key_bytes = ((size_t)n * sizeof(K) + 255) & ~(size_t)255;
   const size_t idx_bytes = ((size_t)n * 4 + 255) & ~(size_t)255;
   const size_t th_bytes = ((size_t)256 * ntiles * 4 + 255) & ~(size_t)255;
-  const size_t head = (hist_words * 8 + 256 * 8 + 255) & ~(size_t)255;
+  const size_t head = (8 * 8 + (size_t)(ND + 1) * 256 * 4 + 255) & ~(size_t)255;   // statistics, then one row of bin totals per pass (+ the class pass)
   void* scratch = nullptr;
   AG_TRY(dev_alloc_async(&scratch, head + 2 * key_bytes + 2 * idx_bytes + th_bytes, st));
   char* base = reinterpret_cast<char*>(scratch);
-  unsigned long long* d_hist = reinterpret_cast<unsigned long long*>(base);
-  unsigned long long* d_binbase = d_hist + hist_words;
+  unsigned long long* d_stats = reinterpret_cast<unsigned long long*>(base);
+  unsigned* d_tot = reinterpret_cast<unsigned*>(base + 64);
   K* keys[2] = {reinterpret_cast<K*>(base + head), reinterpret_cast<K*>(base + head + key_bytes)};
   unsigned* idx[2] = {reinterpret_cast<unsigned*>(base + head + 2 * key_bytes), reinterpret_cast<unsigned*>(base + head + 2 * key_bytes + idx_bytes)};
   unsigned* tile_hist = reinterpret_cast<unsigned*>(base + head + 2 * key_bytes + 2 * idx_bytes);
   ag_status rc = AG_OK;
-  std::vector<unsigned long long> h((size_t)hist_words);
   do {
-    if (cudaMemsetAsync(d_hist, 0, hist_words * 8, st) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "memset", __FILE__, __LINE__); break; }
+    unsigned long long h[8] = {~0ull, 0, 0, 0, 0, 0, 0, 0};
+    if (cudaMemsetAsync(base, 0, head, st) != cudaSuccess ||
+        cudaMemcpyAsync(d_stats, h, 8, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "statistics init", __FILE__, __LINE__); break; }
     const int grid = grid_for(n, kSoTile, 8);
-    sort_prep_hist_kernel<T, K><<<grid, kSoThreads, 0, st>>>(src, d_hist);
-    if ((rc = check_launch("sort_prep_hist_kernel")) != AG_OK) break;
-    if (cudaMemcpyAsync(h.data(), d_hist, hist_words * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-        cudaStreamSynchronize(st) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "histogram read-back", __FILE__, __LINE__); break; }
-    const unsigned long long n_fin = h[(size_t)ND * 256], n_nan = h[(size_t)ND * 256 + 1], n_null = h[(size_t)ND * 256 + 2];
+    sort_prep_kernel<T, K><<<grid, kSoThreads, 0, st>>>(src, d_stats);
+    if ((rc = check_launch("sort_prep_kernel")) != AG_OK) break;
+    if (cudaMemcpyAsync(h, d_stats, 5 * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "statistics read-back", __FILE__, __LINE__); break; }
+    const unsigned long long n_nan = h[3], n_null = h[4], n_fin = (unsigned long long)n - n_nan - n_null;
     if (nulls_out) *nulls_out = (int64_t)n_null;
     if (nans_out) *nans_out = (int64_t)n_nan;
-    // region layout in class-digit order
-    unsigned long long cls_cnt[3];
-    cls_cnt[src.nulls_first ? 2 : 0] = n_fin; cls_cnt[1] = n_nan; cls_cnt[src.nulls_first ? 0 : 2] = n_null;
-    unsigned long long bb[256] = {0};
-    bb[0] = 0; bb[1] = cls_cnt[0]; bb[2] = cls_cnt[0] + cls_cnt[1];
-    const int64_t fin_lo = (int64_t)(src.nulls_first ? n_null + n_nan : 0);
-    // ---- K1: class pass -> pairs in buffer 0
-    if (cudaMemcpyAsync(d_binbase, bb, 3 * 8, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "bin bases", __FILE__, __LINE__); break; }
-    sort_class_hist_kernel<T, K><<<grid, kSoThreads, 0, st>>>(src, tile_hist, ntiles);
-    if ((rc = check_launch("sort_class_hist_kernel")) != AG_OK) break;
-    sort_scan_bins_kernel<<<3, kSoThreads, 0, st>>>(tile_hist, ntiles, d_binbase);
-    if ((rc = check_launch("sort_scan_bins_kernel")) != AG_OK) break;
-    sort_class_scatter_kernel<T, K><<<grid, kSoThreads, 0, st>>>(src, tile_hist, ntiles, keys[0], idx[0]);
-    if ((rc = check_launch("sort_class_scatter_kernel")) != AG_OK) break;
-    // ---- K2: digit passes over the finite region, skipping digits on which every finite key agrees
-    int cur = 0;
+    // the key transform and the digits that can differ
+    SortXform xf{0, 0};
+    int nd = 0;
+    if (n_fin > 1 && h[1] > h[0]) {
+      xf.kmin = h[0];
+      while (xf.tz < 8 * ND - 1 && !((h[2] >> xf.tz) & 1ull)) ++xf.tz;     // h[2] != 0 here (max > min)
+      unsigned long long r = (h[1] - h[0]) >> xf.tz;
+      int bits = 0;
+      while (r) { ++bits; r >>= 1; }
+      nd = (bits + 7) / 8;
+    }
+    const bool classes = (n_nan + n_null) > 0;
     const int64_t fn = (int64_t)n_fin;
-    const int64_t ftiles = (fn + kSoTile - 1) / kSoTile;
-    for (int d = 0; d < ND && fn > 1; ++d) {
-      bool trivial = false;
-      unsigned long long run = 0;
-      for (int b = 0; b < 256; ++b) {
-        if (h[(size_t)d * 256 + b] == n_fin) trivial = true;
-        bb[b] = run;
-        run += h[(size_t)d * 256 + b];
-      }
-      if (trivial) continue;
-      // cudaMemcpyAsync from pageable memory is staged before it returns, so `bb` may be reused next iteration
-      if (cudaMemcpyAsync(d_binbase, bb, 256 * 8, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "bin bases", __FILE__, __LINE__); break; }
-      const int fgrid = grid_for(fn, kSoTile, 8);
-      sort_digit_hist_kernel<K><<<fgrid, kSoThreads, 0, st>>>(keys[cur], fin_lo, fn, 8 * d, tile_hist, ftiles);
-      if ((rc = check_launch("sort_digit_hist_kernel")) != AG_OK) break;
-      sort_scan_bins_kernel<<<256, kSoThreads, 0, st>>>(tile_hist, ftiles, d_binbase);
+    const int64_t fin_lo = (int64_t)(src.nulls_first ? n_null + n_nan : 0);
+    if (classes) {
+      // ---- K1: class pass -> pairs in buffer 0, region layout in class-digit order
+      unsigned cls_cnt[3];
+      cls_cnt[src.nulls_first ? 2 : 0] = (unsigned)n_fin; cls_cnt[1] = (unsigned)n_nan; cls_cnt[src.nulls_first ? 0 : 2] = (unsigned)n_null;
+      unsigned* d_cls_tot = d_tot + (size_t)ND * 256;
+      if (cudaMemcpyAsync(d_cls_tot, cls_cnt, sizeof(cls_cnt), cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "class totals", __FILE__, __LINE__); break; }
+      sort_class_hist_kernel<T, K><<<grid, kSoThreads, 0, st>>>(src, tile_hist, ntiles);
+      if ((rc = check_launch("sort_class_hist_kernel")) != AG_OK) break;
+      sort_scan_bins_kernel<<<3, kSoThreads, 0, st>>>(tile_hist, ntiles, d_cls_tot);
       if ((rc = check_launch("sort_scan_bins_kernel")) != AG_OK) break;
-      sort_digit_scatter_kernel<K><<<fgrid, kSoThreads, kScatterSmem, st>>>(keys[cur], idx[cur], fin_lo, fn, 8 * d, tile_hist, ftiles, keys[cur ^ 1], idx[cur ^ 1]);
-      if ((rc = check_launch("sort_digit_scatter_kernel")) != AG_OK) break;
-      cur ^= 1;
+      sort_class_scatter_kernel<T, K><<<grid, kSoThreads, 0, st>>>(src, xf, tile_hist, ntiles, keys[0], idx[0]);
+      if ((rc = check_launch("sort_class_scatter_kernel")) != AG_OK) break;
+    }
+    // ---- K2: digit passes over the finite region
+    int cur = 0;
+    for (int d = 0; d < nd; ++d) {
+      const bool last = d == nd - 1;
+      if (d == 0 && !classes)
+        rc = launch_digit_pass<T, K, true>(src, xf, nullptr, nullptr, 0, fn, 0, tile_hist, d_tot, keys[0], idx[0], d_out, last, st);
+      else
+        rc = launch_digit_pass<K, K, false>(src, xf, keys[cur], idx[cur], fin_lo, fn, 8 * d, tile_hist, d_tot + (size_t)d * 256, keys[cur ^ 1], idx[cur ^ 1], d_out, last, st);
+      if (rc != AG_OK) break;
+      if (!(d == 0 && !classes)) cur ^= 1;     // a source pass writes buffer 0
     }
     if (rc != AG_OK) break;
-    // NaN / null rows stayed in buffer 0
-    if (cur == 1 && (n_nan + n_null) > 0) {
+    if (nd == 0) {
+      // every finite key equal (or at most one finite row): the class order is the answer
+      if (classes) sort_widen_kernel<<<grid_for(n, kSoThreads * 8, 8), kSoThreads, 0, st>>>(idx[0], n, d_out);
+      else sort_iota_kernel<<<grid_for(n, kSoThreads * 8, 8), kSoThreads, 0, st>>>(n, d_out);
+      rc = check_launch("sort_widen_kernel");
+    } else if (classes) {
+      // NaN / null rows stayed in buffer 0
       const int64_t olo = src.nulls_first ? 0 : fn, ohi = src.nulls_first ? fin_lo : n;
-      sort_copy_u32_kernel<<<grid_for(ohi - olo, kSoThreads * 8, 8), kSoThreads, 0, st>>>(idx[0], idx[1], olo, ohi);
-      if ((rc = check_launch("sort_copy_u32_kernel")) != AG_OK) break;
+      sort_widen_kernel<<<grid_for(ohi - olo, kSoThreads * 8, 8), kSoThreads, 0, st>>>(idx[0] + olo, ohi - olo, d_out + olo);
+      rc = check_launch("sort_widen_kernel");
     }
-    sort_widen_kernel<<<grid_for(n, kSoThreads * 8, 8), kSoThreads, 0, st>>>(idx[cur], n, d_out);
-    rc = check_launch("sort_widen_kernel");
   } while (0);
   const ag_status frc = dev_free_async(scratch, st);
   return rc != AG_OK ? rc : frc;

@@ -521,6 +521,10 @@ ag_status ag_unique(int bit_width, const void* vals, const uint8_t* valid, int64
                     void* out, uint8_t* out_valid, int64_t* out_len, int64_t* out_nulls);
 ag_status ag_unique_dev(int bit_width, const void* d_vals, const uint8_t* d_valid, int64_t offset, int64_t n,
                         void* d_out, uint8_t* d_out_valid, int64_t capacity, int64_t* d_out_len, ag_stream_t s);
+/* unique's table policy: a column of more than `small_rows` rows (default 2^21) is first inserted into a table of
+ * `small_slots` slots (a power of two, default 2^22 = 64 MB, L2-resident); the full-size table (2n slots) is filled only
+ * when more than small_slots/2 distinct values turn up — decided on the device, never changes a result.  0 = default. */
+ag_status ag_unique_set_policy(int64_t small_rows, int64_t small_slots);
 
 /* ================================================================================= *
  * sort_indices, one fixed-width column — replaces kernels.SortIndices for a single

@@ -132,3 +132,75 @@ def test_gpu_set_lookup_100m_rows(ag):
     hv = v.buf.to_numpy(np.int64, 1_000_000)
     _, first = np.unique(hv, return_index=True)
     assert k == 100 and np.array_equal(out.buf.to_numpy(np.int64, k), hv[np.sort(first)])
+
+
+@gpu
+@pytest.mark.parametrize("dt", [np.int64, np.uint32, np.float64, np.uint16, np.int8], ids=lambda d: np.dtype(d).name)
+def test_gpu_is_in_every_probe_path(ag, cpu, dt):
+    """The three membership structures of is_in_kernel — the shared-memory table at load factor <= 1/8 (few hundred
+    values) and <= 1/2 (a few thousand), the HBM table (tens of thousands), the bitmap of 1-/2-byte values — against the
+    oracle, with nulls on both sides, the all-ones key in the set, and every NullMatchingBehavior."""
+    dt = np.dtype(dt); bw = WIDTHS[dt.itemsize]
+    rng = np.random.default_rng(7 + dt.itemsize)
+    n = 200_003
+    for sn in (300, 3000, 20_000):
+        if dt.kind == "f":
+            v = rng.integers(-40_000, 40_000, n).astype(dt); s = rng.integers(-40_000, 40_000, sn).astype(dt)
+            v[:8] = [np.nan, -0.0, 0.0, np.inf, -np.inf, np.nan, 1.5, -1.5]; s[:3] = [np.nan, -0.0, np.inf]
+        else:
+            info = np.iinfo(dt)
+            lo, hi = max(info.min, -40_000), min(info.max, 40_000)
+            v = rng.integers(lo, hi, n, endpoint=True).astype(dt); s = rng.integers(lo, hi, sn, endpoint=True).astype(dt)
+            v[:4] = [info.max, info.min, info.max, 0]; s[:2] = [info.max, 0]
+            if dt.kind == "u" or dt.itemsize == 8:
+                v[4] = dt.type(-1) if dt.kind == "i" else info.max     # the all-ones byte pattern
+                s[2] = v[4]
+        valid = rng.random(n) >= 0.1; svalid = rng.random(sn) >= 0.01
+        vb, sb = pack_bits(valid, 5), pack_bits(svalid, 2)
+        vv = np.concatenate([np.zeros(5, dtype=dt), v]); ss = np.concatenate([np.zeros(2, dtype=dt), s])
+        for matching in range(4):
+            wd, wv, wn = oracle_is_in(cpu, bw, vv, vb, 5, n, ss, sb, 2, sn, matching)
+            gd = np.zeros(n // 8 + 8, dtype=np.uint8); gv = np.zeros(n // 8 + 8, dtype=np.uint8); gn = C.c_int64()
+            ag.call("ag_is_in", bw, ptr(vv), ptr(vb), 5, n, ptr(ss), ptr(sb), 2, sn, matching, ptr(gd), ptr(gv), C.byref(gn))
+            assert np.array_equal(unpack_bits(gd, 0, n), wd) and np.array_equal(unpack_bits(gv, 0, n), wv) and gn.value == wn, (dt.name, sn, matching)
+
+
+@gpu
+def test_gpu_unique_small_table_then_overflow(ag, cpu):
+    """unique's two-table scheme: with the policy forced down to a 1024-slot first table, columns below its capacity
+    (512 distinct values) finish there and columns above it raise the overflow word and are redone on the full-size
+    table — same answers as the oracle either way; then the shipped policy at 6M rows (10 / 3M distinct values)."""
+    rng = np.random.default_rng(99)
+    ag.call("ag_unique_set_policy", 1000, 1024)
+    try:
+        for dt in (np.int64, np.uint32, np.float64, np.uint8):
+            dt = np.dtype(dt); bw = WIDTHS[dt.itemsize]
+            for n in (1001, 70_001):
+                for card in (5, 400, 520, 3000):
+                    for p_null in (0.0, 0.2):
+                        hi = min(card, 255) if dt.itemsize == 1 else card
+                        v = rng.integers(0, hi, n).astype(dt)
+                        if dt.kind == "u":
+                            v[rng.integers(0, n, 3)] = np.iinfo(dt).max      # the all-ones key lives outside the table
+                        valid = rng.random(n) >= p_null
+                        vb = pack_bits(valid, 3) if p_null else None
+                        vv = np.concatenate([np.zeros(3, dtype=dt), v])
+                        wo, wov, wnn = oracle_unique(cpu, bw, vv, vb, 3, n)
+                        go = np.zeros(n, dtype=dt); gov = np.zeros(n // 8 + 8, dtype=np.uint8) if p_null else None
+                        gl, gnn = C.c_int64(), C.c_int64()
+                        ag.call("ag_unique", bw, ptr(vv), ptr(vb), 3, n, ptr(go), ptr(gov), C.byref(gl), C.byref(gnn))
+                        assert gl.value == wo.size, (dt.name, n, card, p_null)
+                        if p_null:
+                            assert np.array_equal(unpack_bits(gov, 0, gl.value), wov) and gnn.value == wnn
+                        assert go[:gl.value][wov].tobytes() == wo[wov].tobytes(), (dt.name, n, card, p_null)
+    finally:
+        ag.call("ag_unique_set_policy", 0, 0)
+    n = 6_000_000
+    for card in (10, 3_000_000):
+        v = rng.integers(-card // 2, card // 2, n).astype(np.int64)
+        dv, out, ln = Dev(v), Dev(nbytes=n * 8), Dev(np.zeros(2, dtype=np.int64))
+        ag.call("ag_unique_dev", 64, dv.ptr, None, 0, n, out.ptr, None, n, ln.ptr, None)
+        ag.call("ag_stream_sync", None)
+        _, first = np.unique(v, return_index=True)
+        k = int(ln.get()[0])
+        assert k == first.size and np.array_equal(out.buf.to_numpy(np.int64, k), v[np.sort(first)]), card

@@ -174,3 +174,44 @@ def test_gpu_100m_rows_properties(ag):
     ag.call("ag_sort_indices_dev", N.INT64, v.ptr, None, 0, m, 0, 0, out.ptr, C.byref(nn), C.byref(na), None)
     ag.call("ag_stream_sync", None)
     assert np.array_equal(out.buf.to_numpy(np.uint64, m), want)
+
+
+@gpu
+def test_gpu_key_range_reduction(ag, cpu):
+    """The sorted key is (key' - min) >> (trailing bits every key shares): columns built to stress that transform —
+    values straddling zero (the sign-biased image straddles 2^63), values packed against the type's limits, doubles
+    holding integers (32 constant low mantissa bits), multiples of 2^k, all rows equal, two distinct values, one finite row
+    among nulls — with and without NaN / null rows (class pass on / off), every order and placement."""
+    rng = np.random.default_rng(4242)
+    n = 50_021
+    cols = []
+    for dt in (np.int64, np.int32, np.int8):
+        info = np.iinfo(dt)
+        cols += [(N.INT64 if dt is np.int64 else N.INT32 if dt is np.int32 else N.INT8, c) for c in (
+            rng.integers(-100, 100, n).astype(dt),
+            (info.max - rng.integers(0, 100, n)).astype(dt),
+            (info.min + rng.integers(0, 100, n)).astype(dt),
+            np.where(rng.random(n) < 0.5, info.min, info.max).astype(dt),
+            np.full(n, -7, dtype=dt),
+        )]
+    cols += [(N.INT64, (rng.integers(-3000, 3000, n) << 20).astype(np.int64)),
+             (N.UINT64, (np.uint64(2**64 - 1) - rng.integers(0, 70_000, n).astype(np.uint64))),
+             (N.UINT64, rng.integers(0, 2**63, n).astype(np.uint64) * np.uint64(2)),
+             (N.UINT16, rng.integers(65_000, 65_536, n).astype(np.uint16)),
+             (N.FLOAT64, rng.integers(-(1 << 20), 1 << 20, n).astype(np.float64)),
+             (N.FLOAT64, rng.integers(-5, 5, n).astype(np.float64) * 0.0),          # -0.0 and +0.0 only: one key
+             (N.FLOAT32, rng.integers(-300, 300, n).astype(np.float32) * np.float32(0.5)),
+             (N.FLOAT64, np.where(rng.random(n) < 0.5, -np.inf, np.inf))]
+    for t, v in cols:
+        for p_null in (0.0, 0.3, 0.9999):
+            valid = rng.random(n) >= p_null
+            vv = v.copy()
+            if vv.dtype.kind == "f" and p_null:
+                vv[rng.integers(0, n, 50)] = np.nan
+            bits = pack_bits(valid, 1) if p_null else None
+            col = np.concatenate([np.zeros(1 if p_null else 0, dtype=vv.dtype), vv])
+            for order in (0, 1):
+                for placement in (0, 1):
+                    want, wn, wa = oracle_sort(cpu, t, col, bits, 1 if p_null else 0, n, order, placement)
+                    got, gn, ga = gpu_sort(ag, t, col, bits, 1 if p_null else 0, n, order, placement, True)
+                    assert np.array_equal(got, want) and (gn, ga) == (wn, wa), (TYPE_NAME[t], str(vv[:3]), p_null, order, placement)
