@@ -13,8 +13,8 @@
 // emitted iff it is the first row of its key, and the emitted rows are compacted in row order by the filter kernel
 // (filter.cu) — so the output order is the reference's and does not depend on the order in which threads reached the
 // table.
-//   is_in : value sets up to 4096 entries are probed in shared memory (8192 key slots = 64 KB, load factor <= 1/8 for
-//           the usual few-hundred-value set, two slots per 128-bit read); 1- and 2-byte values skip hashing altogether:
+//   is_in : value sets up to 4096 entries are probed in shared memory (at most 8192 key slots = 64 KB, load factor <= 1/4
+//           for sets up to 2048 values, two slots per 128-bit read); 1- and 2-byte values skip hashing altogether:
 //           the set becomes a 256 / 65536-bit membership bitmap.  Larger sets are probed in HBM / L2.
 //   unique: a column of more than 2M rows first runs against a 4M-slot table that stays L2-resident (64 MB); only when
 //           more than 2M distinct values turn up does the insert raise an overflow word, and the full-size table
@@ -68,7 +68,8 @@ __device__ __forceinline__ void lower_row(unsigned* p, unsigned seen, unsigned r
   if (seen > row) atomicMin(p, row);
 }
 
-__device__ __forceinline__ void table_insert(const HashTable& t, unsigned long long key, unsigned row) {
+// returns true when this call created the key's slot
+__device__ __forceinline__ bool table_insert(const HashTable& t, unsigned long long key, unsigned row) {
   unsigned long long h = hash_slot(key, t.shift);
   unsigned probes = 0;
   while (true) {
@@ -76,22 +77,22 @@ __device__ __forceinline__ void table_insert(const HashTable& t, unsigned long l
     const ulonglong2 raw = __ldcg(reinterpret_cast<const ulonglong2*>(s));   // key and first row in one L2 request
     unsigned long long cur = raw.x;
     unsigned seen = (unsigned)raw.y;
+    bool made = false;
     if (cur == kEmptyKey) {
       cur = atomicCAS(&s->key, kEmptyKey, key);
-      if (cur == kEmptyKey) {
-        seen = kNoRow;
-        // special[2] is cleared to 0xffffffff: old + 2 (mod 2^32) is the number of keys now in the table
-        if (t.cap != kNoCap && atomicAdd(&t.special[2], 1u) + 2u > t.cap) *reinterpret_cast<volatile unsigned*>(&t.special[3]) = 1u;
-        cur = key;
-      } else if (cur == key) {
-        seen = kNoRow;     // somebody else created it just now: its first row is not in `raw`
-      }
+      if (cur == kEmptyKey) { made = true; seen = kNoRow; cur = key; }
+      else if (cur == key) seen = kNoRow;     // somebody else created it just now: its first row is not in `raw`
     }
-    if (cur == key) { lower_row(&s->first, seen, row); return; }
+    if (cur == key) { lower_row(&s->first, seen, row); return made; }
     h = (h + 1) & t.mask;
-    // a capped table can fill up completely while the inserts that were in flight when the cap was crossed finish:
-    // the overflow word is raised before that can happen (cap = half the slots), so a long probe checks it and gives up
-    if (t.cap != kNoCap && ((++probes & 7u) == 0u) && overflowed(t)) return;
+    // a capped table can fill up completely while the inserts that were in flight when the cap was crossed finish
+    if (t.cap != kNoCap && ((++probes & 7u) == 0u)) {
+      if (overflowed(t)) return false;
+      // a probe this long at load factor <= 1/2 means the table has filled up behind the counter (the lanes that
+      // created the last keys report them only after their warp step, and a lane spinning here would keep its own
+      // warp from ever reporting): raise the word from here
+      if (probes >= 1024u) { *reinterpret_cast<volatile unsigned*>(&t.special[3]) = 1u; return false; }
+    }
   }
 }
 // lowest row that carried `key`, kNoRow when absent (the table is complete: plain cached loads)
@@ -130,23 +131,40 @@ hash_insert_kernel(const V* __restrict__ vals, const uint8_t* __restrict__ valid
     if (__any_sync(0xffffffffu, t.cap != kNoCap && overflowed(t))) return;   // the small table is being abandoned (warp-uniform exit)
     V x[kHUnroll];
     int kind[kHUnroll];                                  // 0 nothing, 1 value, 2 null
+    if (!valid && ((w0 + kHUnroll) << 5) <= n) {         // interior, no nulls: unconditional loads
+      const V* __restrict__ p = vals + off + (w0 << 5) + lane;
 #pragma unroll
-    for (int k = 0; k < kHUnroll; ++k) {
-      const int64_t i = ((w0 + k) << 5) + lane;
-      kind[k] = i < n ? ((valid && !bit_is_set(valid, off + i)) ? 2 : 1) : 0;
-      x[k] = kind[k] == 1 ? __ldcs(vals + off + i) : V(0);
+      for (int k = 0; k < kHUnroll; ++k) { x[k] = __ldcs(p + 32 * k); kind[k] = 1; }
+    } else {
+#pragma unroll
+      for (int k = 0; k < kHUnroll; ++k) {
+        const int64_t i = ((w0 + k) << 5) + lane;
+        kind[k] = i < n ? ((valid && !bit_is_set(valid, off + i)) ? 2 : 1) : 0;
+        x[k] = kind[k] == 1 ? __ldcs(vals + off + i) : V(0);
+      }
     }
 #pragma unroll
     for (int k = 0; k < kHUnroll; ++k) {
       const unsigned row = (unsigned)(((w0 + k) << 5) + lane);
       const unsigned long long key = (unsigned long long)x[k];
       const int cs = warp_cache_slot(key);
+      const bool ones = sizeof(V) == 8 && key == kEmptyKey;     // narrower values zero-extend: never all ones
       if (kind[k] == 2) lower_row(&t.special[1], *reinterpret_cast<volatile unsigned*>(&t.special[1]), row);
-      else if (kind[k] == 1 && key == kEmptyKey) lower_row(&t.special[0], *reinterpret_cast<volatile unsigned*>(&t.special[0]), row);
-      const bool go = kind[k] == 1 && key != kEmptyKey && cache[cs] != key;
+      else if (kind[k] == 1 && ones) lower_row(&t.special[0], *reinterpret_cast<volatile unsigned*>(&t.special[0]), row);
+      const bool go = kind[k] == 1 && !ones && cache[cs] != key;
       __syncwarp();
-      if (go) { table_insert(t, key, row); cache[cs] = key; }
+      bool made = false;
+      if (go) { made = table_insert(t, key, row); cache[cs] = key; }
       __syncwarp();
+      if (t.cap != kNoCap) {
+        // distinct keys so far, one atomic per warp step (a column of all-distinct values would otherwise put 2M
+        // atomics on one word before the cap stops it: 2.9 ms).  special[2] is cleared to 0xffffffff = count - 1.
+        const unsigned m = __ballot_sync(0xffffffffu, made);
+        if (lane == 0 && m) {
+          const unsigned c = (unsigned)__popc(m);
+          if (atomicAdd(&t.special[2], c) + 1u + c > t.cap) *reinterpret_cast<volatile unsigned*>(&t.special[3]) = 1u;
+        }
+      }
     }
   }
 }
@@ -198,7 +216,7 @@ is_in_kernel(const V* __restrict__ vals, const uint8_t* __restrict__ valid, int6
       const unsigned* sb = reinterpret_cast<const unsigned*>(s_keys);
       return (sb[(unsigned)key >> 5] >> ((unsigned)key & 31)) & 1u;
     }
-    if (key == kEmptyKey) return set_has_ones;
+    if (sizeof(V) == 8 && key == kEmptyKey) return set_has_ones;      // narrower values zero-extend: never all ones
     unsigned long long h = hash_slot(key, t.shift);
     while (true) {
       unsigned long long k0, k1;
@@ -218,7 +236,28 @@ is_in_kernel(const V* __restrict__ vals, const uint8_t* __restrict__ valid, int6
   const int64_t warp0 = ((int64_t)blockIdx.x * kHThreads + threadIdx.x) >> 5;
   const int64_t warps = ((int64_t)gridDim.x * kHThreads) >> 5;
   unsigned long long nulls = 0;
+  const bool miss_is_null = null_behavior == AG_NULL_INCONCLUSIVE && set_has_null;
   for (int64_t w0 = warp0 * kHUnroll; w0 < n_words; w0 += warps * kHUnroll) {
+    if (!valid && ((w0 + kHUnroll) << 5) <= n) {
+      // interior, no input nulls: no range tests, no masks; word k of the step is stored by lane k
+      // (profile: the edge handling below was half of the 112 instructions per row of this kernel)
+      const V* __restrict__ p = vals + off + (w0 << 5) + lane;
+      V x[kHUnroll];
+#pragma unroll
+      for (int k = 0; k < kHUnroll; ++k) x[k] = __ldcs(p + 32 * k);
+      uint32_t mine = 0;
+#pragma unroll
+      for (int k = 0; k < kHUnroll; ++k) {
+        const uint32_t dbits = __ballot_sync(0xffffffffu, member((unsigned long long)x[k]));
+        if (lane == k) mine = dbits;
+      }
+      if (lane < kHUnroll) {
+        out_data[w0 + lane] = mine;
+        if (out_valid) out_valid[w0 + lane] = miss_is_null ? mine : 0xffffffffu;
+        if (miss_is_null) nulls += __popc(~mine);
+      }
+      continue;
+    }
     V x[kHUnroll];
     bool have[kHUnroll], isnull[kHUnroll];
 #pragma unroll
@@ -255,7 +294,7 @@ is_in_kernel(const V* __restrict__ vals, const uint8_t* __restrict__ valid, int6
       }
     }
   }
-  if (lane == 0 && nulls && null_count) atomicAdd(null_count, nulls);
+  if (lane < kHUnroll && nulls && null_count) atomicAdd(null_count, nulls);
 }
 
 // unique: row i is kept iff it is the first row of its key (or the first null row).  `big` is the full-size table of an
@@ -283,11 +322,17 @@ unique_mark_kernel(const V* __restrict__ vals, const uint8_t* __restrict__ valid
   for (int64_t w0 = warp0 * kHUnroll; w0 < n_words; w0 += warps * kHUnroll) {
     V x[kHUnroll];
     int kind[kHUnroll];
+    if (!valid && ((w0 + kHUnroll) << 5) <= n) {         // interior, no nulls: unconditional loads
+      const V* __restrict__ p = vals + off + (w0 << 5) + lane;
 #pragma unroll
-    for (int k = 0; k < kHUnroll; ++k) {
-      const int64_t i = ((w0 + k) << 5) + lane;
-      kind[k] = i < n ? ((valid && !bit_is_set(valid, off + i)) ? 2 : 1) : 0;
-      x[k] = kind[k] == 1 ? __ldcs(vals + off + i) : V(0);
+      for (int k = 0; k < kHUnroll; ++k) { x[k] = __ldcs(p + 32 * k); kind[k] = 1; }
+    } else {
+#pragma unroll
+      for (int k = 0; k < kHUnroll; ++k) {
+        const int64_t i = ((w0 + k) << 5) + lane;
+        kind[k] = i < n ? ((valid && !bit_is_set(valid, off + i)) ? 2 : 1) : 0;
+        x[k] = kind[k] == 1 ? __ldcs(vals + off + i) : V(0);
+      }
     }
 #pragma unroll
     for (int k = 0; k < kHUnroll; ++k) {
@@ -296,10 +341,11 @@ unique_mark_kernel(const V* __restrict__ vals, const uint8_t* __restrict__ valid
       const unsigned row = (unsigned)((w << 5) + lane);
       const unsigned long long key = (unsigned long long)x[k];
       const int cs = warp_cache_slot(key);
+      const bool ones = sizeof(V) == 8 && key == kEmptyKey;
       bool kp = false;
       if (kind[k] == 2) kp = first_null == row;
-      else if (kind[k] == 1 && key == kEmptyKey) kp = first_ones == row;
-      const bool go = kind[k] == 1 && key != kEmptyKey && cache[cs] != key;   // a cached key sits at a lower row: not first
+      else if (kind[k] == 1 && ones) kp = first_ones == row;
+      const bool go = kind[k] == 1 && !ones && cache[cs] != key;   // a cached key sits at a lower row: not first
       __syncwarp();
       if (go) { kp = table_first_row(t, key) == row; cache[cs] = key; }
       __syncwarp();
@@ -343,9 +389,10 @@ static ag_status is_in_t(const void* vals, const uint8_t* valid, int64_t off, in
   constexpr bool kSmall = sizeof(V) <= 2;
   TableMem tm;
   // 1-/2-byte values: a 1024-slot block whose first 8 KB hold the membership bitmap (zeroed), `special` behind it as usual
-  // others: load factor <= 1/8 while the table still fits the shared-memory copy, <= 1/2 beyond
+  // others: load factor <= 1/4 while the table still fits the shared-memory copy (a 1000-value set: 4096 slots = 32 KB,
+  // six blocks per SM), <= 1/2 beyond
   unsigned long long min_slots = 1024;
-  if (!kSmall) { while (min_slots < (unsigned long long)set_n * 8 && min_slots < (unsigned long long)kIsInSmemSlots) min_slots <<= 1; }
+  if (!kSmall) { while (min_slots < (unsigned long long)set_n * 4 && min_slots < (unsigned long long)kIsInSmemSlots) min_slots <<= 1; }
   AG_TRY(tm.alloc(kSmall ? 0 : set_n, min_slots, kNoCap, st));
   ag_status rc = tm.clear(st);
   unsigned* bits = reinterpret_cast<unsigned*>(tm.block);

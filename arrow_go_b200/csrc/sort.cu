@@ -95,14 +95,26 @@ sort_prep_kernel(const SortSource src, unsigned long long* __restrict__ stats) {
   const K ref = sort_key<T, K>(vals[0], src.descending, &c0);
   K mn = (K)~(K)0, mx = 0, vr = 0;
   unsigned n_nan = 0, n_null = 0;
-#pragma unroll 4
-  for (int64_t i = (int64_t)blockIdx.x * kSoThreads + threadIdx.x; i < src.n; i += (int64_t)gridDim.x * kSoThreads) {
-    int cls;
-    const K k = sort_key<T, K>(__ldcs(vals + i), src.descending, &cls);
-    if (src.valid && !bit_is_set(src.valid, src.voff + i)) cls = 2;
-    if (cls == 0) { mn = k < mn ? k : mn; mx = k > mx ? k : mx; vr |= k ^ ref; }
-    n_nan += cls == 1;
-    n_null += cls == 2;
+  const int64_t ntiles = (src.n + kSoTile - 1) / kSoTile;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    T v[kSoPerThread];
+#pragma unroll
+    for (int e = 0; e < kSoPerThread; ++e) {      // 8 loads in flight per thread
+      const int64_t i = tile * kSoTile + e * kSoThreads + threadIdx.x;
+      v[e] = i < src.n ? __ldcs(vals + i) : T(0);
+    }
+#pragma unroll
+    for (int e = 0; e < kSoPerThread; ++e) {
+      const int64_t i = tile * kSoTile + e * kSoThreads + threadIdx.x;
+      if (i < src.n) {
+        int cls;
+        const K k = sort_key<T, K>(v[e], src.descending, &cls);
+        if (src.valid && !bit_is_set(src.valid, src.voff + i)) cls = 2;
+        if (cls == 0) { mn = k < mn ? k : mn; mx = k > mx ? k : mx; vr |= k ^ ref; }
+        n_nan += cls == 1;
+        n_null += cls == 2;
+      }
+    }
   }
 #pragma unroll
   for (int m = 16; m >= 1; m >>= 1) {
@@ -167,14 +179,18 @@ sort_scan_bins_kernel(unsigned* __restrict__ tile_hist, int64_t ntiles, const un
   }
 }
 
-// Stable rank of every element of a tile inside its digit: warp w owns rows [512w, 512w+512) of the tile and walks them
-// 32 at a time; lanes with equal digits form a group (__match_any_sync), the group's lowest lane advances the warp's
-// counter of that digit, and a lane's rank is the counter before the step plus its position inside the group.  After
-// the walk the 8 warp counters of a digit are turned into exclusive offsets (thread b handles digit b).
-// digits[e] for e = 0..15 are the digits of rows 512w + 32e + lane; rank[e] receives the rank inside (warp, digit).
+// Stable rank of every element of a tile inside its digit: warp w owns rows [256w, 256w+256) of the tile and walks them
+// 32 at a time; lanes with equal digits form a group, the group's lowest lane advances the warp's counter of that digit,
+// and a lane's rank is the counter before the step plus its position inside the group.  The groups come from one ballot
+// per digit bit (peers = lanes that agree with me on every bit): `match.any` does the same in one instruction but kept the
+// ADU pipe 71 % busy at ~65 cycles per warp instruction and bounded the whole scatter (profiles/r2/ncu_sort_kernels.csv).
+// After the walk the warp counters of a digit are turned into exclusive offsets (thread b handles digit b).
+// digits[e] for e = 0..7 are the digits of rows 256w + 32e + lane; rank[e] receives the rank inside (warp, digit).
 // s_cnt: [kSoWarps][256] counters; on return s_cnt[w][b] = rows of digit b in warps < w, tile_count[b] in s_tot.
+template <int kBits>
 __device__ __forceinline__ void tile_rank(const int (&digits)[kSoPerThread], const bool (&live)[kSoPerThread], unsigned (&rank)[kSoPerThread],
-                                          unsigned* s_cnt, unsigned* s_tot, int nbins) {
+                                          unsigned* s_cnt, unsigned* s_tot) {
+  constexpr int nbins = 1 << kBits;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < kSoWarps * 256; i += kSoThreads) s_cnt[i] = 0;
   __syncthreads();
@@ -182,12 +198,18 @@ __device__ __forceinline__ void tile_rank(const int (&digits)[kSoPerThread], con
   const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
   for (int e = 0; e < kSoPerThread; ++e) {
-    const int d = live[e] ? digits[e] : 256 + lane;          // dead rows match nobody
-    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const int d = digits[e];
+    unsigned peers = __ballot_sync(0xffffffffu, live[e]);      // rows past the end (only the highest lanes of the last step) join no group
+#pragma unroll
+    for (int b = 0; b < kBits; ++b) {
+      const bool bit = (d >> b) & 1;
+      const unsigned m = __ballot_sync(0xffffffffu, bit);
+      peers &= bit ? m : ~m;
+    }
     unsigned old = 0;
     const int leader = __ffs(peers) - 1;
     if (live[e] && lane == leader) { old = mine[d]; mine[d] = old + __popc(peers); }
-    old = __shfl_sync(0xffffffffu, old, leader);
+    old = __shfl_sync(0xffffffffu, old, leader & 31);
     rank[e] = old + __popc(peers & lt);
     __syncwarp();
   }
@@ -267,7 +289,7 @@ sort_class_scatter_kernel(const SortSource src, const SortXform xf, const unsign
       }
     }
     if (threadIdx.x < 3) s_base[threadIdx.x] = tile_off[(int64_t)threadIdx.x * ntiles + tile];
-    tile_rank(digits, live, rank, s_cnt, s_tot, 3);
+    tile_rank<2>(digits, live, rank, s_cnt, s_tot);
 #pragma unroll
     for (int e = 0; e < kSoPerThread; ++e) {
       if (live[e]) {
@@ -304,10 +326,16 @@ sort_digit_hist_kernel(const SortSource src, const SortXform xf, const K* __rest
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     if (threadIdx.x < kSoBins) s_h[threadIdx.x] = 0;
     __syncthreads();
-#pragma unroll 4
+    K kk[kSoPerThread];
+#pragma unroll
+    for (int e = 0; e < kSoPerThread; ++e) {      // every load of the tile in flight before the first atomic
+      const int64_t i = tile * kSoTile + e * kSoThreads + threadIdx.x;
+      kk[e] = i < n ? pass_key<T, K, kFromSource>(src, xf, keys, lo, i) : (K)0;
+    }
+#pragma unroll
     for (int e = 0; e < kSoPerThread; ++e) {
       const int64_t i = tile * kSoTile + e * kSoThreads + threadIdx.x;
-      if (i < n) atomicAdd(&s_h[(int)((pass_key<T, K, kFromSource>(src, xf, keys, lo, i) >> shift) & 0xff)], 1u);
+      if (i < n) atomicAdd(&s_h[(int)((kk[e] >> shift) & 0xff)], 1u);
     }
     __syncthreads();
     if (threadIdx.x < kSoBins) {
@@ -326,7 +354,7 @@ sort_digit_hist_kernel(const SortSource src, const SortXform xf, const K* __rest
 // neighbouring lanes instead of 16 isolated 8-byte stores per bin.
 // kLast: the final pass writes the uint64 row indices into `out64` (positions are absolute) and drops the keys.
 template <typename T, typename K, bool kFromSource, bool kLast>
-__global__ void __launch_bounds__(kSoThreads)
+__global__ void __launch_bounds__(kSoThreads, 2)     // 64 registers: two 512-thread blocks per SM (71 in one variant left one)
 sort_digit_scatter_kernel(const SortSource src, const SortXform xf, const K* __restrict__ keys_in, const unsigned* __restrict__ idx_in, int64_t lo,
                           int64_t n, int shift, const unsigned* __restrict__ tile_off, int64_t ntiles, K* __restrict__ keys_out,
                           unsigned* __restrict__ idx_out, unsigned long long* __restrict__ out64) {
@@ -359,7 +387,7 @@ sort_digit_scatter_kernel(const SortSource src, const SortXform xf, const K* __r
       }
     }
     if (threadIdx.x < kSoBins) s_base[threadIdx.x] = tile_off[(int64_t)threadIdx.x * ntiles + tile];
-    tile_rank(digits, live, rank, s_cnt, s_tot, kSoBins);
+    tile_rank<8>(digits, live, rank, s_cnt, s_tot);
     // exclusive scan of the 256 digit totals of the tile (one digit per thread of the first 8 warps)
     {
       const unsigned c = threadIdx.x < kSoBins ? s_tot[threadIdx.x] : 0u;

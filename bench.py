@@ -632,7 +632,7 @@ def main():
         nn, na = C.c_int64(), C.c_int64()
         ms = timed(lambda: N.call("ag_sort_indices_dev", N.INT64, vi.ptr, None, 0, rows, 0, 0, dout.ptr, C.byref(nn), C.byref(na), None), 1, 3)
         others["sort_indices_i64"] = {"rows_per_s": world * rows / ms * 1e3, "ms": ms, "gbs_per_gpu": 16.0 * rows / ms / 1e6, "frac": 16.0 * rows / ms / 1e6 / peak,
-                                      "note": "keys uniform in [-2^31, 2^31): 4 of 8 radix digits vary -> class pass + 4 digit passes; algorithmic 8 B key in + 8 B index out per row; one host sync inside (2 KB histogram)"}
+                                      "note": "keys uniform in [-2^31, 2^31): sorted as (key - min), 32 significant bits -> 4 digit passes, the first straight from the column (no NaN/null rows: no class pass), the last writing the uint64 indices; algorithmic 8 B key in + 8 B index out per row; one host sync inside (40 B of statistics)"}
         N.call("ag_generate_dev", 1, 0x15 + rank * rows, 0, 99_999, vi.ptr, rows, None)
         sset = DeviceBuffer(8000)
         hs = np.arange(0, 100_000, 100, dtype=np.int64)
@@ -640,11 +640,12 @@ def main():
         bm1, bm2 = DeviceBuffer(rows // 8 + 64), DeviceBuffer(rows // 8 + 64)
         ms = timed(lambda: N.call("ag_is_in_dev", 64, vi.ptr, None, 0, rows, sset.ptr, None, 0, 1000, 0, bm1.ptr, bm2.ptr, scal.ptr, None), W, K)
         others["is_in_i64_1000_values"] = {"rows_per_s": world * rows / ms * 1e3, "ms": ms, "gbs_per_gpu": 8.25 * rows / ms / 1e6, "frac": 8.25 * rows / ms / 1e6 / peak,
-                                           "note": "8 B value in + 2 bitmap bits out per row; the 1000-entry hash table stays in L1/L2"}
+                                           "note": "8 B value in + 2 bitmap bits out per row; the 1000-value set is probed in shared memory (4096 key slots, load factor 1/4, two slots per 128-bit read)"}
         N.call("ag_generate_dev", 1, 0x16 + rank * rows, 0, 99, vi.ptr, rows, None)
         ms = timed(lambda: N.call("ag_unique_dev", 64, vi.ptr, None, 0, rows, dout.ptr, None, rows, scal.ptr, None), 1, 3)
         others["unique_i64_100_distinct"] = {"rows_per_s": world * rows / ms * 1e3, "ms": ms,
-                                             "note": "insert (atomicCAS / atomicMin first row) + mark + compaction; table sized for n distinct rows (3.2 GB memset included)"}
+                                             "gbs_per_gpu": 8.0 * rows / ms / 1e6, "frac": 8.0 * rows / ms / 1e6 / peak,
+                                             "note": "insert (atomicCAS / atomicMin first row) + mark + compaction, 8 B/row algorithmic; L2-resident 4M-slot table first (the full-size one only after an on-device overflow), per-warp seen-key cache"}
         sset.free(); bm1.free(); bm2.free()
         N.call("ag_generate_dev", 1, 0x0FF1CE + rank * rows, 0, 99, vi.ptr, rows, None)
         cstate.free(); idx.free(); bad.free(); scal.free()
