@@ -9,8 +9,8 @@
 // vector_sort_support.go:100-170).  Output: uint64 row indices, like the reference.
 //
 // Algorithm: least-significant-digit radix sort over (key, row) pairs, 8-bit digits.
-//   key' is an order-preserving unsigned image of the value (sign bias for signed ints; floats: flip all bits of
-//   negatives, set the sign bit of the rest, -0.0 folded onto +0.0), complemented for Descending so that an ascending
+//   key' is an order-preserving unsigned image of the value (sign bias for signed ints; floats: 2^(w-1) +- magnitude,
+//   which folds -0.0 onto +0.0 and keeps trailing zero bits on both sides of zero), complemented for Descending so that an ascending
 //   stable sort of key' gives the descending order with ties still in row order.  The sorted key is
 //       key = (key' - min key') >> tz,   tz = trailing bits on which every finite key' agrees,
 //   still order preserving, and only ceil(bits(max - min) - tz) / 8) digits can differ: a column of small integers
@@ -55,15 +55,17 @@ __device__ __forceinline__ K sort_key(T v, int descending, int* cls) {
   K k;
   *cls = 0;
   if constexpr (std::is_same<T, float>::value) {
-    uint32_t b = __float_as_uint(v);
-    if ((b & 0x7fffffffu) > 0x7f800000u) *cls = 1;
-    if (b == 0x80000000u) b = 0;                        // -0.0 == +0.0 (compareOrdered)
-    k = (K)((b & 0x80000000u) ? ~b : (b | 0x80000000u));
+    // sign-magnitude -> offset binary: 2^31 +- magnitude.  Unlike the usual "flip all bits of the negatives" image this
+    // keeps the trailing zero bits of the magnitude on both sides of zero (a float column holding small integers then
+    // loses its constant low digits to the `tz` shift whatever the signs), and -0.0 lands on +0.0 by itself
+    // (compareOrdered: -0.0 == +0.0).
+    const uint32_t b = __float_as_uint(v), mag = b & 0x7fffffffu;
+    if (mag > 0x7f800000u) *cls = 1;
+    k = (K)((b & 0x80000000u) ? (0x80000000u - mag) : (0x80000000u | mag));
   } else if constexpr (std::is_same<T, double>::value) {
-    unsigned long long b = (unsigned long long)__double_as_longlong(v);
-    if ((b & 0x7fffffffffffffffull) > 0x7ff0000000000000ull) *cls = 1;
-    if (b == 0x8000000000000000ull) b = 0;
-    k = (K)((b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull));
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v), mag = b & 0x7fffffffffffffffull;
+    if (mag > 0x7ff0000000000000ull) *cls = 1;
+    k = (K)((b >> 63) ? (0x8000000000000000ull - mag) : (0x8000000000000000ull | mag));
   } else if constexpr (std::is_signed<T>::value) {
     using U = typename std::make_unsigned<T>::type;
     k = (K)(U)((U)v ^ (U)((U)1 << (sizeof(T) * 8 - 1)));
@@ -364,7 +366,7 @@ sort_digit_scatter_kernel(const SortSource src, const SortXform xf, const K* __r
   unsigned* s_cnt = s_idx + kSoTile;                                        // [kSoWarps][256]
   __shared__ unsigned s_tot[kSoBins];
   __shared__ unsigned s_excl[kSoBins];     // exclusive offset of a digit inside the staged tile
-  __shared__ unsigned s_base[kSoBins];     // global position of the tile's first row of a digit
+  __shared__ unsigned s_base[kSoBins];     // global position of the tile's first row of a digit, minus its staged offset
   __shared__ unsigned s_w[kSoBins / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -403,6 +405,7 @@ sort_digit_scatter_kernel(const SortSource src, const SortXform xf, const K* __r
         unsigned wb = 0;
         for (int w = 0; w < warp; ++w) wb += s_w[w];
         s_excl[threadIdx.x] = wb + inc - c;
+        s_base[threadIdx.x] -= wb + inc - c;      // destination of staged element j of this digit = s_base[d] + j (mod 2^32)
       }
     }
     __syncthreads();
@@ -418,7 +421,7 @@ sort_digit_scatter_kernel(const SortSource src, const SortXform xf, const K* __r
     for (int j = threadIdx.x; j < len; j += kSoThreads) {
       const K k = s_key[j];
       const int d = (int)((k >> shift) & 0xff);
-      const int64_t pos = lo + s_base[d] + (unsigned)(j - (int)s_excl[d]);
+      const int64_t pos = lo + (unsigned)(s_base[d] + (unsigned)j);
       if constexpr (kLast) {
         __stcs(out64 + pos, (unsigned long long)s_idx[j]);
       } else {
