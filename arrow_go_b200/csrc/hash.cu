@@ -154,7 +154,7 @@ hash_insert_kernel(const V* __restrict__ vals, const uint8_t* __restrict__ valid
       const bool go = kind[k] == 1 && !ones && cache[cs] != key;
       __syncwarp();
       bool made = false;
-      if (go) { made = table_insert(t, key, row); cache[cs] = key; }
+      if (go) { made = table_insert(t, key, row); atomicExch(&cache[cs], key); }   // several lanes may share a slot: one whole key wins
       __syncwarp();
       if (t.cap != kNoCap) {
         // distinct keys so far, one atomic per warp step (a column of all-distinct values would otherwise put 2M
@@ -347,7 +347,7 @@ unique_mark_kernel(const V* __restrict__ vals, const uint8_t* __restrict__ valid
       else if (kind[k] == 1 && ones) kp = first_ones == row;
       const bool go = kind[k] == 1 && !ones && cache[cs] != key;   // a cached key sits at a lower row: not first
       __syncwarp();
-      if (go) { kp = table_first_row(t, key) == row; cache[cs] = key; }
+      if (go) { kp = table_first_row(t, key) == row; atomicExch(&cache[cs], key); }
       __syncwarp();
       const uint32_t bits = __ballot_sync(0xffffffffu, kp);
       if (lane == 0) keep[w] = bits;
