@@ -64,3 +64,48 @@ func TestSumSiblings(t *testing.T) { // arrow/math/float64_test.go:30-48
 		t.Fatalf("reference-order sum = %v", got)
 	}
 }
+
+func TestIsInUniqueSortIndices(t *testing.T) { // scalar_set_lookup_test.go:104-167, vector_hash_test.go:236-255, vector_sort_test.go:40-110
+	mem := memory.NewCheckedAllocator(arrowgpu.PinnedAllocator{})
+	defer mem.AssertSize(t, 0)
+	ctx := gpuCtx()
+	vals, _, _ := array.FromJSON(mem, arrow.PrimitiveTypes.Int32, strings.NewReader(`[2, 1, 2, 1, 2, 3, null]`))
+	set, _, _ := array.FromJSON(mem, arrow.PrimitiveTypes.Int32, strings.NewReader(`[2, 3, null]`))
+	defer vals.Release()
+	defer set.Release()
+
+	in, err := compute.IsIn(ctx, compute.SetOptions{ValueSet: compute.NewDatum(set)}, compute.NewDatum(vals))
+	if err != nil {
+		t.Fatal(err)
+	}
+	defer in.Release()
+	wantIn, _, _ := array.FromJSON(mem, arrow.FixedWidthTypes.Boolean, strings.NewReader(`[true, false, true, false, true, true, true]`))
+	defer wantIn.Release()
+	if got := in.(*compute.ArrayDatum).MakeArray(); !array.Equal(got, wantIn) {
+		t.Fatalf("is_in: got %v want %v", got, wantIn)
+	}
+
+	uq, err := compute.Unique(ctx, compute.NewDatum(vals))
+	if err != nil {
+		t.Fatal(err)
+	}
+	defer uq.Release()
+	wantUq, _, _ := array.FromJSON(mem, arrow.PrimitiveTypes.Int32, strings.NewReader(`[2, 1, 3, null]`))
+	defer wantUq.Release()
+	if got := uq.(*compute.ArrayDatum).MakeArray(); !array.Equal(got, wantUq) {
+		t.Fatalf("unique: got %v want %v", got, wantUq)
+	}
+
+	key := compute.DefaultSortKey()
+	key.Order = compute.SortOrderDescending
+	si, err := compute.CallFunction(ctx, "sort_indices", compute.SortOptions{key}, compute.NewDatum(vals))
+	if err != nil {
+		t.Fatal(err)
+	}
+	defer si.Release()
+	wantSi, _, _ := array.FromJSON(mem, arrow.PrimitiveTypes.Uint64, strings.NewReader(`[5, 0, 2, 4, 1, 3, 6]`)) // stable, nulls at end
+	defer wantSi.Release()
+	if got := si.(*compute.ArrayDatum).MakeArray(); !array.Equal(got, wantSi) {
+		t.Fatalf("sort_indices: got %v want %v", got, wantSi)
+	}
+}

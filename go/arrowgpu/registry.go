@@ -213,6 +213,7 @@ func NewRegistry() compute.FunctionRegistry {
 	}
 	addVector(reg, parent, filterFn)
 	addVector(reg, parent, takeFn)
+	registerLookupSort(reg, parent) // is_in, unique, sort_indices (lookup_sort.go)
 	return reg
 }
 
