@@ -25,6 +25,47 @@ def test_binding_table_matches_header():
     assert declared == bound, (declared - bound, bound - declared)
 
 
+def test_go_package_calls_only_declared_entry_points():
+    """go/arrowgpu cannot be compiled here (no Go toolchain): at least every C.ag_* function and C.AG_* constant the cgo files
+    use must exist in include/arrowgpu.h with the number of arguments the call passes."""
+    import glob
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = re.sub(r"/\*.*?\*/", "", open(N.HEADER_PATH).read(), flags=re.S)
+    declared = set(N.declared_symbols())
+    arity = {}
+    for m in re.finditer(r"ag_status\s+(ag_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+        args = m.group(2).strip()
+        arity[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    consts = set(re.findall(r"#define\s+(AG_\w+)", text)) | set(re.findall(r"\b(AG_\w+)\s*=", text))
+    files = sorted(glob.glob(os.path.join(root, "go", "arrowgpu", "*.go")))
+    assert len(files) >= 7
+    calls = 0
+    for f in files:
+        src = re.sub(r"//[^\n]*", "", open(f).read())
+        for m in re.finditer(r"\bC\.(ag_\w+)\(", src):
+            name = m.group(1)
+            assert name in declared, (os.path.basename(f), name)
+            # count the arguments of the call (top-level commas up to the matching parenthesis)
+            depth, i, commas, seen = 1, m.end(), 0, False
+            while depth:
+                ch = src[i]
+                if ch in "([{":
+                    depth += 1
+                elif ch in ")]}":
+                    depth -= 1
+                elif ch == "," and depth == 1:
+                    commas += 1
+                if depth and not ch.isspace():
+                    seen = True
+                i += 1
+            if name in arity:
+                assert (commas + 1 if seen else 0) == arity[name], (os.path.basename(f), name, commas + 1, arity[name])
+            calls += 1
+        for name in re.findall(r"\bC\.(AG_\w+)", src):
+            assert name in consts, (os.path.basename(f), name)
+    assert calls >= 30
+
+
 def test_header_cites_reference_for_every_block():
     text = open(N.HEADER_PATH).read()
     for needle in ("arrow/math/_lib/float64.c:20-26", "_lib/base_arithmetic.cc:465-483", "_lib/scalar_comparison.cc:210-256",
