@@ -19,7 +19,7 @@
 //       -> read back (40 bytes) so the host can lay out the three regions and pick the digits;
 //   K1  class pass, only when the column has NaNs or nulls: stable 3-way partition of the rows into the region order
 //       above, materialising the pairs (a column without them feeds the first digit pass straight from the source);
-//   K2+ one pass per digit on the finite region: tile histogram (shared-memory atomics) -> per-bin scan over the tiles
+//   K2+ one pass per digit on the finite region: tile histogram (shared-memory atomics) -> scan over the tiles (segment sums, then each segment rescans itself)
 //       -> scatter with a stable in-tile rank (warp __match_any_sync groups + per-warp digit counters); the last
 //       pass writes the uint64 row indices straight into `out`.
 // Roofline: HBM; per digit pass 8 (histogram read) + 12 + 12 bytes/row for 64-bit keys (first pass from the source:
@@ -138,7 +138,7 @@ sort_prep_kernel(const SortSource src, unsigned long long* __restrict__ stats) {
 }
 
 // ---------------------------------------------------------------- shared pieces of a pass
-// tile_hist layout: [bin][tile] (one contiguous row per bin, scanned by one block per bin)
+// class pass: tile_hist layout [bin][tile] (one contiguous row per bin, scanned by one block per bin; three bins)
 __global__ void __launch_bounds__(kSoThreads)
 sort_scan_bins_kernel(unsigned* __restrict__ tile_hist, int64_t ntiles, const unsigned* __restrict__ tot) {
   __shared__ unsigned long long s_w[kSoWarps];
@@ -178,6 +178,48 @@ sort_scan_bins_kernel(unsigned* __restrict__ tile_hist, int64_t ntiles, const un
     const unsigned c = row[i];
     row[i] = (unsigned)run;     // positions fit 32 bits (n < 2^32)
     run += c;
+  }
+}
+
+// Digit passes keep their tile histograms as [tile][256] (one coalesced 1 KB row per tile for the histogram kernel's
+// write and the scatter's read) and scan them over the tiles in two steps: per-segment column sums, then every segment
+// rescans its own tiles from (rows of lower bins) + (rows of this bin in lower segments).
+constexpr int kSoSegThreads = 256;   // one thread per bin
+__global__ void __launch_bounds__(kSoSegThreads)
+sort_digit_segsum_kernel(const unsigned* __restrict__ th, int64_t ntiles, int64_t tiles_per_seg, unsigned* __restrict__ seg_sums) {
+  const int64_t lo = (int64_t)blockIdx.x * tiles_per_seg, hi = lo + tiles_per_seg < ntiles ? lo + tiles_per_seg : ntiles;
+  unsigned sum = 0;
+#pragma unroll 8
+  for (int64_t t = lo; t < hi; ++t) sum += th[t * 256 + threadIdx.x];
+  seg_sums[(int64_t)blockIdx.x * 256 + threadIdx.x] = sum;
+}
+
+__global__ void __launch_bounds__(kSoSegThreads)
+sort_digit_apply_kernel(unsigned* __restrict__ th, int64_t ntiles, int64_t tiles_per_seg, const unsigned* __restrict__ seg_sums,
+                        const unsigned* __restrict__ tot) {
+  __shared__ unsigned s_w[kSoSegThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // exclusive scan of the 256 bin totals: first position of this thread's bin
+  const unsigned c = tot[threadIdx.x];
+  unsigned inc = c;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) s_w[warp] = inc;
+  __syncthreads();
+  unsigned run = inc - c;
+  for (int w = 0; w < warp; ++w) run += s_w[w];
+  // rows of this bin in the segments below
+#pragma unroll 8
+  for (int64_t sgm = 0; sgm < (int64_t)blockIdx.x; ++sgm) run += seg_sums[sgm * 256 + threadIdx.x];
+  const int64_t lo = (int64_t)blockIdx.x * tiles_per_seg, hi = lo + tiles_per_seg < ntiles ? lo + tiles_per_seg : ntiles;
+#pragma unroll 8
+  for (int64_t t = lo; t < hi; ++t) {
+    const unsigned k = th[t * 256 + threadIdx.x];
+    th[t * 256 + threadIdx.x] = run;     // positions fit 32 bits (n < 2^32)
+    run += k;
   }
 }
 
@@ -352,7 +394,7 @@ sort_digit_hist_kernel(const SortSource src, const SortXform xf, const K* __rest
     __syncthreads();
     if (threadIdx.x < kSoBins) {
       const unsigned c = s_h[threadIdx.x];
-      tile_hist[(int64_t)threadIdx.x * ntiles + tile] = c;
+      tile_hist[tile * kSoBins + threadIdx.x] = c;      // [tile][bin]
       acc += c;
     }
     __syncthreads();
@@ -400,7 +442,7 @@ sort_digit_scatter_kernel(const SortSource src, const SortXform xf, const K* __r
         digits[e] = (int)((key[e] >> shift) & 0xff);
       }
     }
-    if (threadIdx.x < kSoBins) s_base[threadIdx.x] = tile_off[(int64_t)threadIdx.x * ntiles + tile];
+    if (threadIdx.x < kSoBins) s_base[threadIdx.x] = tile_off[tile * kSoBins + threadIdx.x];     // [tile][bin]
     tile_rank<8, kFull>(digits, live, rank, s_cnt, s_tot);
     // exclusive scan of the 256 digit totals of the tile (one digit per thread of the first 8 warps)
     {
@@ -460,8 +502,8 @@ sort_iota_kernel(int64_t n, unsigned long long* __restrict__ out) {
 
 template <typename T, typename K, bool kFromSource>
 static ag_status launch_digit_pass(const SortSource& src, const SortXform& xf, const K* keys_in, const unsigned* idx_in, int64_t lo, int64_t fn, int shift,
-                                   unsigned* tile_hist, unsigned* tot, K* keys_out, unsigned* idx_out, unsigned long long* out64, bool last,
-                                   cudaStream_t st) {
+                                   unsigned* tile_hist, unsigned* seg_sums, unsigned* tot, K* keys_out, unsigned* idx_out, unsigned long long* out64,
+                                   bool last, cudaStream_t st) {
   constexpr size_t kScatterSmem = (sizeof(K) + 4) * (size_t)kSoTile + (size_t)kSoWarps * 256 * 4;
   static std::atomic<unsigned> attr_a{0u}, attr_b{0u};   // per instantiation, one bit per device
   AG_TRY(ensure_dynamic_smem((const void*)sort_digit_scatter_kernel<T, K, kFromSource, false>, (int)kScatterSmem, &attr_a));
@@ -470,8 +512,14 @@ static ag_status launch_digit_pass(const SortSource& src, const SortXform& xf, c
   const int fgrid = grid_for(fn, kSoTile, 8);
   sort_digit_hist_kernel<T, K, kFromSource><<<fgrid, kSoThreads, 0, st>>>(src, xf, keys_in, lo, fn, shift, tile_hist, ftiles, tot);
   AG_TRY(check_launch("sort_digit_hist_kernel"));
-  sort_scan_bins_kernel<<<256, kSoThreads, 0, st>>>(tile_hist, ftiles, tot);
-  AG_TRY(check_launch("sort_scan_bins_kernel"));
+  int64_t nseg = 2 * (int64_t)sm_count();
+  if (nseg > ftiles) nseg = ftiles;
+  const int64_t tps = (ftiles + nseg - 1) / nseg;
+  nseg = (ftiles + tps - 1) / tps;
+  sort_digit_segsum_kernel<<<(int)nseg, kSoSegThreads, 0, st>>>(tile_hist, ftiles, tps, seg_sums);
+  AG_TRY(check_launch("sort_digit_segsum_kernel"));
+  sort_digit_apply_kernel<<<(int)nseg, kSoSegThreads, 0, st>>>(tile_hist, ftiles, tps, seg_sums, tot);
+  AG_TRY(check_launch("sort_digit_apply_kernel"));
   if (last)
     sort_digit_scatter_kernel<T, K, kFromSource, true><<<fgrid, kSoThreads, kScatterSmem, st>>>(src, xf, keys_in, idx_in, lo, fn, shift, tile_hist, ftiles, keys_out, idx_out, out64);
   else
@@ -487,19 +535,23 @@ static ag_status sort_indices_t(const SortSource& src, unsigned long long* d_out
   const size_t key_bytes = ((size_t)n * sizeof(K) + 255) & ~(size_t)255;
   const size_t idx_bytes = ((size_t)n * 4 + 255) & ~(size_t)255;
   const size_t th_bytes = ((size_t)256 * ntiles * 4 + 255) & ~(size_t)255;
-  const size_t head = (8 * 8 + (size_t)(ND + 1) * 256 * 4 + 255) & ~(size_t)255;   // statistics, then one row of bin totals per pass (+ the class pass)
+  const size_t seg_bytes = (size_t)2 * sm_count() * 256 * 4;
+  // statistics, then one row of bin totals per pass (+ the class pass), then the per-segment column sums of a pass
+  const size_t head0 = (8 * 8 + (size_t)(ND + 1) * 256 * 4 + 255) & ~(size_t)255;
+  const size_t head = head0 + ((seg_bytes + 255) & ~(size_t)255);
   void* scratch = nullptr;
   AG_TRY(dev_alloc_async(&scratch, head + 2 * key_bytes + 2 * idx_bytes + th_bytes, st));
   char* base = reinterpret_cast<char*>(scratch);
   unsigned long long* d_stats = reinterpret_cast<unsigned long long*>(base);
   unsigned* d_tot = reinterpret_cast<unsigned*>(base + 64);
+  unsigned* d_seg = reinterpret_cast<unsigned*>(base + head0);
   K* keys[2] = {reinterpret_cast<K*>(base + head), reinterpret_cast<K*>(base + head + key_bytes)};
   unsigned* idx[2] = {reinterpret_cast<unsigned*>(base + head + 2 * key_bytes), reinterpret_cast<unsigned*>(base + head + 2 * key_bytes + idx_bytes)};
   unsigned* tile_hist = reinterpret_cast<unsigned*>(base + head + 2 * key_bytes + 2 * idx_bytes);
   ag_status rc = AG_OK;
   do {
     unsigned long long h[8] = {~0ull, 0, 0, 0, 0, 0, 0, 0};
-    if (cudaMemsetAsync(base, 0, head, st) != cudaSuccess ||
+    if (cudaMemsetAsync(base, 0, head0, st) != cudaSuccess ||
         cudaMemcpyAsync(d_stats, h, 8, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "statistics init", __FILE__, __LINE__); break; }
     const int grid = grid_for(n, kSoTile, 8);
     sort_prep_kernel<T, K><<<grid, kSoThreads, 0, st>>>(src, d_stats);
@@ -541,9 +593,9 @@ static ag_status sort_indices_t(const SortSource& src, unsigned long long* d_out
     for (int d = 0; d < nd; ++d) {
       const bool last = d == nd - 1;
       if (d == 0 && !classes)
-        rc = launch_digit_pass<T, K, true>(src, xf, nullptr, nullptr, 0, fn, 0, tile_hist, d_tot, keys[0], idx[0], d_out, last, st);
+        rc = launch_digit_pass<T, K, true>(src, xf, nullptr, nullptr, 0, fn, 0, tile_hist, d_seg, d_tot, keys[0], idx[0], d_out, last, st);
       else
-        rc = launch_digit_pass<K, K, false>(src, xf, keys[cur], idx[cur], fin_lo, fn, 8 * d, tile_hist, d_tot + (size_t)d * 256, keys[cur ^ 1], idx[cur ^ 1], d_out, last, st);
+        rc = launch_digit_pass<K, K, false>(src, xf, keys[cur], idx[cur], fin_lo, fn, 8 * d, tile_hist, d_seg, d_tot + (size_t)d * 256, keys[cur ^ 1], idx[cur ^ 1], d_out, last, st);
       if (rc != AG_OK) break;
       if (!(d == 0 && !classes)) cur ^= 1;     // a source pass writes buffer 0
     }
