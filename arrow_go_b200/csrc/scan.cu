@@ -759,6 +759,12 @@ cumsum_stream_kernel(const CumsumParams p) {
   const int64_t mine = ((int64_t)blockIdx.x < p.n_tiles) ? (p.n_tiles - blockIdx.x + G - 1) / G : 0;  // tiles of this block
   if (!looker) { if (mine > 0) prefetch(blockIdx.x, 0); cp_async_commit(); }
   A lane_excl_cur = P::zero(), warp_excl_cur = P::zero();
+  // validity words of the rows this lane owns: fetched once per tile, in its reduction, and carried to its finalization
+  // one iteration later; `dense` is made warp-uniform so a warp runs ONE of the two loops, not both under divergence
+  unsigned vb_cur[VW], vb_prev[VW];
+  bool dense_cur = true, dense_prev = true;
+#pragma unroll
+  for (int w = 0; w < VW; ++w) { vb_cur[w] = 0u; vb_prev[w] = 0u; }
   int st_r = 0, st_f = kScStreamStages - 1;   // stage of the tile being reduced (j % 3) / finalized ((j-1) % 3)
   // iteration j: reduce tile j (j < mine), look-back + finalize tile j-1 (j >= 1)
   for (int64_t j = 0; j <= mine; ++j) {
@@ -778,13 +784,13 @@ cumsum_stream_kernel(const CumsumParams p) {
         for (int c = 0; c < kScRows; ++c) raw[c] = *reinterpret_cast<const uint4*>(seg + blk_row + (((uint32_t)c << 4) ^ blk_x));
         const T* o = reinterpret_cast<const T*>(raw);
         A tot = P::zero();
-        unsigned vbits[VW];
-        if (lane_validity(tile_r, vbits)) {
+        dense_cur = __all_sync(0xffffffffu, lane_validity(tile_r, vb_cur));
+        if (dense_cur) {
 #pragma unroll
           for (int i = 0; i < E; ++i) tot = P::add_elem(tot, o[i]);
         } else {
 #pragma unroll
-          for (int i = 0; i < E; ++i) if ((vbits[i >> 5] >> (i & 31)) & 1u) tot = P::add_elem(tot, o[i]);
+          for (int i = 0; i < E; ++i) if ((vb_cur[i >> 5] >> (i & 31)) & 1u) tot = P::add_elem(tot, o[i]);
         }
         A incl = tot;
 #pragma unroll
@@ -846,14 +852,13 @@ cumsum_stream_kernel(const CumsumParams p) {
         T* o = reinterpret_cast<T*>(raw);
         A run = P::add(warp_excl_cur, lane_excl_cur);
         const T off = P::value(s_excl[bf]);
-        unsigned vbits[VW];
-        if (lane_validity(tile_f, vbits)) {
+        if (dense_prev) {
 #pragma unroll
           for (int i = 0; i < E; ++i) { run = P::add_elem(run, o[i]); o[i] = P::offset_add(off, P::value(run)); }
         } else {
 #pragma unroll
           for (int i = 0; i < E; ++i) {
-            if ((vbits[i >> 5] >> (i & 31)) & 1u) { run = P::add_elem(run, o[i]); o[i] = P::offset_add(off, P::value(run)); }
+            if ((vb_prev[i >> 5] >> (i & 31)) & 1u) { run = P::add_elem(run, o[i]); o[i] = P::offset_add(off, P::value(run)); }
             else o[i] = T(0);
           }
         }
@@ -881,6 +886,9 @@ cumsum_stream_kernel(const CumsumParams p) {
       }
       lane_excl_cur = lane_excl_next;
       warp_excl_cur = warp_excl_next;
+      dense_prev = dense_cur;
+#pragma unroll
+      for (int w = 0; w < VW; ++w) vb_prev[w] = vb_cur[w];
     }
     st_f = st_r;
     st_r = st_r + 1 == kScStreamStages ? 0 : st_r + 1;
