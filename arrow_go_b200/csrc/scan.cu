@@ -559,6 +559,11 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, int bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
 }
+// 4- / 8-byte pieces for an input that is only element-aligned (an Arrow slice): same destination layout, more copies
+template <int kB>
+__device__ __forceinline__ void cp_async_small_zfill(uint32_t dst, const void* src, int bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(dst), "l"(src), "n"(kB), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int kPending> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
 
@@ -738,10 +743,33 @@ cumsum_stream_kernel(const CumsumParams p) {
   const uint32_t blk_row = (uint32_t)lane * 128u;
   const uint32_t blk_x = (uint32_t)(lane & 7) << 4;
 
+  const int in_mis = (int)(reinterpret_cast<uintptr_t>(in) & 15);   // 0, or a multiple of sizeof(T) >= 4 (block-uniform)
   auto prefetch = [&](int64_t tile, int stage) {
     const uint32_t dst0 = ring + (uint32_t)stage * kScTileBytes + seg_off;
     const int64_t g0 = tile * kScTileBytes + seg_off + (int64_t)lane * 16;
-    if (g0 - (int64_t)lane * 16 + 4096 <= n_bytes) {
+    if (in_mis) {
+      // element-aligned input: the 16-byte slots of the ring are filled by two 8-byte or four 4-byte copies
+#pragma unroll
+      for (int k = 0; k < kScRows; ++k) {
+        const uint32_t d = dst0 + (str_even ^ ((k & 1) << 6)) + k * 512;
+        const int64_t g = g0 + k * 512;
+        if ((in_mis & 7) == 0) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int64_t room = n_bytes - (g + q * 8);
+            const int bytes = room >= 8 ? 8 : (room > 0 ? (int)room : 0);
+            cp_async_small_zfill<8>(d + q * 8, bytes > 0 ? in + g + q * 8 : in, bytes);
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int64_t room = n_bytes - (g + q * 4);
+            const int bytes = room >= 4 ? 4 : (room > 0 ? (int)room : 0);
+            cp_async_small_zfill<4>(d + q * 4, bytes > 0 ? in + g + q * 4 : in, bytes);
+          }
+        }
+      }
+    } else if (g0 - (int64_t)lane * 16 + 4096 <= n_bytes) {
 #pragma unroll
       for (int k = 0; k < kScRows; ++k) cp_async16(dst0 + (str_even ^ ((k & 1) << 6)) + k * 512, in + g0 + k * 512);
     } else {  // the segment crosses the end of the input: zero-fill what is not there
@@ -984,7 +1012,9 @@ ag_status launch_cumsum(CumsumParams& p, cudaStream_t st) {
     cumsum_validity_kernel<<<grid_for(n_words, 256, 8), 256, 0, st>>>(p.valid, p.voff, p.n, p.skip_nulls, p.first_null, p.state, words, shift, n_words);
     AG_TRY(check_launch("cumsum_validity_kernel"));
   }
-  const bool vec = (reinterpret_cast<uintptr_t>(p.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
+  // the streaming kernel wants a 16-byte aligned OUTPUT; an input that is only element-aligned (a slice) is fetched in
+  // 4- / 8-byte pieces, which needs elements of at least 4 bytes
+  const bool vec = ((reinterpret_cast<uintptr_t>(p.in) & 15) == 0 || sizeof(T) >= 4) && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
   void* args[] = {(void*)&p};
   const void* fn;
   const bool chk = p.checked && !IsFp<T>::v;  // floats: the checked adder is the plain one
