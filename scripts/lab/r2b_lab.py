@@ -63,8 +63,8 @@ def cumsum(t, src, v):
 timed("cumsum_i64 (stream kernel)", lambda: cumsum(N.INT64, a.ptr, None), rows * 16)
 timed("cumsum_f64 (stream kernel)", lambda: cumsum(N.FLOAT64, b.ptr, None), rows * 16)
 timed("cumsum_i32 (stream kernel)", lambda: cumsum(N.INT32, idx.ptr, None), rows * 8)
-timed("cumsum_i64_nulls_skip (general kernel)", lambda: cumsum(N.INT64, a.ptr, valid.ptr), rows * 16)
-timed("cumsum_i64 misaligned (general kernel)", lambda: (N.call("ag_cumulative_sum_state_init_dev", state.ptr, N.INT64, None, None),
+timed("cumsum_i64_nulls_skip (stream kernel + validity)", lambda: cumsum(N.INT64, a.ptr, valid.ptr), rows * 16)
+timed("cumsum_i64 input 8 B off 16 (stream kernel)", lambda: (N.call("ag_cumulative_sum_state_init_dev", state.ptr, N.INT64, None, None),
       N.call("ag_cumulative_sum_dev", N.INT64, a.ptr + 8, None, 0, rows - 1, 1, 0, o.ptr, None, 0, state.ptr, bad.ptr, None)), rows * 16)
 fb = rows * 8 + rows // 8 + cnt * 8
 timed("filter_i64 (2-level look-back)", lambda: N.call("ag_filter_primitive_dev", 64, b.ptr, None, 0, mask.ptr, None, 0, rows, 0, o.ptr, None, cnt, scal.ptr + 8, None), fb)
