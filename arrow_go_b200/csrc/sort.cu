@@ -10,8 +10,8 @@
 //
 // Algorithm: least-significant-digit radix sort over (key, row) pairs, 8-bit digits.
 //   key' is an order-preserving unsigned image of the value (sign bias for signed ints; floats: 2^(w-1) +- magnitude,
-//   which folds -0.0 onto +0.0 and keeps trailing zero bits on both sides of zero), complemented for Descending so that an ascending
-//   stable sort of key' gives the descending order with ties still in row order.  The sorted key is
+//   which folds -0.0 onto +0.0 and keeps trailing zero bits on both sides of zero), complemented for Descending so that
+//   an ascending stable sort of key' gives the descending order with ties still in row order.  The sorted key is
 //       key = (key' - min key') >> tz,   tz = trailing bits on which every finite key' agrees,
 //   still order preserving, and only ceil(bits(max - min) - tz) / 8) digits can differ: a column of small integers
 //   (whatever their sign), or of doubles holding integers, needs one to four passes instead of eight.
@@ -19,9 +19,10 @@
 //       -> read back (40 bytes) so the host can lay out the three regions and pick the digits;
 //   K1  class pass, only when the column has NaNs or nulls: stable 3-way partition of the rows into the region order
 //       above, materialising the pairs (a column without them feeds the first digit pass straight from the source);
-//   K2+ one pass per digit on the finite region: tile histogram (shared-memory atomics) -> scan over the tiles (segment sums, then each segment rescans itself)
-//       -> scatter with a stable in-tile rank (warp __match_any_sync groups + per-warp digit counters); the last
-//       pass writes the uint64 row indices straight into `out`.
+//   K2+ one pass per digit on the finite region: tile histogram (shared-memory atomics, [tile][bin]) -> scan over the
+//       tiles (segment sums, then each segment rescans itself) -> scatter with a stable in-tile rank (digit groups from
+//       one ballot per bit + per-warp digit counters, tile staged in shared memory); the last pass writes the uint64
+//       row indices straight into `out`.
 // Roofline: HBM; per digit pass 8 (histogram read) + 12 + 12 bytes/row for 64-bit keys (first pass from the source:
 // 8 + 8 + 12; last pass: 8 + 12 + 8); the gathers are never random (pairs move with their rows).  The API is synchronous
 // in one spot: the 40-byte read-back after K0.
