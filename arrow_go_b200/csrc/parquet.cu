@@ -66,6 +66,52 @@ bytes_to_bools_kernel(const uint8_t* __restrict__ bytes, int64_t len, uint8_t* _
   }
 }
 
+// bytes_to_bools, bulk part: a thread expands 4 input bytes (one 32-bit load) into 32 output bytes (two 128-bit stores)
+__global__ void __launch_bounds__(kPqThreads)
+bytes_to_bools4_kernel(const uint32_t* __restrict__ in, int64_t n4, uint4* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * kPqThreads + threadIdx.x; i < n4; i += (int64_t)gridDim.x * kPqThreads) {
+    const uint32_t w = __ldcs(in + i);
+    uint32_t o[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {           // output word q holds bits 4q .. 4q+3 as bytes
+      const uint32_t nib = (w >> (4 * q)) & 0xfu;
+      o[q] = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+    }
+    __stcs(out + 2 * i, make_uint4(o[0], o[1], o[2], o[3]));
+    __stcs(out + 2 * i + 1, make_uint4(o[4], o[5], o[6], o[7]));
+  }
+}
+
+// flat definition levels, bulk part: bit i = level[i] > rhs for whole 256-row warp loads.  A lane reads 8 levels with one
+// 128-bit load (the generic compare kernel reads 2 bytes per lane per load), four loads in flight; the 8-bit masks of four
+// neighbouring lanes are merged by two shuffles into one aligned output word.
+__global__ void __launch_bounds__(kPqThreads)
+levels_gt_kernel(const uint4* __restrict__ lv, int64_t nvec, int rhs, uint32_t* __restrict__ out_words) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * kPqThreads + threadIdx.x) >> 5;
+  const int64_t warps = ((int64_t)gridDim.x * kPqThreads) >> 5;
+  for (int64_t v0 = warp0 * 128; v0 < nvec; v0 += warps * 128) {     // nvec is a multiple of 32
+    uint4 x[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) x[k] = (v0 + k * 32 < nvec) ? __ldcs(lv + v0 + k * 32 + lane) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (v0 + k * 32 >= nvec) break;     // warp-uniform
+      const uint32_t wv[4] = {x[k].x, x[k].y, x[k].z, x[k].w};
+      uint32_t m = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        m |= ((int)(short)(wv[j] & 0xffffu) > rhs ? 1u : 0u) << (2 * j);
+        m |= ((int)(short)(wv[j] >> 16) > rhs ? 1u : 0u) << (2 * j + 1);
+      }
+      uint32_t v = m << (8 * (lane & 3));
+      v |= __shfl_xor_sync(0xffffffffu, v, 1);
+      v |= __shfl_xor_sync(0xffffffffu, v, 2);
+      if ((lane & 3) == 0) out_words[((v0 + k * 32) >> 2) + (lane >> 2)] = v;
+    }
+  }
+}
+
 ag_status parquet_unpack32_dev(const uint32_t* in, uint32_t* out, int64_t batch_size, int num_bits, int64_t* unpacked, cudaStream_t st) {
   if (unpacked) *unpacked = 0;
   if (batch_size < 0) AG_FAIL(AG_ERR_INVALID, "unpack32: negative batch size");
@@ -84,8 +130,22 @@ ag_status parquet_bytes_to_bools_dev(const uint8_t* bytes, int64_t len, uint8_t*
   if (len < 0 || outlen < 0) AG_FAIL(AG_ERR_INVALID, "bytes_to_bools: negative length");
   if (len == 0 || outlen == 0) return AG_OK;
   if (!bytes || !out) AG_FAIL(AG_ERR_INVALID, "bytes_to_bools: NULL buffer");
-  bytes_to_bools_kernel<<<grid_for(len, kPqThreads * 4, 8), kPqThreads, 0, st>>>(bytes, len, out, outlen);
-  return check_launch("bytes_to_bools_kernel");
+  // bulk: whole 4-byte groups whose 32 output bytes all exist, when the pointers allow 32- / 128-bit accesses
+  int64_t n4 = 0;
+  if ((reinterpret_cast<uintptr_t>(bytes) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    n4 = len / 4;
+    if (n4 * 32 > outlen) n4 = outlen / 32;
+  }
+  if (n4 > 0) {
+    bytes_to_bools4_kernel<<<grid_for(n4, kPqThreads * 4, 8), kPqThreads, 0, st>>>(reinterpret_cast<const uint32_t*>(bytes), n4, reinterpret_cast<uint4*>(out));
+    AG_TRY(check_launch("bytes_to_bools4_kernel"));
+  }
+  const int64_t rest = len - 4 * n4, rest_out = outlen - 32 * n4;
+  if (rest > 0 && rest_out > 0) {
+    bytes_to_bools_kernel<<<grid_for(rest, kPqThreads * 4, 8), kPqThreads, 0, st>>>(bytes + 4 * n4, rest, out + 32 * n4, rest_out);
+    return check_launch("bytes_to_bools_kernel");
+  }
+  return AG_OK;
 }
 
 // d_counts: [0] values read (bits appended), [1] set bits (non-null values)
@@ -99,7 +159,16 @@ ag_status parquet_def_levels_to_bitmap_dev(const int16_t* levels, int64_t n, int
   const int16_t rhs = (int16_t)(def_level - 1);
   if (repeated_ancestor_def_level < 0) {
     if (n > read_upper_bound) AG_FAIL(AG_ERR_INVALID, "values read exceed upper bound");   // level_conversion.go:138-140
-    AG_TRY(compare_dev(AG_TYPE_INT16, AG_CMP_GT, AG_SHAPE_AS, levels, &rhs, valid_bits + (valid_bits_offset >> 3), n, (int)(valid_bits_offset & 7), st));
+    // bulk: whole 256-level groups when the output starts on a 32-bit word and the levels on a 16-byte boundary
+    int64_t nm = 0;
+    uint8_t* first = valid_bits + (valid_bits_offset >> 3);
+    if ((valid_bits_offset & 7) == 0 && (reinterpret_cast<uintptr_t>(first) & 3) == 0 && (reinterpret_cast<uintptr_t>(levels) & 15) == 0) nm = n / 256 * 256;
+    if (nm > 0) {
+      levels_gt_kernel<<<grid_for(nm / 8, kPqThreads * 4, 8), kPqThreads, 0, st>>>(reinterpret_cast<const uint4*>(levels), nm / 8, (int)rhs, reinterpret_cast<uint32_t*>(first));
+      AG_TRY(check_launch("levels_gt_kernel"));
+    }
+    if (n > nm)
+      AG_TRY(compare_dev(AG_TYPE_INT16, AG_CMP_GT, AG_SHAPE_AS, levels + nm, &rhs, valid_bits + ((valid_bits_offset + nm) >> 3), n - nm, (int)((valid_bits_offset + nm) & 7), st));
     const long long nn = n;
     AG_CUDA_TRY(cudaMemcpyAsync(d_counts, &nn, 8, cudaMemcpyHostToDevice, st));
     return bitmap_popcount_dev(valid_bits, valid_bits_offset, n, d_counts + 1, st);
