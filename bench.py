@@ -624,7 +624,7 @@ def main():
         counts = DeviceBuffer(64)
         ms = timed(lambda: N.call("ag_parquet_def_levels_to_bitmap_dev", dr.ptr, rows, 1, -1, ovalid.ptr, 0, rows, counts.ptr, None), W, K)
         others["parquet_def_levels_to_bitmap"] = {"values_per_s": world * rows / ms * 1e3, "gbs_per_gpu": 2.125 * rows / ms / 1e6, "frac": 2.125 * rows / ms / 1e6 / peak, "ms": ms,
-                                                  "note": "flat column: 2 B level in + 1 bit out per value (compare_kernel int16 >= scalar)"}
+                                                  "note": "flat column: 2 B level in + 1 bit out per value (levels_gt_kernel: 8 levels per 128-bit load, + popcount)"}
         counts.free(); vmask.free(); ovalid.free()
         N.call("ag_generate_dev", 3, 0x94378166 + rank * rows, -(1 << 20), 1 << 20, dr.ptr, rows, None)
         # SURVEY 8f rank 3, same columns: sort_indices (stable radix sort), is_in (1000-value set), unique (100 distinct values)
